@@ -1,0 +1,180 @@
+"""Radiance-field model containers with the reference's parameter names.
+
+The render path is model-agnostic in the reference: ``run_network`` just calls
+``network(inputs)`` (nerf/render.py:73).  The B200 path instead reads the weights of a known
+architecture and evaluates the whole MLP inside one fused CUDA kernel, so it has to recognise
+the model.  Recognition is structural (state-dict keys), which means the *reference's own*
+``NeRF`` (nerf/nerf.py:52-94) and ``FilmSirenNeRF`` (pi_GAN/modules.py:70-118) instances and
+checkpoints work unchanged, and so do the stand-alone classes below (same keys, same
+initialisation order, so ``torch.manual_seed(s); NeRF()`` gives bit-identical weights to the
+reference class -- pinned by tests/golden/weights_sha.json).
+
+Nothing here computes an MLP in PyTorch: ``forward`` goes to the CUDA extension.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+# ---- canonical flat fp32 parameter layout (must match csrc/layout.h) -------------------------
+NERF_KEYS = (
+    [(f"layers_pos.{i}", s) for i, s in enumerate(
+        [(256, 60), (256, 256), (256, 256), (256, 256), (256, 256), (256, 316), (256, 256), (256, 256)])]
+    + [("layers_dir.0", (256, 256)), ("layers_dir.1", (128, 280)),
+       ("output_layer_sigma", (1, 256)), ("output_layer_rgb", (3, 128))]
+)
+FILM_KEYS_DIR = (
+    [("input_layer", (256, 3))]
+    + [(f"hidden_layers.{i}", (256, 256)) for i in range(7)]
+    + [("output_layer_sigma.0", (1, 256)), ("hidden_layer_rgb", (256, 259)), ("output_layer_rgb.0", (3, 256))]
+)
+FILM_KEYS_NODIR = FILM_KEYS_DIR[:9] + [("hidden_layer_rgb", (256, 256)), ("output_layer_rgb.0", (3, 256))]
+
+
+def _numel(keys):
+    return sum(o * i + o for _, (o, i) in keys)
+
+
+NERF_NUMEL = _numel(NERF_KEYS)          # 593,924  
+FILM_NUMEL = _numel(FILM_KEYS_DIR)      # 529,156  
+
+KIND_NERF = 0
+KIND_FILM = 1
+
+
+def model_kind(model) -> int:
+    """Structural dispatch; anything else is a TypeError (no fallback by design)."""
+    if hasattr(model, "module") and isinstance(model, torch.nn.DataParallel):
+        model = model.module
+    if all(hasattr(model, a) for a in ("layers_pos", "layers_dir", "output_layer_sigma", "output_layer_rgb")):
+        w0 = model.layers_pos[0].weight
+        if tuple(w0.shape) == (256, 60):
+            return KIND_NERF
+        raise TypeError("SirenNeRF-shaped model (layers_pos.0 is %s): not supported by this build" % (tuple(w0.shape),))
+    if all(hasattr(model, a) for a in ("input_layer", "hidden_layers", "hidden_layer_rgb", "output_layer_rgb")):
+        return KIND_FILM
+    raise TypeError(
+        f"{type(model).__name__} is not a NeRF / FilmSirenNeRF radiance field; the B200 render path "
+        "evaluates known architectures in a fused kernel and has no generic-callable fallback")
+
+
+def param_list(model, kind: int | None = None):
+    """Parameters in canonical flat order (weight, bias per layer)."""
+    kind = model_kind(model) if kind is None else kind
+    sd = dict(model.named_parameters())
+    if kind == KIND_NERF:
+        keys = NERF_KEYS
+    else:
+        keys = FILM_KEYS_DIR if getattr(model, "use_dir", True) else FILM_KEYS_NODIR
+    out = []
+    for name, (o, i) in keys:
+        w, b = sd[name + ".weight"], sd[name + ".bias"]
+        if tuple(w.shape) != (o, i) or tuple(b.shape) != (o,):
+            raise TypeError(f"{name}: expected weight {(o, i)}, got {tuple(w.shape)}")
+        out += [w, b]
+    return out
+
+
+def flat_params(model, kind: int | None = None) -> torch.Tensor:
+    """One flat fp32 tensor of all parameters (differentiable: grads flow back to each
+    nn.Parameter through torch.cat's backward; the flat layout is also the all-reduce bucket)."""
+    ps = param_list(model, kind)
+    return torch.cat([p.reshape(-1) for p in ps]).float()
+
+
+def film_tensor(model) -> torch.Tensor:
+    """[9,512] gamma||beta tensor from the ``film_params`` list set by set_film_params
+    (pi_GAN/modules.py:96-99).  Raises ValueError when unset, like the reference (:107)."""
+    fp = getattr(model, "film_params", None)
+    if fp is None:
+        raise ValueError("film_params not set")
+    if isinstance(fp, torch.Tensor):
+        return fp
+    return torch.stack([torch.cat([g, b]) for (g, b) in fp])
+
+
+# ---- stand-alone model classes (same keys / init order as the reference) ---------------------
+class _Dense(torch.nn.Linear):
+    """Linear + named activation, Xavier-uniform with the activation's gain, zero bias
+    (nerf/nerf.py:5-28)."""
+
+    def __init__(self, i, o, activation="linear"):
+        self.activation_name = activation
+        super().__init__(i, o)
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.weight, gain=torch.nn.init.calculate_gain(self.activation_name))
+        torch.nn.init.zeros_(self.bias)
+
+
+class NeRF(torch.nn.Module):
+    """8x256 ReLU trunk with posenc(L=10/4); parameter names as nerf/nerf.py:52-73."""
+
+    def __init__(self):
+        super().__init__()
+        dims = [(60, 256)] + [(256, 256)] * 4 + [(316, 256)] + [(256, 256)] * 2
+        self.layers_pos = torch.nn.ModuleList([_Dense(i, o, "relu") for i, o in dims])
+        self.layers_dir = torch.nn.ModuleList([_Dense(256, 256, "linear"), _Dense(280, 128, "relu")])
+        self.output_layer_sigma = _Dense(256, 1, "relu")
+        self.output_layer_rgb = _Dense(128, 3, "sigmoid")
+
+    def forward(self, x):
+        from . import ops
+        return ops.mlp_points(self, x)
+
+
+class _FilmSiren(torch.nn.Module):
+    """Parameter holder for one FiLM-SIREN layer (pi_GAN/modules.py:8-31 init)."""
+
+    def __init__(self, i, o, c=6, w_0=30, is_first_layer=False):
+        super().__init__()
+        self.weight = torch.nn.Parameter(torch.zeros(o, i))
+        self.bias = torch.nn.Parameter(torch.zeros(o))
+        wr = 1 / i if is_first_layer else np.sqrt(c / i) / w_0
+        br = np.sqrt(1 / i)
+        torch.nn.init.uniform_(self.weight, -wr, wr)
+        torch.nn.init.uniform_(self.bias, -br, br)
+
+
+class FilmSirenNeRF(torch.nn.Module):
+    """FiLM-conditioned SIREN field; names as pi_GAN/modules.py:70-94."""
+
+    def __init__(self, hidden_dim=256, hidden_layers=8, c=6, w_0=30, use_dir=True):
+        super().__init__()
+        assert hidden_dim == 256 and hidden_layers == 8 and w_0 == 30, "fused kernel is specialised to 8x256, w0=30"
+        self.use_dir = use_dir
+        self.film_params = None
+        self.input_layer = _FilmSiren(3, 256, c, w_0, True)
+        self.hidden_layers = torch.nn.ModuleList([_FilmSiren(256, 256, c, w_0) for _ in range(7)])
+        self.output_layer_sigma = torch.nn.Sequential(torch.nn.Linear(256, 1), torch.nn.ReLU())
+        self.hidden_layer_rgb = _FilmSiren(259 if use_dir else 256, 256, c, w_0)
+        self.output_layer_rgb = torch.nn.Sequential(torch.nn.Linear(256, 3), torch.nn.Sigmoid())
+        self.n_layers = 7
+
+    def set_film_params(self, mapping_tensor):
+        self.film_params = [torch.chunk(mapping_tensor[i], 2) for i in range(mapping_tensor.shape[0])]
+
+    def forward(self, x, film_params=None):
+        if film_params is not None:
+            self.film_params = film_params
+        elif self.film_params is None:
+            raise ValueError
+        from . import ops
+        return ops.mlp_points(self, x)
+
+
+def damp_nerf_(model: NeRF) -> NeRF:
+    """'Trained-like' 1/f synthetic field used for end-to-end parity: scale the
+    posenc band i columns by 2^-i, sigma head x8, sigma bias -1."""
+    with torch.no_grad():
+        for i in range(10):
+            s = 2.0 ** (-i)
+            model.layers_pos[0].weight[:, 6 * i:6 * i + 6] *= s
+            model.layers_pos[5].weight[:, 6 * i:6 * i + 6] *= s
+        for i in range(4):
+            model.layers_dir[1].weight[:, 256 + 6 * i:256 + 6 * i + 6] *= 2.0 ** (-i)
+        model.output_layer_sigma.weight *= 8.0
+        model.output_layer_sigma.bias.fill_(-1.0)
+    return model
