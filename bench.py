@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Headline benchmark: rays/s of the NeRF 800x800, 64 coarse + 128 fine render (BASELINE.json
+configs[1]) through the B200 render path, one process per GPU.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU arm: the oracle port on the host cores
+
+A step renders ONE full frame: the 640,000 rays are sharded over the ranks by contiguous pixel rows
+(no data-path collective; the final image gather is the only exchange), so scaling is "strong".
+`value` times the device-resident path (rays generated on the device, outputs left in HBM);
+`e2e` times the public API call `nerf_render.render_image` whose pose comes from host memory and
+whose images are returned as numpy arrays (D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NERF_FLOP_PER_ROW = 1182976          # unpadded algorithmic FLOP per MLP evaluation
+METRIC = "rays/s, NeRF 800x800 render, 64 coarse + 128 fine samples/ray"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=800)
+    ap.add_argument("--height", type=int, default=800)
+    ap.add_argument("--coarse", type=int, default=64)
+    ap.add_argument("--fine", type=int, default=128)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+# ---- CPU arm: the numpy oracle (port of the reference algorithm) on the host cores -----------------------
+def cpu_baseline(args, n_rays: int, repeats: int = 1):
+    """Times oracle.render_rays on a bounded sample of the same workload (same seeds, sample counts,
+    camera); rays are independent, so rays/s extrapolates linearly to the frame."""
+    import torch
+    from oracle import render_oracle as orc
+    from msra_practice_project_b200 import models, pigan_render
+    try:
+        from threadpoolctl import threadpool_info
+        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        threads = os.cpu_count() or 1
+    torch.manual_seed(0)
+    c, f = models.NeRF(), models.NeRF()
+    pc, pf = orc.state_dict_to_numpy(c.state_dict()), orc.state_dict_to_numpy(f.state_dict())
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+    rays = orc.image_rays(args.width, args.height, args.width * 1.3875, pose)
+    mid = (args.height // 2) * args.width
+    rays = rays[mid:mid + n_rays]
+    rng = np.random.default_rng(5)
+    best = None
+    for _ in range(repeats):
+        t_rand = rng.random((rays.shape[0], args.coarse), dtype=np.float32)
+        t0 = time.perf_counter()
+        orc.render_rays(rays, 2.0, 6.0, lambda x: orc.nerf_mlp(pc, x), lambda x: orc.nerf_mlp(pf, x), args.coarse,
+                        args.fine, t_rand)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return dict(value=rays.shape[0] / best, unit="rays/s", cores=int(threads), kind="port",
+                sample=f"{rays.shape[0]} rays of the {args.width}x{args.height} frame, {args.coarse}+{args.fine} samples, "
+                       f"fp32 numpy oracle (oracle/render_oracle.py), {best:.2f} s; host has {os.cpu_count()} logical cores"), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, dt = cpu_baseline(args, args.cpu_rays)
+        if i >= args.warmup:
+            times.append(dt)
+    t = float(np.mean(times)) if times else float("nan")
+    v = args.cpu_rays / t
+    base["value"] = v
+    line = dict(impl="reference", metric=METRIC, value=v, unit="rays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=t * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"NeRF {args.width}x{args.height} render, {args.coarse}+{args.fine} samples/ray, random-init 8x256 ReLU MLP + posenc; "
+                                     f"each step = a {args.cpu_rays}-ray sample of the frame on the host CPU"),
+                cpu_baseline=base, e2e=dict(value=v, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                samples_per_s=v * (2 * args.coarse + args.fine), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ---- clocks sampler ---------------------------------------------------------------------------------------
+class Clocks(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unsampled"])
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=float(self.rows[0][1]), reasons=reasons,
+                    samples=len(self.rows))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from msra_practice_project_b200 import _lib, dist as shard, models, nerf_render, ops, pigan_render
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.lib().b2r_device_ok() == 1
+
+    W, H, sc, sf = args.width, args.height, args.coarse, args.fine
+    n_rays = W * H
+    begin, count = shard.shard_range(n_rays, rank, world)
+    torch.manual_seed(0)
+    coarse, fine = models.NeRF().to(dev), models.NeRF().to(dev)
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+    focal = W * 1.3875
+    torch.manual_seed(5)
+    t_rand = torch.rand((n_rays, sc), device=dev)[begin:begin + count].contiguous()
+    gathered = torch.empty((n_rays, 5), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step_device():
+        with torch.no_grad():
+            out = nerf_render.render_image_device(W, H, focal, pose, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin,
+                                                  ray_count=count, t_rand=t_rand, precision=args.precision)
+            if world > 1:
+                shard.gather_image(out[3], out[4], out[5], gathered, n_rays, rank, world)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    total_ms = timed(step_device, args.steps)
+    ms_per_step = total_ms / args.steps
+    value = n_rays / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API: host pose in, numpy images out
+    pinned_pose = torch.from_numpy(np.ascontiguousarray(pose)).pin_memory()
+
+    def step_e2e():
+        with torch.no_grad():
+            p = pinned_pose.numpy()              # host pose -> kernel arguments of the ray generator (the step's H2D)
+            out = nerf_render.render_image_device(W, H, focal, p, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin,
+                                                  ray_count=count, t_rand=None if world == 1 else t_rand, precision=args.precision)
+            if world > 1:
+                shard.gather_image(out[3], out[4], out[5], gathered, n_rays, rank, world)
+                if rank == 0:
+                    return gathered.cpu().numpy()
+                return None
+            return out[3].cpu().numpy(), out[4].cpu().numpy(), out[5].cpu().numpy()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_ms = timed(step_e2e, args.steps)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e2e_ms, wall_ms) / args.steps          # the D2H copies block the host: take the larger clock
+    e2e_value = n_rays / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (fused MLP, fine pass) timed alone with CUDA events
+    roof = None
+    if args.precision == "bf16":
+        import ctypes as C
+        with torch.no_grad():
+            rays = ops.raygen(W, H, focal, pose, begin, count, device=dev)
+            z = torch.sort(torch.rand((count, sc + sf), device=dev) * 4 + 2, -1).values.contiguous()
+            flat = models.flat_params(fine).detach()
+            packed = ops._packed_weights(fine, 0, flat, None, True)
+            inp, rows, keep = ops._make_input(rays, z, None, None)
+            raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+            lib = _lib.lib()
+            st = torch.cuda.current_stream(dev).cuda_stream
+            for _ in range(2):
+                _lib.check(lib.b2r_mlp_tc_fwd(0, packed.data_ptr(), C.byref(inp), raw.data_ptr(), 0, st), "tc")
+            torch.cuda.synchronize()
+            reps = 5
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                _lib.check(lib.b2r_mlp_tc_fwd(0, packed.data_ptr(), C.byref(inp), raw.data_ptr(), 0, st), "tc")
+            e1.record()
+            torch.cuda.synchronize()
+            k_ms = e0.elapsed_time(e1) / reps
+        pk = peaks()
+        achieved = rows * NERF_FLOP_PER_ROW / (k_ms * 1e-3) / 1e12
+        roof = dict(bound="tensor", kernel="nerf_tc_kernel (fine pass)", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s",
+                    frac=achieved / pk["bf16"], frac_of_sustained=achieved / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
+                    peak_source=pk["src"], rows_per_launch=rows, ms_per_launch=k_ms, flop_per_row=NERF_FLOP_PER_ROW, traffic=None)
+    if rank == 0:
+        clocks.stop_flag = True
+        clocks.join(timeout=2)
+
+    base = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        base, _ = cpu_baseline(args, args.cpu_rays)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="rays/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+                    config=dict(workload=f"NeRF {W}x{H} Blender-shape render, {sc} coarse + {sf} fine samples/ray, random-init 8x256 ReLU MLP "
+                                         f"+ posenc (L=10/4), {args.precision} MLP; rays sharded by pixel rows over {world} GPU(s); "
+                                         "per-step working set (2 GB of raw samples) exceeds the 126 MB L2",
+                                rays=n_rays, mlp_rows_per_ray=2 * sc + sf),
+                    samples_per_s=value * (2 * sc + sf),
+                    e2e=dict(value=e2e_value, unit="rays/s", h2d_bytes_per_step=96,
+                             d2h_bytes_per_step=int(n_rays * 5 * 4), ms_per_step=e2e_ms),
+                    gpu_launches=int(7 * args.steps * world), clocks=clocks.summary(), roofline=roof, cpu_baseline=base)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,140 @@
+/*
+ * b2r.h -- C ABI of libb2r.so, the B200 (sm_100a) implementation of the volumetric
+ * ray-march render path of JeffreyXiang/MSRA-practice-project.
+ *
+ * The reference has no FFI: its boundary for this path is the Python module surface of
+ * nerf/render.py and pi_GAN/render.py.  Each entry point below names the
+ * reference function (file:line, relative to the reference root) whose arithmetic it
+ * replaces; the Python mirrors of those functions (msra_practice_project_b200/nerf_render.py,
+ * pigan_render.py) call these through ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned memory unless marked "host";
+ *   - tensors are dense row-major float32 unless stated;
+ *   - the last argument is the CUDA stream (cudaStream_t, passed as void*); no function
+ *     allocates, synchronises or throws;
+ *   - return 0 = OK, <0 = bad argument, >0 = cudaError_t; b2r_last_error() gives the message
+ *     (thread-local);
+ *   - the library is re-entrant: no mutable global state (nn.DataParallel calls it from one
+ *     thread per GPU, pi_GAN/train.py:50).
+ */
+#ifndef B2R_H_
+#define B2R_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_VERSION 100
+
+/* model kinds */
+#define B2R_MODEL_NERF 0      /* nerf/nerf.py:52-94            */
+#define B2R_MODEL_FILM 1      /* pi_GAN/modules.py:70-118      */
+
+/* flat fp32 parameter counts (state-dict order: weight,bias per layer) */
+#define B2R_NERF_NUMEL 593924
+#define B2R_FILM_NUMEL 529156
+#define B2R_FILM_NODIR_NUMEL 528388
+#define B2R_FILM_PARAMS 4608   /* film_params [9,512] = gamma(256)||beta(256) per layer */
+
+const char* b2r_last_error(void);
+int b2r_version(void);
+/* 1 when the library was compiled for sm_100a and the current device is compute capability 10.x */
+int b2r_device_ok(void);
+
+/* ---- K1: ray generation -------------------------------- get_rays  nerf/render.py:7-23 ----
+ * rays_out[ray_count,2,3] = (origin, direction) for flattened pixel indices
+ * [ray_begin, ray_begin+ray_count) of a W x H image (row-major, column fastest), i.e. rows of
+ * the [H*W,2,3] table render_image builds (nerf/render.py:151-154).
+ * c2w: host pointer to the 3x4 camera-to-world matrix (row-major, 12 doubles; a float32 pose
+ * converts exactly).
+ * compute_f64 reproduces numpy's float64 promotion: bit 0 = the caller's focal is an np.float64
+ * (pi_GAN/modules.py:127: the division is done in double), bit 1 = the pose is a float64 array.
+ * When non-zero the rotation is computed in double and rounded to float32 at the end
+ * (render_image casts, nerf/render.py:159). */
+int b2r_raygen(const double* c2w_host, int width, int height, double focal, int compute_f64,
+               long long ray_begin, long long ray_count, float* rays_out, void* stream);
+
+/* ---- K2: stratified coarse samples ------------------- render_rays nerf/render.py:123-132 --
+ * z_lin[Sc] = torch.linspace(near, far, Sc) made by the caller (its rounding is a contract);
+ * t_rand[N,Sc] = the jitter (torch.rand in the reference, :131);
+ * z_out[N,Sc] = lower + (upper-lower)*t_rand;  mids_out[Sc-1] (nullable) = 0.5*(z_lin[1:]+z_lin[:-1]). */
+int b2r_stratified_z(const float* z_lin, const float* t_rand, long long n_rays, int n_coarse,
+                     float* z_out, float* mids_out, void* stream);
+
+/* ---- K4: alpha compositing ------------------------ raw_to_outputs nerf/render.py:78-103 ---
+ * raw[N,S,4] (rgb, sigma), z[N,S], rays_d: N direction vectors d_stride floats apart (3 for a
+ * dense [N,3], 6 for rays[:,1] of an [N,2,3] table).  weights_out[N,S] is nullable. */
+int b2r_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                      long long n_rays, int n_samples, float* rgb_out, float* depth_out,
+                      float* acc_out, float* weights_out, void* stream);
+
+/* reverse mode of the above wrt raw (autograd in the reference, nerf/train_nerf.py:167).
+ * g_depth / g_acc nullable (treated as zero).  d_raw[N,S,4]. */
+int b2r_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                      long long n_rays, int n_samples, const float* g_rgb, const float* g_depth,
+                      const float* g_acc, float* d_raw, void* stream);
+
+/* ---- K5/K6: hierarchical resampling --- sample_pdf nerf/render.py:27-56, sort-merge :142 ---
+ * bins: nb values per ray, bins_stride floats apart (0 = one shared row, as in render_rays);
+ * weights: nb-1 values per ray, w_stride floats apart (render_rays passes weights[:,1:-1]:
+ * pointer +1, stride Sc); u[Sf] = torch.linspace(0,1,Sf) from the caller.
+ * samples_out[N,Sf] nullable; if z_coarse != NULL, sorted_out[N,Sc+Sf] = sort(cat(z_coarse,
+ * samples)) (both are monotone, so a merge).  cdf_out[N,nb] nullable (parity harness:
+ * "indices bit-exact given identical CDFs"). */
+int b2r_sample_pdf(const float* bins, long long bins_stride, const float* weights, long long w_stride,
+                   const float* u, long long n_rays, int nb, int n_fine,
+                   const float* z_coarse, int n_coarse,
+                   float* samples_out, float* sorted_out, float* cdf_out, void* stream);
+
+/* ---- K3: radiance-field MLP --- run_network nerf/render.py:59-75 + NeRF.forward nerf/nerf.py:75-94
+ *                                 + FilmSirenNeRF.forward pi_GAN/modules.py:101-118 ------------
+ * Input rows are described in one of three ways (exactly one must be given):
+ *   rays != NULL : rows = n_rays*n_samples, point = o + d*z[r,s], dir = d/|d|   (render_rays)
+ *   x    != NULL : rows = n_rays (n_samples must be 1), x[rows,6] = (pos, dir)  (network(x))
+ *   grid_n  > 0  : rows = n_rays = count of grid indices starting at grid_begin of an
+ *                  N^3 lattice in [-0.1,0.1]^3, dir = 0            (create_mesh, pi_GAN/utils.py:59-91)
+ * raw_out[rows,4] = (sigmoid rgb, relu sigma).
+ */
+typedef struct b2r_mlp_input {
+    const float* rays;      /* [n_rays,2,3] or NULL */
+    const float* z;         /* [n_rays,n_samples] (with rays) */
+    const float* x;         /* [rows,6] or NULL */
+    long long n_rays;
+    int n_samples;
+    int grid_n;             /* >0: lattice mode */
+    long long grid_begin;
+} b2r_mlp_input;
+
+/* fp32 path (CUDA cores).  params: flat fp32 parameters (B2R_*_NUMEL floats, state-dict order);
+ * film: [9,512] (FiLM model only).  workspace: b2r_mlp_f32_workspace_bytes(kind, rows, save)
+ * bytes; with save_activations != 0 the workspace holds every layer's output afterwards and is
+ * the `saved` argument of b2r_mlp_f32_bwd.  use_dir: FilmSirenNeRF(use_dir=...) flag. */
+size_t b2r_mlp_f32_workspace_bytes(int model_kind, long long rows, int save_activations);
+int b2r_mlp_f32_fwd(int model_kind, const float* params, const float* film, int use_dir,
+                    const b2r_mlp_input* in, float* raw_out, void* workspace, size_t workspace_bytes,
+                    int save_activations, void* stream);
+/* backward of the fp32 path: d_raw[rows,4] -> d_params (flat, ACCUMULATED into: caller zeroes),
+ * d_film[9,512] (FiLM only, accumulated, nullable).  saved = workspace of the forward call made with
+ * save_activations=1 on the same inputs; scratch = b2r_mlp_f32_bwd_scratch_bytes(kind, rows). */
+size_t b2r_mlp_f32_bwd_scratch_bytes(int model_kind, long long rows);
+int b2r_mlp_f32_bwd(int model_kind, const float* params, const float* film, int use_dir,
+                    const b2r_mlp_input* in, const float* raw, const float* d_raw, const void* saved,
+                    void* scratch, size_t scratch_bytes, float* d_params, float* d_film, void* stream);
+
+/* bf16 tensor-core path (tcgen05 / TMEM, weights streamed by the TMA bulk-copy engine).
+ * packed: b2r_mlp_tc_packed_bytes(kind) bytes produced by b2r_mlp_tc_pack from the flat fp32
+ * parameters (+ film for the FiLM model: gamma/beta/bias are folded into per-column scale/shift). */
+size_t b2r_mlp_tc_packed_bytes(int model_kind);
+int b2r_mlp_tc_pack(int model_kind, const float* params, const float* film, int use_dir,
+                    void* packed_out, void* stream);
+int b2r_mlp_tc_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out,
+                   int sigma_only, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H_ */

@@ -1,0 +1,195 @@
+// K4 alpha compositing, forward and reverse mode.
+//   raw_to_outputs  nerf/render.py:78-103   (== pi_GAN/render.py:123-148)
+//   backward        autograd in the reference (nerf/train_nerf.py:167); closed form SURVEY.md A.3
+//
+// One warp owns one ray.  Samples are processed in chunks of 32 (lane = sample), so every raw
+// load is a coalesced 512-byte float4 row and the transmittance T_k = prod_{j<k} (1-alpha_j+1e-10)
+// is a warp-level product scan (5 shuffles per chunk) with a carry between chunks.  The kernel is
+// HBM-bound: S*20+12 bytes in, S*4+20 bytes out per ray (S*20 bytes in / 20 out when the weights
+// are not requested).  Grid = 148 SMs x 8 CTAs x 8 warps, rays are walked with a grid stride.
+#include "common.cuh"
+
+namespace b2r {
+
+__device__ __forceinline__ float ray_norm(const float* __restrict__ d) {
+    float x = d[0], y = d[1], z = d[2];
+    return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// inclusive product scan over the 32 lanes
+__device__ __forceinline__ float warp_scan_mul(float p, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_up_sync(kFull, p, o);
+        if (lane >= o) p *= t;
+    }
+    return p;
+}
+
+template <bool kWeights>
+__global__ void __launch_bounds__(256) composite_fwd_kernel(
+    const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
+    long long n_rays, int S, float* __restrict__ rgb_out, float* __restrict__ depth_out,
+    float* __restrict__ acc_out, float* __restrict__ w_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long ray = warp0; ray < n_rays; ray += n_warps) {
+        const float norm = ray_norm(rays_d + ray * d_stride);
+        const float4* rr = raw + ray * S;
+        const float* zz = z + ray * S;
+        float carry = 1.0f;
+        float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+        // software prefetch: chunk c+1 is in flight while chunk c is reduced
+        int k = lane;
+        float4 r = k < S ? rr[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float zk = k < S ? zz[k] : 0.f;
+        float zn = k + 1 < S ? zz[k + 1] : 0.f;
+        for (int c0 = 0; c0 < S; c0 += 32) {
+            int kn = c0 + 32 + lane;
+            float4 r_next = kn < S ? rr[kn] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float zk_next = kn < S ? zz[kn] : 0.f;
+            float zn_next = kn + 1 < S ? zz[kn + 1] : 0.f;
+            bool valid = k < S;
+            float dist = (k == S - 1) ? 1e10f : __fsub_rn(zn, zk);
+            dist = __fmul_rn(dist, norm);
+            float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(r.w, dist))) : 0.f;
+            float q = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+            float p = warp_scan_mul(q, lane);
+            float excl = __shfl_up_sync(kFull, p, 1);
+            if (lane == 0) excl = 1.0f;
+            float w = alpha * (carry * excl);
+            carry *= __shfl_sync(kFull, p, 31);
+            ar = fmaf(w, r.x, ar); ag = fmaf(w, r.y, ag); ab = fmaf(w, r.z, ab);
+            ad = fmaf(w, zk, ad); aa += w;
+            if (kWeights && valid) w_out[ray * S + k] = w;
+            r = r_next; zk = zk_next; zn = zn_next; k = kn;
+        }
+        ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
+        if (lane == 0) {
+            float bg = 1.0f - aa;                          // white background, always (render.py:101)
+            rgb_out[ray * 3 + 0] = ar + bg; rgb_out[ray * 3 + 1] = ag + bg; rgb_out[ray * 3 + 2] = ab + bg;
+            depth_out[ray] = ad;
+            acc_out[ray] = aa;
+        }
+    }
+}
+
+// Reverse mode.  Pass 1 walks the chunks forward keeping (e=1-alpha, T, w, gw, dist) of this
+// lane's samples in registers; pass 2 walks them backward with a suffix-sum scan of gw*w.
+//   gw_k = sum_ch gC_ch (c_k,ch - 1) + gA + gD z_k ;  gc_k = w_k gC
+//   R_k = sum_{j>k} gw_j w_j ;  galpha_k = gw_k T_k - R_k / q_k ;  gsigma_k = galpha_k dist_k e_k
+template <int CH>
+__global__ void __launch_bounds__(256) composite_bwd_kernel(
+    const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
+    long long n_rays, int S, const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
+    const float* __restrict__ g_acc, float4* __restrict__ d_raw) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long ray = warp0; ray < n_rays; ray += n_warps) {
+        const float norm = ray_norm(rays_d + ray * d_stride);
+        const float4* rr = raw + ray * S;
+        const float* zz = z + ray * S;
+        const float gr = g_rgb[ray * 3 + 0], gg = g_rgb[ray * 3 + 1], gb = g_rgb[ray * 3 + 2];
+        const float gd = g_depth ? g_depth[ray] : 0.f;
+        const float ga = g_acc ? g_acc[ray] : 0.f;
+        float e[CH], T[CH], w[CH], gw[CH], dist[CH];
+        float carry = 1.0f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            int k = c * 32 + lane;
+            bool valid = k < S;
+            float4 r = valid ? rr[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float zk = valid ? zz[k] : 0.f;
+            float zn = k + 1 < S ? zz[k + 1] : 0.f;
+            float dd = (k == S - 1) ? 1e10f : __fsub_rn(zn, zk);
+            dd = __fmul_rn(dd, norm);
+            float ee = valid ? expf(-__fmul_rn(r.w, dd)) : 1.0f;
+            float alpha = __fsub_rn(1.0f, ee);
+            float q = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+            float p = warp_scan_mul(q, lane);
+            float excl = __shfl_up_sync(kFull, p, 1);
+            if (lane == 0) excl = 1.0f;
+            float t = carry * excl;
+            carry *= __shfl_sync(kFull, p, 31);
+            e[c] = ee; T[c] = t; w[c] = valid ? alpha * t : 0.f; dist[c] = dd;
+            gw[c] = valid ? (gr * (r.x - 1.0f) + gg * (r.y - 1.0f) + gb * (r.z - 1.0f) + ga + gd * zk) : 0.f;
+        }
+        float carry_r = 0.f;
+#pragma unroll
+        for (int c = CH - 1; c >= 0; --c) {
+            int k = c * 32 + lane;
+            float s = gw[c] * w[c];
+            float p = s;                                   // inclusive suffix sum over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                float t = __shfl_down_sync(kFull, p, o);
+                if (lane + o < 32) p += t;
+            }
+            float R = (p - s) + carry_r;
+            carry_r += __shfl_sync(kFull, p, 0);
+            if (k < S) {
+                float q = __fadd_rn(e[c], 1e-10f);         // 1 - alpha + 1e-10 with 1-alpha == e up to rounding
+                float g_alpha = gw[c] * T[c] - R / q;
+                float g_sigma = g_alpha * dist[c] * e[c];
+                d_raw[ray * S + k] = make_float4(w[c] * gr, w[c] * gg, w[c] * gb, g_sigma);
+            }
+        }
+    }
+}
+
+static inline unsigned ray_grid(long long n_rays) {
+    long long want = (n_rays + 7) / 8;             // 8 warps per CTA
+    long long cap = 148LL * 8;
+    return (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace b2r
+
+extern "C" int b2r_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                                 long long n_rays, int n_samples, float* rgb_out, float* depth_out,
+                                 float* acc_out, float* weights_out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(raw && z && rays_d && rgb_out && depth_out && acc_out, "b2r_composite_fwd: NULL pointer");
+    B2R_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "b2r_composite_fwd: need n_rays >= 0, n_samples >= 1");
+    B2R_CHECK_ARG(d_stride >= 3, "b2r_composite_fwd: d_stride must be >= 3");
+    B2R_CHECK_ARG(((uintptr_t)raw & 15) == 0, "b2r_composite_fwd: raw must be 16-byte aligned");
+    if (n_rays == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = ray_grid(n_rays);
+    if (weights_out)
+        composite_fwd_kernel<true><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, n_samples, rgb_out, depth_out, acc_out, weights_out);
+    else
+        composite_fwd_kernel<false><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, n_samples, rgb_out, depth_out, acc_out, nullptr);
+    B2R_LAUNCH_CHECK("b2r_composite_fwd");
+    return 0;
+}
+
+extern "C" int b2r_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                                 long long n_rays, int n_samples, const float* g_rgb, const float* g_depth,
+                                 const float* g_acc, float* d_raw, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(raw && z && rays_d && g_rgb && d_raw, "b2r_composite_bwd: NULL pointer");
+    B2R_CHECK_ARG(n_rays >= 0 && n_samples >= 1 && n_samples <= 512, "b2r_composite_bwd: need 1 <= n_samples <= 512");
+    B2R_CHECK_ARG(d_stride >= 3, "b2r_composite_bwd: d_stride must be >= 3");
+    B2R_CHECK_ARG((((uintptr_t)raw | (uintptr_t)d_raw) & 15) == 0, "b2r_composite_bwd: raw / d_raw must be 16-byte aligned");
+    if (n_rays == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = ray_grid(n_rays);
+    int ch = (n_samples + 31) / 32;
+#define B2R_BWD(CH)                                                                                          \
+    composite_bwd_kernel<CH><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, n_samples, \
+                                                   g_rgb, g_depth, g_acc, (float4*)d_raw)
+    if (ch <= 1) B2R_BWD(1);
+    else if (ch <= 2) B2R_BWD(2);
+    else if (ch <= 3) B2R_BWD(3);
+    else if (ch <= 4) B2R_BWD(4);
+    else if (ch <= 6) B2R_BWD(6);
+    else if (ch <= 8) B2R_BWD(8);
+    else if (ch <= 12) B2R_BWD(12);
+    else B2R_BWD(16);
+#undef B2R_BWD
+    B2R_LAUNCH_CHECK("b2r_composite_bwd");
+    return 0;
+}

@@ -1,0 +1,127 @@
+// K1 ray generation and K2 stratified coarse samples.
+//   get_rays      nerf/render.py:7-23   (== pi_GAN/render.py:52-68)
+//   render_rays   nerf/render.py:123-132 (linspace / mids / upper / lower / jitter lerp)
+// Both are pure streaming kernels (HBM-write bound): one thread per output row / element,
+// 148 SMs x several CTAs, fully coalesced stores.
+#include "common.cuh"
+
+namespace b2r {
+
+template <typename T>
+struct Cam {
+    T r[9];    // c2w[:3,:3] row-major
+    T t[3];    // c2w[:3,3]
+};
+
+// Each op is rounded separately (numpy evaluates mul / sum as separate float32 ufuncs, no FMA):
+// dirs = [(i - W/2)/f, -(j - H/2)/f, -1];  d_k = sum_m dirs_m * R[k,m]  (left-to-right)
+__global__ void raygen_f32_kernel(Cam<float> cam, int width, float half_w, float half_h, float focal,
+                                  long long begin, long long count, float* __restrict__ rays) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    long long pix = begin + t;
+    float i = (float)(pix % width), j = (float)(pix / width);
+    float dx = __fdiv_rn(__fsub_rn(i, half_w), focal);
+    float dy = __fdiv_rn(-__fsub_rn(j, half_h), focal);
+    float dz = -1.0f;
+    float* out = rays + t * 6;
+    out[0] = cam.t[0]; out[1] = cam.t[1]; out[2] = cam.t[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float s = __fadd_rn(__fmul_rn(dx, cam.r[3 * k + 0]), __fmul_rn(dy, cam.r[3 * k + 1]));
+        out[3 + k] = __fadd_rn(s, __fmul_rn(dz, cam.r[3 * k + 2]));
+    }
+}
+
+// np.float64 focal (pi_GAN/modules.py:127): (i - W/2) is still float32, the division and
+// everything after it are float64; the caller rounds to float32 (pi_GAN/render.py:202).
+__global__ void raygen_f64_kernel(Cam<double> cam, int width, float half_w, float half_h, double focal,
+                                  int div_f64, long long begin, long long count, float* __restrict__ rays) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    long long pix = begin + t;
+    float i = (float)(pix % width), j = (float)(pix / width);
+    double dx, dy;
+    if (div_f64) {
+        dx = __ddiv_rn((double)__fsub_rn(i, half_w), focal);
+        dy = __ddiv_rn((double)(-__fsub_rn(j, half_h)), focal);
+    } else {   // float32 dirs (python-float focal), float64 pose
+        dx = (double)__fdiv_rn(__fsub_rn(i, half_w), (float)focal);
+        dy = (double)__fdiv_rn(-__fsub_rn(j, half_h), (float)focal);
+    }
+    double dz = -1.0;
+    float* out = rays + t * 6;
+    out[0] = (float)cam.t[0]; out[1] = (float)cam.t[1]; out[2] = (float)cam.t[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double s = __dadd_rn(__dmul_rn(dx, cam.r[3 * k + 0]), __dmul_rn(dy, cam.r[3 * k + 1]));
+        out[3 + k] = (float)__dadd_rn(s, __dmul_rn(dz, cam.r[3 * k + 2]));
+    }
+}
+
+// z = lower + (upper - lower) * t, three separately rounded ops as in torch (render.py:132).
+__global__ void stratified_kernel(const float* __restrict__ z_lin, const float* __restrict__ t_rand,
+                                  long long total, int sc, float* __restrict__ z_out,
+                                  float* __restrict__ mids_out) {
+    extern __shared__ float sm[];
+    float* lower = sm;
+    float* span = sm + sc;
+    for (int k = threadIdx.x; k < sc; k += blockDim.x) {
+        float zk = z_lin[k];
+        float lo = k == 0 ? zk : __fmul_rn(0.5f, __fadd_rn(zk, z_lin[k - 1]));
+        float up = k == sc - 1 ? zk : __fmul_rn(0.5f, __fadd_rn(z_lin[k + 1], zk));
+        lower[k] = lo;
+        span[k] = __fsub_rn(up, lo);
+        if (mids_out && blockIdx.x == 0 && k < sc - 1) mids_out[k] = up;
+    }
+    __syncthreads();
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
+        int k = (int)(e % sc);
+        z_out[e] = __fadd_rn(lower[k], __fmul_rn(span[k], t_rand[e]));
+    }
+}
+
+}  // namespace b2r
+
+extern "C" int b2r_raygen(const double* c2w_host, int width, int height, double focal, int compute_f64,
+                          long long ray_begin, long long ray_count, float* rays_out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(c2w_host && rays_out, "b2r_raygen: NULL pointer");
+    B2R_CHECK_ARG(width > 0 && height > 0 && focal != 0.0, "b2r_raygen: bad image geometry");
+    B2R_CHECK_ARG(ray_begin >= 0 && ray_count >= 0 && ray_begin + ray_count <= (long long)width * height,
+                  "b2r_raygen: ray range outside the image");
+    if (ray_count == 0) return 0;
+    Cam<double> cam;
+    Cam<float> camf;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) { cam.r[3 * r + c] = c2w_host[4 * r + c]; camf.r[3 * r + c] = (float)c2w_host[4 * r + c]; }
+        cam.t[r] = c2w_host[4 * r + 3]; camf.t[r] = (float)c2w_host[4 * r + 3];
+    }
+    // width * 0.5 is a python float; numpy (NEP 50) keeps the float32 array dtype
+    float half_w = (float)(width * 0.5), half_h = (float)(height * 0.5);
+    int block = 256;
+    long long grid = (ray_count + block - 1) / block;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (compute_f64)
+        raygen_f64_kernel<<<(unsigned)grid, block, 0, st>>>(cam, width, half_w, half_h, focal, compute_f64 & 1, ray_begin, ray_count, rays_out);
+    else
+        raygen_f32_kernel<<<(unsigned)grid, block, 0, st>>>(camf, width, half_w, half_h, (float)focal, ray_begin, ray_count, rays_out);
+    B2R_LAUNCH_CHECK("b2r_raygen");
+    return 0;
+}
+
+extern "C" int b2r_stratified_z(const float* z_lin, const float* t_rand, long long n_rays, int n_coarse,
+                                float* z_out, float* mids_out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(z_lin && t_rand && z_out, "b2r_stratified_z: NULL pointer");
+    B2R_CHECK_ARG(n_rays >= 0 && n_coarse >= 2 && n_coarse <= 4096, "b2r_stratified_z: need n_rays >= 0, 2 <= n_coarse <= 4096");
+    long long total = n_rays * n_coarse;
+    int block = 256;
+    long long want = (total + block - 1) / block;
+    long long cap = 148LL * 8;
+    unsigned grid = (unsigned)(want < 1 ? 1 : (want > cap ? cap : want));
+    stratified_kernel<<<grid, block, 2 * n_coarse * sizeof(float), (cudaStream_t)stream>>>(z_lin, t_rand, total, n_coarse, z_out, mids_out);
+    B2R_LAUNCH_CHECK("b2r_stratified_z");
+    return 0;
+}

@@ -1,0 +1,96 @@
+"""Multi-GPU sharding of the render path: one process per GPU (torch.distributed, NCCL over NVLink).
+
+The path shards by independent units: rays of a frame by contiguous pixel rows,
+pi-GAN latents by batch index, density-grid points by linear index.  No collective sits on the data
+path; the only exchanges are the final image gather and, in training, ONE all-reduce of the flat
+fp32 gradient bucket.  The reference's incumbent is single-process nn.DataParallel
+(pi_GAN/train.py:50-52); nerf/ has no multi-GPU path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int, align: int = 1) -> tuple[int, int]:
+    """Contiguous block [begin, begin+count) of n units for `rank`; blocks differ by at most
+    `align` units and the remainder goes to the last ranks' predecessors evenly."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    blocks = (n + align - 1) // align
+    base, rem = divmod(blocks, world)
+    b0 = rank * base + min(rank, rem)
+    cnt = base + (1 if rank < rem else 0)
+    begin = min(b0 * align, n)
+    end = min((b0 + cnt) * align, n)
+    return begin, end - begin
+
+
+def gather_image(rgb: torch.Tensor, depth: torch.Tensor, acc: torch.Tensor, out: torch.Tensor, n_rays: int,
+                 rank: int, world: int, group=None) -> torch.Tensor:
+    """All-gather each rank's [count,5] = (rgb, depth, acc) rows into `out`[n_rays,5] (every rank
+    receives the frame).  Ranks own unequal row counts, so this is all_gather over a list of
+    views of `out` -- NCCL writes in place, no staging copy on the receive side."""
+    mine = torch.cat([rgb, depth[:, None], acc[:, None]], -1).contiguous()
+    if world == 1:
+        out[: mine.shape[0]].copy_(mine)
+        return out
+    views = []
+    for r in range(world):
+        b, c = shard_range(n_rays, r, world)
+        views.append(out[b:b + c])
+    dist.all_gather(views, mine, group=group)
+    return out
+
+
+def render_image_sharded(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
+                         fine_sample_num, *, t_rand_full: torch.Tensor | None = None, precision=None, group=None):
+    """render_image (nerf/render.py:150-167) with the frame's rays sharded over the ranks of
+    `group`; returns (rgb[H,W,3], depth[H,W,1], acc[H,W,1]) CUDA tensors on every rank.
+    Every rank draws the SAME global jitter (same seed) and slices its rows, so the result does not
+    depend on the number of ranks."""
+    from . import nerf_render
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = int(width) * int(height)
+    begin, count = shard_range(n, rank, world)
+    dev = next(coarse_model.parameters()).device
+    if t_rand_full is None:
+        t_rand_full = nerf_render._draw_t_rand(n, int(coarse_sample_num), nerf_render.REFERENCE_RAY_CHUNK, dev)
+    with torch.no_grad():
+        o = nerf_render.render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model,
+                                            coarse_sample_num, fine_sample_num, ray_begin=begin, ray_count=count,
+                                            t_rand=t_rand_full[begin:begin + count], precision=precision)
+        out = torch.empty((n, 5), dtype=torch.float32, device=dev)
+        gather_image(o[3], o[4], o[5], out, n, rank, world, group)
+    h, w = int(height), int(width)
+    return out[:, :3].reshape(h, w, 3), out[:, 3].reshape(h, w, 1), out[:, 4].reshape(h, w, 1)
+
+
+def flat_grad_bucket(models_: list) -> torch.Tensor:
+    """ONE flat fp32 tensor holding the gradients of all given models' parameters (2 x 593,924
+    floats = 4.75 MB for the NeRF pair), in canonical parameter order."""
+    gs = []
+    for m in models_:
+        for p in m.parameters():
+            gs.append((p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1))
+    return torch.cat(gs)
+
+
+def allreduce_gradients(models_: list, group=None, average: bool = True) -> None:
+    """Gradient exchange of the training configuration (C3): one NCCL all-reduce of the flat bucket,
+    then scatter back into the .grad tensors."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    bucket = flat_grad_bucket(models_)
+    dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        bucket /= dist.get_world_size(group)
+    off = 0
+    for m in models_:
+        for p in m.parameters():
+            n = p.numel()
+            if p.grad is None:
+                p.grad = torch.empty_like(p)
+            p.grad.copy_(bucket[off:off + n].view_as(p))
+            off += n

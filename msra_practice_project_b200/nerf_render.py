@@ -1,0 +1,155 @@
+"""Drop-in replacement for the reference's ``nerf/render.py`` backed by libb2r.so (sm_100a CUDA).
+
+Same names, argument order and return conventions as the reference module (file:line cited per
+function), so ``from render import *`` callers (nerf/train_nerf.py:8, test_nerf.py:8,
+show_nerf.py:5, demo_view.py:8, demo_param.py:8) keep working; ``np``, ``torch`` and ``tqdm`` are
+re-exported because those callers rely on the star-import leaking them (train_nerf.py:69,78-83).
+
+Backwards-compatible keyword-only additions: ``t_rand`` (inject the jitter the reference draws
+with torch.rand, for parity runs), ``z_lin`` / ``u`` (inject the two torch.linspace vectors),
+``precision`` ("bf16" tensor-core MLP or "fp32"), ``stages`` (dict that receives intermediates).
+
+There is no CPU path: tensors and models must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from . import ops
+
+__all__ = ["np", "torch", "tqdm", "to8b", "get_rays", "sample_pdf", "run_network", "raw_to_outputs", "render_rays",
+           "render_image", "render_video"]
+
+to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)       # nerf/render.py:5
+
+REFERENCE_RAY_CHUNK = 1024 * 16                                  # nerf/render.py:150
+
+
+def _model_device(model) -> torch.device:
+    return next(model.parameters()).device
+
+
+def get_rays(width, height, focal, c2w):
+    """nerf/render.py:7-23 -- (rays_o, rays_d) numpy arrays [H,W,3], generated on the GPU (K1)."""
+    rays = ops.raygen(int(width), int(height), focal, c2w).cpu().numpy()
+    rays = rays.reshape(int(height), int(width), 2, 3)
+    return rays[:, :, 0], rays[:, :, 1]
+
+
+def sample_pdf(bins, weights, N_samples, *, u=None):
+    """nerf/render.py:27-56 -- hierarchical inverse-CDF samples [N, N_samples] (K5)."""
+    return ops.sample_pdf(bins, weights, int(N_samples), u=u)["samples"]
+
+
+def run_network(ray_samples, view_dirs, network, chunk=1024 * 64, *, precision=None):
+    """nerf/render.py:59-75 -- evaluate ``network`` on every sample point -> [N,S,4].
+
+    ``chunk`` is accepted for signature compatibility; the fused kernel has O(tile) memory so the
+    points are evaluated in one launch."""
+    n, s = ray_samples.shape[0], ray_samples.shape[1]
+    pts = ray_samples.reshape(-1, 3)
+    vd = view_dirs[:, None, :].expand(n, s, 3).reshape(-1, 3)
+    x = torch.cat([pts, vd], -1)
+    return ops.mlp(network, x=x, precision=precision).reshape(n, s, 4)
+
+
+def raw_to_outputs(raw, z_vals, rays_d):
+    """nerf/render.py:78-103 -- (rgb_map[N,3], depth_map[N], acc_map[N], weights[N,S]) (K4)."""
+    return ops.composite(raw, z_vals, rays_d, want_weights=True)
+
+
+def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num, *,
+                t_rand=None, z_lin=None, u=None, precision=None, stages=None, coarse_no_grad=False):
+    """nerf/render.py:106-147 -- coarse pass, sample_pdf on the un-jittered mids with
+    weights[:,1:-1], sort-merge, fine pass on all Sc+Sf samples.  Returns the reference's 6-tuple
+    (rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f).  ``coarse_no_grad`` runs the coarse pass in
+    inference mode (used by the pi-GAN wrappers, whose loss never touches the coarse outputs)."""
+    if not isinstance(rays, torch.Tensor):
+        rays = torch.as_tensor(np.asarray(rays), dtype=torch.float32)
+    if not rays.is_cuda:
+        rays = rays.to(_model_device(coarse_model))
+    rays = rays.float().reshape(-1, 2, 3).contiguous()          # no .squeeze(): N == 1 works
+    dev = rays.device
+    sc, sf = int(coarse_sample_num), int(fine_sample_num)       # callers pass floats (test_nerf.py:34-35)
+    n = rays.shape[0]
+    if z_lin is None:
+        # made on the host: torch.linspace's last-bit rounding is part of the contract
+        z_lin = torch.linspace(float(near), float(far), steps=sc, device="cpu")
+    z_lin = torch.as_tensor(z_lin, dtype=torch.float32).to(dev)
+    if t_rand is None:
+        t_rand = torch.rand((n, sc), device=dev)                # nerf/render.py:131 (jitter is always on)
+    t_rand = torch.as_tensor(t_rand, dtype=torch.float32).to(dev)
+    rays_d = rays[:, 1]
+
+    z_vals, mids = ops.stratified_z(z_lin, t_rand)
+    with torch.set_grad_enabled(torch.is_grad_enabled() and not coarse_no_grad):
+        raw = ops.mlp(coarse_model, rays=rays, z=z_vals, precision=precision).view(n, sc, 4)
+        rgb_c, depth_c, acc_c, weights = ops.composite(raw, z_vals, rays_d, want_weights=True)
+
+    if u is None:
+        u = torch.linspace(0.0, 1.0, steps=sf, device="cpu")
+    res = ops.sample_pdf(mids, weights[:, 1:-1], sf, u=torch.as_tensor(u, dtype=torch.float32).to(dev), z_coarse=z_vals,
+                         want_samples=stages is not None)
+    z_fine = res["sorted"]
+    raw_f = ops.mlp(fine_model, rays=rays, z=z_fine, precision=precision).view(n, sc + sf, 4)
+    rgb_f, depth_f, acc_f, w_f = ops.composite(raw_f, z_fine, rays_d, want_weights=stages is not None)
+    if stages is not None:
+        stages.update(z_coarse=z_vals, mids=mids, raw_coarse=raw, weights_coarse=weights, z_samples=res["samples"],
+                      z_fine=z_fine, raw_fine=raw_f, weights_fine=w_f)
+    return rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f
+
+
+def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
+    """The jitter of a whole image, drawn exactly as the reference does: one torch.rand([chunk,Sc])
+    per ray chunk (nerf/render.py:158-160,131), so a seeded render reproduces the reference."""
+    parts = [torch.rand((min(chunk, n - i), sc), device=device) for i in range(0, n, chunk)]
+    return parts[0] if len(parts) == 1 else torch.cat(parts)
+
+
+def render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
+                        fine_sample_num, chunk=REFERENCE_RAY_CHUNK, *, ray_begin=0, ray_count=None, t_rand=None,
+                        precision=None, launch_rays=1 << 20, coarse_no_grad=False):
+    """Device-resident core of render_image: renders flattened pixel rows [ray_begin, +ray_count)
+    and returns the six per-ray outputs of the fine AND coarse pass as CUDA tensors.  Rays are
+    generated on the device (K1); ``launch_rays`` bounds the rays per kernel launch sequence."""
+    dev = _model_device(coarse_model)
+    width, height = int(width), int(height)
+    total = width * height
+    ray_count = total - ray_begin if ray_count is None else ray_count
+    sc = int(coarse_sample_num)
+    if t_rand is None:
+        t_full = _draw_t_rand(total, sc, int(chunk), dev)
+        t_rand = t_full[ray_begin:ray_begin + ray_count]
+    outs = []
+    for b in range(0, ray_count, launch_rays):
+        cnt = min(launch_rays, ray_count - b)
+        rays = ops.raygen(width, height, focal, pose, ray_begin + b, cnt, device=dev)
+        outs.append(render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                                t_rand=t_rand[b:b + cnt], precision=precision, coarse_no_grad=coarse_no_grad))
+    if len(outs) == 1:
+        return outs[0]
+    return tuple(torch.cat([o[i] for o in outs]) for i in range(6))
+
+
+def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                 chunk=1024 * 16, *, t_rand=None, precision=None):
+    """nerf/render.py:150-167 -- numpy (H,W,3), (H,W,1), (H,W,1) = fine rgb / depth / acc."""
+    with torch.no_grad():
+        out = render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
+                                  fine_sample_num, chunk, t_rand=t_rand, precision=precision)
+    h, w = int(height), int(width)
+    return (out[3].cpu().numpy().reshape(h, w, 3), out[4].cpu().numpy().reshape(h, w, 1),
+            out[5].cpu().numpy().reshape(h, w, 1))
+
+
+def render_video(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                 chunk=1024 * 16):
+    """nerf/render.py:170-182 -- stacked per-pose render_image outputs."""
+    rgb_video, depth_video, acc_video = [], [], []
+    for _, p in enumerate(tqdm(poses)):
+        rgb, depth, acc = render_image(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
+                                       fine_sample_num, chunk)
+        rgb_video.append(rgb); depth_video.append(depth); acc_video.append(acc)
+    return np.stack(rgb_video), np.stack(depth_video), np.stack(acc_video)

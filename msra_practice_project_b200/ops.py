@@ -1,0 +1,305 @@
+"""Host-side operators over the C ABI of libb2r.so (include/b2r.h).
+
+Each function mirrors one stage of the reference's render path and calls exactly one CUDA entry
+point; the autograd-aware ones (``composite``, ``mlp``) own their saved-for-backward buffers, as
+torch autograd does for the reference (nerf/train_nerf.py:167).  Everything here requires CUDA
+tensors and raises otherwise -- there is no CPU or PyTorch-op fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib, models
+from ._lib import MlpInput, check, lib, ptr
+
+# MLP arithmetic used when no gradient is required: "bf16" = fused tcgen05 kernel (mlp_tc.cu),
+# "fp32" = layer-wise CUDA-core path (mlp_f32.cu).  Gradients always use the fp32 path.
+_MLP_PRECISION = "bf16"
+
+
+def set_mlp_precision(p: str) -> str:
+    global _MLP_PRECISION
+    if p not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    old, _MLP_PRECISION = _MLP_PRECISION, p
+    return old
+
+
+def get_mlp_precision() -> str:
+    return _MLP_PRECISION
+
+
+def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 render path has no CPU fallback")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+# ---- K1 / K2 ---------------------------------------------------------------------------------------
+def raygen(width: int, height: int, focal, c2w, begin: int = 0, count: int | None = None,
+           device=None) -> torch.Tensor:
+    """rows [begin, begin+count) of the [H*W,2,3] ray table (get_rays + render_image reshaping,
+    nerf/render.py:7-23,151-154)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    c2w_np = c2w.detach().cpu().numpy() if isinstance(c2w, torch.Tensor) else np.asarray(c2w)
+    f64 = (1 if isinstance(focal, np.float64) else 0) | (2 if c2w_np.dtype == np.float64 else 0)
+    m = np.ascontiguousarray(c2w_np[:3, :4], dtype=np.float64)
+    count = width * height - begin if count is None else count
+    out = torch.empty((count, 2, 3), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        check(lib().b2r_raygen(m.ctypes.data_as(C.POINTER(C.c_double)), int(width), int(height), float(focal), f64,
+                               int(begin), int(count), ptr(out), _stream(out)), "b2r_raygen")
+    return out
+
+
+def stratified_z(z_lin: torch.Tensor, t_rand: torch.Tensor):
+    """z_vals[N,Sc], mids[Sc-1] from linspace(near,far,Sc) and the jitter (nerf/render.py:123-132)."""
+    z_lin = _cuda_f32(z_lin, "z_lin")
+    t_rand = _cuda_f32(t_rand, "t_rand")
+    n, sc = t_rand.shape
+    z = torch.empty_like(t_rand)
+    mids = torch.empty((sc - 1,), dtype=torch.float32, device=t_rand.device)
+    with torch.cuda.device(t_rand.device):
+        check(lib().b2r_stratified_z(ptr(z_lin), ptr(t_rand), n, sc, ptr(z), ptr(mids), _stream(z)), "b2r_stratified_z")
+    return z, mids
+
+
+# ---- K4 ----------------------------------------------------------------------------------------------
+def _dirs_view(rays_d: torch.Tensor):
+    """(tensor to keep alive, pointer, stride in floats) for N direction vectors."""
+    if rays_d.dim() != 2 or rays_d.shape[1] != 3:
+        raise RuntimeError("rays_d must be [N,3]")
+    if rays_d.dtype == torch.float32 and rays_d.is_cuda and rays_d.stride(1) == 1 and rays_d.stride(0) >= 3:
+        return rays_d, rays_d.data_ptr(), rays_d.stride(0)          # e.g. rays[:,1] of an [N,2,3] table: stride 6
+    d = _cuda_f32(rays_d, "rays_d")
+    return d, d.data_ptr(), 3
+
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, z, rays_d, want_weights):
+        raw = _cuda_f32(raw, "raw")
+        z = _cuda_f32(z, "z_vals")
+        keep, dptr, dstride = _dirs_view(rays_d.detach())
+        n, s = z.shape
+        dev = z.device
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        depth = torch.empty((n,), dtype=torch.float32, device=dev)
+        acc = torch.empty((n,), dtype=torch.float32, device=dev)
+        w = torch.empty((n, s), dtype=torch.float32, device=dev) if want_weights else None
+        with torch.cuda.device(dev):
+            check(lib().b2r_composite_fwd(ptr(raw), ptr(z), dptr, dstride, n, s, ptr(rgb), ptr(depth), ptr(acc), ptr(w),
+                                          _stream(z)), "b2r_composite_fwd")
+        ctx.save_for_backward(raw, z, keep)
+        ctx.dstride = dstride
+        if w is None:
+            w = torch.empty((0,), device=dev)
+        ctx.mark_non_differentiable(w)
+        return rgb, depth, acc, w
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_acc, _g_w):
+        raw, z, keep = ctx.saved_tensors
+        n, s = z.shape
+        g_rgb = torch.zeros((n, 3), device=z.device) if g_rgb is None else _cuda_f32(g_rgb, "g_rgb")
+        g_depth = None if g_depth is None else _cuda_f32(g_depth, "g_depth")
+        g_acc = None if g_acc is None else _cuda_f32(g_acc, "g_acc")
+        d_raw = torch.empty_like(raw)
+        with torch.cuda.device(z.device):
+            check(lib().b2r_composite_bwd(ptr(raw), ptr(z), keep.data_ptr(), ctx.dstride, n, s, ptr(g_rgb), ptr(g_depth),
+                                          ptr(g_acc), ptr(d_raw), _stream(z)), "b2r_composite_bwd")
+        return d_raw, None, None, None
+
+
+def composite(raw, z_vals, rays_d, want_weights: bool = True):
+    """raw_to_outputs (nerf/render.py:78-103): (rgb[N,3], depth[N], acc[N], weights[N,S] or None).
+    Differentiable wrt ``raw``; the weights are returned detached (the reference only uses them
+    through sample_pdf, whose result is detached, nerf/render.py:141)."""
+    rgb, depth, acc, w = _Composite.apply(raw, z_vals, rays_d, bool(want_weights))
+    return rgb, depth, acc, (w if want_weights else None)
+
+
+# ---- K5 / K6 -------------------------------------------------------------------------------------------
+def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: torch.Tensor | None = None,
+               z_coarse: torch.Tensor | None = None, want_samples: bool = True, want_cdf: bool = False):
+    """sample_pdf (nerf/render.py:27-56) and, when ``z_coarse`` is given, the sort-merge of :142.
+
+    ``weights`` may be a strided view such as ``w[:, 1:-1]`` (no copy).  Returns a dict with the
+    requested tensors: samples[N,Sf], sorted[N,Sc+Sf], cdf[N,nb]."""
+    if not weights.is_cuda:
+        raise RuntimeError("weights must be a CUDA tensor")
+    weights = weights.detach()
+    if weights.dtype != torch.float32 or weights.stride(1) != 1:
+        weights = weights.float().contiguous()
+    n, nw = weights.shape
+    nb = nw + 1
+    dev = weights.device
+    bins = bins.detach()
+    if bins.dim() == 1 or bins.stride(0) == 0:
+        b = _cuda_f32(bins if bins.dim() == 1 else bins[0], "bins")
+        b_stride = 0
+    else:
+        b = _cuda_f32(bins, "bins")
+        b_stride = nb
+    if b.shape[-1] != nb:
+        raise RuntimeError(f"bins has {b.shape[-1]} entries, expected len(weights)+1 = {nb}")
+    if u is None:
+        u = torch.linspace(0.0, 1.0, steps=int(n_samples)).to(dev)       # host-made: its rounding is a contract
+    u = _cuda_f32(u, "u")
+    sf = int(n_samples)
+    samples = torch.empty((n, sf), dtype=torch.float32, device=dev) if want_samples else None
+    cdf = torch.empty((n, nb), dtype=torch.float32, device=dev) if want_cdf else None
+    merged, zc, sc = None, None, 0
+    if z_coarse is not None:
+        zc = _cuda_f32(z_coarse.detach(), "z_coarse")
+        sc = zc.shape[1]
+        merged = torch.empty((n, sc + sf), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().b2r_sample_pdf(ptr(b), b_stride, weights.data_ptr(), weights.stride(0), ptr(u), n, nb, sf, ptr(zc), sc,
+                                   ptr(samples), ptr(merged), ptr(cdf), _stream(weights)), "b2r_sample_pdf")
+    return {"samples": samples, "sorted": merged, "cdf": cdf}
+
+
+# ---- K3 / K7 / K8 ------------------------------------------------------------------------------------------
+_pack_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _packed_weights(model, kind: int, flat: torch.Tensor, film: torch.Tensor | None, use_dir: bool) -> torch.Tensor:
+    """bf16 / swizzled copy of the weights for the tensor-core kernel, cached per model and
+    invalidated when any parameter (or the FiLM tensor) changes in place or is replaced."""
+    ps = models.param_list(model, kind)
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    if film is not None:
+        key += ((film.data_ptr(), film._version),)
+    hit = _pack_cache.get(model)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    nbytes = lib().b2r_mlp_tc_packed_bytes(kind)
+    if nbytes == 0:
+        raise RuntimeError(f"model kind {kind} has no tensor-core path in this build")
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=flat.device)
+    with torch.cuda.device(flat.device):
+        check(lib().b2r_mlp_tc_pack(kind, ptr(flat), ptr(film), int(use_dir), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack")
+    _pack_cache[model] = (key, packed)
+    return packed
+
+
+def _make_input(rays, z, x, grid):
+    """(MlpInput, rows, tensors to keep alive)"""
+    inp = MlpInput()
+    if rays is not None:
+        rays = _cuda_f32(rays, "rays")
+        z = _cuda_f32(z, "z_vals")
+        if rays.dim() != 3 or tuple(rays.shape[1:]) != (2, 3) or z.shape[0] != rays.shape[0]:
+            raise RuntimeError("rays must be [N,2,3] and z [N,S]")
+        inp.rays, inp.z, inp.n_rays, inp.n_samples = rays.data_ptr(), z.data_ptr(), rays.shape[0], z.shape[1]
+        return inp, rays.shape[0] * z.shape[1], (rays, z)
+    if x is not None:
+        x = _cuda_f32(x, "x")
+        if x.dim() != 2 or x.shape[1] != 6:
+            raise RuntimeError("x must be [M,6] = (position, direction)")
+        inp.x, inp.n_rays, inp.n_samples = x.data_ptr(), x.shape[0], 1
+        return inp, x.shape[0], (x,)
+    n, begin, count = grid
+    inp.grid_n, inp.grid_begin, inp.n_rays, inp.n_samples = int(n), int(begin), int(count), 1
+    return inp, int(count), ()
+
+
+class _MlpF32(torch.autograd.Function):
+    """fp32 forward that keeps every layer's output, and its reverse mode (K8)."""
+
+    @staticmethod
+    def forward(ctx, flat, film, kind, use_dir, rays, z, x):
+        inp, rows, keep = _make_input(rays, z, x, None)
+        dev = flat.device
+        raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, rows, 1)
+        ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().b2r_mlp_f32_fwd(kind, ptr(flat), ptr(film), int(use_dir), C.byref(inp), ptr(raw), ptr(ws), ws_bytes, 1,
+                                        _stream(flat)), "b2r_mlp_f32_fwd")
+        ctx.kind, ctx.use_dir, ctx.rows = kind, use_dir, rows
+        ctx.keep = keep
+        ctx.has_film = film is not None
+        ctx.save_for_backward(flat, film if film is not None else flat.new_empty(0), raw, ws)
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        flat, film, raw, ws = ctx.saved_tensors
+        film = film if ctx.has_film else None
+        rays = ctx.keep[0] if len(ctx.keep) == 2 else None
+        z = ctx.keep[1] if len(ctx.keep) == 2 else None
+        x = ctx.keep[0] if len(ctx.keep) == 1 else None
+        inp, rows, _ = _make_input(rays, z, x, None)
+        dev = flat.device
+        d_raw = _cuda_f32(d_raw, "d_raw")
+        need_w = ctx.needs_input_grad[0]
+        need_f = ctx.has_film and ctx.needs_input_grad[1]
+        d_flat = torch.zeros_like(flat) if need_w else None
+        d_film = torch.zeros_like(film) if need_f else None
+        if d_flat is None and d_film is None:
+            return (None,) * 7
+        sc_bytes = lib().b2r_mlp_f32_bwd_scratch_bytes(ctx.kind, rows)
+        scratch = torch.empty((max(sc_bytes, 16) // 4,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().b2r_mlp_f32_bwd(ctx.kind, ptr(flat), ptr(film), int(ctx.use_dir), C.byref(inp), ptr(raw), ptr(d_raw),
+                                        ptr(ws), ptr(scratch), sc_bytes, ptr(d_flat), ptr(d_film), _stream(flat)),
+                  "b2r_mlp_f32_bwd")
+        return d_flat, d_film, None, None, None, None, None
+
+
+def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, x: torch.Tensor | None = None,
+        grid: tuple | None = None, precision: str | None = None, sigma_only: bool = False) -> torch.Tensor:
+    """Evaluate the radiance field on rows described by (rays, z) | x | grid -> raw[rows,4]
+    (run_network + network.forward, nerf/render.py:59-75).  Differentiable wrt the model's
+    parameters (and FiLM parameters) when any of them requires grad and grad mode is on."""
+    kind = models.model_kind(model)
+    net = model.module if isinstance(model, torch.nn.DataParallel) else model
+    use_dir = bool(getattr(net, "use_dir", True))
+    ps = models.param_list(net, kind)
+    dev = ps[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("model parameters must live on a CUDA device: the B200 render path has no CPU fallback")
+    film = None
+    if kind == models.KIND_FILM:
+        film = models.film_tensor(net)
+        film = film.to(dev).float()
+        if tuple(film.shape) != (9, 512):
+            raise RuntimeError(f"film_params must be [9,512], got {tuple(film.shape)}")
+        film = film.contiguous()
+    needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in ps) or (film is not None and film.requires_grad))
+    flat = models.flat_params(net, kind) if needs_grad else torch.cat([p.detach().reshape(-1) for p in ps]).float()
+    precision = precision or _MLP_PRECISION
+    if needs_grad:
+        if grid is not None:
+            raise RuntimeError("grid queries are inference-only")
+        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x)
+    inp, rows, keep = _make_input(rays, z, x, grid)
+    raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        if precision == "bf16":
+            packed = _packed_weights(net, kind, flat, film, use_dir)
+            check(lib().b2r_mlp_tc_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), int(sigma_only), _stream(flat)), "b2r_mlp_tc_fwd")
+        else:
+            ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, rows, 0)
+            ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=dev)
+            check(lib().b2r_mlp_f32_fwd(kind, ptr(flat), ptr(film), int(use_dir), C.byref(inp), ptr(raw), ptr(ws), ws_bytes, 0,
+                                        _stream(flat)), "b2r_mlp_f32_fwd")
+    del keep
+    return raw
+
+
+def mlp_points(model, x: torch.Tensor) -> torch.Tensor:
+    """``network(x)`` for x[M,6] (the call of nerf/render.py:73 and pi_GAN/utils.py:86)."""
+    return mlp(model, x=x)

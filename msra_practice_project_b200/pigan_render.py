@@ -1,0 +1,104 @@
+"""Drop-in replacement for the reference's ``pi_GAN/render.py`` backed by libb2r.so (sm_100a CUDA).
+
+Lines 52-192 of the reference file are byte-identical to ``nerf/render.py:7-147``, so
+the shared functions are re-exported from :mod:`nerf_render`; this module adds the radian camera
+helpers (pi_GAN/render.py:6-49) and the pi-GAN image wrappers (:195-241).  Callers:
+pi_GAN/modules.py:3,160, train.py:8, synthesis.py:9, extract_mesh.py:8, utils.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from tqdm import tqdm
+
+from . import ops
+from .nerf_render import (get_rays, raw_to_outputs, render_image_device, render_rays, run_network, sample_pdf, to8b)
+
+__all__ = ["np", "torch", "tqdm", "to8b", "trans_t", "rot_phi", "rot_theta", "blender_coord",
+           "camera_pos_to_transform_matrix", "get_rays", "sample_pdf", "run_network", "raw_to_outputs", "render_rays",
+           "render_image", "render_image_np", "render_video_np", "render_batch", "density_grid"]
+
+# pi_GAN/render.py:6-35 (angles in radians)
+trans_t = lambda t: np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, t], [0, 0, 0, 1]], dtype=np.float32)
+rot_phi = lambda phi: np.array([[1, 0, 0, 0], [0, np.cos(phi), -np.sin(phi), 0], [0, np.sin(phi), np.cos(phi), 0],
+                                [0, 0, 0, 1]], dtype=np.float32)
+rot_theta = lambda th: np.array([[np.cos(th), 0, -np.sin(th), 0], [0, 1, 0, 0], [np.sin(th), 0, np.cos(th), 0],
+                                 [0, 0, 0, 1]], dtype=np.float32)
+blender_coord = np.array([[-1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=np.float32)
+
+
+def camera_pos_to_transform_matrix(radius, theta, phi):
+    """pi_GAN/render.py:38-49 -- camera-to-world matrix of a camera on a sphere."""
+    c2w = trans_t(radius)
+    c2w = rot_phi(phi) @ c2w
+    c2w = rot_theta(theta) @ c2w
+    return c2w
+
+
+def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                 chunk=1024 * 16, *, t_rand=None, precision=None):
+    """pi_GAN/render.py:195-206 -- fine rgb as a torch tensor [H,W,3] on the device, carrying the
+    autograd graph to the model parameters and the FiLM parameters (pi_GAN/train.py:134,
+    synthesis.py:107).  In pi-GAN coarse_model is fine_model and only the fine rgb is consumed, so
+    the coarse pass carries no gradient and runs in inference mode."""
+    out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                  chunk, t_rand, precision, coarse_no_grad=True)
+    return out[3].reshape(int(height), int(width), 3)
+
+
+def _render(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk, t_rand, precision,
+            coarse_no_grad=False):
+    return render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk,
+                               t_rand=t_rand, precision=precision, coarse_no_grad=coarse_no_grad)
+
+
+def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
+                    fine_sample_num, chunk=1024 * 16, *, t_rand=None, precision=None):
+    """pi_GAN/render.py:209-226 -- numpy (H,W,3), (H,W,1), (H,W,1)."""
+    with torch.no_grad():
+        out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                      chunk, t_rand, precision)
+    h, w = int(height), int(width)
+    return (out[3].cpu().numpy().reshape(h, w, 3), out[4].cpu().numpy().reshape(h, w, 1),
+            out[5].cpu().numpy().reshape(h, w, 1))
+
+
+def render_video_np(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num,
+                    fine_sample_num, chunk=1024 * 16):
+    """pi_GAN/render.py:229-241.  The reference unpacks three values from render_image (which returns
+    one tensor) and so raises as shipped; this calls render_image_np as evidently meant."""
+    rgb_video, depth_video, acc_video = [], [], []
+    for _, p in enumerate(tqdm(poses)):
+        rgb, depth, acc = render_image_np(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
+                                          fine_sample_num, chunk)
+        rgb_video.append(rgb); depth_video.append(depth); acc_video.append(acc)
+    return np.stack(rgb_video), np.stack(depth_video), np.stack(acc_video)
+
+
+def render_batch(model, film_params, poses, width, height, focal, near, far, coarse_sample_num, fine_sample_num, *,
+                 t_rand=None, precision=None):
+    """Batched counterpart of Generator.forward's per-latent loop (pi_GAN/modules.py:176-184):
+    film_params[B,9,512], poses[B,4,4] -> images [B,3,H,W].  This is the latent-sharding unit for
+    multi-GPU runs (each rank renders its slice of B)."""
+    imgs = []
+    for i in range(film_params.shape[0]):
+        model.set_film_params(film_params[i])
+        tr = None if t_rand is None else t_rand[i]
+        imgs.append(render_image(width, height, focal, poses[i], near, far, model, model, coarse_sample_num,
+                                 fine_sample_num, t_rand=tr, precision=precision))
+    return torch.stack(imgs).permute(0, 3, 1, 2).contiguous()
+
+
+def density_grid(model, N=256, max_batch=64 ** 3, *, begin=0, count=None, precision=None):
+    """The sampling loop of create_mesh (pi_GAN/utils.py:59-91): -sigma at the N^3 lattice points of
+    [-0.1,0.1]^3 with zero view direction, as a CUDA tensor [count].  Coordinates are generated on
+    the device from the linear index; ``max_batch`` bounds the points per launch like the reference."""
+    n3 = N ** 3
+    count = n3 - begin if count is None else count
+    out = []
+    with torch.no_grad():
+        for b in range(begin, begin + count, max_batch):
+            c = min(max_batch, begin + count - b)
+            raw = ops.mlp(model, grid=(N, b, c), precision=precision)
+            out.append(-raw[:, 3])
+    return out[0] if len(out) == 1 else torch.cat(out)

@@ -269,6 +269,28 @@ def sample_pdf(bins: np.ndarray, weights: np.ndarray, n_samples: int, u: np.ndar
     return samples
 
 
+def sample_pdf_from_cdf(bins: np.ndarray, cdf: np.ndarray, u: np.ndarray):
+    """The part of sample_pdf after the CDF (nerf/render.py:39-54): searchsorted(right=True),
+    clamp, gather, denom<1e-5 -> 1, lerp.  Used for the "indices and samples bit-exact GIVEN identical
+    CDFs" check (north_star): feed the CDF a kernel produced and compare the rest exactly.
+    Returns (samples, inds)."""
+    cdf = np.asarray(cdf, F32)
+    n, nb = cdf.shape
+    bins = np.asarray(bins, F32)
+    if bins.ndim == 1:
+        bins = np.broadcast_to(bins[None, :], (n, nb))
+    u = np.asarray(u, F32)
+    inds = np.stack([np.searchsorted(cdf[r], u, side="right") for r in range(n)]).astype(np.int64)
+    below = np.maximum(0, inds - 1)
+    above = np.minimum(nb - 1, inds)
+    cdf_b = np.take_along_axis(cdf, below, -1); cdf_a = np.take_along_axis(cdf, above, -1)
+    bins_b = np.take_along_axis(bins, below, -1); bins_a = np.take_along_axis(bins, above, -1)
+    denom = (cdf_a - cdf_b).astype(F32)
+    denom = np.where(denom < F32(1e-5), F32(1.0), denom).astype(F32)
+    t = ((u[None, :] - cdf_b) / denom).astype(F32)
+    return (bins_b + (t * (bins_a - bins_b)).astype(F32)).astype(F32), inds
+
+
 def sample_pdf_tolerance(bins, weights, u, cdf_ulps: float = 8.0) -> np.ndarray:
     """Per-sample max-abs tolerance for comparing two evaluations of sample_pdf whose CDFs
     differ by a few float32 ulps (different summation order: torch CPU uses a double

@@ -1,0 +1,113 @@
+// Stand-alone hardware probe for the primitives mlp_tc.cu relies on (test infrastructure, not product):
+// one CTA computes D[128,256] = A[128,64] * B[256,64]^T with tcgen05.mma from hand-swizzled shared-memory
+// operands (A: SWIZZLE_128B, B: two 32-K SWIZZLE_64B chunks), reads D back with tcgen05.ld and the host
+// compares with an exact integer reference.  Several layout hypotheses are tried so that one GPU run
+// tells which encoding the hardware implements.  Build: nvcc -gencode arch=compute_100a,code=sm_100a
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../msra_practice_project_b200/csrc/umma.cuh"
+
+using namespace b2r::umma;
+
+struct Variant { uint32_t a_layout, a_sbo, b_layout, b_sbo, use_bulk; };
+
+__global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* a_img, const uint8_t* b_img, Variant v, float* d_out) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* gen = raw + (base - smem_u32(raw));
+    const uint32_t a_s = base, b_s = base + 16384, bar = base + 16384 + 32768, slot = bar + 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(slot, 256);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    uint32_t tmem; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+    // A by plain stores, B by plain stores or by the bulk-copy engine
+    for (int i = threadIdx.x; i < 16384 / 16; i += 128) reinterpret_cast<uint4*>(gen)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+    if (!v.use_bulk) {
+        for (int i = threadIdx.x; i < 32768 / 16; i += 128) reinterpret_cast<uint4*>(gen + 16384)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+    } else if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar + 8, 32768);
+        bulk_g2s(b_s, b_img, 16384, bar + 8);
+        bulk_g2s(b_s + 16384, b_img + 16384, 16384, bar + 8);
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (v.use_bulk) mbar_wait(bar + 8, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(128, 256);
+        for (int c = 0; c < 2; ++c)
+            for (int k = 0; k < 2; ++k) {
+                uint64_t ad = make_desc(a_s + c * 64 + k * 32, 16, v.a_sbo, v.a_layout);
+                uint64_t bd = make_desc(b_s + c * 16384 + k * 32, 16, v.b_sbo, v.b_layout);
+                mma_bf16(tmem, ad, bd, idesc, (c | k) != 0);
+            }
+        mma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    for (int j = 0; j < 8; ++j) {
+        uint32_t x[32];
+        tmem_ld32(tmem + ((uint32_t)warp << 21) + j * 32, x);
+        tmem_ld_wait();
+        for (int e = 0; e < 32; ++e) d_out[r * 256 + j * 32 + e] = __uint_as_float(x[e]);
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static uint16_t bf16_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); }   // exact for small ints
+
+int main() {
+    const int M = 128, N = 256, K = 64;
+    std::vector<float> A(M * K), B(N * K), D(M * N);
+    srand(1);
+    for (auto& x : A) x = (float)(rand() % 7 - 3);
+    for (auto& x : B) x = (float)(rand() % 5 - 2);
+    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < K; ++k) s += A[m * K + k] * B[n * K + k]; D[m * N + n] = s; }
+    std::vector<uint8_t> a_img(16384), b_img[2] = {std::vector<uint8_t>(32768), std::vector<uint8_t>(32768)};
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) {
+        uint16_t h = bf16_bits(A[m * K + k]);
+        memcpy(&a_img[sw128_offset(m, k / 8) + (k % 8) * 2], &h, 2);
+    }
+    for (int var = 0; var < 2; ++var)
+        for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) {
+            uint16_t h = bf16_bits(B[n * K + k]);
+            int c = k / 32, kk = k % 32;
+            uint32_t off = var == 0 ? sw64_offset(n, kk / 8)
+                                    : (uint32_t)((n >> 3) * 512 + (n & 7) * 64 + (((kk / 8) ^ (n & 3)) << 4));
+            memcpy(&b_img[var][c * 16384 + off + (kk % 8) * 2], &h, 2);
+        }
+    uint8_t *da, *db; float* dd;
+    cudaMalloc(&da, 16384); cudaMalloc(&db, 32768); cudaMalloc(&dd, M * N * 4);
+    cudaMemcpy(da, a_img.data(), 16384, cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    struct { const char* name; int bvar; Variant v; } cases[] = {
+        {"A=SW128/sbo1024 B=SW64(r>>1)/sbo512 plain-store", 0, {2, 1024, 4, 512, 0}},
+        {"A=SW128/sbo1024 B=SW64(r>>1)/sbo512 bulk-copy  ", 0, {2, 1024, 4, 512, 1}},
+        {"A=SW128/sbo1024 B=SW64(r&3)/sbo512 plain-store ", 1, {2, 1024, 4, 512, 0}},
+    };
+    int ok_any = 0;
+    for (auto& cs : cases) {
+        cudaMemcpy(db, b_img[cs.bvar].data(), 32768, cudaMemcpyHostToDevice);
+        cudaMemset(dd, 0xff, M * N * 4);
+        probe_kernel<<<1, 128, 64 * 1024>>>(da, db, cs.v, dd);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("PROBE %s : CUDA error %s\n", cs.name, cudaGetErrorString(e)); return 2; }
+        std::vector<float> got(M * N);
+        cudaMemcpy(got.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
+        int bad = 0, first = -1;
+        for (int i = 0; i < M * N; ++i) if (got[i] != D[i]) { if (first < 0) first = i; ++bad; }
+        printf("PROBE %s : mismatches %d / %d", cs.name, bad, M * N);
+        if (bad) printf("  first at (m=%d,n=%d) got %g want %g", first / N, first % N, got[first], D[first]);
+        printf("\n");
+        if (!bad) ok_any = 1;
+    }
+    printf(ok_any ? "PROBE OK\n" : "PROBE FAILED\n");
+    return 0;
+}
