@@ -61,11 +61,15 @@ def raw_to_outputs(raw, z_vals, rays_d):
 
 
 def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num, *,
-                t_rand=None, z_lin=None, u=None, precision=None, stages=None, coarse_no_grad=False):
+                t_rand=None, z_lin=None, u=None, precision=None, stages=None, coarse_no_grad=False,
+                exact_last_sample=False):
     """nerf/render.py:106-147 -- coarse pass, sample_pdf on the un-jittered mids with
     weights[:,1:-1], sort-merge, fine pass on all Sc+Sf samples.  Returns the reference's 6-tuple
     (rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f).  ``coarse_no_grad`` runs the coarse pass in
-    inference mode (used by the pi-GAN wrappers, whose loss never touches the coarse outputs)."""
+    inference mode (used by the pi-GAN wrappers, whose loss never touches the coarse outputs).
+    ``exact_last_sample`` re-evaluates the LAST sample of every ray with the fp32 MLP when the bf16
+    tensor-core path is in use: its interval is 1e10 (nerf/render.py:92), so alpha_last is a step
+    function of sign(sigma_last) and a bf16 rounding flips ~0.2 % of rays."""
     if not isinstance(rays, torch.Tensor):
         rays = torch.as_tensor(np.asarray(rays), dtype=torch.float32)
     if not rays.is_cuda:
@@ -85,7 +89,7 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
 
     z_vals, mids = ops.stratified_z(z_lin, t_rand)
     with torch.set_grad_enabled(torch.is_grad_enabled() and not coarse_no_grad):
-        raw = ops.mlp(coarse_model, rays=rays, z=z_vals, precision=precision).view(n, sc, 4)
+        raw = _mlp_rays(coarse_model, rays, z_vals, precision, exact_last_sample)
         rgb_c, depth_c, acc_c, weights = ops.composite(raw, z_vals, rays_d, want_weights=True)
 
     if u is None:
@@ -93,12 +97,23 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     res = ops.sample_pdf(mids, weights[:, 1:-1], sf, u=torch.as_tensor(u, dtype=torch.float32).to(dev), z_coarse=z_vals,
                          want_samples=stages is not None)
     z_fine = res["sorted"]
-    raw_f = ops.mlp(fine_model, rays=rays, z=z_fine, precision=precision).view(n, sc + sf, 4)
+    raw_f = _mlp_rays(fine_model, rays, z_fine, precision, exact_last_sample)
     rgb_f, depth_f, acc_f, w_f = ops.composite(raw_f, z_fine, rays_d, want_weights=stages is not None)
     if stages is not None:
         stages.update(z_coarse=z_vals, mids=mids, raw_coarse=raw, weights_coarse=weights, z_samples=res["samples"],
                       z_fine=z_fine, raw_fine=raw_f, weights_fine=w_f)
     return rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f
+
+
+def _mlp_rays(model, rays, z, precision, exact_last_sample):
+    """run_network on (rays, z) -> raw[N,S,4]; optionally the last sample of each ray in fp32."""
+    n, s = z.shape
+    raw = ops.mlp(model, rays=rays, z=z, precision=precision).view(n, s, 4)
+    used = precision or ops.get_mlp_precision()
+    if exact_last_sample and used == "bf16" and not raw.requires_grad:
+        last = ops.mlp(model, rays=rays, z=z[:, -1:].contiguous(), precision="fp32")
+        raw[:, -1, :] = last
+    return raw
 
 
 def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
@@ -110,7 +125,7 @@ def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
 
 def render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                         fine_sample_num, chunk=REFERENCE_RAY_CHUNK, *, ray_begin=0, ray_count=None, t_rand=None,
-                        precision=None, launch_rays=1 << 20, coarse_no_grad=False):
+                        precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=False):
     """Device-resident core of render_image: renders flattened pixel rows [ray_begin, +ray_count)
     and returns the six per-ray outputs of the fine AND coarse pass as CUDA tensors.  Rays are
     generated on the device (K1); ``launch_rays`` bounds the rays per kernel launch sequence."""
@@ -127,18 +142,20 @@ def render_image_device(width, height, focal, pose, near, far, coarse_model, fin
         cnt = min(launch_rays, ray_count - b)
         rays = ops.raygen(width, height, focal, pose, ray_begin + b, cnt, device=dev)
         outs.append(render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                                t_rand=t_rand[b:b + cnt], precision=precision, coarse_no_grad=coarse_no_grad))
+                                t_rand=t_rand[b:b + cnt], precision=precision, coarse_no_grad=coarse_no_grad,
+                                exact_last_sample=exact_last_sample))
     if len(outs) == 1:
         return outs[0]
     return tuple(torch.cat([o[i] for o in outs]) for i in range(6))
 
 
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                 chunk=1024 * 16, *, t_rand=None, precision=None):
+                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=False):
     """nerf/render.py:150-167 -- numpy (H,W,3), (H,W,1), (H,W,1) = fine rgb / depth / acc."""
     with torch.no_grad():
         out = render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
-                                  fine_sample_num, chunk, t_rand=t_rand, precision=precision)
+                                  fine_sample_num, chunk, t_rand=t_rand, precision=precision,
+                                  exact_last_sample=exact_last_sample)
     h, w = int(height), int(width)
     return (out[3].cpu().numpy().reshape(h, w, 3), out[4].cpu().numpy().reshape(h, w, 1),
             out[5].cpu().numpy().reshape(h, w, 1))
