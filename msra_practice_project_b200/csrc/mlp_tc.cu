@@ -3,14 +3,15 @@
 //   run_network + NeRF.forward            nerf/render.py:59-75, nerf/nerf.py:44-49, 75-94
 //   FilmSirenNeRF.forward / create_mesh   pi_GAN/modules.py:22-25, 101-118, pi_GAN/utils.py:59-91
 //
-// Design (one CTA per SM, 384 threads, persistent over 256-row tiles = two 128-row sub-tiles):
-//   warp 0        weight producer: streams pre-swizzled bf16 weight chunks (N x 32 K, SWIZZLE_64B image,
-//                 packed once by b2r_mlp_tc_pack) L2 -> shared memory with cp.async.bulk (TMA engine)
-//                 through a 4-stage mbarrier ring (4 x 16 KB);
-//   warp 1        tcgen05.mma issuer (one elected lane): M=128, N=256|128, K=16 bf16 MMAs, A = the
+// Design (one CTA per SM, 640 threads, persistent over 256-row tiles = two 128-row sub-tiles):
+//   warp 0        weight producer (one thread): streams pre-swizzled bf16 weight chunks (N x 32 K,
+//                 SWIZZLE_64B image, packed once by b2r_mlp_tc_pack) L2 -> shared memory with
+//                 cp.async.bulk (TMA engine) through a 3-stage mbarrier ring (3 x 16 KB);
+//   warp 1        tcgen05.mma issuer (one thread): M=128, N=256|128, K=16 bf16 MMAs, A = the
 //                 sub-tile's activations in shared memory (K-major, SWIZZLE_128B), D = fp32 accumulator
 //                 in tensor memory (2 x 256 columns = the two sub-tiles, ping-pong);
-//   warps 4-7     epilogue of sub-tile 0, warps 8-11 epilogue of sub-tile 1 (thread = row = TMEM lane):
+//   warps 4-11    epilogue of sub-tile 0, warps 12-19 epilogue of sub-tile 1 (thread = row = TMEM lane,
+//                 two warps per lane quadrant, each converting half of the columns):
 //                 tcgen05.ld the accumulator, + bias, ReLU (or sin(s*acc+t) for FiLM-SIREN), round to
 //                 bf16 and write the next layer's A operand back into shared memory IN PLACE -- the
 //                 activations never touch HBM.  The first stage of the same threads generates the
@@ -30,17 +31,14 @@ namespace tc {
 
 using namespace umma;
 
-constexpr int kThreads = 384;
 constexpr int kRowsSub = 128;
 constexpr int kRowsTile = 256;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr uint32_t kStageBytes = 16384;                 // 256 rows x 64 B
 constexpr uint32_t kPeBytes = 16384;                    // 128 rows x 64 bf16 (SW128): pos-enc / dir-enc block
 constexpr uint32_t kHBytes = 65536;                     // 4 K-blocks of 128 rows x 64 bf16
 constexpr uint32_t kSubBytes = kPeBytes + kHBytes;      // 80 KB per sub-tile
 constexpr uint32_t kRingOff = 2 * kSubBytes;
-constexpr uint32_t kBarOff = kRingOff + kStages * kStageBytes;   // 224 KB
-constexpr uint32_t kSmemBytes = kBarOff + 128 + 1024;            // + barriers + alignment slack
 
 // ---- NeRF schedule: 10 MMA steps ------------------------------------------------------------------
 // step 0..7 = layers_pos.0..7, 8 = layers_dir.0, 9 = layers_dir.1.  A chunk is N x 32 K.
@@ -116,6 +114,15 @@ __global__ void nerf_pack_kernel(const float* __restrict__ params, uint8_t* __re
 }
 
 // ---- fused kernel --------------------------------------------------------------------------------------
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr uint32_t kTabOff = kRingOff + kStages * kStageBytes;          // fp32 tables (bias / head weights)
+constexpr uint32_t kTabBytes = kNerfTabFloats * 4;                      // 12,816
+constexpr uint32_t kPartOff = kTabOff + kTabBytes;                      // head partial sums: 2 x 128 x float4
+constexpr uint32_t kPartBytes = 2 * kRowsSub * 16;
+constexpr uint32_t kBarOff = kPartOff + kPartBytes;                     // mbarriers + TMEM slot
+constexpr uint32_t kSmemBytes = kBarOff + 128 + 1024;                   // + alignment slack
+static_assert(kBarOff % 8 == 0 && kSmemBytes <= 232448, "shared-memory budget");
+
 struct Ctx {
     uint32_t smem;        // 1024-aligned shared base (shared-window address)
     uint32_t w_full, w_empty, act_ready, acc_full, tmem_slot;
@@ -132,18 +139,26 @@ __device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
     return c;
 }
 
-// positional encoding of 3 values with L octaves into out[6L]: [sin(2^i x)(3), cos(2^i x)(3)] per octave.
-// Octave 0 uses the accurate sincosf; higher octaves use the double-angle recurrence (abs. error grows
-// ~2x per octave, < 1e-4 at octave 9: far below the bf16 rounding of the operand).
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// Positional encoding of 3 values with L octaves as 3L packed bf16x2 words, in the reference's order
+// [sin(2^i x)(3), cos(2^i x)(3)] per octave (nerf/nerf.py:44-49): 6 values = 3 words per octave.
+// Octave 0 uses the accurate sincosf; higher octaves the double-angle recurrence (abs. error grows ~2x per
+// octave, < 1e-4 at octave 9: far below the bf16 rounding of the operand).
 template <int L>
-__device__ __forceinline__ void posenc_bf16(const float x[3], float* out) {
+__device__ __forceinline__ void posenc_words(const float x[3], uint32_t* w) {
     float s[3], c[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) sincosf(x[k], &s[k], &c[k]);
 #pragma unroll
     for (int i = 0; i < L; ++i) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { out[6 * i + k] = s[k]; out[6 * i + 3 + k] = c[k]; }
+        w[3 * i + 0] = pack_bf16(s[0], s[1]);
+        w[3 * i + 1] = pack_bf16(s[2], c[0]);
+        w[3 * i + 2] = pack_bf16(c[1], c[2]);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             float s2 = 2.0f * s[k] * c[k];
@@ -153,29 +168,30 @@ __device__ __forceinline__ void posenc_bf16(const float x[3], float* out) {
     }
 }
 
-// write `n16` 16-byte chunks (8 bf16 each) of row r of a SW128 K-block
-template <int N16>
-__device__ __forceinline__ void store_row_sw128(uint32_t block_base, int r, int first_chunk, const uint32_t* packed) {
-#pragma unroll
-    for (int q = 0; q < N16; ++q)
-        st_shared_v4(block_base + sw128_offset((uint32_t)r, (uint32_t)(first_chunk + q)),
-                     packed[4 * q + 0], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-}
+constexpr int kCtrlWarps = 4;                       // 0 producer, 1 MMA issuer (+TMEM alloc), 2-3 idle
+constexpr int kEpiWarps = 16;                       // 2 sub-tiles x 2 column halves x 4 TMEM lane quadrants
+constexpr int kThreadsV2 = (kCtrlWarps + kEpiWarps) * 32;   // 640
 
-__global__ void __launch_bounds__(kThreads, 1) nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src,
-                                                              long long rows, float4* __restrict__ raw_out) {
+__global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src,
+                                                                long long rows, float4* __restrict__ raw_out) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
-    const float* __restrict__ tab = reinterpret_cast<const float*>(packed + kNerfChunkBytes);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, 1); mbar_init(cx.w_empty + 8 * i, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, kRowsSub); mbar_init(cx.acc_full + 8 * g, 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 2 * kRowsSub); mbar_init(cx.acc_full + 8 * g, 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(cx.tmem_slot, 512);
+    {   // bias / head-weight tables -> shared memory
+        const float4* tab_g = reinterpret_cast<const float4*>(packed + kNerfChunkBytes);
+        for (int i = threadIdx.x; i < kNerfTabFloats / 4; i += kThreadsV2) {
+            float4 v = __ldg(tab_g + i);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -183,67 +199,81 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_tc_kernel(const uint8_t* __r
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
 
     if (warp == 0) {
-        // ===== weight producer =====
-        uint32_t stage = 0, phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int s = 0; s < kNerfSteps; ++s) {
-                const int nc = nerf_chunks(s);
-                const uint32_t bytes = (uint32_t)nerf_n(s) * 64u;
-                for (int g = 0; g < 2; ++g) {
-                    for (int c = 0; c < nc; ++c) {
-                        if (lane == 0) {
+        if (lane == 0) {
+            // ===== weight producer (one thread) =====
+            uint32_t stage = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint8_t* src_w = packed;
+                for (int s = 0; s < kNerfSteps; ++s) {
+                    const int nc = nerf_chunks(s);
+                    const uint32_t bytes = (uint32_t)nerf_n(s) * 64u;
+                    for (int g = 0; g < 2; ++g) {
+                        for (int c = 0; c < nc; ++c) {
                             mbar_wait(cx.w_empty + 8 * stage, phase ^ 1u);
                             mbar_arrive_expect_tx(cx.w_full + 8 * stage, bytes);
-                            bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, packed + nerf_chunk_off(s, 0) + (long long)c * bytes,
-                                     bytes, cx.w_full + 8 * stage);
+                            bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, src_w + (size_t)c * bytes, bytes, cx.w_full + 8 * stage);
+                            if (++stage == kStages) { stage = 0; phase ^= 1u; }
                         }
-                        __syncwarp();
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
+                    src_w += (size_t)nc * bytes;
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        uint32_t stage = 0, phase = 0, act_phase[2] = {0u, 0u};
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int s = 0; s < kNerfSteps; ++s) {
-                const int nc = nerf_chunks(s);
-                const uint32_t idesc = make_idesc_bf16(128, (uint32_t)nerf_n(s));
-                for (int g = 0; g < 2; ++g) {
-                    if (lane == 0) {
-                        mbar_wait(cx.act_ready + 8 * g, act_phase[g]);
+        if (lane == 0) {
+            // ===== MMA issuer (one thread) =====
+            uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0;
+            const uint64_t a_hi = desc_sw128(0), b_hi = desc_sw64(0);     // descriptors with a zero address field
+            auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, uint32_t accumulate) {
+                mbar_wait(cx.w_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
+                const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+                const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+                mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+                mma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);               // +32 B = next 16 K
+                mma_commit(cx.w_empty + 8 * stage);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            };
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < kNerfSteps; ++s) {
+                    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)nerf_n(s));
+                    const int n_pre = (s == 0 || s == 5) ? 2 : 0;          // chunks reading the pe block first
+                    const int n_h = (s == 0) ? 0 : 8;                      // chunks reading h
+                    const int n_post = (s == 9) ? 1 : 0;                   // dir-enc chunk (pe block) last
+                    for (int g = 0; g < 2; ++g) {
+                        if (g == 0) { mbar_wait(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
+                        else { mbar_wait(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
                         tc_fence_after();
-                    }
-                    __syncwarp();
-                    act_phase[g] ^= 1u;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
-                    const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
-                    for (int c = 0; c < nc; ++c) {
-                        if (lane == 0) {
-                            mbar_wait(cx.w_full + 8 * stage, phase);
-                            tc_fence_after();
-                            const uint32_t a_addr = a_base + nerf_a_off(s, c);
-                            const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
-#pragma unroll
-                            for (int k = 0; k < 2; ++k)
-                                mma_bf16(d_tmem, desc_sw128(a_addr + 32u * k), desc_sw64(b_addr + 32u * k), idesc, (uint32_t)((c | k) != 0));
-                            mma_commit(cx.w_empty + 8 * stage);
-                            if (c == nc - 1) mma_commit(cx.acc_full + 8 * g);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
+                        const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
+                        uint32_t acc = 0;
+                        for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base + (uint32_t)c * 64u, idesc, acc); acc = 1; }
+                        for (int c = 0; c < n_h; ++c) {
+                            issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)(c >> 1) * 16384u + (uint32_t)(c & 1) * 64u, idesc, acc);
+                            acc = 1;
                         }
-                        __syncwarp();
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                        for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u);
+                        mma_commit(cx.acc_full + 8 * g);
                     }
                 }
             }
         }
-    } else if (warp >= 4) {
-        // ===== input generation + epilogue; thread = row of sub-tile g = TMEM lane =====
-        const int g = (warp - 4) >> 2;
-        const int r = ((warp & 3) << 5) | lane;
+    } else if (warp >= kCtrlWarps) {
+        // ===== input generation + epilogue =====
+        // warp = 4 + g*8 + half*4 + quad;  thread = row (quad*32 + lane) of sub-tile g = TMEM lane;
+        // `half` selects which half of the columns of every layer this warp converts.
+        const int ew = warp - kCtrlWarps;
+        const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
+        const int r = (quad << 5) | lane;
         const uint32_t sub = cx.smem + (uint32_t)g * kSubBytes;
         const uint32_t pe_base = sub, h_base = sub + kPeBytes;
-        const uint32_t t_addr = tmem_base + ((uint32_t)(warp & 3) << 21) + (uint32_t)g * 256u;   // lane (warp%4)*32 in bits [16,32)
+        const uint32_t t_addr = tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;   // SW128 row offset
+        const uint32_t xr = (uint32_t)(r & 7);
+        const uint32_t tab = cx.smem + kTabOff;
+        const uint32_t part = cx.smem + kPartOff + (uint32_t)(g * kRowsSub + r) * 16u;
+        const uint32_t bar_id = 1 + g;                      // named barrier of this sub-tile's 8 warps
         uint32_t acc_phase = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long row = tile * kRowsTile + g * kRowsSub + r;
@@ -251,14 +281,22 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_tc_kernel(const uint8_t* __r
             float p[3], vdir[3];
             load_row(src, valid ? row : rows - 1, p, vdir);
             {
-                // positional encoding: 60 values + 4 zero pads -> 64 bf16 = 8 chunks of the pe block
-                float pe[64];
-                posenc_bf16<10>(p, pe);
-                pe[60] = pe[61] = pe[62] = pe[63] = 0.f;
-                uint32_t pk[32];
+                // positional encoding: 60 values + 4 zero pads = 32 words = 8 chunks; this half writes 4 of them
+                uint32_t pw[32];
+                posenc_words<10>(p, pw);
+                pw[30] = 0u; pw[31] = 0u;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) pk[i] = pack_bf16(pe[2 * i], pe[2 * i + 1]);
-                store_row_sw128<8>(pe_base, r, 0, pk);
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t cidx = (uint32_t)(half * 4 + q);
+                    const int wq = (half * 4 + q) * 4;
+                    // half is warp-uniform: select with a predicated copy to keep pw[] in registers
+                    uint32_t a0 = half ? pw[16 + 4 * q + 0] : pw[4 * q + 0];
+                    uint32_t a1 = half ? pw[16 + 4 * q + 1] : pw[4 * q + 1];
+                    uint32_t a2 = half ? pw[16 + 4 * q + 2] : pw[4 * q + 2];
+                    uint32_t a3 = half ? pw[16 + 4 * q + 3] : pw[4 * q + 3];
+                    (void)wq;
+                    st_shared_v4(pe_base + row_off + ((cidx ^ xr) << 4), a0, a1, a2, a3);
+                }
             }
             fence_proxy_async_smem();
             mbar_arrive(cx.act_ready + 8 * g);
@@ -268,27 +306,31 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_tc_kernel(const uint8_t* __r
                 mbar_wait(cx.acc_full + 8 * g, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                const int nj = nerf_n(s) / 32;
-                const float* __restrict__ bias = tab + kNerfTabBias + s * 256;
-                for (int j = 0; j < nj; ++j) {
+                const int njh = nerf_n(s) / 64;                         // 32-column groups per half: 4 (N=256) or 2 (N=128)
+                const uint32_t bias = tab + (uint32_t)(kNerfTabBias + s * 256) * 4u;
+                for (int jj = 0; jj < njh; ++jj) {
+                    const int j = half * njh + jj;
                     uint32_t v[32];
                     tmem_ld32(t_addr + (uint32_t)j * 32u, v);
-                    tmem_ld_wait();
                     float f[32];
+                    // bias loads (shared-memory broadcast) overlap the TMEM load
+                    float4 b[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) b[q] = lds128(bias + (uint32_t)(j * 32 + q * 4) * 4u);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        float4 b = __ldg(reinterpret_cast<const float4*>(bias + j * 32) + q);
-                        f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b.x;
-                        f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b.y;
-                        f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b.z;
-                        f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b.w;
+                        f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b[q].x;
+                        f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b[q].y;
+                        f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b[q].z;
+                        f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b[q].w;
                     }
                     if (s == 7) {
                         // sigma head on the fp32 activations (output_layer_sigma, nerf/nerf.py:72,88)
-                        const float* __restrict__ ws = tab + kNerfTabWSigma + j * 32;
+                        const uint32_t ws = tab + (uint32_t)(kNerfTabWSigma + j * 32) * 4u;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            float4 w = __ldg(reinterpret_cast<const float4*>(ws) + q);
+                            float4 w = lds128(ws + 16u * q);
                             sigma = fmaf(fmaxf(f[4 * q + 0], 0.f), w.x, sigma);
                             sigma = fmaf(fmaxf(f[4 * q + 1], 0.f), w.y, sigma);
                             sigma = fmaf(fmaxf(f[4 * q + 2], 0.f), w.z, sigma);
@@ -297,37 +339,49 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_tc_kernel(const uint8_t* __r
                     }
                     if (s == 9) {
                         // rgb head (output_layer_rgb: 128 -> 3) on the fp32 relu activations
+                        const uint32_t wr = tab + (uint32_t)(kNerfTabWRgb + j * 32) * 4u;
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            float h = fmaxf(f[e], 0.f);
-                            int k = j * 32 + e;
-                            rgb0 = fmaf(h, __ldg(tab + kNerfTabWRgb + k), rgb0);
-                            rgb1 = fmaf(h, __ldg(tab + kNerfTabWRgb + 128 + k), rgb1);
-                            rgb2 = fmaf(h, __ldg(tab + kNerfTabWRgb + 256 + k), rgb2);
+                        for (int q = 0; q < 8; ++q) {
+                            float4 w0 = lds128(wr + 16u * q), w1 = lds128(wr + 512u + 16u * q), w2 = lds128(wr + 1024u + 16u * q);
+                            float h0 = fmaxf(f[4 * q + 0], 0.f), h1 = fmaxf(f[4 * q + 1], 0.f);
+                            float h2 = fmaxf(f[4 * q + 2], 0.f), h3 = fmaxf(f[4 * q + 3], 0.f);
+                            rgb0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, rgb0))));
+                            rgb1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, rgb1))));
+                            rgb2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, rgb2))));
                         }
                     } else {
-                        uint32_t pk[16];
-                        if (s == 8) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(f[2 * i], f[2 * i + 1]);        // layers_dir.0 is linear
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16_relu(f[2 * i], f[2 * i + 1]);
-                        }
                         // columns j*32 .. j*32+31 of this layer = K of the next: K-block j/2, chunks (j&1)*4 .. +3
-                        store_row_sw128<4>(h_base + (uint32_t)(j >> 1) * 16384u, r, (j & 1) * 4, pk);
+                        const uint32_t blk = h_base + (uint32_t)(j >> 1) * 16384u + row_off;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t w0, w1, w2, w3;
+                            if (s == 8) {                                  // layers_dir.0 is linear
+                                w0 = pack_bf16(f[8 * q + 0], f[8 * q + 1]); w1 = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+                                w2 = pack_bf16(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+                            } else {
+                                w0 = pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]); w1 = pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]);
+                                w2 = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
+                            }
+                            const uint32_t cidx = (uint32_t)((j & 1) * 4 + q);
+                            st_shared_v4(blk + ((cidx ^ xr) << 4), w0, w1, w2, w3);
+                        }
                     }
                 }
                 if (s == 8) {
-                    // view-direction encoding for layers_dir.1: 24 values + 8 zero pads -> chunks 0..3 of the pe block
-                    float de[32];
-                    posenc_bf16<4>(vdir, de);
+                    // view-direction encoding for layers_dir.1: 24 values + 8 zero pads = 16 words = chunks 0..3 of the
+                    // pe block; each half writes two chunks
+                    uint32_t dw[16];
+                    posenc_words<4>(vdir, dw);
+                    dw[12] = dw[13] = dw[14] = dw[15] = 0u;
 #pragma unroll
-                    for (int i = 24; i < 32; ++i) de[i] = 0.f;
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16(de[2 * i], de[2 * i + 1]);
-                    store_row_sw128<4>(pe_base, r, 0, pk);
+                    for (int q = 0; q < 2; ++q) {
+                        const uint32_t cidx = (uint32_t)(half * 2 + q);
+                        uint32_t a0 = half ? dw[8 + 4 * q + 0] : dw[4 * q + 0];
+                        uint32_t a1 = half ? dw[8 + 4 * q + 1] : dw[4 * q + 1];
+                        uint32_t a2 = half ? dw[8 + 4 * q + 2] : dw[4 * q + 2];
+                        uint32_t a3 = half ? dw[8 + 4 * q + 3] : dw[4 * q + 3];
+                        st_shared_v4(pe_base + row_off + ((cidx ^ xr) << 4), a0, a1, a2, a3);
+                    }
                 }
                 tc_fence_before();
                 if (s < kNerfSteps - 1) {
@@ -335,16 +389,23 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_tc_kernel(const uint8_t* __r
                     mbar_arrive(cx.act_ready + 8 * g);
                 }
             }
-            if (valid) {
-                float bs = __ldg(tab + kNerfTabBHead);
-                float b0 = __ldg(tab + kNerfTabBHead + 1), b1 = __ldg(tab + kNerfTabBHead + 2), b2 = __ldg(tab + kNerfTabBHead + 3);
-                float4 o;
-                o.x = 1.0f / (1.0f + __expf(-(rgb0 + b0)));
-                o.y = 1.0f / (1.0f + __expf(-(rgb1 + b1)));
-                o.z = 1.0f / (1.0f + __expf(-(rgb2 + b2)));
-                o.w = fmaxf(sigma + bs, 0.f);
-                raw_out[row] = o;
+            // combine the two halves' head partial sums and write raw[row] = (sigmoid rgb, relu sigma)
+            if (half == 1)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part), "f"(rgb0), "f"(rgb1), "f"(rgb2), "f"(sigma) : "memory");
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+            if (half == 0) {
+                float4 o2 = lds128(part);
+                if (valid) {
+                    float4 bh = lds128(tab + (uint32_t)kNerfTabBHead * 4u);      // (b_sigma, b_rgb[3])
+                    float4 o;
+                    o.x = 1.0f / (1.0f + __expf(-(rgb0 + o2.x + bh.y)));
+                    o.y = 1.0f / (1.0f + __expf(-(rgb1 + o2.y + bh.z)));
+                    o.z = 1.0f / (1.0f + __expf(-(rgb2 + o2.z + bh.w)));
+                    o.w = fmaxf(sigma + o2.w + bh.x, 0.f);
+                    raw_out[row] = o;
+                }
             }
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");         // partial slot reusable
         }
     }
     tc_fence_before();
@@ -395,7 +456,7 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, const b2r_mlp_
     if (rc) return rc;
     long long n_tiles = (rows + tc::kRowsTile - 1) / tc::kRowsTile;
     unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-    tc::nerf_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
+    tc::nerf_tc_kernel<<<grid, tc::kThreadsV2, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
                                                                                   (float4*)raw_out);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
     return 0;
