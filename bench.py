@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--coarse", type=int, default=64)
     ap.add_argument("--fine", type=int, default=128)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -57,35 +57,34 @@ def peaks():
 
 # ---- CPU arm: the numpy oracle (port of the reference algorithm) on the host cores -----------------------
 def cpu_baseline(args, n_rays: int, repeats: int = 1):
-    """Times oracle.render_rays on a bounded sample of the same workload (same seeds, sample counts,
-    camera); rays are independent, so rays/s extrapolates linearly to the frame."""
+    """Times the ATen port of the reference path (oracle/torch_port.py: the same torch CPU ops the
+    reference calls, MKL on every host thread) on a bounded sample of the same workload (same weights,
+    sample counts, camera, a contiguous block of the frame's rays); rays are independent, so rays/s
+    extrapolates linearly to the frame."""
     import torch
-    from oracle import render_oracle as orc
+    from oracle import render_oracle as orc, torch_port as tp
     from msra_practice_project_b200 import models, pigan_render
-    try:
-        from threadpoolctl import threadpool_info
-        threads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
-    except Exception:
-        threads = os.cpu_count() or 1
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     torch.manual_seed(0)
     c, f = models.NeRF(), models.NeRF()
-    pc, pf = orc.state_dict_to_numpy(c.state_dict()), orc.state_dict_to_numpy(f.state_dict())
+    sc_, sf_ = dict(c.state_dict()), dict(f.state_dict())
     pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
     rays = orc.image_rays(args.width, args.height, args.width * 1.3875, pose)
     mid = (args.height // 2) * args.width
-    rays = rays[mid:mid + n_rays]
-    rng = np.random.default_rng(5)
+    rays = torch.from_numpy(np.ascontiguousarray(rays[mid:mid + n_rays]))
     best = None
-    for _ in range(repeats):
-        t_rand = rng.random((rays.shape[0], args.coarse), dtype=np.float32)
-        t0 = time.perf_counter()
-        orc.render_rays(rays, 2.0, 6.0, lambda x: orc.nerf_mlp(pc, x), lambda x: orc.nerf_mlp(pf, x), args.coarse,
-                        args.fine, t_rand)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return dict(value=rays.shape[0] / best, unit="rays/s", cores=int(threads), kind="port",
-                sample=f"{rays.shape[0]} rays of the {args.width}x{args.height} frame, {args.coarse}+{args.fine} samples, "
-                       f"fp32 numpy oracle (oracle/render_oracle.py), {best:.2f} s; host has {os.cpu_count()} logical cores"), best
+    torch.manual_seed(5)
+    with torch.no_grad():
+        for _ in range(repeats):
+            t_rand = torch.rand(rays.shape[0], args.coarse)
+            t0 = time.perf_counter()
+            tp.render_rays(rays, 2.0, 6.0, lambda x: tp.nerf_mlp(sc_, x), lambda x: tp.nerf_mlp(sf_, x), args.coarse, args.fine, t_rand)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return dict(value=rays.shape[0] / best, unit="rays/s", cores=int(torch.get_num_threads()), kind="port",
+                sample=f"{rays.shape[0]} rays of the {args.width}x{args.height} frame, {args.coarse}+{args.fine} samples, fp32 "
+                       f"ATen port of the reference path (oracle/torch_port.py), {best:.2f} s; host has {os.cpu_count()} logical cores"), best
 
 
 def run_reference(args):
@@ -238,13 +237,13 @@ def run_b200(args):
             lib = _lib.lib()
             st = torch.cuda.current_stream(dev).cuda_stream
             for _ in range(2):
-                _lib.check(lib.b2r_mlp_tc_fwd(0, packed.data_ptr(), C.byref(inp), raw.data_ptr(), 0, st), "tc")
+                _lib.check(lib.b2r_mlp_tc_fwd(0, packed.data_ptr(), 1, C.byref(inp), raw.data_ptr(), 0, st), "tc")
             torch.cuda.synchronize()
             reps = 5
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
-                _lib.check(lib.b2r_mlp_tc_fwd(0, packed.data_ptr(), C.byref(inp), raw.data_ptr(), 0, st), "tc")
+                _lib.check(lib.b2r_mlp_tc_fwd(0, packed.data_ptr(), 1, C.byref(inp), raw.data_ptr(), 0, st), "tc")
             e1.record()
             torch.cuda.synchronize()
             k_ms = e0.elapsed_time(e1) / reps
@@ -253,6 +252,41 @@ def run_b200(args):
         roof = dict(bound="tensor", kernel="nerf_tc_kernel (fine pass)", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s",
                     frac=achieved / pk["bf16"], frac_of_sustained=achieved / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
                     peak_source=pk["src"], rows_per_launch=rows, ms_per_launch=k_ms, flop_per_row=NERF_FLOP_PER_ROW, traffic=None)
+    # ---- the HBM-bound stages, each timed alone with CUDA events on the launching stream
+    hbm_kernels = []
+    with torch.no_grad():
+        pk = peaks()
+        rays = ops.raygen(W, H, focal, pose, begin, count, device=dev)
+        zc, mids = ops.stratified_z(torch.linspace(2.0, 6.0, sc).to(dev), t_rand)
+        raw_c = torch.rand((count, sc, 4), device=dev)
+        raw_f = torch.rand((count, sc + sf, 4), device=dev)
+        zf = torch.sort(torch.rand((count, sc + sf), device=dev) * 4 + 2, -1).values.contiguous()
+        w_c = torch.rand((count, sc), device=dev)
+        u = torch.linspace(0.0, 1.0, sf).to(dev)
+
+        def time_it(fn, reps=10):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        cases = [
+            ("composite_fwd coarse (weights written)", lambda: ops.composite(raw_c, zc, rays[:, 1], True), count * (sc * 24 + 32)),
+            ("composite_fwd fine (weights skipped)", lambda: ops.composite(raw_f, zf, rays[:, 1], False), count * ((sc + sf) * 20 + 32)),
+            ("sample_pdf + merge", lambda: ops.sample_pdf(mids, w_c[:, 1:-1], sf, u=u, z_coarse=zc, want_samples=False),
+             count * ((sc - 2) * 4 + sc * 4 + (sc + sf) * 4)),
+            ("stratified_z", lambda: ops.stratified_z(torch.linspace(2.0, 6.0, sc).to(dev), t_rand), count * sc * 8),
+            ("raygen", lambda: ops.raygen(W, H, focal, pose, begin, count, device=dev), count * 24),
+        ]
+        for name, fn, nbytes in cases:
+            ms = time_it(fn)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            hbm_kernels.append(dict(kernel=name, bound="hbm", algorithmic_bytes=int(nbytes), ms=ms, achieved=gbs, unit="GB/s",
+                                    peak=pk["hbm"], frac=gbs / pk["hbm"]))
+        del raw_c, raw_f, zf, w_c
     if rank == 0:
         clocks.stop_flag = True
         clocks.join(timeout=2)
@@ -272,7 +306,8 @@ def run_b200(args):
                     samples_per_s=value * (2 * sc + sf),
                     e2e=dict(value=e2e_value, unit="rays/s", h2d_bytes_per_step=96,
                              d2h_bytes_per_step=int(n_rays * 5 * 4), ms_per_step=e2e_ms),
-                    gpu_launches=int(7 * args.steps * world), clocks=clocks.summary(), roofline=roof, cpu_baseline=base)
+                    gpu_launches=int(7 * args.steps * world), clocks=clocks.summary(), roofline=roof, hbm_kernels=hbm_kernels,
+                    cpu_baseline=base)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

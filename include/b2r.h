@@ -131,7 +131,9 @@ int b2r_mlp_f32_bwd(int model_kind, const float* params, const float* film, int 
 size_t b2r_mlp_tc_packed_bytes(int model_kind);
 int b2r_mlp_tc_pack(int model_kind, const float* params, const float* film, int use_dir,
                     void* packed_out, void* stream);
-int b2r_mlp_tc_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out,
+/* use_dir: the FilmSirenNeRF(use_dir=...) flag the weights were packed with (ignored for NeRF).
+ * sigma_only != 0 (FiLM only): stop after the sigma head, raw_out[:, :3] = 0 (create_mesh density query). */
+int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_mlp_input* in, float* raw_out,
                    int sigma_only, void* stream);
 
 #ifdef __cplusplus

@@ -45,7 +45,7 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_size_t, c_float_p, c_float_p, C.c_void_p]),
     "b2r_mlp_tc_packed_bytes": (C.c_size_t, [C.c_int]),
     "b2r_mlp_tc_pack": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "b2r_mlp_tc_fwd": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(MlpInput), c_float_p, C.c_int, C.c_void_p]),
+    "b2r_mlp_tc_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_int, C.c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -168,6 +168,95 @@ __device__ __forceinline__ void posenc_words(const float x[3], uint32_t* w) {
     }
 }
 
+// ---- schedules -------------------------------------------------------------------------------------------
+// A step = one layer's MMAs for one sub-tile: n_pre chunks whose A operand is the aux block (pos-enc),
+// then n_h chunks reading h, then n_post chunks reading the aux block again (dir-enc / view direction).
+struct NerfSched {
+    __device__ static int n_pre(int s, int) { return (s == 0 || s == 5) ? 2 : 0; }
+    __device__ static int n_h(int s, int) { return s == 0 ? 0 : 8; }
+    __device__ static int n_post(int s, int) { return s == 9 ? 1 : 0; }
+    __device__ static int n(int s) { return nerf_n(s); }
+};
+// FiLM-SIREN: steps 0..6 = hidden_layers.0..6, step 7 = hidden_layer_rgb ([h | dir]); flag = use_dir
+struct FilmSched {
+    __device__ static int n_pre(int, int) { return 0; }
+    __device__ static int n_h(int, int) { return 8; }
+    __device__ static int n_post(int s, int use_dir) { return (s == 7 && use_dir) ? 1 : 0; }
+    __device__ static int n(int) { return 256; }
+};
+
+// weight producer: one thread streams the chunk images in schedule order (each step twice: once per sub-tile)
+template <class S>
+__device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __restrict__ packed, long long n_tiles, int n_steps, int flag) {
+    uint32_t stage = 0, phase = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint8_t* src_w = packed;
+        for (int s = 0; s < n_steps; ++s) {
+            const int nc = S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag);
+            const uint32_t bytes = (uint32_t)S::n(s) * 64u;
+            for (int g = 0; g < 2; ++g) {
+                for (int c = 0; c < nc; ++c) {
+                    mbar_wait(cx.w_empty + 8 * stage, phase ^ 1u);
+                    mbar_arrive_expect_tx(cx.w_full + 8 * stage, bytes);
+                    bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, src_w + (size_t)c * bytes, bytes, cx.w_full + 8 * stage);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+            src_w += (size_t)nc * bytes;
+        }
+    }
+}
+
+// MMA issuer: one thread; alternates the two sub-tiles step by step
+template <class S>
+__device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, long long n_tiles, int n_steps, int flag) {
+    uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0;
+    const uint64_t a_hi = desc_sw128(0), b_hi = desc_sw64(0);     // descriptors with a zero address field
+    auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, uint32_t accumulate) {
+        mbar_wait(cx.w_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
+        const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+        const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+        mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+        mma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);               // +32 B = next 16 K
+        mma_commit(cx.w_empty + 8 * stage);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    };
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int s = 0; s < n_steps; ++s) {
+            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)S::n(s));
+            const int n_pre = S::n_pre(s, flag), n_h = S::n_h(s, flag), n_post = S::n_post(s, flag);
+            for (int g = 0; g < 2; ++g) {
+                if (g == 0) { mbar_wait(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
+                else { mbar_wait(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
+                const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
+                uint32_t acc = 0;
+                for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base + (uint32_t)c * 64u, idesc, acc); acc = 1; }
+                for (int c = 0; c < n_h; ++c) {
+                    issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)(c >> 1) * 16384u + (uint32_t)(c & 1) * 64u, idesc, acc);
+                    acc = 1;
+                }
+                for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u);
+                mma_commit(cx.acc_full + 8 * g);
+            }
+        }
+    }
+}
+
+// common prologue: barriers, TMEM allocation; returns the TMEM base address
+__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, 1); mbar_init(cx.w_empty + 8 * i, 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 2 * kRowsSub); mbar_init(cx.acc_full + 8 * g, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(cx.tmem_slot, 512);
+    return 0;
+}
+
 constexpr int kCtrlWarps = 4;                       // 0 producer, 1 MMA issuer (+TMEM alloc), 2-3 idle
 constexpr int kEpiWarps = 16;                       // 2 sub-tiles x 2 column halves x 4 TMEM lane quadrants
 constexpr int kThreadsV2 = (kCtrlWarps + kEpiWarps) * 32;   // 640
@@ -179,12 +268,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, 1); mbar_init(cx.w_empty + 8 * i, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 2 * kRowsSub); mbar_init(cx.acc_full + 8 * g, 1); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(cx.tmem_slot, 512);
+    tc_prologue(cx, warp);
     {   // bias / head-weight tables -> shared memory
         const float4* tab_g = reinterpret_cast<const float4*>(packed + kNerfChunkBytes);
         for (int i = threadIdx.x; i < kNerfTabFloats / 4; i += kThreadsV2) {
@@ -199,66 +283,9 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== weight producer (one thread) =====
-            uint32_t stage = 0, phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const uint8_t* src_w = packed;
-                for (int s = 0; s < kNerfSteps; ++s) {
-                    const int nc = nerf_chunks(s);
-                    const uint32_t bytes = (uint32_t)nerf_n(s) * 64u;
-                    for (int g = 0; g < 2; ++g) {
-                        for (int c = 0; c < nc; ++c) {
-                            mbar_wait(cx.w_empty + 8 * stage, phase ^ 1u);
-                            mbar_arrive_expect_tx(cx.w_full + 8 * stage, bytes);
-                            bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, src_w + (size_t)c * bytes, bytes, cx.w_full + 8 * stage);
-                            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                        }
-                    }
-                    src_w += (size_t)nc * bytes;
-                }
-            }
-        }
+        if (lane == 0) producer_loop<NerfSched>(cx, packed, n_tiles, kNerfSteps, 0);
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer (one thread) =====
-            uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0;
-            const uint64_t a_hi = desc_sw128(0), b_hi = desc_sw64(0);     // descriptors with a zero address field
-            auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, uint32_t accumulate) {
-                mbar_wait(cx.w_full + 8 * stage, phase);
-                tc_fence_after();
-                const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
-                const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
-                const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
-                mma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                mma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);               // +32 B = next 16 K
-                mma_commit(cx.w_empty + 8 * stage);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            };
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int s = 0; s < kNerfSteps; ++s) {
-                    const uint32_t idesc = make_idesc_bf16(128, (uint32_t)nerf_n(s));
-                    const int n_pre = (s == 0 || s == 5) ? 2 : 0;          // chunks reading the pe block first
-                    const int n_h = (s == 0) ? 0 : 8;                      // chunks reading h
-                    const int n_post = (s == 9) ? 1 : 0;                   // dir-enc chunk (pe block) last
-                    for (int g = 0; g < 2; ++g) {
-                        if (g == 0) { mbar_wait(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
-                        else { mbar_wait(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
-                        const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
-                        uint32_t acc = 0;
-                        for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base + (uint32_t)c * 64u, idesc, acc); acc = 1; }
-                        for (int c = 0; c < n_h; ++c) {
-                            issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)(c >> 1) * 16384u + (uint32_t)(c & 1) * 64u, idesc, acc);
-                            acc = 1;
-                        }
-                        for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u);
-                        mma_commit(cx.acc_full + 8 * g);
-                    }
-                }
-            }
-        }
+        if (lane == 0) mma_loop<NerfSched>(cx, tmem_base, n_tiles, kNerfSteps, 0);
     } else if (warp >= kCtrlWarps) {
         // ===== input generation + epilogue =====
         // warp = 4 + g*8 + half*4 + quad;  thread = row (quad*32 + lane) of sub-tile g = TMEM lane;
@@ -413,18 +440,234 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =====================================================================================================
+// FiLM-SIREN (pi_GAN/modules.py:22-25, 70-118): sin(30 (gamma (W x + b) + beta)) layers.
+//   input_layer (3 -> 256) runs on CUDA cores in fp32 inside the input stage (K = 3 is no GEMM and its
+//   30x-amplified argument must not see bf16 inputs); hidden_layers.0..6 and hidden_layer_rgb are tcgen05
+//   steps whose epilogue is sin(scale * acc + shift) with scale = 30 gamma, shift = 30 (gamma b + beta)
+//   folded once per (weights, film) pair by the pack kernel; the sigma head (256 -> 1) rides on the
+//   epilogue of hidden_layers.6 and the rgb head (256 -> 3) on the epilogue of hidden_layer_rgb, both fp32.
+//   sigma_only (create_mesh, pi_GAN/utils.py:82-90) stops after hidden_layers.6: 919,552 FLOP per row.
+// Per row the epilogue issues 2304 MUFU.SIN: at 16 / clk / SM that is as long as the MMAs.
+constexpr int kFilmSteps = 8;
+constexpr long long kFilmChunkBytes = (7 * 8 + 9) * 16384LL;           // 1,064,960 (dir chunk present even if unused)
+// fp32 tables: scale[8][256] | shift[8][256] | w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
+//              w_sigma[256] | w_rgb[3][256] | b_sigma, b_rgb[3]
+constexpr int kFSc = 0, kFSh = 2048, kFW0 = 4096, kFS0 = 4864, kFT0 = 5120, kFWS = 5376, kFWR = 5632, kFBH = 6400, kFilmTabFloats = 6404;
+constexpr long long kFilmPackedBytes = kFilmChunkBytes + kFilmTabFloats * 4;
+
+__global__ void film_pack_kernel(const float* __restrict__ params, const float* __restrict__ film, int use_dir,
+                                 uint8_t* __restrict__ packed) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool ud = use_dir != 0;
+    if (t < kFilmChunkBytes / 16) {
+        long long byte = t * 16;
+        int chunk = (int)(byte / 16384);
+        int rem = (int)(byte % 16384);
+        int row = rem / 64, grp = (rem % 64) / 16;
+        int s = chunk < 56 ? chunk / 8 : 7, c = chunk < 56 ? chunk % 8 : chunk - 56;
+        LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);           // hidden_layers.s | hidden_layer_rgb
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int kk = grp * 8 + e;
+            int col = c < 8 ? c * 32 + kk : ((ud && kk < 3) ? 256 + kk : -1);
+            v[e] = __float2bfloat16_rn(col >= 0 ? params[L.w_off + (long long)row * L.in + col] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(packed + (long long)chunk * 16384 + sw64_offset((uint32_t)row, (uint32_t)grp)) =
+            *reinterpret_cast<const uint4*>(v);
+    }
+    if (t < kFilmTabFloats) {
+        float* tab = reinterpret_cast<float*>(packed + kFilmChunkBytes);
+        int i = (int)t;
+        float val;
+        if (i < kFW0) {                                            // scale / shift of the 8 tensor-core steps
+            int which = i / 2048, s = (i % 2048) / 256, n = i % 256;
+            int fl = s + 1;                                        // film row: 1..7 hidden, 8 rgb layer
+            LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);
+            float gm = film[fl * 512 + n], bt = film[fl * 512 + 256 + n], b = params[L.b_off + n];
+            val = which == 0 ? 30.0f * gm : 30.0f * (gm * b + bt);
+        } else if (i < kFS0) {
+            int k = (i - kFW0) / 256, n = (i - kFW0) % 256;
+            val = params[film_layer(0, ud).w_off + n * 3 + k];
+        } else if (i < kFT0) val = 30.0f * film[i - kFS0];
+        else if (i < kFWS) { int n = i - kFT0; val = 30.0f * (film[n] * params[film_layer(0, ud).b_off + n] + film[256 + n]); }
+        else if (i < kFWR) val = params[film_layer(8, ud).w_off + (i - kFWS)];
+        else if (i < kFBH) val = params[film_layer(10, ud).w_off + (i - kFWR)];
+        else if (i == kFBH) val = params[film_layer(8, ud).b_off];
+        else val = params[film_layer(10, ud).b_off + (i - kFBH - 1)];
+        tab[i] = val;
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsV2, 1) film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows,
+                                                                int use_dir, int sigma_only, float4* __restrict__ raw_out) {
+    extern __shared__ uint8_t smem_raw[];
+    const Ctx cx = make_ctx(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
+    const float* __restrict__ tab = reinterpret_cast<const float*>(packed + kFilmChunkBytes);
+    const int n_steps = sigma_only ? 7 : kFilmSteps;
+
+    tc_prologue(cx, warp);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
+
+    if (warp == 0) {
+        if (lane == 0) producer_loop<FilmSched>(cx, packed, n_tiles, n_steps, use_dir);
+    } else if (warp == 1) {
+        if (lane == 0) mma_loop<FilmSched>(cx, tmem_base, n_tiles, n_steps, use_dir);
+    } else if (warp >= kCtrlWarps) {
+        const int ew = warp - kCtrlWarps;
+        const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
+        const int r = (quad << 5) | lane;
+        const uint32_t sub = cx.smem + (uint32_t)g * kSubBytes;
+        const uint32_t pe_base = sub, h_base = sub + kPeBytes;
+        const uint32_t t_addr = tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const uint32_t xr = (uint32_t)(r & 7);
+        const uint32_t part = cx.smem + kPartOff + (uint32_t)(g * kRowsSub + r) * 16u;
+        const uint32_t bar_id = 1 + g;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long row = tile * kRowsTile + g * kRowsSub + r;
+            const bool valid = row < rows;
+            float p[3], vdir[3];
+            load_row(src, valid ? row : rows - 1, p, vdir);
+            // ---- input_layer on CUDA cores: this half produces columns half*128 .. +127 of h0
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = half * 4 + jj;
+                uint32_t pk[16];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n0 = j * 32 + q * 4;
+                    float4 wx = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + n0));
+                    float4 wy = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 256 + n0));
+                    float4 wz = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 512 + n0));
+                    float4 sc = __ldg(reinterpret_cast<const float4*>(tab + kFS0 + n0));
+                    float4 sh = __ldg(reinterpret_cast<const float4*>(tab + kFT0 + n0));
+                    // W x accumulated in the order of a dot product, then the folded FiLM affine, accurate sinf
+                    float a0 = fmaf(wz.x, p[2], fmaf(wy.x, p[1], wx.x * p[0]));
+                    float a1 = fmaf(wz.y, p[2], fmaf(wy.y, p[1], wx.y * p[0]));
+                    float a2 = fmaf(wz.z, p[2], fmaf(wy.z, p[1], wx.z * p[0]));
+                    float a3 = fmaf(wz.w, p[2], fmaf(wy.w, p[1], wx.w * p[0]));
+                    pk[2 * q + 0] = pack_bf16(sinf(fmaf(a0, sc.x, sh.x)), sinf(fmaf(a1, sc.y, sh.y)));
+                    pk[2 * q + 1] = pack_bf16(sinf(fmaf(a2, sc.z, sh.z)), sinf(fmaf(a3, sc.w, sh.w)));
+                }
+                const uint32_t blk = h_base + (uint32_t)(j >> 1) * 16384u + row_off;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    st_shared_v4(blk + (((uint32_t)((j & 1) * 4 + q) ^ xr) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+            if (half == 0) {
+                // view direction (3 values, zero-padded to 32) -> chunks 0..3 of the aux block (hidden_layer_rgb's extra K)
+                st_shared_v4(pe_base + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 0.f), 0u, 0u);
+#pragma unroll
+                for (uint32_t c = 1; c < 4; ++c) st_shared_v4(pe_base + row_off + ((c ^ xr) << 4), 0u, 0u, 0u, 0u);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(cx.act_ready + 8 * g);
+
+            float sigma = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
+            for (int s = 0; s < n_steps; ++s) {
+                mbar_wait(cx.acc_full + 8 * g, acc_phase);
+                acc_phase ^= 1u;
+                tc_fence_after();
+                const float* __restrict__ scp = tab + kFSc + s * 256;
+                const float* __restrict__ shp = tab + kFSh + s * 256;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = half * 4 + jj;
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + (uint32_t)j * 32u, v);
+                    float4 sc[8], sh[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        sc[q] = __ldg(reinterpret_cast<const float4*>(scp + j * 32) + q);
+                        sh[q] = __ldg(reinterpret_cast<const float4*>(shp + j * 32) + q);
+                    }
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        f[4 * q + 0] = __sinf(fmaf(__uint_as_float(v[4 * q + 0]), sc[q].x, sh[q].x));
+                        f[4 * q + 1] = __sinf(fmaf(__uint_as_float(v[4 * q + 1]), sc[q].y, sh[q].y));
+                        f[4 * q + 2] = __sinf(fmaf(__uint_as_float(v[4 * q + 2]), sc[q].z, sh[q].z));
+                        f[4 * q + 3] = __sinf(fmaf(__uint_as_float(v[4 * q + 3]), sc[q].w, sh[q].w));
+                    }
+                    if (s == 6) {                                   // sigma head on h7 (output_layer_sigma, modules.py:112)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 w = __ldg(reinterpret_cast<const float4*>(tab + kFWS + j * 32) + q);
+                            sigma = fmaf(f[4 * q + 0], w.x, fmaf(f[4 * q + 1], w.y, fmaf(f[4 * q + 2], w.z, fmaf(f[4 * q + 3], w.w, sigma))));
+                        }
+                    }
+                    if (s == 7) {                                   // rgb head (output_layer_rgb: 256 -> 3, modules.py:116)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 w0 = __ldg(reinterpret_cast<const float4*>(tab + kFWR + j * 32) + q);
+                            float4 w1 = __ldg(reinterpret_cast<const float4*>(tab + kFWR + 256 + j * 32) + q);
+                            float4 w2 = __ldg(reinterpret_cast<const float4*>(tab + kFWR + 512 + j * 32) + q);
+                            rgb0 = fmaf(f[4 * q + 0], w0.x, fmaf(f[4 * q + 1], w0.y, fmaf(f[4 * q + 2], w0.z, fmaf(f[4 * q + 3], w0.w, rgb0))));
+                            rgb1 = fmaf(f[4 * q + 0], w1.x, fmaf(f[4 * q + 1], w1.y, fmaf(f[4 * q + 2], w1.z, fmaf(f[4 * q + 3], w1.w, rgb1))));
+                            rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
+                        }
+                    } else {
+                        const uint32_t blk = h_base + (uint32_t)(j >> 1) * 16384u + row_off;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            st_shared_v4(blk + (((uint32_t)((j & 1) * 4 + q) ^ xr) << 4),
+                                         pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
+                                         pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
+                    }
+                }
+                tc_fence_before();
+                if (s < n_steps - 1) {
+                    fence_proxy_async_smem();
+                    mbar_arrive(cx.act_ready + 8 * g);
+                }
+            }
+            if (half == 1)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part), "f"(rgb0), "f"(rgb1), "f"(rgb2), "f"(sigma) : "memory");
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+            if (half == 0) {
+                float4 o2 = lds128(part);
+                if (valid) {
+                    float4 bh = __ldg(reinterpret_cast<const float4*>(tab + kFBH));     // (b_sigma, b_rgb[3])
+                    float4 o;
+                    if (sigma_only) { o.x = o.y = o.z = 0.f; }
+                    else {
+                        o.x = 1.0f / (1.0f + __expf(-(rgb0 + o2.x + bh.y)));
+                        o.y = 1.0f / (1.0f + __expf(-(rgb1 + o2.y + bh.z)));
+                        o.z = 1.0f / (1.0f + __expf(-(rgb2 + o2.z + bh.w)));
+                    }
+                    o.w = fmaxf(sigma + o2.w + bh.x, 0.f);
+                    raw_out[row] = o;
+                }
+            }
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace tc
 }  // namespace b2r
 
 extern "C" size_t b2r_mlp_tc_packed_bytes(int model_kind) {
     if (model_kind == B2R_MODEL_NERF) return (size_t)b2r::tc::kNerfPackedBytes;
+    if (model_kind == B2R_MODEL_FILM) return (size_t)b2r::tc::kFilmPackedBytes;
     return 0;
 }
 
 extern "C" int b2r_mlp_tc_pack(int model_kind, const float* params, const float* film, int use_dir,
                                void* packed_out, void* stream) {
     using namespace b2r;
-    (void)film; (void)use_dir;
     B2R_CHECK_ARG(params && packed_out, "b2r_mlp_tc_pack: NULL pointer");
     B2R_CHECK_ARG(((uintptr_t)packed_out & 15) == 0, "b2r_mlp_tc_pack: packed_out must be 16-byte aligned");
     if (model_kind == B2R_MODEL_NERF) {
@@ -433,10 +676,17 @@ extern "C" int b2r_mlp_tc_pack(int model_kind, const float* params, const float*
         B2R_LAUNCH_CHECK("b2r_mlp_tc_pack");
         return 0;
     }
-    return fail(-2, "b2r_mlp_tc_pack: model kind %d has no tensor-core path in this build", model_kind);
+    if (model_kind == B2R_MODEL_FILM) {
+        B2R_CHECK_ARG(film, "b2r_mlp_tc_pack: FiLM model needs film params");
+        long long threads = tc::kFilmChunkBytes / 16;
+        tc::film_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, film, use_dir, (uint8_t*)packed_out);
+        B2R_LAUNCH_CHECK("b2r_mlp_tc_pack");
+        return 0;
+    }
+    return fail(-2, "b2r_mlp_tc_pack: unknown model kind %d", model_kind);
 }
 
-extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out,
+extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_mlp_input* in, float* raw_out,
                               int sigma_only, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(packed && raw_out, "b2r_mlp_tc_fwd: NULL pointer");
@@ -445,17 +695,25 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, const b2r_mlp_
     if (rc) return rc;
     long long rows = row_count(in);
     if (rows == 0) return 0;
-    if (model_kind != B2R_MODEL_NERF || sigma_only)
-        return fail(-2, "b2r_mlp_tc_fwd: model kind %d (sigma_only=%d) has no tensor-core path in this build", model_kind, sigma_only);
+    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM, "b2r_mlp_tc_fwd: unknown model kind %d", model_kind);
+    B2R_CHECK_ARG(!(sigma_only && model_kind == B2R_MODEL_NERF), "b2r_mlp_tc_fwd: sigma_only is a FiLM-SIREN mode");
     int dev = 0, sms = 0;
     rc = cuda_result(cudaGetDevice(&dev), "cudaGetDevice");
     if (rc) return rc;
     rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
-    if (rc) return rc;
     long long n_tiles = (rows + tc::kRowsTile - 1) / tc::kRowsTile;
     unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    if (model_kind == B2R_MODEL_FILM) {
+        rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+        if (rc) return rc;
+        tc::film_tc_kernel<<<grid, tc::kThreadsV2, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
+                                                                                         use_dir, sigma_only, (float4*)raw_out);
+        B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
+        return 0;
+    }
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+    if (rc) return rc;
     tc::nerf_tc_kernel<<<grid, tc::kThreadsV2, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
                                                                                   (float4*)raw_out);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");

@@ -35,11 +35,20 @@ def gather_image(rgb: torch.Tensor, depth: torch.Tensor, acc: torch.Tensor, out:
     if world == 1:
         out[: mine.shape[0]].copy_(mine)
         return out
-    views = []
+    counts = [shard_range(n_rays, r, world)[1] for r in range(world)]
+    if min(counts) == max(counts):
+        # equal blocks: the collective writes every rank's rows straight into the final buffer
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return out
+    # ragged blocks: pad to the largest, gather, unpack
+    cmax = max(counts)
+    padded = mine.new_zeros((cmax, 5))
+    padded[: mine.shape[0]] = mine
+    stage = mine.new_empty((world * cmax, 5))
+    dist.all_gather_into_tensor(stage, padded, group=group)
     for r in range(world):
         b, c = shard_range(n_rays, r, world)
-        views.append(out[b:b + c])
-    dist.all_gather(views, mine, group=group)
+        out[b:b + c] = stage[r * cmax:r * cmax + c]
     return out
 
 

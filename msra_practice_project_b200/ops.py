@@ -179,9 +179,9 @@ def _packed_weights(model, kind: int, flat: torch.Tensor, film: torch.Tensor | N
     invalidated when any parameter (or the FiLM tensor) changes in place or is replaced."""
     ps = models.param_list(model, kind)
     key = tuple((p.data_ptr(), p._version) for p in ps)
-    if film is not None:
-        key += ((film.data_ptr(), film._version),)
-    hit = _pack_cache.get(model)
+    # FiLM tensors are rebuilt per latent (set_film_params) and may reuse a freed address, so a pointer /
+    # version key cannot prove they are unchanged: FiLM models are re-packed on every call (~10 us).
+    hit = _pack_cache.get(model) if film is None else None
     if hit is not None and hit[0] == key:
         return hit[1]
     nbytes = lib().b2r_mlp_tc_packed_bytes(kind)
@@ -190,7 +190,8 @@ def _packed_weights(model, kind: int, flat: torch.Tensor, film: torch.Tensor | N
     packed = torch.empty((nbytes,), dtype=torch.uint8, device=flat.device)
     with torch.cuda.device(flat.device):
         check(lib().b2r_mlp_tc_pack(kind, ptr(flat), ptr(film), int(use_dir), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack")
-    _pack_cache[model] = (key, packed)
+    if film is None:
+        _pack_cache[model] = (key, packed)
     return packed
 
 
@@ -290,7 +291,8 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
     with torch.cuda.device(dev):
         if precision == "bf16":
             packed = _packed_weights(net, kind, flat, film, use_dir)
-            check(lib().b2r_mlp_tc_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), int(sigma_only), _stream(flat)), "b2r_mlp_tc_fwd")
+            check(lib().b2r_mlp_tc_fwd(kind, ptr(packed), int(use_dir), C.byref(inp), ptr(raw), int(sigma_only), _stream(flat)),
+                  "b2r_mlp_tc_fwd")
         else:
             ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, rows, 0)
             ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=dev)

@@ -47,17 +47,18 @@ def render_image(width, height, focal, pose, near, far, coarse_model, fine_model
 
 
 def _render(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk, t_rand, precision,
-            coarse_no_grad=False):
+            coarse_no_grad=False, exact_last_sample=False):
     return render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk,
-                               t_rand=t_rand, precision=precision, coarse_no_grad=coarse_no_grad)
+                               t_rand=t_rand, precision=precision, coarse_no_grad=coarse_no_grad,
+                               exact_last_sample=exact_last_sample)
 
 
 def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
-                    fine_sample_num, chunk=1024 * 16, *, t_rand=None, precision=None):
+                    fine_sample_num, chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=False):
     """pi_GAN/render.py:209-226 -- numpy (H,W,3), (H,W,1), (H,W,1)."""
     with torch.no_grad():
         out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                      chunk, t_rand, precision)
+                      chunk, t_rand, precision, exact_last_sample=exact_last_sample)
     h, w = int(height), int(width)
     return (out[3].cpu().numpy().reshape(h, w, 3), out[4].cpu().numpy().reshape(h, w, 1),
             out[5].cpu().numpy().reshape(h, w, 1))
@@ -99,6 +100,6 @@ def density_grid(model, N=256, max_batch=64 ** 3, *, begin=0, count=None, precis
     with torch.no_grad():
         for b in range(begin, begin + count, max_batch):
             c = min(max_batch, begin + count - b)
-            raw = ops.mlp(model, grid=(N, b, c), precision=precision)
+            raw = ops.mlp(model, grid=(N, b, c), precision=precision, sigma_only=True)
             out.append(-raw[:, 3])
     return out[0] if len(out) == 1 else torch.cat(out)

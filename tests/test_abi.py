@@ -44,7 +44,7 @@ def test_bad_arguments_return_negative_and_set_message():
     rc = lib.b2r_sample_pdf(None, 0, None, 0, None, 1, 4, 4, None, 0, None, None, None, None)
     assert rc < 0
     inp = _lib.MlpInput()
-    rc = lib.b2r_mlp_tc_fwd(0, 16, C.byref(inp), 16, 0, None)
+    rc = lib.b2r_mlp_tc_fwd(0, 16, 1, C.byref(inp), 16, 0, None)
     assert rc < 0 and b"exactly one" in lib.b2r_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "b2r_mlp_tc_fwd")

@@ -285,6 +285,49 @@ def test_mlp_tc_ragged_rows_vs_fp32(rows):
     assert bool(torch.all(err[:, 3] < 4e-2 * torch.clamp(b[:, 3], min=1.0)))
 
 
+def test_mlp_tc_film_vs_reference(golden):
+    """FiLM-SIREN on the tensor-core path: points mode, sigma-only grid mode, use_dir=False, film update."""
+    k, p = golden.kernels, golden.pigan
+    m = seeded_film()
+    m.set_film_params(cu(k["film_params"]))
+    with torch.no_grad():
+        out = ops.mlp(m, x=cu(k["film_x"]), precision="bf16").cpu().numpy()
+    ref = k["film_seed0_out"]
+    err = np.abs(out - ref)
+    print("bf16 FiLM-SIREN max-abs rgb %.4g sigma %.4g (sigma max %.3g)" % (err[:, :3].max(), err[:, 3].max(), ref[:, 3].max()))
+    assert err[:, :3].max() < 2e-2 and np.all(err[:, 3] < 4e-2 * np.maximum(1.0, ref[:, 3]))
+    m.set_film_params(cu(p["film"]))                      # new FiLM tensor -> packed tables must be rebuilt
+    n = int(p["grid_N"])
+    neg = pigan_render.density_grid(m, n, max_batch=100, precision="bf16").cpu().numpy()
+    assert np.all(np.abs(neg - p["grid_neg_sigma"]) < 4e-2 * np.maximum(1.0, -p["grid_neg_sigma"]))
+    m2 = seeded_film(use_dir=False)
+    m2.set_film_params(cu(k["film_params"]))
+    g = torch.Generator().manual_seed(3)
+    x = torch.cat([torch.rand(700, 3, generator=g) * 0.6 - 0.3, torch.nn.functional.normalize(torch.randn(700, 3, generator=g), dim=-1)], -1).cuda()
+    with torch.no_grad():
+        a = ops.mlp(m2, x=x, precision="bf16")
+        b = ops.mlp(m2, x=x, precision="fp32")
+    e = (a - b).abs()
+    assert e[:, :3].max().item() < 2e-2 and bool(torch.all(e[:, 3] < 4e-2 * torch.clamp(b[:, 3], min=1.0)))
+
+
+def test_pigan_render_bf16_vs_fp32(golden):
+    p = golden.pigan
+    m = seeded_film()
+    m.set_film_params(cu(p["film"]))
+    w = 32
+    focal = np.float64(w / 2 / np.tan(6 * np.pi / 180))
+    torch.manual_seed(3)
+    t = torch.rand(w * w, 24, device="cuda")
+    a = pigan_render.render_image_np(w, w, focal, p["pose"], 0.5, 1.5, m, m, 24, 24, t_rand=t, precision="fp32")
+    b = pigan_render.render_image_np(w, w, focal, p["pose"], 0.5, 1.5, m, m, 24, 24, t_rand=t, precision="bf16",
+                                     exact_last_sample=True)
+    err = np.abs(a[0] - b[0]).max(axis=-1)
+    print("pi-GAN 32x32 24+24 bf16 vs fp32: max-abs rgb %.4g, rays > 2e-2: %d / %d, PSNR %.1f dB"
+          % (err.max(), (err > 2e-2).sum(), w * w, orc.psnr(a[0], b[0])))
+    assert (err > 2e-2).sum() <= 0.01 * w * w and orc.psnr(a[0], b[0]) > 35
+
+
 def test_tc_pack_cache_invalidation():
     c, _ = seeded_nerf()
     x = torch.rand(300, 6, device="cuda")

@@ -131,3 +131,16 @@ def test_density_grid(golden):
     fm = models.FilmSirenNeRF()
     out = orc.density_query(orc.state_dict_to_numpy(fm.state_dict()), p["film"], n)
     np.testing.assert_allclose(out, p["grid_neg_sigma"], atol=2e-4, rtol=0)
+
+
+def test_torch_port_matches_reference_goldens(golden):
+    """oracle/torch_port.py (the CPU-baseline port timed by bench.py) reproduces the reference's outputs."""
+    from oracle import torch_port as tp
+    s = golden.nerf_stages
+    c, f = seeded_nerf()
+    sc_, sf_ = dict(c.state_dict()), dict(f.state_dict())
+    with torch.no_grad():
+        out = tp.render_rays(torch.from_numpy(s["rays"]), 2.0, 6.0, lambda x: tp.nerf_mlp(sc_, x), lambda x: tp.nerf_mlp(sf_, x),
+                             64, 64, torch.from_numpy(s["t_rand"]))
+    for got, name in zip(out, ["rgb_c", "depth_c", "acc_c", "rgb_f", "depth_f", "acc_f"]):
+        np.testing.assert_allclose(got.numpy(), s[name], atol=1e-6, rtol=0, err_msg=name)
