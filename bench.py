@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NERF_FLOP_PER_ROW = 1182976          # unpadded algorithmic FLOP per MLP evaluation
+TC_DRAM_BYTES_PER_ROW = 15.8         # profiles/r1_nerf_tc_ncu.txt: (53.6 MB read + 145.0 MB written) / 12,582,912 rows
 METRIC = "rays/s, NeRF 800x800 render, 64 coarse + 128 fine samples/ray"
 
 
@@ -251,7 +252,10 @@ def run_b200(args):
         achieved = rows * NERF_FLOP_PER_ROW / (k_ms * 1e-3) / 1e12
         roof = dict(bound="tensor", kernel="nerf_tc_kernel (fine pass)", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s",
                     frac=achieved / pk["bf16"], frac_of_sustained=achieved / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
-                    peak_source=pk["src"], rows_per_launch=rows, ms_per_launch=k_ms, flop_per_row=NERF_FLOP_PER_ROW, traffic=None)
+                    peak_source=pk["src"], rows_per_launch=rows, ms_per_launch=k_ms, flop_per_row=NERF_FLOP_PER_ROW,
+                    traffic=int(rows * TC_DRAM_BYTES_PER_ROW),
+                    traffic_source="dram__bytes_read+write per row of the ncu --set full capture in profiles/ (fine-pass launch), "
+                                   "scaled to this launch's rows; algorithmic = 16 B/row written")
     # ---- the HBM-bound stages, each timed alone with CUDA events on the launching stream
     hbm_kernels = []
     with torch.no_grad():
