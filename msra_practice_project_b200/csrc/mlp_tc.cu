@@ -3,13 +3,18 @@
 //   run_network + NeRF.forward            nerf/render.py:59-75, nerf/nerf.py:44-49, 75-94
 //   FilmSirenNeRF.forward / create_mesh   pi_GAN/modules.py:22-25, 101-118, pi_GAN/utils.py:59-91
 //
-// Design (one CTA per SM, 640 threads, persistent over 256-row tiles = two 128-row sub-tiles):
-//   warp 0        weight producer (one thread): streams pre-swizzled bf16 weight chunks (N x 32 K,
-//                 SWIZZLE_64B image, packed once by b2r_mlp_tc_pack) L2 -> shared memory with
-//                 cp.async.bulk (TMA engine) through a 3-stage mbarrier ring (3 x 16 KB);
-//   warp 1        tcgen05.mma issuer (one thread): M=128, N=256|128, K=16 bf16 MMAs, A = the
-//                 sub-tile's activations in shared memory (K-major, SWIZZLE_128B), D = fp32 accumulator
-//                 in tensor memory (2 x 256 columns = the two sub-tiles, ping-pong);
+// Design: CTA PAIRS (cluster of 2, tcgen05 cta_group::2), one CTA per SM, 640 threads, persistent.
+// Each CTA owns a 256-row tile = two 128-row sub-tiles; one MMA instruction covers sub-tile g of BOTH
+// CTAs (M = 256) and every CTA stages only ITS HALF of the weight rows (N/2), so the L2 -> shared-memory
+// weight stream and the shared-memory -> tensor-core B traffic per SM are half of a single-CTA design.
+//   warp 0        weight producer (one thread per CTA): streams this CTA's half of each pre-swizzled bf16
+//                 weight chunk (N/2 x 64 K, SWIZZLE_128B image, packed once by b2r_mlp_tc_pack) L2 ->
+//                 shared memory with cp.async.bulk (TMA engine) through a 3-stage mbarrier ring;
+//   warp 1        leader CTA: tcgen05.mma issuer (one thread): M=256, N=256|128, K=16 bf16 MMAs, A = the
+//                 sub-tile's activations in each CTA's shared memory (K-major, SWIZZLE_128B), D = fp32
+//                 accumulators in each CTA's tensor memory (2 x 256 columns = the two sub-tiles, ping-pong);
+//                 tcgen05.commit multicast frees the ring stage / publishes the accumulator in both CTAs.
+//                 peer CTA: relay thread forwarding "my half landed" to the leader's ring barrier;
 //   warps 4-11    epilogue of sub-tile 0, warps 12-19 epilogue of sub-tile 1 (thread = row = TMEM lane,
 //                 two warps per lane quadrant, each converting half of the columns):
 //                 tcgen05.ld the accumulator, + bias, ReLU (or sin(s*acc+t) for FiLM-SIREN), round to
@@ -22,7 +27,7 @@
 //   MMAs of the other.  Skip connections are extra K-chunks ([pe | h] for layers_pos.5,
 //   [h | dir-enc] for layers_dir.1), zero-padded to the MMA K granularity in the packed weights.
 //
-// Algorithmic work: 1,182,976 FLOP per NeRF row; padded: 1,187,840 (+0.4 %).
+// Algorithmic work: 1,182,976 FLOP per NeRF row; issued (padded): 1,191,936 (+0.8 %).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -32,69 +37,95 @@ namespace tc {
 using namespace umma;
 
 constexpr int kRowsSub = 128;
-constexpr int kRowsTile = 256;
+constexpr int kRowsTile = 256;                          // rows per CTA per iteration (a pair covers 512)
 constexpr int kStages = 3;
-constexpr uint32_t kStageBytes = 16384;                 // 256 rows x 64 B
+constexpr uint32_t kStageBytes = 16384;                 // 128 weight rows x 64 K bf16 (this CTA's N-half)
 constexpr uint32_t kPeBytes = 16384;                    // 128 rows x 64 bf16 (SW128): pos-enc / dir-enc block
 constexpr uint32_t kHBytes = 65536;                     // 4 K-blocks of 128 rows x 64 bf16
 constexpr uint32_t kSubBytes = kPeBytes + kHBytes;      // 80 KB per sub-tile
 constexpr uint32_t kRingOff = 2 * kSubBytes;
 
-// ---- NeRF schedule: 10 MMA steps ------------------------------------------------------------------
-// step 0..7 = layers_pos.0..7, 8 = layers_dir.0, 9 = layers_dir.1.  A chunk is N x 32 K.
-constexpr int kNerfSteps = 10;
-__host__ __device__ constexpr int nerf_chunks(int s) { return s == 0 ? 2 : (s == 5 ? 10 : (s == 9 ? 9 : 8)); }
-__host__ __device__ constexpr int nerf_n(int s) { return s == 9 ? 128 : 256; }
-// byte offset of the A operand of chunk c of step s inside the sub-tile region [pe | h]
-__host__ __device__ constexpr uint32_t nerf_a_off(int s, int c) {
-    if (s == 0) return (uint32_t)c * 64u;
-    if (s == 5) { if (c < 2) return (uint32_t)c * 64u; c -= 2; }
-    if (s == 9 && c == 8) return 0u;
-    return kPeBytes + (uint32_t)(c >> 1) * 16384u + (uint32_t)(c & 1) * 64u;
-}
-__host__ __device__ constexpr long long nerf_chunk_off(int s, int c) {
+constexpr int kCtrlWarps = 4;                           // 0 producer, 1 MMA issuer / relay (+TMEM alloc), 2-3 idle
+constexpr int kEpiWarps = 16;                           // 2 sub-tiles x 2 column halves x 4 TMEM lane quadrants
+constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32; // 640
+
+// ---- schedules (chunks of 64 K) ---------------------------------------------------------------------------
+// A step = one layer's MMAs for one sub-tile: n_pre chunks whose A operand is the aux block (pos-enc),
+// then n_h chunks reading the K-blocks of h, then n_post chunks reading the aux block again (dir-enc /
+// view direction; only kPostMmas x 16 K of it are issued).
+struct NerfSched {       // step 0..7 = layers_pos.0..7, 8 = layers_dir.0, 9 = layers_dir.1
+    static constexpr int kSteps = 10;
+    __host__ __device__ static constexpr int n_pre(int s, int) { return (s == 0 || s == 5) ? 1 : 0; }
+    __host__ __device__ static constexpr int n_h(int s, int) { return s == 0 ? 0 : 4; }
+    __host__ __device__ static constexpr int n_post(int s, int) { return s == 9 ? 1 : 0; }
+    __host__ __device__ static constexpr int n(int s) { return s == 9 ? 128 : 256; }
+    static constexpr int kPostMmas = 2;                  // dir-enc: 24 -> 32 K
+};
+struct FilmSched {       // steps 0..6 = hidden_layers.0..6, step 7 = hidden_layer_rgb ([h | dir]); flag = use_dir
+    static constexpr int kSteps = 8;
+    __host__ __device__ static constexpr int n_pre(int, int) { return 0; }
+    __host__ __device__ static constexpr int n_h(int, int) { return 4; }
+    __host__ __device__ static constexpr int n_post(int s, int use_dir) { return (s == 7 && use_dir) ? 1 : 0; }
+    __host__ __device__ static constexpr int n(int) { return 256; }
+    static constexpr int kPostMmas = 1;                  // view direction: 3 -> 16 K
+};
+template <class S>
+__host__ __device__ constexpr uint32_t half_bytes(int s) { return (uint32_t)(S::n(s) / 2) * 128u; }
+// packed chunks of a step (the post chunk is always stored, even when use_dir = 0 skips it)
+template <class S>
+__host__ __device__ constexpr int stored_chunks(int s) { return S::n_pre(s, 1) + S::n_h(s, 1) + S::n_post(s, 1); }
+template <class S>
+__host__ __device__ constexpr long long step_base(int s) {
     long long off = 0;
-    for (int t = 0; t < s; ++t) off += (long long)nerf_chunks(t) * nerf_n(t) * 64;
-    return off + (long long)c * nerf_n(s) * 64;
+    for (int t = 0; t < s; ++t) off += 2LL * stored_chunks<S>(t) * half_bytes<S>(t);
+    return off;
 }
-constexpr long long kNerfChunkBytes = nerf_chunk_off(kNerfSteps, 0);      // 1,187,840
-// fp32 tables after the chunks: bias[10][256] | w_sigma[256] | w_rgb[3][128] | b_sigma, b_rgb[3]
+
+constexpr long long kNerfChunkBytes = step_base<NerfSched>(NerfSched::kSteps);      // 1,196,032
+constexpr long long kFilmChunkBytes = step_base<FilmSched>(FilmSched::kSteps);      // 1,081,344
+static_assert(kNerfChunkBytes == 1196032 && kFilmChunkBytes == 1081344, "packed chunk bytes");
+// NeRF fp32 tables after the chunks: bias[10][256] | w_sigma[256] | w_rgb[3][128] | b_sigma, b_rgb[3]
 constexpr int kNerfTabBias = 0, kNerfTabWSigma = 2560, kNerfTabWRgb = 2816, kNerfTabBHead = 3200, kNerfTabFloats = 3204;
 constexpr long long kNerfPackedBytes = kNerfChunkBytes + kNerfTabFloats * 4;
-static_assert(kNerfChunkBytes == 1187840, "NeRF packed chunk bytes");
+// FiLM fp32 tables: scale[8][256] | shift[8][256] | w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
+//                   w_sigma[256] | w_rgb[3][256] | b_sigma, b_rgb[3]
+constexpr int kFSc = 0, kFSh = 2048, kFW0 = 4096, kFS0 = 4864, kFT0 = 5120, kFWS = 5376, kFWR = 5632, kFBH = 6400, kFilmTabFloats = 6404;
+constexpr long long kFilmPackedBytes = kFilmChunkBytes + kFilmTabFloats * 4;
 
-// ---- pack kernel: fp32 state-dict parameters -> swizzled bf16 chunk images + fp32 tables -------------
+// ---- pack kernels: fp32 state-dict parameters -> swizzled bf16 half-chunk images + fp32 tables ---------------
+// one thread per 16-byte group: (step, chunk, half, row of the half, 8 consecutive k)
+template <class S>
+__device__ __forceinline__ void locate(long long byte, int& s, int& c, int& hf, int& row, int& grp) {
+    s = 0;
+    while (s + 1 < S::kSteps && byte >= step_base<S>(s + 1)) ++s;
+    long long in_step = byte - step_base<S>(s);
+    const int hb = (int)half_bytes<S>(s);
+    int hc = (int)(in_step / hb);
+    c = hc >> 1; hf = hc & 1;
+    int rem = (int)(in_step % hb);
+    row = rem / 128; grp = (rem % 128) / 16;
+}
+
 __global__ void nerf_pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed) {
-    // one thread per (step, chunk, row, 16-byte group of 8 k)
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    long long total = kNerfChunkBytes / 16;
-    if (t < total) {
-        long long byte = t * 16;
-        int s = 0;
-        while (s + 1 < kNerfSteps && byte >= nerf_chunk_off(s + 1, 0)) ++s;
-        long long in_step = byte - nerf_chunk_off(s, 0);
-        int n_rows = nerf_n(s);
-        int c = (int)(in_step / (n_rows * 64));
-        int rem = (int)(in_step % (n_rows * 64));
-        int row = rem / 64, grp = (rem % 64) / 16;        // logical (row, 16-byte chunk) of this thread
-        int layer = s;                                     // nerf_layer index: 0..7 trunk, 8 dir.0, 9 dir.1
-        LayerDesc L = nerf_layer(layer);
+    if (t < kNerfChunkBytes / 16) {
+        int s, c, hf, row, grp;
+        locate<NerfSched>(t * 16, s, c, hf, row, grp);
+        LayerDesc L = nerf_layer(s);                              // 0..7 trunk, 8 layers_dir.0, 9 layers_dir.1
+        const int n = hf * (NerfSched::n(s) / 2) + row;           // output feature (weight row)
         __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            int kk = grp * 8 + e;                          // 0..31 inside the chunk
+            int kk = grp * 8 + e;                                 // 0..63 inside the chunk
             int col = -1;
-            if (s == 0) { int k = c * 32 + kk; col = k < 60 ? k : -1; }
-            else if (s == 5) {
-                if (c < 2) { int k = c * 32 + kk; col = k < 60 ? k : -1; }
-                else col = 60 + (c - 2) * 32 + kk;
-            } else if (s == 9) {
-                if (c < 8) col = c * 32 + kk; else col = kk < 24 ? 256 + kk : -1;
-            } else col = c * 32 + kk;
-            float w = col >= 0 ? params[L.w_off + (long long)row * L.in + col] : 0.f;
-            v[e] = __float2bfloat16_rn(w);
+            if (s == 0) col = kk < 60 ? kk : -1;
+            else if (s == 5) col = c == 0 ? (kk < 60 ? kk : -1) : 60 + (c - 1) * 64 + kk;
+            else if (s == 9) col = c < 4 ? c * 64 + kk : (kk < 24 ? 256 + kk : -1);
+            else col = c * 64 + kk;
+            v[e] = __float2bfloat16_rn(col >= 0 ? params[L.w_off + (long long)n * L.in + col] : 0.f);
         }
-        uint8_t* dst = packed + nerf_chunk_off(s, c) + sw64_offset((uint32_t)row, (uint32_t)grp);
+        uint8_t* dst = packed + step_base<NerfSched>(s) + (long long)(c * 2 + hf) * half_bytes<NerfSched>(s) +
+                       sw128_offset((uint32_t)row, (uint32_t)grp);
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
     }
     if (t < kNerfTabFloats) {
@@ -113,9 +144,51 @@ __global__ void nerf_pack_kernel(const float* __restrict__ params, uint8_t* __re
     }
 }
 
-// ---- fused kernel --------------------------------------------------------------------------------------
-// shared-memory map (offsets from the 1024-aligned base)
-constexpr uint32_t kTabOff = kRingOff + kStages * kStageBytes;          // fp32 tables (bias / head weights)
+__global__ void film_pack_kernel(const float* __restrict__ params, const float* __restrict__ film, int use_dir,
+                                 uint8_t* __restrict__ packed) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool ud = use_dir != 0;
+    if (t < kFilmChunkBytes / 16) {
+        int s, c, hf, row, grp;
+        locate<FilmSched>(t * 16, s, c, hf, row, grp);
+        LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);           // hidden_layers.s | hidden_layer_rgb
+        const int n = hf * 128 + row;
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int kk = grp * 8 + e;
+            int col = c < 4 ? c * 64 + kk : ((ud && kk < 3) ? 256 + kk : -1);
+            v[e] = __float2bfloat16_rn(col >= 0 ? params[L.w_off + (long long)n * L.in + col] : 0.f);
+        }
+        uint8_t* dst = packed + step_base<FilmSched>(s) + (long long)(c * 2 + hf) * half_bytes<FilmSched>(s) +
+                       sw128_offset((uint32_t)row, (uint32_t)grp);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+    if (t < kFilmTabFloats) {
+        float* tab = reinterpret_cast<float*>(packed + kFilmChunkBytes);
+        int i = (int)t;
+        float val;
+        if (i < kFW0) {                                            // scale / shift of the 8 tensor-core steps
+            int which = i / 2048, s = (i % 2048) / 256, n = i % 256;
+            int fl = s + 1;                                        // film row: 1..7 hidden, 8 rgb layer
+            LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);
+            float gm = film[fl * 512 + n], bt = film[fl * 512 + 256 + n], b = params[L.b_off + n];
+            val = which == 0 ? 30.0f * gm : 30.0f * (gm * b + bt);
+        } else if (i < kFS0) {
+            int k = (i - kFW0) / 256, n = (i - kFW0) % 256;
+            val = params[film_layer(0, ud).w_off + n * 3 + k];
+        } else if (i < kFT0) val = 30.0f * film[i - kFS0];
+        else if (i < kFWS) { int n = i - kFT0; val = 30.0f * (film[n] * params[film_layer(0, ud).b_off + n] + film[256 + n]); }
+        else if (i < kFWR) val = params[film_layer(8, ud).w_off + (i - kFWS)];
+        else if (i < kFBH) val = params[film_layer(10, ud).w_off + (i - kFWR)];
+        else if (i == kFBH) val = params[film_layer(8, ud).b_off];
+        else val = params[film_layer(10, ud).b_off + (i - kFBH - 1)];
+        tab[i] = val;
+    }
+}
+
+// ---- shared-memory map (offsets from the 1024-aligned base; identical in both CTAs of a pair) -------------------
+constexpr uint32_t kTabOff = kRingOff + kStages * kStageBytes;          // fp32 tables (NeRF bias / head weights)
 constexpr uint32_t kTabBytes = kNerfTabFloats * 4;                      // 12,816
 constexpr uint32_t kPartOff = kTabOff + kTabBytes;                      // head partial sums: 2 x 128 x float4
 constexpr uint32_t kPartBytes = 2 * kRowsSub * 16;
@@ -126,6 +199,7 @@ static_assert(kBarOff % 8 == 0 && kSmemBytes <= 232448, "shared-memory budget");
 struct Ctx {
     uint32_t smem;        // 1024-aligned shared base (shared-window address)
     uint32_t w_full, w_empty, act_ready, acc_full, tmem_slot;
+    uint32_t rank;        // CTA rank in the pair (0 = leader: issues the MMAs)
 };
 
 __device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
@@ -136,6 +210,7 @@ __device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
     c.act_ready = c.w_empty + 8 * kStages;
     c.acc_full = c.act_ready + 16;
     c.tmem_slot = c.acc_full + 16;
+    c.rank = cluster_ctarank();
     return c;
 }
 
@@ -168,124 +243,151 @@ __device__ __forceinline__ void posenc_words(const float x[3], uint32_t* w) {
     }
 }
 
-// ---- schedules -------------------------------------------------------------------------------------------
-// A step = one layer's MMAs for one sub-tile: n_pre chunks whose A operand is the aux block (pos-enc),
-// then n_h chunks reading h, then n_post chunks reading the aux block again (dir-enc / view direction).
-struct NerfSched {
-    __device__ static int n_pre(int s, int) { return (s == 0 || s == 5) ? 2 : 0; }
-    __device__ static int n_h(int s, int) { return s == 0 ? 0 : 8; }
-    __device__ static int n_post(int s, int) { return s == 9 ? 1 : 0; }
-    __device__ static int n(int s) { return nerf_n(s); }
-};
-// FiLM-SIREN: steps 0..6 = hidden_layers.0..6, step 7 = hidden_layer_rgb ([h | dir]); flag = use_dir
-struct FilmSched {
-    __device__ static int n_pre(int, int) { return 0; }
-    __device__ static int n_h(int, int) { return 8; }
-    __device__ static int n_post(int s, int use_dir) { return (s == 7 && use_dir) ? 1 : 0; }
-    __device__ static int n(int) { return 256; }
+// tile pairs walked by the cluster: pair p -> tiles 2p (leader) and 2p+1 (peer)
+struct PairLoop {
+    long long n_pairs, first, stride;
+    __device__ PairLoop(long long rows) {
+        long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
+        n_pairs = (n_tiles + 1) / 2;
+        first = blockIdx.x >> 1;
+        stride = gridDim.x >> 1;
+    }
 };
 
-// weight producer: one thread streams the chunk images in schedule order (each step twice: once per sub-tile)
+// weight producer: one thread per CTA streams ITS half of every chunk in schedule order (each step twice: once per sub-tile)
 template <class S>
-__device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __restrict__ packed, long long n_tiles, int n_steps, int flag) {
+__device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __restrict__ packed, const PairLoop& pl, int n_steps, int flag) {
     uint32_t stage = 0, phase = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint8_t* src_w = packed;
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
         for (int s = 0; s < n_steps; ++s) {
             const int nc = S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag);
-            const uint32_t bytes = (uint32_t)S::n(s) * 64u;
+            const uint32_t bytes = half_bytes<S>(s);
+            const uint8_t* src_w = packed + step_base<S>(s) + (size_t)cx.rank * bytes;
             for (int g = 0; g < 2; ++g) {
                 for (int c = 0; c < nc; ++c) {
-                    mbar_wait(cx.w_empty + 8 * stage, phase ^ 1u);
+                    mbar_wait_cluster(cx.w_empty + 8 * stage, phase ^ 1u);
                     mbar_arrive_expect_tx(cx.w_full + 8 * stage, bytes);
-                    bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, src_w + (size_t)c * bytes, bytes, cx.w_full + 8 * stage);
+                    bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, src_w + (size_t)c * 2 * bytes, bytes, cx.w_full + 8 * stage);
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
-            src_w += (size_t)nc * bytes;
         }
     }
 }
 
-// MMA issuer: one thread; alternates the two sub-tiles step by step
+// peer CTA: forward "my half of this stage has landed" to the leader's ring barrier (count 2 there)
 template <class S>
-__device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, long long n_tiles, int n_steps, int flag) {
+__device__ __forceinline__ void relay_loop(const Ctx& cx, const PairLoop& pl, int n_steps, int flag) {
+    uint32_t stage = 0, phase = 0;
+    const uint32_t remote0 = mapa(cx.w_full, 0);
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        for (int s = 0; s < n_steps; ++s) {
+            const int nc = 2 * (S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag));
+            for (int c = 0; c < nc; ++c) {
+                mbar_wait_cluster(cx.w_full + 8 * stage, phase);
+                mbar_arrive_cluster(remote0 + 8 * stage);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    }
+}
+
+// MMA issuer: one thread of the leader CTA; alternates the two sub-tiles step by step
+template <class S>
+__device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, const PairLoop& pl, int n_steps, int flag) {
     uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0;
-    const uint64_t a_hi = desc_sw128(0), b_hi = desc_sw64(0);     // descriptors with a zero address field
-    auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, uint32_t accumulate) {
-        mbar_wait(cx.w_full + 8 * stage, phase);
+    const uint64_t d_hi = desc_sw128(0);                          // A and B: K-major SWIZZLE_128B, zero address field
+    auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, uint32_t accumulate, int n_mma) {
+        mbar_wait_cluster(cx.w_full + 8 * stage, phase);
         tc_fence_after();
         const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
-        const uint64_t ad = a_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
-        const uint64_t bd = b_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
-        mma_bf16(d_tmem, ad, bd, idesc, accumulate);
-        mma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);               // +32 B = next 16 K
-        mma_commit(cx.w_empty + 8 * stage);
+        const uint64_t ad = d_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+        const uint64_t bd = d_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+        mma_bf16_2cta(d_tmem, ad, bd, idesc, accumulate);
+        for (int k = 1; k < n_mma; ++k) mma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);   // +32 B = next 16 K
+        mma_commit_2cta(cx.w_empty + 8 * stage, (uint16_t)3);
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
     };
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
         for (int s = 0; s < n_steps; ++s) {
-            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)S::n(s));
+            const uint32_t idesc = make_idesc_bf16(256, (uint32_t)S::n(s));
             const int n_pre = S::n_pre(s, flag), n_h = S::n_h(s, flag), n_post = S::n_post(s, flag);
             for (int g = 0; g < 2; ++g) {
-                if (g == 0) { mbar_wait(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
-                else { mbar_wait(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
+                if (g == 0) { mbar_wait_cluster(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
+                else { mbar_wait_cluster(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
                 const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
                 uint32_t acc = 0;
-                for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base + (uint32_t)c * 64u, idesc, acc); acc = 1; }
-                for (int c = 0; c < n_h; ++c) {
-                    issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)(c >> 1) * 16384u + (uint32_t)(c & 1) * 64u, idesc, acc);
-                    acc = 1;
-                }
-                for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u);
-                mma_commit(cx.acc_full + 8 * g);
+                for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base, idesc, acc, 4); acc = 1; }
+                for (int c = 0; c < n_h; ++c) { issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)c * 16384u, idesc, acc, 4); acc = 1; }
+                for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u, S::kPostMmas);
+                mma_commit_2cta(cx.acc_full + 8 * g, (uint16_t)3);
             }
         }
     }
 }
 
-// common prologue: barriers, TMEM allocation; returns the TMEM base address
+// common prologue: barriers, TMEM allocation (both CTAs), cluster rendezvous; returns the TMEM base address
 __device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp) {
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, 1); mbar_init(cx.w_empty + 8 * i, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 2 * kRowsSub); mbar_init(cx.acc_full + 8 * g, 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 16); mbar_init(cx.acc_full + 8 * g, 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(cx.tmem_slot, 512);
-    return 0;
+    if (warp == 1) tmem_alloc_2cta(cx.tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
+    return tmem_base;
+}
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
 }
 
-constexpr int kCtrlWarps = 4;                       // 0 producer, 1 MMA issuer (+TMEM alloc), 2-3 idle
-constexpr int kEpiWarps = 16;                       // 2 sub-tiles x 2 column halves x 4 TMEM lane quadrants
-constexpr int kThreadsV2 = (kCtrlWarps + kEpiWarps) * 32;   // 640
+// epilogue warp -> leader's act_ready[g]: this warp's rows of the next A operand are written and its TMEM reads are done
+__device__ __forceinline__ void arrive_act(uint32_t act_bar_local, uint32_t act_bar_leader, uint32_t rank, int lane) {
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (rank == 0) mbar_arrive_release_cluster_local(act_bar_local);
+        else mbar_arrive_cluster(act_bar_leader);
+    }
+}
 
-__global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src,
-                                                                long long rows, float4* __restrict__ raw_out) {
+// ======================================================================================================
+// NeRF (nerf/nerf.py:52-94)
+// ======================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
+    const PairLoop pl(rows);
 
-    tc_prologue(cx, warp);
     {   // bias / head-weight tables -> shared memory
         const float4* tab_g = reinterpret_cast<const float4*>(packed + kNerfChunkBytes);
-        for (int i = threadIdx.x; i < kNerfTabFloats / 4; i += kThreadsV2) {
+        for (int i = threadIdx.x; i < kNerfTabFloats / 4; i += kThreads) {
             float4 v = __ldg(tab_g + i);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
+    const uint32_t tmem_base = tc_prologue(cx, warp);
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<NerfSched>(cx, packed, n_tiles, kNerfSteps, 0);
+        if (lane == 0) producer_loop<NerfSched>(cx, packed, pl, NerfSched::kSteps, 0);
     } else if (warp == 1) {
-        if (lane == 0) mma_loop<NerfSched>(cx, tmem_base, n_tiles, kNerfSteps, 0);
+        if (lane == 0) {
+            if (cx.rank == 0) mma_loop<NerfSched>(cx, tmem_base, pl, NerfSched::kSteps, 0);
+            else relay_loop<NerfSched>(cx, pl, NerfSched::kSteps, 0);
+        }
     } else if (warp >= kCtrlWarps) {
         // ===== input generation + epilogue =====
         // warp = 4 + g*8 + half*4 + quad;  thread = row (quad*32 + lane) of sub-tile g = TMEM lane;
@@ -301,39 +403,37 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
         const uint32_t tab = cx.smem + kTabOff;
         const uint32_t part = cx.smem + kPartOff + (uint32_t)(g * kRowsSub + r) * 16u;
         const uint32_t bar_id = 1 + g;                      // named barrier of this sub-tile's 8 warps
+        const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
+        const uint32_t acc_bar = cx.acc_full + 8 * g;
         uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long row = tile * kRowsTile + g * kRowsSub + r;
+        for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+            const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
             const bool valid = row < rows;
-            float p[3], vdir[3];
-            load_row(src, valid ? row : rows - 1, p, vdir);
+            float pnt[3], vdir[3];
+            load_row(src, valid ? row : rows - 1, pnt, vdir);
             {
                 // positional encoding: 60 values + 4 zero pads = 32 words = 8 chunks; this half writes 4 of them
                 uint32_t pw[32];
-                posenc_words<10>(p, pw);
+                posenc_words<10>(pnt, pw);
                 pw[30] = 0u; pw[31] = 0u;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const uint32_t cidx = (uint32_t)(half * 4 + q);
-                    const int wq = (half * 4 + q) * 4;
-                    // half is warp-uniform: select with a predicated copy to keep pw[] in registers
                     uint32_t a0 = half ? pw[16 + 4 * q + 0] : pw[4 * q + 0];
                     uint32_t a1 = half ? pw[16 + 4 * q + 1] : pw[4 * q + 1];
                     uint32_t a2 = half ? pw[16 + 4 * q + 2] : pw[4 * q + 2];
                     uint32_t a3 = half ? pw[16 + 4 * q + 3] : pw[4 * q + 3];
-                    (void)wq;
                     st_shared_v4(pe_base + row_off + ((cidx ^ xr) << 4), a0, a1, a2, a3);
                 }
             }
-            fence_proxy_async_smem();
-            mbar_arrive(cx.act_ready + 8 * g);
+            arrive_act(act_local, act_leader, cx.rank, lane);
 
             float sigma = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-            for (int s = 0; s < kNerfSteps; ++s) {
-                mbar_wait(cx.acc_full + 8 * g, acc_phase);
+            for (int s = 0; s < NerfSched::kSteps; ++s) {
+                mbar_wait_cluster(acc_bar, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                const int njh = nerf_n(s) / 64;                         // 32-column groups per half: 4 (N=256) or 2 (N=128)
+                const int njh = NerfSched::n(s) / 64;                   // 32-column groups per half: 4 (N=256) or 2 (N=128)
                 const uint32_t bias = tab + (uint32_t)(kNerfTabBias + s * 256) * 4u;
                 for (int jj = 0; jj < njh; ++jj) {
                     const int j = half * njh + jj;
@@ -396,7 +496,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
                 }
                 if (s == 8) {
                     // view-direction encoding for layers_dir.1: 24 values + 8 zero pads = 16 words = chunks 0..3 of the
-                    // pe block; each half writes two chunks
+                    // aux block; each half writes two chunks
                     uint32_t dw[16];
                     posenc_words<4>(vdir, dw);
                     dw[12] = dw[13] = dw[14] = dw[15] = 0u;
@@ -410,11 +510,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
                         st_shared_v4(pe_base + row_off + ((cidx ^ xr) << 4), a0, a1, a2, a3);
                     }
                 }
-                tc_fence_before();
-                if (s < kNerfSteps - 1) {
-                    fence_proxy_async_smem();
-                    mbar_arrive(cx.act_ready + 8 * g);
-                }
+                if (s < NerfSched::kSteps - 1) arrive_act(act_local, act_leader, cx.rank, lane);
+                else tc_fence_before();
             }
             // combine the two halves' head partial sums and write raw[row] = (sigmoid rgb, relu sigma)
             if (half == 1)
@@ -435,11 +532,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");         // partial slot reusable
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    tc_teardown(tmem_base, warp);
 }
-
 
 // =====================================================================================================
 // FiLM-SIREN (pi_GAN/modules.py:22-25, 70-118): sin(30 (gamma (W x + b) + beta)) layers.
@@ -450,77 +544,24 @@ __global__ void __launch_bounds__(kThreadsV2, 1) nerf_tc_kernel(const uint8_t* _
 //   epilogue of hidden_layers.6 and the rgb head (256 -> 3) on the epilogue of hidden_layer_rgb, both fp32.
 //   sigma_only (create_mesh, pi_GAN/utils.py:82-90) stops after hidden_layers.6: 919,552 FLOP per row.
 // Per row the epilogue issues 2304 MUFU.SIN: at 16 / clk / SM that is as long as the MMAs.
-constexpr int kFilmSteps = 8;
-constexpr long long kFilmChunkBytes = (7 * 8 + 9) * 16384LL;           // 1,064,960 (dir chunk present even if unused)
-// fp32 tables: scale[8][256] | shift[8][256] | w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
-//              w_sigma[256] | w_rgb[3][256] | b_sigma, b_rgb[3]
-constexpr int kFSc = 0, kFSh = 2048, kFW0 = 4096, kFS0 = 4864, kFT0 = 5120, kFWS = 5376, kFWR = 5632, kFBH = 6400, kFilmTabFloats = 6404;
-constexpr long long kFilmPackedBytes = kFilmChunkBytes + kFilmTabFloats * 4;
-
-__global__ void film_pack_kernel(const float* __restrict__ params, const float* __restrict__ film, int use_dir,
-                                 uint8_t* __restrict__ packed) {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const bool ud = use_dir != 0;
-    if (t < kFilmChunkBytes / 16) {
-        long long byte = t * 16;
-        int chunk = (int)(byte / 16384);
-        int rem = (int)(byte % 16384);
-        int row = rem / 64, grp = (rem % 64) / 16;
-        int s = chunk < 56 ? chunk / 8 : 7, c = chunk < 56 ? chunk % 8 : chunk - 56;
-        LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);           // hidden_layers.s | hidden_layer_rgb
-        __nv_bfloat16 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int kk = grp * 8 + e;
-            int col = c < 8 ? c * 32 + kk : ((ud && kk < 3) ? 256 + kk : -1);
-            v[e] = __float2bfloat16_rn(col >= 0 ? params[L.w_off + (long long)row * L.in + col] : 0.f);
-        }
-        *reinterpret_cast<uint4*>(packed + (long long)chunk * 16384 + sw64_offset((uint32_t)row, (uint32_t)grp)) =
-            *reinterpret_cast<const uint4*>(v);
-    }
-    if (t < kFilmTabFloats) {
-        float* tab = reinterpret_cast<float*>(packed + kFilmChunkBytes);
-        int i = (int)t;
-        float val;
-        if (i < kFW0) {                                            // scale / shift of the 8 tensor-core steps
-            int which = i / 2048, s = (i % 2048) / 256, n = i % 256;
-            int fl = s + 1;                                        // film row: 1..7 hidden, 8 rgb layer
-            LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);
-            float gm = film[fl * 512 + n], bt = film[fl * 512 + 256 + n], b = params[L.b_off + n];
-            val = which == 0 ? 30.0f * gm : 30.0f * (gm * b + bt);
-        } else if (i < kFS0) {
-            int k = (i - kFW0) / 256, n = (i - kFW0) % 256;
-            val = params[film_layer(0, ud).w_off + n * 3 + k];
-        } else if (i < kFT0) val = 30.0f * film[i - kFS0];
-        else if (i < kFWS) { int n = i - kFT0; val = 30.0f * (film[n] * params[film_layer(0, ud).b_off + n] + film[256 + n]); }
-        else if (i < kFWR) val = params[film_layer(8, ud).w_off + (i - kFWS)];
-        else if (i < kFBH) val = params[film_layer(10, ud).w_off + (i - kFWR)];
-        else if (i == kFBH) val = params[film_layer(8, ud).b_off];
-        else val = params[film_layer(10, ud).b_off + (i - kFBH - 1)];
-        tab[i] = val;
-    }
-}
-
-__global__ void __launch_bounds__(kThreadsV2, 1) film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows,
-                                                                int use_dir, int sigma_only, float4* __restrict__ raw_out) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int use_dir, int sigma_only,
+               float4* __restrict__ raw_out) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
+    const PairLoop pl(rows);
     const float* __restrict__ tab = reinterpret_cast<const float*>(packed + kFilmChunkBytes);
-    const int n_steps = sigma_only ? 7 : kFilmSteps;
-
-    tc_prologue(cx, warp);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
+    const int n_steps = sigma_only ? 7 : FilmSched::kSteps;
+    const uint32_t tmem_base = tc_prologue(cx, warp);
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<FilmSched>(cx, packed, n_tiles, n_steps, use_dir);
+        if (lane == 0) producer_loop<FilmSched>(cx, packed, pl, n_steps, use_dir);
     } else if (warp == 1) {
-        if (lane == 0) mma_loop<FilmSched>(cx, tmem_base, n_tiles, n_steps, use_dir);
+        if (lane == 0) {
+            if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, use_dir);
+            else relay_loop<FilmSched>(cx, pl, n_steps, use_dir);
+        }
     } else if (warp >= kCtrlWarps) {
         const int ew = warp - kCtrlWarps;
         const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
@@ -532,12 +573,14 @@ __global__ void __launch_bounds__(kThreadsV2, 1) film_tc_kernel(const uint8_t* _
         const uint32_t xr = (uint32_t)(r & 7);
         const uint32_t part = cx.smem + kPartOff + (uint32_t)(g * kRowsSub + r) * 16u;
         const uint32_t bar_id = 1 + g;
+        const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
+        const uint32_t acc_bar = cx.acc_full + 8 * g;
         uint32_t acc_phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long row = tile * kRowsTile + g * kRowsSub + r;
+        for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+            const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
             const bool valid = row < rows;
-            float p[3], vdir[3];
-            load_row(src, valid ? row : rows - 1, p, vdir);
+            float pnt[3], vdir[3];
+            load_row(src, valid ? row : rows - 1, pnt, vdir);
             // ---- input_layer on CUDA cores: this half produces columns half*128 .. +127 of h0
             for (int jj = 0; jj < 4; ++jj) {
                 const int j = half * 4 + jj;
@@ -550,11 +593,10 @@ __global__ void __launch_bounds__(kThreadsV2, 1) film_tc_kernel(const uint8_t* _
                     float4 wz = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 512 + n0));
                     float4 sc = __ldg(reinterpret_cast<const float4*>(tab + kFS0 + n0));
                     float4 sh = __ldg(reinterpret_cast<const float4*>(tab + kFT0 + n0));
-                    // W x accumulated in the order of a dot product, then the folded FiLM affine, accurate sinf
-                    float a0 = fmaf(wz.x, p[2], fmaf(wy.x, p[1], wx.x * p[0]));
-                    float a1 = fmaf(wz.y, p[2], fmaf(wy.y, p[1], wx.y * p[0]));
-                    float a2 = fmaf(wz.z, p[2], fmaf(wy.z, p[1], wx.z * p[0]));
-                    float a3 = fmaf(wz.w, p[2], fmaf(wy.w, p[1], wx.w * p[0]));
+                    float a0 = fmaf(wz.x, pnt[2], fmaf(wy.x, pnt[1], wx.x * pnt[0]));
+                    float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
+                    float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
+                    float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
                     pk[2 * q + 0] = pack_bf16(sinf(fmaf(a0, sc.x, sh.x)), sinf(fmaf(a1, sc.y, sh.y)));
                     pk[2 * q + 1] = pack_bf16(sinf(fmaf(a2, sc.z, sh.z)), sinf(fmaf(a3, sc.w, sh.w)));
                 }
@@ -564,17 +606,15 @@ __global__ void __launch_bounds__(kThreadsV2, 1) film_tc_kernel(const uint8_t* _
                     st_shared_v4(blk + (((uint32_t)((j & 1) * 4 + q) ^ xr) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
             }
             if (half == 0) {
-                // view direction (3 values, zero-padded to 32) -> chunks 0..3 of the aux block (hidden_layer_rgb's extra K)
+                // view direction (3 values, zero-padded to 16) -> chunks 0..1 of the aux block (hidden_layer_rgb's extra K)
                 st_shared_v4(pe_base + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 0.f), 0u, 0u);
-#pragma unroll
-                for (uint32_t c = 1; c < 4; ++c) st_shared_v4(pe_base + row_off + ((c ^ xr) << 4), 0u, 0u, 0u, 0u);
+                st_shared_v4(pe_base + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(cx.act_ready + 8 * g);
+            arrive_act(act_local, act_leader, cx.rank, lane);
 
             float sigma = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
             for (int s = 0; s < n_steps; ++s) {
-                mbar_wait(cx.acc_full + 8 * g, acc_phase);
+                mbar_wait_cluster(acc_bar, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
                 const float* __restrict__ scp = tab + kFSc + s * 256;
@@ -624,11 +664,8 @@ __global__ void __launch_bounds__(kThreadsV2, 1) film_tc_kernel(const uint8_t* _
                                          pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
                     }
                 }
-                tc_fence_before();
-                if (s < n_steps - 1) {
-                    fence_proxy_async_smem();
-                    mbar_arrive(cx.act_ready + 8 * g);
-                }
+                if (s < n_steps - 1) arrive_act(act_local, act_leader, cx.rank, lane);
+                else tc_fence_before();
             }
             if (half == 1)
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part), "f"(rgb0), "f"(rgb1), "f"(rgb2), "f"(sigma) : "memory");
@@ -651,9 +688,7 @@ __global__ void __launch_bounds__(kThreadsV2, 1) film_tc_kernel(const uint8_t* _
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
         }
     }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    tc_teardown(tmem_base, warp);
 }
 
 }  // namespace tc
@@ -702,20 +737,22 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (rc) return rc;
     rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
     if (rc) return rc;
+    // one CTA pair per two SMs; a pair walks tile pairs (2 x 256 rows)
     long long n_tiles = (rows + tc::kRowsTile - 1) / tc::kRowsTile;
-    unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+    long long n_pairs = (n_tiles + 1) / 2;
+    long long clusters = sms / 2 < n_pairs ? sms / 2 : n_pairs;
+    unsigned grid = (unsigned)(2 * clusters);
+    cudaStream_t st = (cudaStream_t)stream;
     if (model_kind == B2R_MODEL_FILM) {
         rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
-        tc::film_tc_kernel<<<grid, tc::kThreadsV2, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
-                                                                                         use_dir, sigma_only, (float4*)raw_out);
-        B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
-        return 0;
+        tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, use_dir, sigma_only,
+                                                                      (float4*)raw_out);
+    } else {
+        rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+        if (rc) return rc;
+        tc::nerf_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out);
     }
-    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
-    if (rc) return rc;
-    tc::nerf_tc_kernel<<<grid, tc::kThreadsV2, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
-                                                                                  (float4*)raw_out);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
     return 0;
 }

@@ -61,6 +61,105 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* a_img, con
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
+static uint16_t bf16_bits(float f);
+
+// ---- CTA-pair probe: cluster of 2, tcgen05.mma.cta_group::2, M=256 (128 rows per CTA), N=256 (128 B rows per CTA), K=64 ----
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+probe2_kernel(const uint8_t* a_img /*2 x 16 KB*/, const uint8_t* b_img /*2 x 16 KB*/, float* d_out /*[256,256]*/) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* gen = raw + (base - smem_u32(raw));
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t a_s = base, b_s = base + 16384, bar_full = base + 32768, bar_done = bar_full + 8, slot = bar_full + 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar_full, 2); mbar_init(bar_done, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc_2cta(slot, 256);
+    for (int i = threadIdx.x; i < 16384 / 16; i += 128) {
+        reinterpret_cast<uint4*>(gen)[i] = reinterpret_cast<const uint4*>(a_img + rank * 16384)[i];
+        reinterpret_cast<uint4*>(gen + 16384)[i] = reinterpret_cast<const uint4*>(b_img + rank * 16384)[i];
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+    // both CTAs report "operands ready" to the leader's barrier (local arrive in the leader, remote from the peer)
+    if (threadIdx.x == 0) {
+        if (rank == 0) mbar_arrive_release_cluster_local(bar_full);
+        else mbar_arrive_cluster(mapa(bar_full, 0));
+    }
+    if (rank == 0 && threadIdx.x == 0) {
+        mbar_wait_cluster(bar_full, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(256, 256);
+        for (int k = 0; k < 4; ++k)
+            mma_bf16_2cta(tmem, make_desc(a_s + k * 32, 16, 1024, 2), make_desc(b_s + k * 32, 16, 1024, 2), idesc, k != 0);
+        mma_commit_2cta(bar_done, (uint16_t)3);
+    }
+    __syncwarp();
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    for (int j = 0; j < 8; ++j) {
+        uint32_t x[32];
+        tmem_ld32(tmem + ((uint32_t)warp << 21) + j * 32, x);
+        tmem_ld_wait();
+        for (int e = 0; e < 32; ++e) d_out[(rank * 128 + r) * 256 + j * 32 + e] = __uint_as_float(x[e]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_2cta(tmem, 256);
+}
+
+static int run_probe2() {
+    const int M = 256, N = 256, K = 64;
+    std::vector<float> A(M * K), B(N * K), D(M * N);
+    srand(7);
+    for (auto& x : A) x = (float)(rand() % 7 - 3);
+    for (auto& x : B) x = (float)(rand() % 5 - 2);
+    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < K; ++k) s += A[m * K + k] * B[n * K + k]; D[m * N + n] = s; }
+    std::vector<uint8_t> a_img(32768), b_img(32768);
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) {
+        uint16_t h = bf16_bits(A[m * K + k]);
+        memcpy(&a_img[(m / 128) * 16384 + sw128_offset(m % 128, k / 8) + (k % 8) * 2], &h, 2);
+    }
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) {      // hypothesis: CTA r holds B rows [128 r, 128 r + 128)
+        uint16_t h = bf16_bits(B[n * K + k]);
+        memcpy(&b_img[(n / 128) * 16384 + sw128_offset(n % 128, k / 8) + (k % 8) * 2], &h, 2);
+    }
+    uint8_t *da, *db; float* dd;
+    cudaMalloc(&da, 32768); cudaMalloc(&db, 32768); cudaMalloc(&dd, M * N * 4);
+    cudaMemcpy(da, a_img.data(), 32768, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, b_img.data(), 32768, cudaMemcpyHostToDevice);
+    cudaMemset(dd, 0xff, M * N * 4);
+    cudaFuncSetAttribute(probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    probe2_kernel<<<2, 128, 48 * 1024>>>(da, db, dd);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("PROBE2 cta_group::2 : CUDA error %s\n", cudaGetErrorString(e)); return 2; }
+    std::vector<float> got(M * N);
+    cudaMemcpy(got.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
+    int bad = 0, first = -1;
+    for (int i = 0; i < M * N; ++i) if (got[i] != D[i]) { if (first < 0) first = i; ++bad; }
+    printf("PROBE2 cta_group::2 M=256 N=256 (A rows and B rows split by CTA rank) : mismatches %d / %d", bad, M * N);
+    if (bad) {
+        printf("  first at (m=%d,n=%d) got %g want %g\n", first / N, first % N, got[first], D[first]);
+        // diagnose the column mapping of row 0 and row 128
+        for (int m : {0, 128}) {
+            printf("   row %d: D columns 0,1,2,128,129 match expected n =", m);
+            for (int j : {0, 1, 2, 128, 129}) {
+                int hit = -1;
+                for (int n = 0; n < N; ++n) if (got[m * N + j] == D[m * N + n]) { hit = n; break; }
+                printf(" %d", hit);
+            }
+            printf("\n");
+        }
+    } else printf("\n");
+    printf(bad ? "PROBE2 FAILED\n" : "PROBE2 OK\n");
+    return bad ? 1 : 0;
+}
+
 static uint16_t bf16_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); }   // exact for small ints
 
 int main() {
@@ -109,5 +208,6 @@ int main() {
         if (!bad) ok_any = 1;
     }
     printf(ok_any ? "PROBE OK\n" : "PROBE FAILED\n");
+    run_probe2();
     return 0;
 }
