@@ -362,6 +362,78 @@ __device__ __forceinline__ void arrive_act(uint32_t act_bar_local, uint32_t act_
     }
 }
 
+// packed fp32x2 add (FADD2): {a0,a1} += {b0,b1}
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+
+// One NeRF layer's epilogue for this warp's half of the columns, fully unrolled (no per-step branches in the hot loop).
+//   MODE 0: + bias, ReLU -> bf16 h                       (layers_pos.0..6)
+//   MODE 1: same + partial sigma head on the fp32 values  (layers_pos.7; output_layer_sigma, nerf/nerf.py:72,88)
+//   MODE 2: + bias, linear -> bf16 h                      (layers_dir.0)
+//   MODE 3: + bias, ReLU -> partial rgb head, no store    (layers_dir.1, N = 128; output_layer_rgb, nerf/nerf.py:73,93)
+// t_half / bias_half / h_half already include this warp's column-half offset; xoff[c] = ((c ^ (row & 7)) << 4).
+template <int MODE>
+__device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, uint32_t head_half, uint32_t h_half,
+                                         const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2) {
+    constexpr int NJH = MODE == 3 ? 2 : 4;
+#pragma unroll
+    for (int jj = 0; jj < NJH; ++jj) {
+        uint32_t v[32];
+        tmem_ld32(t_half + (uint32_t)jj * 32u, v);
+        float4 b[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[q] = lds128(bias_half + (uint32_t)(jj * 32 + q * 4) * 4u);     // overlaps the TMEM load
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            f[4 * q + 0] = __uint_as_float(v[4 * q + 0]); f[4 * q + 1] = __uint_as_float(v[4 * q + 1]);
+            f[4 * q + 2] = __uint_as_float(v[4 * q + 2]); f[4 * q + 3] = __uint_as_float(v[4 * q + 3]);
+            add2(f[4 * q + 0], f[4 * q + 1], b[q].x, b[q].y);
+            add2(f[4 * q + 2], f[4 * q + 3], b[q].z, b[q].w);
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 w = lds128(head_half + (uint32_t)(jj * 32 + q * 4) * 4u);
+                sigma = fmaf(fmaxf(f[4 * q + 0], 0.f), w.x, sigma);
+                sigma = fmaf(fmaxf(f[4 * q + 1], 0.f), w.y, sigma);
+                sigma = fmaf(fmaxf(f[4 * q + 2], 0.f), w.z, sigma);
+                sigma = fmaf(fmaxf(f[4 * q + 3], 0.f), w.w, sigma);
+            }
+        }
+        if (MODE == 3) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t wa = head_half + (uint32_t)(jj * 32 + q * 4) * 4u;
+                float4 w0 = lds128(wa), w1 = lds128(wa + 512u), w2 = lds128(wa + 1024u);
+                float h0 = fmaxf(f[4 * q + 0], 0.f), h1 = fmaxf(f[4 * q + 1], 0.f);
+                float h2 = fmaxf(f[4 * q + 2], 0.f), h3 = fmaxf(f[4 * q + 3], 0.f);
+                rgb0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, rgb0))));
+                rgb1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, rgb1))));
+                rgb2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, rgb2))));
+            }
+        } else {
+            // columns of this 32-group = K of the next layer: K-block (jj >> 1) of this half, chunks (jj & 1) * 4 .. + 3
+            const uint32_t blk = h_half + (uint32_t)(jj >> 1) * 16384u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w0, w1, w2, w3;
+                if (MODE == 2) {
+                    w0 = pack_bf16(f[8 * q + 0], f[8 * q + 1]); w1 = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+                    w2 = pack_bf16(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+                } else {
+                    w0 = pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]); w1 = pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]);
+                    w2 = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
+                }
+                st_shared_v4(blk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
+            }
+        }
+    }
+}
+
 // ======================================================================================================
 // NeRF (nerf/nerf.py:52-94)
 // ======================================================================================================
@@ -405,6 +477,13 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         const uint32_t bar_id = 1 + g;                      // named barrier of this sub-tile's 8 warps
         const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
         const uint32_t acc_bar = cx.acc_full + 8 * g;
+        // this warp's column half (N = 256 layers): TMEM columns, bias slice, destination K-blocks
+        const uint32_t t_half = t_addr + (uint32_t)half * 128u;
+        const uint32_t bias_half = tab + (uint32_t)(kNerfTabBias + half * 128) * 4u;
+        const uint32_t h_half = h_base + row_off + (uint32_t)half * 2u * 16384u;
+        uint32_t xoff[8];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
         uint32_t acc_phase = 0;
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
             const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
@@ -429,90 +508,41 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             arrive_act(act_local, act_leader, cx.rank, lane);
 
             float sigma = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-            for (int s = 0; s < NerfSched::kSteps; ++s) {
+            auto wait_acc = [&]() {
                 mbar_wait_cluster(acc_bar, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                const int njh = NerfSched::n(s) / 64;                   // 32-column groups per half: 4 (N=256) or 2 (N=128)
-                const uint32_t bias = tab + (uint32_t)(kNerfTabBias + s * 256) * 4u;
-                for (int jj = 0; jj < njh; ++jj) {
-                    const int j = half * njh + jj;
-                    uint32_t v[32];
-                    tmem_ld32(t_addr + (uint32_t)j * 32u, v);
-                    float f[32];
-                    // bias loads (shared-memory broadcast) overlap the TMEM load
-                    float4 b[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) b[q] = lds128(bias + (uint32_t)(j * 32 + q * 4) * 4u);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        f[4 * q + 0] = __uint_as_float(v[4 * q + 0]) + b[q].x;
-                        f[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + b[q].y;
-                        f[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + b[q].z;
-                        f[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + b[q].w;
-                    }
-                    if (s == 7) {
-                        // sigma head on the fp32 activations (output_layer_sigma, nerf/nerf.py:72,88)
-                        const uint32_t ws = tab + (uint32_t)(kNerfTabWSigma + j * 32) * 4u;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 w = lds128(ws + 16u * q);
-                            sigma = fmaf(fmaxf(f[4 * q + 0], 0.f), w.x, sigma);
-                            sigma = fmaf(fmaxf(f[4 * q + 1], 0.f), w.y, sigma);
-                            sigma = fmaf(fmaxf(f[4 * q + 2], 0.f), w.z, sigma);
-                            sigma = fmaf(fmaxf(f[4 * q + 3], 0.f), w.w, sigma);
-                        }
-                    }
-                    if (s == 9) {
-                        // rgb head (output_layer_rgb: 128 -> 3) on the fp32 relu activations
-                        const uint32_t wr = tab + (uint32_t)(kNerfTabWRgb + j * 32) * 4u;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 w0 = lds128(wr + 16u * q), w1 = lds128(wr + 512u + 16u * q), w2 = lds128(wr + 1024u + 16u * q);
-                            float h0 = fmaxf(f[4 * q + 0], 0.f), h1 = fmaxf(f[4 * q + 1], 0.f);
-                            float h2 = fmaxf(f[4 * q + 2], 0.f), h3 = fmaxf(f[4 * q + 3], 0.f);
-                            rgb0 = fmaf(h0, w0.x, fmaf(h1, w0.y, fmaf(h2, w0.z, fmaf(h3, w0.w, rgb0))));
-                            rgb1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, rgb1))));
-                            rgb2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, rgb2))));
-                        }
-                    } else {
-                        // columns j*32 .. j*32+31 of this layer = K of the next: K-block j/2, chunks (j&1)*4 .. +3
-                        const uint32_t blk = h_base + (uint32_t)(j >> 1) * 16384u + row_off;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t w0, w1, w2, w3;
-                            if (s == 8) {                                  // layers_dir.0 is linear
-                                w0 = pack_bf16(f[8 * q + 0], f[8 * q + 1]); w1 = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
-                                w2 = pack_bf16(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-                            } else {
-                                w0 = pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]); w1 = pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]);
-                                w2 = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
-                            }
-                            const uint32_t cidx = (uint32_t)((j & 1) * 4 + q);
-                            st_shared_v4(blk + ((cidx ^ xr) << 4), w0, w1, w2, w3);
-                        }
-                    }
-                }
-                if (s == 8) {
-                    // view-direction encoding for layers_dir.1: 24 values + 8 zero pads = 16 words = chunks 0..3 of the
-                    // aux block; each half writes two chunks
-                    uint32_t dw[16];
-                    posenc_words<4>(vdir, dw);
-                    dw[12] = dw[13] = dw[14] = dw[15] = 0u;
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const uint32_t cidx = (uint32_t)(half * 2 + q);
-                        uint32_t a0 = half ? dw[8 + 4 * q + 0] : dw[4 * q + 0];
-                        uint32_t a1 = half ? dw[8 + 4 * q + 1] : dw[4 * q + 1];
-                        uint32_t a2 = half ? dw[8 + 4 * q + 2] : dw[4 * q + 2];
-                        uint32_t a3 = half ? dw[8 + 4 * q + 3] : dw[4 * q + 3];
-                        st_shared_v4(pe_base + row_off + ((cidx ^ xr) << 4), a0, a1, a2, a3);
-                    }
-                }
-                if (s < NerfSched::kSteps - 1) arrive_act(act_local, act_leader, cx.rank, lane);
-                else tc_fence_before();
+            };
+            for (int s = 0; s < 7; ++s) {                               // layers_pos.0 .. layers_pos.6
+                wait_acc();
+                nerf_epi<0>(t_half, bias_half + (uint32_t)s * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+                arrive_act(act_local, act_leader, cx.rank, lane);
             }
+            wait_acc();                                                 // layers_pos.7 (+ sigma head)
+            nerf_epi<1>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+            arrive_act(act_local, act_leader, cx.rank, lane);
+            wait_acc();                                                 // layers_dir.0 (linear) + view-direction encoding
+            nerf_epi<2>(t_half, bias_half + 8u * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+            {
+                // layers_dir.1's extra K: 24 values + 8 zero pads = 16 words = chunks 0..3 of the aux block; each half writes two
+                uint32_t dw[16];
+                posenc_words<4>(vdir, dw);
+                dw[12] = dw[13] = dw[14] = dw[15] = 0u;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t a0 = half ? dw[8 + 4 * q + 0] : dw[4 * q + 0];
+                    uint32_t a1 = half ? dw[8 + 4 * q + 1] : dw[4 * q + 1];
+                    uint32_t a2 = half ? dw[8 + 4 * q + 2] : dw[4 * q + 2];
+                    uint32_t a3 = half ? dw[8 + 4 * q + 3] : dw[4 * q + 3];
+                    st_shared_v4(pe_base + row_off + ((((uint32_t)(half * 2 + q)) ^ xr) << 4), a0, a1, a2, a3);
+                }
+            }
+            arrive_act(act_local, act_leader, cx.rank, lane);
+            wait_acc();                                                 // layers_dir.1 (N = 128) + rgb head
+            nerf_epi<3>(tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)half * 64u,
+                        tab + (uint32_t)(kNerfTabBias + 9 * 256 + half * 64) * 4u, tab + (uint32_t)(kNerfTabWRgb + half * 64) * 4u, 0u, xoff,
+                        sigma, rgb0, rgb1, rgb2);
+            tc_fence_before();
             // combine the two halves' head partial sums and write raw[row] = (sigmoid rgb, relu sigma)
             if (half == 1)
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part), "f"(rgb0), "f"(rgb1), "f"(rgb2), "f"(sigma) : "memory");
