@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid"],
+                    help="render = the headline NeRF 800x800 frame (default; BASELINE.json configs[1]); the others are the "
+                         "secondary BASELINE configs: train = 4096-ray NeRF training step (configs[2]), pigan = pi-GAN 128x128 "
+                         "24+24 x 64 latents (configs[3]), grid = 256^3 density query (configs[4])")
     return ap.parse_args()
 
 
@@ -317,10 +321,124 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+
+# ---- secondary BASELINE.json configs (not the headline line; printed with the same keys) ----------------------
+def run_secondary(args):
+    import torch
+    import torch.distributed as dist
+    from msra_practice_project_b200 import _lib, dist as shard, models, nerf_render, pigan_render
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.lib().b2r_device_ok() == 1
+
+    def timed(fn, steps, warmup):
+        for _ in range(max(warmup, 3)):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    if args.config == "train":
+        # nerf/train_nerf.py:151-168: render_rays on a 4096-ray batch, MSE(coarse)+MSE(fine), backward, Adam; the batch is
+        # sharded over ranks and the flat fp32 gradient bucket is all-reduced once per step
+        n_batch, sc, sf = 4096, args.coarse, args.fine
+        b, c = shard.shard_range(n_batch, rank, world)
+        torch.manual_seed(0)
+        coarse, fine = models.NeRF().to(dev), models.NeRF().to(dev)
+        opt = torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()), lr=5e-4)
+        pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+        from msra_practice_project_b200 import ops
+        rays = ops.raygen(800, 800, 800 * 1.3875, pose, 320000 + b, c, device=dev)
+        torch.manual_seed(1)
+        target = torch.rand((n_batch, 3), device=dev)[b:b + c]
+        torch.manual_seed(5)
+        t_rand = torch.rand((n_batch, sc), device=dev)[b:b + c].contiguous()
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            rc, _, _, rf, _, _ = nerf_render.render_rays(rays, 2.0, 6.0, coarse, fine, sc, sf, t_rand=t_rand)
+            loss = ((rf - target) ** 2).sum() / (n_batch * 3) + ((rc - target) ** 2).sum() / (n_batch * 3)
+            loss.backward()
+            shard.allreduce_gradients([coarse, fine], average=False)
+            opt.step()
+        ms = timed(step, args.steps, args.warmup)
+        rows = n_batch * (2 * sc + sf)
+        line = dict(metric="rays/s, NeRF training step (4096-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
+                    unit="rays/s", ms_per_step=ms, dtype="f32", scaling="strong",
+                    config=dict(workload="NeRF train step, 4096 rays sharded over ranks, fp32 CUDA-core MLP forward with saved activations + "
+                                         "CUDA reverse mode, one NCCL all-reduce of the 4.75 MB gradient bucket, torch Adam"),
+                    tflops_fp32=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
+    elif args.config == "pigan":
+        n_lat, res, s_ = 64, 128, 24
+        b, c = shard.shard_range(n_lat, rank, world)
+        torch.manual_seed(0)
+        net = models.FilmSirenNeRF().to(dev)
+        g = torch.Generator().manual_seed(0)
+        film = torch.cat([1.0 + 0.2 * torch.randn(n_lat, 9, 256, generator=g), 0.1 * torch.randn(n_lat, 9, 256, generator=g)], -1).to(dev)
+        focal = np.float64(res / 2 / np.tan(6 * np.pi / 180))
+        poses = [pigan_render.camera_pos_to_transform_matrix(1, 0.3 * np.sin(i), 0.15 * np.cos(i)) for i in range(n_lat)]
+        out_all = torch.empty((n_lat, 3, res, res), device=dev) if world > 1 else None
+
+        def step():
+            with torch.no_grad():
+                imgs = pigan_render.render_batch(net, film[b:b + c], poses[b:b + c], res, res, focal, 0.5, 1.5, s_, s_, precision=args.precision)
+                if world > 1:
+                    dist.all_gather_into_tensor(out_all, imgs.contiguous())
+        ms = timed(step, args.steps, args.warmup)
+        rays = n_lat * res * res
+        line = dict(metric="rays/s, pi-GAN FiLM-SIREN render 128x128, 24+24 samples, 64 latents", value=rays / (ms * 1e-3), unit="rays/s",
+                    ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
+                    config=dict(workload="pi-GAN generator render, 64 latents sharded over ranks, one pack + 4 kernels per latent"),
+                    images_per_s=n_lat / (ms * 1e-3), tflops=rays * 72 * 1053696 / (ms * 1e-3) / 1e12)
+    else:
+        n = 256
+        n3 = n ** 3
+        b, c = shard.shard_range(n3, rank, world)
+        torch.manual_seed(0)
+        net = models.FilmSirenNeRF().to(dev)
+        g = torch.Generator().manual_seed(0)
+        net.set_film_params(torch.cat([1.0 + 0.2 * torch.randn(9, 256, generator=g), 0.1 * torch.randn(9, 256, generator=g)], -1).to(dev))
+        out_all = torch.empty((n3,), device=dev) if world > 1 else None
+
+        def step():
+            sig = pigan_render.density_grid(net, n, max_batch=n3, begin=b, count=c, precision=args.precision)
+            if world > 1:
+                dist.all_gather_into_tensor(out_all, sig.contiguous())
+        ms = timed(step, args.steps, args.warmup)
+        line = dict(metric="points/s, pi-GAN create_mesh density query on a 256^3 grid (sigma only)", value=n3 / (ms * 1e-3), unit="points/s",
+                    ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
+                    config=dict(workload="256^3 lattice in [-0.1,0.1]^3, coordinates generated on the device, sigma-only FiLM-SIREN kernel"),
+                    tflops=n3 * 919552 / (ms * 1e-3) / 1e12)
+    if rank == 0:
+        line.update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, vs_baseline=None, data="synthetic")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "render":
+        run_secondary(args)
     else:
         run_b200(args)
 
