@@ -26,6 +26,9 @@ __device__ __forceinline__ float warp_scan_mul(float p, int lane) {
     return p;
 }
 
+// Forward: every lane owns TWO consecutive samples of a 64-sample chunk (32 contiguous bytes of raw per lane,
+// 1 KB per warp-load), so the transmittance scan costs 5 shuffle steps per 64 samples; the next chunk's loads
+// are issued before the current one is reduced.  exp() is ex2.approx (|error| < 2e-7 on alpha).
 template <bool kWeights>
 __global__ void __launch_bounds__(256) composite_fwd_kernel(
     const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
@@ -34,36 +37,45 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (long long ray = warp0; ray < n_rays; ray += n_warps) {
         const float norm = ray_norm(rays_d + ray * d_stride);
         const float4* rr = raw + ray * S;
         const float* zz = z + ray * S;
         float carry = 1.0f;
         float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
-        // software prefetch: chunk c+1 is in flight while chunk c is reduced
-        int k = lane;
-        float4 r = k < S ? rr[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-        float zk = k < S ? zz[k] : 0.f;
-        float zn = k + 1 < S ? zz[k + 1] : 0.f;
-        for (int c0 = 0; c0 < S; c0 += 32) {
-            int kn = c0 + 32 + lane;
-            float4 r_next = kn < S ? rr[kn] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float zk_next = kn < S ? zz[kn] : 0.f;
-            float zn_next = kn + 1 < S ? zz[kn + 1] : 0.f;
-            bool valid = k < S;
-            float dist = (k == S - 1) ? 1e10f : __fsub_rn(zn, zk);
-            dist = __fmul_rn(dist, norm);
-            float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(r.w, dist))) : 0.f;
-            float q = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
-            float p = warp_scan_mul(q, lane);
+        int k = 2 * lane;
+        float4 r0 = k < S ? rr[k] : zero4, r1 = k + 1 < S ? rr[k + 1] : zero4;
+        float z0 = k < S ? zz[k] : 0.f, z1 = k + 1 < S ? zz[k + 1] : 0.f;
+        float ze = (lane == 31 && 64 < S) ? zz[64] : 0.f;          // first z of the next chunk (needed by lane 31 only)
+        for (int c0 = 0; c0 < S; c0 += 64) {
+            const int kn = c0 + 64 + 2 * lane;
+            float4 r0n = kn < S ? rr[kn] : zero4, r1n = kn + 1 < S ? rr[kn + 1] : zero4;
+            float z0n = kn < S ? zz[kn] : 0.f, z1n = kn + 1 < S ? zz[kn + 1] : 0.f;
+            float zen = (lane == 31 && c0 + 128 < S) ? zz[c0 + 128] : 0.f;
+            float z2 = __shfl_down_sync(kFull, z0, 1);                 // z[k+2] = next lane's first sample
+            if (lane == 31) z2 = ze;
+            const bool v0 = k < S, v1 = k + 1 < S;
+            float d0 = (k == S - 1) ? 1e10f : __fsub_rn(z1, z0);
+            float d1 = (k + 1 == S - 1) ? 1e10f : __fsub_rn(z2, z1);
+            d0 = __fmul_rn(d0, norm); d1 = __fmul_rn(d1, norm);
+            float a0 = v0 ? 1.0f - __expf(-r0.w * d0) : 0.f;
+            float a1 = v1 ? 1.0f - __expf(-r1.w * d1) : 0.f;
+            float q0 = v0 ? (1.0f - a0) + 1e-10f : 1.0f;
+            float q1 = v1 ? (1.0f - a1) + 1e-10f : 1.0f;
+            float p = warp_scan_mul(q0 * q1, lane);
             float excl = __shfl_up_sync(kFull, p, 1);
             if (lane == 0) excl = 1.0f;
-            float w = alpha * (carry * excl);
+            const float t0 = carry * excl, t1 = t0 * q0;
+            const float w0 = a0 * t0, w1 = a1 * t1;
             carry *= __shfl_sync(kFull, p, 31);
-            ar = fmaf(w, r.x, ar); ag = fmaf(w, r.y, ag); ab = fmaf(w, r.z, ab);
-            ad = fmaf(w, zk, ad); aa += w;
-            if (kWeights && valid) w_out[ray * S + k] = w;
-            r = r_next; zk = zk_next; zn = zn_next; k = kn;
+            ar = fmaf(w0, r0.x, fmaf(w1, r1.x, ar)); ag = fmaf(w0, r0.y, fmaf(w1, r1.y, ag)); ab = fmaf(w0, r0.z, fmaf(w1, r1.z, ab));
+            ad = fmaf(w0, z0, fmaf(w1, z1, ad)); aa += w0 + w1;
+            if (kWeights) {
+                if (v0) w_out[ray * S + k] = w0;
+                if (v1) w_out[ray * S + k + 1] = w1;
+            }
+            r0 = r0n; r1 = r1n; z0 = z0n; z1 = z1n; ze = zen; k = kn;
         }
         ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
         if (lane == 0) {

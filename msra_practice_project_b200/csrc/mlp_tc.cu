@@ -565,6 +565,54 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     tc_teardown(tmem_base, warp);
 }
 
+// One FiLM-SIREN layer's epilogue for this warp's half of the columns: sin(scale * acc + shift), unrolled.
+//   MODE 0: -> bf16 h (hidden_layers.0..5);  MODE 1: -> bf16 h + partial sigma head (hidden_layers.6, modules.py:112);
+//   MODE 2: -> partial rgb head, no store (hidden_layer_rgb, modules.py:114-116)
+// sc_half / sh_half: shared-memory addresses of this step's scale / shift slices; head: global fp32 head weights.
+template <int MODE>
+__device__ __forceinline__ void film_epi(uint32_t t_half, uint32_t sc_half, uint32_t sh_half, const float* __restrict__ head,
+                                         uint32_t h_half, const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        uint32_t v[32];
+        tmem_ld32(t_half + (uint32_t)jj * 32u, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 sc = lds128(sc_half + (uint32_t)(jj * 32 + q * 4) * 4u), sh = lds128(sh_half + (uint32_t)(jj * 32 + q * 4) * 4u);
+            f[4 * q + 0] = __sinf(fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x));
+            f[4 * q + 1] = __sinf(fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y));
+            f[4 * q + 2] = __sinf(fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z));
+            f[4 * q + 3] = __sinf(fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w));
+        }
+        if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 w = __ldg(reinterpret_cast<const float4*>(head + jj * 32) + q);
+                sigma = fmaf(f[4 * q + 0], w.x, fmaf(f[4 * q + 1], w.y, fmaf(f[4 * q + 2], w.z, fmaf(f[4 * q + 3], w.w, sigma))));
+            }
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 w0 = __ldg(reinterpret_cast<const float4*>(head + jj * 32) + q);
+                float4 w1 = __ldg(reinterpret_cast<const float4*>(head + 256 + jj * 32) + q);
+                float4 w2 = __ldg(reinterpret_cast<const float4*>(head + 512 + jj * 32) + q);
+                rgb0 = fmaf(f[4 * q + 0], w0.x, fmaf(f[4 * q + 1], w0.y, fmaf(f[4 * q + 2], w0.z, fmaf(f[4 * q + 3], w0.w, rgb0))));
+                rgb1 = fmaf(f[4 * q + 0], w1.x, fmaf(f[4 * q + 1], w1.y, fmaf(f[4 * q + 2], w1.z, fmaf(f[4 * q + 3], w1.w, rgb1))));
+                rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
+            }
+        } else {
+            const uint32_t blk = h_half + (uint32_t)(jj >> 1) * 16384u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                st_shared_v4(blk + xoff[(jj & 1) * 4 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
+                             pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
+        }
+    }
+}
+
 // =====================================================================================================
 // FiLM-SIREN (pi_GAN/modules.py:22-25, 70-118): sin(30 (gamma (W x + b) + beta)) layers.
 //   input_layer (3 -> 256) runs on CUDA cores in fp32 inside the input stage (K = 3 is no GEMM and its
@@ -583,6 +631,14 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     const PairLoop pl(rows);
     const float* __restrict__ tab = reinterpret_cast<const float*>(packed + kFilmChunkBytes);
     const int n_steps = sigma_only ? 7 : FilmSched::kSteps;
+    {   // scale[8][256] | shift[8][256] (16 KB) -> shared memory; the head weights stay in global memory (L1)
+        static_assert(kFSc == 0 && kFSh == 2048 && 4096 * 4 <= kTabBytes + kPartBytes, "FiLM table region");
+        const float4* tab_g = reinterpret_cast<const float4*>(tab);
+        for (int i = threadIdx.x; i < 4096 / 4; i += kThreads) {
+            float4 v = __ldg(tab_g + i);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+        }
+    }
     const uint32_t tmem_base = tc_prologue(cx, warp);
 
     if (warp == 0) {
@@ -601,10 +657,16 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         const uint32_t t_addr = tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u;
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         const uint32_t xr = (uint32_t)(r & 7);
-        const uint32_t part = cx.smem + kPartOff + (uint32_t)(g * kRowsSub + r) * 16u;
+        const uint32_t part = pe_base + 8192u + (uint32_t)r * 16u;     // head partials live in the aux block (free at tile end)
         const uint32_t bar_id = 1 + g;
         const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
         const uint32_t acc_bar = cx.acc_full + 8 * g;
+        const uint32_t t_half = t_addr + (uint32_t)half * 128u;
+        const uint32_t sc_half = cx.smem + kTabOff + (uint32_t)(half * 128) * 4u, sh_half = sc_half + 2048u * 4u;
+        const uint32_t h_half = h_base + row_off + (uint32_t)half * 2u * 16384u;
+        uint32_t xoff[8];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
         uint32_t acc_phase = 0;
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
             const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
@@ -643,60 +705,24 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             arrive_act(act_local, act_leader, cx.rank, lane);
 
             float sigma = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-            for (int s = 0; s < n_steps; ++s) {
+            auto wait_acc = [&]() {
                 mbar_wait_cluster(acc_bar, acc_phase);
                 acc_phase ^= 1u;
                 tc_fence_after();
-                const float* __restrict__ scp = tab + kFSc + s * 256;
-                const float* __restrict__ shp = tab + kFSh + s * 256;
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = half * 4 + jj;
-                    uint32_t v[32];
-                    tmem_ld32(t_addr + (uint32_t)j * 32u, v);
-                    float4 sc[8], sh[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        sc[q] = __ldg(reinterpret_cast<const float4*>(scp + j * 32) + q);
-                        sh[q] = __ldg(reinterpret_cast<const float4*>(shp + j * 32) + q);
-                    }
-                    tmem_ld_wait();
-                    float f[32];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        f[4 * q + 0] = __sinf(fmaf(__uint_as_float(v[4 * q + 0]), sc[q].x, sh[q].x));
-                        f[4 * q + 1] = __sinf(fmaf(__uint_as_float(v[4 * q + 1]), sc[q].y, sh[q].y));
-                        f[4 * q + 2] = __sinf(fmaf(__uint_as_float(v[4 * q + 2]), sc[q].z, sh[q].z));
-                        f[4 * q + 3] = __sinf(fmaf(__uint_as_float(v[4 * q + 3]), sc[q].w, sh[q].w));
-                    }
-                    if (s == 6) {                                   // sigma head on h7 (output_layer_sigma, modules.py:112)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 w = __ldg(reinterpret_cast<const float4*>(tab + kFWS + j * 32) + q);
-                            sigma = fmaf(f[4 * q + 0], w.x, fmaf(f[4 * q + 1], w.y, fmaf(f[4 * q + 2], w.z, fmaf(f[4 * q + 3], w.w, sigma))));
-                        }
-                    }
-                    if (s == 7) {                                   // rgb head (output_layer_rgb: 256 -> 3, modules.py:116)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 w0 = __ldg(reinterpret_cast<const float4*>(tab + kFWR + j * 32) + q);
-                            float4 w1 = __ldg(reinterpret_cast<const float4*>(tab + kFWR + 256 + j * 32) + q);
-                            float4 w2 = __ldg(reinterpret_cast<const float4*>(tab + kFWR + 512 + j * 32) + q);
-                            rgb0 = fmaf(f[4 * q + 0], w0.x, fmaf(f[4 * q + 1], w0.y, fmaf(f[4 * q + 2], w0.z, fmaf(f[4 * q + 3], w0.w, rgb0))));
-                            rgb1 = fmaf(f[4 * q + 0], w1.x, fmaf(f[4 * q + 1], w1.y, fmaf(f[4 * q + 2], w1.z, fmaf(f[4 * q + 3], w1.w, rgb1))));
-                            rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
-                        }
-                    } else {
-                        const uint32_t blk = h_base + (uint32_t)(j >> 1) * 16384u + row_off;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            st_shared_v4(blk + (((uint32_t)((j & 1) * 4 + q) ^ xr) << 4),
-                                         pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
-                                         pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
-                    }
-                }
-                if (s < n_steps - 1) arrive_act(act_local, act_leader, cx.rank, lane);
-                else tc_fence_before();
+            };
+            for (int s = 0; s < 6; ++s) {                               // hidden_layers.0 .. 5
+                wait_acc();
+                film_epi<0>(t_half, sc_half + (uint32_t)s * 1024u, sh_half + (uint32_t)s * 1024u, nullptr, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+                arrive_act(act_local, act_leader, cx.rank, lane);
             }
+            wait_acc();                                                 // hidden_layers.6 (+ sigma head)
+            film_epi<1>(t_half, sc_half + 6u * 1024u, sh_half + 6u * 1024u, tab + kFWS + half * 128, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+            if (!sigma_only) {
+                arrive_act(act_local, act_leader, cx.rank, lane);
+                wait_acc();                                             // hidden_layer_rgb (+ rgb head)
+                film_epi<2>(t_half, sc_half + 7u * 1024u, sh_half + 7u * 1024u, tab + kFWR + half * 128, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+            }
+            tc_fence_before();
             if (half == 1)
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part), "f"(rgb0), "f"(rgb1), "f"(rgb2), "f"(sigma) : "memory");
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");

@@ -15,22 +15,28 @@ struct Cam {
 
 // Each op is rounded separately (numpy evaluates mul / sum as separate float32 ufuncs, no FMA):
 // dirs = [(i - W/2)/f, -(j - H/2)/f, -1];  d_k = sum_m dirs_m * R[k,m]  (left-to-right)
+// one thread per output float: element e = ray*6 + c, c < 3 origin, c >= 3 direction component (coalesced stores)
 __global__ void raygen_f32_kernel(Cam<float> cam, int width, float half_w, float half_h, float focal,
                                   long long begin, long long count, float* __restrict__ rays) {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    long long pix = begin + t;
-    float i = (float)(pix % width), j = (float)(pix / width);
-    float dx = __fdiv_rn(__fsub_rn(i, half_w), focal);
-    float dy = __fdiv_rn(-__fsub_rn(j, half_h), focal);
-    float dz = -1.0f;
-    float* out = rays + t * 6;
-    out[0] = cam.t[0]; out[1] = cam.t[1]; out[2] = cam.t[2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float s = __fadd_rn(__fmul_rn(dx, cam.r[3 * k + 0]), __fmul_rn(dy, cam.r[3 * k + 1]));
-        out[3 + k] = __fadd_rn(s, __fmul_rn(dz, cam.r[3 * k + 2]));
+    long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e >= count * 6) return;
+    long long t = e / 6;
+    int c = (int)(e - t * 6);
+    float v;
+    if (c < 3) v = c == 0 ? cam.t[0] : (c == 1 ? cam.t[1] : cam.t[2]);
+    else {
+        long long pix = begin + t;
+        float i = (float)(pix % width), j = (float)(pix / width);
+        float dx = __fdiv_rn(__fsub_rn(i, half_w), focal);
+        float dy = __fdiv_rn(-__fsub_rn(j, half_h), focal);
+        int k = c - 3;
+        float r0 = k == 0 ? cam.r[0] : (k == 1 ? cam.r[3] : cam.r[6]);
+        float r1 = k == 0 ? cam.r[1] : (k == 1 ? cam.r[4] : cam.r[7]);
+        float r2 = k == 0 ? cam.r[2] : (k == 1 ? cam.r[5] : cam.r[8]);
+        float s = __fadd_rn(__fmul_rn(dx, r0), __fmul_rn(dy, r1));
+        v = __fadd_rn(s, __fmul_rn(-1.0f, r2));
     }
+    rays[e] = v;
 }
 
 // np.float64 focal (pi_GAN/modules.py:127): (i - W/2) is still float32, the division and
@@ -76,6 +82,23 @@ __global__ void stratified_kernel(const float* __restrict__ z_lin, const float* 
     }
     __syncthreads();
     long long stride = (long long)gridDim.x * blockDim.x;
+    if ((sc & 3) == 0 && ((((uintptr_t)t_rand) | ((uintptr_t)z_out)) & 15) == 0) {
+        // 16-byte path: 4 consecutive samples of one ray per thread-iteration
+        const float4* t4 = reinterpret_cast<const float4*>(t_rand);
+        float4* z4 = reinterpret_cast<float4*>(z_out);
+        const long long total4 = total >> 2;
+        const int sc4 = sc >> 2;
+        for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total4; e += stride) {
+            const int k = (int)(e % sc4) * 4;
+            float4 t = t4[e], o;
+            o.x = __fadd_rn(lower[k + 0], __fmul_rn(span[k + 0], t.x));
+            o.y = __fadd_rn(lower[k + 1], __fmul_rn(span[k + 1], t.y));
+            o.z = __fadd_rn(lower[k + 2], __fmul_rn(span[k + 2], t.z));
+            o.w = __fadd_rn(lower[k + 3], __fmul_rn(span[k + 3], t.w));
+            z4[e] = o;
+        }
+        return;
+    }
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += stride) {
         int k = (int)(e % sc);
         z_out[e] = __fadd_rn(lower[k], __fmul_rn(span[k], t_rand[e]));
@@ -106,7 +129,8 @@ extern "C" int b2r_raygen(const double* c2w_host, int width, int height, double 
     if (compute_f64)
         raygen_f64_kernel<<<(unsigned)grid, block, 0, st>>>(cam, width, half_w, half_h, focal, compute_f64 & 1, ray_begin, ray_count, rays_out);
     else
-        raygen_f32_kernel<<<(unsigned)grid, block, 0, st>>>(camf, width, half_w, half_h, (float)focal, ray_begin, ray_count, rays_out);
+        raygen_f32_kernel<<<(unsigned)((ray_count * 6 + block - 1) / block), block, 0, st>>>(camf, width, half_w, half_h, (float)focal, ray_begin,
+                                                                                            ray_count, rays_out);
     B2R_LAUNCH_CHECK("b2r_raygen");
     return 0;
 }
