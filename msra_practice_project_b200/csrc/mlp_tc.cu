@@ -292,7 +292,8 @@ __device__ __forceinline__ void relay_loop(const Ctx& cx, const PairLoop& pl, in
     }
 }
 
-// MMA issuer: one thread of the leader CTA; alternates the two sub-tiles step by step
+// MMA issuer: warp 1 of the leader CTA, converged (every lane walks the schedule and polls the barriers; one elected
+// lane issues), so the descriptors live in uniform registers.  Alternates the two sub-tiles step by step.
 template <class S>
 __device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, const PairLoop& pl, int n_steps, int flag) {
     uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0;
@@ -303,9 +304,12 @@ __device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, cons
         const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
         const uint64_t ad = d_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
         const uint64_t bd = d_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
-        mma_bf16_2cta(d_tmem, ad, bd, idesc, accumulate);
-        for (int k = 1; k < n_mma; ++k) mma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);   // +32 B = next 16 K
-        mma_commit_2cta(cx.w_empty + 8 * stage, (uint16_t)3);
+        if (elect_one()) {
+            mma_bf16_2cta(d_tmem, ad, bd, idesc, accumulate);
+            for (int k = 1; k < n_mma; ++k) mma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);   // +32 B = next 16 K
+            mma_commit_2cta(cx.w_empty + 8 * stage, (uint16_t)3);
+        }
+        __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1u; }
     };
     for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
@@ -320,9 +324,13 @@ __device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, cons
                 const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
                 uint32_t acc = 0;
                 for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base, idesc, acc, 4); acc = 1; }
-                for (int c = 0; c < n_h; ++c) { issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)c * 16384u, idesc, acc, 4); acc = 1; }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < n_h) { issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)c * 16384u, idesc, acc, 4); acc = 1; }
+                }
                 for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u, S::kPostMmas);
-                mma_commit_2cta(cx.acc_full + 8 * g, (uint16_t)3);
+                if (elect_one()) mma_commit_2cta(cx.acc_full + 8 * g, (uint16_t)3);
+                __syncwarp();
             }
         }
     }
@@ -456,10 +464,8 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     if (warp == 0) {
         if (lane == 0) producer_loop<NerfSched>(cx, packed, pl, NerfSched::kSteps, 0);
     } else if (warp == 1) {
-        if (lane == 0) {
-            if (cx.rank == 0) mma_loop<NerfSched>(cx, tmem_base, pl, NerfSched::kSteps, 0);
-            else relay_loop<NerfSched>(cx, pl, NerfSched::kSteps, 0);
-        }
+        if (cx.rank == 0) mma_loop<NerfSched>(cx, tmem_base, pl, NerfSched::kSteps, 0);
+        else if (lane == 0) relay_loop<NerfSched>(cx, pl, NerfSched::kSteps, 0);
     } else if (warp >= kCtrlWarps) {
         // ===== input generation + epilogue =====
         // warp = 4 + g*8 + half*4 + quad;  thread = row (quad*32 + lane) of sub-tile g = TMEM lane;
@@ -644,10 +650,8 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     if (warp == 0) {
         if (lane == 0) producer_loop<FilmSched>(cx, packed, pl, n_steps, use_dir);
     } else if (warp == 1) {
-        if (lane == 0) {
-            if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, use_dir);
-            else relay_loop<FilmSched>(cx, pl, n_steps, use_dir);
-        }
+        if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, use_dir);
+        else if (lane == 0) relay_loop<FilmSched>(cx, pl, n_steps, use_dir);
     } else if (warp >= kCtrlWarps) {
         const int ew = warp - kCtrlWarps;
         const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;

@@ -138,6 +138,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 
 
+// one elected lane of a converged warp (warp-uniform predicate: lets ptxas keep MMA operands in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- thread-block cluster / CTA-pair (cta_group::2) primitives ---------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

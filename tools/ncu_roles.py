@@ -2,9 +2,11 @@
 """Compact role-level view of an ncu source page of the fused MLP kernel: mbarrier waits (spin counts) and MMA issue."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
-hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
+his = [i for i, r in enumerate(rows) if r and r[0] == 'Address']
+hi = his[0]
+end = his[1] - 1 if len(his) > 1 else len(rows)
 hdr = rows[hi]; ix = {h: i for i, h in enumerate(hdr)}
-data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+data = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
 num = lambda x: int(float(x)) if x not in ('', None) else 0
 tot = sum(num(r[ix['# Samples']]) for r in data)
 print('total samples', tot)
