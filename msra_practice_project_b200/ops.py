@@ -97,9 +97,10 @@ class _Composite(torch.autograd.Function):
         depth = torch.empty((n,), dtype=torch.float32, device=dev)
         acc = torch.empty((n,), dtype=torch.float32, device=dev)
         w = torch.empty((n, s), dtype=torch.float32, device=dev) if want_weights else None
-        with torch.cuda.device(dev):
-            check(lib().b2r_composite_fwd(ptr(raw), ptr(z), dptr, dstride, n, s, ptr(rgb), ptr(depth), ptr(acc), ptr(w),
-                                          _stream(z)), "b2r_composite_fwd")
+        if n > 0:
+            with torch.cuda.device(dev):
+                check(lib().b2r_composite_fwd(ptr(raw), ptr(z), dptr, dstride, n, s, ptr(rgb), ptr(depth), ptr(acc), ptr(w),
+                                              _stream(z)), "b2r_composite_fwd")
         ctx.save_for_backward(raw, z, keep)
         ctx.dstride = dstride
         if w is None:
@@ -115,6 +116,8 @@ class _Composite(torch.autograd.Function):
         g_depth = None if g_depth is None else _cuda_f32(g_depth, "g_depth")
         g_acc = None if g_acc is None else _cuda_f32(g_acc, "g_acc")
         d_raw = torch.empty_like(raw)
+        if n == 0:
+            return d_raw, None, None, None
         with torch.cuda.device(z.device):
             check(lib().b2r_composite_bwd(ptr(raw), ptr(z), keep.data_ptr(), ctx.dstride, n, s, ptr(g_rgb), ptr(g_depth),
                                           ptr(g_acc), ptr(d_raw), _stream(z)), "b2r_composite_bwd")
@@ -154,7 +157,7 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: tor
     if b.shape[-1] != nb:
         raise RuntimeError(f"bins has {b.shape[-1]} entries, expected len(weights)+1 = {nb}")
     if u is None:
-        u = torch.linspace(0.0, 1.0, steps=int(n_samples)).to(dev)       # host-made: its rounding is a contract
+        u = torch.linspace(0.0, 1.0, steps=int(n_samples), device="cpu").to(dev)   # host-made: its rounding is a contract
     u = _cuda_f32(u, "u")
     sf = int(n_samples)
     samples = torch.empty((n, sf), dtype=torch.float32, device=dev) if want_samples else None
@@ -164,6 +167,8 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: tor
         zc = _cuda_f32(z_coarse.detach(), "z_coarse")
         sc = zc.shape[1]
         merged = torch.empty((n, sc + sf), dtype=torch.float32, device=dev)
+    if n == 0:
+        return {"samples": samples, "sorted": merged, "cdf": cdf}
     with torch.cuda.device(dev):
         check(lib().b2r_sample_pdf(ptr(b), b_stride, weights.data_ptr(), weights.stride(0), ptr(u), n, nb, sf, ptr(zc), sc,
                                    ptr(samples), ptr(merged), ptr(cdf), _stream(weights)), "b2r_sample_pdf")
@@ -288,6 +293,8 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
         return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x)
     inp, rows, keep = _make_input(rays, z, x, grid)
     raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+    if rows == 0:
+        return raw
     with torch.cuda.device(dev):
         if precision == "bf16":
             packed = _packed_weights(net, kind, flat, film, use_dir)

@@ -427,3 +427,97 @@ def test_non_cuda_inputs_fail_loudly():
         ops.composite(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3))
     with pytest.raises(TypeError):
         ops.mlp(torch.nn.Linear(6, 4).cuda(), x=torch.zeros(4, 6).cuda())
+
+
+# ---- full-size property tests (BASELINE.json configs[1]: 800x800, 64+128) ---------------------------------------
+def test_full_size_render_properties():
+    """Size-independent properties at the headline size: sortedness / sub-sequence of the merged samples, weights sum to
+    acc, ranges, determinism, sharded == slice of the full frame, white-background linearity of the composite."""
+    torch.manual_seed(0)
+    c, f = models.NeRF().cuda(), models.NeRF().cuda()
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+    W = H = 800
+    n = W * H
+    torch.manual_seed(5)
+    t = torch.rand(n, 64, device="cuda")
+    rays = ops.raygen(W, H, W * 1.3875, pose)
+    st = {}
+    with torch.no_grad():
+        out = nerf_render.render_rays(rays, 2.0, 6.0, c, f, 64, 128, t_rand=t, stages=st)
+        out2 = nerf_render.render_rays(rays, 2.0, 6.0, c, f, 64, 128, t_rand=t)
+    assert all(torch.equal(a, b) for a, b in zip(out, out2)), "render is not deterministic"
+    zc, zf, zs = st["z_coarse"], st["z_fine"], st["z_samples"]
+    assert zf.shape == (n, 192) and bool((zf[:, 1:] >= zf[:, :-1]).all())                  # sorted
+    assert bool((zc[:, 1:] >= zc[:, :-1]).all()) and bool((zs[:, 1:] >= zs[:, :-1]).all())
+    assert torch.equal(torch.sort(torch.cat([zc, zs], -1), -1).values, zf)                  # exactly the merged multiset
+    mids = st["mids"]
+    assert float(zs.min()) >= float(mids[0]) - 1e-6 and float(zs.max()) <= float(mids[-1]) + 1e-6
+    wc = st["weights_coarse"]
+    assert torch.allclose(wc.sum(-1), out[2], atol=1e-5) and float(out[2].max()) <= 1.0 + 1e-4 and float(wc.min()) >= 0.0
+    for rgb in (out[0], out[3]):
+        assert float(rgb.min()) >= -1e-4 and float(rgb.max()) <= 1.0 + 1e-4 and bool(torch.isfinite(rgb).all())
+    assert bool((out[4] >= 0).all()) and float(out[4].max()) <= 6.0 * 1.3                    # depth <= far * |d|max
+    # a pixel-row shard renders exactly the slice of the full frame (what multi-GPU sharding relies on)
+    b0, cnt = 800 * 300, 800 * 100
+    with torch.no_grad():
+        part = nerf_render.render_image_device(W, H, W * 1.3875, pose, 2.0, 6.0, c, f, 64, 128, ray_begin=b0, ray_count=cnt,
+                                               t_rand=t[b0:b0 + cnt])
+    assert all(torch.equal(p, o[b0:b0 + cnt]) for p, o in zip(part, out))
+    # composite: rgb_map - (1 - acc) is linear in the sample colours
+    raw = st["raw_fine"][:50000].clone()
+    z, d = zf[:50000], rays[:50000, 1]
+    r1 = ops.composite(raw, z, d, want_weights=False)
+    raw2 = raw.clone(); raw2[..., :3] *= 0.5
+    r2 = ops.composite(raw2, z, d, want_weights=False)
+    lin1 = r1[0] - (1 - r1[2])[:, None]; lin2 = r2[0] - (1 - r2[2])[:, None]
+    assert torch.allclose(lin2, 0.5 * lin1, atol=2e-6) and torch.equal(r1[1], r2[1]) and torch.equal(r1[2], r2[2])
+
+
+def test_edge_shapes():
+    """N == 1 (crashes the reference), float sample counts, tiny sample counts, empty input."""
+    c, f = seeded_nerf()
+    rays = torch.tensor([[[0.0, 0.0, 4.0], [0.05, -0.02, -1.0]]], device="cuda")
+    with torch.no_grad():
+        out = nerf_render.render_rays(rays, 2.0, 6.0, c, f, 64.0, 128.0)             # float counts (test_nerf.py:34-35)
+        assert out[3].shape == (1, 3) and bool(torch.isfinite(out[3]).all())
+        out = nerf_render.render_rays(rays.expand(5, 2, 3).contiguous(), 2.0, 6.0, c, f, 4, 3)
+        assert out[0].shape == (5, 3)
+        empty = ops.mlp(c, x=torch.zeros(0, 6, device="cuda"))
+        assert empty.shape == (0, 4)
+    r = ops.composite(torch.zeros(0, 7, 4, device="cuda"), torch.zeros(0, 7, device="cuda"), torch.zeros(0, 3, device="cuda"))
+    assert r[0].shape == (0, 3)
+
+
+def test_drop_in_usage_like_the_reference_scripts():
+    """The way nerf/train_nerf.py and show_nerf.py use the module: CUDA default tensor type, star import, render_image to
+    numpy, then a training step (render_rays + MSE + backward + Adam, train_nerf.py:151-168) on the same models."""
+    torch.set_default_tensor_type('torch.cuda.FloatTensor')                       # nerf/train_nerf.py:11
+    try:
+        ns = {}
+        exec("from msra_practice_project_b200.nerf_render import *", ns)          # `from render import *`
+        for name in ("np", "torch", "tqdm", "to8b", "get_rays", "sample_pdf", "run_network", "raw_to_outputs", "render_rays",
+                     "render_image", "render_video"):
+            assert name in ns, name
+        torch.manual_seed(0)
+        coarse, fine = models.NeRF(), models.NeRF()                                # created on the default (CUDA) device
+        pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.1, -0.5)
+        with torch.no_grad():
+            rgb, depth, acc = ns["render_image"](40, 30, 40 * 1.3875, pose, 2.0, 6.0, coarse, fine, 64, 128)
+        assert rgb.shape == (30, 40, 3) and depth.shape == (30, 40, 1) and acc.shape == (30, 40, 1) and rgb.dtype == np.float32
+        img8 = ns["to8b"](rgb)
+        assert img8.dtype == np.uint8
+        vid = ns["render_video"](8, 6, 8 * 1.3875, [pose, pose], 2.0, 6.0, coarse, fine, 8, 8)
+        assert vid[0].shape == (2, 6, 8, 3)
+        opt = torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()), lr=5e-4)
+        rays = torch.tensor(np.stack(ns["get_rays"](16, 16, 16 * 1.3875, pose), 0).transpose(1, 2, 0, 3).reshape(-1, 2, 3))
+        target = torch.rand(256, 3)
+        losses = []
+        for _ in range(3):
+            rc, _, _, rf, _, _ = ns["render_rays"](rays, 2.0, 6.0, coarse, fine, 16, 16)
+            loss = torch.mean((rf - target) ** 2) + torch.mean((rc - target) ** 2)
+            opt.zero_grad(); loss.backward(); opt.step()
+            losses.append(float(loss.detach()))
+        assert all(np.isfinite(losses)) and all(p.grad is not None for p in coarse.parameters())
+    finally:
+        torch.set_default_tensor_type(torch.FloatTensor)
+        torch.set_default_device("cpu")
