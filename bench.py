@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--coarse", type=int, default=64)
     ap.add_argument("--fine", type=int, default=128)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--grad-precision", default="tf32", choices=["fp32", "tf32"], help="GEMM engine of the training config")
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid"],
@@ -365,6 +366,7 @@ def run_secondary(args):
         opt = torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()), lr=5e-4)
         pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
         from msra_practice_project_b200 import ops
+        ops.set_grad_precision(args.grad_precision)
         rays = ops.raygen(800, 800, 800 * 1.3875, pose, 320000 + b, c, device=dev)
         torch.manual_seed(1)
         target = torch.rand((n_batch, 3), device=dev)[b:b + c]
@@ -381,10 +383,11 @@ def run_secondary(args):
         ms = timed(step, args.steps, args.warmup)
         rows = n_batch * (2 * sc + sf)
         line = dict(metric="rays/s, NeRF training step (4096-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
-                    unit="rays/s", ms_per_step=ms, dtype="f32", scaling="strong",
-                    config=dict(workload="NeRF train step, 4096 rays sharded over ranks, fp32 CUDA-core MLP forward with saved activations + "
-                                         "CUDA reverse mode, one NCCL all-reduce of the 4.75 MB gradient bucket, torch Adam"),
-                    tflops_fp32=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
+                    unit="rays/s", ms_per_step=ms, dtype="tf32" if args.grad_precision == "tf32" else "f32", scaling="strong",
+                    config=dict(workload="NeRF train step, 4096 rays sharded over ranks, layer-wise MLP forward with saved fp32 activations + "
+                                         f"CUDA reverse mode, GEMMs in {args.grad_precision}, one NCCL all-reduce of the 4.75 MB gradient bucket, "
+                                         "torch Adam"),
+                    tflops=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
     elif args.config == "pigan":
         n_lat, res, s_ = 64, 128, 24
         b, c = shard.shard_range(n_lat, rank, world)

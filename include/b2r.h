@@ -114,16 +114,18 @@ typedef struct b2r_mlp_input {
  * bytes; with save_activations != 0 the workspace holds every layer's output afterwards and is
  * the `saved` argument of b2r_mlp_f32_bwd.  use_dir: FilmSirenNeRF(use_dir=...) flag. */
 size_t b2r_mlp_f32_workspace_bytes(int model_kind, long long rows, int save_activations);
+/* gemm_mode: 0 = fp32 FMAs on the CUDA cores (exact: the fp32 parity path), 1 = the same layer-wise algorithm with the
+ * GEMMs on the tensor cores in TF32 (tcgen05 kind::tf32, fp32 accumulate; ~1e-3 relative: the fast training path). */
 int b2r_mlp_f32_fwd(int model_kind, const float* params, const float* film, int use_dir,
                     const b2r_mlp_input* in, float* raw_out, void* workspace, size_t workspace_bytes,
-                    int save_activations, void* stream);
+                    int save_activations, int gemm_mode, void* stream);
 /* backward of the fp32 path: d_raw[rows,4] -> d_params (flat, ACCUMULATED into: caller zeroes),
  * d_film[9,512] (FiLM only, accumulated, nullable).  saved = workspace of the forward call made with
  * save_activations=1 on the same inputs; scratch = b2r_mlp_f32_bwd_scratch_bytes(kind, rows). */
 size_t b2r_mlp_f32_bwd_scratch_bytes(int model_kind, long long rows);
 int b2r_mlp_f32_bwd(int model_kind, const float* params, const float* film, int use_dir,
                     const b2r_mlp_input* in, const float* raw, const float* d_raw, const void* saved,
-                    void* scratch, size_t scratch_bytes, float* d_params, float* d_film, void* stream);
+                    void* scratch, size_t scratch_bytes, float* d_params, float* d_film, int gemm_mode, void* stream);
 
 /* bf16 tensor-core path (tcgen05 / TMEM, weights streamed by the TMA bulk-copy engine).
  * packed: b2r_mlp_tc_packed_bytes(kind) bytes produced by b2r_mlp_tc_pack from the flat fp32

@@ -39,10 +39,10 @@ SIGNATURES = {
                                  c_float_p, c_float_p, c_float_p, C.c_void_p]),
     "b2r_mlp_f32_workspace_bytes": (C.c_size_t, [C.c_int, c_ll, C.c_int]),
     "b2r_mlp_f32_fwd": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_void_p,
-                                  C.c_size_t, C.c_int, C.c_void_p]),
+                                  C.c_size_t, C.c_int, C.c_int, C.c_void_p]),
     "b2r_mlp_f32_bwd_scratch_bytes": (C.c_size_t, [C.c_int, c_ll]),
     "b2r_mlp_f32_bwd": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.POINTER(MlpInput), c_float_p, c_float_p,
-                                  C.c_void_p, C.c_void_p, C.c_size_t, c_float_p, c_float_p, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_size_t, c_float_p, c_float_p, C.c_int, C.c_void_p]),
     "b2r_mlp_tc_packed_bytes": (C.c_size_t, [C.c_int]),
     "b2r_mlp_tc_pack": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p]),
     "b2r_mlp_tc_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_int, C.c_void_p]),

@@ -9,6 +9,7 @@
 //   backward               autograd in the reference (nerf/train_nerf.py:167, pi_GAN/train.py:134,
 //                          pi_GAN/synthesis.py:107); formulas SURVEY.md A.5 / A.6
 #include "sgemm.cuh"
+#include "tgemm.cuh"
 
 namespace b2r {
 
@@ -212,6 +213,17 @@ __global__ void __launch_bounds__(256) film_act_bwd_kernel(float* __restrict__ d
     if (d_gamma) { atomicAdd(d_gamma + j, 30.0f * sg); atomicAdd(d_beta + j, 30.0f * sb); }
 }
 
+// GEMM engine of the current call on this host thread: 0 = fp32 CUDA cores (exact), 1 = tf32 tensor cores (tgemm.cuh).
+// thread_local, set at every API entry: the library stays re-entrant (nn.DataParallel calls it from one thread per GPU).
+static thread_local int t_gemm_mode = 0;
+
+template <bool kPT, bool kQT>
+static int launch_gemm(GemmArgs g, cudaStream_t st, const char* what) {
+    // tiny reductions (K = 3 input layer) stay on the CUDA cores
+    if (t_gemm_mode == 1 && g.R >= 16) return tg::launch_tgemm<kPT, kQT>(g, st, what);
+    return launch_sgemm<kPT, kQT>(g, st, what);
+}
+
 // ---- helpers ------------------------------------------------------------------------------------
 struct Lin { const float* W; const float* b; int out, in; };
 static inline Lin lin(const float* params, LayerDesc d) { return Lin{params + d.w_off, params + d.b_off, d.out, d.in}; }
@@ -223,7 +235,7 @@ static int fwd_layer(const float* X, long long ldx, Lin L, int k_off, int K, flo
     g.P = X; g.ldp = ldx; g.Q = L.W + k_off; g.ldq = L.in; g.C = Y; g.ldc = ldy;
     g.I = rows; g.J = L.out; g.R = K; g.r_chunk = K; g.epi = epi; g.bias = L.b;
     g.gamma = gamma; g.beta = beta; g.pre = pre; g.ldpre = 256;
-    return launch_sgemm<false, false>(g, st, "mlp_f32 forward gemm");
+    return launch_gemm<false, false>(g, st, "mlp_f32 forward gemm");
 }
 // dX = G W[:, k_off:k_off+K]  (optionally += existing, optionally relu-masked by `mask`)
 static int dgrad_layer(const float* G, long long ldg, Lin L, int k_off, int K, float* dX, long long lddx, long long rows,
@@ -232,15 +244,15 @@ static int dgrad_layer(const float* G, long long ldg, Lin L, int k_off, int K, f
     g.P = G; g.ldp = ldg; g.Q = L.W + k_off; g.ldq = L.in; g.C = dX; g.ldc = lddx;
     g.I = rows; g.J = K; g.R = L.out; g.r_chunk = L.out; g.epi = EPI_DGRAD;
     g.mask = mask; g.ldmask = ldmask; g.accumulate = accumulate;
-    return launch_sgemm<false, true>(g, st, "mlp_f32 dgrad gemm");
+    return launch_gemm<false, true>(g, st, "mlp_f32 dgrad gemm");
 }
 // dW += G^T X ; db += colsum(G)
 static int wgrad_layer(const float* G, long long ldg, const float* X, long long ldx, LayerDesc d, float* d_params,
                        long long rows, cudaStream_t st) {
     GemmArgs g{};
     g.P = G; g.ldp = ldg; g.Q = X; g.ldq = ldx; g.C = d_params + d.w_off; g.ldc = d.in;
-    g.I = d.out; g.J = d.in; g.R = rows; g.r_chunk = 2048; g.epi = EPI_ATOMIC;
-    int rc = launch_sgemm<true, true>(g, st, "mlp_f32 wgrad gemm");
+    g.I = d.out; g.J = d.in; g.R = rows; g.r_chunk = t_gemm_mode == 1 ? 8192 : 2048; g.epi = EPI_ATOMIC;
+    int rc = launch_gemm<true, true>(g, st, "mlp_f32 wgrad gemm");
     if (rc) return rc;
     int rpc = 512;
     unsigned grid = (unsigned)((rows + rpc - 1) / rpc);
@@ -319,8 +331,10 @@ extern "C" size_t b2r_mlp_f32_workspace_bytes(int model_kind, long long rows, in
 
 extern "C" int b2r_mlp_f32_fwd(int model_kind, const float* params, const float* film, int use_dir,
                                const b2r_mlp_input* in, float* raw_out, void* workspace, size_t workspace_bytes,
-                               int save_activations, void* stream) {
+                               int save_activations, int gemm_mode, void* stream) {
     using namespace b2r;
+    B2R_CHECK_ARG(gemm_mode == 0 || gemm_mode == 1, "b2r_mlp_f32_fwd: gemm_mode must be 0 (fp32) or 1 (tf32)");
+    t_gemm_mode = gemm_mode;
     B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM, "b2r_mlp_f32_fwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(params && raw_out && workspace, "b2r_mlp_f32_fwd: NULL pointer");
     B2R_CHECK_ARG(model_kind != B2R_MODEL_FILM || film, "b2r_mlp_f32_fwd: FiLM model needs film params");
@@ -353,8 +367,10 @@ extern "C" size_t b2r_mlp_f32_bwd_scratch_bytes(int model_kind, long long rows) 
 
 extern "C" int b2r_mlp_f32_bwd(int model_kind, const float* params, const float* film, int use_dir,
                                const b2r_mlp_input* in, const float* raw, const float* d_raw, const void* saved,
-                               void* scratch, size_t scratch_bytes, float* d_params, float* d_film, void* stream) {
+                               void* scratch, size_t scratch_bytes, float* d_params, float* d_film, int gemm_mode, void* stream) {
     using namespace b2r;
+    B2R_CHECK_ARG(gemm_mode == 0 || gemm_mode == 1, "b2r_mlp_f32_bwd: gemm_mode must be 0 (fp32) or 1 (tf32)");
+    t_gemm_mode = gemm_mode;
     B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM, "b2r_mlp_f32_bwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(params && raw && d_raw && saved && scratch, "b2r_mlp_f32_bwd: NULL pointer");
     B2R_CHECK_ARG(d_params || d_film, "b2r_mlp_f32_bwd: nothing to differentiate (d_params and d_film are NULL)");

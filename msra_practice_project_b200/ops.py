@@ -23,14 +23,31 @@ _MLP_PRECISION = "bf16"
 
 def set_mlp_precision(p: str) -> str:
     global _MLP_PRECISION
-    if p not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if p not in ("bf16", "fp32", "tf32"):
+        raise ValueError("precision must be 'bf16', 'fp32' or 'tf32'")
     old, _MLP_PRECISION = _MLP_PRECISION, p
     return old
 
 
 def get_mlp_precision() -> str:
     return _MLP_PRECISION
+
+
+# GEMM engine of the layer-wise path used whenever gradients are required: "fp32" = CUDA-core FMAs (exact: the parity
+# path, default), "tf32" = the same algorithm with every GEMM on the tensor cores (tcgen05 kind::tf32, fp32 accumulate).
+_GRAD_PRECISION = "fp32"
+
+
+def set_grad_precision(p: str) -> str:
+    global _GRAD_PRECISION
+    if p not in ("fp32", "tf32"):
+        raise ValueError("grad precision must be 'fp32' or 'tf32'")
+    old, _GRAD_PRECISION = _GRAD_PRECISION, p
+    return old
+
+
+def get_grad_precision() -> str:
+    return _GRAD_PRECISION
 
 
 def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -225,15 +242,16 @@ class _MlpF32(torch.autograd.Function):
     """fp32 forward that keeps every layer's output, and its reverse mode (K8)."""
 
     @staticmethod
-    def forward(ctx, flat, film, kind, use_dir, rays, z, x):
+    def forward(ctx, flat, film, kind, use_dir, rays, z, x, gemm_mode):
         inp, rows, keep = _make_input(rays, z, x, None)
+        ctx.gemm_mode = gemm_mode
         dev = flat.device
         raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
         ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, rows, 1)
         ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             check(lib().b2r_mlp_f32_fwd(kind, ptr(flat), ptr(film), int(use_dir), C.byref(inp), ptr(raw), ptr(ws), ws_bytes, 1,
-                                        _stream(flat)), "b2r_mlp_f32_fwd")
+                                        gemm_mode, _stream(flat)), "b2r_mlp_f32_fwd")
         ctx.kind, ctx.use_dir, ctx.rows = kind, use_dir, rows
         ctx.keep = keep
         ctx.has_film = film is not None
@@ -255,14 +273,14 @@ class _MlpF32(torch.autograd.Function):
         d_flat = torch.zeros_like(flat) if need_w else None
         d_film = torch.zeros_like(film) if need_f else None
         if d_flat is None and d_film is None:
-            return (None,) * 7
+            return (None,) * 8
         sc_bytes = lib().b2r_mlp_f32_bwd_scratch_bytes(ctx.kind, rows)
         scratch = torch.empty((max(sc_bytes, 16) // 4,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             check(lib().b2r_mlp_f32_bwd(ctx.kind, ptr(flat), ptr(film), int(ctx.use_dir), C.byref(inp), ptr(raw), ptr(d_raw),
-                                        ptr(ws), ptr(scratch), sc_bytes, ptr(d_flat), ptr(d_film), _stream(flat)),
+                                        ptr(ws), ptr(scratch), sc_bytes, ptr(d_flat), ptr(d_film), ctx.gemm_mode, _stream(flat)),
                   "b2r_mlp_f32_bwd")
-        return d_flat, d_film, None, None, None, None, None
+        return d_flat, d_film, None, None, None, None, None, None
 
 
 def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, x: torch.Tensor | None = None,
@@ -290,7 +308,7 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
     if needs_grad:
         if grid is not None:
             raise RuntimeError("grid queries are inference-only")
-        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x)
+        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, 1 if _GRAD_PRECISION == "tf32" else 0)
     inp, rows, keep = _make_input(rays, z, x, grid)
     raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     if rows == 0:
@@ -304,7 +322,7 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
             ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, rows, 0)
             ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=dev)
             check(lib().b2r_mlp_f32_fwd(kind, ptr(flat), ptr(film), int(use_dir), C.byref(inp), ptr(raw), ptr(ws), ws_bytes, 0,
-                                        _stream(flat)), "b2r_mlp_f32_fwd")
+                                        1 if precision == "tf32" else 0, _stream(flat)), "b2r_mlp_f32_fwd")
     del keep
     return raw
 

@@ -12,6 +12,14 @@
 
 using namespace b2r::umma;
 
+__device__ __forceinline__ void mma_any(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
 struct Variant { uint32_t a_layout, a_sbo, b_layout, b_sbo, use_bulk; };
 
 __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* a_img, const uint8_t* b_img, Variant v, float* d_out) {
@@ -113,6 +121,84 @@ probe2_kernel(const uint8_t* a_img /*2 x 16 KB*/, const uint8_t* b_img /*2 x 16 
     if (warp == 0) tmem_dealloc_2cta(tmem, 256);
 }
 
+// ---- tf32 probe: D[128,256] = A[128,32] * B[256,32]^T with kind::tf32, operands K-major (kmaj=1) or MN-major (kmaj=0) ----
+// MN-major SWIZZLE_128B tile: [mn group of 32][k row][128 B]; LBO = rows_k * 128 (next MN group), SBO = 1024 (next 8 k rows)
+__global__ void __launch_bounds__(128, 1) probe3_kernel(const uint8_t* a_img, const uint8_t* b_img, int kmaj, float* d_out) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* gen = raw + (base - smem_u32(raw));
+    const uint32_t a_s = base, b_s = base + 16384, bar = base + 16384 + 32768, slot = bar + 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(slot, 256);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    uint32_t tmem; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+    for (int i = threadIdx.x; i < 16384 / 16; i += 128) reinterpret_cast<uint4*>(gen)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+    for (int i = threadIdx.x; i < 32768 / 16; i += 128) reinterpret_cast<uint4*>(gen + 16384)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_fence_after();
+        // idesc: D f32 (1<<4), A/B tf32 (2<<7, 2<<10), majors bits 15/16, N>>3 at 17, M>>4 at 24
+        uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+        if (!kmaj) idesc |= (1u << 15) | (1u << 16);
+        for (int k = 0; k < 4; ++k) {      // 4 x K=8
+            uint64_t ad, bd;
+            if (kmaj) { ad = make_desc(a_s + k * 32, 16, 1024, 2); bd = make_desc(b_s + k * 32, 16, 1024, 2); }
+            else { ad = make_desc(a_s + k * 1024, 4096, 1024, 2); bd = make_desc(b_s + k * 1024, 4096, 1024, 2); }
+            mma_any(tmem, ad, bd, idesc, k != 0);
+        }
+        mma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    for (int j = 0; j < 8; ++j) {
+        uint32_t x[32];
+        tmem_ld32(tmem + ((uint32_t)warp << 21) + j * 32, x);
+        tmem_ld_wait();
+        for (int e = 0; e < 32; ++e) d_out[r * 256 + j * 32 + e] = __uint_as_float(x[e]);
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static int run_probe3(int kmaj) {
+    const int M = 128, N = 256, K = 32;
+    std::vector<float> A(M * K), B(N * K), D(M * N);
+    srand(11 + kmaj);
+    for (auto& x : A) x = (float)(rand() % 9 - 4);
+    for (auto& x : B) x = (float)(rand() % 7 - 3);
+    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < K; ++k) s += A[m * K + k] * B[n * K + k]; D[m * N + n] = s; }
+    std::vector<uint8_t> a_img(16384), b_img(32768);
+    auto put = [&](std::vector<uint8_t>& img, int mn, int k, float v) {
+        uint32_t off;
+        if (kmaj) off = sw128_offset(mn, k / 4) + (k % 4) * 4;                                   // row = mn, 32 k per 128 B row
+        else { int g = mn / 32, w = mn % 32; off = g * 4096 + k * 128 + (((w / 4) ^ (k & 7)) << 4) + (w % 4) * 4; }
+        memcpy(&img[off], &v, 4);
+    };
+    for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) put(a_img, m, k, A[m * K + k]);
+    for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) put(b_img, n, k, B[n * K + k]);
+    uint8_t *da, *db; float* dd;
+    cudaMalloc(&da, 16384); cudaMalloc(&db, 32768); cudaMalloc(&dd, M * N * 4);
+    cudaMemcpy(da, a_img.data(), 16384, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, b_img.data(), 32768, cudaMemcpyHostToDevice);
+    cudaMemset(dd, 0xff, M * N * 4);
+    cudaFuncSetAttribute(probe3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    probe3_kernel<<<1, 128, 64 * 1024>>>(da, db, kmaj, dd);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("PROBE3 tf32 %s : CUDA error %s\n", kmaj ? "K-major" : "MN-major", cudaGetErrorString(e)); return 2; }
+    std::vector<float> got(M * N);
+    cudaMemcpy(got.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
+    int bad = 0, first = -1;
+    for (int i = 0; i < M * N; ++i) if (got[i] != D[i]) { if (first < 0) first = i; ++bad; }
+    printf("PROBE3 kind::tf32 %s operands : mismatches %d / %d", kmaj ? "K-major " : "MN-major", bad, M * N);
+    if (bad) printf("  first at (m=%d,n=%d) got %g want %g", first / N, first % N, got[first], D[first]);
+    printf("\n%s\n", bad ? "PROBE3 FAILED" : "PROBE3 OK");
+    return bad ? 1 : 0;
+}
+
 static int run_probe2() {
     const int M = 256, N = 256, K = 64;
     std::vector<float> A(M * K), B(N * K), D(M * N);
@@ -209,5 +295,7 @@ int main() {
     }
     printf(ok_any ? "PROBE OK\n" : "PROBE FAILED\n");
     run_probe2();
+    run_probe3(1);
+    run_probe3(0);
     return 0;
 }
