@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--coarse", type=int, default=64)
     ap.add_argument("--fine", type=int, default=128)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--grad-precision", default="tf32", choices=["fp32", "tf32"], help="GEMM engine of the training config")
+    ap.add_argument("--grad-precision", default="bf16", choices=["fp32", "tf32", "bf16"],
+                    help="training config: bf16 = fused tensor-core forward + reverse mode, tf32 / fp32 = layer-wise GEMMs")
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid"],
@@ -383,10 +384,12 @@ def run_secondary(args):
         ms = timed(step, args.steps, args.warmup)
         rows = n_batch * (2 * sc + sf)
         line = dict(metric="rays/s, NeRF training step (4096-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
-                    unit="rays/s", ms_per_step=ms, dtype="tf32" if args.grad_precision == "tf32" else "f32", scaling="strong",
-                    config=dict(workload="NeRF train step, 4096 rays sharded over ranks, layer-wise MLP forward with saved fp32 activations + "
-                                         f"CUDA reverse mode, GEMMs in {args.grad_precision}, one NCCL all-reduce of the 4.75 MB gradient bucket, "
-                                         "torch Adam"),
+                    unit="rays/s", ms_per_step=ms, dtype={"tf32": "tf32", "fp32": "f32", "bf16": "bf16"}[args.grad_precision], scaling="strong",
+                    config=dict(workload="NeRF train step, 4096 rays sharded over ranks, " + (
+                        "fused tcgen05 MLP forward with bf16 activations kept in HBM + fused dgrad / MN-major wgrad reverse mode (bf16 operands, fp32 "
+                        "accumulate), " if args.grad_precision == "bf16" else
+                        f"layer-wise MLP forward with saved fp32 activations + CUDA reverse mode, GEMMs in {args.grad_precision}, ") +
+                        "one NCCL all-reduce of the 4.75 MB gradient bucket, torch Adam"),
                     tflops=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
     elif args.config == "pigan":
         n_lat, res, s_ = 64, 128, 24

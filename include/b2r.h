@@ -138,6 +138,23 @@ int b2r_mlp_tc_pack(int model_kind, const float* params, const float* film, int 
 int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_mlp_input* in, float* raw_out,
                    int sigma_only, void* stream);
 
+/* ---- K8 on the tensor cores: training forward + reverse mode of the NeRF MLP (bf16 operands, fp32 accumulate) --------
+ * Replaces autograd through NeRF.forward (nerf/nerf.py:75-94) as used by nerf/train_nerf.py:151-168.
+ * b2r_mlp_tc_train_fwd = b2r_mlp_tc_fwd that also keeps every layer input as tiled bf16 tensors in `saved`
+ * (b2r_mlp_tc_train_saved_bytes(kind, rows) bytes, 5,120 B per row, rows padded to 512).
+ * b2r_mlp_tc_train_bwd: d_raw[rows,4] -> d_params (flat fp32, ACCUMULATED into: caller zeroes).  packed_bwd: transposed
+ * weights from b2r_mlp_tc_pack_bwd (b2r_mlp_tc_bwd_packed_bytes bytes); raw = the forward's output; scratch:
+ * b2r_mlp_tc_train_scratch_bytes(kind, rows) bytes (per-layer d(pre-activation) tiles for the weight-gradient GEMMs).
+ * Only B2R_MODEL_NERF has this path; other kinds return <0 (callers use the fp32 / tf32 layer-wise path). */
+size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows);
+int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,
+                         size_t saved_bytes, void* stream);
+size_t b2r_mlp_tc_bwd_packed_bytes(int model_kind);
+int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* packed_out, void* stream);
+size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows);
+int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows, const float* raw, const float* d_raw,
+                         const void* saved, void* scratch, size_t scratch_bytes, float* d_params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

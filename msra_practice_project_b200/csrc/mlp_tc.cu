@@ -28,84 +28,13 @@
 //   [h | dir-enc] for layers_dir.1), zero-padded to the MMA K granularity in the packed weights.
 //
 // Algorithmic work: 1,182,976 FLOP per NeRF row; issued (padded): 1,191,936 (+0.8 %).
-#include "common.cuh"
-#include "umma.cuh"
+
+#include "tc_core.cuh"
 
 namespace b2r {
 namespace tc {
 
-using namespace umma;
-
-constexpr int kRowsSub = 128;
-constexpr int kRowsTile = 256;                          // rows per CTA per iteration (a pair covers 512)
-constexpr int kStages = 3;
-constexpr uint32_t kStageBytes = 16384;                 // 128 weight rows x 64 K bf16 (this CTA's N-half)
-constexpr uint32_t kPeBytes = 16384;                    // 128 rows x 64 bf16 (SW128): pos-enc / dir-enc block
-constexpr uint32_t kHBytes = 65536;                     // 4 K-blocks of 128 rows x 64 bf16
-constexpr uint32_t kSubBytes = kPeBytes + kHBytes;      // 80 KB per sub-tile
-constexpr uint32_t kRingOff = 2 * kSubBytes;
-
-constexpr int kCtrlWarps = 4;                           // 0 producer, 1 MMA issuer / relay (+TMEM alloc), 2-3 idle
-constexpr int kEpiWarps = 16;                           // 2 sub-tiles x 2 column halves x 4 TMEM lane quadrants
-constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32; // 640
-
-// ---- schedules (chunks of 64 K) ---------------------------------------------------------------------------
-// A step = one layer's MMAs for one sub-tile: n_pre chunks whose A operand is the aux block (pos-enc),
-// then n_h chunks reading the K-blocks of h, then n_post chunks reading the aux block again (dir-enc /
-// view direction; only kPostMmas x 16 K of it are issued).
-struct NerfSched {       // step 0..7 = layers_pos.0..7, 8 = layers_dir.0, 9 = layers_dir.1
-    static constexpr int kSteps = 10;
-    __host__ __device__ static constexpr int n_pre(int s, int) { return (s == 0 || s == 5) ? 1 : 0; }
-    __host__ __device__ static constexpr int n_h(int s, int) { return s == 0 ? 0 : 4; }
-    __host__ __device__ static constexpr int n_post(int s, int) { return s == 9 ? 1 : 0; }
-    __host__ __device__ static constexpr int n(int s) { return s == 9 ? 128 : 256; }
-    static constexpr int kPostMmas = 2;                  // dir-enc: 24 -> 32 K
-};
-struct FilmSched {       // steps 0..6 = hidden_layers.0..6, step 7 = hidden_layer_rgb ([h | dir]); flag = use_dir
-    static constexpr int kSteps = 8;
-    __host__ __device__ static constexpr int n_pre(int, int) { return 0; }
-    __host__ __device__ static constexpr int n_h(int, int) { return 4; }
-    __host__ __device__ static constexpr int n_post(int s, int use_dir) { return (s == 7 && use_dir) ? 1 : 0; }
-    __host__ __device__ static constexpr int n(int) { return 256; }
-    static constexpr int kPostMmas = 1;                  // view direction: 3 -> 16 K
-};
-template <class S>
-__host__ __device__ constexpr uint32_t half_bytes(int s) { return (uint32_t)(S::n(s) / 2) * 128u; }
-// packed chunks of a step (the post chunk is always stored, even when use_dir = 0 skips it)
-template <class S>
-__host__ __device__ constexpr int stored_chunks(int s) { return S::n_pre(s, 1) + S::n_h(s, 1) + S::n_post(s, 1); }
-template <class S>
-__host__ __device__ constexpr long long step_base(int s) {
-    long long off = 0;
-    for (int t = 0; t < s; ++t) off += 2LL * stored_chunks<S>(t) * half_bytes<S>(t);
-    return off;
-}
-
-constexpr long long kNerfChunkBytes = step_base<NerfSched>(NerfSched::kSteps);      // 1,196,032
-constexpr long long kFilmChunkBytes = step_base<FilmSched>(FilmSched::kSteps);      // 1,081,344
-static_assert(kNerfChunkBytes == 1196032 && kFilmChunkBytes == 1081344, "packed chunk bytes");
-// NeRF fp32 tables after the chunks: bias[10][256] | w_sigma[256] | w_rgb[3][128] | b_sigma, b_rgb[3]
-constexpr int kNerfTabBias = 0, kNerfTabWSigma = 2560, kNerfTabWRgb = 2816, kNerfTabBHead = 3200, kNerfTabFloats = 3204;
-constexpr long long kNerfPackedBytes = kNerfChunkBytes + kNerfTabFloats * 4;
-// FiLM fp32 tables: scale[8][256] | shift[8][256] | w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
-//                   w_sigma[256] | w_rgb[3][256] | b_sigma, b_rgb[3]
-constexpr int kFSc = 0, kFSh = 2048, kFW0 = 4096, kFS0 = 4864, kFT0 = 5120, kFWS = 5376, kFWR = 5632, kFBH = 6400, kFilmTabFloats = 6404;
-constexpr long long kFilmPackedBytes = kFilmChunkBytes + kFilmTabFloats * 4;
-
 // ---- pack kernels: fp32 state-dict parameters -> swizzled bf16 half-chunk images + fp32 tables ---------------
-// one thread per 16-byte group: (step, chunk, half, row of the half, 8 consecutive k)
-template <class S>
-__device__ __forceinline__ void locate(long long byte, int& s, int& c, int& hf, int& row, int& grp) {
-    s = 0;
-    while (s + 1 < S::kSteps && byte >= step_base<S>(s + 1)) ++s;
-    long long in_step = byte - step_base<S>(s);
-    const int hb = (int)half_bytes<S>(s);
-    int hc = (int)(in_step / hb);
-    c = hc >> 1; hf = hc & 1;
-    int rem = (int)(in_step % hb);
-    row = rem / 128; grp = (rem % 128) / 16;
-}
-
 __global__ void nerf_pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t < kNerfChunkBytes / 16) {
@@ -187,204 +116,18 @@ __global__ void film_pack_kernel(const float* __restrict__ params, const float* 
     }
 }
 
-// ---- shared-memory map (offsets from the 1024-aligned base; identical in both CTAs of a pair) -------------------
-constexpr uint32_t kTabOff = kRingOff + kStages * kStageBytes;          // fp32 tables (NeRF bias / head weights)
-constexpr uint32_t kTabBytes = kNerfTabFloats * 4;                      // 12,816
-constexpr uint32_t kPartOff = kTabOff + kTabBytes;                      // head partial sums: 2 x 128 x float4
-constexpr uint32_t kPartBytes = 2 * kRowsSub * 16;
-constexpr uint32_t kBarOff = kPartOff + kPartBytes;                     // mbarriers + TMEM slot
-constexpr uint32_t kSmemBytes = kBarOff + 128 + 1024;                   // + alignment slack
-static_assert(kBarOff % 8 == 0 && kSmemBytes <= 232448, "shared-memory budget");
-
-struct Ctx {
-    uint32_t smem;        // 1024-aligned shared base (shared-window address)
-    uint32_t w_full, w_empty, act_ready, acc_full, tmem_slot;
-    uint32_t rank;        // CTA rank in the pair (0 = leader: issues the MMAs)
-};
-
-__device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
-    Ctx c;
-    c.smem = (smem_u32(raw) + 1023u) & ~1023u;
-    c.w_full = c.smem + kBarOff;
-    c.w_empty = c.w_full + 8 * kStages;
-    c.act_ready = c.w_empty + 8 * kStages;
-    c.acc_full = c.act_ready + 16;
-    c.tmem_slot = c.acc_full + 16;
-    c.rank = cluster_ctarank();
-    return c;
-}
-
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
-// Positional encoding of 3 values with L octaves as 3L packed bf16x2 words, in the reference's order
-// [sin(2^i x)(3), cos(2^i x)(3)] per octave (nerf/nerf.py:44-49): 6 values = 3 words per octave.
-// Octave 0 uses the accurate sincosf; higher octaves the double-angle recurrence (abs. error grows ~2x per
-// octave, < 1e-4 at octave 9: far below the bf16 rounding of the operand).
-template <int L>
-__device__ __forceinline__ void posenc_words(const float x[3], uint32_t* w) {
-    float s[3], c[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) sincosf(x[k], &s[k], &c[k]);
-#pragma unroll
-    for (int i = 0; i < L; ++i) {
-        w[3 * i + 0] = pack_bf16(s[0], s[1]);
-        w[3 * i + 1] = pack_bf16(s[2], c[0]);
-        w[3 * i + 2] = pack_bf16(c[1], c[2]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            float s2 = 2.0f * s[k] * c[k];
-            float c2 = 1.0f - 2.0f * s[k] * s[k];
-            s[k] = s2; c[k] = c2;
-        }
-    }
-}
-
-// tile pairs walked by the cluster: pair p -> tiles 2p (leader) and 2p+1 (peer)
-struct PairLoop {
-    long long n_pairs, first, stride;
-    __device__ PairLoop(long long rows) {
-        long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
-        n_pairs = (n_tiles + 1) / 2;
-        first = blockIdx.x >> 1;
-        stride = gridDim.x >> 1;
-    }
-};
-
-// weight producer: one thread per CTA streams ITS half of every chunk in schedule order (each step twice: once per sub-tile)
-template <class S>
-__device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __restrict__ packed, const PairLoop& pl, int n_steps, int flag) {
-    uint32_t stage = 0, phase = 0;
-    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
-        for (int s = 0; s < n_steps; ++s) {
-            const int nc = S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag);
-            const uint32_t bytes = half_bytes<S>(s);
-            const uint8_t* src_w = packed + step_base<S>(s) + (size_t)cx.rank * bytes;
-            for (int g = 0; g < 2; ++g) {
-                for (int c = 0; c < nc; ++c) {
-                    mbar_wait_cluster(cx.w_empty + 8 * stage, phase ^ 1u);
-                    mbar_arrive_expect_tx(cx.w_full + 8 * stage, bytes);
-                    bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, src_w + (size_t)c * 2 * bytes, bytes, cx.w_full + 8 * stage);
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
-                }
-            }
-        }
-    }
-}
-
-// peer CTA: forward "my half of this stage has landed" to the leader's ring barrier (count 2 there)
-template <class S>
-__device__ __forceinline__ void relay_loop(const Ctx& cx, const PairLoop& pl, int n_steps, int flag) {
-    uint32_t stage = 0, phase = 0;
-    const uint32_t remote0 = mapa(cx.w_full, 0);
-    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
-        for (int s = 0; s < n_steps; ++s) {
-            const int nc = 2 * (S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag));
-            for (int c = 0; c < nc; ++c) {
-                mbar_wait_cluster(cx.w_full + 8 * stage, phase);
-                mbar_arrive_cluster(remote0 + 8 * stage);
-                if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            }
-        }
-    }
-}
-
-// MMA issuer: warp 1 of the leader CTA, converged (every lane walks the schedule and polls the barriers; one elected
-// lane issues), so the descriptors live in uniform registers.  Alternates the two sub-tiles step by step.
-template <class S>
-__device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, const PairLoop& pl, int n_steps, int flag) {
-    uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0;
-    const uint64_t d_hi = desc_sw128(0);                          // A and B: K-major SWIZZLE_128B, zero address field
-    auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, uint32_t accumulate, int n_mma) {
-        mbar_wait_cluster(cx.w_full + 8 * stage, phase);
-        tc_fence_after();
-        const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
-        const uint64_t ad = d_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
-        const uint64_t bd = d_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
-        if (elect_one()) {
-            mma_bf16_2cta(d_tmem, ad, bd, idesc, accumulate);
-            for (int k = 1; k < n_mma; ++k) mma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);   // +32 B = next 16 K
-            mma_commit_2cta(cx.w_empty + 8 * stage, (uint16_t)3);
-        }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
-    };
-    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
-        for (int s = 0; s < n_steps; ++s) {
-            const uint32_t idesc = make_idesc_bf16(256, (uint32_t)S::n(s));
-            const int n_pre = S::n_pre(s, flag), n_h = S::n_h(s, flag), n_post = S::n_post(s, flag);
-            for (int g = 0; g < 2; ++g) {
-                if (g == 0) { mbar_wait_cluster(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
-                else { mbar_wait_cluster(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
-                const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
-                uint32_t acc = 0;
-                for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base, idesc, acc, 4); acc = 1; }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < n_h) { issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)c * 16384u, idesc, acc, 4); acc = 1; }
-                }
-                for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u, S::kPostMmas);
-                if (elect_one()) mma_commit_2cta(cx.acc_full + 8 * g, (uint16_t)3);
-                __syncwarp();
-            }
-        }
-    }
-}
-
-// common prologue: barriers, TMEM allocation (both CTAs), cluster rendezvous; returns the TMEM base address
-__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp) {
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 16); mbar_init(cx.acc_full + 8 * g, 1); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc_2cta(cx.tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
-    return tmem_base;
-}
-__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
-    tc_fence_before();
-    __syncthreads();
-    cluster_sync_all();
-    if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
-}
-
-// epilogue warp -> leader's act_ready[g]: this warp's rows of the next A operand are written and its TMEM reads are done
-__device__ __forceinline__ void arrive_act(uint32_t act_bar_local, uint32_t act_bar_leader, uint32_t rank, int lane) {
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-        if (rank == 0) mbar_arrive_release_cluster_local(act_bar_local);
-        else mbar_arrive_cluster(act_bar_leader);
-    }
-}
-
-// packed fp32x2 add (FADD2): {a0,a1} += {b0,b1}
-__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
-    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
-        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
-}
-
 // One NeRF layer's epilogue for this warp's half of the columns, fully unrolled (no per-step branches in the hot loop).
 //   MODE 0: + bias, ReLU -> bf16 h                       (layers_pos.0..6)
 //   MODE 1: same + partial sigma head on the fp32 values  (layers_pos.7; output_layer_sigma, nerf/nerf.py:72,88)
 //   MODE 2: + bias, linear -> bf16 h                      (layers_dir.0)
 //   MODE 3: + bias, ReLU -> partial rgb head, no store    (layers_dir.1, N = 128; output_layer_rgb, nerf/nerf.py:73,93)
 // t_half / bias_half / h_half already include this warp's column-half offset; xoff[c] = ((c ^ (row & 7)) << 4).
-template <int MODE>
+// kSave (training forward): every bf16 word written to shared memory is also stored to `spill`, this thread's row of the
+// layer's tiled activation tensor in global memory (tc_core.cuh), same block / chunk offsets; MODE 3 stores relu(h_d).
+template <int MODE, bool kSave>
 __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, uint32_t head_half, uint32_t h_half,
-                                         const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2) {
+                                         const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2,
+                                         uint8_t* __restrict__ spill) {
     constexpr int NJH = MODE == 3 ? 2 : 4;
 #pragma unroll
     for (int jj = 0; jj < NJH; ++jj) {
@@ -423,6 +166,12 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
                 rgb1 = fmaf(h0, w1.x, fmaf(h1, w1.y, fmaf(h2, w1.z, fmaf(h3, w1.w, rgb1))));
                 rgb2 = fmaf(h0, w2.x, fmaf(h1, w2.y, fmaf(h2, w2.z, fmaf(h3, w2.w, rgb2))));
             }
+            if (kSave) {                                            // HD tile: block = this half, chunks jj * 4 .. + 3
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    stg128(spill + xoff[jj * 4 + q], pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]), pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]),
+                           pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]), pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]));
+            }
         } else {
             // columns of this 32-group = K of the next layer: K-block (jj >> 1) of this half, chunks (jj & 1) * 4 .. + 3
             const uint32_t blk = h_half + (uint32_t)(jj >> 1) * 16384u;
@@ -437,6 +186,7 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
                     w2 = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
                 }
                 st_shared_v4(blk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
+                if (kSave) stg128(spill + (uint32_t)(jj >> 1) * kBlk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
             }
         }
     }
@@ -445,8 +195,11 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
 // ======================================================================================================
 // NeRF (nerf/nerf.py:52-94)
 // ======================================================================================================
+// kSave = training forward: additionally writes every layer input the reverse mode needs (pos-enc, h0..h7, layers_dir.0
+// output, dir-enc, h_d) as tiled bf16 tensors into `saved` (5,120 B per row).
+template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out) {
+nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -491,9 +244,13 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
         uint32_t acc_phase = 0;
+        const size_t n_sub = (size_t)pl.n_pairs * 4;               // 128-row sub-tiles in the saved tensors
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
             const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
             const bool valid = row < rows;
+            const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+            // this thread's row inside block 0 of tile T of a saved tensor with `nb` blocks per tile at block offset `off`
+            auto sav = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk + row_off; };
             float pnt[3], vdir[3];
             load_row(src, valid ? row : rows - 1, pnt, vdir);
             {
@@ -509,6 +266,7 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     uint32_t a2 = half ? pw[16 + 4 * q + 2] : pw[4 * q + 2];
                     uint32_t a3 = half ? pw[16 + 4 * q + 3] : pw[4 * q + 3];
                     st_shared_v4(pe_base + row_off + ((cidx ^ xr) << 4), a0, a1, a2, a3);
+                    if (kSave) stg128(sav(kSavPE, 1) + ((cidx ^ xr) << 4), a0, a1, a2, a3);
                 }
             }
             arrive_act(act_local, act_leader, cx.rank, lane);
@@ -521,14 +279,17 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             };
             for (int s = 0; s < 7; ++s) {                               // layers_pos.0 .. layers_pos.6
                 wait_acc();
-                nerf_epi<0>(t_half, bias_half + (uint32_t)s * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+                nerf_epi<0, kSave>(t_half, bias_half + (uint32_t)s * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2,
+                                   kSave ? sav(sav_h(s), 4) + (size_t)half * 2 * kBlk : nullptr);
                 arrive_act(act_local, act_leader, cx.rank, lane);
             }
             wait_acc();                                                 // layers_pos.7 (+ sigma head)
-            nerf_epi<1>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+            nerf_epi<1, kSave>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2,
+                               kSave ? sav(sav_h(7), 4) + (size_t)half * 2 * kBlk : nullptr);
             arrive_act(act_local, act_leader, cx.rank, lane);
             wait_acc();                                                 // layers_dir.0 (linear) + view-direction encoding
-            nerf_epi<2>(t_half, bias_half + 8u * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+            nerf_epi<2, kSave>(t_half, bias_half + 8u * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2,
+                               kSave ? sav(kSavGL, 4) + (size_t)half * 2 * kBlk : nullptr);
             {
                 // layers_dir.1's extra K: 24 values + 8 zero pads = 16 words = chunks 0..3 of the aux block; each half writes two
                 uint32_t dw[16];
@@ -541,13 +302,18 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     uint32_t a2 = half ? dw[8 + 4 * q + 2] : dw[4 * q + 2];
                     uint32_t a3 = half ? dw[8 + 4 * q + 3] : dw[4 * q + 3];
                     st_shared_v4(pe_base + row_off + ((((uint32_t)(half * 2 + q)) ^ xr) << 4), a0, a1, a2, a3);
+                    if (kSave) {                                    // DE tile: chunks 0..3 = the encoding, 4..7 = zero
+                        uint8_t* de = sav(kSavDE, 1);
+                        stg128(de + ((((uint32_t)(half * 2 + q)) ^ xr) << 4), a0, a1, a2, a3);
+                        stg128(de + ((((uint32_t)(4 + half * 2 + q)) ^ xr) << 4), 0u, 0u, 0u, 0u);
+                    }
                 }
             }
             arrive_act(act_local, act_leader, cx.rank, lane);
             wait_acc();                                                 // layers_dir.1 (N = 128) + rgb head
-            nerf_epi<3>(tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)half * 64u,
-                        tab + (uint32_t)(kNerfTabBias + 9 * 256 + half * 64) * 4u, tab + (uint32_t)(kNerfTabWRgb + half * 64) * 4u, 0u, xoff,
-                        sigma, rgb0, rgb1, rgb2);
+            nerf_epi<3, kSave>(tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)half * 64u,
+                               tab + (uint32_t)(kNerfTabBias + 9 * 256 + half * 64) * 4u, tab + (uint32_t)(kNerfTabWRgb + half * 64) * 4u, 0u, xoff,
+                               sigma, rgb0, rgb1, rgb2, kSave ? sav(kSavHD, 2) + (size_t)half * kBlk : nullptr);
             tc_fence_before();
             // combine the two halves' head partial sums and write raw[row] = (sigmoid rgb, relu sigma)
             if (half == 1)
@@ -781,6 +547,24 @@ extern "C" int b2r_mlp_tc_pack(int model_kind, const float* params, const float*
     return fail(-2, "b2r_mlp_tc_pack: unknown model kind %d", model_kind);
 }
 
+namespace b2r {
+namespace tc {
+// grid of a fused-MLP launch: one CTA pair per two SMs; a pair walks tile pairs (2 x 256 rows)
+int pair_grid(long long rows, unsigned* grid) {
+    int dev = 0, sms = 0;
+    int rc = cuda_result(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
+    if (rc) return rc;
+    long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
+    long long n_pairs = (n_tiles + 1) / 2;
+    long long clusters = sms / 2 < n_pairs ? sms / 2 : n_pairs;
+    *grid = (unsigned)(2 * clusters);
+    return 0;
+}
+}  // namespace tc
+}  // namespace b2r
+
 extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_mlp_input* in, float* raw_out,
                               int sigma_only, void* stream) {
     using namespace b2r;
@@ -792,16 +576,9 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (rows == 0) return 0;
     B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM, "b2r_mlp_tc_fwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(!(sigma_only && model_kind == B2R_MODEL_NERF), "b2r_mlp_tc_fwd: sigma_only is a FiLM-SIREN mode");
-    int dev = 0, sms = 0;
-    rc = cuda_result(cudaGetDevice(&dev), "cudaGetDevice");
+    unsigned grid = 0;
+    rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
-    rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
-    if (rc) return rc;
-    // one CTA pair per two SMs; a pair walks tile pairs (2 x 256 rows)
-    long long n_tiles = (rows + tc::kRowsTile - 1) / tc::kRowsTile;
-    long long n_pairs = (n_tiles + 1) / 2;
-    long long clusters = sms / 2 < n_pairs ? sms / 2 : n_pairs;
-    unsigned grid = (unsigned)(2 * clusters);
     cudaStream_t st = (cudaStream_t)stream;
     if (model_kind == B2R_MODEL_FILM) {
         rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
@@ -809,10 +586,37 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
         tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, use_dir, sigma_only,
                                                                       (float4*)raw_out);
     } else {
-        rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+        rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
-        tc::nerf_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out);
+        tc::nerf_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr);
     }
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
+    return 0;
+}
+
+extern "C" size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows) {
+    if (model_kind != B2R_MODEL_NERF || rows < 0) return 0;
+    return (size_t)b2r::tc::n_sub_tiles(rows) * b2r::tc::kSavBlocks * b2r::tc::kBlk;
+}
+
+extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,
+                                    size_t saved_bytes, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF, "b2r_mlp_tc_train_fwd: only the NeRF model has a tensor-core training path (kind %d)", model_kind);
+    B2R_CHECK_ARG(packed && raw_out && saved, "b2r_mlp_tc_train_fwd: NULL pointer");
+    B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out | (uintptr_t)saved) & 15) == 0, "b2r_mlp_tc_train_fwd: buffers must be 16-byte aligned");
+    int rc = check_mlp_input(in);
+    if (rc) return rc;
+    long long rows = row_count(in);
+    B2R_CHECK_ARG(saved_bytes >= b2r_mlp_tc_train_saved_bytes(model_kind, rows), "b2r_mlp_tc_train_fwd: saved buffer too small (%zu B)", saved_bytes);
+    if (rows == 0) return 0;
+    unsigned grid = 0;
+    rc = tc::pair_grid(rows, &grid);
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+    if (rc) return rc;
+    tc::nerf_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
+                                                                                           (float4*)raw_out, (uint8_t*)saved);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd");
     return 0;
 }

@@ -1,0 +1,541 @@
+// K8 (tensor-core path): reverse mode of the fused NeRF MLP -- the backward pass nerf/train_nerf.py:167 gets from
+// autograd (loss.backward() through NeRF.forward, nerf/nerf.py:75-94), restructured for the B200:
+//
+//   forward  (mlp_tc.cu, nerf_tc_kernel<true>)  the inference kernel + every layer input spilled as tiled bf16 tensors;
+//   dgrad    (nerf_tc_bwd_kernel, here)         ONE persistent CTA-pair kernel walking the layers backwards: the incoming
+//            gradient of a 128-row sub-tile stays in shared memory as the A operand of the next tcgen05 step
+//            (dX = dPre W, weights pre-packed TRANSPOSED by b2r_mlp_tc_pack_bwd and streamed by the bulk-copy engine);
+//            the epilogue applies relu'(h) from the saved activation (packed bf16x2 compare + mask), adds the sigma-head
+//            term, rounds to bf16, writes the next A operand in place and spills d(pre-activation) for wgrad;
+//   wgrad    (nerf_tc_wgrad_kernel, here)       dW_l = dPre_l^T X_l over all rows: both operands are the spilled tiles read
+//            back as MN-major SWIZZLE_128B operands (row index = K, no transposition), 64-row stages through a 3-stage
+//            bulk-copy ring, fp32 accumulators in TMEM for a whole range of tiles, flushed once with float atomics;
+//            four otherwise idle warps add up the bias gradients (column sums of dPre) from the staged tiles;
+//   heads    (nerf_head_wgrad_kernel)           output_layer_sigma / output_layer_rgb weight + bias gradients (1 and 3 rows).
+//
+// Arithmetic: bf16 operands, fp32 accumulation, gradients accumulated into the caller's fp32 flat bucket (the layout the
+// NCCL all-reduce and Adam use).  HBM traffic per row: 5,120 B written by the forward, 4,352 B read + 4,880 B written by
+// dgrad, 10,624 B read by wgrad -- the training step is HBM-bound, not tensor-bound.
+#include "tc_core.cuh"
+
+namespace b2r {
+namespace tc {
+
+// ---- dgrad schedule -------------------------------------------------------------------------------------------------
+// step 0: d g  = dPre(layers_dir.1)[128] . W_d1[:, 0:256]        (K = 128: two chunks)
+// step 1: d h7 = d g . W_d0            (+ sigma-head term, relu'(h7))
+// step 2, 3: layers_pos.7, layers_pos.6;  step 4: layers_pos.5[:, 60:316] (the h4 part of the skip input);
+// step 5..8: layers_pos.4 .. layers_pos.1.   layers_pos.0 has no dgrad (its input is the encoding).
+struct BwdSched {
+    static constexpr int kSteps = 9;
+    __host__ __device__ static constexpr int n_pre(int, int) { return 0; }
+    __host__ __device__ static constexpr int n_h(int s, int) { return s == 0 ? 2 : 4; }
+    __host__ __device__ static constexpr int n_post(int, int) { return 0; }
+    __host__ __device__ static constexpr int n(int) { return 256; }
+    static constexpr int kPostMmas = 1;
+};
+__host__ __device__ constexpr int bwd_layer(int s) { return s == 0 ? 9 : (s == 1 ? 8 : 9 - s); }
+constexpr long long kBwdChunkBytes = step_base<BwdSched>(BwdSched::kSteps);           // 34 chunks x 2 halves x 16 KB
+static_assert(kBwdChunkBytes == 34LL * 32768, "bwd packed chunk bytes");
+constexpr int kBwdTabWSigma = 0, kBwdTabWRgb = 256, kBwdTabFloats = 640;              // w_sigma[256] | w_rgb[3][128]
+constexpr long long kBwdPackedBytes = kBwdChunkBytes + kBwdTabFloats * 4;
+
+// B operand of dgrad step s: B[n][k] = W_L[k][n + col_off]  (n = input feature = output column of dX, k = output feature)
+__global__ void nerf_pack_bwd_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < kBwdChunkBytes / 16) {
+        int s, c, hf, row, grp;
+        locate<BwdSched>(t * 16, s, c, hf, row, grp);
+        LayerDesc L = nerf_layer(bwd_layer(s));
+        const int n = hf * 128 + row + (s == 4 ? 60 : 0);
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            int k = c * 64 + grp * 8 + e;
+            v[e] = __float2bfloat16_rn(k < L.out ? params[L.w_off + (long long)k * L.in + n] : 0.f);
+        }
+        uint8_t* dst = packed + step_base<BwdSched>(s) + (long long)(c * 2 + hf) * half_bytes<BwdSched>(s) +
+                       sw128_offset((uint32_t)row, (uint32_t)grp);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+    if (t < kBwdTabFloats) {
+        float* tab = reinterpret_cast<float*>(packed + kBwdChunkBytes);
+        int i = (int)t;
+        tab[i] = i < kBwdTabWRgb ? params[nerf_layer(10).w_off + i] : params[nerf_layer(11).w_off + (i - kBwdTabWRgb)];
+    }
+}
+
+// 0xFFFF in every half whose bf16 value is > 0 (relu'(h) for a packed pair of saved activations)
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t h2) {
+    __nv_bfloat162 a, z;
+    *reinterpret_cast<uint32_t*>(&a) = h2;
+    *reinterpret_cast<uint32_t*>(&z) = 0u;
+    return __hgt2_mask(a, z);
+}
+
+// One dgrad step's epilogue for this warp's half (128) of the columns.
+//   MODE 0: linear (d g: layers_dir.0 has no activation)           -> next A operand + spill
+//   MODE 1: + gs * w_sigma (sigma-head term), relu'(h7)             -> next A operand + spill
+//   MODE 2: relu'(h)                                                -> next A operand + spill
+//   MODE 3: relu'(h0), spill only (layers_pos.0 has no dgrad)
+// hsrc: this thread's row in block 0 of its half of the saved activation tile; gdst: same for the gradient tile.
+template <int MODE>
+__device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const uint32_t (&xoff)[8], const uint8_t* __restrict__ hsrc,
+                                        uint8_t* __restrict__ gdst, float gs, uint32_t wsig_half, uint32_t acc_bar, uint32_t& acc_phase) {
+    uint4 hm[4];
+    if (MODE != 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hm[q] = ldg128(hsrc + xoff[q]);                 // in flight while the MMAs finish
+    }
+    mbar_wait_cluster(acc_bar, acc_phase);
+    acc_phase ^= 1u;
+    tc_fence_after();
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        uint32_t v[32];
+        tmem_ld32(t_half + (uint32_t)jj * 32u, v);
+        uint4 hn[4];
+        if (MODE != 0 && jj < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hn[q] = ldg128(hsrc + (uint32_t)((jj + 1) >> 1) * kBlk + xoff[((jj + 1) & 1) * 4 + q]);
+        }
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
+        if (MODE == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 w = lds128(wsig_half + (uint32_t)(jj * 32 + q * 4) * 4u);
+                f[4 * q + 0] = fmaf(gs, w.x, f[4 * q + 0]); f[4 * q + 1] = fmaf(gs, w.y, f[4 * q + 1]);
+                f[4 * q + 2] = fmaf(gs, w.z, f[4 * q + 2]); f[4 * q + 3] = fmaf(gs, w.w, f[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t w0 = pack_bf16(f[8 * q + 0], f[8 * q + 1]), w1 = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
+            uint32_t w2 = pack_bf16(f[8 * q + 4], f[8 * q + 5]), w3 = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
+            if (MODE != 0) {
+                w0 &= relu_mask2(hm[q].x); w1 &= relu_mask2(hm[q].y); w2 &= relu_mask2(hm[q].z); w3 &= relu_mask2(hm[q].w);
+            }
+            const uint32_t off = (uint32_t)(jj >> 1) * kBlk + xoff[(jj & 1) * 4 + q];
+            if (MODE != 3) st_shared_v4(h_half + off, w0, w1, w2, w3);
+            stg128(gdst + off, w0, w1, w2, w3);
+        }
+        if (MODE != 0 && jj < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hm[q] = hn[q];
+        }
+    }
+}
+
+// =====================================================================================================================
+// dgrad: d_raw -> d(pre-activation) of every layer (tiled bf16 tensors in `scratch`) + head gradients HG
+// =====================================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const float4* __restrict__ raw, const float4* __restrict__ d_raw,
+                   const uint8_t* __restrict__ saved, uint8_t* __restrict__ scratch) {
+    extern __shared__ uint8_t smem_raw[];
+    const Ctx cx = make_ctx(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PairLoop pl(rows);
+    {   // w_sigma | w_rgb -> shared memory
+        const float4* tab_g = reinterpret_cast<const float4*>(packed + kBwdChunkBytes);
+        for (int i = threadIdx.x; i < kBwdTabFloats / 4; i += kThreads) {
+            float4 v = __ldg(tab_g + i);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+        }
+    }
+    const uint32_t tmem_base = tc_prologue(cx, warp);
+
+    if (warp == 0) {
+        if (lane == 0) producer_loop<BwdSched>(cx, packed, pl, BwdSched::kSteps, 0);
+    } else if (warp == 1) {
+        if (cx.rank == 0) mma_loop<BwdSched>(cx, tmem_base, pl, BwdSched::kSteps, 0);
+        else if (lane == 0) relay_loop<BwdSched>(cx, pl, BwdSched::kSteps, 0);
+    } else if (warp >= kCtrlWarps) {
+        const int ew = warp - kCtrlWarps;
+        const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
+        const int r = (quad << 5) | lane;
+        const uint32_t sub = cx.smem + (uint32_t)g * kSubBytes;
+        const uint32_t h_base = sub + kPeBytes;
+        const uint32_t t_addr = tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const uint32_t xr = (uint32_t)(r & 7);
+        const uint32_t tab = cx.smem + kTabOff;
+        const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
+        const uint32_t acc_bar = cx.acc_full + 8 * g;
+        const uint32_t t_half = t_addr + (uint32_t)half * 128u;
+        const uint32_t h_half = h_base + row_off + (uint32_t)half * 2u * kBlk;
+        const uint32_t wsig_half = tab + (uint32_t)(kBwdTabWSigma + half * 128) * 4u;
+        uint32_t xoff[8];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
+        uint32_t acc_phase = 0;
+        const size_t n_sub = (size_t)pl.n_pairs * 4;
+        float4* __restrict__ hg_out = reinterpret_cast<float4*>(scratch + (size_t)kScrBlocks * n_sub * kBlk);
+        for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+            const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
+            const bool valid = row < rows;
+            const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+            auto sav = [&](int off, int nb) -> const uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk + row_off; };
+            auto scr = [&](int off, int nb) -> uint8_t* { return scratch + ((size_t)off * n_sub + T * (size_t)nb) * kBlk + row_off; };
+            // ---- heads: d raw -> (d rgb pre-sigmoid, d sigma pre-relu); rows past the end contribute zero everywhere
+            float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, gs = 0.f;
+            if (valid) {
+                const float4 y = __ldg(raw + row), dy = __ldg(d_raw + row);
+                gc0 = dy.x * (y.x * (1.0f - y.x));
+                gc1 = dy.y * (y.y * (1.0f - y.y));
+                gc2 = dy.z * (y.z * (1.0f - y.z));
+                gs = y.w > 0.f ? dy.w : 0.f;
+            }
+            if (half == 0) hg_out[T * kRowsSub + r] = make_float4(gc0, gc1, gc2, gs);
+            {
+                // d h_d = (d rgb pre) . W_rgb, relu'(h_d): this half produces columns half*64 .. +63 = K-block `half` of step 0
+                const uint8_t* hd = sav(kSavHD, 2) + (size_t)half * kBlk;
+                uint8_t* gd = scr(kScrGD1, 2) + (size_t)half * kBlk;
+                const uint32_t wr = tab + (uint32_t)(kBwdTabWRgb + half * 64) * 4u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 hm = ldg128(hd + xoff[q]);
+                    float f[8];
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const uint32_t wa = wr + (uint32_t)(q * 8 + hq * 4) * 4u;
+                        const float4 w0 = lds128(wa), w1 = lds128(wa + 512u), w2 = lds128(wa + 1024u);
+                        f[4 * hq + 0] = fmaf(gc2, w2.x, fmaf(gc1, w1.x, gc0 * w0.x));
+                        f[4 * hq + 1] = fmaf(gc2, w2.y, fmaf(gc1, w1.y, gc0 * w0.y));
+                        f[4 * hq + 2] = fmaf(gc2, w2.z, fmaf(gc1, w1.z, gc0 * w0.z));
+                        f[4 * hq + 3] = fmaf(gc2, w2.w, fmaf(gc1, w1.w, gc0 * w0.w));
+                    }
+                    const uint32_t w0 = pack_bf16(f[0], f[1]) & relu_mask2(hm.x), w1 = pack_bf16(f[2], f[3]) & relu_mask2(hm.y);
+                    const uint32_t w2 = pack_bf16(f[4], f[5]) & relu_mask2(hm.z), w3 = pack_bf16(f[6], f[7]) & relu_mask2(hm.w);
+                    st_shared_v4(h_base + (uint32_t)half * kBlk + row_off + xoff[q], w0, w1, w2, w3);
+                    stg128(gd + xoff[q], w0, w1, w2, w3);
+                }
+            }
+            arrive_act(act_local, act_leader, cx.rank, lane);
+            const size_t hoff = (size_t)half * 2 * kBlk;
+            // step 0: d g (linear)
+            bwd_epi<0>(t_half, h_half, xoff, nullptr, scr(kScrGG, 4) + hoff, 0.f, 0u, acc_bar, acc_phase);
+            arrive_act(act_local, act_leader, cx.rank, lane);
+            // step 1: d h7 (+ sigma head), relu'(h7)
+            bwd_epi<1>(t_half, h_half, xoff, sav(sav_h(7), 4) + hoff, scr(scr_gh(7), 4) + hoff, gs, wsig_half, acc_bar, acc_phase);
+            arrive_act(act_local, act_leader, cx.rank, lane);
+            // steps 2..7: d h6 .. d h1
+            for (int s = 2; s < 8; ++s) {
+                const int l = 8 - s;
+                bwd_epi<2>(t_half, h_half, xoff, sav(sav_h(l), 4) + hoff, scr(scr_gh(l), 4) + hoff, 0.f, 0u, acc_bar, acc_phase);
+                arrive_act(act_local, act_leader, cx.rank, lane);
+            }
+            // step 8: d h0 -> dPre0, spill only
+            bwd_epi<3>(t_half, h_half, xoff, sav(sav_h(0), 4) + hoff, scr(scr_gh(0), 4) + hoff, 0.f, 0u, acc_bar, acc_phase);
+            tc_fence_before();
+        }
+    }
+    tc_teardown(tmem_base, warp);
+}
+
+// =====================================================================================================================
+// wgrad: dW[out, in] += sum_rows dPre[row, out] * X[row, in];  db[out] += sum_rows dPre[row, out]
+// =====================================================================================================================
+struct WUnit {
+    int g_off, g_nb;        // gradient tensor in scratch: block offset, blocks per tile (4 = two 128-row output halves, 2 = one)
+    int x_off, x_nb;        // layer-input tensor in saved: block offset, blocks per tile
+    int layer;              // nerf_layer index (w_off, in, b_off)
+    int col_off, n_valid;   // columns [col_off, col_off + n_valid) of dW come from this X tensor
+    int bias;               // this unit also reduces the bias gradient
+};
+constexpr int kWUnits = 12;
+__constant__ WUnit c_wunits[kWUnits] = {
+    {scr_gh(0), 4, kSavPE, 1, 0, 0, 60, 1},
+    {scr_gh(1), 4, sav_h(0), 4, 1, 0, 256, 1},
+    {scr_gh(2), 4, sav_h(1), 4, 2, 0, 256, 1},
+    {scr_gh(3), 4, sav_h(2), 4, 3, 0, 256, 1},
+    {scr_gh(4), 4, sav_h(3), 4, 4, 0, 256, 1},
+    {scr_gh(5), 4, kSavPE, 1, 5, 0, 60, 0},
+    {scr_gh(5), 4, sav_h(4), 4, 5, 60, 256, 1},
+    {scr_gh(6), 4, sav_h(5), 4, 6, 0, 256, 1},
+    {scr_gh(7), 4, sav_h(6), 4, 7, 0, 256, 1},
+    {kScrGG, 4, sav_h(7), 4, 8, 0, 256, 1},
+    {kScrGD1, 2, kSavGL, 4, 9, 0, 256, 1},
+    {kScrGD1, 2, kSavDE, 1, 9, 256, 24, 0},
+};
+constexpr int kWCostTotal = 5 + 4 * 8 + 5 + 8 + 2 * 8 + 8 + 6 + 3;      // half-block loads per 64-row stage, all units: 83
+
+constexpr int kWStages = 3;
+constexpr uint32_t kWSlot = 65536;                                       // up to 8 half blocks of 8 KB
+constexpr uint32_t kWBarOff = kWStages * kWSlot;
+constexpr uint32_t kWSmem = kWBarOff + 128 + 1024;
+constexpr int kWThreads = 192;                                           // producer, MMA issuer, 4 reduce / flush warps
+
+struct WPiece { int u; long long t0, t1; };
+// CTA b owns the slice [b, b+1) * total / grid of the cost line (units laid end to end, each n_sub tiles x cost(u)); both
+// ends are rounded to tiles with the same function, so neighbouring CTAs agree on the boundary.
+__device__ __forceinline__ bool wpiece(int u, long long n_sub, long long lo, long long hi, long long& base, WPiece& pc) {
+    const WUnit un = c_wunits[u];
+    const long long cost = un.g_nb + un.x_nb;
+    const long long b0 = base, b1 = base + n_sub * cost;
+    base = b1;
+    if (hi <= b0 || lo >= b1) return false;
+    const long long a = lo > b0 ? lo : b0, b = hi < b1 ? hi : b1;
+    pc.u = u;
+    pc.t0 = (a - b0 + cost - 1) / cost;
+    pc.t1 = (b - b0 + cost - 1) / cost;
+    return pc.t0 < pc.t1;
+}
+
+__global__ void __launch_bounds__(kWThreads, 1)
+nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub, float* __restrict__ d_params) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t full = smem + kWBarOff, empty = full + 8 * kWStages, acc_full = empty + 8 * kWStages, tmem_empty = acc_full + 8,
+                   slot_addr = tmem_empty + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWStages; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 5); }
+        mbar_init(acc_full, 1);
+        mbar_init(tmem_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(slot_addr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot_addr));
+
+    const long long total = n_sub * kWCostTotal;
+    const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            long long base = 0;
+            for (int u = 0; u < kWUnits; ++u) {
+                WPiece pc;
+                if (!wpiece(u, n_sub, lo, hi, base, pc)) continue;
+                const WUnit un = c_wunits[u];
+                const uint8_t* gsrc = scratch + (size_t)un.g_off * n_sub * kBlk;
+                const uint8_t* xsrc = saved + (size_t)un.x_off * n_sub * kBlk;
+                const uint32_t bytes = (uint32_t)(un.g_nb + un.x_nb) * 8192u;
+                for (long long T = pc.t0; T < pc.t1; ++T) {
+                    for (int hs = 0; hs < 2; ++hs) {
+                        mbar_wait(empty + 8 * stage, phase ^ 1u);
+                        mbar_arrive_expect_tx(full + 8 * stage, bytes);
+                        const uint32_t dst = smem + stage * kWSlot;
+                        for (int i = 0; i < un.g_nb; ++i)
+                            bulk_g2s(dst + (uint32_t)i * 8192u, gsrc + ((size_t)T * un.g_nb + i) * kBlk + (size_t)hs * 8192, 8192u, full + 8 * stage);
+                        for (int j = 0; j < un.x_nb; ++j)
+                            bulk_g2s(dst + (uint32_t)(un.g_nb + j) * 8192u, xsrc + ((size_t)T * un.x_nb + j) * kBlk + (size_t)hs * 8192, 8192u,
+                                     full + 8 * stage);
+                        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        uint32_t stage = 0, phase = 0, te_phase = 0;
+        bool first_piece = true;
+        long long base = 0;
+        // A = dPre half blocks, B = X half blocks: MN-major SWIZZLE_128B, LBO = 8 KB (next 64 columns), SBO = 1 KB (next 8 rows of K)
+        const uint64_t d_hi = make_desc(0, 8192, 1024, kLayoutSW128);
+        for (int u = 0; u < kWUnits; ++u) {
+            WPiece pc;
+            if (!wpiece(u, n_sub, lo, hi, base, pc)) continue;
+            const WUnit un = c_wunits[u];
+            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)un.x_nb * 64u) | (1u << 15) | (1u << 16);
+            const int n_m = un.g_nb >> 1;
+            if (!first_piece) { mbar_wait(tmem_empty, te_phase); te_phase ^= 1u; tc_fence_after(); }
+            first_piece = false;
+            uint32_t acc = 0;
+            for (long long st = 0; st < 2 * (pc.t1 - pc.t0); ++st) {
+                mbar_wait(full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t a_s = smem + stage * kWSlot, b_s = a_s + (uint32_t)un.g_nb * 8192u;
+                if (elect_one()) {
+                    for (int m = 0; m < n_m; ++m) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = d_hi | (uint64_t)(((a_s + (uint32_t)m * 16384u + (uint32_t)k * 2048u) >> 4) & 0x3FFFu);
+                            const uint64_t bd = d_hi | (uint64_t)(((b_s + (uint32_t)k * 2048u) >> 4) & 0x3FFFu);
+                            mma_bf16(tmem + (uint32_t)m * 256u, ad, bd, idesc, acc | (uint32_t)k);
+                        }
+                    }
+                    mma_commit(empty + 8 * stage);
+                }
+                __syncwarp();
+                acc = 1;
+                if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+            }
+            if (elect_one()) mma_commit(acc_full);
+            __syncwarp();
+        }
+    } else {
+        const int w = warp - 2;                    // 0..3: G block reduced by this warp
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+        uint32_t stage = 0, phase = 0, af_phase = 0;
+        long long base = 0;
+        for (int u = 0; u < kWUnits; ++u) {
+            WPiece pc;
+            if (!wpiece(u, n_sub, lo, hi, base, pc)) continue;
+            const WUnit un = c_wunits[u];
+            const LayerDesc L = nerf_layer(un.layer);
+            const bool do_bias = un.bias && w < un.g_nb;
+            float s0 = 0.f, s1 = 0.f;
+            for (long long st = 0; st < 2 * (pc.t1 - pc.t0); ++st) {
+                mbar_wait(full + 8 * stage, phase);
+                if (do_bias) {
+                    const uint32_t blk = smem + stage * kWSlot + (uint32_t)w * 8192u + (uint32_t)(lane & 3) * 4u;
+#pragma unroll 8
+                    for (uint32_t row = 0; row < 64; ++row) {
+                        uint32_t x;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(blk + row * 128u + ((((uint32_t)lane >> 2) ^ (row & 7u)) << 4)));
+                        s0 += __uint_as_float(x << 16);
+                        s1 += __uint_as_float(x & 0xFFFF0000u);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + 8 * stage);
+                if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+            }
+            // ---- flush the accumulators of this piece
+            mbar_wait(acc_full, af_phase);
+            af_phase ^= 1u;
+            tc_fence_after();
+            const int n_m = un.g_nb >> 1;
+            float* __restrict__ dW = d_params + L.w_off;
+            for (int m = 0; m < n_m; ++m) {
+                const long long o = m * 128 + quad * 32 + lane;
+                for (int j = 0; j < un.x_nb * 2; ++j) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)quad << 21) + (uint32_t)m * 256u + (uint32_t)j * 32u, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int col = j * 32 + e;
+                        if (col < un.n_valid) atomicAdd(dW + o * L.in + un.col_off + col, __uint_as_float(v[e]));
+                    }
+                }
+            }
+            if (do_bias) {
+                atomicAdd(d_params + L.b_off + w * 64 + 2 * lane, s0);
+                atomicAdd(d_params + L.b_off + w * 64 + 2 * lane + 1, s1);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// output_layer_sigma (256 -> 1, input h7) and output_layer_rgb (128 -> 3, input h_d): weight and bias gradients from the
+// head gradients HG and the saved tiles.  Thread = one bf16x2 word (two columns) of h7 (threads 0..127) or h_d (128..191).
+__global__ void __launch_bounds__(192) nerf_head_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub,
+                                                              float* __restrict__ d_params) {
+    const int t = threadIdx.x;
+    const bool is_sigma = t < 128;
+    const int wq = is_sigma ? t : t - 128;                  // word index inside the tensor's row: block = wq / 32, word = wq % 32
+    const int blk = wq >> 5, wd = wq & 31;
+    const float4* __restrict__ hg = reinterpret_cast<const float4*>(scratch + (size_t)kScrBlocks * n_sub * kBlk);
+    const uint8_t* __restrict__ xt = saved + (size_t)(is_sigma ? sav_h(7) : kSavHD) * n_sub * kBlk;
+    const int nb = is_sigma ? 4 : 2;
+    float a0[3] = {0.f, 0.f, 0.f}, a1[3] = {0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long T = blockIdx.x; T < n_sub; T += gridDim.x) {
+        const uint8_t* tile = xt + ((size_t)T * nb + blk) * kBlk + (size_t)(wd & 3) * 4;
+        const float4* g = hg + T * kRowsSub;
+#pragma unroll 4
+        for (int row = 0; row < kRowsSub; ++row) {
+            const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(tile + row * 128 + ((((uint32_t)wd >> 2) ^ ((uint32_t)row & 7u)) << 4)));
+            const float x0 = __uint_as_float(x << 16), x1 = __uint_as_float(x & 0xFFFF0000u);
+            const float4 gg = __ldg(g + row);
+            if (is_sigma) { a0[0] = fmaf(gg.w, x0, a0[0]); a1[0] = fmaf(gg.w, x1, a1[0]); }
+            else {
+                a0[0] = fmaf(gg.x, x0, a0[0]); a1[0] = fmaf(gg.x, x1, a1[0]);
+                a0[1] = fmaf(gg.y, x0, a0[1]); a1[1] = fmaf(gg.y, x1, a1[1]);
+                a0[2] = fmaf(gg.z, x0, a0[2]); a1[2] = fmaf(gg.z, x1, a1[2]);
+            }
+            if (t == 0 || t == 128) { bsum[0] += gg.x; bsum[1] += gg.y; bsum[2] += gg.z; bsum[3] += gg.w; }
+        }
+    }
+    const int col = blk * 64 + wd * 2;
+    if (is_sigma) {
+        const LayerDesc L = nerf_layer(10);
+        atomicAdd(d_params + L.w_off + col, a0[0]);
+        atomicAdd(d_params + L.w_off + col + 1, a1[0]);
+        if (t == 0) atomicAdd(d_params + L.b_off, bsum[3]);
+    } else {
+        const LayerDesc L = nerf_layer(11);
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            atomicAdd(d_params + L.w_off + n * 128 + col, a0[n]);
+            atomicAdd(d_params + L.w_off + n * 128 + col + 1, a1[n]);
+        }
+        if (t == 128) { atomicAdd(d_params + L.b_off, bsum[0]); atomicAdd(d_params + L.b_off + 1, bsum[1]); atomicAdd(d_params + L.b_off + 2, bsum[2]); }
+    }
+}
+
+int pair_grid(long long rows, unsigned* grid);   // mlp_tc.cu
+
+}  // namespace tc
+}  // namespace b2r
+
+extern "C" size_t b2r_mlp_tc_bwd_packed_bytes(int model_kind) {
+    return model_kind == B2R_MODEL_NERF ? (size_t)b2r::tc::kBwdPackedBytes : 0;
+}
+
+extern "C" int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* packed_out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF, "b2r_mlp_tc_pack_bwd: only the NeRF model has a tensor-core training path (kind %d)", model_kind);
+    B2R_CHECK_ARG(params && packed_out, "b2r_mlp_tc_pack_bwd: NULL pointer");
+    B2R_CHECK_ARG(((uintptr_t)packed_out & 15) == 0, "b2r_mlp_tc_pack_bwd: packed_out must be 16-byte aligned");
+    long long threads = tc::kBwdChunkBytes / 16;
+    tc::nerf_pack_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, (uint8_t*)packed_out);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_pack_bwd");
+    return 0;
+}
+
+extern "C" size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows) {
+    if (model_kind != B2R_MODEL_NERF || rows < 0) return 0;
+    return (size_t)b2r::tc::n_sub_tiles(rows) * ((size_t)b2r::tc::kScrBlocks * b2r::tc::kBlk + b2r::tc::kRowsSub * 16);
+}
+
+extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows, const float* raw, const float* d_raw,
+                                    const void* saved, void* scratch, size_t scratch_bytes, float* d_params, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF, "b2r_mlp_tc_train_bwd: only the NeRF model has a tensor-core training path (kind %d)", model_kind);
+    B2R_CHECK_ARG(packed_bwd && raw && d_raw && saved && scratch && d_params, "b2r_mlp_tc_train_bwd: NULL pointer");
+    B2R_CHECK_ARG((((uintptr_t)packed_bwd | (uintptr_t)raw | (uintptr_t)d_raw | (uintptr_t)saved | (uintptr_t)scratch | (uintptr_t)d_params) & 15) == 0,
+                  "b2r_mlp_tc_train_bwd: buffers must be 16-byte aligned");
+    B2R_CHECK_ARG(rows >= 0, "b2r_mlp_tc_train_bwd: negative row count");
+    B2R_CHECK_ARG(scratch_bytes >= b2r_mlp_tc_train_scratch_bytes(model_kind, rows), "b2r_mlp_tc_train_bwd: scratch too small (%zu B)", scratch_bytes);
+    if (rows == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = 0;
+    int rc = tc::pair_grid(rows, &grid);
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc bwd smem attribute");
+    if (rc) return rc;
+    tc::nerf_tc_bwd_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed_bwd, rows, (const float4*)raw, (const float4*)d_raw,
+                                                                      (const uint8_t*)saved, (uint8_t*)scratch);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (dgrad)");
+    const long long n_sub = tc::n_sub_tiles(rows);
+    int dev = 0, sms = 0;
+    rc = cuda_result(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
+    if (rc) return rc;
+    const long long work = n_sub * tc::kWUnits;
+    unsigned wgrid = (unsigned)(work < sms ? work : sms);
+    tc::nerf_tc_wgrad_kernel<<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (wgrad)");
+    unsigned hgrid = (unsigned)(n_sub < 4LL * sms ? n_sub : 4LL * sms);
+    tc::nerf_head_wgrad_kernel<<<hgrid, 192, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (heads)");
+    return 0;
+}

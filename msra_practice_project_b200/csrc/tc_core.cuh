@@ -1,0 +1,303 @@
+// Shared device-side machinery of the fused tensor-core MLP kernels (mlp_tc.cu: inference + training forward,
+// mlp_tc_train.cu: reverse mode): schedules, packed-weight layout, shared-memory map, mbarrier protocol, the weight
+// producer / relay / MMA-issuer loops of a CTA pair.  See mlp_tc.cu for the design.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace b2r {
+namespace tc {
+
+using namespace umma;
+
+constexpr int kRowsSub = 128;
+constexpr int kRowsTile = 256;                          // rows per CTA per iteration (a pair covers 512)
+constexpr int kStages = 3;
+constexpr uint32_t kStageBytes = 16384;                 // 128 weight rows x 64 K bf16 (this CTA's N-half)
+constexpr uint32_t kPeBytes = 16384;                    // 128 rows x 64 bf16 (SW128): pos-enc / dir-enc block
+constexpr uint32_t kHBytes = 65536;                     // 4 K-blocks of 128 rows x 64 bf16
+constexpr uint32_t kSubBytes = kPeBytes + kHBytes;      // 80 KB per sub-tile
+constexpr uint32_t kRingOff = 2 * kSubBytes;
+
+constexpr int kCtrlWarps = 4;                           // 0 producer, 1 MMA issuer / relay (+TMEM alloc), 2-3 idle
+constexpr int kEpiWarps = 16;                           // 2 sub-tiles x 2 column halves x 4 TMEM lane quadrants
+constexpr int kThreads = (kCtrlWarps + kEpiWarps) * 32; // 640
+
+// ---- schedules (chunks of 64 K) ---------------------------------------------------------------------------
+// A step = one layer's MMAs for one sub-tile: n_pre chunks whose A operand is the aux block (pos-enc),
+// then n_h chunks reading the K-blocks of h, then n_post chunks reading the aux block again (dir-enc /
+// view direction; only kPostMmas x 16 K of it are issued).
+struct NerfSched {       // step 0..7 = layers_pos.0..7, 8 = layers_dir.0, 9 = layers_dir.1
+    static constexpr int kSteps = 10;
+    __host__ __device__ static constexpr int n_pre(int s, int) { return (s == 0 || s == 5) ? 1 : 0; }
+    __host__ __device__ static constexpr int n_h(int s, int) { return s == 0 ? 0 : 4; }
+    __host__ __device__ static constexpr int n_post(int s, int) { return s == 9 ? 1 : 0; }
+    __host__ __device__ static constexpr int n(int s) { return s == 9 ? 128 : 256; }
+    static constexpr int kPostMmas = 2;                  // dir-enc: 24 -> 32 K
+};
+struct FilmSched {       // steps 0..6 = hidden_layers.0..6, step 7 = hidden_layer_rgb ([h | dir]); flag = use_dir
+    static constexpr int kSteps = 8;
+    __host__ __device__ static constexpr int n_pre(int, int) { return 0; }
+    __host__ __device__ static constexpr int n_h(int, int) { return 4; }
+    __host__ __device__ static constexpr int n_post(int s, int use_dir) { return (s == 7 && use_dir) ? 1 : 0; }
+    __host__ __device__ static constexpr int n(int) { return 256; }
+    static constexpr int kPostMmas = 1;                  // view direction: 3 -> 16 K
+};
+template <class S>
+__host__ __device__ constexpr uint32_t half_bytes(int s) { return (uint32_t)(S::n(s) / 2) * 128u; }
+// packed chunks of a step (the post chunk is always stored, even when use_dir = 0 skips it)
+template <class S>
+__host__ __device__ constexpr int stored_chunks(int s) { return S::n_pre(s, 1) + S::n_h(s, 1) + S::n_post(s, 1); }
+template <class S>
+__host__ __device__ constexpr long long step_base(int s) {
+    long long off = 0;
+    for (int t = 0; t < s; ++t) off += 2LL * stored_chunks<S>(t) * half_bytes<S>(t);
+    return off;
+}
+
+constexpr long long kNerfChunkBytes = step_base<NerfSched>(NerfSched::kSteps);      // 1,196,032
+constexpr long long kFilmChunkBytes = step_base<FilmSched>(FilmSched::kSteps);      // 1,081,344
+static_assert(kNerfChunkBytes == 1196032 && kFilmChunkBytes == 1081344, "packed chunk bytes");
+// NeRF fp32 tables after the chunks: bias[10][256] | w_sigma[256] | w_rgb[3][128] | b_sigma, b_rgb[3]
+constexpr int kNerfTabBias = 0, kNerfTabWSigma = 2560, kNerfTabWRgb = 2816, kNerfTabBHead = 3200, kNerfTabFloats = 3204;
+constexpr long long kNerfPackedBytes = kNerfChunkBytes + kNerfTabFloats * 4;
+// FiLM fp32 tables: scale[8][256] | shift[8][256] | w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
+//                   w_sigma[256] | w_rgb[3][256] | b_sigma, b_rgb[3]
+constexpr int kFSc = 0, kFSh = 2048, kFW0 = 4096, kFS0 = 4864, kFT0 = 5120, kFWS = 5376, kFWR = 5632, kFBH = 6400, kFilmTabFloats = 6404;
+constexpr long long kFilmPackedBytes = kFilmChunkBytes + kFilmTabFloats * 4;
+
+// ---- packed weights: which (step, chunk, half, row, 16-byte group) a byte of the chunk area belongs to ----
+// one thread per 16-byte group: (step, chunk, half, row of the half, 8 consecutive k)
+template <class S>
+__device__ __forceinline__ void locate(long long byte, int& s, int& c, int& hf, int& row, int& grp) {
+    s = 0;
+    while (s + 1 < S::kSteps && byte >= step_base<S>(s + 1)) ++s;
+    long long in_step = byte - step_base<S>(s);
+    const int hb = (int)half_bytes<S>(s);
+    int hc = (int)(in_step / hb);
+    c = hc >> 1; hf = hc & 1;
+    int rem = (int)(in_step % hb);
+    row = rem / 128; grp = (rem % 128) / 16;
+}
+
+
+// ---- tiled activation tensors kept for the reverse mode (training) ------------------------------------------------
+// A tensor [rows x C] bf16 is stored as blocks of [128 rows x 64 columns]: exactly the K-major SWIZZLE_128B shared-memory
+// image of that block (16 KB; 16-byte chunk c of row r at c ^ (r & 7)).  The forward / dgrad kernels write a block with
+// the same per-thread offsets they use for shared memory, and the wgrad kernel streams half blocks (64 rows, 8 KB
+// contiguous) back with the bulk-copy engine and feeds them to tcgen05 as MN-major operands (row index = K) with no
+// transposition anywhere.  Tensors are stored one after the other (tensor-major); block (T, kb) of a tensor with nb
+// blocks per 128-row tile T sits at tensor_base + (T * nb + kb) * 16 KB.
+constexpr uint32_t kBlk = 16384;
+// forward ("saved"): PE | H0..H7 | GL (layers_dir.0 output) | DE | HD   -- block offsets in units of n_sub blocks
+constexpr int kSavPE = 0, kSavH0 = 1, kSavGL = 33, kSavDE = 37, kSavHD = 38, kSavBlocks = 40;
+// reverse ("scratch"): GD1 (d pre-activation of layers_dir.1) | GG (d layers_dir.0 output) | GH0..GH7 (d pre-activations of the
+// trunk), then the head gradients HG[row] = (d rgb pre-sigmoid x3, d sigma pre-relu) as float4
+constexpr int kScrGD1 = 0, kScrGG = 2, kScrGH0 = 6, kScrBlocks = 38;
+__host__ __device__ constexpr int sav_h(int l) { return kSavH0 + 4 * l; }
+__host__ __device__ constexpr int scr_gh(int l) { return kScrGH0 + 4 * l; }
+// 128-row sub-tiles covered by the CTA pairs (every pair always processes 4 sub-tiles)
+__host__ __device__ inline long long n_sub_tiles(long long rows) {
+    long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
+    return ((n_tiles + 1) / 2) * 4;
+}
+__device__ __forceinline__ void stg128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ldg128(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// ---- shared-memory map (offsets from the 1024-aligned base; identical in both CTAs of a pair) -------------------
+constexpr uint32_t kTabOff = kRingOff + kStages * kStageBytes;          // fp32 tables (NeRF bias / head weights)
+constexpr uint32_t kTabBytes = kNerfTabFloats * 4;                      // 12,816
+constexpr uint32_t kPartOff = kTabOff + kTabBytes;                      // head partial sums: 2 x 128 x float4
+constexpr uint32_t kPartBytes = 2 * kRowsSub * 16;
+constexpr uint32_t kBarOff = kPartOff + kPartBytes;                     // mbarriers + TMEM slot
+constexpr uint32_t kSmemBytes = kBarOff + 128 + 1024;                   // + alignment slack
+static_assert(kBarOff % 8 == 0 && kSmemBytes <= 232448, "shared-memory budget");
+
+struct Ctx {
+    uint32_t smem;        // 1024-aligned shared base (shared-window address)
+    uint32_t w_full, w_empty, act_ready, acc_full, tmem_slot;
+    uint32_t rank;        // CTA rank in the pair (0 = leader: issues the MMAs)
+};
+
+__device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
+    Ctx c;
+    c.smem = (smem_u32(raw) + 1023u) & ~1023u;
+    c.w_full = c.smem + kBarOff;
+    c.w_empty = c.w_full + 8 * kStages;
+    c.act_ready = c.w_empty + 8 * kStages;
+    c.acc_full = c.act_ready + 16;
+    c.tmem_slot = c.acc_full + 16;
+    c.rank = cluster_ctarank();
+    return c;
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// Positional encoding of 3 values with L octaves as 3L packed bf16x2 words, in the reference's order
+// [sin(2^i x)(3), cos(2^i x)(3)] per octave (nerf/nerf.py:44-49): 6 values = 3 words per octave.
+// Octave 0 uses the accurate sincosf; higher octaves the double-angle recurrence (abs. error grows ~2x per
+// octave, < 1e-4 at octave 9: far below the bf16 rounding of the operand).
+template <int L>
+__device__ __forceinline__ void posenc_words(const float x[3], uint32_t* w) {
+    float s[3], c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) sincosf(x[k], &s[k], &c[k]);
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+        w[3 * i + 0] = pack_bf16(s[0], s[1]);
+        w[3 * i + 1] = pack_bf16(s[2], c[0]);
+        w[3 * i + 2] = pack_bf16(c[1], c[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float s2 = 2.0f * s[k] * c[k];
+            float c2 = 1.0f - 2.0f * s[k] * s[k];
+            s[k] = s2; c[k] = c2;
+        }
+    }
+}
+
+// tile pairs walked by the cluster: pair p -> tiles 2p (leader) and 2p+1 (peer)
+struct PairLoop {
+    long long n_pairs, first, stride;
+    __device__ PairLoop(long long rows) {
+        long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
+        n_pairs = (n_tiles + 1) / 2;
+        first = blockIdx.x >> 1;
+        stride = gridDim.x >> 1;
+    }
+};
+
+// weight producer: one thread per CTA streams ITS half of every chunk in schedule order (each step twice: once per sub-tile)
+template <class S>
+__device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __restrict__ packed, const PairLoop& pl, int n_steps, int flag) {
+    uint32_t stage = 0, phase = 0;
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        for (int s = 0; s < n_steps; ++s) {
+            const int nc = S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag);
+            const uint32_t bytes = half_bytes<S>(s);
+            const uint8_t* src_w = packed + step_base<S>(s) + (size_t)cx.rank * bytes;
+            for (int g = 0; g < 2; ++g) {
+                for (int c = 0; c < nc; ++c) {
+                    mbar_wait_cluster(cx.w_empty + 8 * stage, phase ^ 1u);
+                    mbar_arrive_expect_tx(cx.w_full + 8 * stage, bytes);
+                    bulk_g2s(cx.smem + kRingOff + stage * kStageBytes, src_w + (size_t)c * 2 * bytes, bytes, cx.w_full + 8 * stage);
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    }
+}
+
+// peer CTA: forward "my half of this stage has landed" to the leader's ring barrier (count 2 there)
+template <class S>
+__device__ __forceinline__ void relay_loop(const Ctx& cx, const PairLoop& pl, int n_steps, int flag) {
+    uint32_t stage = 0, phase = 0;
+    const uint32_t remote0 = mapa(cx.w_full, 0);
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        for (int s = 0; s < n_steps; ++s) {
+            const int nc = 2 * (S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag));
+            for (int c = 0; c < nc; ++c) {
+                mbar_wait_cluster(cx.w_full + 8 * stage, phase);
+                mbar_arrive_cluster(remote0 + 8 * stage);
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    }
+}
+
+// MMA issuer: warp 1 of the leader CTA, converged (every lane walks the schedule and polls the barriers; one elected
+// lane issues), so the descriptors live in uniform registers.  Alternates the two sub-tiles step by step.
+template <class S>
+__device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, const PairLoop& pl, int n_steps, int flag) {
+    uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0;
+    const uint64_t d_hi = desc_sw128(0);                          // A and B: K-major SWIZZLE_128B, zero address field
+    auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_addr, uint32_t idesc, uint32_t accumulate, int n_mma) {
+        mbar_wait_cluster(cx.w_full + 8 * stage, phase);
+        tc_fence_after();
+        const uint32_t b_addr = cx.smem + kRingOff + stage * kStageBytes;
+        const uint64_t ad = d_hi | (uint64_t)((a_addr >> 4) & 0x3FFFu);
+        const uint64_t bd = d_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+        if (elect_one()) {
+            mma_bf16_2cta(d_tmem, ad, bd, idesc, accumulate);
+            for (int k = 1; k < n_mma; ++k) mma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);   // +32 B = next 16 K
+            mma_commit_2cta(cx.w_empty + 8 * stage, (uint16_t)3);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    };
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        for (int s = 0; s < n_steps; ++s) {
+            const uint32_t idesc = make_idesc_bf16(256, (uint32_t)S::n(s));
+            const int n_pre = S::n_pre(s, flag), n_h = S::n_h(s, flag), n_post = S::n_post(s, flag);
+            for (int g = 0; g < 2; ++g) {
+                if (g == 0) { mbar_wait_cluster(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
+                else { mbar_wait_cluster(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
+                const uint32_t a_base = cx.smem + (uint32_t)g * kSubBytes;
+                uint32_t acc = 0;
+                for (int c = 0; c < n_pre; ++c) { issue_chunk(d_tmem, a_base, idesc, acc, 4); acc = 1; }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < n_h) { issue_chunk(d_tmem, a_base + kPeBytes + (uint32_t)c * 16384u, idesc, acc, 4); acc = 1; }
+                }
+                for (int c = 0; c < n_post; ++c) issue_chunk(d_tmem, a_base, idesc, 1u, S::kPostMmas);
+                if (elect_one()) mma_commit_2cta(cx.acc_full + 8 * g, (uint16_t)3);
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// common prologue: barriers, TMEM allocation (both CTAs), cluster rendezvous; returns the TMEM base address
+__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 16); mbar_init(cx.acc_full + 8 * g, 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2cta(cx.tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(cx.tmem_slot));
+    return tmem_base;
+}
+__device__ __forceinline__ void tc_teardown(uint32_t tmem_base, int warp) {
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2cta(tmem_base, 512);
+}
+
+// epilogue warp -> leader's act_ready[g]: this warp's rows of the next A operand are written and its TMEM reads are done
+__device__ __forceinline__ void arrive_act(uint32_t act_bar_local, uint32_t act_bar_leader, uint32_t rank, int lane) {
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (rank == 0) mbar_arrive_release_cluster_local(act_bar_local);
+        else mbar_arrive_cluster(act_bar_leader);
+    }
+}
+
+// packed fp32x2 add (FADD2): {a0,a1} += {b0,b1}
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+
+}  // namespace tc
+}  // namespace b2r

@@ -37,11 +37,21 @@ def _numel(keys):
     return sum(o * i + o for _, (o, i) in keys)
 
 
+# SirenNeRF (nerf/nerf.py:120-170): same topology as NeRF with sin(30 (W x + b)) layers and raw 3-d inputs
+SIREN_KEYS = (
+    [(f"layers_pos.{i}", s) for i, s in enumerate(
+        [(256, 3), (256, 256), (256, 256), (256, 256), (256, 256), (256, 259), (256, 256), (256, 256)])]
+    + [("layers_dir.0", (256, 256)), ("layers_dir.1", (128, 259)),
+       ("output_layer_sigma", (1, 256)), ("output_layer_rgb", (3, 128))]
+)
+
 NERF_NUMEL = _numel(NERF_KEYS)          # 593,924  
 FILM_NUMEL = _numel(FILM_KEYS_DIR)      # 529,156  
+SIREN_NUMEL = _numel(SIREN_KEYS)        # 562,052
 
 KIND_NERF = 0
 KIND_FILM = 1
+KIND_SIREN = 2
 
 
 def model_kind(model) -> int:
@@ -52,7 +62,9 @@ def model_kind(model) -> int:
         w0 = model.layers_pos[0].weight
         if tuple(w0.shape) == (256, 60):
             return KIND_NERF
-        raise TypeError("SirenNeRF-shaped model (layers_pos.0 is %s): not supported by this build" % (tuple(w0.shape),))
+        if tuple(w0.shape) == (256, 3):
+            return KIND_SIREN
+        raise TypeError("NeRF-shaped model with an unknown first layer %s" % (tuple(w0.shape),))
     if all(hasattr(model, a) for a in ("input_layer", "hidden_layers", "hidden_layer_rgb", "output_layer_rgb")):
         return KIND_FILM
     raise TypeError(
@@ -66,6 +78,8 @@ def param_list(model, kind: int | None = None):
     sd = dict(model.named_parameters())
     if kind == KIND_NERF:
         keys = NERF_KEYS
+    elif kind == KIND_SIREN:
+        keys = SIREN_KEYS
     else:
         keys = FILM_KEYS_DIR if getattr(model, "use_dir", True) else FILM_KEYS_NODIR
     out = []
@@ -117,6 +131,32 @@ class NeRF(torch.nn.Module):
         dims = [(60, 256)] + [(256, 256)] * 4 + [(316, 256)] + [(256, 256)] * 2
         self.layers_pos = torch.nn.ModuleList([_Dense(i, o, "relu") for i, o in dims])
         self.layers_dir = torch.nn.ModuleList([_Dense(256, 256, "linear"), _Dense(280, 128, "relu")])
+        self.output_layer_sigma = _Dense(256, 1, "relu")
+        self.output_layer_rgb = _Dense(128, 3, "sigmoid")
+
+    def forward(self, x):
+        from . import ops
+        return ops.mlp_points(self, x)
+
+
+class _Siren(torch.nn.Linear):
+    """Linear layer whose output goes through sin(30 x) (nerf/nerf.py:97-117): U(+-sqrt(6/in)/30) weights, zero bias."""
+
+    def reset_parameters(self):
+        torch.nn.init.uniform_(self.weight, -np.sqrt(6 / self.in_features) / 30, np.sqrt(6 / self.in_features) / 30)
+        torch.nn.init.zeros_(self.bias)
+
+
+class SirenNeRF(torch.nn.Module):
+    """NeRF topology with SIREN layers and raw (un-encoded) inputs; parameter names and init order as
+    nerf/nerf.py:120-150 (selected by `use_siren`, nerf/train_nerf.py:89-91)."""
+
+    def __init__(self):
+        super().__init__()
+        dims = [(3, 256)] + [(256, 256)] * 4 + [(259, 256)] + [(256, 256)] * 2
+        self.layers_pos = torch.nn.ModuleList([_Siren(i, o) for i, o in dims])
+        torch.nn.init.uniform_(self.layers_pos[0].weight, -1 / 30, 1 / 30)            # nerf.py:135
+        self.layers_dir = torch.nn.ModuleList([_Dense(256, 256, "linear"), _Siren(259, 128)])
         self.output_layer_sigma = _Dense(256, 1, "relu")
         self.output_layer_rgb = _Dense(128, 3, "sigmoid")
 

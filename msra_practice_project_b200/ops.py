@@ -33,15 +33,17 @@ def get_mlp_precision() -> str:
     return _MLP_PRECISION
 
 
-# GEMM engine of the layer-wise path used whenever gradients are required: "fp32" = CUDA-core FMAs (exact: the parity
-# path, default), "tf32" = the same algorithm with every GEMM on the tensor cores (tcgen05 kind::tf32, fp32 accumulate).
+# Arithmetic of the path used whenever gradients are required: "fp32" = layer-wise, CUDA-core FMAs (exact: the parity path,
+# default), "tf32" = the same algorithm with every GEMM on the tensor cores (tcgen05 kind::tf32, fp32 accumulate), "bf16" =
+# the fused tensor-core training path (mlp_tc.cu forward with saved bf16 activations + mlp_tc_train.cu reverse mode; NeRF
+# model only -- other models fall back to "tf32" layer-wise GEMMs).
 _GRAD_PRECISION = "fp32"
 
 
 def set_grad_precision(p: str) -> str:
     global _GRAD_PRECISION
-    if p not in ("fp32", "tf32"):
-        raise ValueError("grad precision must be 'fp32' or 'tf32'")
+    if p not in ("fp32", "tf32", "bf16"):
+        raise ValueError("grad precision must be 'fp32', 'tf32' or 'bf16'")
     old, _GRAD_PRECISION = _GRAD_PRECISION, p
     return old
 
@@ -283,6 +285,65 @@ class _MlpF32(torch.autograd.Function):
         return d_flat, d_film, None, None, None, None, None, None
 
 
+_pack_bwd_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def _packed_bwd_weights(model, kind: int, flat: torch.Tensor) -> torch.Tensor:
+    """transposed bf16 weight images for the dgrad kernel, cached per model like the forward pack."""
+    ps = models.param_list(model, kind)
+    key = tuple((p.data_ptr(), p._version) for p in ps)
+    hit = _pack_bwd_cache.get(model)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    nbytes = lib().b2r_mlp_tc_bwd_packed_bytes(kind)
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=flat.device)
+    with torch.cuda.device(flat.device):
+        check(lib().b2r_mlp_tc_pack_bwd(kind, ptr(flat), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_bwd")
+    _pack_bwd_cache[model] = (key, packed)
+    return packed
+
+
+class _MlpTcTrain(torch.autograd.Function):
+    """Fused bf16 tensor-core forward that keeps the layer inputs as tiled bf16 tensors, and its reverse mode
+    (dgrad + wgrad + heads, mlp_tc_train.cu).  NeRF model only."""
+
+    @staticmethod
+    def forward(ctx, flat, model, kind, rays, z, x):
+        inp, rows, keep = _make_input(rays, z, x, None)
+        dev = flat.device
+        raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        fd = flat.detach()
+        packed = _packed_weights(model, kind, fd, None, True)
+        nbytes = lib().b2r_mlp_tc_train_saved_bytes(kind, rows)
+        saved = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+        if rows > 0:
+            with torch.cuda.device(dev):
+                check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, _stream(flat)),
+                      "b2r_mlp_tc_train_fwd")
+        ctx.model, ctx.kind, ctx.rows = model, kind, rows
+        ctx.save_for_backward(flat, raw, saved)
+        del keep
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        flat, raw, saved = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 6
+        dev = flat.device
+        d_flat = torch.zeros_like(flat)
+        if ctx.rows == 0:
+            return d_flat, None, None, None, None, None
+        d_raw = _cuda_f32(d_raw, "d_raw")
+        packed_bwd = _packed_bwd_weights(ctx.model, ctx.kind, flat.detach())
+        sbytes = lib().b2r_mlp_tc_train_scratch_bytes(ctx.kind, ctx.rows)
+        scratch = torch.empty((sbytes,), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().b2r_mlp_tc_train_bwd(ctx.kind, ptr(packed_bwd), ctx.rows, ptr(raw), ptr(d_raw), ptr(saved), ptr(scratch),
+                                             sbytes, ptr(d_flat), _stream(flat)), "b2r_mlp_tc_train_bwd")
+        return d_flat, None, None, None, None, None
+
+
 def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, x: torch.Tensor | None = None,
         grid: tuple | None = None, precision: str | None = None, sigma_only: bool = False) -> torch.Tensor:
     """Evaluate the radiance field on rows described by (rays, z) | x | grid -> raw[rows,4]
@@ -308,7 +369,9 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
     if needs_grad:
         if grid is not None:
             raise RuntimeError("grid queries are inference-only")
-        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, 1 if _GRAD_PRECISION == "tf32" else 0)
+        if _GRAD_PRECISION == "bf16" and kind == models.KIND_NERF:
+            return _MlpTcTrain.apply(flat, net, kind, rays, z, x)
+        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, 0 if _GRAD_PRECISION == "fp32" else 1)
     inp, rows, keep = _make_input(rays, z, x, grid)
     raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     if rows == 0:

@@ -130,6 +130,28 @@ def nerf_mlp(p: dict, x: np.ndarray) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# (8f-1)  SirenNeRF MLP                                          nerf/nerf.py:97-170
+# --------------------------------------------------------------------------------------
+def siren_nerf_mlp(p: dict, x: np.ndarray) -> np.ndarray:
+    """sin(30 (W x + b)) trunk on raw inputs, skip [pos | h] into layer 5, relu sigma head, linear layers_dir.0,
+    sin layers_dir.1 on [h | dir], sigmoid rgb head.  Keys as NeRF."""
+    x = np.asarray(x, F32)
+    pos, d = x[:, :3], x[:, 3:]
+    sin30 = lambda a: np.sin(F32(30.0) * a, dtype=F32)
+    h = sin30(_linear(pos, p["layers_pos.0.weight"], p["layers_pos.0.bias"]))
+    for l in range(1, 5):
+        h = sin30(_linear(h, p[f"layers_pos.{l}.weight"], p[f"layers_pos.{l}.bias"]))
+    h = np.concatenate([pos, h], -1)                                  # nerf.py:158 (pos first)
+    for l in range(5, 8):
+        h = sin30(_linear(h, p[f"layers_pos.{l}.weight"], p[f"layers_pos.{l}.bias"]))
+    sigma = np.maximum(_linear(h, p["output_layer_sigma.weight"], p["output_layer_sigma.bias"]), F32(0))
+    h = _linear(h, p["layers_dir.0.weight"], p["layers_dir.0.bias"])
+    h = sin30(_linear(np.concatenate([h, d], -1), p["layers_dir.1.weight"], p["layers_dir.1.bias"]))
+    rgb = _sigmoid(_linear(h, p["output_layer_rgb.weight"], p["output_layer_rgb.bias"]))
+    return np.concatenate([rgb, sigma], -1).astype(F32)
+
+
+# --------------------------------------------------------------------------------------
 # a8  FiLM-SIREN MLP                          pi_GAN/modules.py:22-25, 96-99, 101-118
 # --------------------------------------------------------------------------------------
 def film_siren_mlp(p: dict, film: np.ndarray, x: np.ndarray, use_dir: bool = True, w0: float = 30.0,

@@ -199,6 +199,85 @@ static int run_probe3(int kmaj) {
     return bad ? 1 : 0;
 }
 
+static uint16_t bf16_bits(float f);
+
+// ---- bf16 MN-major probe (wgrad operand layout): D[128 m, N n] = sum_k A[k][m] * B[k][n], K = 64 rows.
+// Operands are the tiled activation images the training kernels spill: blocks of [K rows x 64 columns] bf16, row pitch
+// 128 B, 16-byte chunk c of row r at c ^ (r & 7) (the K-major SWIZZLE_128B image of a [rows x 64] tile, re-read with the
+// row index as K).  Stage = half blocks of 64 rows (8 KB), M / N extend over consecutive half blocks.
+__global__ void __launch_bounds__(128, 1) probe4_kernel(const uint8_t* a_img, const uint8_t* b_img, int n_cols, uint32_t lbo, uint32_t sbo,
+                                                        float* d_out) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* gen = raw + (base - smem_u32(raw));
+    const uint32_t a_s = base, b_s = base + 16384, bar = base + 16384 + 32768, slot = bar + 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (warp == 0) tmem_alloc(slot, 256);
+    tc_fence_before(); __syncthreads(); tc_fence_after();
+    uint32_t tmem; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+    for (int i = threadIdx.x; i < 16384 / 16; i += 128) reinterpret_cast<uint4*>(gen)[i] = reinterpret_cast<const uint4*>(a_img)[i];
+    for (int i = threadIdx.x; i < 32768 / 16; i += 128) reinterpret_cast<uint4*>(gen + 16384)[i] = reinterpret_cast<const uint4*>(b_img)[i];
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)n_cols) | (1u << 15) | (1u << 16);     // A and B MN-major
+        for (int k = 0; k < 4; ++k) {      // 4 x K=16 = two 8-row groups each
+            uint64_t ad = make_desc(a_s + k * 2048, lbo, sbo, 2), bd = make_desc(b_s + k * 2048, lbo, sbo, 2);
+            mma_bf16(tmem, ad, bd, idesc, k != 0);
+        }
+        mma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    for (int j = 0; j < n_cols / 32; ++j) {
+        uint32_t x[32];
+        tmem_ld32(tmem + ((uint32_t)warp << 21) + j * 32, x);
+        tmem_ld_wait();
+        for (int e = 0; e < 32; ++e) d_out[r * 256 + j * 32 + e] = __uint_as_float(x[e]);
+    }
+    tc_fence_before(); __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static int run_probe4(int n_cols, uint32_t lbo, uint32_t sbo) {
+    const int M = 128, N = 256, K = 64;
+    std::vector<float> A(K * M), B(K * N), D(M * N, 0.f);
+    srand(23);
+    for (auto& x : A) x = (float)(rand() % 9 - 4);
+    for (auto& x : B) x = (float)(rand() % 7 - 3);
+    for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < K; ++k) s += A[k * M + m] * B[k * N + n]; D[m * N + n] = s; }
+    std::vector<uint8_t> a_img(16384), b_img(32768);
+    auto put = [&](std::vector<uint8_t>& img, int k, int col, float v) {
+        uint16_t h = bf16_bits(v);
+        uint32_t off = (uint32_t)(col / 64) * 8192u + sw128_offset((uint32_t)k, (uint32_t)((col % 64) / 8)) + (uint32_t)(col % 8) * 2u;
+        memcpy(&img[off], &h, 2);
+    };
+    for (int k = 0; k < K; ++k) for (int m = 0; m < M; ++m) put(a_img, k, m, A[k * M + m]);
+    for (int k = 0; k < K; ++k) for (int n = 0; n < N; ++n) put(b_img, k, n, B[k * N + n]);
+    uint8_t *da, *db; float* dd;
+    cudaMalloc(&da, 16384); cudaMalloc(&db, 32768); cudaMalloc(&dd, M * N * 4);
+    cudaMemcpy(da, a_img.data(), 16384, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, b_img.data(), 32768, cudaMemcpyHostToDevice);
+    cudaMemset(dd, 0xff, M * N * 4);
+    cudaFuncSetAttribute(probe4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    probe4_kernel<<<1, 128, 64 * 1024>>>(da, db, n_cols, lbo, sbo, dd);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("PROBE4 bf16 MN-major : CUDA error %s\n", cudaGetErrorString(e)); return 2; }
+    std::vector<float> got(M * N);
+    cudaMemcpy(got.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
+    int bad = 0, first = -1;
+    for (int m = 0; m < M; ++m) for (int n = 0; n < n_cols; ++n) if (got[m * N + n] != D[m * N + n]) { if (first < 0) first = m * N + n; ++bad; }
+    printf("PROBE4 bf16 MN-major A,B (tiled activation images) N=%d LBO=%u SBO=%u : mismatches %d / %d", n_cols, lbo, sbo, bad, M * n_cols);
+    if (bad) printf("  first at (m=%d,n=%d) got %g want %g", first / N, first % N, got[first], D[first]);
+    printf("\n%s\n", bad ? "PROBE4 variant failed" : "PROBE4 OK");
+    cudaFree(da); cudaFree(db); cudaFree(dd);
+    return bad ? 1 : 0;
+}
+
 static int run_probe2() {
     const int M = 256, N = 256, K = 64;
     std::vector<float> A(M * K), B(N * K), D(M * N);
@@ -297,5 +376,8 @@ int main() {
     run_probe2();
     run_probe3(1);
     run_probe3(0);
+    run_probe4(256, 8192, 1024);
+    run_probe4(64, 8192, 1024);
+    run_probe4(256, 1024, 8192);
     return 0;
 }

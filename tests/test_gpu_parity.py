@@ -572,3 +572,40 @@ def test_tf32_layerwise_path_matches_fp32(golden):
         res[mode] = (img.detach(), film.grad.clone())
     assert (res["tf32"][0] - res["fp32"][0]).abs().max().item() < 2e-2
     assert (res["tf32"][1] - res["fp32"][1]).norm().item() < 5e-2 * res["fp32"][1].norm().item()
+
+
+@pytest.mark.parametrize("rows_shape", [(37, 24), (700, 64), (4096, 3)])
+def test_bf16_tensor_core_training_path_matches_fp32(rows_shape):
+    """Fused tcgen05 training path (mlp_tc.cu forward with saved activations + mlp_tc_train.cu dgrad / wgrad / heads):
+    raw outputs and EVERY parameter gradient against the exact fp32 layer-wise path on identical inputs and upstream
+    gradient.  Tolerance: bf16 operands, fp32 accumulation -> <= 2e-2 max-abs on raw (north_star), <= 3e-2 relative (L2) per
+    gradient tensor."""
+    n, s = rows_shape
+    g = torch.Generator().manual_seed(n)
+    torch.manual_seed(0)
+    net = models.damp_nerf_(models.NeRF()).cuda()
+    o = torch.tensor([0.0, 0.0, 4.0]).expand(n, 3)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * 0.25 + torch.tensor([0.0, 0.0, -1.0]), dim=-1) * 1.1
+    rays = torch.stack([o, d], 1).cuda()
+    z = (torch.sort(torch.rand(n, s, generator=g), -1).values * 4 + 2).cuda()
+    up = torch.randn(n * s, 4, generator=g).cuda()
+    res = {}
+    for mode in ("fp32", "bf16"):
+        old = ops.set_grad_precision(mode)
+        try:
+            net.zero_grad(set_to_none=True)
+            raw = ops.mlp(net, rays=rays, z=z)
+            (raw * up).sum().backward()
+        finally:
+            ops.set_grad_precision(old)
+        res[mode] = (raw.detach().clone(), {k: p.grad.detach().clone() for k, p in net.named_parameters()})
+    a, b = res["fp32"][0], res["bf16"][0]
+    assert (a[:, :3] - b[:, :3]).abs().max().item() < 2e-2
+    assert ((a[:, 3] - b[:, 3]).abs() / (1 + a[:, 3].abs())).max().item() < 4e-2
+    worst = 0.0
+    for k in res["fp32"][1]:
+        ga, gb = res["fp32"][1][k], res["bf16"][1][k]
+        rel = (ga - gb).norm().item() / max(ga.norm().item(), 1e-20)
+        worst = max(worst, rel)
+        assert rel < 3e-2, (k, rel, ga.norm().item(), gb.norm().item())
+    print("bf16 training path vs fp32 (%d x %d rows): worst relative gradient error %.3g" % (n, s, worst))
