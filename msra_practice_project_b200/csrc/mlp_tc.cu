@@ -122,12 +122,13 @@ __global__ void film_pack_kernel(const float* __restrict__ params, const float* 
 //   MODE 2: + bias, linear -> bf16 h                      (layers_dir.0)
 //   MODE 3: + bias, ReLU -> partial rgb head, no store    (layers_dir.1, N = 128; output_layer_rgb, nerf/nerf.py:73,93)
 // t_half / bias_half / h_half already include this warp's column-half offset; xoff[c] = ((c ^ (row & 7)) << 4).
-// kSave (training forward): every bf16 word written to shared memory is also stored to `spill`, this thread's row of the
-// layer's tiled activation tensor in global memory (tc_core.cuh), same block / chunk offsets; MODE 3 stores relu(h_d).
+// kSave (training forward): the relu bits of every activation are gathered into mk[jj] (tc_core.cuh: mask_put) and MODE 3
+// also writes relu(h_d) as bf16 into shared memory (block = this half at h_half), so that the spill thread can copy the
+// tile to global memory with the bulk-copy engine.
 template <int MODE, bool kSave>
 __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, uint32_t head_half, uint32_t h_half,
                                          const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2,
-                                         uint8_t* __restrict__ spill) {
+                                         uint32_t (&mk)[4]) {
     constexpr int NJH = MODE == 3 ? 2 : 4;
 #pragma unroll
     for (int jj = 0; jj < NJH; ++jj) {
@@ -168,9 +169,12 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
             }
             if (kSave) {                                            // HD tile: block = this half, chunks jj * 4 .. + 3
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    stg128(spill + xoff[jj * 4 + q], pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]), pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]),
-                           pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]), pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]));
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t w0 = pack_bf16_relu(f[8 * q + 0], f[8 * q + 1]), w1 = pack_bf16_relu(f[8 * q + 2], f[8 * q + 3]);
+                    const uint32_t w2 = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]), w3 = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
+                    mask_put(mk[jj], w0, 4 * q + 0); mask_put(mk[jj], w1, 4 * q + 1); mask_put(mk[jj], w2, 4 * q + 2); mask_put(mk[jj], w3, 4 * q + 3);
+                    st_shared_v4(h_half + xoff[jj * 4 + q], w0, w1, w2, w3);
+                }
             }
         } else {
             // columns of this 32-group = K of the next layer: K-block (jj >> 1) of this half, chunks (jj & 1) * 4 .. + 3
@@ -186,7 +190,9 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
                     w2 = pack_bf16_relu(f[8 * q + 4], f[8 * q + 5]); w3 = pack_bf16_relu(f[8 * q + 6], f[8 * q + 7]);
                 }
                 st_shared_v4(blk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
-                if (kSave) stg128(spill + (uint32_t)(jj >> 1) * kBlk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
+                if (kSave && MODE != 2) {
+                    mask_put(mk[jj], w0, 4 * q + 0); mask_put(mk[jj], w1, 4 * q + 1); mask_put(mk[jj], w2, 4 * q + 2); mask_put(mk[jj], w3, 4 * q + 3);
+                }
             }
         }
     }
@@ -195,8 +201,11 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
 // ======================================================================================================
 // NeRF (nerf/nerf.py:52-94)
 // ======================================================================================================
-// kSave = training forward: additionally writes every layer input the reverse mode needs (pos-enc, h0..h7, layers_dir.0
-// output, dir-enc, h_d) as tiled bf16 tensors into `saved` (5,120 B per row).
+// kSave = training forward: additionally keeps every layer input the reverse mode needs (pos-enc, h0..h7, layers_dir.0
+// output, dir-enc, h_d) as tiled bf16 tensors in `saved` (5,120 B per row) plus one relu bit per activation (272 B per row).
+// The tiles are already in shared memory as the next layer's A operand: warps 2 / 3 (one thread each, sub-tile 0 / 1) copy them
+// out with the bulk-copy engine (64 KB per layer and sub-tile, full-line writes) while the next layer's MMAs run; the epilogue
+// warps wait for "tile has been read" (spill_done) before they overwrite it in place.
 template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved) {
@@ -219,7 +228,26 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     } else if (warp == 1) {
         if (cx.rank == 0) mma_loop<NerfSched>(cx, tmem_base, pl, NerfSched::kSteps, 0);
         else if (lane == 0) relay_loop<NerfSched>(cx, pl, NerfSched::kSteps, 0);
-    } else if (warp >= kCtrlWarps) {
+    } else if (warp < kCtrlWarps) {
+        if (kSave && lane == 0) {
+            // ===== spill thread of sub-tile g: shared-memory tiles -> tiled tensors in global memory =====
+            const int g = warp - 2;
+            const uint32_t aux = cx.smem + (uint32_t)g * kSubBytes, hreg = aux + kPeBytes;
+            const uint32_t ready = cx.spill_ready + 8 * g, done = cx.spill_done + 8 * g;
+            const size_t n_sub = (size_t)pl.n_pairs * 4;
+            uint32_t ph = 0;
+            for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+                const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+                auto tile = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
+                auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
+                mbar_wait(ready, ph); bulk_s2g(tile(kSavPE, 1), aux, kBlk); finish();                       // positional encoding
+                for (int l = 0; l < 8; ++l) { mbar_wait(ready, ph); bulk_s2g(tile(sav_h(l), 4), hreg, 4 * kBlk); finish(); }   // h0 .. h7
+                mbar_wait(ready, ph); bulk_s2g(tile(kSavGL, 4), hreg, 4 * kBlk); bulk_s2g(tile(kSavDE, 1), aux, kBlk); finish();   // g, dir-enc
+                mbar_wait(ready, ph); bulk_s2g(tile(kSavHD, 2), hreg, 2 * kBlk); finish();                  // h_d
+            }
+            bulk_wait_all();
+        }
+    } else {
         // ===== input generation + epilogue =====
         // warp = 4 + g*8 + half*4 + quad;  thread = row (quad*32 + lane) of sub-tile g = TMEM lane;
         // `half` selects which half of the columns of every layer this warp converts.
@@ -243,16 +271,23 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         uint32_t xoff[8];
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, sp_phase = 0;
+        bool first_tile = true;
         const size_t n_sub = (size_t)pl.n_pairs * 4;               // 128-row sub-tiles in the saved tensors
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
             const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
             const bool valid = row < rows;
             const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
-            // this thread's row inside block 0 of tile T of a saved tensor with `nb` blocks per tile at block offset `off`
-            auto sav = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk + row_off; };
+            // kSave: tile written (and fenced) -> spill thread; wait until the previous tile copy has read shared memory
+            auto spill_sig = [&]() { if (kSave && lane == 0) mbar_arrive(cx.spill_ready + 8 * g); };
+            auto spill_wait = [&]() { if (kSave) { mbar_wait(cx.spill_done + 8 * g, sp_phase); sp_phase ^= 1u; } };
+            auto put_mask = [&](int l, const uint32_t (&mk)[4]) {
+                if (kSave) *reinterpret_cast<uint4*>(saved + mask_off(n_sub, l, T, half, r)) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
+            };
             float pnt[3], vdir[3];
             load_row(src, valid ? row : rows - 1, pnt, vdir);
+            if (!first_tile) spill_wait();                          // previous tile's h_d copy
+            first_tile = false;
             {
                 // positional encoding: 60 values + 4 zero pads = 32 words = 8 chunks; this half writes 4 of them
                 uint32_t pw[32];
@@ -266,10 +301,10 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     uint32_t a2 = half ? pw[16 + 4 * q + 2] : pw[4 * q + 2];
                     uint32_t a3 = half ? pw[16 + 4 * q + 3] : pw[4 * q + 3];
                     st_shared_v4(pe_base + row_off + ((cidx ^ xr) << 4), a0, a1, a2, a3);
-                    if (kSave) stg128(sav(kSavPE, 1) + ((cidx ^ xr) << 4), a0, a1, a2, a3);
                 }
             }
             arrive_act(act_local, act_leader, cx.rank, lane);
+            spill_sig();
 
             float sigma = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
             auto wait_acc = [&]() {
@@ -279,17 +314,26 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             };
             for (int s = 0; s < 7; ++s) {                               // layers_pos.0 .. layers_pos.6
                 wait_acc();
-                nerf_epi<0, kSave>(t_half, bias_half + (uint32_t)s * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2,
-                                   kSave ? sav(sav_h(s), 4) + (size_t)half * 2 * kBlk : nullptr);
+                spill_wait();
+                uint32_t mk[4] = {0u, 0u, 0u, 0u};
+                nerf_epi<0, kSave>(t_half, bias_half + (uint32_t)s * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2, mk);
                 arrive_act(act_local, act_leader, cx.rank, lane);
+                spill_sig();
+                put_mask(s, mk);
             }
-            wait_acc();                                                 // layers_pos.7 (+ sigma head)
-            nerf_epi<1, kSave>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2,
-                               kSave ? sav(sav_h(7), 4) + (size_t)half * 2 * kBlk : nullptr);
-            arrive_act(act_local, act_leader, cx.rank, lane);
+            {
+                wait_acc();                                             // layers_pos.7 (+ sigma head)
+                spill_wait();
+                uint32_t mk[4] = {0u, 0u, 0u, 0u};
+                nerf_epi<1, kSave>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2, mk);
+                arrive_act(act_local, act_leader, cx.rank, lane);
+                spill_sig();
+                put_mask(7, mk);
+            }
+            uint32_t mk[4] = {0u, 0u, 0u, 0u};
             wait_acc();                                                 // layers_dir.0 (linear) + view-direction encoding
-            nerf_epi<2, kSave>(t_half, bias_half + 8u * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2,
-                               kSave ? sav(kSavGL, 4) + (size_t)half * 2 * kBlk : nullptr);
+            spill_wait();
+            nerf_epi<2, kSave>(t_half, bias_half + 8u * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2, mk);
             {
                 // layers_dir.1's extra K: 24 values + 8 zero pads = 16 words = chunks 0..3 of the aux block; each half writes two
                 uint32_t dw[16];
@@ -302,18 +346,23 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     uint32_t a2 = half ? dw[8 + 4 * q + 2] : dw[4 * q + 2];
                     uint32_t a3 = half ? dw[8 + 4 * q + 3] : dw[4 * q + 3];
                     st_shared_v4(pe_base + row_off + ((((uint32_t)(half * 2 + q)) ^ xr) << 4), a0, a1, a2, a3);
-                    if (kSave) {                                    // DE tile: chunks 0..3 = the encoding, 4..7 = zero
-                        uint8_t* de = sav(kSavDE, 1);
-                        stg128(de + ((((uint32_t)(half * 2 + q)) ^ xr) << 4), a0, a1, a2, a3);
-                        stg128(de + ((((uint32_t)(4 + half * 2 + q)) ^ xr) << 4), 0u, 0u, 0u, 0u);
-                    }
+                    // DE tile kept for wgrad: chunks 0..3 = the encoding, 4..7 = zero
+                    if (kSave) st_shared_v4(pe_base + row_off + ((((uint32_t)(4 + half * 2 + q)) ^ xr) << 4), 0u, 0u, 0u, 0u);
                 }
             }
             arrive_act(act_local, act_leader, cx.rank, lane);
+            spill_sig();
             wait_acc();                                                 // layers_dir.1 (N = 128) + rgb head
+            spill_wait();
             nerf_epi<3, kSave>(tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)half * 64u,
-                               tab + (uint32_t)(kNerfTabBias + 9 * 256 + half * 64) * 4u, tab + (uint32_t)(kNerfTabWRgb + half * 64) * 4u, 0u, xoff,
-                               sigma, rgb0, rgb1, rgb2, kSave ? sav(kSavHD, 2) + (size_t)half * kBlk : nullptr);
+                               tab + (uint32_t)(kNerfTabBias + 9 * 256 + half * 64) * 4u, tab + (uint32_t)(kNerfTabWRgb + half * 64) * 4u,
+                               h_base + row_off + (uint32_t)half * kBlk, xoff, sigma, rgb0, rgb1, rgb2, mk);
+            if (kSave) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                spill_sig();
+                *reinterpret_cast<uint2*>(saved + hdmask_off(n_sub, T, half, r)) = make_uint2(mk[0], mk[1]);
+            }
             tc_fence_before();
             // combine the two halves' head partial sums and write raw[row] = (sigmoid rgb, relu sigma)
             if (half == 1)
@@ -596,7 +645,7 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
 
 extern "C" size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows) {
     if (model_kind != B2R_MODEL_NERF || rows < 0) return 0;
-    return (size_t)b2r::tc::n_sub_tiles(rows) * b2r::tc::kSavBlocks * b2r::tc::kBlk;
+    return (size_t)b2r::tc::n_sub_tiles(rows) * b2r::tc::saved_bytes_per_sub();
 }
 
 extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,

@@ -65,40 +65,25 @@ __global__ void nerf_pack_bwd_kernel(const float* __restrict__ params, uint8_t* 
     }
 }
 
-// 0xFFFF in every half whose bf16 value is > 0 (relu'(h) for a packed pair of saved activations)
-__device__ __forceinline__ uint32_t relu_mask2(uint32_t h2) {
-    __nv_bfloat162 a, z;
-    *reinterpret_cast<uint32_t*>(&a) = h2;
-    *reinterpret_cast<uint32_t*>(&z) = 0u;
-    return __hgt2_mask(a, z);
-}
-
 // One dgrad step's epilogue for this warp's half (128) of the columns.
-//   MODE 0: linear (d g: layers_dir.0 has no activation)           -> next A operand + spill
-//   MODE 1: + gs * w_sigma (sigma-head term), relu'(h7)             -> next A operand + spill
-//   MODE 2: relu'(h)                                                -> next A operand + spill
-//   MODE 3: relu'(h0), spill only (layers_pos.0 has no dgrad)
-// hsrc: this thread's row in block 0 of its half of the saved activation tile; gdst: same for the gradient tile.
+//   MODE 0: linear (d g: layers_dir.0 has no activation);  MODE 1: + gs * w_sigma (sigma-head term), relu'(h7);  MODE 2: relu'(h)
+// The result (bf16) is written in place as the next step's A operand; the spill thread copies the same tile to global
+// memory for wgrad.  mask_ptr: this thread's 16-byte relu-bit word of the layer (prefetched while the MMAs finish).
 template <int MODE>
-__device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const uint32_t (&xoff)[8], const uint8_t* __restrict__ hsrc,
-                                        uint8_t* __restrict__ gdst, float gs, uint32_t wsig_half, uint32_t acc_bar, uint32_t& acc_phase) {
-    uint4 hm[4];
-    if (MODE != 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hm[q] = ldg128(hsrc + xoff[q]);                 // in flight while the MMAs finish
-    }
+__device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const uint32_t (&xoff)[8], const uint8_t* __restrict__ mask_ptr,
+                                        float gs, uint32_t wsig_half, uint32_t acc_bar, uint32_t& acc_phase, uint32_t done_bar, uint32_t& sp_phase) {
+    uint4 mk4 = make_uint4(0u, 0u, 0u, 0u);
+    if (MODE != 0) mk4 = ldg128(mask_ptr);
     mbar_wait_cluster(acc_bar, acc_phase);
     acc_phase ^= 1u;
     tc_fence_after();
+    mbar_wait(done_bar, sp_phase);                 // the previous tile copy has read the blocks this epilogue overwrites
+    sp_phase ^= 1u;
+    const uint32_t mk[4] = {mk4.x, mk4.y, mk4.z, mk4.w};
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
         uint32_t v[32];
         tmem_ld32(t_half + (uint32_t)jj * 32u, v);
-        uint4 hn[4];
-        if (MODE != 0 && jj < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hn[q] = ldg128(hsrc + (uint32_t)((jj + 1) >> 1) * kBlk + xoff[((jj + 1) & 1) * 4 + q]);
-        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -116,15 +101,10 @@ __device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const 
             uint32_t w0 = pack_bf16(f[8 * q + 0], f[8 * q + 1]), w1 = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
             uint32_t w2 = pack_bf16(f[8 * q + 4], f[8 * q + 5]), w3 = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
             if (MODE != 0) {
-                w0 &= relu_mask2(hm[q].x); w1 &= relu_mask2(hm[q].y); w2 &= relu_mask2(hm[q].z); w3 &= relu_mask2(hm[q].w);
+                w0 &= mask_get(mk[jj], 4 * q + 0); w1 &= mask_get(mk[jj], 4 * q + 1);
+                w2 &= mask_get(mk[jj], 4 * q + 2); w3 &= mask_get(mk[jj], 4 * q + 3);
             }
-            const uint32_t off = (uint32_t)(jj >> 1) * kBlk + xoff[(jj & 1) * 4 + q];
-            if (MODE != 3) st_shared_v4(h_half + off, w0, w1, w2, w3);
-            stg128(gdst + off, w0, w1, w2, w3);
-        }
-        if (MODE != 0 && jj < 3) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hm[q] = hn[q];
+            st_shared_v4(h_half + (uint32_t)(jj >> 1) * kBlk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
         }
     }
 }
@@ -153,7 +133,25 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
     } else if (warp == 1) {
         if (cx.rank == 0) mma_loop<BwdSched>(cx, tmem_base, pl, BwdSched::kSteps, 0);
         else if (lane == 0) relay_loop<BwdSched>(cx, pl, BwdSched::kSteps, 0);
-    } else if (warp >= kCtrlWarps) {
+    } else if (warp < kCtrlWarps) {
+        if (lane == 0) {
+            // ===== spill thread of sub-tile g: gradient tiles (the A operands) -> tiled tensors in `scratch` =====
+            const int g = warp - 2;
+            const uint32_t hreg = cx.smem + (uint32_t)g * kSubBytes + kPeBytes;
+            const uint32_t ready = cx.spill_ready + 8 * g, done = cx.spill_done + 8 * g;
+            const size_t n_sub = (size_t)pl.n_pairs * 4;
+            uint32_t ph = 0;
+            for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+                const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+                auto tile = [&](int off, int nb) -> uint8_t* { return scratch + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
+                auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
+                mbar_wait(ready, ph); bulk_s2g(tile(kScrGD1, 2), hreg, 2 * kBlk); finish();                 // d pre(layers_dir.1)
+                mbar_wait(ready, ph); bulk_s2g(tile(kScrGG, 4), hreg, 4 * kBlk); finish();                  // d g
+                for (int l = 7; l >= 0; --l) { mbar_wait(ready, ph); bulk_s2g(tile(scr_gh(l), 4), hreg, 4 * kBlk); finish(); }
+            }
+            bulk_wait_all();
+        }
+    } else {
         const int ew = warp - kCtrlWarps;
         const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
         const int r = (quad << 5) | lane;
@@ -165,21 +163,22 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
         const uint32_t tab = cx.smem + kTabOff;
         const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
         const uint32_t acc_bar = cx.acc_full + 8 * g;
+        const uint32_t ready_bar = cx.spill_ready + 8 * g, done_bar = cx.spill_done + 8 * g;
         const uint32_t t_half = t_addr + (uint32_t)half * 128u;
         const uint32_t h_half = h_base + row_off + (uint32_t)half * 2u * kBlk;
         const uint32_t wsig_half = tab + (uint32_t)(kBwdTabWSigma + half * 128) * 4u;
         uint32_t xoff[8];
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, sp_phase = 0;
+        bool first_tile = true;
         const size_t n_sub = (size_t)pl.n_pairs * 4;
         float4* __restrict__ hg_out = reinterpret_cast<float4*>(scratch + (size_t)kScrBlocks * n_sub * kBlk);
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
             const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
             const bool valid = row < rows;
             const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
-            auto sav = [&](int off, int nb) -> const uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk + row_off; };
-            auto scr = [&](int off, int nb) -> uint8_t* { return scratch + ((size_t)off * n_sub + T * (size_t)nb) * kBlk + row_off; };
+            auto spill_sig = [&]() { if (lane == 0) mbar_arrive(ready_bar); };
             // ---- heads: d raw -> (d rgb pre-sigmoid, d sigma pre-relu); rows past the end contribute zero everywhere
             float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, gs = 0.f;
             if (valid) {
@@ -192,12 +191,12 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
             if (half == 0) hg_out[T * kRowsSub + r] = make_float4(gc0, gc1, gc2, gs);
             {
                 // d h_d = (d rgb pre) . W_rgb, relu'(h_d): this half produces columns half*64 .. +63 = K-block `half` of step 0
-                const uint8_t* hd = sav(kSavHD, 2) + (size_t)half * kBlk;
-                uint8_t* gd = scr(kScrGD1, 2) + (size_t)half * kBlk;
+                const uint2 hm = *reinterpret_cast<const uint2*>(saved + hdmask_off(n_sub, T, half, r));
                 const uint32_t wr = tab + (uint32_t)(kBwdTabWRgb + half * 64) * 4u;
+                if (!first_tile) { mbar_wait(done_bar, sp_phase); sp_phase ^= 1u; }          // previous tile's d h0 copy
+                first_tile = false;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const uint4 hm = ldg128(hd + xoff[q]);
                     float f[8];
 #pragma unroll
                     for (int hq = 0; hq < 2; ++hq) {
@@ -208,29 +207,36 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                         f[4 * hq + 2] = fmaf(gc2, w2.z, fmaf(gc1, w1.z, gc0 * w0.z));
                         f[4 * hq + 3] = fmaf(gc2, w2.w, fmaf(gc1, w1.w, gc0 * w0.w));
                     }
-                    const uint32_t w0 = pack_bf16(f[0], f[1]) & relu_mask2(hm.x), w1 = pack_bf16(f[2], f[3]) & relu_mask2(hm.y);
-                    const uint32_t w2 = pack_bf16(f[4], f[5]) & relu_mask2(hm.z), w3 = pack_bf16(f[6], f[7]) & relu_mask2(hm.w);
+                    const uint32_t bits = (q >> 2) ? hm.y : hm.x;
+                    const int i0 = 4 * (q & 3);
+                    const uint32_t w0 = pack_bf16(f[0], f[1]) & mask_get(bits, i0 + 0), w1 = pack_bf16(f[2], f[3]) & mask_get(bits, i0 + 1);
+                    const uint32_t w2 = pack_bf16(f[4], f[5]) & mask_get(bits, i0 + 2), w3 = pack_bf16(f[6], f[7]) & mask_get(bits, i0 + 3);
                     st_shared_v4(h_base + (uint32_t)half * kBlk + row_off + xoff[q], w0, w1, w2, w3);
-                    stg128(gd + xoff[q], w0, w1, w2, w3);
                 }
             }
             arrive_act(act_local, act_leader, cx.rank, lane);
-            const size_t hoff = (size_t)half * 2 * kBlk;
+            spill_sig();
+            auto mptr = [&](int l) -> const uint8_t* { return saved + mask_off(n_sub, l, T, half, r); };
             // step 0: d g (linear)
-            bwd_epi<0>(t_half, h_half, xoff, nullptr, scr(kScrGG, 4) + hoff, 0.f, 0u, acc_bar, acc_phase);
+            bwd_epi<0>(t_half, h_half, xoff, nullptr, 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
             arrive_act(act_local, act_leader, cx.rank, lane);
+            spill_sig();
             // step 1: d h7 (+ sigma head), relu'(h7)
-            bwd_epi<1>(t_half, h_half, xoff, sav(sav_h(7), 4) + hoff, scr(scr_gh(7), 4) + hoff, gs, wsig_half, acc_bar, acc_phase);
+            bwd_epi<1>(t_half, h_half, xoff, mptr(7), gs, wsig_half, acc_bar, acc_phase, done_bar, sp_phase);
             arrive_act(act_local, act_leader, cx.rank, lane);
+            spill_sig();
             // steps 2..7: d h6 .. d h1
             for (int s = 2; s < 8; ++s) {
-                const int l = 8 - s;
-                bwd_epi<2>(t_half, h_half, xoff, sav(sav_h(l), 4) + hoff, scr(scr_gh(l), 4) + hoff, 0.f, 0u, acc_bar, acc_phase);
+                bwd_epi<2>(t_half, h_half, xoff, mptr(8 - s), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
                 arrive_act(act_local, act_leader, cx.rank, lane);
+                spill_sig();
             }
-            // step 8: d h0 -> dPre0, spill only
-            bwd_epi<3>(t_half, h_half, xoff, sav(sav_h(0), 4) + hoff, scr(scr_gh(0), 4) + hoff, 0.f, 0u, acc_bar, acc_phase);
+            // step 8: d h0 -> dPre0: only wgrad reads it (layers_pos.0 has no dgrad), no MMA follows
+            bwd_epi<2>(t_half, h_half, xoff, mptr(0), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
+            fence_proxy_async_smem();
             tc_fence_before();
+            __syncwarp();
+            spill_sig();
         }
     }
     tc_teardown(tmem_base, warp);

@@ -101,6 +101,27 @@ __host__ __device__ inline long long n_sub_tiles(long long rows) {
     long long n_tiles = (rows + kRowsTile - 1) / kRowsTile;
     return ((n_tiles + 1) / 2) * 4;
 }
+// relu masks (training): one bit per activation, written by the forward epilogue thread (= row) as one 16-byte word per
+// layer and column half: mask tensor [8 layers][n_sub][2 halves][128 rows] uint4 after the blocks, then the h_d mask
+// [n_sub][2][128] uint2.  Bit i of word jj <-> column 32 jj + 2 i of the half, bit 16 + i <-> column 32 jj + 2 i + 1.
+__host__ __device__ constexpr size_t saved_bytes_per_sub() { return (size_t)kSavBlocks * kBlk + 8 * 2 * 128 * 16 + 2 * 128 * 8; }
+__device__ __forceinline__ size_t mask_off(size_t n_sub, int layer, size_t T, int half, int r) {
+    return (size_t)kSavBlocks * n_sub * kBlk + ((((size_t)layer * n_sub + T) * 2 + half) * 128 + r) * 16;
+}
+__device__ __forceinline__ size_t hdmask_off(size_t n_sub, size_t T, int half, int r) {
+    return (size_t)kSavBlocks * n_sub * kBlk + (size_t)8 * n_sub * 2 * 128 * 16 + ((T * 2 + half) * 128 + r) * 8;
+}
+// 0xFFFF in every half whose bf16 value is > 0
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t h2) {
+    __nv_bfloat162 a, z;
+    *reinterpret_cast<uint32_t*>(&a) = h2;
+    *reinterpret_cast<uint32_t*>(&z) = 0u;
+    return __hgt2_mask(a, z);
+}
+// gather the two relu bits of packed word i of a 32-column group / expand them back to a bf16x2 AND-mask
+__device__ __forceinline__ void mask_put(uint32_t& bits, uint32_t w, int i) { bits |= relu_mask2(w) & (0x00010001u << i); }
+__device__ __forceinline__ uint32_t mask_get(uint32_t bits, int i) { return ((bits >> i) & 0x00010001u) * 0xFFFFu; }
+
 __device__ __forceinline__ void stg128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -121,7 +142,7 @@ static_assert(kBarOff % 8 == 0 && kSmemBytes <= 232448, "shared-memory budget");
 
 struct Ctx {
     uint32_t smem;        // 1024-aligned shared base (shared-window address)
-    uint32_t w_full, w_empty, act_ready, acc_full, tmem_slot;
+    uint32_t w_full, w_empty, act_ready, acc_full, tmem_slot, spill_ready, spill_done;
     uint32_t rank;        // CTA rank in the pair (0 = leader: issues the MMAs)
 };
 
@@ -133,6 +154,8 @@ __device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
     c.act_ready = c.w_empty + 8 * kStages;
     c.acc_full = c.act_ready + 16;
     c.tmem_slot = c.acc_full + 16;
+    c.spill_ready = c.tmem_slot + 16;      // training kernels: tile written -> spill thread (count 8: the sub-tile's epilogue warps)
+    c.spill_done = c.spill_ready + 16;     // spill thread -> epilogue warps: the bulk store has read the tile (count 1)
     c.rank = cluster_ctarank();
     return c;
 }
@@ -263,7 +286,10 @@ __device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, cons
 __device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
-        for (int g = 0; g < 2; ++g) { mbar_init(cx.act_ready + 8 * g, 16); mbar_init(cx.acc_full + 8 * g, 1); }
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(cx.act_ready + 8 * g, 16); mbar_init(cx.acc_full + 8 * g, 1);
+            mbar_init(cx.spill_ready + 8 * g, 8); mbar_init(cx.spill_done + 8 * g, 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2cta(cx.tmem_slot, 512);
