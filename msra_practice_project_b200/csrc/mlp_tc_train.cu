@@ -439,48 +439,77 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
 }
 
 // output_layer_sigma (256 -> 1, input h7) and output_layer_rgb (128 -> 3, input h_d): weight and bias gradients from the
-// head gradients HG and the saved tiles.  Thread = one bf16x2 word (two columns) of h7 (threads 0..127) or h_d (128..191).
-__global__ void __launch_bounds__(192) nerf_head_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub,
+// head gradients HG and the saved tiles.  A thread owns one 16-byte chunk (8 columns) of a tile row: warps 0-3 walk the
+// rows of h7 (a warp reads one 512-byte row of the 4 blocks per step), warps 4-7 the rows of h_d (a half warp per row),
+// 8 rows in flight per thread.
+__device__ __forceinline__ void fma8(float (&acc)[8], float g, const uint4& x) {
+    acc[0] = fmaf(g, __uint_as_float(x.x << 16), acc[0]); acc[1] = fmaf(g, __uint_as_float(x.x & 0xFFFF0000u), acc[1]);
+    acc[2] = fmaf(g, __uint_as_float(x.y << 16), acc[2]); acc[3] = fmaf(g, __uint_as_float(x.y & 0xFFFF0000u), acc[3]);
+    acc[4] = fmaf(g, __uint_as_float(x.z << 16), acc[4]); acc[5] = fmaf(g, __uint_as_float(x.z & 0xFFFF0000u), acc[5]);
+    acc[6] = fmaf(g, __uint_as_float(x.w << 16), acc[6]); acc[7] = fmaf(g, __uint_as_float(x.w & 0xFFFF0000u), acc[7]);
+}
+__global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub,
                                                               float* __restrict__ d_params) {
-    const int t = threadIdx.x;
-    const bool is_sigma = t < 128;
-    const int wq = is_sigma ? t : t - 128;                  // word index inside the tensor's row: block = wq / 32, word = wq % 32
-    const int blk = wq >> 5, wd = wq & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float4* __restrict__ hg = reinterpret_cast<const float4*>(scratch + (size_t)kScrBlocks * n_sub * kBlk);
-    const uint8_t* __restrict__ xt = saved + (size_t)(is_sigma ? sav_h(7) : kSavHD) * n_sub * kBlk;
-    const int nb = is_sigma ? 4 : 2;
-    float a0[3] = {0.f, 0.f, 0.f}, a1[3] = {0.f, 0.f, 0.f}, bsum[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long T = blockIdx.x; T < n_sub; T += gridDim.x) {
-        const uint8_t* tile = xt + ((size_t)T * nb + blk) * kBlk + (size_t)(wd & 3) * 4;
-        const float4* g = hg + T * kRowsSub;
-#pragma unroll 4
-        for (int row = 0; row < kRowsSub; ++row) {
-            const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(tile + row * 128 + ((((uint32_t)wd >> 2) ^ ((uint32_t)row & 7u)) << 4)));
-            const float x0 = __uint_as_float(x << 16), x1 = __uint_as_float(x & 0xFFFF0000u);
-            const float4 gg = __ldg(g + row);
-            if (is_sigma) { a0[0] = fmaf(gg.w, x0, a0[0]); a1[0] = fmaf(gg.w, x1, a1[0]); }
-            else {
-                a0[0] = fmaf(gg.x, x0, a0[0]); a1[0] = fmaf(gg.x, x1, a1[0]);
-                a0[1] = fmaf(gg.y, x0, a0[1]); a1[1] = fmaf(gg.y, x1, a1[1]);
-                a0[2] = fmaf(gg.z, x0, a0[2]); a1[2] = fmaf(gg.z, x1, a1[2]);
+    const uint32_t c = (uint32_t)lane & 7u;                 // logical chunk of the row this thread owns (columns blk*64 + c*8 ..)
+    if (warp < 4) {
+        const int blk = lane >> 3;
+        const uint8_t* __restrict__ xt = saved + (size_t)sav_h(7) * n_sub * kBlk + (size_t)blk * kBlk;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
+        for (long long T = blockIdx.x; T < n_sub; T += gridDim.x) {
+            const uint8_t* tile = xt + (size_t)T * 4 * kBlk;
+            const float4* g = hg + T * kRowsSub;
+#pragma unroll 1
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+                uint4 x[8]; float gs[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t row = (uint32_t)(warp + 4 * (i0 + i));
+                    x[i] = ldg128(tile + row * 128u + ((c ^ (row & 7u)) << 4));
+                    gs[i] = __ldg(&g[row].w);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { fma8(acc, gs[i], x[i]); bsum += gs[i]; }
             }
-            if (t == 0 || t == 128) { bsum[0] += gg.x; bsum[1] += gg.y; bsum[2] += gg.z; bsum[3] += gg.w; }
         }
-    }
-    const int col = blk * 64 + wd * 2;
-    if (is_sigma) {
         const LayerDesc L = nerf_layer(10);
-        atomicAdd(d_params + L.w_off + col, a0[0]);
-        atomicAdd(d_params + L.w_off + col + 1, a1[0]);
-        if (t == 0) atomicAdd(d_params + L.b_off, bsum[3]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(d_params + L.w_off + blk * 64 + (int)c * 8 + j, acc[j]);
+        if (lane == 0) atomicAdd(d_params + L.b_off, bsum);
     } else {
+        const int blk = (lane >> 3) & 1, sub = lane >> 4;   // half warp `sub` takes every other row
+        const uint8_t* __restrict__ xt = saved + (size_t)kSavHD * n_sub * kBlk + (size_t)blk * kBlk;
+        float a0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+              a2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        for (long long T = blockIdx.x; T < n_sub; T += gridDim.x) {
+            const uint8_t* tile = xt + (size_t)T * 2 * kBlk;
+            const float4* g = hg + T * kRowsSub;
+#pragma unroll 1
+            for (int i0 = 0; i0 < 16; i0 += 4) {
+                uint4 x[4]; float4 gg[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t row = (uint32_t)((warp - 4) * 2 + sub + 8 * (i0 + i));
+                    x[i] = ldg128(tile + row * 128u + ((c ^ (row & 7u)) << 4));
+                    gg[i] = __ldg(&g[row]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    fma8(a0, gg[i].x, x[i]); fma8(a1, gg[i].y, x[i]); fma8(a2, gg[i].z, x[i]);
+                    b0 += gg[i].x; b1 += gg[i].y; b2 += gg[i].z;
+                }
+            }
+        }
         const LayerDesc L = nerf_layer(11);
 #pragma unroll
-        for (int n = 0; n < 3; ++n) {
-            atomicAdd(d_params + L.w_off + n * 128 + col, a0[n]);
-            atomicAdd(d_params + L.w_off + n * 128 + col + 1, a1[n]);
+        for (int j = 0; j < 8; ++j) {
+            const int col = blk * 64 + (int)c * 8 + j;
+            atomicAdd(d_params + L.w_off + col, a0[j]);
+            atomicAdd(d_params + L.w_off + 128 + col, a1[j]);
+            atomicAdd(d_params + L.w_off + 256 + col, a2[j]);
         }
-        if (t == 128) { atomicAdd(d_params + L.b_off, bsum[0]); atomicAdd(d_params + L.b_off + 1, bsum[1]); atomicAdd(d_params + L.b_off + 2, bsum[2]); }
+        if ((lane & 15) == 0) { atomicAdd(d_params + L.b_off, b0); atomicAdd(d_params + L.b_off + 1, b1); atomicAdd(d_params + L.b_off + 2, b2); }
     }
 }
 
@@ -541,7 +570,7 @@ extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long
     tc::nerf_tc_wgrad_kernel<<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (wgrad)");
     unsigned hgrid = (unsigned)(n_sub < 4LL * sms ? n_sub : 4LL * sms);
-    tc::nerf_head_wgrad_kernel<<<hgrid, 192, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
+    tc::nerf_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (heads)");
     return 0;
 }
