@@ -374,22 +374,30 @@ def run_secondary(args):
         torch.manual_seed(5)
         t_rand = torch.rand((n_batch, sc), device=dev)[b:b + c].contiguous()
 
-        def step():
-            opt.zero_grad(set_to_none=True)
-            rc, _, _, rf, _, _ = nerf_render.render_rays(rays, 2.0, 6.0, coarse, fine, sc, sf, t_rand=t_rand)
-            loss = ((rf - target) ** 2).sum() / (n_batch * 3) + ((rc - target) ** 2).sum() / (n_batch * 3)
-            loss.backward()
-            shard.allreduce_gradients([coarse, fine], average=False)
-            opt.step()
+        if args.grad_precision == "bf16":
+            # fused step (train_step.py): explicit kernel sequence on flat buffers, CUDA-graph replay, fused Adam
+            from msra_practice_project_b200.train_step import NerfTrainStep
+            trainer = NerfTrainStep(coarse, fine, 2.0, 6.0, sc, sf, c, learning_rate=5e-4, learning_rate_decay=500)
+
+            def step():
+                trainer(rays, target, t_rand=t_rand)
+        else:
+            def step():
+                opt.zero_grad(set_to_none=True)
+                rc, _, _, rf, _, _ = nerf_render.render_rays(rays, 2.0, 6.0, coarse, fine, sc, sf, t_rand=t_rand)
+                loss = ((rf - target) ** 2).sum() / (n_batch * 3) + ((rc - target) ** 2).sum() / (n_batch * 3)
+                loss.backward()
+                shard.allreduce_gradients([coarse, fine], average=False)
+                opt.step()
         ms = timed(step, args.steps, args.warmup)
         rows = n_batch * (2 * sc + sf)
         line = dict(metric="rays/s, NeRF training step (4096-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
                     unit="rays/s", ms_per_step=ms, dtype={"tf32": "tf32", "fp32": "f32", "bf16": "bf16"}[args.grad_precision], scaling="strong",
                     config=dict(workload="NeRF train step, 4096 rays sharded over ranks, " + (
                         "fused tcgen05 MLP forward with bf16 activations kept in HBM + fused dgrad / MN-major wgrad reverse mode (bf16 operands, fp32 "
-                        "accumulate), " if args.grad_precision == "bf16" else
+                        "accumulate), fused Adam, whole step replayed as CUDA graphs, " if args.grad_precision == "bf16" else
                         f"layer-wise MLP forward with saved fp32 activations + CUDA reverse mode, GEMMs in {args.grad_precision}, ") +
-                        "one NCCL all-reduce of the 4.75 MB gradient bucket, torch Adam"),
+                        "one NCCL all-reduce of the 4.75 MB gradient bucket" + ("" if args.grad_precision == "bf16" else ", torch Adam")),
                     tflops=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
     elif args.config == "pigan":
         n_lat, res, s_ = 64, 128, 24

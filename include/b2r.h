@@ -155,6 +155,16 @@ size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows);
 int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows, const float* raw, const float* d_raw,
                          const void* saved, void* scratch, size_t scratch_bytes, float* d_params, void* stream);
 
+/* ---- fused Adam on a flat fp32 bucket ----------- optimizer.step() + LR decay, nerf/train_nerf.py:168-175 ----------
+ * torch.optim.Adam semantics (no weight decay / amsgrad) on n contiguous floats; grads are multiplied by grad_scale first
+ * (1/world for an averaged all-reduce).  state: 4 device floats, zero-initialised by the caller before the first step,
+ * owned by the optimiser afterwards ([0] = step count as int32 bits, [1] = current lr, [2], [3] = bias corrections): the
+ * step count and the decayed learning rate lr0 * decay_rate^((t-1)/decay_steps) (decay_steps <= 0: constant lr0) advance
+ * ON THE DEVICE, so the two launches replay unchanged inside a CUDA graph. */
+int b2r_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                  float lr0, float decay_rate, float decay_steps, float beta1, float beta2, float eps, float grad_scale,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,22 +104,45 @@ def _dirs_view(rays_d: torch.Tensor):
     return d, d.data_ptr(), 3
 
 
+def composite_forward(raw, z, rays_d, want_weights: bool = True):
+    """b2r_composite_fwd without autograd: (rgb, depth, acc, weights | None, (raw, z, dirs tensor, dirs stride))."""
+    raw = _cuda_f32(raw, "raw")
+    z = _cuda_f32(z, "z_vals")
+    keep, dptr, dstride = _dirs_view(rays_d.detach())
+    n, s = z.shape
+    dev = z.device
+    rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    depth = torch.empty((n,), dtype=torch.float32, device=dev)
+    acc = torch.empty((n,), dtype=torch.float32, device=dev)
+    w = torch.empty((n, s), dtype=torch.float32, device=dev) if want_weights else None
+    if n > 0:
+        with torch.cuda.device(dev):
+            check(lib().b2r_composite_fwd(ptr(raw), ptr(z), dptr, dstride, n, s, ptr(rgb), ptr(depth), ptr(acc), ptr(w),
+                                          _stream(z)), "b2r_composite_fwd")
+    return rgb, depth, acc, w, (raw, z, keep, dstride)
+
+
+def composite_backward(ctx4, g_rgb, g_depth=None, g_acc=None) -> torch.Tensor:
+    """b2r_composite_bwd: d_raw[N,S,4] from the upstream gradients of (rgb, depth, acc); ctx4 = composite_forward's last item."""
+    raw, z, keep, dstride = ctx4
+    n, s = z.shape
+    d_raw = torch.empty_like(raw)
+    if n == 0:
+        return d_raw
+    g_rgb = _cuda_f32(g_rgb, "g_rgb")
+    g_depth = None if g_depth is None else _cuda_f32(g_depth, "g_depth")
+    g_acc = None if g_acc is None else _cuda_f32(g_acc, "g_acc")
+    with torch.cuda.device(z.device):
+        check(lib().b2r_composite_bwd(ptr(raw), ptr(z), keep.data_ptr(), dstride, n, s, ptr(g_rgb), ptr(g_depth), ptr(g_acc),
+                                      ptr(d_raw), _stream(z)), "b2r_composite_bwd")
+    return d_raw
+
+
 class _Composite(torch.autograd.Function):
     @staticmethod
     def forward(ctx, raw, z, rays_d, want_weights):
-        raw = _cuda_f32(raw, "raw")
-        z = _cuda_f32(z, "z_vals")
-        keep, dptr, dstride = _dirs_view(rays_d.detach())
-        n, s = z.shape
+        rgb, depth, acc, w, (raw, z, keep, dstride) = composite_forward(raw, z, rays_d, want_weights)
         dev = z.device
-        rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
-        depth = torch.empty((n,), dtype=torch.float32, device=dev)
-        acc = torch.empty((n,), dtype=torch.float32, device=dev)
-        w = torch.empty((n, s), dtype=torch.float32, device=dev) if want_weights else None
-        if n > 0:
-            with torch.cuda.device(dev):
-                check(lib().b2r_composite_fwd(ptr(raw), ptr(z), dptr, dstride, n, s, ptr(rgb), ptr(depth), ptr(acc), ptr(w),
-                                              _stream(z)), "b2r_composite_fwd")
         ctx.save_for_backward(raw, z, keep)
         ctx.dstride = dstride
         if w is None:
@@ -301,6 +324,66 @@ def _packed_bwd_weights(model, kind: int, flat: torch.Tensor) -> torch.Tensor:
         check(lib().b2r_mlp_tc_pack_bwd(kind, ptr(flat), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_bwd")
     _pack_bwd_cache[model] = (key, packed)
     return packed
+
+
+def pack_tc(flat: torch.Tensor, kind: int, film=None, use_dir: bool = True) -> torch.Tensor:
+    """b2r_mlp_tc_pack of a flat fp32 parameter tensor (no cache)."""
+    packed = torch.empty((lib().b2r_mlp_tc_packed_bytes(kind),), dtype=torch.uint8, device=flat.device)
+    with torch.cuda.device(flat.device):
+        check(lib().b2r_mlp_tc_pack(kind, ptr(flat), ptr(film), int(use_dir), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack")
+    return packed
+
+
+def pack_tc_bwd(flat: torch.Tensor, kind: int) -> torch.Tensor:
+    """b2r_mlp_tc_pack_bwd (transposed weights for the dgrad kernel; no cache)."""
+    packed = torch.empty((lib().b2r_mlp_tc_bwd_packed_bytes(kind),), dtype=torch.uint8, device=flat.device)
+    with torch.cuda.device(flat.device):
+        check(lib().b2r_mlp_tc_pack_bwd(kind, ptr(flat), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_bwd")
+    return packed
+
+
+def tc_train_forward(packed: torch.Tensor, kind: int, rays: torch.Tensor, z: torch.Tensor):
+    """b2r_mlp_tc_train_fwd on (rays, z): (raw[rows,4], saved activation buffer)."""
+    inp, rows, keep = _make_input(rays, z, None, None)
+    dev = packed.device
+    raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+    nbytes = lib().b2r_mlp_tc_train_saved_bytes(kind, rows)
+    saved = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+    if rows > 0:
+        with torch.cuda.device(dev):
+            check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, _stream(packed)),
+                  "b2r_mlp_tc_train_fwd")
+    del keep
+    return raw, saved
+
+
+def tc_train_backward(packed_bwd: torch.Tensor, kind: int, raw: torch.Tensor, d_raw: torch.Tensor, saved: torch.Tensor,
+                      d_flat: torch.Tensor) -> None:
+    """b2r_mlp_tc_train_bwd: ACCUMULATES the parameter gradients into d_flat (flat fp32, state-dict order)."""
+    rows = raw.shape[0]
+    if rows == 0:
+        return
+    dev = raw.device
+    d_raw = _cuda_f32(d_raw, "d_raw")
+    sbytes = lib().b2r_mlp_tc_train_scratch_bytes(kind, rows)
+    scratch = torch.empty((sbytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().b2r_mlp_tc_train_bwd(kind, ptr(packed_bwd), rows, ptr(raw), ptr(d_raw), ptr(saved), ptr(scratch), sbytes,
+                                         ptr(d_flat), _stream(raw)), "b2r_mlp_tc_train_bwd")
+
+
+def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, state: torch.Tensor,
+              lr0: float, decay_rate: float = 1.0, decay_steps: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
+              grad_scale: float = 1.0) -> None:
+    """b2r_adam_step: torch.optim.Adam on a flat fp32 bucket with the train_nerf.py:170-175 learning-rate decay; the step
+    counter lives in `state` (4 floats on the device, zero before the first step)."""
+    for t in (params, grads, exp_avg, exp_avg_sq, state):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("adam_step needs contiguous fp32 CUDA tensors")
+    with torch.cuda.device(params.device):
+        check(lib().b2r_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(state), float(lr0),
+                                  float(decay_rate), float(decay_steps), float(betas[0]), float(betas[1]), float(eps),
+                                  float(grad_scale), _stream(params)), "b2r_adam_step")
 
 
 class _MlpTcTrain(torch.autograd.Function):
