@@ -47,6 +47,7 @@ def parse():
                     help="training config: bf16 = fused tensor-core forward + reverse mode, tf32 / fp32 = layer-wise GEMMs")
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="training config: launch the step's kernels directly (for ncu)")
     ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid"],
                     help="render = the headline NeRF 800x800 frame (default; BASELINE.json configs[1]); the others are the "
                          "secondary BASELINE configs: train = 4096-ray NeRF training step (configs[2]), pigan = pi-GAN 128x128 "
@@ -377,7 +378,7 @@ def run_secondary(args):
         if args.grad_precision == "bf16":
             # fused step (train_step.py): explicit kernel sequence on flat buffers, CUDA-graph replay, fused Adam
             from msra_practice_project_b200.train_step import NerfTrainStep
-            trainer = NerfTrainStep(coarse, fine, 2.0, 6.0, sc, sf, c, learning_rate=5e-4, learning_rate_decay=500)
+            trainer = NerfTrainStep(coarse, fine, 2.0, 6.0, sc, sf, c, learning_rate=5e-4, learning_rate_decay=500, graph=not args.no_graph)
 
             def step():
                 trainer(rays, target, t_rand=t_rand)

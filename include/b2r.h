@@ -33,10 +33,12 @@ extern "C" {
 /* model kinds */
 #define B2R_MODEL_NERF 0      /* nerf/nerf.py:52-94            */
 #define B2R_MODEL_FILM 1      /* pi_GAN/modules.py:70-118      */
+#define B2R_MODEL_SIREN 2     /* nerf/nerf.py:120-170 (SirenNeRF; layer-wise fp32 / tf32 path) */
 
 /* flat fp32 parameter counts (state-dict order: weight,bias per layer) */
 #define B2R_NERF_NUMEL 593924
 #define B2R_FILM_NUMEL 529156
+#define B2R_SIREN_NUMEL 562052
 #define B2R_FILM_NODIR_NUMEL 528388
 #define B2R_FILM_PARAMS 4608   /* film_params [9,512] = gamma(256)||beta(256) per layer */
 

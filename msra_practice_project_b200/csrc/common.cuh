@@ -66,6 +66,17 @@ __host__ __device__ constexpr LayerDesc film_layer(int i, bool use_dir) {
     for (int k = 0; k < i; ++k) off += (long long)outs[k] * ins[k] + outs[k];
     return LayerDesc{outs[i], ins[i], off, off + (long long)outs[i] * ins[i]};
 }
+// SirenNeRF (nerf/nerf.py:120-150): same topology as NeRF on raw 3-d inputs: layers_pos.0..7 (sin), layers_dir.0 (linear),
+// layers_dir.1 (sin), sigma, rgb
+constexpr int kSirenLayers = 12;
+__host__ __device__ constexpr LayerDesc siren_layer(int i) {
+    constexpr int outs[kSirenLayers] = {256, 256, 256, 256, 256, 256, 256, 256, 256, 128, 1, 3};
+    constexpr int ins[kSirenLayers] = {3, 256, 256, 256, 256, 259, 256, 256, 256, 259, 256, 128};
+    long long off = 0;
+    for (int k = 0; k < i; ++k) off += (long long)outs[k] * ins[k] + outs[k];
+    return LayerDesc{outs[i], ins[i], off, off + (long long)outs[i] * ins[i]};
+}
+static_assert(siren_layer(11).b_off + 3 == B2R_SIREN_NUMEL, "SirenNeRF flat layout");
 static_assert(nerf_layer(11).b_off + 3 == B2R_NERF_NUMEL, "NeRF flat layout");
 static_assert(film_layer(10, true).b_off + 3 == B2R_FILM_NUMEL, "FiLM flat layout");
 static_assert(film_layer(10, false).b_off + 3 == B2R_FILM_NODIR_NUMEL, "FiLM (no dir) flat layout");

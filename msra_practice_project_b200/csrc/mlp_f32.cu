@@ -49,6 +49,27 @@ struct FilmWs {
     }
 };
 
+// SirenNeRF: X0[4] (pos) | A0..A7[256] (pre-sine linear outputs) | H0..H3[256] | B5[260] = pos(3) || h4(256) | H5, H6, H7[256] |
+//            B9[260] = g(256) || dir(3) | A9[128] | HD[128]
+struct SirenWs {
+    static constexpr int kX0 = 4, kB = 260, kH = 256;
+    static constexpr int per_row = kX0 + 8 * kH + 4 * kH + kB + 3 * kH + kB + 128 + 128;   // 4628
+    float *X0, *A[8], *H[8], *B5, *B9, *A9, *HD;
+    long long ldH[8];
+    SirenWs(float* base, long long rows) {
+        float* p = base;
+        X0 = p; p += rows * kX0;
+        for (int l = 0; l < 8; ++l) { A[l] = p; p += rows * kH; }
+        for (int l = 0; l < 4; ++l) { H[l] = p; ldH[l] = kH; p += rows * kH; }
+        B5 = p; p += rows * kB;
+        H[4] = B5 + 3; ldH[4] = kB;
+        for (int l = 5; l < 8; ++l) { H[l] = p; ldH[l] = kH; p += rows * kH; }
+        B9 = p; p += rows * kB;
+        A9 = p; p += rows * 128;
+        HD = p;
+    }
+};
+
 constexpr long long kInferChunk = 65536;   // rows per pass when activations are not kept
 
 // ---- input encoders ---------------------------------------------------------------------------
@@ -85,6 +106,21 @@ __global__ void film_encode_kernel(RowSource src, long long row0, long long rows
     float* x = X0 + row * FilmWs::kX0;
     x[0] = p[0]; x[1] = p[1]; x[2] = p[2]; x[3] = 0.f;
     float* d = B8 + row * FilmWs::kB8 + 256;
+    d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = 0.f;
+}
+
+// SirenNeRF takes raw inputs: pos -> X0 (layer 0) and B5[:, 0:3] (skip), dir -> B9[:, 256:259]
+__global__ void siren_encode_kernel(RowSource src, long long row0, long long rows, float* __restrict__ X0, float* __restrict__ B5,
+                                    float* __restrict__ B9) {
+    long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float p[3], v[3];
+    load_row(src, row0 + row, p, v);
+    float* x = X0 + row * SirenWs::kX0;
+    x[0] = p[0]; x[1] = p[1]; x[2] = p[2]; x[3] = 0.f;
+    float* b5 = B5 + row * SirenWs::kB;
+    b5[0] = p[0]; b5[1] = p[1]; b5[2] = p[2]; b5[259] = 0.f;
+    float* d = B9 + row * SirenWs::kB + 256;
     d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = 0.f;
 }
 
@@ -193,17 +229,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ G
 
 // FiLM-SIREN activation reverse, in place on the incoming gradient:
 //   t = 30 (gamma a + beta); g_t = dH cos t; dgamma += 30 sum g_t a; dbeta += 30 sum g_t; G = 30 gamma g_t
+// gamma == NULL: plain SIREN layer (gamma 1, beta 0; nerf/nerf.py:111-112).  J = columns (<= 256), A has leading dimension J.
 __global__ void __launch_bounds__(256) film_act_bwd_kernel(float* __restrict__ dH, long long ldd,
                                                            const float* __restrict__ A, long long rows, int rows_per_cta,
                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-    const int j = threadIdx.x;   // 256 columns
+                                                           float* __restrict__ d_gamma, float* __restrict__ d_beta, int J = 256) {
+    const int j = threadIdx.x;
+    if (j >= J) return;
     long long r0 = (long long)blockIdx.x * rows_per_cta;
     long long r1 = min(rows, r0 + rows_per_cta);
-    const float gm = gamma[j], bt = beta[j];
+    const float gm = gamma ? gamma[j] : 1.0f, bt = gamma ? beta[j] : 0.0f;
     float sg = 0.f, sb = 0.f;
     for (long long row = r0; row < r1; ++row) {
-        float a = A[row * 256 + j];
+        float a = A[row * J + j];
         float t = __fmul_rn(30.0f, __fadd_rn(__fmul_rn(gm, a), bt));
         float gt = dH[row * ldd + j] * cosf(t);
         sg = fmaf(gt, a, sg);
@@ -318,13 +356,51 @@ static int film_forward_rows(const float* params, const float* film, bool use_di
     return 0;
 }
 
-static inline int per_row(int kind) { return kind == B2R_MODEL_NERF ? NerfWs::per_row : FilmWs::per_row; }
+static int siren_forward_rows(const float* params, const RowSource& src, long long row0, long long rows, SirenWs& ws, float* raw, bool save,
+                              cudaStream_t st) {
+    siren_encode_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(src, row0, rows, ws.X0, ws.B5, ws.B9);
+    B2R_TRY(cuda_result(cudaGetLastError(), "siren_encode"));
+    auto L = [&](int i) { return lin(params, siren_layer(i)); };
+    B2R_TRY(fwd_layer(ws.X0, SirenWs::kX0, L(0), 0, 3, ws.H[0], ws.ldH[0], rows, EPI_FILM_SIN, st, nullptr, nullptr, save ? ws.A[0] : nullptr));
+    for (int l = 1; l <= 4; ++l)
+        B2R_TRY(fwd_layer(ws.H[l - 1], ws.ldH[l - 1], L(l), 0, 256, ws.H[l], ws.ldH[l], rows, EPI_FILM_SIN, st, nullptr, nullptr,
+                          save ? ws.A[l] : nullptr));
+    B2R_TRY(fwd_layer(ws.B5, SirenWs::kB, L(5), 0, 259, ws.H[5], 256, rows, EPI_FILM_SIN, st, nullptr, nullptr, save ? ws.A[5] : nullptr));   // [pos | h4]
+    B2R_TRY(fwd_layer(ws.H[5], 256, L(6), 0, 256, ws.H[6], 256, rows, EPI_FILM_SIN, st, nullptr, nullptr, save ? ws.A[6] : nullptr));
+    B2R_TRY(fwd_layer(ws.H[6], 256, L(7), 0, 256, ws.H[7], 256, rows, EPI_FILM_SIN, st, nullptr, nullptr, save ? ws.A[7] : nullptr));
+    unsigned hgrid = (unsigned)((rows * 32 + 255) / 256);
+    {
+        Lin s = L(10);
+        head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.H[7], 256, 256, s.W, s.b, rows, 1, raw + row0 * 4, 3);
+        B2R_TRY(cuda_result(cudaGetLastError(), "siren sigma head"));
+    }
+    B2R_TRY(fwd_layer(ws.H[7], 256, L(8), 0, 256, ws.B9, SirenWs::kB, rows, EPI_STORE, st));                                                  // linear
+    {
+        GemmArgs g{};                                                                                                                      // [g | dir] -> 128, sin
+        Lin l9 = L(9);
+        g.P = ws.B9; g.ldp = SirenWs::kB; g.Q = l9.W; g.ldq = l9.in; g.C = ws.HD; g.ldc = 128;
+        g.I = rows; g.J = 128; g.R = 259; g.r_chunk = 259; g.epi = EPI_FILM_SIN; g.bias = l9.b;
+        g.pre = save ? ws.A9 : nullptr; g.ldpre = 128;
+        B2R_TRY((launch_gemm<false, false>(g, st, "siren layers_dir.1")));
+    }
+    {
+        Lin c = L(11);
+        head_fwd_kernel<3><<<hgrid, 256, 0, st>>>(ws.HD, 128, 128, c.W, c.b, rows, 2, raw + row0 * 4, 0);
+        B2R_TRY(cuda_result(cudaGetLastError(), "siren rgb head"));
+    }
+    return 0;
+}
+
+static inline bool known_kind(int kind) { return kind == B2R_MODEL_NERF || kind == B2R_MODEL_FILM || kind == B2R_MODEL_SIREN; }
+static inline int per_row(int kind) {
+    return kind == B2R_MODEL_NERF ? NerfWs::per_row : (kind == B2R_MODEL_FILM ? FilmWs::per_row : SirenWs::per_row);
+}
 
 }  // namespace b2r
 
 extern "C" size_t b2r_mlp_f32_workspace_bytes(int model_kind, long long rows, int save_activations) {
     using namespace b2r;
-    if (rows < 0 || (model_kind != B2R_MODEL_NERF && model_kind != B2R_MODEL_FILM)) return 0;
+    if (rows < 0 || !known_kind(model_kind)) return 0;
     long long r = save_activations ? rows : (rows < kInferChunk ? rows : kInferChunk);
     return (size_t)r * per_row(model_kind) * sizeof(float);
 }
@@ -335,7 +411,7 @@ extern "C" int b2r_mlp_f32_fwd(int model_kind, const float* params, const float*
     using namespace b2r;
     B2R_CHECK_ARG(gemm_mode == 0 || gemm_mode == 1, "b2r_mlp_f32_fwd: gemm_mode must be 0 (fp32) or 1 (tf32)");
     t_gemm_mode = gemm_mode;
-    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM, "b2r_mlp_f32_fwd: unknown model kind %d", model_kind);
+    B2R_CHECK_ARG(known_kind(model_kind), "b2r_mlp_f32_fwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(params && raw_out && workspace, "b2r_mlp_f32_fwd: NULL pointer");
     B2R_CHECK_ARG(model_kind != B2R_MODEL_FILM || film, "b2r_mlp_f32_fwd: FiLM model needs film params");
     B2R_TRY(check_mlp_input(in));
@@ -352,6 +428,9 @@ extern "C" int b2r_mlp_f32_fwd(int model_kind, const float* params, const float*
         if (model_kind == B2R_MODEL_NERF) {
             NerfWs ws((float*)workspace, n);
             B2R_TRY(nerf_forward_rows(params, src, r0, n, ws, raw_out, st));
+        } else if (model_kind == B2R_MODEL_SIREN) {
+            SirenWs ws((float*)workspace, n);
+            B2R_TRY(siren_forward_rows(params, src, r0, n, ws, raw_out, save_activations != 0, st));
         } else {
             FilmWs ws((float*)workspace, n);
             B2R_TRY(film_forward_rows(params, film, use_dir != 0, src, r0, n, ws, raw_out, save_activations != 0, st));
@@ -361,7 +440,7 @@ extern "C" int b2r_mlp_f32_fwd(int model_kind, const float* params, const float*
 }
 
 extern "C" size_t b2r_mlp_f32_bwd_scratch_bytes(int model_kind, long long rows) {
-    if (rows < 0 || (model_kind != B2R_MODEL_NERF && model_kind != B2R_MODEL_FILM)) return 0;
+    if (rows < 0 || !b2r::known_kind(model_kind)) return 0;
     return (size_t)rows * (2 * 256) * sizeof(float);   // two ping-pong gradient buffers [rows,256]
 }
 
@@ -371,7 +450,7 @@ extern "C" int b2r_mlp_f32_bwd(int model_kind, const float* params, const float*
     using namespace b2r;
     B2R_CHECK_ARG(gemm_mode == 0 || gemm_mode == 1, "b2r_mlp_f32_bwd: gemm_mode must be 0 (fp32) or 1 (tf32)");
     t_gemm_mode = gemm_mode;
-    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM, "b2r_mlp_f32_bwd: unknown model kind %d", model_kind);
+    B2R_CHECK_ARG(known_kind(model_kind), "b2r_mlp_f32_bwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(params && raw && d_raw && saved && scratch, "b2r_mlp_f32_bwd: NULL pointer");
     B2R_CHECK_ARG(d_params || d_film, "b2r_mlp_f32_bwd: nothing to differentiate (d_params and d_film are NULL)");
     B2R_TRY(check_mlp_input(in));
@@ -427,6 +506,47 @@ extern "C" int b2r_mlp_f32_bwd(int model_kind, const float* params, const float*
             float* t = Gc; Gc = Gn; Gn = t;
         }
         B2R_TRY(wgrad_layer(Gc, 256, ws.B5, NerfWs::kB5, nerf_layer(0), d_params, rows, st));
+        return 0;
+    }
+
+    if (model_kind == B2R_MODEL_SIREN) {
+        // SirenNeRF (nerf/nerf.py:152-170): y = sin(30 a), a = W x + b  ->  dA = 30 cos(30 a) dY (film_act_bwd with gamma 1, beta 0)
+        B2R_CHECK_ARG(d_params, "b2r_mlp_f32_bwd: SirenNeRF needs d_params");
+        SirenWs ws((float*)const_cast<void*>(saved), rows);
+        auto act_bwd = [&](float* G, long long ldg, const float* A, int J) -> int {
+            film_act_bwd_kernel<<<slab_grid, 256, 0, st>>>(G, ldg, A, rows, rpc, nullptr, nullptr, nullptr, nullptr, J);
+            return cuda_result(cudaGetLastError(), "siren act bwd");
+        };
+        {
+            LayerDesc d = siren_layer(11);
+            head_bwd_kernel<3><<<slab_grid, 256, 0, st>>>(ws.HD, 128, 128, params + d.w_off, rows, rpc, 2, raw, d_raw, 0,
+                                                         d_params + d.w_off, d_params + d.b_off, G0, 128);
+            B2R_TRY(cuda_result(cudaGetLastError(), "siren rgb head bwd"));
+        }
+        B2R_TRY(act_bwd(G0, 128, ws.A9, 128));
+        B2R_TRY(wgrad_layer(G0, 128, ws.B9, SirenWs::kB, siren_layer(9), d_params, rows, st));
+        B2R_TRY(dgrad_layer(G0, 128, lin(params, siren_layer(9)), 0, 256, G1, 256, rows, nullptr, 0, 0, st));          // d g
+        B2R_TRY(wgrad_layer(G1, 256, ws.H[7], 256, siren_layer(8), d_params, rows, st));
+        {
+            LayerDesc d = siren_layer(10);
+            head_bwd_kernel<1><<<slab_grid, 256, 0, st>>>(ws.H[7], 256, 256, params + d.w_off, rows, rpc, 1, raw, d_raw, 3,
+                                                         d_params + d.w_off, d_params + d.b_off, G0, 256);
+            B2R_TRY(cuda_result(cudaGetLastError(), "siren sigma head bwd"));
+        }
+        B2R_TRY(dgrad_layer(G1, 256, lin(params, siren_layer(8)), 0, 256, G0, 256, rows, nullptr, 0, 1, st));          // d h7 (+ sigma term)
+        float* Gc = G0; float* Gn = G1;
+        for (int l = 7; l >= 0; --l) {
+            B2R_TRY(act_bwd(Gc, 256, ws.A[l], 256));
+            if (l == 0) { B2R_TRY(wgrad_layer(Gc, 256, ws.X0, SirenWs::kX0, siren_layer(0), d_params, rows, st)); break; }
+            if (l == 5) {
+                B2R_TRY(wgrad_layer(Gc, 256, ws.B5, SirenWs::kB, siren_layer(5), d_params, rows, st));
+                B2R_TRY(dgrad_layer(Gc, 256, lin(params, siren_layer(5)), 3, 256, Gn, 256, rows, nullptr, 0, 0, st));
+            } else {
+                B2R_TRY(wgrad_layer(Gc, 256, ws.H[l - 1], ws.ldH[l - 1], siren_layer(l), d_params, rows, st));
+                B2R_TRY(dgrad_layer(Gc, 256, lin(params, siren_layer(l)), 0, 256, Gn, 256, rows, nullptr, 0, 0, st));
+            }
+            float* t = Gc; Gc = Gn; Gn = t;
+        }
         return 0;
     }
 

@@ -450,6 +450,8 @@ __device__ __forceinline__ void fma8(float (&acc)[8], float g, const uint4& x) {
 }
 __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub,
                                                               float* __restrict__ d_params) {
+    __shared__ float red_s[4][256 + 1];          // sigma: per-warp partial weight gradients (+ bias sum)
+    __shared__ float red_c[8][384 + 3];          // rgb: per half-warp partials (+ 3 bias sums)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float4* __restrict__ hg = reinterpret_cast<const float4*>(scratch + (size_t)kScrBlocks * n_sub * kBlk);
     const uint32_t c = (uint32_t)lane & 7u;                 // logical chunk of the row this thread owns (columns blk*64 + c*8 ..)
@@ -473,10 +475,9 @@ __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __r
                 for (int i = 0; i < 8; ++i) { fma8(acc, gs[i], x[i]); bsum += gs[i]; }
             }
         }
-        const LayerDesc L = nerf_layer(10);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) atomicAdd(d_params + L.w_off + blk * 64 + (int)c * 8 + j, acc[j]);
-        if (lane == 0) atomicAdd(d_params + L.b_off, bsum);
+        for (int j = 0; j < 8; ++j) red_s[warp][blk * 64 + (int)c * 8 + j] = acc[j];
+        if (lane == 0) red_s[warp][256] = bsum;
     } else {
         const int blk = (lane >> 3) & 1, sub = lane >> 4;   // half warp `sub` takes every other row
         const uint8_t* __restrict__ xt = saved + (size_t)kSavHD * n_sub * kBlk + (size_t)blk * kBlk;
@@ -501,15 +502,30 @@ __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __r
                 }
             }
         }
-        const LayerDesc L = nerf_layer(11);
+        float* dst = red_c[(warp - 4) * 2 + sub];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int col = blk * 64 + (int)c * 8 + j;
-            atomicAdd(d_params + L.w_off + col, a0[j]);
-            atomicAdd(d_params + L.w_off + 128 + col, a1[j]);
-            atomicAdd(d_params + L.w_off + 256 + col, a2[j]);
+            dst[col] = a0[j]; dst[128 + col] = a1[j]; dst[256 + col] = a2[j];
         }
-        if ((lane & 15) == 0) { atomicAdd(d_params + L.b_off, b0); atomicAdd(d_params + L.b_off + 1, b1); atomicAdd(d_params + L.b_off + 2, b2); }
+        if ((lane & 15) == 0) { dst[384] = b0; dst[385] = b1; dst[386] = b2; }
+    }
+    __syncthreads();
+    // one atomic per output and CTA
+    const int t = threadIdx.x;
+    {
+        const LayerDesc L = nerf_layer(10);
+        atomicAdd(d_params + L.w_off + t, red_s[0][t] + red_s[1][t] + red_s[2][t] + red_s[3][t]);
+        if (t == 0) atomicAdd(d_params + L.b_off, red_s[0][256] + red_s[1][256] + red_s[2][256] + red_s[3][256]);
+    }
+    {
+        const LayerDesc L = nerf_layer(11);
+        for (int i = t; i < 387; i += 256) {
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum += red_c[k][i];
+            atomicAdd(i < 384 ? d_params + L.w_off + i : d_params + L.b_off + (i - 384), sum);
+        }
     }
 }
 
@@ -569,7 +585,7 @@ extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long
     unsigned wgrid = (unsigned)(work < sms ? work : sms);
     tc::nerf_tc_wgrad_kernel<<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (wgrad)");
-    unsigned hgrid = (unsigned)(n_sub < 4LL * sms ? n_sub : 4LL * sms);
+    unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
     tc::nerf_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (heads)");
     return 0;

@@ -26,7 +26,7 @@ struct GemmArgs {
     int vec;                // 1: every operand row is 16-byte aligned and the contiguous extents are multiples of 4
     int epi;
     const float* bias;      // [J]                         (forward)
-    const float* gamma;     // [J] FiLM                    (EPI_FILM_SIN)
+    const float* gamma;     // [J] FiLM                    (EPI_FILM_SIN; NULL = plain SIREN, gamma 1 / beta 0)
     const float* beta;      // [J]
     float* pre; long long ldpre;            // optional pre-activation copy (EPI_FILM_SIN, saved for backward)
     const float* mask; long long ldmask;    // EPI_DGRAD: multiply by (mask[i,j] > 0) when non-null
@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
                     float a_lin = __fadd_rn(v, g.bias[j]);
                     if (g.pre) g.pre[i * g.ldpre + j] = a_lin;
                     // sin(w0 * (gamma * x + beta)), w0 = 30 (pi_GAN/modules.py:22-25)
-                    *c = sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[j], a_lin), g.beta[j])));
+                    // gamma == NULL: plain SIREN layer sin(30 (W x + b)) (nerf/nerf.py:111-112)
+                    *c = g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[j], a_lin), g.beta[j]))) : sinf(__fmul_rn(30.0f, a_lin));
                     break;
                 }
                 case EPI_DGRAD: {

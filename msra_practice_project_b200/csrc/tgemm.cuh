@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(256, 1) tgemm_kernel(GemmArgs g) {
                     case EPI_FILM_SIN: {
                         float a_lin = __fadd_rn(x, bs[q]);
                         if (g.pre && q < nv) g.pre[i * g.ldpre + j + q] = a_lin;
-                        x = q < nv ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[j + q], a_lin), g.beta[j + q]))) : 0.f;
+                        x = q >= nv ? 0.f : (g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[j + q], a_lin), g.beta[j + q]))) : sinf(__fmul_rn(30.0f, a_lin)));
                         break;
                     }
                     case EPI_DGRAD: x = (x + old[q]) * (msk[q] > 0.f ? 1.0f : 0.f); break;

@@ -783,3 +783,30 @@ def test_fused_train_step_matches_autograd_path(golden, graph):
     with torch.no_grad():
         img = nerf_render.render_rays(rays[:64], 2.0, 6.0, c2, f2, sc, sf, t_rand=ts[0][:64])[3]
     assert torch.isfinite(img).all()
+
+
+def test_siren_nerf_forward_and_training_gradients(golden):
+    """SirenNeRF (nerf/nerf.py:97-170; `use_siren`, nerf/train_nerf.py:89-91) through the layer-wise fp32 path: network(x)
+    against the reference's forward, then render_rays + MSE loss + backward against the reference's autograd gradients of
+    all 24 tensors of both models (fixture tests/golden/siren.npz)."""
+    g = golden.siren
+    torch.manual_seed(0)
+    m = models.SirenNeRF().cuda()
+    with torch.no_grad():
+        out = ops.mlp(m, x=cu(g["x"]), precision="fp32").cpu().numpy()
+        out_tf32 = ops.mlp(m, x=cu(g["x"])).cpu().numpy()              # default precision -> tf32 tensor-core GEMMs
+    np.testing.assert_allclose(out[:, :3], g["out"][:, :3], atol=2e-4, rtol=0)
+    np.testing.assert_allclose(out[:, 3], g["out"][:, 3], atol=2e-4, rtol=1e-3)
+    assert np.abs(out_tf32[:, :3] - g["out"][:, :3]).max() < 2e-2
+    torch.manual_seed(0)
+    c, f = models.SirenNeRF().cuda(), models.SirenNeRF().cuda()
+    rc, _, _, rf, _, _ = nerf_render.render_rays(cu(g["rays"]), 2.0, 6.0, c, f, 16, 16, t_rand=cu(g["t_rand"]), z_lin=g["z_lin"], u=g["u"],
+                                                 precision="fp32")
+    target = cu(g["target"])
+    loss = ((rf - target) ** 2).mean() + ((rc - target) ** 2).mean()
+    loss.backward()
+    np.testing.assert_allclose(rc.detach().cpu().numpy(), g["rgb_c"], atol=2e-4)
+    np.testing.assert_allclose(rf.detach().cpu().numpy(), g["rgb_f"], atol=2e-3)
+    assert abs(float(loss.detach()) - float(g["loss"])) < 2e-4
+    _grad_check(c, "coarse", g, rel=2e-2)
+    _grad_check(f, "fine", g, rel=5e-2)
