@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="training config: launch the step's kernels directly (for ncu)")
-    ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid"],
+    ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid", "siren"],
                     help="render = the headline NeRF 800x800 frame (default; BASELINE.json configs[1]); the others are the "
                          "secondary BASELINE configs: train = 4096-ray NeRF training step (configs[2]), pigan = pi-GAN 128x128 "
                          "24+24 x 64 latents (configs[3]), grid = 256^3 density query (configs[4])")
@@ -400,6 +400,27 @@ def run_secondary(args):
                         f"layer-wise MLP forward with saved fp32 activations + CUDA reverse mode, GEMMs in {args.grad_precision}, ") +
                         "one NCCL all-reduce of the 4.75 MB gradient bucket" + ("" if args.grad_precision == "bf16" else ", torch Adam")),
                     tflops=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
+    elif args.config == "siren":
+        # SirenNeRF (use_siren, nerf/train_nerf.py:89-91): the 800x800, 64+128 render with the fused SIREN kernel
+        w = h = 800
+        n = w * h
+        b, c = shard.shard_range(n, rank, world)
+        torch.manual_seed(0)
+        coarse, fine = models.SirenNeRF().to(dev), models.SirenNeRF().to(dev)
+        pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+        torch.manual_seed(5)
+        t_rand = torch.rand((n, args.coarse), device=dev)[b:b + c].contiguous()
+
+        def step():
+            with torch.no_grad():
+                nerf_render.render_image_device(w, h, w * 1.3875, pose, 2.0, 6.0, coarse, fine, args.coarse, args.fine, ray_begin=b, ray_count=c,
+                                                t_rand=t_rand, precision=args.precision)
+        ms = timed(step, args.steps, args.warmup)
+        rows = n * (2 * args.coarse + args.fine)
+        line = dict(metric="rays/s, SirenNeRF 800x800 render, 64 coarse + 128 fine samples/ray", value=n / (ms * 1e-3), unit="rays/s",
+                    ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
+                    config=dict(workload="SirenNeRF 800x800 render, 64+128 samples, rays sharded by pixel rows, fused tcgen05 SIREN kernel"),
+                    tflops=rows * 1123840 / (ms * 1e-3) / 1e12)
     elif args.config == "pigan":
         n_lat, res, s_ = 64, 128, 24
         b, c = shard.shard_range(n_lat, rank, world)

@@ -33,7 +33,7 @@ extern "C" {
 /* model kinds */
 #define B2R_MODEL_NERF 0      /* nerf/nerf.py:52-94            */
 #define B2R_MODEL_FILM 1      /* pi_GAN/modules.py:70-118      */
-#define B2R_MODEL_SIREN 2     /* nerf/nerf.py:120-170 (SirenNeRF; layer-wise fp32 / tf32 path) */
+#define B2R_MODEL_SIREN 2     /* nerf/nerf.py:120-170 (SirenNeRF)       */
 
 /* flat fp32 parameter counts (state-dict order: weight,bias per layer) */
 #define B2R_NERF_NUMEL 593924

@@ -569,7 +569,17 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
 }  // namespace tc
 }  // namespace b2r
 
+namespace b2r {
+namespace tc {
+// SirenNeRF (mlp_tc_siren.cu)
+size_t siren_packed_bytes();
+int siren_pack(const float* params, void* packed_out, cudaStream_t st);
+int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, cudaStream_t st);
+}  // namespace tc
+}  // namespace b2r
+
 extern "C" size_t b2r_mlp_tc_packed_bytes(int model_kind) {
+    if (model_kind == B2R_MODEL_SIREN) return b2r::tc::siren_packed_bytes();
     if (model_kind == B2R_MODEL_NERF) return (size_t)b2r::tc::kNerfPackedBytes;
     if (model_kind == B2R_MODEL_FILM) return (size_t)b2r::tc::kFilmPackedBytes;
     return 0;
@@ -593,6 +603,7 @@ extern "C" int b2r_mlp_tc_pack(int model_kind, const float* params, const float*
         B2R_LAUNCH_CHECK("b2r_mlp_tc_pack");
         return 0;
     }
+    if (model_kind == B2R_MODEL_SIREN) return tc::siren_pack(params, packed_out, (cudaStream_t)stream);
     return fail(-2, "b2r_mlp_tc_pack: unknown model kind %d", model_kind);
 }
 
@@ -623,8 +634,9 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (rc) return rc;
     long long rows = row_count(in);
     if (rows == 0) return 0;
-    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM, "b2r_mlp_tc_fwd: unknown model kind %d", model_kind);
-    B2R_CHECK_ARG(!(sigma_only && model_kind == B2R_MODEL_NERF), "b2r_mlp_tc_fwd: sigma_only is a FiLM-SIREN mode");
+    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM || model_kind == B2R_MODEL_SIREN, "b2r_mlp_tc_fwd: unknown model kind %d", model_kind);
+    B2R_CHECK_ARG(!(sigma_only && model_kind != B2R_MODEL_FILM), "b2r_mlp_tc_fwd: sigma_only is a FiLM-SIREN mode");
+    if (model_kind == B2R_MODEL_SIREN) return tc::siren_fwd(packed, in, rows, raw_out, (cudaStream_t)stream);
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;

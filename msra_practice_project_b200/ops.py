@@ -460,16 +460,15 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
     if rows == 0:
         return raw
     with torch.cuda.device(dev):
-        if precision == "bf16" and kind != models.KIND_SIREN:
+        if precision == "bf16":
             packed = _packed_weights(net, kind, flat, film, use_dir)
             check(lib().b2r_mlp_tc_fwd(kind, ptr(packed), int(use_dir), C.byref(inp), ptr(raw), int(sigma_only), _stream(flat)),
                   "b2r_mlp_tc_fwd")
         else:
             ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, rows, 0)
             ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=dev)
-            # SirenNeRF has no fused bf16 kernel yet: its throughput path is the layer-wise one with tf32 tensor-core GEMMs
             check(lib().b2r_mlp_f32_fwd(kind, ptr(flat), ptr(film), int(use_dir), C.byref(inp), ptr(raw), ptr(ws), ws_bytes, 0,
-                                        0 if precision == "fp32" else 1, _stream(flat)), "b2r_mlp_f32_fwd")
+                                        1 if precision == "tf32" else 0, _stream(flat)), "b2r_mlp_f32_fwd")
     del keep
     return raw
 
