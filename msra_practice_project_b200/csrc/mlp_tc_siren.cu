@@ -188,8 +188,8 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                     float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
                     float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
                     float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
-                    pk[2 * q + 0] = pack_bf16(sinf(fmaf(a0, 30.0f, sh.x)), sinf(fmaf(a1, 30.0f, sh.y)));
-                    pk[2 * q + 1] = pack_bf16(sinf(fmaf(a2, 30.0f, sh.z)), sinf(fmaf(a3, 30.0f, sh.w)));
+                    pk[2 * q + 0] = pack_bf16(__sinf(fmaf(a0, 30.0f, sh.x)), __sinf(fmaf(a1, 30.0f, sh.y)));
+                    pk[2 * q + 1] = pack_bf16(__sinf(fmaf(a2, 30.0f, sh.z)), __sinf(fmaf(a3, 30.0f, sh.w)));
                 }
                 const uint32_t blk = h_base + (uint32_t)(j >> 1) * 16384u + row_off;
 #pragma unroll
