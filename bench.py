@@ -441,7 +441,7 @@ def run_secondary(args):
         rays = n_lat * res * res
         line = dict(metric="rays/s, pi-GAN FiLM-SIREN render 128x128, 24+24 samples, 64 latents", value=rays / (ms * 1e-3), unit="rays/s",
                     ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
-                    config=dict(workload="pi-GAN generator render, 64 latents sharded over ranks, one pack + 4 kernels per latent"),
+                    config=dict(workload="pi-GAN generator render, 64 latents sharded over ranks, all latents of a rank in one launch sequence (per-latent FiLM tables)"),
                     images_per_s=n_lat / (ms * 1e-3), tflops=rays * 72 * 1053696 / (ms * 1e-3) / 1e12)
     else:
         n = 256

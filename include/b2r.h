@@ -167,6 +167,16 @@ int b2r_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float lr0, float decay_rate, float decay_steps, float beta1, float beta2, float eps, float grad_scale,
                   void* stream);
 
+/* ---- batched FiLM-SIREN evaluation --------- Generator.forward's per-latent loop, pi_GAN/modules.py:176-184 --------
+ * One launch for B latents: the bf16 weight chunks of `packed` (b2r_mlp_tc_pack with any film) are shared, every latent
+ * has its own fp32 table set (scale / shift per layer, folded input layer): tables[B][b2r_mlp_tc_film_table_bytes()/4],
+ * made by b2r_mlp_tc_film_tables from film[B,9,512].  Rows [b*rows_per_latent, (b+1)*rows_per_latent) of the input are
+ * evaluated with latent b's tables; rows_per_latent must be a multiple of 256. */
+size_t b2r_mlp_tc_film_table_bytes(void);
+int b2r_mlp_tc_film_tables(const float* params, const float* film, int use_dir, int n_latents, float* tables_out, void* stream);
+int b2r_mlp_tc_fwd_film_batched(const void* packed, const float* tables, int n_latents, long long rows_per_latent, int use_dir,
+                                const b2r_mlp_input* in, float* raw_out, int sigma_only, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

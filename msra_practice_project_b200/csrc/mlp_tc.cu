@@ -73,6 +73,27 @@ __global__ void nerf_pack_kernel(const float* __restrict__ params, uint8_t* __re
     }
 }
 
+// fp32 table entry i of a (weights, film) pair (layout kFSc .. kFBH, tc_core.cuh)
+__device__ __forceinline__ float film_table_value(const float* __restrict__ params, const float* __restrict__ film, bool ud, int i) {
+    float val;
+    if (i < kFW0) {                                            // scale / shift of the 8 tensor-core steps
+        int which = i / 2048, s = (i % 2048) / 256, n = i % 256;
+        int fl = s + 1;                                        // film row: 1..7 hidden, 8 rgb layer
+        LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);
+        float gm = film[fl * 512 + n], bt = film[fl * 512 + 256 + n], b = params[L.b_off + n];
+        val = which == 0 ? 30.0f * gm : 30.0f * (gm * b + bt);
+    } else if (i < kFS0) {
+        int k = (i - kFW0) / 256, n = (i - kFW0) % 256;
+        val = params[film_layer(0, ud).w_off + n * 3 + k];
+    } else if (i < kFT0) val = 30.0f * film[i - kFS0];
+    else if (i < kFWS) { int n = i - kFT0; val = 30.0f * (film[n] * params[film_layer(0, ud).b_off + n] + film[256 + n]); }
+    else if (i < kFWR) val = params[film_layer(8, ud).w_off + (i - kFWS)];
+    else if (i < kFBH) val = params[film_layer(10, ud).w_off + (i - kFWR)];
+    else if (i == kFBH) val = params[film_layer(8, ud).b_off];
+    else val = params[film_layer(10, ud).b_off + (i - kFBH - 1)];
+    return val;
+}
+
 __global__ void film_pack_kernel(const float* __restrict__ params, const float* __restrict__ film, int use_dir,
                                  uint8_t* __restrict__ packed) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -95,25 +116,15 @@ __global__ void film_pack_kernel(const float* __restrict__ params, const float* 
     }
     if (t < kFilmTabFloats) {
         float* tab = reinterpret_cast<float*>(packed + kFilmChunkBytes);
-        int i = (int)t;
-        float val;
-        if (i < kFW0) {                                            // scale / shift of the 8 tensor-core steps
-            int which = i / 2048, s = (i % 2048) / 256, n = i % 256;
-            int fl = s + 1;                                        // film row: 1..7 hidden, 8 rgb layer
-            LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);
-            float gm = film[fl * 512 + n], bt = film[fl * 512 + 256 + n], b = params[L.b_off + n];
-            val = which == 0 ? 30.0f * gm : 30.0f * (gm * b + bt);
-        } else if (i < kFS0) {
-            int k = (i - kFW0) / 256, n = (i - kFW0) % 256;
-            val = params[film_layer(0, ud).w_off + n * 3 + k];
-        } else if (i < kFT0) val = 30.0f * film[i - kFS0];
-        else if (i < kFWS) { int n = i - kFT0; val = 30.0f * (film[n] * params[film_layer(0, ud).b_off + n] + film[256 + n]); }
-        else if (i < kFWR) val = params[film_layer(8, ud).w_off + (i - kFWS)];
-        else if (i < kFBH) val = params[film_layer(10, ud).w_off + (i - kFWR)];
-        else if (i == kFBH) val = params[film_layer(8, ud).b_off];
-        else val = params[film_layer(10, ud).b_off + (i - kFBH - 1)];
-        tab[i] = val;
+        tab[t] = film_table_value(params, film, ud, (int)t);
     }
+}
+
+// per-latent fp32 tables for the batched kernel mode: tables_out[b][kFilmTabFloats] from film[b][9][512]
+__global__ void film_tables_kernel(const float* __restrict__ params, const float* __restrict__ film, int use_dir, float* __restrict__ tables_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kFilmTabFloats)
+        tables_out[(size_t)blockIdx.y * kFilmTabFloats + i] = film_table_value(params, film + (size_t)blockIdx.y * B2R_FILM_PARAMS, use_dir != 0, i);
 }
 
 // One NeRF layer's epilogue for this warp's half of the columns, fully unrolled (no per-step branches in the hot loop).
@@ -444,13 +455,21 @@ __device__ __forceinline__ void film_epi(uint32_t t_half, uint32_t sc_half, uint
 //   sigma_only (create_mesh, pi_GAN/utils.py:82-90) stops after hidden_layers.6: 919,552 FLOP per row.
 // Per row the epilogue issues 2304 MUFU.SIN: at 16 / clk / SM that is as long as the MMAs.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// Batched mode (Generator.forward's latent loop in one launch, pi_GAN/modules.py:176-184): `tables` != NULL holds one fp32
+// table set per latent and rows [b * rows_per_latent, (b+1) * rows_per_latent) belong to latent b (rows_per_latent is a
+// multiple of the 256-row tile); a CTA reloads its shared-memory scale / shift tables when its next tile is another latent's.
 film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int use_dir, int sigma_only,
-               float4* __restrict__ raw_out) {
+               float4* __restrict__ raw_out, const float* __restrict__ tables, long long rows_per_latent) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PairLoop pl(rows);
-    const float* __restrict__ tab = reinterpret_cast<const float*>(packed + kFilmChunkBytes);
+    auto latent_of = [&](long long p) -> long long { return tables ? ((2 * p + cx.rank) * kRowsTile) / rows_per_latent : 0; };
+    auto table_of = [&](long long lat) -> const float* {
+        return tables ? tables + (size_t)lat * kFilmTabFloats : reinterpret_cast<const float*>(packed + kFilmChunkBytes);
+    };
+    long long cur_lat = latent_of(pl.first < pl.n_pairs ? pl.first : 0);
+    const float* __restrict__ tab = table_of(cur_lat);
     const int n_steps = sigma_only ? 7 : FilmSched::kSteps;
     {   // scale[8][256] | shift[8][256] (16 KB) -> shared memory; the head weights stay in global memory (L1)
         static_assert(kFSc == 0 && kFSh == 2048 && 4096 * 4 <= kTabBytes + kPartBytes, "FiLM table region");
@@ -488,6 +507,21 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
         uint32_t acc_phase = 0;
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+            if (tables) {
+                const long long lat = latent_of(p);
+                if (lat != cur_lat) {
+                    // another latent: all 16 epilogue warps are done with the old tables, then reload scale / shift (16 KB)
+                    cur_lat = lat;
+                    tab = table_of(lat);
+                    asm volatile("bar.sync 3, 512;" ::: "memory");
+                    const float4* tab_g = reinterpret_cast<const float4*>(tab);
+                    for (int i = threadIdx.x - kCtrlWarps * 32; i < 4096 / 4; i += kEpiWarps * 32) {
+                        float4 v = __ldg(tab_g + i);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+                    }
+                    asm volatile("bar.sync 3, 512;" ::: "memory");
+                }
+            }
             const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
             const bool valid = row < rows;
             float pnt[3], vdir[3];
@@ -645,13 +679,49 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
         rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
         tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, use_dir, sigma_only,
-                                                                      (float4*)raw_out);
+                                                                      (float4*)raw_out, nullptr, 0);
     } else {
         rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
         tc::nerf_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr);
     }
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
+    return 0;
+}
+
+extern "C" size_t b2r_mlp_tc_film_table_bytes(void) { return (size_t)b2r::tc::kFilmTabFloats * sizeof(float); }
+
+extern "C" int b2r_mlp_tc_film_tables(const float* params, const float* film, int use_dir, int n_latents, float* tables_out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(params && film && tables_out, "b2r_mlp_tc_film_tables: NULL pointer");
+    B2R_CHECK_ARG(n_latents >= 0 && n_latents <= 65535, "b2r_mlp_tc_film_tables: n_latents out of range");
+    if (n_latents == 0) return 0;
+    dim3 grid((tc::kFilmTabFloats + 255) / 256, (unsigned)n_latents);
+    tc::film_tables_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, film, use_dir, tables_out);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_film_tables");
+    return 0;
+}
+
+extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, const float* tables, int n_latents, long long rows_per_latent, int use_dir,
+                                           const b2r_mlp_input* in, float* raw_out, int sigma_only, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(packed && tables && raw_out, "b2r_mlp_tc_fwd_film_batched: NULL pointer");
+    B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out | (uintptr_t)tables) & 15) == 0, "b2r_mlp_tc_fwd_film_batched: buffers must be 16-byte aligned");
+    int rc = check_mlp_input(in);
+    if (rc) return rc;
+    long long rows = row_count(in);
+    B2R_CHECK_ARG(rows_per_latent > 0 && rows_per_latent % tc::kRowsTile == 0,
+                  "b2r_mlp_tc_fwd_film_batched: rows_per_latent (%lld) must be a positive multiple of %d", rows_per_latent, tc::kRowsTile);
+    B2R_CHECK_ARG(rows <= rows_per_latent * (long long)n_latents, "b2r_mlp_tc_fwd_film_batched: %lld rows need more than %d latents", rows, n_latents);
+    if (rows == 0) return 0;
+    unsigned grid = 0;
+    rc = tc::pair_grid(rows, &grid);
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+    if (rc) return rc;
+    tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, use_dir, sigma_only,
+                                                                                     (float4*)raw_out, tables, rows_per_latent);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd_film_batched");
     return 0;
 }
 

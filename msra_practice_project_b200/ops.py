@@ -476,3 +476,35 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
 def mlp_points(model, x: torch.Tensor) -> torch.Tensor:
     """``network(x)`` for x[M,6] (the call of nerf/render.py:73 and pi_GAN/utils.py:86)."""
     return mlp(model, x=x)
+
+
+def mlp_film_batched(model, film: torch.Tensor, rays: torch.Tensor, z: torch.Tensor, rows_per_latent: int,
+                     sigma_only: bool = False) -> torch.Tensor:
+    """FiLM-SIREN on (rays, z) rows for B latents in ONE launch (Generator.forward's per-latent loop, pi_GAN/modules.py:176-184):
+    film[B,9,512]; rows [b * rows_per_latent, (b+1) * rows_per_latent) use latent b.  Inference only (bf16 tensor-core kernel)."""
+    kind = models.model_kind(model)
+    if kind != models.KIND_FILM:
+        raise TypeError("mlp_film_batched needs a FilmSirenNeRF model")
+    net = model.module if isinstance(model, torch.nn.DataParallel) else model
+    use_dir = bool(getattr(net, "use_dir", True))
+    ps = models.param_list(net, kind)
+    dev = ps[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("model parameters must live on a CUDA device: the B200 render path has no CPU fallback")
+    film = _cuda_f32(film.detach(), "film")
+    if film.dim() != 3 or tuple(film.shape[1:]) != (9, 512):
+        raise RuntimeError(f"film must be [B,9,512], got {tuple(film.shape)}")
+    flat = torch.cat([p.detach().reshape(-1) for p in ps]).float()
+    inp, rows, keep = _make_input(rays, z, None, None)
+    raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+    if rows == 0:
+        return raw
+    n_lat = film.shape[0]
+    tables = torch.empty((n_lat, lib().b2r_mlp_tc_film_table_bytes() // 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        packed = pack_tc(flat, kind, film[0].contiguous(), use_dir)
+        check(lib().b2r_mlp_tc_film_tables(ptr(flat), ptr(film), int(use_dir), n_lat, ptr(tables), _stream(flat)), "b2r_mlp_tc_film_tables")
+        check(lib().b2r_mlp_tc_fwd_film_batched(ptr(packed), ptr(tables), n_lat, int(rows_per_latent), int(use_dir), C.byref(inp), ptr(raw),
+                                                int(sigma_only), _stream(flat)), "b2r_mlp_tc_fwd_film_batched")
+    del keep
+    return raw

@@ -12,7 +12,8 @@ import torch
 from tqdm import tqdm
 
 from . import ops
-from .nerf_render import (get_rays, raw_to_outputs, render_image_device, render_rays, run_network, sample_pdf, to8b)
+from .nerf_render import (REFERENCE_RAY_CHUNK, _draw_t_rand, get_rays, raw_to_outputs, render_image_device, render_rays, run_network,
+                          sample_pdf, to8b)
 
 __all__ = ["np", "torch", "tqdm", "to8b", "trans_t", "rot_phi", "rot_theta", "blender_coord",
            "camera_pos_to_transform_matrix", "get_rays", "sample_pdf", "run_network", "raw_to_outputs", "render_rays",
@@ -80,14 +81,45 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
                  t_rand=None, precision=None):
     """Batched counterpart of Generator.forward's per-latent loop (pi_GAN/modules.py:176-184):
     film_params[B,9,512], poses[B,4,4] -> images [B,3,H,W].  This is the latent-sharding unit for
-    multi-GPU runs (each rank renders its slice of B)."""
-    imgs = []
-    for i in range(film_params.shape[0]):
-        model.set_film_params(film_params[i])
-        tr = None if t_rand is None else t_rand[i]
-        imgs.append(render_image(width, height, focal, poses[i], near, far, model, model, coarse_sample_num,
-                                 fine_sample_num, t_rand=tr, precision=precision))
-    return torch.stack(imgs).permute(0, 3, 1, 2).contiguous()
+    multi-GPU runs (each rank renders its slice of B).
+
+    Without gradients and with the bf16 tensor-core MLP the B latents are rendered by ONE launch sequence (rays of all poses,
+    one batched MLP launch per pass with per-latent FiLM tables); otherwise latent by latent through render_image."""
+    b = film_params.shape[0]
+    w, h, sc, sf = int(width), int(height), int(coarse_sample_num), int(fine_sample_num)
+    used = precision or ops.get_mlp_precision()
+    batched = (not torch.is_grad_enabled() or not _needs_grad(model, film_params)) and used == "bf16" and b > 0 \
+        and (w * h * sc) % 256 == 0 and (w * h * (sc + sf)) % 256 == 0
+    if not batched:
+        imgs = []
+        for i in range(b):
+            model.set_film_params(film_params[i])
+            tr = None if t_rand is None else t_rand[i]
+            imgs.append(render_image(width, height, focal, poses[i], near, far, model, model, coarse_sample_num,
+                                     fine_sample_num, t_rand=tr, precision=precision))
+        return torch.stack(imgs).permute(0, 3, 1, 2).contiguous()
+    dev = next(model.parameters()).device
+    n = w * h
+    with torch.no_grad():
+        rays = torch.cat([ops.raygen(w, h, focal, poses[i], device=dev) for i in range(b)])            # [B*HW,2,3]
+        if t_rand is None:
+            t_all = torch.cat([_draw_t_rand(n, sc, REFERENCE_RAY_CHUNK, dev) for _ in range(b)])         # the reference's draw order
+        else:
+            t_all = torch.as_tensor(t_rand, dtype=torch.float32).to(dev).reshape(b * n, sc)
+        z_lin = torch.linspace(float(near), float(far), steps=sc, device="cpu").to(dev)
+        u = torch.linspace(0.0, 1.0, steps=sf, device="cpu").to(dev)
+        film = torch.as_tensor(film_params, dtype=torch.float32).to(dev).reshape(b, 9, 512)
+        z, mids = ops.stratified_z(z_lin, t_all)
+        raw = ops.mlp_film_batched(model, film, rays, z, n * sc)
+        _, _, _, wts, _ = ops.composite_forward(raw, z, rays[:, 1], True)
+        z_f = ops.sample_pdf(mids, wts[:, 1:-1], sf, u=u, z_coarse=z, want_samples=False)["sorted"]
+        raw_f = ops.mlp_film_batched(model, film, rays, z_f, n * (sc + sf))
+        rgb, _, _, _, _ = ops.composite_forward(raw_f, z_f, rays[:, 1], False)
+    return rgb.reshape(b, h, w, 3).permute(0, 3, 1, 2).contiguous()
+
+
+def _needs_grad(model, film_params) -> bool:
+    return any(p.requires_grad for p in model.parameters()) or (isinstance(film_params, torch.Tensor) and film_params.requires_grad)
 
 
 def density_grid(model, N=256, max_batch=64 ** 3, *, begin=0, count=None, precision=None):
