@@ -177,6 +177,11 @@ int b2r_mlp_tc_film_tables(const float* params, const float* film, int use_dir, 
 int b2r_mlp_tc_fwd_film_batched(const void* packed, const float* tables, int n_latents, long long rows_per_latent, int use_dir,
                                 const b2r_mlp_input* in, float* raw_out, int sigma_only, void* stream);
 
+/* ---- image-space output ---------------------------------------------------- to8b  nerf/render.py:5 ---------------
+ * out[i] = (uint8)(255 * clip(x[i], 0, 1)) with numpy's float32 product and truncation (show_nerf.py:60-66,
+ * train_nerf.py:199 quantise every frame on the host); lets frames leave the device as 1 byte per channel. */
+int b2r_to8b(const float* x, long long n, unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,7 @@ SIGNATURES = {
     "b2r_mlp_tc_film_tables": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, c_float_p, C.c_void_p]),
     "b2r_mlp_tc_fwd_film_batched": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_ll, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_int,
                                               C.c_void_p]),
+    "b2r_to8b": (C.c_int, [c_float_p, c_ll, C.c_void_p, C.c_void_p]),
     "b2r_adam_step": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_ll, c_float_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "b2r_mlp_tc_train_bwd": (C.c_int, [C.c_int, C.c_void_p, c_ll, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -149,3 +149,33 @@ extern "C" int b2r_stratified_z(const float* z_lin, const float* t_rand, long lo
     B2R_LAUNCH_CHECK("b2r_stratified_z");
     return 0;
 }
+
+// ---- image-space output: to8b (nerf/render.py:5) on the device -----------------------------------------------------
+//   to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)      float32 product, truncation toward zero
+namespace b2r {
+__global__ void __launch_bounds__(256) to8b_kernel(const float4* __restrict__ x, long long n4, long long n, uchar4* __restrict__ out) {
+    auto q = [](float v) -> unsigned char { return (unsigned char)__float2uint_rz(__fmul_rn(255.0f, fminf(fmaxf(v, 0.0f), 1.0f))); };
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        out[i] = make_uchar4(q(v.x), q(v.y), q(v.z), q(v.w));
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - 4 * n4)) {
+        const long long i = 4 * n4 + threadIdx.x;
+        reinterpret_cast<unsigned char*>(out)[i] = q(reinterpret_cast<const float*>(x)[i]);
+    }
+}
+}  // namespace b2r
+
+extern "C" int b2r_to8b(const float* x, long long n, unsigned char* out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(n >= 0, "b2r_to8b: negative size");
+    if (n == 0) return 0;
+    B2R_CHECK_ARG(x && out, "b2r_to8b: NULL pointer");
+    B2R_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 3) == 0, "b2r_to8b: x must be 16-byte and out 4-byte aligned");
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    blocks = blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks);
+    to8b_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, n4, n, (uchar4*)out);
+    B2R_LAUNCH_CHECK("b2r_to8b");
+    return 0;
+}

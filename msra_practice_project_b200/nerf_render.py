@@ -20,7 +20,7 @@ from tqdm import tqdm
 from . import ops
 
 __all__ = ["np", "torch", "tqdm", "to8b", "get_rays", "sample_pdf", "run_network", "raw_to_outputs", "render_rays",
-           "render_image", "render_video"]
+           "render_image", "render_video", "render_video_u8"]
 
 to8b = lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8)       # nerf/render.py:5
 
@@ -170,3 +170,38 @@ def render_video(width, height, focal, poses, near, far, coarse_model, fine_mode
                                        fine_sample_num, chunk)
         rgb_video.append(rgb); depth_video.append(depth); acc_video.append(acc)
     return np.stack(rgb_video), np.stack(depth_video), np.stack(acc_video)
+
+
+def render_video_u8(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                    chunk=1024 * 16, *, precision=None):
+    """render_video + to8b (what show_nerf.py:55-66 does per frame on the host) with the quantisation on the device and the
+    frames streamed out through two pinned buffers: frame k's 1.9 MB uint8 copy overlaps frame k+1's render, and the host
+    waits only once per frame on an event.  Returns rgb uint8 [P,H,W,3]."""
+    dev = _model_device(coarse_model)
+    h, w = int(height), int(width)
+    poses = list(poses)
+    out = np.empty((len(poses), h, w, 3), dtype=np.uint8)
+    pinned = [torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    events = [torch.cuda.Event() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = [None, None]
+    with torch.no_grad():
+        for k, p in enumerate(tqdm(poses)):
+            o = render_image_device(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
+                                    fine_sample_num, chunk, precision=precision)
+            frame = ops.to8b(o[3]).reshape(h, w, 3)
+            slot = k & 1
+            if pending[slot] is not None:                       # the buffer's previous frame must have landed
+                events[slot].synchronize()
+                out[pending[slot]] = pinned[slot].numpy()
+            copy_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(copy_stream):
+                pinned[slot].copy_(frame, non_blocking=True)
+                frame.record_stream(copy_stream)
+                events[slot].record(copy_stream)
+            pending[slot] = k
+    for slot in range(2):
+        if pending[slot] is not None:
+            events[slot].synchronize()
+            out[pending[slot]] = pinned[slot].numpy()
+    return out

@@ -508,3 +508,12 @@ def mlp_film_batched(model, film: torch.Tensor, rays: torch.Tensor, z: torch.Ten
                                                 int(sigma_only), _stream(flat)), "b2r_mlp_tc_fwd_film_batched")
     del keep
     return raw
+
+
+def to8b(x: torch.Tensor) -> torch.Tensor:
+    """to8b (nerf/render.py:5) on the device: uint8 tensor of the same shape, (255 * clip(x, 0, 1)) truncated like numpy."""
+    x = _cuda_f32(x, "x")
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().b2r_to8b(ptr(x), x.numel(), ptr(out), _stream(x)), "b2r_to8b")
+    return out

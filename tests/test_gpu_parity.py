@@ -872,3 +872,20 @@ def test_pigan_render_batch_one_launch_matches_per_latent_loop():
     assert batched.shape == (b, 3, res, res)
     assert torch.equal(batched, loop), (batched - loop).abs().max().item()
     # (the per-latent path's own parity against the reference is test_pigan_render_bf16_vs_fp32 / test_mlp_tc_film_vs_reference)
+
+
+def test_to8b_device_and_streamed_video():
+    """b2r_to8b against the reference's numpy to8b (nerf/render.py:5) bit for bit, and render_video_u8 (device quantise +
+    double-buffered pinned copies) against to8b(render_video(...)) with the same seeds."""
+    g = torch.Generator().manual_seed(0)
+    x = torch.cat([torch.rand(100003, generator=g) * 1.4 - 0.2, torch.tensor([0.0, 1.0, -0.0, 0.5, 1.0 / 255, 254.999 / 255, 2.0, -3.0])])
+    got = ops.to8b(x.cuda()).cpu().numpy()
+    assert np.array_equal(got, nerf_render.to8b(x.numpy()))
+    c, f = seeded_nerf()
+    poses = [pigan_render.camera_pos_to_transform_matrix(4.0, 0.2 * i, -0.5) for i in range(3)]
+    torch.manual_seed(11)
+    vid = nerf_render.render_video_u8(24, 16, 24 * 1.3875, poses, 2.0, 6.0, c, f, 8, 8)
+    torch.manual_seed(11)
+    ref, _, _ = nerf_render.render_video(24, 16, 24 * 1.3875, poses, 2.0, 6.0, c, f, 8, 8)
+    assert vid.shape == (3, 16, 24, 3) and vid.dtype == np.uint8
+    assert np.array_equal(vid, nerf_render.to8b(ref))
