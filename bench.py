@@ -45,8 +45,9 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--grad-precision", default="bf16", choices=["fp32", "tf32", "bf16"],
                     help="training config: bf16 = fused tensor-core forward + reverse mode, tf32 / fp32 = layer-wise GEMMs")
-    ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=32768, help="rays in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="headline run: skip the other BASELINE.json configs")
     ap.add_argument("--no-graph", action="store_true", help="training config: launch the step's kernels directly (for ncu)")
     ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid", "siren"],
                     help="render = the headline NeRF 800x800 frame (default; BASELINE.json configs[1]); the others are the "
@@ -306,6 +307,16 @@ def run_b200(args):
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         base, _ = cpu_baseline(args, args.cpu_rays)
 
+    # the other BASELINE.json configs (training step, pi-GAN batch, density grid, SirenNeRF frame), measured in the same job
+    secondary = []
+    if not args.no_secondary:
+        for cfg in ("train", "pigan", "grid", "siren"):
+            try:
+                res = run_secondary(args, cfg, embedded=True)
+            except Exception as e:          # a secondary config must never take the headline line down
+                res = {"config": {"workload": cfg}, "error": repr(e)[:300]}
+            secondary.append(res)
+
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="rays/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None,
@@ -318,7 +329,7 @@ def run_b200(args):
                     e2e=dict(value=e2e_value, unit="rays/s", h2d_bytes_per_step=96,
                              d2h_bytes_per_step=int(n_rays * 5 * 4), ms_per_step=e2e_ms),
                     gpu_launches=int(7 * args.steps * world), clocks=clocks.summary(), roofline=roof, hbm_kernels=hbm_kernels,
-                    cpu_baseline=base)
+                    cpu_baseline=base, secondary=secondary)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -326,15 +337,18 @@ def run_b200(args):
 
 
 # ---- secondary BASELINE.json configs (not the headline line; printed with the same keys) ----------------------
-def run_secondary(args):
+def run_secondary(args, config=None, embedded=False):
+    """One of the other BASELINE.json configs.  embedded=True: called from the headline run (process group already up);
+    returns the result dict on rank 0 instead of printing it."""
     import torch
     import torch.distributed as dist
     from msra_practice_project_b200 import _lib, dist as shard, models, nerf_render, pigan_render
 
+    config = config or args.config
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not embedded:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.lib().b2r_device_ok() == 1
@@ -358,7 +372,7 @@ def run_secondary(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
-    if args.config == "train":
+    if config == "train":
         # nerf/train_nerf.py:151-168: render_rays on a 4096-ray batch, MSE(coarse)+MSE(fine), backward, Adam; the batch is
         # sharded over ranks and the flat fp32 gradient bucket is all-reduced once per step
         n_batch, sc, sf = 4096, args.coarse, args.fine
@@ -400,7 +414,7 @@ def run_secondary(args):
                         f"layer-wise MLP forward with saved fp32 activations + CUDA reverse mode, GEMMs in {args.grad_precision}, ") +
                         "one NCCL all-reduce of the 4.75 MB gradient bucket" + ("" if args.grad_precision == "bf16" else ", torch Adam")),
                     tflops=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
-    elif args.config == "siren":
+    elif config == "siren":
         # SirenNeRF (use_siren, nerf/train_nerf.py:89-91): the 800x800, 64+128 render with the fused SIREN kernel
         w = h = 800
         n = w * h
@@ -421,7 +435,7 @@ def run_secondary(args):
                     ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
                     config=dict(workload="SirenNeRF 800x800 render, 64+128 samples, rays sharded by pixel rows, fused tcgen05 SIREN kernel"),
                     tflops=rows * 1123840 / (ms * 1e-3) / 1e12)
-    elif args.config == "pigan":
+    elif config == "pigan":
         n_lat, res, s_ = 64, 128, 24
         b, c = shard.shard_range(n_lat, rank, world)
         torch.manual_seed(0)
@@ -462,8 +476,11 @@ def run_secondary(args):
                     ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
                     config=dict(workload="256^3 lattice in [-0.1,0.1]^3, coordinates generated on the device, sigma-only FiLM-SIREN kernel"),
                     tflops=n3 * 919552 / (ms * 1e-3) / 1e12)
+    line.update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, vs_baseline=None, data="synthetic")
+    if embedded:
+        torch.cuda.empty_cache()
+        return line
     if rank == 0:
-        line.update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, vs_baseline=None, data="synthetic")
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

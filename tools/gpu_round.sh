@@ -2,7 +2,7 @@
 # One GPU session: tests, smoke, bench, then (each only after its plain run exited 0) the ncu launch
 # list and one full capture of the fused MLP kernel.  Outputs land in gpurun_out/<tag>_*.
 TAG=${1:-run}
-SMALL="--width 256 --height 256 --steps 1 --warmup 1 --no-cpu-baseline"
+SMALL="--width 256 --height 256 --steps 1 --warmup 1 --no-cpu-baseline --no-secondary"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt
 timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider -s > gpurun_out/${TAG}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.txt
