@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--grad-precision", default="bf16", choices=["fp32", "tf32", "bf16"],
                     help="training config: bf16 = fused tensor-core forward + reverse mode, tf32 / fp32 = layer-wise GEMMs")
     ap.add_argument("--cpu-rays", type=int, default=32768, help="rays in the bounded CPU-baseline sample")
+    ap.add_argument("--ref-rays", type=int, default=16384, help="--impl reference: rays per step (the reference's own chunk, nerf/render.py:150)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="headline run: skip the other BASELINE.json configs")
     ap.add_argument("--no-graph", action="store_true", help="training config: launch the step's kernels directly (for ncu)")
@@ -103,16 +104,16 @@ def run_reference(args):
     times = []
     base = None
     for i in range(args.warmup + args.steps):
-        base, dt = cpu_baseline(args, args.cpu_rays)
+        base, dt = cpu_baseline(args, args.ref_rays)
         if i >= args.warmup:
             times.append(dt)
     t = float(np.mean(times)) if times else float("nan")
-    v = args.cpu_rays / t
+    v = args.ref_rays / t
     base["value"] = v
     line = dict(impl="reference", metric=METRIC, value=v, unit="rays/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=t * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=f"NeRF {args.width}x{args.height} render, {args.coarse}+{args.fine} samples/ray, random-init 8x256 ReLU MLP + posenc; "
-                                     f"each step = a {args.cpu_rays}-ray sample of the frame on the host CPU"),
+                                     f"each step = a {args.ref_rays}-ray sample of the frame on the host CPU"),
                 cpu_baseline=base, e2e=dict(value=v, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 samples_per_s=v * (2 * args.coarse + args.fine), gpu_launches=0)
     print(json.dumps(line))
