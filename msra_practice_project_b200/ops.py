@@ -33,17 +33,18 @@ def get_mlp_precision() -> str:
     return _MLP_PRECISION
 
 
-# Arithmetic of the path used whenever gradients are required: "fp32" = layer-wise, CUDA-core FMAs (exact: the parity path,
-# default), "tf32" = the same algorithm with every GEMM on the tensor cores (tcgen05 kind::tf32, fp32 accumulate), "bf16" =
-# the fused tensor-core training path (mlp_tc.cu forward with saved bf16 activations + mlp_tc_train.cu reverse mode; NeRF
-# model only -- other models fall back to "tf32" layer-wise GEMMs).
-_GRAD_PRECISION = "fp32"
+# Arithmetic of the path used whenever gradients are required: "fp32" = layer-wise, CUDA-core FMAs (exact: the parity path),
+# "tf32" = the same algorithm with every GEMM on the tensor cores (tcgen05 kind::tf32, fp32 accumulate), "bf16" = the fused
+# tensor-core training path (mlp_tc.cu forward with kept bf16 activations + mlp_tc_train.cu reverse mode, fp32 master weights /
+# gradients; NeRF model only -- other models use "tf32" layer-wise GEMMs), "auto" (default) = "bf16" for NeRF models -- the
+# same arithmetic class the no-grad render path uses by default -- and the exact "fp32" path for FiLM-SIREN / SirenNeRF.
+_GRAD_PRECISION = "auto"
 
 
 def set_grad_precision(p: str) -> str:
     global _GRAD_PRECISION
-    if p not in ("fp32", "tf32", "bf16"):
-        raise ValueError("grad precision must be 'fp32', 'tf32' or 'bf16'")
+    if p not in ("auto", "fp32", "tf32", "bf16"):
+        raise ValueError("grad precision must be 'auto', 'fp32', 'tf32' or 'bf16'")
     old, _GRAD_PRECISION = _GRAD_PRECISION, p
     return old
 
@@ -452,9 +453,12 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
     if needs_grad:
         if grid is not None:
             raise RuntimeError("grid queries are inference-only")
-        if _GRAD_PRECISION == "bf16" and kind == models.KIND_NERF:
+        gp = _GRAD_PRECISION
+        if gp == "auto":
+            gp = "bf16" if kind == models.KIND_NERF else "fp32"
+        if gp == "bf16" and kind == models.KIND_NERF:
             return _MlpTcTrain.apply(flat, net, kind, rays, z, x)
-        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, 0 if _GRAD_PRECISION == "fp32" else 1)
+        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, 0 if gp == "fp32" else 1)
     inp, rows, keep = _make_input(rays, z, x, grid)
     raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     if rows == 0:

@@ -381,12 +381,16 @@ def test_nerf_train_step_gradients(golden):
     torch.manual_seed(0)
     c, f = models.damp_nerf_(models.NeRF()).cuda(), models.damp_nerf_(models.NeRF()).cuda()
     sc, sf = int(tr["Sc"]), int(tr["Sf"])
-    rc, _, ac, rf, _, af = nerf_render.render_rays(cu(tr["rays"]), 2.0, 6.0, c, f, sc, sf, t_rand=cu(tr["t_rand"]),
-                                                   z_lin=tr["z_lin"], u=tr["u"])
-    target, target_a = cu(tr["target"]), cu(tr["target_a"])
-    loss = ((rf - target) ** 2).mean() + ((rc - target) ** 2).mean() + 0.1 * ((ac - target_a) ** 2).mean() \
-        + 0.1 * ((af - target_a) ** 2).mean()
-    loss.backward()
+    old = ops.set_grad_precision("fp32")            # the exact path: the fixture holds the reference's fp32 autograd gradients
+    try:
+        rc, _, ac, rf, _, af = nerf_render.render_rays(cu(tr["rays"]), 2.0, 6.0, c, f, sc, sf, t_rand=cu(tr["t_rand"]),
+                                                       z_lin=tr["z_lin"], u=tr["u"])
+        target, target_a = cu(tr["target"]), cu(tr["target_a"])
+        loss = ((rf - target) ** 2).mean() + ((rc - target) ** 2).mean() + 0.1 * ((ac - target_a) ** 2).mean() \
+            + 0.1 * ((af - target_a) ** 2).mean()
+        loss.backward()
+    finally:
+        ops.set_grad_precision(old)
     np.testing.assert_allclose(rc.detach().cpu().numpy(), tr["rgb_c"], atol=1e-4)
     np.testing.assert_allclose(rf.detach().cpu().numpy(), tr["rgb_f"], atol=1e-3)
     assert abs(float(loss.detach()) - float(tr["loss"])) < 1e-4
