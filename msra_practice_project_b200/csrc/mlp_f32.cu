@@ -53,7 +53,7 @@ struct FilmWs {
 //            B9[260] = g(256) || dir(3) | A9[128] | HD[128]
 struct SirenWs {
     static constexpr int kX0 = 4, kB = 260, kH = 256;
-    static constexpr int per_row = kX0 + 8 * kH + 4 * kH + kB + 3 * kH + kB + 128 + 128;   // 4628
+    static constexpr int per_row = kX0 + 8 * kH + 4 * kH + kB + 3 * kH + kB + 128 + 128;   // 4620
     float *X0, *A[8], *H[8], *B5, *B9, *A9, *HD;
     long long ldH[8];
     SirenWs(float* base, long long rows) {
