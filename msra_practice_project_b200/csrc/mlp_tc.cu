@@ -397,22 +397,24 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     tc_teardown(tmem_base, warp);
 }
 
-// One FiLM-SIREN layer's epilogue for this warp's half of the columns: sin(scale * acc + shift), unrolled.
+// One FiLM-SIREN layer's epilogue for this warp's QUARTER of the columns (64 = one K-block of the next layer):
+// sin(scale * acc + shift), unrolled.
 //   MODE 0: -> bf16 h (hidden_layers.0..5);  MODE 1: -> bf16 h + partial sigma head (hidden_layers.6, modules.py:112);
 //   MODE 2: -> partial rgb head, no store (hidden_layer_rgb, modules.py:114-116)
-// sc_half / sh_half: shared-memory addresses of this step's scale / shift slices; head: global fp32 head weights.
+// t_q: TMEM address of the quarter; sc_q / sh_q: shared-memory addresses of this step's scale / shift slices; head: global
+// fp32 head weights of the quarter; h_blk: this thread's row in the destination K-block.
 template <int MODE>
-__device__ __forceinline__ void film_epi(uint32_t t_half, uint32_t sc_half, uint32_t sh_half, const float* __restrict__ head,
-                                         uint32_t h_half, const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2) {
+__device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t sc_q, uint32_t sh_q, const float* __restrict__ head,
+                                         uint32_t h_blk, const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2) {
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
+    for (int jj = 0; jj < 2; ++jj) {
         uint32_t v[32];
-        tmem_ld32(t_half + (uint32_t)jj * 32u, v);
+        tmem_ld32(t_q + (uint32_t)jj * 32u, v);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 sc = lds128(sc_half + (uint32_t)(jj * 32 + q * 4) * 4u), sh = lds128(sh_half + (uint32_t)(jj * 32 + q * 4) * 4u);
+            const float4 sc = lds128(sc_q + (uint32_t)(jj * 32 + q * 4) * 4u), sh = lds128(sh_q + (uint32_t)(jj * 32 + q * 4) * 4u);
             f[4 * q + 0] = __sinf(fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x));
             f[4 * q + 1] = __sinf(fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y));
             f[4 * q + 2] = __sinf(fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z));
@@ -436,10 +438,9 @@ __device__ __forceinline__ void film_epi(uint32_t t_half, uint32_t sc_half, uint
                 rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
             }
         } else {
-            const uint32_t blk = h_half + (uint32_t)(jj >> 1) * 16384u;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                st_shared_v4(blk + xoff[(jj & 1) * 4 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
+                st_shared_v4(h_blk + xoff[jj * 4 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
                              pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
         }
     }
@@ -453,11 +454,15 @@ __device__ __forceinline__ void film_epi(uint32_t t_half, uint32_t sc_half, uint
 //   folded once per (weights, film) pair by the pack kernel; the sigma head (256 -> 1) rides on the
 //   epilogue of hidden_layers.6 and the rgb head (256 -> 3) on the epilogue of hidden_layer_rgb, both fp32.
 //   sigma_only (create_mesh, pi_GAN/utils.py:82-90) stops after hidden_layers.6: 919,552 FLOP per row.
-// Per row the epilogue issues 2304 MUFU.SIN: at 16 / clk / SM that is as long as the MMAs.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+// Per row the epilogue issues 2304 MUFU.SIN: the sine epilogue of a sub-tile is ~2.5x longer than its MMAs, so here the 16
+// epilogue warps are NOT split between the two sub-tiles (as in nerf_tc_kernel, where a sub-tile's warps idle while its own
+// MMAs run): every warp owns one 64-column quarter (= one K-block of the next layer) of BOTH sub-tiles and alternates
+// between them, so that the epilogue of one sub-tile always overlaps the MMAs of the other and no warp waits for "its" MMA.
+//
 // Batched mode (Generator.forward's latent loop in one launch, pi_GAN/modules.py:176-184): `tables` != NULL holds one fp32
 // table set per latent and rows [b * rows_per_latent, (b+1) * rows_per_latent) belong to latent b (rows_per_latent is a
 // multiple of the 256-row tile); a CTA reloads its shared-memory scale / shift tables when its next tile is another latent's.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int use_dir, int sigma_only,
                float4* __restrict__ raw_out, const float* __restrict__ tables, long long rows_per_latent) {
     extern __shared__ uint8_t smem_raw[];
@@ -479,7 +484,7 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
         }
     }
-    const uint32_t tmem_base = tc_prologue(cx, warp);
+    const uint32_t tmem_base = tc_prologue(cx, warp, 32);      // act_ready: 16 warps x 2 CTAs arrive per sub-tile and step
 
     if (warp == 0) {
         if (lane == 0) producer_loop<FilmSched>(cx, packed, pl, n_steps, use_dir);
@@ -487,25 +492,27 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, use_dir);
         else if (lane == 0) relay_loop<FilmSched>(cx, pl, n_steps, use_dir);
     } else if (warp >= kCtrlWarps) {
+        // warp = 4 + cq*4 + quad: column quarter cq (64 columns = K-block cq), TMEM lane quadrant quad; thread = row r of BOTH sub-tiles
         const int ew = warp - kCtrlWarps;
-        const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
+        const int cq = ew >> 2, quad = ew & 3;
         const int r = (quad << 5) | lane;
-        const uint32_t sub = cx.smem + (uint32_t)g * kSubBytes;
-        const uint32_t pe_base = sub, h_base = sub + kPeBytes;
-        const uint32_t t_addr = tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u;
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         const uint32_t xr = (uint32_t)(r & 7);
-        const uint32_t part = pe_base + 8192u + (uint32_t)r * 16u;     // head partials live in the aux block (free at tile end)
-        const uint32_t bar_id = 1 + g;
-        const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
-        const uint32_t acc_bar = cx.acc_full + 8 * g;
-        const uint32_t t_half = t_addr + (uint32_t)half * 128u;
-        const uint32_t sc_half = cx.smem + kTabOff + (uint32_t)(half * 128) * 4u, sh_half = sc_half + 2048u * 4u;
-        const uint32_t h_half = h_base + row_off + (uint32_t)half * 2u * 16384u;
+        const uint32_t act_leader0 = mapa(cx.act_ready, 0);
+        const uint32_t sc_q = cx.smem + kTabOff + (uint32_t)(cq * 64) * 4u, sh_q = sc_q + 2048u * 4u;
         uint32_t xoff[8];
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase[2] = {0u, 0u};
+        auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSubBytes; };
+        auto t_q = [&](int g) -> uint32_t { return tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)cq * 64u; };
+        auto h_blk = [&](int g) -> uint32_t { return sub_base(g) + kPeBytes + (uint32_t)cq * 16384u + row_off; };
+        auto arrive = [&](int g) { arrive_act(cx.act_ready + 8 * g, act_leader0 + 8 * g, cx.rank, lane); };
+        auto wait_acc = [&](int g) {
+            mbar_wait_cluster(cx.acc_full + 8 * g, acc_phase[g]);
+            acc_phase[g] ^= 1u;
+            tc_fence_after();
+        };
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
             if (tables) {
                 const long long lat = latent_of(p);
@@ -522,79 +529,94 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     asm volatile("bar.sync 3, 512;" ::: "memory");
                 }
             }
-            const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
-            const bool valid = row < rows;
-            float pnt[3], vdir[3];
-            load_row(src, valid ? row : rows - 1, pnt, vdir);
-            // ---- input_layer on CUDA cores: this half produces columns half*128 .. +127 of h0
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = half * 4 + jj;
-                uint32_t pk[16];
+            bool valid[2];
+            long long row[2];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int n0 = j * 32 + q * 4;
-                    float4 wx = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + n0));
-                    float4 wy = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 256 + n0));
-                    float4 wz = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 512 + n0));
-                    float4 sc = __ldg(reinterpret_cast<const float4*>(tab + kFS0 + n0));
-                    float4 sh = __ldg(reinterpret_cast<const float4*>(tab + kFT0 + n0));
-                    float a0 = fmaf(wz.x, pnt[2], fmaf(wy.x, pnt[1], wx.x * pnt[0]));
-                    float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
-                    float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
-                    float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
-                    pk[2 * q + 0] = pack_bf16(__sinf(fmaf(a0, sc.x, sh.x)), __sinf(fmaf(a1, sc.y, sh.y)));
-                    pk[2 * q + 1] = pack_bf16(__sinf(fmaf(a2, sc.z, sh.z)), __sinf(fmaf(a3, sc.w, sh.w)));
+            for (int g = 0; g < 2; ++g) {
+                row[g] = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
+                valid[g] = row[g] < rows;
+                float pnt[3], vdir[3];
+                load_row(src, valid[g] ? row[g] : rows - 1, pnt, vdir);
+                // ---- input_layer on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int n0 = cq * 64 + jj * 32 + q * 4;
+                        float4 wx = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + n0));
+                        float4 wy = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 256 + n0));
+                        float4 wz = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 512 + n0));
+                        float4 sc = __ldg(reinterpret_cast<const float4*>(tab + kFS0 + n0));
+                        float4 sh = __ldg(reinterpret_cast<const float4*>(tab + kFT0 + n0));
+                        float a0 = fmaf(wz.x, pnt[2], fmaf(wy.x, pnt[1], wx.x * pnt[0]));
+                        float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
+                        float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
+                        float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
+                        pk[2 * q + 0] = pack_bf16(__sinf(fmaf(a0, sc.x, sh.x)), __sinf(fmaf(a1, sc.y, sh.y)));
+                        pk[2 * q + 1] = pack_bf16(__sinf(fmaf(a2, sc.z, sh.z)), __sinf(fmaf(a3, sc.w, sh.w)));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
-                const uint32_t blk = h_base + (uint32_t)(j >> 1) * 16384u + row_off;
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    st_shared_v4(blk + (((uint32_t)((j & 1) * 4 + q) ^ xr) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                if (cq == 0) {
+                    // view direction (3 values, zero-padded to 16) -> chunks 0..1 of the aux block (hidden_layer_rgb's extra K)
+                    st_shared_v4(sub_base(g) + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 0.f), 0u, 0u);
+                    st_shared_v4(sub_base(g) + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
+                }
+                arrive(g);
             }
-            if (half == 0) {
-                // view direction (3 values, zero-padded to 16) -> chunks 0..1 of the aux block (hidden_layer_rgb's extra K)
-                st_shared_v4(pe_base + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 0.f), 0u, 0u);
-                st_shared_v4(pe_base + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
-            }
-            arrive_act(act_local, act_leader, cx.rank, lane);
 
-            float sigma = 0.f, rgb0 = 0.f, rgb1 = 0.f, rgb2 = 0.f;
-            auto wait_acc = [&]() {
-                mbar_wait_cluster(acc_bar, acc_phase);
-                acc_phase ^= 1u;
-                tc_fence_after();
-            };
+            float sigma[2] = {0.f, 0.f}, rgb0[2] = {0.f, 0.f}, rgb1[2] = {0.f, 0.f}, rgb2[2] = {0.f, 0.f};
             for (int s = 0; s < 6; ++s) {                               // hidden_layers.0 .. 5
-                wait_acc();
-                film_epi<0>(t_half, sc_half + (uint32_t)s * 1024u, sh_half + (uint32_t)s * 1024u, nullptr, h_half, xoff, sigma, rgb0, rgb1, rgb2);
-                arrive_act(act_local, act_leader, cx.rank, lane);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    wait_acc(g);
+                    film_epi<0>(t_q(g), sc_q + (uint32_t)s * 1024u, sh_q + (uint32_t)s * 1024u, nullptr, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                    arrive(g);
+                }
             }
-            wait_acc();                                                 // hidden_layers.6 (+ sigma head)
-            film_epi<1>(t_half, sc_half + 6u * 1024u, sh_half + 6u * 1024u, tab + kFWS + half * 128, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {                               // hidden_layers.6 (+ sigma head)
+                wait_acc(g);
+                film_epi<1>(t_q(g), sc_q + 6u * 1024u, sh_q + 6u * 1024u, tab + kFWS + cq * 64, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                if (!sigma_only) arrive(g);
+            }
             if (!sigma_only) {
-                arrive_act(act_local, act_leader, cx.rank, lane);
-                wait_acc();                                             // hidden_layer_rgb (+ rgb head)
-                film_epi<2>(t_half, sc_half + 7u * 1024u, sh_half + 7u * 1024u, tab + kFWR + half * 128, h_half, xoff, sigma, rgb0, rgb1, rgb2);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {                           // hidden_layer_rgb (+ rgb head)
+                    wait_acc(g);
+                    film_epi<2>(t_q(g), sc_q + 7u * 1024u, sh_q + 7u * 1024u, tab + kFWR + cq * 64, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                }
             }
             tc_fence_before();
-            if (half == 1)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part), "f"(rgb0), "f"(rgb1), "f"(rgb2), "f"(sigma) : "memory");
-            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-            if (half == 0) {
-                float4 o2 = lds128(part);
-                if (valid) {
+            // head partials of the four column quarters -> the aux blocks' upper halves (free once the last MMA is done):
+            // part[g][r][cq] as float4; the quarter-0 / quarter-1 warps finish sub-tile 0 / 1
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sub_base(g) + 8192u + (uint32_t)(r * 4 + cq) * 16u), "f"(rgb0[g]),
+                             "f"(rgb1[g]), "f"(rgb2[g]), "f"(sigma[g]) : "memory");
+            asm volatile("bar.sync 3, 512;" ::: "memory");
+            if (cq < 2) {
+                const int g = cq;
+                const bool ok = cq == 0 ? valid[0] : valid[1];
+                const long long out_row = cq == 0 ? row[0] : row[1];
+                const uint32_t pa = sub_base(g) + 8192u + (uint32_t)(r * 4) * 16u;
+                const float4 p0 = lds128(pa), p1 = lds128(pa + 16u), p2 = lds128(pa + 32u), p3 = lds128(pa + 48u);
+                if (ok) {
                     float4 bh = __ldg(reinterpret_cast<const float4*>(tab + kFBH));     // (b_sigma, b_rgb[3])
                     float4 o;
                     if (sigma_only) { o.x = o.y = o.z = 0.f; }
                     else {
-                        o.x = 1.0f / (1.0f + __expf(-(rgb0 + o2.x + bh.y)));
-                        o.y = 1.0f / (1.0f + __expf(-(rgb1 + o2.y + bh.z)));
-                        o.z = 1.0f / (1.0f + __expf(-(rgb2 + o2.z + bh.w)));
+                        o.x = 1.0f / (1.0f + __expf(-((p0.x + p1.x) + (p2.x + p3.x) + bh.y)));
+                        o.y = 1.0f / (1.0f + __expf(-((p0.y + p1.y) + (p2.y + p3.y) + bh.z)));
+                        o.z = 1.0f / (1.0f + __expf(-((p0.z + p1.z) + (p2.z + p3.z) + bh.w)));
                     }
-                    o.w = fmaxf(sigma + o2.w + bh.x, 0.f);
-                    raw_out[row] = o;
+                    o.w = fmaxf((p0.w + p1.w) + (p2.w + p3.w) + bh.x, 0.f);
+                    raw_out[out_row] = o;
                 }
             }
-            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+            asm volatile("bar.sync 3, 512;" ::: "memory");         // partial slots (and the aux rows they overlay) reusable
         }
     }
     tc_teardown(tmem_base, warp);

@@ -283,11 +283,12 @@ __device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, cons
 }
 
 // common prologue: barriers, TMEM allocation (both CTAs), cluster rendezvous; returns the TMEM base address
-__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp) {
+// act_count: arrivals per act_ready phase (epilogue warps per sub-tile x 2 CTAs)
+__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp, uint32_t act_count = 16) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
         for (int g = 0; g < 2; ++g) {
-            mbar_init(cx.act_ready + 8 * g, 16); mbar_init(cx.acc_full + 8 * g, 1);
+            mbar_init(cx.act_ready + 8 * g, act_count); mbar_init(cx.acc_full + 8 * g, 1);
             mbar_init(cx.spill_ready + 8 * g, 8); mbar_init(cx.spill_done + 8 * g, 1);
         }
         fence_barrier_init();
