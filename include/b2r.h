@@ -168,14 +168,13 @@ int b2r_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   void* stream);
 
 /* ---- batched FiLM-SIREN evaluation --------- Generator.forward's per-latent loop, pi_GAN/modules.py:176-184 --------
- * One launch for B latents: the bf16 weight chunks of `packed` (b2r_mlp_tc_pack with any film) are shared, every latent
- * has its own fp32 table set (scale / shift per layer, folded input layer): tables[B][b2r_mlp_tc_film_table_bytes()/4],
- * made by b2r_mlp_tc_film_tables from film[B,9,512].  Rows [b*rows_per_latent, (b+1)*rows_per_latent) of the input are
- * evaluated with latent b's tables; rows_per_latent must be a multiple of 256. */
-size_t b2r_mlp_tc_film_table_bytes(void);
-int b2r_mlp_tc_film_tables(const float* params, const float* film, int use_dir, int n_latents, float* tables_out, void* stream);
-int b2r_mlp_tc_fwd_film_batched(const void* packed, const float* tables, int n_latents, long long rows_per_latent, int use_dir,
-                                const b2r_mlp_input* in, float* raw_out, int sigma_only, void* stream);
+ * One launch for B latents.  packed: B images of b2r_mlp_tc_packed_bytes(B2R_MODEL_FILM) bytes one after the other, made by
+ * b2r_mlp_tc_pack_film_batched from film[B,9,512] (the FiLM scale / shift are folded into each latent's bf16 weights).
+ * Rows [b*rows_per_latent, (b+1)*rows_per_latent) of the input are evaluated with latent b; rows_per_latent must be a
+ * multiple of 256. */
+int b2r_mlp_tc_pack_film_batched(const float* params, const float* film, int use_dir, int n_latents, void* packed_out, void* stream);
+int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in, float* raw_out,
+                                int sigma_only, void* stream);
 
 /* ---- image-space output ---------------------------------------------------- to8b  nerf/render.py:5 ---------------
  * out[i] = (uint8)(255 * clip(x[i], 0, 1)) with numpy's float32 product and truncation (show_nerf.py:60-66,

@@ -51,10 +51,8 @@ SIGNATURES = {
     "b2r_mlp_tc_bwd_packed_bytes": (C.c_size_t, [C.c_int]),
     "b2r_mlp_tc_pack_bwd": (C.c_int, [C.c_int, c_float_p, C.c_void_p, C.c_void_p]),
     "b2r_mlp_tc_train_scratch_bytes": (C.c_size_t, [C.c_int, c_ll]),
-    "b2r_mlp_tc_film_table_bytes": (C.c_size_t, []),
-    "b2r_mlp_tc_film_tables": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, c_float_p, C.c_void_p]),
-    "b2r_mlp_tc_fwd_film_batched": (C.c_int, [C.c_void_p, c_float_p, C.c_int, c_ll, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_int,
-                                              C.c_void_p]),
+    "b2r_mlp_tc_pack_film_batched": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_mlp_tc_fwd_film_batched": (C.c_int, [C.c_void_p, C.c_int, c_ll, C.POINTER(MlpInput), c_float_p, C.c_int, C.c_void_p]),
     "b2r_to8b": (C.c_int, [c_float_p, c_ll, C.c_void_p, C.c_void_p]),
     "b2r_adam_step": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_ll, c_float_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),

@@ -73,16 +73,21 @@ __global__ void nerf_pack_kernel(const float* __restrict__ params, uint8_t* __re
     }
 }
 
-// fp32 table entry i of a (weights, film) pair (layout kFSc .. kFBH, tc_core.cuh)
+// FiLM scale / shift of tensor-core step s (film row s + 1: 1..7 hidden, 8 rgb layer), column n:
+//   sin(30 (gamma (W x + b) + beta)) = sin((30 gamma) W x + 30 (gamma b + beta))      (pi_GAN/modules.py:22-25)
+__device__ __forceinline__ void film_scale_shift(const float* __restrict__ params, const float* __restrict__ film, bool ud, int s, int n,
+                                                 float& scale, float& shift) {
+    const int fl = s + 1;
+    LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);
+    const float gm = film[fl * 512 + n], bt = film[fl * 512 + 256 + n], b = params[L.b_off + n];
+    scale = 30.0f * gm;
+    shift = 30.0f * (gm * b + bt);
+}
+
+// fp32 table entry i of a (weights, film) pair (layout kFW0 .. kFBH, tc_core.cuh)
 __device__ __forceinline__ float film_table_value(const float* __restrict__ params, const float* __restrict__ film, bool ud, int i) {
     float val;
-    if (i < kFW0) {                                            // scale / shift of the 8 tensor-core steps
-        int which = i / 2048, s = (i % 2048) / 256, n = i % 256;
-        int fl = s + 1;                                        // film row: 1..7 hidden, 8 rgb layer
-        LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);
-        float gm = film[fl * 512 + n], bt = film[fl * 512 + 256 + n], b = params[L.b_off + n];
-        val = which == 0 ? 30.0f * gm : 30.0f * (gm * b + bt);
-    } else if (i < kFS0) {
+    if (i < kFS0) {
         int k = (i - kFW0) / 256, n = (i - kFW0) % 256;
         val = params[film_layer(0, ud).w_off + n * 3 + k];
     } else if (i < kFT0) val = 30.0f * film[i - kFS0];
@@ -94,21 +99,32 @@ __device__ __forceinline__ float film_table_value(const float* __restrict__ para
     return val;
 }
 
-__global__ void film_pack_kernel(const float* __restrict__ params, const float* __restrict__ film, int use_dir,
-                                 uint8_t* __restrict__ packed) {
+// blockIdx.y = latent: packed[latent] = chunks (bf16, rows pre-multiplied by the FiLM scale; post chunk = [W_dir(3) | shift hi | shift lo])
+// + fp32 tables.  film: [n_latents][9][512]
+__global__ void film_pack_kernel(const float* __restrict__ params, const float* __restrict__ film_all, int use_dir,
+                                 uint8_t* __restrict__ packed_all) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const bool ud = use_dir != 0;
+    const float* __restrict__ film = film_all + (size_t)blockIdx.y * B2R_FILM_PARAMS;
+    uint8_t* __restrict__ packed = packed_all + (size_t)blockIdx.y * kFilmPackedBytes;
     if (t < kFilmChunkBytes / 16) {
         int s, c, hf, row, grp;
         locate<FilmSched>(t * 16, s, c, hf, row, grp);
         LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);           // hidden_layers.s | hidden_layer_rgb
         const int n = hf * 128 + row;
+        float scale, shift;
+        film_scale_shift(params, film, ud, s, n, scale, shift);
+        const __nv_bfloat16 sh_hi = __float2bfloat16_rn(shift);
+        const __nv_bfloat16 sh_lo = __float2bfloat16_rn(shift - __bfloat162float(sh_hi));
         __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             int kk = grp * 8 + e;
-            int col = c < 4 ? c * 64 + kk : ((ud && kk < 3) ? 256 + kk : -1);
-            v[e] = __float2bfloat16_rn(col >= 0 ? params[L.w_off + (long long)n * L.in + col] : 0.f);
+            if (c < 4) v[e] = __float2bfloat16_rn(scale * params[L.w_off + (long long)n * L.in + c * 64 + kk]);
+            else if (kk < 3) v[e] = __float2bfloat16_rn((s == 7 && ud) ? scale * params[L.w_off + (long long)n * L.in + 256 + kk] : 0.f);
+            else if (kk == 3) v[e] = sh_hi;
+            else if (kk == 4) v[e] = sh_lo;
+            else v[e] = __float2bfloat16_rn(0.f);
         }
         uint8_t* dst = packed + step_base<FilmSched>(s) + (long long)(c * 2 + hf) * half_bytes<FilmSched>(s) +
                        sw128_offset((uint32_t)row, (uint32_t)grp);
@@ -118,13 +134,6 @@ __global__ void film_pack_kernel(const float* __restrict__ params, const float* 
         float* tab = reinterpret_cast<float*>(packed + kFilmChunkBytes);
         tab[t] = film_table_value(params, film, ud, (int)t);
     }
-}
-
-// per-latent fp32 tables for the batched kernel mode: tables_out[b][kFilmTabFloats] from film[b][9][512]
-__global__ void film_tables_kernel(const float* __restrict__ params, const float* __restrict__ film, int use_dir, float* __restrict__ tables_out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < kFilmTabFloats)
-        tables_out[(size_t)blockIdx.y * kFilmTabFloats + i] = film_table_value(params, film + (size_t)blockIdx.y * B2R_FILM_PARAMS, use_dir != 0, i);
 }
 
 // One NeRF layer's epilogue for this warp's half of the columns, fully unrolled (no per-step branches in the hot loop).
@@ -397,50 +406,46 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     tc_teardown(tmem_base, warp);
 }
 
-// One FiLM-SIREN layer's epilogue for this warp's QUARTER of the columns (64 = one K-block of the next layer):
-// sin(scale * acc + shift), unrolled.
-//   MODE 0: -> bf16 h (hidden_layers.0..5);  MODE 1: -> bf16 h + partial sigma head (hidden_layers.6, modules.py:112);
+// One FiLM-SIREN layer's epilogue for this warp's QUARTER of the columns (64 = one K-block of the next layer).  The FiLM
+// scale is folded into the weight rows and the shift rides on the aux chunk, so the accumulator is the sine's argument:
+//   MODE 0: sin(acc) -> bf16 h (hidden_layers.0..5);  MODE 1: -> bf16 h + partial sigma head (hidden_layers.6, modules.py:112);
 //   MODE 2: -> partial rgb head, no store (hidden_layer_rgb, modules.py:114-116)
-// t_q: TMEM address of the quarter; sc_q / sh_q: shared-memory addresses of this step's scale / shift slices; head: global
-// fp32 head weights of the quarter; h_blk: this thread's row in the destination K-block.
+// t_q: TMEM address of the quarter; head: shared-memory address of the quarter's fp32 head weights; h_blk: this thread's row in
+// the destination K-block.  No table loads in MODE 0: per element FMUL (1/2pi) + MUFU.SIN + half a bf16x2 pack.
 template <int MODE>
-__device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t sc_q, uint32_t sh_q, const float* __restrict__ head,
-                                         uint32_t h_blk, const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2) {
+__device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h_blk, const uint32_t (&xoff)[8], float& sigma, float& rgb0,
+                                         float& rgb1, float& rgb2) {
+    // 4 units of 16 columns, the TMEM load of unit u+1 in flight while unit u is evaluated
+    uint32_t va[16], vb[16];
+    tmem_ld16(t_q, va);
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-        uint32_t v[32];
-        tmem_ld32(t_q + (uint32_t)jj * 32u, v);
+    for (int u = 0; u < 4; ++u) {
+        uint32_t (&v)[16] = (u & 1) ? vb : va;
         tmem_ld_wait();
-        float f[32];
+        if (u < 3) tmem_ld16(t_q + (uint32_t)(u + 1) * 16u, (u & 1) ? va : vb);
+        float f[16];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 sc = lds128(sc_q + (uint32_t)(jj * 32 + q * 4) * 4u), sh = lds128(sh_q + (uint32_t)(jj * 32 + q * 4) * 4u);
-            f[4 * q + 0] = __sinf(fmaf(__uint_as_float(v[4 * q + 0]), sc.x, sh.x));
-            f[4 * q + 1] = __sinf(fmaf(__uint_as_float(v[4 * q + 1]), sc.y, sh.y));
-            f[4 * q + 2] = __sinf(fmaf(__uint_as_float(v[4 * q + 2]), sc.z, sh.z));
-            f[4 * q + 3] = __sinf(fmaf(__uint_as_float(v[4 * q + 3]), sc.w, sh.w));
-        }
+        for (int e = 0; e < 16; ++e) f[e] = __sinf(__uint_as_float(v[e]));
         if (MODE == 1) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 w = __ldg(reinterpret_cast<const float4*>(head + jj * 32) + q);
+            for (int q = 0; q < 4; ++q) {
+                float4 w = lds128(head + (uint32_t)(u * 16 + q * 4) * 4u);
                 sigma = fmaf(f[4 * q + 0], w.x, fmaf(f[4 * q + 1], w.y, fmaf(f[4 * q + 2], w.z, fmaf(f[4 * q + 3], w.w, sigma))));
             }
         }
         if (MODE == 2) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float4 w0 = __ldg(reinterpret_cast<const float4*>(head + jj * 32) + q);
-                float4 w1 = __ldg(reinterpret_cast<const float4*>(head + 256 + jj * 32) + q);
-                float4 w2 = __ldg(reinterpret_cast<const float4*>(head + 512 + jj * 32) + q);
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t wa = head + (uint32_t)(u * 16 + q * 4) * 4u;
+                float4 w0 = lds128(wa), w1 = lds128(wa + 1024u), w2 = lds128(wa + 2048u);
                 rgb0 = fmaf(f[4 * q + 0], w0.x, fmaf(f[4 * q + 1], w0.y, fmaf(f[4 * q + 2], w0.z, fmaf(f[4 * q + 3], w0.w, rgb0))));
                 rgb1 = fmaf(f[4 * q + 0], w1.x, fmaf(f[4 * q + 1], w1.y, fmaf(f[4 * q + 2], w1.z, fmaf(f[4 * q + 3], w1.w, rgb1))));
                 rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
             }
         } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                st_shared_v4(h_blk + xoff[jj * 4 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
+            for (int q = 0; q < 2; ++q)
+                st_shared_v4(h_blk + xoff[u * 2 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
                              pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
         }
     }
@@ -448,49 +453,50 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t sc_q, uint32_t s
 
 // =====================================================================================================
 // FiLM-SIREN (pi_GAN/modules.py:22-25, 70-118): sin(30 (gamma (W x + b) + beta)) layers.
-//   input_layer (3 -> 256) runs on CUDA cores in fp32 inside the input stage (K = 3 is no GEMM and its
-//   30x-amplified argument must not see bf16 inputs); hidden_layers.0..6 and hidden_layer_rgb are tcgen05
-//   steps whose epilogue is sin(scale * acc + shift) with scale = 30 gamma, shift = 30 (gamma b + beta)
-//   folded once per (weights, film) pair by the pack kernel; the sigma head (256 -> 1) rides on the
-//   epilogue of hidden_layers.6 and the rgb head (256 -> 3) on the epilogue of hidden_layer_rgb, both fp32.
+//   input_layer (3 -> 256) runs on CUDA cores in fp32 inside the input stage (K = 3 is no GEMM and its 30x-amplified
+//   argument must not see bf16 inputs; tables in shared memory); hidden_layers.0..6 and hidden_layer_rgb are tcgen05 steps
+//   whose accumulator already is the sine's argument: the pack kernel folds scale = 30 gamma into the bf16 weight rows and
+//   puts shift = 30 (gamma b + beta), split into two bf16 terms, on two extra K columns that meet constant ones in the aux
+//   block [dir(3), 1, 1] (one 16-K MMA per step).  The sigma head (256 -> 1) rides on the epilogue of hidden_layers.6 and
+//   the rgb head (256 -> 3) on the epilogue of hidden_layer_rgb, both fp32.
 //   sigma_only (create_mesh, pi_GAN/utils.py:82-90) stops after hidden_layers.6: 919,552 FLOP per row.
-// Per row the epilogue issues 2304 MUFU.SIN: the sine epilogue of a sub-tile is ~2.5x longer than its MMAs, so here the 16
-// epilogue warps are NOT split between the two sub-tiles (as in nerf_tc_kernel, where a sub-tile's warps idle while its own
-// MMAs run): every warp owns one 64-column quarter (= one K-block of the next layer) of BOTH sub-tiles and alternates
-// between them, so that the epilogue of one sub-tile always overlaps the MMAs of the other and no warp waits for "its" MMA.
+// Per row the epilogue issues 2304 MUFU.SIN: the sine epilogue of a sub-tile is longer than its MMAs, so the 16 epilogue
+// warps are NOT split between the two sub-tiles (as in nerf_tc_kernel, where a sub-tile's warps idle while its own MMAs
+// run): every warp owns one 64-column quarter (= one K-block of the next layer) of BOTH sub-tiles and alternates between
+// them, so that the epilogue of one sub-tile always overlaps the MMAs of the other and no warp waits for "its" MMA.
 //
-// Batched mode (Generator.forward's latent loop in one launch, pi_GAN/modules.py:176-184): `tables` != NULL holds one fp32
-// table set per latent and rows [b * rows_per_latent, (b+1) * rows_per_latent) belong to latent b (rows_per_latent is a
-// multiple of the 256-row tile); a CTA reloads its shared-memory scale / shift tables when its next tile is another latent's.
+// Batched mode (Generator.forward's latent loop in one launch, pi_GAN/modules.py:176-184): n_latents > 1 packed images one
+// after the other (b2r_mlp_tc_pack_film_batched); rows [b * rows_per_latent, (b+1) * rows_per_latent) belong to latent b
+// (rows_per_latent is a multiple of the 256-row tile); the producer streams the tile's latent's weights and the epilogue
+// warps reload the small fp32 tables when their next tile is another latent's.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int use_dir, int sigma_only,
-               float4* __restrict__ raw_out, const float* __restrict__ tables, long long rows_per_latent) {
+film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int sigma_only, float4* __restrict__ raw_out,
+               int n_latents, long long rows_per_latent) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PairLoop pl(rows);
-    auto latent_of = [&](long long p) -> long long { return tables ? ((2 * p + cx.rank) * kRowsTile) / rows_per_latent : 0; };
-    auto table_of = [&](long long lat) -> const float* {
-        return tables ? tables + (size_t)lat * kFilmTabFloats : reinterpret_cast<const float*>(packed + kFilmChunkBytes);
-    };
+    const bool batched = n_latents > 1;
+    auto latent_of = [&](long long p) -> long long { return batched ? ((2 * p + cx.rank) * kRowsTile) / rows_per_latent : 0; };
+    auto packed_of = [&](long long p) -> const uint8_t* { return packed + (size_t)latent_of(p) * kFilmPackedBytes; };
     long long cur_lat = latent_of(pl.first < pl.n_pairs ? pl.first : 0);
-    const float* __restrict__ tab = table_of(cur_lat);
     const int n_steps = sigma_only ? 7 : FilmSched::kSteps;
-    {   // scale[8][256] | shift[8][256] (16 KB) -> shared memory; the head weights stay in global memory (L1)
-        static_assert(kFSc == 0 && kFSh == 2048 && 4096 * 4 <= kTabBytes + kPartBytes, "FiLM table region");
-        const float4* tab_g = reinterpret_cast<const float4*>(tab);
-        for (int i = threadIdx.x; i < 4096 / 4; i += kThreads) {
+    static_assert(kFilmTabFloats * 4 <= (int)(kTabBytes + kPartBytes), "FiLM table region");
+    const uint32_t tab = cx.smem + kTabOff;                    // fp32 tables of the current latent (9.2 KB)
+    {
+        const float4* tab_g = reinterpret_cast<const float4*>(packed + (size_t)cur_lat * kFilmPackedBytes + kFilmChunkBytes);
+        for (int i = threadIdx.x; i < kFilmTabFloats / 4; i += kThreads) {
             float4 v = __ldg(tab_g + i);
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tab + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
         }
     }
     const uint32_t tmem_base = tc_prologue(cx, warp, 32);      // act_ready: 16 warps x 2 CTAs arrive per sub-tile and step
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<FilmSched>(cx, packed, pl, n_steps, use_dir);
+        if (lane == 0) producer_loop_fn<FilmSched>(cx, packed_of, pl, n_steps, 1);
     } else if (warp == 1) {
-        if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, use_dir);
-        else if (lane == 0) relay_loop<FilmSched>(cx, pl, n_steps, use_dir);
+        if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, 1);
+        else if (lane == 0) relay_loop<FilmSched>(cx, pl, n_steps, 1);
     } else if (warp >= kCtrlWarps) {
         // warp = 4 + cq*4 + quad: column quarter cq (64 columns = K-block cq), TMEM lane quadrant quad; thread = row r of BOTH sub-tiles
         const int ew = warp - kCtrlWarps;
@@ -499,7 +505,6 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
         const uint32_t xr = (uint32_t)(r & 7);
         const uint32_t act_leader0 = mapa(cx.act_ready, 0);
-        const uint32_t sc_q = cx.smem + kTabOff + (uint32_t)(cq * 64) * 4u, sh_q = sc_q + 2048u * 4u;
         uint32_t xoff[8];
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
@@ -514,17 +519,16 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             tc_fence_after();
         };
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
-            if (tables) {
+            if (batched) {
                 const long long lat = latent_of(p);
                 if (lat != cur_lat) {
-                    // another latent: all 16 epilogue warps are done with the old tables, then reload scale / shift (16 KB)
+                    // another latent: all 16 epilogue warps are done with the old tables, then reload them (9.2 KB)
                     cur_lat = lat;
-                    tab = table_of(lat);
                     asm volatile("bar.sync 3, 512;" ::: "memory");
-                    const float4* tab_g = reinterpret_cast<const float4*>(tab);
-                    for (int i = threadIdx.x - kCtrlWarps * 32; i < 4096 / 4; i += kEpiWarps * 32) {
+                    const float4* tab_g = reinterpret_cast<const float4*>(packed + (size_t)lat * kFilmPackedBytes + kFilmChunkBytes);
+                    for (int i = threadIdx.x - kCtrlWarps * 32; i < kFilmTabFloats / 4; i += kEpiWarps * 32) {
                         float4 v = __ldg(tab_g + i);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tab + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
                     }
                     asm volatile("bar.sync 3, 512;" ::: "memory");
                 }
@@ -543,12 +547,9 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     uint32_t pk[16];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const int n0 = cq * 64 + jj * 32 + q * 4;
-                        float4 wx = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + n0));
-                        float4 wy = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 256 + n0));
-                        float4 wz = __ldg(reinterpret_cast<const float4*>(tab + kFW0 + 512 + n0));
-                        float4 sc = __ldg(reinterpret_cast<const float4*>(tab + kFS0 + n0));
-                        float4 sh = __ldg(reinterpret_cast<const float4*>(tab + kFT0 + n0));
+                        const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
+                        const float4 wx = lds128(tab + kFW0 * 4u + n0), wy = lds128(tab + (kFW0 + 256) * 4u + n0), wz = lds128(tab + (kFW0 + 512) * 4u + n0);
+                        const float4 sc = lds128(tab + kFS0 * 4u + n0), sh = lds128(tab + kFT0 * 4u + n0);
                         float a0 = fmaf(wz.x, pnt[2], fmaf(wy.x, pnt[1], wx.x * pnt[0]));
                         float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
                         float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
@@ -560,8 +561,9 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     for (int q = 0; q < 4; ++q) st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
                 }
                 if (cq == 0) {
-                    // view direction (3 values, zero-padded to 16) -> chunks 0..1 of the aux block (hidden_layer_rgb's extra K)
-                    st_shared_v4(sub_base(g) + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 0.f), 0u, 0u);
+                    // aux block = [view direction (3), 1, 1, 0 ...] (16 K): the direction columns of hidden_layer_rgb and the two
+                    // constant ones that pick up every layer's FiLM shift (hi + lo)
+                    st_shared_v4(sub_base(g) + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 1.0f), pack_bf16(1.0f, 0.f), 0u);
                     st_shared_v4(sub_base(g) + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
                 }
                 arrive(g);
@@ -572,21 +574,21 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     wait_acc(g);
-                    film_epi<0>(t_q(g), sc_q + (uint32_t)s * 1024u, sh_q + (uint32_t)s * 1024u, nullptr, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                    film_epi<0>(t_q(g), 0u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
                     arrive(g);
                 }
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {                               // hidden_layers.6 (+ sigma head)
                 wait_acc(g);
-                film_epi<1>(t_q(g), sc_q + 6u * 1024u, sh_q + 6u * 1024u, tab + kFWS + cq * 64, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                film_epi<1>(t_q(g), tab + (uint32_t)(kFWS + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
                 if (!sigma_only) arrive(g);
             }
             if (!sigma_only) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {                           // hidden_layer_rgb (+ rgb head)
                     wait_acc(g);
-                    film_epi<2>(t_q(g), sc_q + 7u * 1024u, sh_q + 7u * 1024u, tab + kFWR + cq * 64, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                    film_epi<2>(t_q(g), tab + (uint32_t)(kFWR + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
                 }
             }
             tc_fence_before();
@@ -604,7 +606,7 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 const uint32_t pa = sub_base(g) + 8192u + (uint32_t)(r * 4) * 16u;
                 const float4 p0 = lds128(pa), p1 = lds128(pa + 16u), p2 = lds128(pa + 32u), p3 = lds128(pa + 48u);
                 if (ok) {
-                    float4 bh = __ldg(reinterpret_cast<const float4*>(tab + kFBH));     // (b_sigma, b_rgb[3])
+                    const float4 bh = lds128(tab + kFBH * 4u);          // (b_sigma, b_rgb[3])
                     float4 o;
                     if (sigma_only) { o.x = o.y = o.z = 0.f; }
                     else {
@@ -655,7 +657,7 @@ extern "C" int b2r_mlp_tc_pack(int model_kind, const float* params, const float*
     if (model_kind == B2R_MODEL_FILM) {
         B2R_CHECK_ARG(film, "b2r_mlp_tc_pack: FiLM model needs film params");
         long long threads = tc::kFilmChunkBytes / 16;
-        tc::film_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, film, use_dir, (uint8_t*)packed_out);
+        tc::film_pack_kernel<<<dim3((unsigned)((threads + 255) / 256), 1), 256, 0, (cudaStream_t)stream>>>(params, film, use_dir, (uint8_t*)packed_out);
         B2R_LAUNCH_CHECK("b2r_mlp_tc_pack");
         return 0;
     }
@@ -700,8 +702,7 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (model_kind == B2R_MODEL_FILM) {
         rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
-        tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, use_dir, sigma_only,
-                                                                      (float4*)raw_out, nullptr, 0);
+        tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0);
     } else {
         rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
@@ -711,38 +712,39 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     return 0;
 }
 
-extern "C" size_t b2r_mlp_tc_film_table_bytes(void) { return (size_t)b2r::tc::kFilmTabFloats * sizeof(float); }
-
-extern "C" int b2r_mlp_tc_film_tables(const float* params, const float* film, int use_dir, int n_latents, float* tables_out, void* stream) {
+extern "C" int b2r_mlp_tc_pack_film_batched(const float* params, const float* film, int use_dir, int n_latents, void* packed_out, void* stream) {
     using namespace b2r;
-    B2R_CHECK_ARG(params && film && tables_out, "b2r_mlp_tc_film_tables: NULL pointer");
-    B2R_CHECK_ARG(n_latents >= 0 && n_latents <= 65535, "b2r_mlp_tc_film_tables: n_latents out of range");
+    B2R_CHECK_ARG(params && film && packed_out, "b2r_mlp_tc_pack_film_batched: NULL pointer");
+    B2R_CHECK_ARG(((uintptr_t)packed_out & 15) == 0, "b2r_mlp_tc_pack_film_batched: packed_out must be 16-byte aligned");
+    B2R_CHECK_ARG(n_latents >= 0 && n_latents <= 65535, "b2r_mlp_tc_pack_film_batched: n_latents out of range");
     if (n_latents == 0) return 0;
-    dim3 grid((tc::kFilmTabFloats + 255) / 256, (unsigned)n_latents);
-    tc::film_tables_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, film, use_dir, tables_out);
-    B2R_LAUNCH_CHECK("b2r_mlp_tc_film_tables");
+    long long threads = tc::kFilmChunkBytes / 16;
+    tc::film_pack_kernel<<<dim3((unsigned)((threads + 255) / 256), (unsigned)n_latents), 256, 0, (cudaStream_t)stream>>>(params, film, use_dir,
+                                                                                                                  (uint8_t*)packed_out);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_pack_film_batched");
     return 0;
 }
 
-extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, const float* tables, int n_latents, long long rows_per_latent, int use_dir,
-                                           const b2r_mlp_input* in, float* raw_out, int sigma_only, void* stream) {
+extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in, float* raw_out,
+                                           int sigma_only, void* stream) {
     using namespace b2r;
-    B2R_CHECK_ARG(packed && tables && raw_out, "b2r_mlp_tc_fwd_film_batched: NULL pointer");
-    B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out | (uintptr_t)tables) & 15) == 0, "b2r_mlp_tc_fwd_film_batched: buffers must be 16-byte aligned");
+    B2R_CHECK_ARG(packed && raw_out, "b2r_mlp_tc_fwd_film_batched: NULL pointer");
+    B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out) & 15) == 0, "b2r_mlp_tc_fwd_film_batched: buffers must be 16-byte aligned");
     int rc = check_mlp_input(in);
     if (rc) return rc;
     long long rows = row_count(in);
     B2R_CHECK_ARG(rows_per_latent > 0 && rows_per_latent % tc::kRowsTile == 0,
                   "b2r_mlp_tc_fwd_film_batched: rows_per_latent (%lld) must be a positive multiple of %d", rows_per_latent, tc::kRowsTile);
-    B2R_CHECK_ARG(rows <= rows_per_latent * (long long)n_latents, "b2r_mlp_tc_fwd_film_batched: %lld rows need more than %d latents", rows, n_latents);
+    B2R_CHECK_ARG(n_latents >= 1 && rows <= rows_per_latent * (long long)n_latents, "b2r_mlp_tc_fwd_film_batched: %lld rows need more than %d latents", rows, n_latents);
     if (rows == 0) return 0;
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
     rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
     if (rc) return rc;
-    tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, use_dir, sigma_only,
-                                                                                     (float4*)raw_out, tables, rows_per_latent);
+    // n_latents == 1 still goes through the batched indexing (latent 0 for every row) when rows_per_latent covers all rows
+    tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only,
+                                                                                     (float4*)raw_out, n_latents, rows_per_latent);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd_film_batched");
     return 0;
 }

@@ -35,13 +35,17 @@ struct NerfSched {       // step 0..7 = layers_pos.0..7, 8 = layers_dir.0, 9 = l
     __host__ __device__ static constexpr int n(int s) { return s == 9 ? 128 : 256; }
     static constexpr int kPostMmas = 2;                  // dir-enc: 24 -> 32 K
 };
-struct FilmSched {       // steps 0..6 = hidden_layers.0..6, step 7 = hidden_layer_rgb ([h | dir]); flag = use_dir
+// FiLM-SIREN: steps 0..6 = hidden_layers.0..6, step 7 = hidden_layer_rgb ([h | dir]).  Every step has a 16-K "post" chunk read
+// from the aux block [dir(3), 1, 1, 0...]: its weights carry the view-direction columns (step 7) and the FiLM SHIFT of the
+// layer as two bf16 terms (hi + lo) against the two constant ones, and the weight rows are pre-multiplied by the FiLM SCALE
+// (30 gamma) -- so the accumulator IS the sine's argument and the epilogue needs no table at all.
+struct FilmSched {
     static constexpr int kSteps = 8;
     __host__ __device__ static constexpr int n_pre(int, int) { return 0; }
     __host__ __device__ static constexpr int n_h(int, int) { return 4; }
-    __host__ __device__ static constexpr int n_post(int s, int use_dir) { return (s == 7 && use_dir) ? 1 : 0; }
+    __host__ __device__ static constexpr int n_post(int, int) { return 1; }
     __host__ __device__ static constexpr int n(int) { return 256; }
-    static constexpr int kPostMmas = 1;                  // view direction: 3 -> 16 K
+    static constexpr int kPostMmas = 1;                  // [dir(3), 1, 1] -> 16 K
 };
 template <class S>
 __host__ __device__ constexpr uint32_t half_bytes(int s) { return (uint32_t)(S::n(s) / 2) * 128u; }
@@ -56,14 +60,14 @@ __host__ __device__ constexpr long long step_base(int s) {
 }
 
 constexpr long long kNerfChunkBytes = step_base<NerfSched>(NerfSched::kSteps);      // 1,196,032
-constexpr long long kFilmChunkBytes = step_base<FilmSched>(FilmSched::kSteps);      // 1,081,344
-static_assert(kNerfChunkBytes == 1196032 && kFilmChunkBytes == 1081344, "packed chunk bytes");
+constexpr long long kFilmChunkBytes = step_base<FilmSched>(FilmSched::kSteps);      // 1,310,720
+static_assert(kNerfChunkBytes == 1196032 && kFilmChunkBytes == 8 * 5 * 32768, "packed chunk bytes");
 // NeRF fp32 tables after the chunks: bias[10][256] | w_sigma[256] | w_rgb[3][128] | b_sigma, b_rgb[3]
 constexpr int kNerfTabBias = 0, kNerfTabWSigma = 2560, kNerfTabWRgb = 2816, kNerfTabBHead = 3200, kNerfTabFloats = 3204;
 constexpr long long kNerfPackedBytes = kNerfChunkBytes + kNerfTabFloats * 4;
-// FiLM fp32 tables: scale[8][256] | shift[8][256] | w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
+// FiLM fp32 tables (all staged in shared memory): w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
 //                   w_sigma[256] | w_rgb[3][256] | b_sigma, b_rgb[3]
-constexpr int kFSc = 0, kFSh = 2048, kFW0 = 4096, kFS0 = 4864, kFT0 = 5120, kFWS = 5376, kFWR = 5632, kFBH = 6400, kFilmTabFloats = 6404;
+constexpr int kFW0 = 0, kFS0 = 768, kFT0 = 1024, kFWS = 1280, kFWR = 1536, kFBH = 2304, kFilmTabFloats = 2308;
 constexpr long long kFilmPackedBytes = kFilmChunkBytes + kFilmTabFloats * 4;
 
 // ---- packed weights: which (step, chunk, half, row, 16-byte group) a byte of the chunk area belongs to ----
@@ -201,10 +205,12 @@ struct PairLoop {
 };
 
 // weight producer: one thread per CTA streams ITS half of every chunk in schedule order (each step twice: once per sub-tile)
-template <class S>
-__device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __restrict__ packed, const PairLoop& pl, int n_steps, int flag) {
+// base_of(p): packed chunk area used by tile pair p (one per latent in the batched FiLM mode)
+template <class S, class BaseFn>
+__device__ __forceinline__ void producer_loop_fn(const Ctx& cx, BaseFn base_of, const PairLoop& pl, int n_steps, int flag) {
     uint32_t stage = 0, phase = 0;
     for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        const uint8_t* __restrict__ packed = base_of(p);
         for (int s = 0; s < n_steps; ++s) {
             const int nc = S::n_pre(s, flag) + S::n_h(s, flag) + S::n_post(s, flag);
             const uint32_t bytes = half_bytes<S>(s);
@@ -219,6 +225,11 @@ __device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __re
             }
         }
     }
+}
+
+template <class S>
+__device__ __forceinline__ void producer_loop(const Ctx& cx, const uint8_t* __restrict__ packed, const PairLoop& pl, int n_steps, int flag) {
+    producer_loop_fn<S>(cx, [packed](long long) { return packed; }, pl, n_steps, flag);
 }
 
 // peer CTA: forward "my half of this stage has landed" to the leader's ring barrier (count 2 there)

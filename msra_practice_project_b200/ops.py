@@ -504,12 +504,12 @@ def mlp_film_batched(model, film: torch.Tensor, rays: torch.Tensor, z: torch.Ten
     if rows == 0:
         return raw
     n_lat = film.shape[0]
-    tables = torch.empty((n_lat, lib().b2r_mlp_tc_film_table_bytes() // 4), dtype=torch.float32, device=dev)
+    packed = torch.empty((n_lat, lib().b2r_mlp_tc_packed_bytes(kind)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        packed = pack_tc(flat, kind, film[0].contiguous(), use_dir)
-        check(lib().b2r_mlp_tc_film_tables(ptr(flat), ptr(film), int(use_dir), n_lat, ptr(tables), _stream(flat)), "b2r_mlp_tc_film_tables")
-        check(lib().b2r_mlp_tc_fwd_film_batched(ptr(packed), ptr(tables), n_lat, int(rows_per_latent), int(use_dir), C.byref(inp), ptr(raw),
-                                                int(sigma_only), _stream(flat)), "b2r_mlp_tc_fwd_film_batched")
+        check(lib().b2r_mlp_tc_pack_film_batched(ptr(flat), ptr(film), int(use_dir), n_lat, ptr(packed), _stream(flat)),
+              "b2r_mlp_tc_pack_film_batched")
+        check(lib().b2r_mlp_tc_fwd_film_batched(ptr(packed), n_lat, int(rows_per_latent), C.byref(inp), ptr(raw), int(sigma_only),
+                                                _stream(flat)), "b2r_mlp_tc_fwd_film_batched")
     del keep
     return raw
 

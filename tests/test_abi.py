@@ -59,7 +59,7 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     assert lib.b2r_mlp_tc_train_scratch_bytes(0, 1000) == 8 * (38 * 16384 + 128 * 16)
     assert lib.b2r_mlp_tc_train_saved_bytes(1, 1000) == 0 and lib.b2r_mlp_tc_train_saved_bytes(0, 0) == 0
     assert lib.b2r_mlp_tc_bwd_packed_bytes(0) == 34 * 32768 + 640 * 4 and lib.b2r_mlp_tc_bwd_packed_bytes(1) == 0
-    assert lib.b2r_mlp_tc_film_table_bytes() == 6404 * 4
+    assert lib.b2r_mlp_tc_packed_bytes(1) == 8 * 5 * 32768 + 2308 * 4                                     # FiLM-SIREN
     assert lib.b2r_mlp_tc_packed_bytes(2) == (4 * 4 + 5 + 2 * 4 + 4) * 32768 + 5 * 16384 + 3972 * 4      # SirenNeRF
     assert lib.b2r_mlp_f32_workspace_bytes(2, 10, 1) == 10 * 4620 * 4
     inp = _lib.MlpInput()
@@ -67,7 +67,8 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     assert lib.b2r_mlp_tc_train_fwd(1, 16, C.byref(inp), 16, 16, 1 << 30, None) < 0 and b"NeRF" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_fwd(0, 16, C.byref(inp), 16, 16, 64, None) < 0 and b"too small" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_bwd(0, 16, 512, 16, 16, 16, 16, 64, 16, None) < 0 and b"scratch" in lib.b2r_last_error()
-    assert lib.b2r_mlp_tc_fwd_film_batched(16, 16, 2, 100, 1, C.byref(inp), 16, 0, None) < 0 and b"multiple of 256" in lib.b2r_last_error()
-    assert lib.b2r_mlp_tc_fwd_film_batched(16, 16, 1, 256, 1, C.byref(inp), 16, 0, None) < 0 and b"latents" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_fwd_film_batched(16, 2, 100, C.byref(inp), 16, 0, None) < 0 and b"multiple of 256" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_fwd_film_batched(16, 1, 256, C.byref(inp), 16, 0, None) < 0 and b"latents" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_pack_film_batched(None, None, 1, 2, None, None) < 0
     assert lib.b2r_adam_step(None, None, None, None, 4, None, 1e-3, 0.1, 0.0, 0.9, 0.999, 1e-8, 1.0, None) < 0
     assert lib.b2r_to8b(None, 4, None, None) < 0 and lib.b2r_to8b(None, 0, None, None) == 0
