@@ -60,7 +60,7 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     assert lib.b2r_mlp_tc_train_saved_bytes(1, 1000) == 0 and lib.b2r_mlp_tc_train_saved_bytes(0, 0) == 0
     assert lib.b2r_mlp_tc_bwd_packed_bytes(0) == 34 * 32768 + 640 * 4 and lib.b2r_mlp_tc_bwd_packed_bytes(1) == 0
     assert lib.b2r_mlp_tc_packed_bytes(1) == 8 * 5 * 32768 + 2308 * 4                                     # FiLM-SIREN
-    assert lib.b2r_mlp_tc_packed_bytes(2) == (4 * 4 + 5 + 2 * 4 + 4) * 32768 + 5 * 16384 + 3972 * 4      # SirenNeRF
+    assert lib.b2r_mlp_tc_packed_bytes(2) == 8 * 5 * 32768 + 5 * 16384 + 1668 * 4      # SirenNeRF
     assert lib.b2r_mlp_f32_workspace_bytes(2, 10, 1) == 10 * 4620 * 4
     inp = _lib.MlpInput()
     inp.x, inp.n_rays, inp.n_samples = 256, 512, 1
