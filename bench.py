@@ -415,6 +415,18 @@ def run_secondary(args, config=None, embedded=False):
                         f"layer-wise MLP forward with saved fp32 activations + CUDA reverse mode, GEMMs in {args.grad_precision}, ") +
                         "one NCCL all-reduce of the 4.75 MB gradient bucket" + ("" if args.grad_precision == "bf16" else ", torch Adam")),
                     tflops=rows * 1182976 * 3 / (ms * 1e-3) / 1e12)
+        if args.grad_precision == "bf16":
+            # the fused training kernels are HBM-bound: algorithmic bytes per MLP row = checkpoints + relu bits written by
+            # the forward (5,392), d(pre-activation) tiles written + bits read by dgrad (5,152 incl. head gradients), tiles read by wgrad +
+            # heads (10,624 + 784), raw / d_raw (48)
+            bytes_row = 5392 + 5152 + 10624 + 784 + 48
+            pk = peaks()
+            line["roofline"] = dict(bound="hbm", kernel="whole training step (nerf_tc_kernel<true> + nerf_tc_bwd_kernel + nerf_tc_wgrad_kernel + heads)",
+                                    achieved=rows / world * bytes_row / (ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
+                                    frac=rows / world * bytes_row / (ms * 1e-3) / 1e9 / pk["hbm"], peak_source=pk["src"],
+                                    bytes_per_row=bytes_row, traffic=None,
+                                    note="per-kernel DRAM traffic and times: profiles/r1_train_{fwd,bwd,wgrad}_ncu.txt (forward / dgrad at the "
+                                         "3.93 TB/s write-only ceiling, wgrad at 0.83 of the copy peak)")
     elif config == "siren":
         # SirenNeRF (use_siren, nerf/train_nerf.py:89-91): the 800x800, 64+128 render with the fused SIREN kernel
         w = h = 800
