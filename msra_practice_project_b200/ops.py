@@ -220,6 +220,14 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: tor
 
 # ---- K3 / K7 / K8 ------------------------------------------------------------------------------------------
 _pack_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_pack_bwd_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def invalidate_packed(model) -> None:
+    """Forget the cached bf16 weight images of `model` (call after changing its parameters in a way torch cannot see,
+    e.g. a kernel writing the flat master buffer: train_step.NerfTrainStep does this after every step)."""
+    _pack_cache.pop(model, None)
+    _pack_bwd_cache.pop(model, None)
 
 
 def _packed_weights(model, kind: int, flat: torch.Tensor, film: torch.Tensor | None, use_dir: bool) -> torch.Tensor:
@@ -307,9 +315,6 @@ class _MlpF32(torch.autograd.Function):
                                         ptr(ws), ptr(scratch), sc_bytes, ptr(d_flat), ptr(d_film), ctx.gemm_mode, _stream(flat)),
                   "b2r_mlp_f32_bwd")
         return d_flat, d_film, None, None, None, None, None, None
-
-
-_pack_bwd_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 
 
 def _packed_bwd_weights(model, kind: int, flat: torch.Tensor) -> torch.Tensor:

@@ -154,6 +154,8 @@ class NerfTrainStep:
             self._graphs[1].replay()
         else:
             self._optimize()
+        for m in self.models:                       # the weights changed behind torch's version counters
+            ops.invalidate_packed(m)
         return self.loss, self.psnr
 
     # ---- bookkeeping ----------------------------------------------------------------------------------------------

@@ -784,9 +784,17 @@ def test_fused_train_step_matches_autograd_path(golden, graph):
     # Adam moves every weight by ~lr per step whatever the gradient's size: a weight whose gradient is summation-order noise
     # (float atomics in wgrad) may walk the other way -> bounded by 2 * 6 * lr; on average the updates agree
     assert worst <= 2 * 6 * 5e-4 + 1e-6 and mean < 2e-4, (worst, mean)
+    # a render through the drop-in module in the middle of training must see the CURRENT weights (the fused step updates the
+    # flat master buffer behind torch's version counters): compare with fresh models loaded from the state dicts
+    c3, f3 = models.NeRF().cuda(), models.NeRF().cuda()
+    c3.load_state_dict(c2.state_dict()); f3.load_state_dict(f2.state_dict())
     with torch.no_grad():
         img = nerf_render.render_rays(rays[:64], 2.0, 6.0, c2, f2, sc, sf, t_rand=ts[0][:64])[3]
-    assert torch.isfinite(img).all()
+        step(rays, target, alpha, t_rand=ts[0])
+        img_after = nerf_render.render_rays(rays[:64], 2.0, 6.0, c2, f2, sc, sf, t_rand=ts[0][:64])[3]
+        img_ref = nerf_render.render_rays(rays[:64], 2.0, 6.0, c3, f3, sc, sf, t_rand=ts[0][:64])[3]
+    assert torch.isfinite(img).all() and torch.equal(img, img_ref)
+    assert not torch.equal(img_after, img), "render after another training step used stale packed weights"
 
 
 def test_siren_nerf_forward_and_training_gradients(golden):
