@@ -277,8 +277,8 @@ def run_b200(args):
         w_c = torch.rand((count, sc), device=dev)
         u = torch.linspace(0.0, 1.0, sf).to(dev)
 
-        def time_it(fn, reps=10):
-            fn(); torch.cuda.synchronize()
+        def time_it(fn, reps=20):
+            fn(); fn(); torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(reps):
@@ -286,13 +286,31 @@ def run_b200(args):
             e1.record(); torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
 
+        # kernel-only timings: the C ABI is called directly on preallocated buffers (no autograd wrapper, no allocation, no
+        # host-side linspace inside the timed loop), back to back on the current stream
+        import ctypes as C
+        L, P_, st = _lib.lib(), _lib.ptr, torch.cuda.current_stream(dev).cuda_stream
+        S2 = sc + sf
+        o_rgb, o_d, o_a = torch.empty((count, 3), device=dev), torch.empty((count,), device=dev), torch.empty((count,), device=dev)
+        o_w, o_sorted, o_z = torch.empty((count, sc), device=dev), torch.empty((count, S2), device=dev), torch.empty((count, sc), device=dev)
+        o_mids, o_rays = torch.empty((sc - 1,), device=dev), torch.empty((count, 2, 3), device=dev)
+        z_lin_d = torch.linspace(2.0, 6.0, sc).to(dev)
+        dptr = rays.data_ptr() + 12
+        c2w = np.ascontiguousarray(np.asarray(pose)[:3, :4], dtype=np.float64)
+
+        def chk(rc):
+            assert rc == 0, L.b2r_last_error()
         cases = [
-            ("composite_fwd coarse (weights written)", lambda: ops.composite(raw_c, zc, rays[:, 1], True), count * (sc * 24 + 32)),
-            ("composite_fwd fine (weights skipped)", lambda: ops.composite(raw_f, zf, rays[:, 1], False), count * ((sc + sf) * 20 + 32)),
-            ("sample_pdf + merge", lambda: ops.sample_pdf(mids, w_c[:, 1:-1], sf, u=u, z_coarse=zc, want_samples=False),
-             count * ((sc - 2) * 4 + sc * 4 + (sc + sf) * 4)),
-            ("stratified_z", lambda: ops.stratified_z(torch.linspace(2.0, 6.0, sc).to(dev), t_rand), count * sc * 8),
-            ("raygen", lambda: ops.raygen(W, H, focal, pose, begin, count, device=dev), count * 24),
+            ("composite_fwd coarse (weights written)",
+             lambda: chk(L.b2r_composite_fwd(P_(raw_c), P_(zc), dptr, 6, count, sc, P_(o_rgb), P_(o_d), P_(o_a), P_(o_w), st)), count * (sc * 24 + 32)),
+            ("composite_fwd fine (weights skipped)",
+             lambda: chk(L.b2r_composite_fwd(P_(raw_f), P_(zf), dptr, 6, count, S2, P_(o_rgb), P_(o_d), P_(o_a), None, st)), count * (S2 * 20 + 32)),
+            ("sample_pdf + merge",
+             lambda: chk(L.b2r_sample_pdf(P_(mids), 0, w_c.data_ptr() + 4, sc, P_(u), count, sc - 1, sf, P_(zc), sc, None, P_(o_sorted), None, st)),
+             count * ((sc - 2) * 4 + sc * 4 + S2 * 4)),
+            ("stratified_z", lambda: chk(L.b2r_stratified_z(P_(z_lin_d), P_(t_rand), count, sc, P_(o_z), P_(o_mids), st)), count * sc * 8),
+            ("raygen", lambda: chk(L.b2r_raygen(c2w.ctypes.data_as(C.POINTER(C.c_double)), W, H, float(focal), 0, begin, count, P_(o_rays), st)),
+             count * 24),
         ]
         for name, fn, nbytes in cases:
             ms = time_it(fn)
