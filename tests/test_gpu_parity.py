@@ -901,3 +901,34 @@ def test_to8b_device_and_streamed_video():
     ref, _, _ = nerf_render.render_video(24, 16, 24 * 1.3875, poses, 2.0, 6.0, c, f, 8, 8)
     assert vid.shape == (3, 16, 24, 3) and vid.dtype == np.uint8
     assert np.array_equal(vid, nerf_render.to8b(ref))
+
+
+def test_fused_train_step_draws_its_own_jitter_inside_the_graph(golden):
+    """NerfTrainStep with t_rand=None: the jitter of nerf/render.py:131 is drawn by torch.rand INSIDE the captured graph
+    (philox state advanced on every replay): steps see different jitter, the loss goes down, state_dict round-trips."""
+    from msra_practice_project_b200.train_step import NerfTrainStep
+    tr = golden.nerf_train
+    nb, sc, sf = 256, 16, 16
+    gen = torch.Generator().manual_seed(1)
+    rays = torch.cat([cu(tr["rays"])] * 20)[:nb].contiguous()
+    target = (torch.rand(nb, 3, generator=gen) * 0.5 + 0.25).cuda()
+    torch.manual_seed(0)
+    c, f = models.damp_nerf_(models.NeRF()).cuda(), models.damp_nerf_(models.NeRF()).cuda()
+    step = NerfTrainStep(c, f, 2.0, 6.0, sc, sf, nb, learning_rate=5e-4, learning_rate_decay=1)
+    jit, losses = [], []
+    for _ in range(6):
+        loss, psnr = step(rays, target)
+        losses.append(float(loss)); jit.append(step.in_t.clone())
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    assert not torch.equal(jit[0], jit[1]) and not torch.equal(jit[1], jit[2])
+    assert 0.0 <= float(jit[3].min()) and float(jit[3].max()) < 1.0
+    assert step.global_step == 6 and abs(step.learning_rate - 5e-4 * 0.1 ** (6 / 1000.0)) < 1e-9
+    sd = step.state_dict()
+    c2, f2 = models.NeRF().cuda(), models.NeRF().cuda()
+    c2.load_state_dict(c.state_dict()); f2.load_state_dict(f.state_dict())
+    step2 = NerfTrainStep(c2, f2, 2.0, 6.0, sc, sf, nb, learning_rate=5e-4, learning_rate_decay=1, graph=False)
+    step2.load_state_dict(sd)
+    t = torch.rand(nb, sc, generator=gen).cuda()
+    l1 = float(step(rays, target, t_rand=t)[0]); l2 = float(step2(rays, target, t_rand=t)[0])
+    assert abs(l1 - l2) < 1e-5 * max(1.0, abs(l1)) and step2.global_step == 7
+    assert (step.params - step2.params).abs().max().item() <= 2 * 5e-4 + 1e-6
