@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="headline run: skip the other BASELINE.json configs")
     ap.add_argument("--no-graph", action="store_true", help="training config: launch the step's kernels directly (for ncu)")
-    ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid", "siren"],
+    ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid", "siren", "siren_train", "pigan_grad"],
                     help="render = the headline NeRF 800x800 frame (default; BASELINE.json configs[1]); the others are the "
                          "secondary BASELINE configs: train = 4096-ray NeRF training step (configs[2]), pigan = pi-GAN 128x128 "
                          "24+24 x 64 latents (configs[3]), grid = 256^3 density query (configs[4])")
@@ -329,7 +329,7 @@ def run_b200(args):
     # the other BASELINE.json configs (training step, pi-GAN batch, density grid, SirenNeRF frame), measured in the same job
     secondary = []
     if not args.no_secondary:
-        for cfg in ("train", "pigan", "grid", "siren"):
+        for cfg in ("train", "pigan", "grid", "siren", "siren_train", "pigan_grad"):
             try:
                 res = run_secondary(args, cfg, embedded=True)
             except Exception as e:          # a secondary config must never take the headline line down
@@ -466,6 +466,74 @@ def run_secondary(args, config=None, embedded=False):
                     ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
                     config=dict(workload="SirenNeRF 800x800 render, 64+128 samples, rays sharded by pixel rows, fused tcgen05 SIREN kernel"),
                     tflops=rows * 1123840 / (ms * 1e-3) / 1e12)
+    elif config == "siren_train":
+        # train_nerf.py with use_siren (nerf/train_nerf.py:89-91,151-168): SirenNeRF has no fused reverse mode yet; its gradients run
+        # through the layer-wise path (autograd wrappers + torch Adam), GEMMs in bf16 on tcgen05
+        n_batch, sc, sf = 4096, args.coarse, args.fine
+        b, c = shard.shard_range(n_batch, rank, world)
+        torch.manual_seed(0)
+        coarse, fine = models.SirenNeRF().to(dev), models.SirenNeRF().to(dev)
+        opt = torch.optim.Adam(list(coarse.parameters()) + list(fine.parameters()), lr=5e-4)
+        pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+        from msra_practice_project_b200 import ops
+        rays = ops.raygen(800, 800, 800 * 1.3875, pose, 320000 + b, c, device=dev)
+        torch.manual_seed(1)
+        target = torch.rand((n_batch, 3), device=dev)[b:b + c]
+        torch.manual_seed(5)
+        t_rand = torch.rand((n_batch, sc), device=dev)[b:b + c].contiguous()
+
+        def step():
+            old = ops.set_grad_precision("bf16")
+            try:
+                opt.zero_grad(set_to_none=True)
+                rc, _, _, rf, _, _ = nerf_render.render_rays(rays, 2.0, 6.0, coarse, fine, sc, sf, t_rand=t_rand)
+                loss = ((rf - target) ** 2).sum() / (n_batch * 3) + ((rc - target) ** 2).sum() / (n_batch * 3)
+                loss.backward()
+                shard.allreduce_gradients([coarse, fine], average=False)
+                opt.step()
+            finally:
+                ops.set_grad_precision(old)
+        ms = timed(step, min(args.steps, 3), args.warmup)
+        rows = n_batch * (2 * sc + sf)
+        line = dict(metric="rays/s, SirenNeRF training step (4096-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
+                    unit="rays/s", ms_per_step=ms, dtype="bf16", scaling="strong",
+                    config=dict(workload="SirenNeRF train step, 4096 rays sharded over ranks, layer-wise forward with saved fp32 activations + CUDA "
+                                         "reverse mode, GEMMs in bf16 on tcgen05 (bgemm.cuh), torch Adam"),
+                    tflops=rows * 1123840 * 3 / (ms * 1e-3) / 1e12)
+    elif config == "pigan_grad":
+        # pi-GAN gradient step through the renderer (pi_GAN/train.py:128-134 generator update without the discriminator; the
+        # latent inversion of synthesis.py:92-107 is the same with frozen weights): 4 latents x 64x64, 24+24 samples, gradients to the
+        # FiLM parameters and the FiLM-SIREN weights; coarse pass without gradient, fine pass layer-wise fp32 + reverse mode
+        n_lat, res, s_ = 4, 64, 24
+        b, c = shard.shard_range(n_lat, rank, world)
+        torch.manual_seed(0)
+        net = models.FilmSirenNeRF().to(dev)
+        g = torch.Generator().manual_seed(0)
+        film = torch.cat([1.0 + 0.2 * torch.randn(n_lat, 9, 256, generator=g), 0.1 * torch.randn(n_lat, 9, 256, generator=g)], -1).to(dev)
+        film.requires_grad_(True)
+        focal = np.float64(res / 2 / np.tan(6 * np.pi / 180))
+        poses = [pigan_render.camera_pos_to_transform_matrix(1, 0.3 * np.sin(i), 0.15 * np.cos(i)) for i in range(n_lat)]
+        target = torch.rand((n_lat, 3, res, res), generator=g).to(dev)
+
+        def step():
+            from msra_practice_project_b200 import ops
+            old = ops.set_grad_precision("bf16")
+            try:
+                net.zero_grad(set_to_none=True)
+                film.grad = None
+                if c > 0:
+                    imgs = pigan_render.render_batch(net, film[b:b + c], poses[b:b + c], res, res, focal, 0.5, 1.5, s_, s_)
+                    ((imgs - target[b:b + c]) ** 2).mean().backward()
+                shard.allreduce_gradients([net], average=False)
+            finally:
+                ops.set_grad_precision(old)
+        ms = timed(step, min(args.steps, 3), args.warmup)
+        rows = n_lat * res * res * 2 * s_
+        line = dict(metric="rays/s, pi-GAN gradient step through the renderer (4 latents x 64x64, 24+24 samples; d/dfilm + d/dweights)",
+                    value=n_lat * res * res / (ms * 1e-3), unit="rays/s", ms_per_step=ms, dtype="bf16", scaling="strong",
+                    config=dict(workload="pi-GAN generator-side gradient step, latents sharded over ranks, coarse pass bf16 inference, fine pass "
+                                         "layer-wise forward + CUDA reverse mode with bf16 tcgen05 GEMMs (FiLM d gamma / d beta and weight gradients)"),
+                    tflops=rows * 1053696 * 3 / (ms * 1e-3) / 1e12)
     elif config == "pigan":
         n_lat, res, s_ = 64, 128, 24
         b, c = shard.shard_range(n_lat, rank, world)

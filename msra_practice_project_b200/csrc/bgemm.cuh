@@ -1,0 +1,218 @@
+// BF16 tensor-core GEMM (tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM) with the same contract as sgemm.cuh /
+// tgemm.cuh -- the engine of the layer-wise path when gemm_mode = 2 (FiLM-SIREN / SirenNeRF training in bf16 class):
+//
+//   C[i,j] (op)= sum_r P(i,r) * Q(j,r)          tile 128 (i) x 256 (j) x 64 (r), 256 threads, 2-stage pipeline, 2 CTAs / SM
+//
+// It reads the SAME fp32 buffers as the other two engines and converts to bf16 while staging (global -> registers ->
+// cvt.rn.bf16x2 -> st.shared, SWIZZLE_128B).  No operand is ever transposed: a tile is always copied as
+// [rows of the global matrix] x [64 contiguous columns] blocks, and the MMA reads a block either K-major (the rows are the
+// M / N index: forward's x and W, dgrad's g) or MN-major (the rows are the reduction index: dgrad's W, wgrad's g and x) --
+// the MN-major SWIZZLE_128B descriptors (LBO = 8 KB to the next 64 columns, SBO = 1 KB to the next 8 rows) are the ones
+// PROBE4 of tests/native/umma_probe.cu pins.
+//   forward   y = x W^T      : P = x [m][k] K-major,        Q = W [n][k] K-major
+//   dgrad     dx = g W       : P = g [m][n] K-major,        Q = W [n][k] read as Q(j=k, r=n): MN-major
+//   wgrad     dW += g^T x    : P = g [m][n] as P(i=n, r=m): MN-major,   Q = x [m][k] as Q(j=k, r=m): MN-major (split over r, fp32 atomics)
+#pragma once
+#include "sgemm.cuh"
+#include "umma.cuh"
+
+namespace b2r {
+namespace bg {
+
+using namespace umma;
+
+constexpr int BBM = 128, BBN = 256, BBK = 64, BSTAGES = 2;
+constexpr uint32_t kAStage = BBM * BBK * 2;            // 16 KB
+constexpr uint32_t kBStage = BBN * BBK * 2;            // 32 KB
+constexpr uint32_t kStage = kAStage + kBStage;         // 48 KB
+constexpr uint32_t kBgBarOff = BSTAGES * kStage;       // full[2], empty[2], acc, tmem slot
+constexpr uint32_t kBgSmem = kBgBarOff + 128 + 1024;   // 99,456 B -> 2 CTAs per SM
+
+__device__ __forceinline__ float4 ld4(const float* __restrict__ p, long long have, int vec) {
+    // up to 4 consecutive floats starting at p, `have` of them inside the matrix
+    if (vec && have >= 4) return __ldg(reinterpret_cast<const float4*>(p));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have > 0) v.x = __ldg(p);
+    if (have > 1) v.y = __ldg(p + 1);
+    if (have > 2) v.z = __ldg(p + 2);
+    if (have > 3) v.w = __ldg(p + 3);
+    return v;
+}
+
+// stage a tile into SWIZZLE_128B bf16 blocks of [rows x 64 columns] (128 B per row) at `dst`
+//   kT = false (K-major operand):  smem rows = kRows tile rows (i or j), smem columns = 64 r        (global base[row * ld + r])
+//                                  blocks of 128 rows, 16 KB apart
+//   kT = true  (MN-major operand): smem rows = 64 r, smem columns = kRows tile rows (i or j)        (global base[r * ld + row])
+//                                  column blocks of 64, 8 KB apart
+// Every thread handles kRows * 8 / 256 chunks of 8 values: all global loads are issued first, then converted and stored.
+template <bool kT, int kRows>
+__device__ __forceinline__ void stage_tile(uint32_t dst, const float* __restrict__ base, long long ld, long long row0,
+                                           long long row_max, long long r0, long long r_max, int vec, int tid) {
+    constexpr int NC = kRows * 8 / 256;                // 16-byte (8 x bf16) chunks per thread
+    float4 lo[NC], hi[NC];
+#pragma unroll
+    for (int it = 0; it < NC; ++it) {
+        const int f = tid + it * 256;
+        long long grow, gcol, cols_left;
+        bool row_ok;
+        if (!kT) { const int row = f >> 3, c = f & 7; grow = row0 + row; gcol = r0 + c * 8; row_ok = grow < row_max; cols_left = r_max - gcol; }
+        else { constexpr int CPR = kRows / 8; const int r = f / CPR, c = f - r * CPR; grow = r0 + r; gcol = row0 + c * 8; row_ok = grow < r_max; cols_left = row_max - gcol; }
+        lo[it] = hi[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && cols_left > 0) {
+            const float* p = base + grow * ld + gcol;
+            lo[it] = ld4(p, cols_left, vec);
+            hi[it] = ld4(p + 4, cols_left - 4, vec);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < NC; ++it) {
+        const int f = tid + it * 256;
+        uint32_t off;
+        if (!kT) { const uint32_t row = (uint32_t)(f >> 3), c = (uint32_t)(f & 7); off = (row >> 7) * 16384u + sw128_offset(row & 127u, c); }
+        else { constexpr int CPR = kRows / 8; const uint32_t r = (uint32_t)(f / CPR), c = (uint32_t)(f - (int)r * CPR); off = (c >> 3) * 8192u + sw128_offset(r, c & 7u); }
+        st_shared_v4(dst + off, pack_bf16(lo[it].x, lo[it].y), pack_bf16(lo[it].z, lo[it].w), pack_bf16(hi[it].x, hi[it].y), pack_bf16(hi[it].z, hi[it].w));
+    }
+}
+
+template <bool kPT, bool kQT>
+__global__ void __launch_bounds__(256, 2) bgemm_kernel(GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t full = smem + kBgBarOff, empty = full + 8 * BSTAGES, acc_bar = empty + 8 * BSTAGES, slot = acc_bar + 8;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long i0 = (long long)blockIdx.x * BBM;
+    const long long j0 = (long long)blockIdx.y * BBN;
+    const long long r_begin = (long long)blockIdx.z * g.r_chunk;
+    const long long r_end = min(g.R, r_begin + g.r_chunk);
+    const int n_cols = (int)min((long long)BBN, (long long)g.J - j0);          // valid columns of this tile
+    const uint32_t n_mma = (uint32_t)((n_cols + 15) & ~15);                      // UMMA N (multiple of 16)
+    const int b_rows = n_mma > 128 ? 256 : 128;                                   // rows of Q staged per stage
+    if (tid == 0) {
+        for (int s = 0; s < BSTAGES; ++s) { mbar_init(full + 8 * s, 256); mbar_init(empty + 8 * s, 1); }
+        mbar_init(acc_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot));
+
+    const uint32_t idesc = make_idesc_bf16(128, n_mma) | (kPT ? (1u << 15) : 0u) | (kQT ? (1u << 16) : 0u);
+    const uint64_t dk = desc_sw128(0);                                            // K-major: SBO 1024
+    const uint64_t dmn = make_desc(0, 8192, 1024, kLayoutSW128);                  // MN-major: LBO 8 KB (next 64 columns), SBO 1 KB
+    const int nk = (int)((r_end - r_begin + BBK - 1) / BBK);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int stage = kt % BSTAGES, use = kt / BSTAGES;
+        const uint32_t a_s = smem + (uint32_t)stage * kStage, b_s = a_s + kAStage;
+        if (kt >= BSTAGES) mbar_wait(empty + 8 * stage, (uint32_t)((use - 1) & 1));   // MMAs of iteration kt - BSTAGES are done
+        const long long r0 = r_begin + (long long)kt * BBK;
+        stage_tile<kPT, BBM>(a_s, g.P, g.ldp, i0, g.I, r0, r_end, g.vec, tid);
+        if (b_rows == 256) stage_tile<kQT, 256>(b_s, g.Q, g.ldq, j0, g.J, r0, r_end, g.vec, tid);
+        else stage_tile<kQT, 128>(b_s, g.Q, g.ldq, j0, g.J, r0, r_end, g.vec, tid);
+        fence_proxy_async_smem();
+        mbar_arrive(full + 8 * stage);
+        if (warp == 0) {
+            mbar_wait(full + 8 * stage, (uint32_t)(use & 1));
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                                     // 4 x K=16
+                    const uint32_t aa = kPT ? a_s + (uint32_t)k * 2048u : a_s + (uint32_t)k * 32u;
+                    const uint32_t ba = kQT ? b_s + (uint32_t)k * 2048u : b_s + (uint32_t)k * 32u;
+                    const uint64_t ad = (kPT ? dmn : dk) | (uint64_t)((aa >> 4) & 0x3FFFu);
+                    const uint64_t bd = (kQT ? dmn : dk) | (uint64_t)((ba >> 4) & 0x3FFFu);
+                    mma_bf16(tmem, ad, bd, idesc, (uint32_t)((kt | k) != 0));
+                }
+                mma_commit(empty + 8 * stage);
+                if (kt == nk - 1) mma_commit(acc_bar);
+            }
+            __syncwarp();
+        }
+    }
+    // ---- epilogue: thread = row (TMEM lane), warps 0-3 take columns [0,128), warps 4-7 columns [128,256)
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int quad = warp & 3, chalf = warp >> 2;
+    const long long i = i0 + quad * 32 + lane;
+    const bool c_vec = (((uintptr_t)g.C & 15) == 0) && (g.ldc % 4 == 0);
+    const bool m_vec = g.mask && (((uintptr_t)g.mask & 15) == 0) && (g.ldmask % 4 == 0);
+    for (int jj = 0; jj < 4; ++jj) {
+        const int c0 = chalf * 128 + jj * 32;
+        if (c0 >= (int)n_mma) break;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)quad << 21) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (i >= g.I) continue;
+#pragma unroll
+        for (int e4 = 0; e4 < 32; e4 += 4) {
+            const long long j = j0 + c0 + e4;
+            if (j >= g.J) break;
+            float val[4] = {__uint_as_float(v[e4]), __uint_as_float(v[e4 + 1]), __uint_as_float(v[e4 + 2]), __uint_as_float(v[e4 + 3])};
+            float* c = g.C + i * g.ldc + j;
+            const bool full4 = j + 3 < g.J;
+            const bool vec_c = full4 && c_vec;
+            float old[4] = {0.f, 0.f, 0.f, 0.f}, msk[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+            const int nv = full4 ? 4 : (int)(g.J - j);
+            if (g.epi != EPI_DGRAD && g.epi != EPI_ATOMIC && g.bias) {
+                for (int q = 0; q < nv; ++q) bs[q] = g.bias[j + q];
+            }
+            if (g.epi == EPI_DGRAD) {
+                if (g.accumulate) {
+                    if (vec_c) { float4 t = *reinterpret_cast<const float4*>(c); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
+                    else for (int q = 0; q < nv; ++q) old[q] = c[q];
+                }
+                if (g.mask) {
+                    const float* mp = g.mask + i * g.ldmask + j;
+                    if (full4 && m_vec) { float4 t = *reinterpret_cast<const float4*>(mp); msk[0] = t.x; msk[1] = t.y; msk[2] = t.z; msk[3] = t.w; }
+                    else for (int q = 0; q < nv; ++q) msk[q] = mp[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float x = val[q];
+                switch (g.epi) {
+                    case EPI_STORE: x = g.bias ? __fadd_rn(x, bs[q]) : x; break;
+                    case EPI_RELU: x = fmaxf(__fadd_rn(x, bs[q]), 0.f); break;
+                    case EPI_SIGMOID: x = 1.0f / (1.0f + expf(-__fadd_rn(x, bs[q]))); break;
+                    case EPI_FILM_SIN: {
+                        float a_lin = __fadd_rn(x, bs[q]);
+                        if (g.pre && q < nv) g.pre[i * g.ldpre + j + q] = a_lin;
+                        x = q >= nv ? 0.f : (g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[j + q], a_lin), g.beta[j + q]))) : sinf(__fmul_rn(30.0f, a_lin)));
+                        break;
+                    }
+                    case EPI_DGRAD: x = (x + old[q]) * (msk[q] > 0.f ? 1.0f : 0.f); break;
+                    default: break;
+                }
+                val[q] = x;
+            }
+            if (g.epi == EPI_ATOMIC) { for (int q = 0; q < nv; ++q) atomicAdd(c + q, val[q]); }
+            else if (vec_c) *reinterpret_cast<float4*>(c) = make_float4(val[0], val[1], val[2], val[3]);
+            else for (int q = 0; q < nv; ++q) c[q] = val[q];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <bool kPT, bool kQT>
+inline int launch_bgemm(GemmArgs g, cudaStream_t st, const char* what) {
+    if (g.I == 0 || g.J == 0) return 0;
+    long long gz = 1;
+    if (g.epi == EPI_ATOMIC) gz = (g.R + g.r_chunk - 1) / g.r_chunk; else g.r_chunk = g.R;
+    // 16-byte loads need every touched row start and column offset 16-byte aligned
+    bool vec = aligned16(g.P) && aligned16(g.Q) && (g.ldp % 4 == 0) && (g.ldq % 4 == 0);
+    g.vec = vec ? 1 : 0;
+    {
+        int rc = cuda_result(cudaFuncSetAttribute(bgemm_kernel<kPT, kQT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmem), "bgemm smem attribute");
+        if (rc) return rc;
+    }
+    dim3 grid((unsigned)((g.I + BBM - 1) / BBM), (unsigned)((g.J + BBN - 1) / BBN), (unsigned)gz);
+    bgemm_kernel<kPT, kQT><<<grid, 256, kBgSmem, st>>>(g);
+    return cuda_result(cudaGetLastError(), what);
+}
+
+}  // namespace bg
+}  // namespace b2r

@@ -10,6 +10,7 @@
 //                          pi_GAN/synthesis.py:107); formulas SURVEY.md A.5 / A.6
 #include "sgemm.cuh"
 #include "tgemm.cuh"
+#include "bgemm.cuh"
 
 namespace b2r {
 
@@ -251,13 +252,15 @@ __global__ void __launch_bounds__(256) film_act_bwd_kernel(float* __restrict__ d
     if (d_gamma) { atomicAdd(d_gamma + j, 30.0f * sg); atomicAdd(d_beta + j, 30.0f * sb); }
 }
 
-// GEMM engine of the current call on this host thread: 0 = fp32 CUDA cores (exact), 1 = tf32 tensor cores (tgemm.cuh).
+// GEMM engine of the current call on this host thread: 0 = fp32 CUDA cores (exact), 1 = tf32 tensor cores (tgemm.cuh),
+// 2 = bf16 tensor cores (bgemm.cuh: fp32 buffers converted while staging, MN-major operands instead of transposes).
 // thread_local, set at every API entry: the library stays re-entrant (nn.DataParallel calls it from one thread per GPU).
 static thread_local int t_gemm_mode = 0;
 
 template <bool kPT, bool kQT>
 static int launch_gemm(GemmArgs g, cudaStream_t st, const char* what) {
     // tiny reductions (K = 3 input layer) stay on the CUDA cores
+    if (t_gemm_mode == 2 && g.R >= 16) return bg::launch_bgemm<kPT, kQT>(g, st, what);
     if (t_gemm_mode == 1 && g.R >= 16) return tg::launch_tgemm<kPT, kQT>(g, st, what);
     return launch_sgemm<kPT, kQT>(g, st, what);
 }
@@ -289,7 +292,7 @@ static int wgrad_layer(const float* G, long long ldg, const float* X, long long 
                        long long rows, cudaStream_t st) {
     GemmArgs g{};
     g.P = G; g.ldp = ldg; g.Q = X; g.ldq = ldx; g.C = d_params + d.w_off; g.ldc = d.in;
-    g.I = d.out; g.J = d.in; g.R = rows; g.r_chunk = t_gemm_mode == 1 ? 8192 : 2048; g.epi = EPI_ATOMIC;
+    g.I = d.out; g.J = d.in; g.R = rows; g.r_chunk = t_gemm_mode >= 1 ? 8192 : 2048; g.epi = EPI_ATOMIC;
     int rc = launch_gemm<true, true>(g, st, "mlp_f32 wgrad gemm");
     if (rc) return rc;
     int rpc = 512;
@@ -409,7 +412,7 @@ extern "C" int b2r_mlp_f32_fwd(int model_kind, const float* params, const float*
                                const b2r_mlp_input* in, float* raw_out, void* workspace, size_t workspace_bytes,
                                int save_activations, int gemm_mode, void* stream) {
     using namespace b2r;
-    B2R_CHECK_ARG(gemm_mode == 0 || gemm_mode == 1, "b2r_mlp_f32_fwd: gemm_mode must be 0 (fp32) or 1 (tf32)");
+    B2R_CHECK_ARG(gemm_mode >= 0 && gemm_mode <= 2, "b2r_mlp_f32_fwd: gemm_mode must be 0 (fp32), 1 (tf32) or 2 (bf16)");
     t_gemm_mode = gemm_mode;
     B2R_CHECK_ARG(known_kind(model_kind), "b2r_mlp_f32_fwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(params && raw_out && workspace, "b2r_mlp_f32_fwd: NULL pointer");
@@ -448,7 +451,7 @@ extern "C" int b2r_mlp_f32_bwd(int model_kind, const float* params, const float*
                                const b2r_mlp_input* in, const float* raw, const float* d_raw, const void* saved,
                                void* scratch, size_t scratch_bytes, float* d_params, float* d_film, int gemm_mode, void* stream) {
     using namespace b2r;
-    B2R_CHECK_ARG(gemm_mode == 0 || gemm_mode == 1, "b2r_mlp_f32_bwd: gemm_mode must be 0 (fp32) or 1 (tf32)");
+    B2R_CHECK_ARG(gemm_mode >= 0 && gemm_mode <= 2, "b2r_mlp_f32_bwd: gemm_mode must be 0 (fp32), 1 (tf32) or 2 (bf16)");
     t_gemm_mode = gemm_mode;
     B2R_CHECK_ARG(known_kind(model_kind), "b2r_mlp_f32_bwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(params && raw && d_raw && saved && scratch, "b2r_mlp_f32_bwd: NULL pointer");

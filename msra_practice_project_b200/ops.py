@@ -36,7 +36,7 @@ def get_mlp_precision() -> str:
 # Arithmetic of the path used whenever gradients are required: "fp32" = layer-wise, CUDA-core FMAs (exact: the parity path),
 # "tf32" = the same algorithm with every GEMM on the tensor cores (tcgen05 kind::tf32, fp32 accumulate), "bf16" = the fused
 # tensor-core training path (mlp_tc.cu forward with kept bf16 activations + mlp_tc_train.cu reverse mode, fp32 master weights /
-# gradients; NeRF model only -- other models use "tf32" layer-wise GEMMs), "auto" (default) = "bf16" for NeRF models -- the
+# gradients; NeRF model only -- other models run the layer-wise algorithm with bf16 tensor-core GEMMs, bgemm.cuh), "auto" (default) = "bf16" for NeRF models -- the
 # same arithmetic class the no-grad render path uses by default -- and the exact "fp32" path for FiLM-SIREN / SirenNeRF.
 _GRAD_PRECISION = "auto"
 
@@ -463,7 +463,7 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
             gp = "bf16" if kind == models.KIND_NERF else "fp32"
         if gp == "bf16" and kind == models.KIND_NERF:
             return _MlpTcTrain.apply(flat, net, kind, rays, z, x)
-        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, 0 if gp == "fp32" else 1)
+        return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, {"fp32": 0, "tf32": 1, "bf16": 2}[gp])
     inp, rows, keep = _make_input(rays, z, x, grid)
     raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
     if rows == 0:
