@@ -131,33 +131,48 @@ __global__ void __launch_bounds__(256, 2) bgemm_kernel(GemmArgs g) {
             __syncwarp();
         }
     }
-    // ---- epilogue: thread = row (TMEM lane), warps 0-3 take columns [0,128), warps 4-7 columns [128,256)
+    // ---- epilogue: warps 0-3 take columns [0,128), warps 4-7 columns [128,256) of their TMEM lane quadrant.  A TMEM load gives
+    // thread = row; writing C that way touches 32 different 128-byte lines per instruction (8x the L2 requests of a coalesced
+    // store: that, not the MMAs, bounded the first version).  Each 32 x 32 block is therefore transposed through a per-warp
+    // scratch in the (now idle) stage buffers so that 8 consecutive lanes cover one 128-byte row segment of C / pre / mask.
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     const int quad = warp & 3, chalf = warp >> 2;
-    const long long i = i0 + quad * 32 + lane;
+    const uint32_t scratch = smem + (uint32_t)warp * (32u * 144u);               // 32 rows x (32 + 4) floats
+    const int sub_row = lane >> 3, cg = lane & 7;                                 // transposed domain: 4 rows x 8 column groups per pass
     const bool c_vec = (((uintptr_t)g.C & 15) == 0) && (g.ldc % 4 == 0);
     const bool m_vec = g.mask && (((uintptr_t)g.mask & 15) == 0) && (g.ldmask % 4 == 0);
+    const bool p_vec = g.pre && (((uintptr_t)g.pre & 15) == 0) && (g.ldpre % 4 == 0);
     for (int jj = 0; jj < 4; ++jj) {
         const int c0 = chalf * 128 + jj * 32;
         if (c0 >= (int)n_mma) break;
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)quad << 21) + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (i >= g.I) continue;
 #pragma unroll
-        for (int e4 = 0; e4 < 32; e4 += 4) {
-            const long long j = j0 + c0 + e4;
-            if (j >= g.J) break;
-            float val[4] = {__uint_as_float(v[e4]), __uint_as_float(v[e4 + 1]), __uint_as_float(v[e4 + 2]), __uint_as_float(v[e4 + 3])};
-            float* c = g.C + i * g.ldc + j;
-            const bool full4 = j + 3 < g.J;
-            const bool vec_c = full4 && c_vec;
-            float old[4] = {0.f, 0.f, 0.f, 0.f}, msk[4] = {1.f, 1.f, 1.f, 1.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
-            const int nv = full4 ? 4 : (int)(g.J - j);
-            if (g.epi != EPI_DGRAD && g.epi != EPI_ATOMIC && g.bias) {
-                for (int q = 0; q < nv; ++q) bs[q] = g.bias[j + q];
+        for (int q = 0; q < 8; ++q) st_shared_v4(scratch + (uint32_t)lane * 144u + (uint32_t)q * 16u, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+        const long long j = j0 + c0 + cg * 4;
+        const bool full4 = j + 3 < g.J;
+        const int nv = j >= g.J ? 0 : (full4 ? 4 : (int)(g.J - j));
+        float bs[4] = {0.f, 0.f, 0.f, 0.f}, gm[4] = {1.f, 1.f, 1.f, 1.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
+        if (g.epi != EPI_DGRAD && g.epi != EPI_ATOMIC && g.bias) for (int q = 0; q < nv; ++q) bs[q] = g.bias[j + q];
+        if (g.epi == EPI_FILM_SIN && g.gamma) for (int q = 0; q < nv; ++q) { gm[q] = g.gamma[j + q]; bt[q] = g.beta[j + q]; }
+#pragma unroll 2
+        for (int rr = 0; rr < 8; ++rr) {
+            const int row = rr * 4 + sub_row;
+            const long long i = i0 + quad * 32 + row;
+            float val[4];
+            {
+                float4 t;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                             : "r"(scratch + (uint32_t)row * 144u + (uint32_t)cg * 16u));
+                val[0] = t.x; val[1] = t.y; val[2] = t.z; val[3] = t.w;
             }
+            if (i >= g.I || nv == 0) continue;
+            float* c = g.C + i * g.ldc + j;
+            const bool vec_c = full4 && c_vec;
+            float old[4] = {0.f, 0.f, 0.f, 0.f}, msk[4] = {1.f, 1.f, 1.f, 1.f};
             if (g.epi == EPI_DGRAD) {
                 if (g.accumulate) {
                     if (vec_c) { float4 t = *reinterpret_cast<const float4*>(c); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
@@ -169,6 +184,7 @@ __global__ void __launch_bounds__(256, 2) bgemm_kernel(GemmArgs g) {
                     else for (int q = 0; q < nv; ++q) msk[q] = mp[q];
                 }
             }
+            float pre[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float x = val[q];
@@ -177,9 +193,9 @@ __global__ void __launch_bounds__(256, 2) bgemm_kernel(GemmArgs g) {
                     case EPI_RELU: x = fmaxf(__fadd_rn(x, bs[q]), 0.f); break;
                     case EPI_SIGMOID: x = 1.0f / (1.0f + expf(-__fadd_rn(x, bs[q]))); break;
                     case EPI_FILM_SIN: {
-                        float a_lin = __fadd_rn(x, bs[q]);
-                        if (g.pre && q < nv) g.pre[i * g.ldpre + j + q] = a_lin;
-                        x = q >= nv ? 0.f : (g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[j + q], a_lin), g.beta[j + q]))) : sinf(__fmul_rn(30.0f, a_lin)));
+                        const float a_lin = __fadd_rn(x, bs[q]);
+                        pre[q] = a_lin;
+                        x = g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(gm[q], a_lin), bt[q]))) : sinf(__fmul_rn(30.0f, a_lin));
                         break;
                     }
                     case EPI_DGRAD: x = (x + old[q]) * (msk[q] > 0.f ? 1.0f : 0.f); break;
@@ -187,10 +203,16 @@ __global__ void __launch_bounds__(256, 2) bgemm_kernel(GemmArgs g) {
                 }
                 val[q] = x;
             }
+            if (g.epi == EPI_FILM_SIN && g.pre) {
+                float* pp = g.pre + i * g.ldpre + j;
+                if (full4 && p_vec) *reinterpret_cast<float4*>(pp) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+                else for (int q = 0; q < nv; ++q) pp[q] = pre[q];
+            }
             if (g.epi == EPI_ATOMIC) { for (int q = 0; q < nv; ++q) atomicAdd(c + q, val[q]); }
             else if (vec_c) *reinterpret_cast<float4*>(c) = make_float4(val[0], val[1], val[2], val[3]);
             else for (int q = 0; q < nv; ++q) c[q] = val[q];
         }
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();

@@ -241,7 +241,21 @@ __global__ void __launch_bounds__(256) film_act_bwd_kernel(float* __restrict__ d
     long long r1 = min(rows, r0 + rows_per_cta);
     const float gm = gamma ? gamma[j] : 1.0f, bt = gamma ? beta[j] : 0.0f;
     float sg = 0.f, sb = 0.f;
-    for (long long row = r0; row < r1; ++row) {
+    long long row = r0;
+    for (; row + 4 <= r1; row += 4) {                       // 4 rows in flight per thread (the loop is load-latency bound)
+        float a[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = A[(row + u) * J + j]; d[u] = dH[(row + u) * ldd + j]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float t = __fmul_rn(30.0f, __fadd_rn(__fmul_rn(gm, a[u]), bt));
+            float gt = d[u] * cosf(t);
+            sg = fmaf(gt, a[u], sg);
+            sb += gt;
+            dH[(row + u) * ldd + j] = 30.0f * gm * gt;
+        }
+    }
+    for (; row < r1; ++row) {
         float a = A[row * J + j];
         float t = __fmul_rn(30.0f, __fadd_rn(__fmul_rn(gm, a), bt));
         float gt = dH[row * ldd + j] * cosf(t);
