@@ -156,61 +156,78 @@ __global__ void __launch_bounds__(256, 2) bgemm_kernel(GemmArgs g) {
         const bool full4 = j + 3 < g.J;
         const int nv = j >= g.J ? 0 : (full4 ? 4 : (int)(g.J - j));
         float bs[4] = {0.f, 0.f, 0.f, 0.f}, gm[4] = {1.f, 1.f, 1.f, 1.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
-        if (g.epi != EPI_DGRAD && g.epi != EPI_ATOMIC && g.bias) for (int q = 0; q < nv; ++q) bs[q] = g.bias[j + q];
-        if (g.epi == EPI_FILM_SIN && g.gamma) for (int q = 0; q < nv; ++q) { gm[q] = g.gamma[j + q]; bt[q] = g.beta[j + q]; }
-#pragma unroll 2
-        for (int rr = 0; rr < 8; ++rr) {
-            const int row = rr * 4 + sub_row;
-            const long long i = i0 + quad * 32 + row;
-            float val[4];
-            {
+        if (g.epi != EPI_DGRAD && g.epi != EPI_ATOMIC && g.bias) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < nv) bs[q] = g.bias[j + q];
+        }
+        if (g.epi == EPI_FILM_SIN && g.gamma) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (q < nv) { gm[q] = g.gamma[j + q]; bt[q] = g.beta[j + q]; }
+        }
+        // two batches of 4 row passes: the global reads of a batch (old C / relu mask of EPI_DGRAD) are all issued before any
+        // of them is used -- the epilogue is otherwise a chain of dependent ~1 us loads
+#pragma unroll
+        for (int rb = 0; rb < 8; rb += 4) {
+            float4 old4[4], msk4[4];
+            if (g.epi == EPI_DGRAD) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long i = i0 + quad * 32 + (rb + u) * 4 + sub_row;
+                    old4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    msk4[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (i < g.I && nv > 0) {
+                        const float* c = g.C + i * g.ldc + j;
+                        if (g.accumulate) {
+                            if (full4 && c_vec) old4[u] = *reinterpret_cast<const float4*>(c);
+                            else { old4[u].x = c[0]; if (nv > 1) old4[u].y = c[1]; if (nv > 2) old4[u].z = c[2]; if (nv > 3) old4[u].w = c[3]; }
+                        }
+                        if (g.mask) {
+                            const float* mp = g.mask + i * g.ldmask + j;
+                            if (full4 && m_vec) msk4[u] = *reinterpret_cast<const float4*>(mp);
+                            else { msk4[u].x = mp[0]; if (nv > 1) msk4[u].y = mp[1]; if (nv > 2) msk4[u].z = mp[2]; if (nv > 3) msk4[u].w = mp[3]; }
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = (rb + u) * 4 + sub_row;
+                const long long i = i0 + quad * 32 + row;
                 float4 t;
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
                              : "r"(scratch + (uint32_t)row * 144u + (uint32_t)cg * 16u));
-                val[0] = t.x; val[1] = t.y; val[2] = t.z; val[3] = t.w;
-            }
-            if (i >= g.I || nv == 0) continue;
-            float* c = g.C + i * g.ldc + j;
-            const bool vec_c = full4 && c_vec;
-            float old[4] = {0.f, 0.f, 0.f, 0.f}, msk[4] = {1.f, 1.f, 1.f, 1.f};
-            if (g.epi == EPI_DGRAD) {
-                if (g.accumulate) {
-                    if (vec_c) { float4 t = *reinterpret_cast<const float4*>(c); old[0] = t.x; old[1] = t.y; old[2] = t.z; old[3] = t.w; }
-                    else for (int q = 0; q < nv; ++q) old[q] = c[q];
-                }
-                if (g.mask) {
-                    const float* mp = g.mask + i * g.ldmask + j;
-                    if (full4 && m_vec) { float4 t = *reinterpret_cast<const float4*>(mp); msk[0] = t.x; msk[1] = t.y; msk[2] = t.z; msk[3] = t.w; }
-                    else for (int q = 0; q < nv; ++q) msk[q] = mp[q];
-                }
-            }
-            float pre[4] = {0.f, 0.f, 0.f, 0.f};
+                if (i >= g.I || nv == 0) continue;
+                float* c = g.C + i * g.ldc + j;
+                const bool vec_c = full4 && c_vec;
+                float val[4] = {t.x, t.y, t.z, t.w}, pre[4] = {0.f, 0.f, 0.f, 0.f};
+                const float old[4] = {old4[u].x, old4[u].y, old4[u].z, old4[u].w}, msk[4] = {msk4[u].x, msk4[u].y, msk4[u].z, msk4[u].w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float x = val[q];
-                switch (g.epi) {
-                    case EPI_STORE: x = g.bias ? __fadd_rn(x, bs[q]) : x; break;
-                    case EPI_RELU: x = fmaxf(__fadd_rn(x, bs[q]), 0.f); break;
-                    case EPI_SIGMOID: x = 1.0f / (1.0f + expf(-__fadd_rn(x, bs[q]))); break;
-                    case EPI_FILM_SIN: {
-                        const float a_lin = __fadd_rn(x, bs[q]);
-                        pre[q] = a_lin;
-                        x = g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(gm[q], a_lin), bt[q]))) : sinf(__fmul_rn(30.0f, a_lin));
-                        break;
+                for (int q = 0; q < 4; ++q) {
+                    float x = val[q];
+                    switch (g.epi) {
+                        case EPI_STORE: x = g.bias ? __fadd_rn(x, bs[q]) : x; break;
+                        case EPI_RELU: x = fmaxf(__fadd_rn(x, bs[q]), 0.f); break;
+                        case EPI_SIGMOID: x = 1.0f / (1.0f + expf(-__fadd_rn(x, bs[q]))); break;
+                        case EPI_FILM_SIN: {
+                            const float a_lin = __fadd_rn(x, bs[q]);
+                            pre[q] = a_lin;
+                            x = g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(gm[q], a_lin), bt[q]))) : sinf(__fmul_rn(30.0f, a_lin));
+                            break;
+                        }
+                        case EPI_DGRAD: x = (x + old[q]) * (msk[q] > 0.f ? 1.0f : 0.f); break;
+                        default: break;
                     }
-                    case EPI_DGRAD: x = (x + old[q]) * (msk[q] > 0.f ? 1.0f : 0.f); break;
-                    default: break;
+                    val[q] = x;
                 }
-                val[q] = x;
+                if (g.epi == EPI_FILM_SIN && g.pre) {
+                    float* pp = g.pre + i * g.ldpre + j;
+                    if (full4 && p_vec) *reinterpret_cast<float4*>(pp) = make_float4(pre[0], pre[1], pre[2], pre[3]);
+                    else { pp[0] = pre[0]; if (nv > 1) pp[1] = pre[1]; if (nv > 2) pp[2] = pre[2]; if (nv > 3) pp[3] = pre[3]; }
+                }
+                if (g.epi == EPI_ATOMIC) { atomicAdd(c, val[0]); if (nv > 1) atomicAdd(c + 1, val[1]); if (nv > 2) atomicAdd(c + 2, val[2]); if (nv > 3) atomicAdd(c + 3, val[3]); }
+                else if (vec_c) *reinterpret_cast<float4*>(c) = make_float4(val[0], val[1], val[2], val[3]);
+                else { c[0] = val[0]; if (nv > 1) c[1] = val[1]; if (nv > 2) c[2] = val[2]; if (nv > 3) c[3] = val[3]; }
             }
-            if (g.epi == EPI_FILM_SIN && g.pre) {
-                float* pp = g.pre + i * g.ldpre + j;
-                if (full4 && p_vec) *reinterpret_cast<float4*>(pp) = make_float4(pre[0], pre[1], pre[2], pre[3]);
-                else for (int q = 0; q < nv; ++q) pp[q] = pre[q];
-            }
-            if (g.epi == EPI_ATOMIC) { for (int q = 0; q < nv; ++q) atomicAdd(c + q, val[q]); }
-            else if (vec_c) *reinterpret_cast<float4*>(c) = make_float4(val[0], val[1], val[2], val[3]);
-            else for (int q = 0; q < nv; ++q) c[q] = val[q];
         }
         __syncwarp();
     }
