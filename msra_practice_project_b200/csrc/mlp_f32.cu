@@ -266,6 +266,29 @@ __global__ void __launch_bounds__(256) film_act_bwd_kernel(float* __restrict__ d
     if (d_gamma) { atomicAdd(d_gamma + j, 30.0f * sg); atomicAdd(d_beta + j, 30.0f * sb); }
 }
 
+// First layer of the SIREN networks (K = 3 inputs): y = sin(30 (gamma (W x + b) + beta)), pre = W x + b.  No GEMM: one thread per
+// (row, 4 output columns), exact fp32 with the same individually rounded operations as the sgemm epilogue; coalesced float4 stores.
+__global__ void __launch_bounds__(256) siren_first_layer_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ W,
+                                                                const float* __restrict__ b, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, long long rows, float* __restrict__ Y,
+                                                                long long ldy, float* __restrict__ pre) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long row = t >> 6;                     // 64 column groups of 4 = 256 outputs
+    const int n0 = (int)(t & 63) * 4;
+    if (row >= rows) return;
+    const float x0 = X[row * ldx], x1 = X[row * ldx + 1], x2 = X[row * ldx + 2];
+    float y[4], a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float* w = W + (n0 + q) * 3;
+        float acc = fmaf(x2, w[2], fmaf(x1, w[1], x0 * w[0]));          // same k order as the sgemm inner loop
+        a[q] = __fadd_rn(acc, b[n0 + q]);
+        y[q] = gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(gamma[n0 + q], a[q]), beta[n0 + q]))) : sinf(__fmul_rn(30.0f, a[q]));
+    }
+    *reinterpret_cast<float4*>(Y + row * ldy + n0) = make_float4(y[0], y[1], y[2], y[3]);
+    if (pre) *reinterpret_cast<float4*>(pre + row * 256 + n0) = make_float4(a[0], a[1], a[2], a[3]);
+}
+
 // GEMM engine of the current call on this host thread: 0 = fp32 CUDA cores (exact), 1 = tf32 tensor cores (tgemm.cuh),
 // 2 = bf16 tensor cores (bgemm.cuh: fp32 buffers converted while staging, MN-major operands instead of transposes).
 // thread_local, set at every API entry: the library stays re-entrant (nn.DataParallel calls it from one thread per GPU).
@@ -286,6 +309,12 @@ static inline Lin lin(const float* params, LayerDesc d) { return Lin{params + d.
 static int fwd_layer(const float* X, long long ldx, Lin L, int k_off, int K, float* Y, long long ldy, long long rows,
                      int epi, cudaStream_t st, const float* gamma = nullptr, const float* beta = nullptr,
                      float* pre = nullptr) {
+    if (t_gemm_mode != 0 && K == 3 && L.in == 3 && L.out == 256 && epi == EPI_FILM_SIN && ldy % 4 == 0 && aligned16(Y) && (!pre || aligned16(pre))) {
+        // tensor-core modes: the K = 3 first layer is no GEMM (the exact fp32 mode keeps the sgemm path its parity fixtures were made with)
+        const long long threads = rows * 64;
+        siren_first_layer_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, ldx, L.W, L.b, gamma, beta, rows, Y, ldy, pre);
+        return cuda_result(cudaGetLastError(), "siren first layer");
+    }
     GemmArgs g{};
     g.P = X; g.ldp = ldx; g.Q = L.W + k_off; g.ldq = L.in; g.C = Y; g.ldc = ldy;
     g.I = rows; g.J = L.out; g.R = K; g.r_chunk = K; g.epi = epi; g.bias = L.b;
