@@ -36,8 +36,8 @@ def get_mlp_precision() -> str:
 # Arithmetic of the path used whenever gradients are required: "fp32" = layer-wise, CUDA-core FMAs (exact: the parity path),
 # "tf32" = the same algorithm with every GEMM on the tensor cores (tcgen05 kind::tf32, fp32 accumulate), "bf16" = the fused
 # tensor-core training path (mlp_tc.cu forward with kept bf16 activations + mlp_tc_train.cu reverse mode, fp32 master weights /
-# gradients; NeRF model only -- other models run the layer-wise algorithm with bf16 tensor-core GEMMs, bgemm.cuh), "auto" (default) = "bf16" for NeRF models -- the
-# same arithmetic class the no-grad render path uses by default -- and the exact "fp32" path for FiLM-SIREN / SirenNeRF.
+# gradients; NeRF model only -- other models run the layer-wise algorithm with bf16 tensor-core GEMMs, bgemm.cuh), "auto" (default) = "bf16":
+# the same arithmetic class the no-grad render path uses by default.  "fp32" is the exact path the gradient parity fixtures are checked on.
 _GRAD_PRECISION = "auto"
 
 
@@ -460,7 +460,7 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
             raise RuntimeError("grid queries are inference-only")
         gp = _GRAD_PRECISION
         if gp == "auto":
-            gp = "bf16" if kind == models.KIND_NERF else "fp32"
+            gp = "bf16"
         if gp == "bf16" and kind == models.KIND_NERF:
             return _MlpTcTrain.apply(flat, net, kind, rays, z, x)
         return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, {"fp32": 0, "tf32": 1, "bf16": 2}[gp])

@@ -26,6 +26,14 @@ def seeded_nerf():
     return models.NeRF().cuda(), models.NeRF().cuda()
 
 
+@pytest.fixture
+def exact_grads():
+    """gradient fixtures hold the reference's fp32 autograd results: check them on the exact (fp32 CUDA-core) reverse mode"""
+    old = ops.set_grad_precision("fp32")
+    yield
+    ops.set_grad_precision(old)
+
+
 def seeded_film(use_dir=True):
     torch.manual_seed(0)
     return models.FilmSirenNeRF(use_dir=use_dir).cuda()
@@ -398,7 +406,7 @@ def test_nerf_train_step_gradients(golden):
     _grad_check(f, "fine", tr, rel=2e-2)     # fine samples move with the coarse weights (ill-conditioned bins)
 
 
-def test_pigan_render_image_and_film_gradients(golden):
+def test_pigan_render_image_and_film_gradients(golden, exact_grads):
     """pi_GAN render_image -> image, d/d film_params and d/d weights (pi_GAN/train.py:134, synthesis.py:107)."""
     p = golden.pigan
     m = seeded_film()
@@ -797,7 +805,7 @@ def test_fused_train_step_matches_autograd_path(golden, graph):
     assert not torch.equal(img_after, img), "render after another training step used stale packed weights"
 
 
-def test_siren_nerf_forward_and_training_gradients(golden):
+def test_siren_nerf_forward_and_training_gradients(golden, exact_grads):
     """SirenNeRF (nerf/nerf.py:97-170; `use_siren`, nerf/train_nerf.py:89-91) through the layer-wise fp32 path: network(x)
     against the reference's forward, then render_rays + MSE loss + backward against the reference's autograd gradients of
     all 24 tensors of both models (fixture tests/golden/siren.npz)."""
