@@ -467,8 +467,7 @@ def run_secondary(args, config=None, embedded=False):
                     config=dict(workload="SirenNeRF 800x800 render, 64+128 samples, rays sharded by pixel rows, fused tcgen05 SIREN kernel"),
                     tflops=rows * 1123840 / (ms * 1e-3) / 1e12)
     elif config == "siren_train":
-        # train_nerf.py with use_siren (nerf/train_nerf.py:89-91,151-168): SirenNeRF has no fused reverse mode yet; its gradients run
-        # through the layer-wise path (autograd wrappers + torch Adam), GEMMs in bf16 on tcgen05
+        # train_nerf.py with use_siren (nerf/train_nerf.py:89-91,151-168): the fused training step on two SirenNeRF models
         n_batch, sc, sf = 4096, args.coarse, args.fine
         b, c = shard.shard_range(n_batch, rank, world)
         torch.manual_seed(0)
@@ -482,23 +481,17 @@ def run_secondary(args, config=None, embedded=False):
         torch.manual_seed(5)
         t_rand = torch.rand((n_batch, sc), device=dev)[b:b + c].contiguous()
 
+        from msra_practice_project_b200.train_step import NerfTrainStep
+        trainer = NerfTrainStep(coarse, fine, 2.0, 6.0, sc, sf, c, learning_rate=5e-4, learning_rate_decay=500, graph=not args.no_graph)
+
         def step():
-            old = ops.set_grad_precision("bf16")
-            try:
-                opt.zero_grad(set_to_none=True)
-                rc, _, _, rf, _, _ = nerf_render.render_rays(rays, 2.0, 6.0, coarse, fine, sc, sf, t_rand=t_rand)
-                loss = ((rf - target) ** 2).sum() / (n_batch * 3) + ((rc - target) ** 2).sum() / (n_batch * 3)
-                loss.backward()
-                shard.allreduce_gradients([coarse, fine], average=False)
-                opt.step()
-            finally:
-                ops.set_grad_precision(old)
-        ms = timed(step, min(args.steps, 3), args.warmup)
+            trainer(rays, target, t_rand=t_rand)
+        ms = timed(step, args.steps, args.warmup)
         rows = n_batch * (2 * sc + sf)
         line = dict(metric="rays/s, SirenNeRF training step (4096-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
                     unit="rays/s", ms_per_step=ms, dtype="bf16", scaling="strong",
-                    config=dict(workload="SirenNeRF train step, 4096 rays sharded over ranks, layer-wise forward with saved fp32 activations + CUDA "
-                                         "reverse mode, GEMMs in bf16 on tcgen05 (bgemm.cuh), torch Adam"),
+                    config=dict(workload="SirenNeRF train step, 4096 rays sharded over ranks, fused tcgen05 forward with bf16 activation + cosine "
+                                         "checkpoints, fused dgrad / MN-major wgrad reverse mode, fused Adam, CUDA-graph replay"),
                     tflops=rows * 1123840 * 3 / (ms * 1e-3) / 1e12)
     elif config == "pigan_grad":
         # pi-GAN gradient step through the renderer (pi_GAN/train.py:128-134 generator update without the discriminator; the

@@ -633,6 +633,8 @@ namespace tc {
 size_t siren_packed_bytes();
 int siren_pack(const float* params, void* packed_out, cudaStream_t st);
 int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, cudaStream_t st);
+size_t siren_saved_bytes(long long rows);
+int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, void* saved, cudaStream_t st);
 }  // namespace tc
 }  // namespace b2r
 
@@ -750,6 +752,7 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
 }
 
 extern "C" size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows) {
+    if (model_kind == B2R_MODEL_SIREN && rows >= 0) return b2r::tc::siren_saved_bytes(rows);
     if (model_kind != B2R_MODEL_NERF || rows < 0) return 0;
     return (size_t)b2r::tc::n_sub_tiles(rows) * b2r::tc::saved_bytes_per_sub();
 }
@@ -757,7 +760,8 @@ extern "C" size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows) {
 extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,
                                     size_t saved_bytes, void* stream) {
     using namespace b2r;
-    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF, "b2r_mlp_tc_train_fwd: only the NeRF model has a tensor-core training path (kind %d)", model_kind);
+    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_SIREN,
+                  "b2r_mlp_tc_train_fwd: only the NeRF and SirenNeRF models have a fused tensor-core training path (kind %d)", model_kind);
     B2R_CHECK_ARG(packed && raw_out && saved, "b2r_mlp_tc_train_fwd: NULL pointer");
     B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out | (uintptr_t)saved) & 15) == 0, "b2r_mlp_tc_train_fwd: buffers must be 16-byte aligned");
     int rc = check_mlp_input(in);
@@ -765,6 +769,7 @@ extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2
     long long rows = row_count(in);
     B2R_CHECK_ARG(saved_bytes >= b2r_mlp_tc_train_saved_bytes(model_kind, rows), "b2r_mlp_tc_train_fwd: saved buffer too small (%zu B)", saved_bytes);
     if (rows == 0) return 0;
+    if (model_kind == B2R_MODEL_SIREN) return tc::siren_train_fwd(packed, in, rows, raw_out, saved, (cudaStream_t)stream);
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;

@@ -80,11 +80,12 @@ __global__ void siren_pack_kernel(const float* __restrict__ params, uint8_t* __r
 
 // One SirenNeRF step's epilogue for this warp's quarter of the columns (64, or 32 of the 128 of the last layer).
 //   MODE 0: sin(acc) -> bf16 h;   MODE 1: same + partial sigma head;   MODE 2: acc -> bf16 h (linear layers_dir.0);
-//   MODE 3: N = 128 (32 columns per quarter): sin(acc) -> partial rgb head, no store
-// head: shared-memory address of this quarter's fp32 head weights.
-template <int MODE>
+//   MODE 3: N = 128 (32 columns per quarter): sin(acc) -> partial rgb head (kSave: also bf16 h_d into shared memory at h_blk)
+// head: shared-memory address of this quarter's fp32 head weights.  kSave (training forward): cos(acc) of the sine layers is
+// stored as bf16x2 words, two uint4 per 16-column unit, thread-major at cosp + w * 2048 (tc_core.cuh: siren_cos_off).
+template <int MODE, bool kSave>
 __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t h_blk, const uint32_t (&xoff)[8], float& sigma, float& rgb0,
-                                          float& rgb1, float& rgb2) {
+                                          float& rgb1, float& rgb2, uint8_t* __restrict__ cosp) {
     constexpr int NU = MODE == 3 ? 2 : 4;                       // units of 16 columns
     uint32_t va[16], vb[16];
     tmem_ld16(t_q, va);
@@ -96,6 +97,13 @@ __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t 
         float f[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) f[e] = MODE == 2 ? __uint_as_float(v[e]) : __sinf(__uint_as_float(v[e]));
+        if (kSave && MODE != 2) {
+            uint32_t cw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cw[e] = pack_bf16(__cosf(__uint_as_float(v[2 * e])), __cosf(__uint_as_float(v[2 * e + 1])));
+            stg128(cosp + (size_t)(2 * u) * 2048, cw[0], cw[1], cw[2], cw[3]);
+            stg128(cosp + (size_t)(2 * u + 1) * 2048, cw[4], cw[5], cw[6], cw[7]);
+        }
         if (MODE == 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -112,7 +120,8 @@ __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t 
                 rgb1 = fmaf(f[4 * q + 0], w1.x, fmaf(f[4 * q + 1], w1.y, fmaf(f[4 * q + 2], w1.z, fmaf(f[4 * q + 3], w1.w, rgb1))));
                 rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
             }
-        } else {
+        }
+        if (MODE != 3 || kSave) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
                 st_shared_v4(h_blk + xoff[u * 2 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
@@ -123,8 +132,12 @@ __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t 
 
 // Like film_tc_kernel, the 16 epilogue warps are shared by the two sub-tiles: a warp owns one 64-column quarter (= one
 // K-block of the next layer) of BOTH and alternates between them.
+// kSave = training forward: the layer inputs (aux, h0..h7, layers_dir.0 output, h_d) leave shared memory as tiled bf16 tensors
+// through the bulk-copy engine (warps 2 / 3: one spill thread per sub-tile, as in nerf_tc_kernel<true>) and cos(t) of every
+// sine layer is stored thread-major for the reverse mode (mlp_tc_train.cu).
+template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out) {
+siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,14 +150,39 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tab + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
         }
     }
-    const uint32_t tmem_base = tc_prologue(cx, warp, 32);
+    if (kSave) {   // the aux blocks are copied out whole: their never-written chunks must not hold stale bits
+        for (int i = threadIdx.x; i < 2 * (int)(kPeBytes / 16); i += kThreads) {
+            const uint32_t g = (uint32_t)i / (kPeBytes / 16), o = (uint32_t)i % (kPeBytes / 16);
+            st_shared_v4(cx.smem + g * kSubBytes + o * 16u, 0u, 0u, 0u, 0u);
+        }
+    }
+    const uint32_t tmem_base = tc_prologue(cx, warp, 32, 16);
 
     if (warp == 0) {
         if (lane == 0) producer_loop<SirenSched>(cx, packed, pl, SirenSched::kSteps, 0);
     } else if (warp == 1) {
         if (cx.rank == 0) mma_loop<SirenSched>(cx, tmem_base, pl, SirenSched::kSteps, 0);
         else if (lane == 0) relay_loop<SirenSched>(cx, pl, SirenSched::kSteps, 0);
-    } else if (warp >= kCtrlWarps) {
+    } else if (warp < kCtrlWarps) {
+        if (kSave && lane == 0) {
+            // ===== spill thread of sub-tile g =====
+            const int g = warp - 2;
+            const uint32_t aux = cx.smem + (uint32_t)g * kSubBytes, hreg = aux + kPeBytes;
+            const uint32_t ready = cx.spill_ready + 8 * g, done = cx.spill_done + 8 * g;
+            const size_t n_sub = (size_t)pl.n_pairs * 4;
+            uint32_t ph = 0;
+            for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+                const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+                auto tile = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
+                auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
+                mbar_wait(ready, ph); bulk_s2g(tile(kSsAUX, 1), aux, kBlk); bulk_s2g(tile(ss_h(0), 4), hreg, 4 * kBlk); finish();    // aux, h0
+                for (int l = 1; l < 8; ++l) { mbar_wait(ready, ph); bulk_s2g(tile(ss_h(l), 4), hreg, 4 * kBlk); finish(); }             // h1 .. h7
+                mbar_wait(ready, ph); bulk_s2g(tile(kSsGL, 4), hreg, 4 * kBlk); finish();                                                // layers_dir.0 output
+                mbar_wait(ready, ph); bulk_s2g(tile(kSsHD, 2), hreg, 2 * kBlk); finish();                                                // h_d
+            }
+            bulk_wait_all();
+        }
+    } else {
         const int ew = warp - kCtrlWarps;
         const int cq = ew >> 2, quad = ew & 3;
         const int r = (quad << 5) | lane;
@@ -154,7 +192,15 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
         uint32_t xoff[8];
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
-        uint32_t acc_phase[2] = {0u, 0u};
+        uint32_t xoff_hd[8];                                      // h_d: this quarter's 32 columns = chunks (cq & 1) * 4 .. + 3 of a K-block
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) xoff_hd[c] = ((((uint32_t)(cq & 1) * 4u + (c & 3u)) ^ xr) << 4);
+        uint32_t acc_phase[2] = {0u, 0u}, sp_phase[2] = {0u, 0u};
+        bool first_tile = true;
+        const size_t n_sub = (size_t)pl.n_pairs * 4;
+        // kSave: tile written (and fenced by arrive_act) -> spill thread; wait until the previous copy has read shared memory
+        auto spill_sig = [&](int g) { if (kSave && lane == 0) mbar_arrive(cx.spill_ready + 8 * g); };
+        auto spill_wait = [&](int g) { if (kSave) { mbar_wait(cx.spill_done + 8 * g, sp_phase[g]); sp_phase[g] ^= 1u; } };
         auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSubBytes; };
         auto t_row = [&](int g) -> uint32_t { return tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u; };
         auto h_blk = [&](int g) -> uint32_t { return sub_base(g) + kPeBytes + (uint32_t)cq * 16384u + row_off; };
@@ -173,10 +219,12 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                 valid[g] = row[g] < rows;
                 float pnt[3], vdir[3];
                 load_row(src, valid[g] ? row[g] : rows - 1, pnt, vdir);
+                if (!first_tile) spill_wait(g);                      // previous tile's h_d copy
+                const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 // ---- layers_pos.0 on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    uint32_t pk[16];
+                    uint32_t pk[16], ck[16];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
@@ -186,11 +234,16 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                         float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
                         float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
                         float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
-                        pk[2 * q + 0] = pack_bf16(__sinf(fmaf(a0, 30.0f, sh.x)), __sinf(fmaf(a1, 30.0f, sh.y)));
-                        pk[2 * q + 1] = pack_bf16(__sinf(fmaf(a2, 30.0f, sh.z)), __sinf(fmaf(a3, 30.0f, sh.w)));
+                        const float t0 = fmaf(a0, 30.0f, sh.x), t1 = fmaf(a1, 30.0f, sh.y), t2 = fmaf(a2, 30.0f, sh.z), t3 = fmaf(a3, 30.0f, sh.w);
+                        pk[2 * q + 0] = pack_bf16(__sinf(t0), __sinf(t1));
+                        pk[2 * q + 1] = pack_bf16(__sinf(t2), __sinf(t3));
+                        if (kSave) { ck[2 * q + 0] = pack_bf16(__cosf(t0), __cosf(t1)); ck[2 * q + 1] = pack_bf16(__cosf(t2), __cosf(t3)); }
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q) {
+                        st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        if (kSave) stg128(saved + siren_cos_off(n_sub, 0, T, cq, jj * 4 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
+                    }
                 }
                 if (cq == 0) {
                     // aux block = [pos(3), 1, 1, dir(3), 0 ...] (16 K): raw inputs of the two skip layers + the constant ones of the shifts
@@ -199,33 +252,54 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                     st_shared_v4(sub_base(g) + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
                 }
                 arrive(g);
+                spill_sig(g);
             }
+            first_tile = false;
+            auto cosp = [&](int layer, int g) -> uint8_t* {
+                return kSave ? saved + siren_cos_off(n_sub, layer, (size_t)((2 * p + cx.rank) * 2 + g), cq, 0, r) : nullptr;
+            };
 
             float sigma[2] = {0.f, 0.f}, rgb0[2] = {0.f, 0.f}, rgb1[2] = {0.f, 0.f}, rgb2[2] = {0.f, 0.f};
             for (int s = 0; s < 6; ++s) {                               // layers_pos.1 .. layers_pos.6
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     wait_acc(g);
-                    siren_epi<0>(t_row(g) + (uint32_t)cq * 64u, 0u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                    spill_wait(g);
+                    siren_epi<0, kSave>(t_row(g) + (uint32_t)cq * 64u, 0u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g], cosp(s + 1, g));
                     arrive(g);
+                    spill_sig(g);
                 }
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {                               // layers_pos.7 (+ sigma head)
                 wait_acc(g);
-                siren_epi<1>(t_row(g) + (uint32_t)cq * 64u, tab + (uint32_t)(kSWS + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                spill_wait(g);
+                siren_epi<1, kSave>(t_row(g) + (uint32_t)cq * 64u, tab + (uint32_t)(kSWS + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g],
+                                    cosp(7, g));
                 arrive(g);
+                spill_sig(g);
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {                               // layers_dir.0 (linear)
                 wait_acc(g);
-                siren_epi<2>(t_row(g) + (uint32_t)cq * 64u, 0u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                spill_wait(g);
+                siren_epi<2, kSave>(t_row(g) + (uint32_t)cq * 64u, 0u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g], nullptr);
                 arrive(g);
+                spill_sig(g);
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {                               // layers_dir.1 (N = 128: 32 columns per quarter) + rgb head
                 wait_acc(g);
-                siren_epi<3>(t_row(g) + (uint32_t)cq * 32u, tab + (uint32_t)(kSWR + cq * 32) * 4u, 0u, xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                spill_wait(g);
+                // kSave: bf16 h_d goes to K-block cq / 2 of the (now free) h region, chunks (cq & 1) * 4 ..; its cosine to the 4-word layout
+                siren_epi<3, kSave>(t_row(g) + (uint32_t)cq * 32u, tab + (uint32_t)(kSWR + cq * 32) * 4u,
+                                    sub_base(g) + kPeBytes + (uint32_t)(cq >> 1) * 16384u + row_off + (uint32_t)0, xoff_hd, sigma[g], rgb0[g], rgb1[g], rgb2[g],
+                                    kSave ? saved + siren_cos9_off(n_sub, (size_t)((2 * p + cx.rank) * 2 + g), cq, 0, r) : nullptr);
+                if (kSave) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    spill_sig(g);
+                }
             }
             tc_fence_before();
             // head partials of the four column quarters -> the aux blocks' upper halves (free once the last MMA is done)
@@ -271,10 +345,23 @@ int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float
     unsigned grid = 0;
     int rc = pair_grid(rows, &grid);
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes), "tc smem attribute");
+    rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes), "tc smem attribute");
     if (rc) return rc;
-    siren_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out);
+    siren_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd (SirenNeRF)");
+    return 0;
+}
+
+size_t siren_saved_bytes(long long rows) { return (size_t)n_sub_tiles(rows) * siren_saved_bytes_per_sub(); }
+
+int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, void* saved, cudaStream_t st) {
+    unsigned grid = 0;
+    int rc = pair_grid(rows, &grid);
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes), "tc smem attribute");
+    if (rc) return rc;
+    siren_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, (uint8_t*)saved);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd (SirenNeRF)");
     return 0;
 }
 

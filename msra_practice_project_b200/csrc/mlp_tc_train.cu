@@ -40,19 +40,23 @@ static_assert(kBwdChunkBytes == 34LL * 32768, "bwd packed chunk bytes");
 constexpr int kBwdTabWSigma = 0, kBwdTabWRgb = 256, kBwdTabFloats = 640;              // w_sigma[256] | w_rgb[3][128]
 constexpr long long kBwdPackedBytes = kBwdChunkBytes + kBwdTabFloats * 4;
 
-// B operand of dgrad step s: B[n][k] = W_L[k][n + col_off]  (n = input feature = output column of dX, k = output feature)
+// B operand of dgrad step s: B[n][k] = scale_L * W_L[k][n + col_off]  (n = input feature = output column of dX, k = output feature).
+// kSiren: the SirenNeRF layer table, skip offset 3 (raw position first, nerf/nerf.py:158) and the factor 30 of the sine layers
+// folded into the rows exactly as in the forward's packed weights (t = 30 (W x + b)  =>  dt/dx = 30 W).
+template <bool kSiren>
 __global__ void nerf_pack_bwd_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t < kBwdChunkBytes / 16) {
         int s, c, hf, row, grp;
         locate<BwdSched>(t * 16, s, c, hf, row, grp);
-        LayerDesc L = nerf_layer(bwd_layer(s));
-        const int n = hf * 128 + row + (s == 4 ? 60 : 0);
+        LayerDesc L = kSiren ? siren_layer(bwd_layer(s)) : nerf_layer(bwd_layer(s));
+        const int n = hf * 128 + row + (s == 4 ? (kSiren ? 3 : 60) : 0);
+        const float scale = (kSiren && s != 1) ? 30.0f : 1.0f;                // step 1 = layers_dir.0 (linear)
         __nv_bfloat16 v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             int k = c * 64 + grp * 8 + e;
-            v[e] = __float2bfloat16_rn(k < L.out ? params[L.w_off + (long long)k * L.in + n] : 0.f);
+            v[e] = __float2bfloat16_rn(k < L.out ? scale * params[L.w_off + (long long)k * L.in + n] : 0.f);
         }
         uint8_t* dst = packed + step_base<BwdSched>(s) + (long long)(c * 2 + hf) * half_bytes<BwdSched>(s) +
                        sw128_offset((uint32_t)row, (uint32_t)grp);
@@ -61,19 +65,38 @@ __global__ void nerf_pack_bwd_kernel(const float* __restrict__ params, uint8_t* 
     if (t < kBwdTabFloats) {
         float* tab = reinterpret_cast<float*>(packed + kBwdChunkBytes);
         int i = (int)t;
-        tab[i] = i < kBwdTabWRgb ? params[nerf_layer(10).w_off + i] : params[nerf_layer(11).w_off + (i - kBwdTabWRgb)];
+        const LayerDesc Ls = kSiren ? siren_layer(10) : nerf_layer(10), Lc = kSiren ? siren_layer(11) : nerf_layer(11);
+        tab[i] = i < kBwdTabWRgb ? params[Ls.w_off + i] : params[Lc.w_off + (i - kBwdTabWRgb)];
     }
 }
 
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 x, y;
+    *reinterpret_cast<uint32_t*>(&x) = a;
+    *reinterpret_cast<uint32_t*>(&y) = b;
+    x = __hmul2(x, y);
+    return *reinterpret_cast<uint32_t*>(&x);
+}
+
 // One dgrad step's epilogue for this warp's half (128) of the columns.
-//   MODE 0: linear (d g: layers_dir.0 has no activation);  MODE 1: + gs * w_sigma (sigma-head term), relu'(h7);  MODE 2: relu'(h)
-// The result (bf16) is written in place as the next step's A operand; the spill thread copies the same tile to global
-// memory for wgrad.  mask_ptr: this thread's 16-byte relu-bit word of the layer (prefetched while the MMAs finish).
-template <int MODE>
-__device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const uint32_t (&xoff)[8], const uint8_t* __restrict__ mask_ptr,
+//   MODE 0: linear (d g: layers_dir.0 has no activation);  MODE 1: + gs * w_sigma (sigma-head term), act'(h7);  MODE 2: act'(h)
+// act' = relu' from the layer's relu bits (NeRF: one prefetched 16-byte word per thread) or, kSiren, cos(t) from the forward's
+// thread-major bf16x2 checkpoint (four 16-byte words per 32-column group, the next group's in flight).
+// The result (bf16) is written in place as the next step's A operand; the spill thread copies the same tile to global memory
+// for wgrad.  dptr: NeRF: this thread's relu-bit word of the layer; SirenNeRF: its first cosine word (quarter 2 * half, w = 0).
+template <int MODE, bool kSiren>
+__device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const uint32_t (&xoff)[8], const uint8_t* __restrict__ dptr,
                                         float gs, uint32_t wsig_half, uint32_t acc_bar, uint32_t& acc_phase, uint32_t done_bar, uint32_t& sp_phase) {
     uint4 mk4 = make_uint4(0u, 0u, 0u, 0u);
-    if (MODE != 0) mk4 = ldg128(mask_ptr);
+    uint4 cw[4];
+    // cosine words of 32-column group jj: quarter (jj >> 1) of this half, words (jj & 1) * 4 .. + 3; 2048 B between words, 8 words per quarter
+    auto cos_ptr = [&](int jj, int q) -> const uint8_t* { return dptr + (size_t)((jj >> 1) * 8 + (jj & 1) * 4 + q) * 2048; };
+    if (MODE != 0) {
+        if (kSiren) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cw[q] = ldg128(cos_ptr(0, q));
+        } else mk4 = ldg128(dptr);
+    }
     mbar_wait_cluster(acc_bar, acc_phase);
     acc_phase ^= 1u;
     tc_fence_after();
@@ -84,6 +107,11 @@ __device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const 
     for (int jj = 0; jj < 4; ++jj) {
         uint32_t v[32];
         tmem_ld32(t_half + (uint32_t)jj * 32u, v);
+        uint4 cn[4];
+        if (kSiren && MODE != 0 && jj < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cn[q] = ldg128(cos_ptr(jj + 1, q));
+        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -101,10 +129,18 @@ __device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const 
             uint32_t w0 = pack_bf16(f[8 * q + 0], f[8 * q + 1]), w1 = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
             uint32_t w2 = pack_bf16(f[8 * q + 4], f[8 * q + 5]), w3 = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
             if (MODE != 0) {
-                w0 &= mask_get(mk[jj], 4 * q + 0); w1 &= mask_get(mk[jj], 4 * q + 1);
-                w2 &= mask_get(mk[jj], 4 * q + 2); w3 &= mask_get(mk[jj], 4 * q + 3);
+                if (kSiren) {
+                    w0 = mul_bf16x2(w0, cw[q].x); w1 = mul_bf16x2(w1, cw[q].y); w2 = mul_bf16x2(w2, cw[q].z); w3 = mul_bf16x2(w3, cw[q].w);
+                } else {
+                    w0 &= mask_get(mk[jj], 4 * q + 0); w1 &= mask_get(mk[jj], 4 * q + 1);
+                    w2 &= mask_get(mk[jj], 4 * q + 2); w3 &= mask_get(mk[jj], 4 * q + 3);
+                }
             }
             st_shared_v4(h_half + (uint32_t)(jj >> 1) * kBlk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
+        }
+        if (kSiren && MODE != 0 && jj < 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cw[q] = cn[q];
         }
     }
 }
@@ -112,6 +148,7 @@ __device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const 
 // =====================================================================================================================
 // dgrad: d_raw -> d(pre-activation) of every layer (tiled bf16 tensors in `scratch`) + head gradients HG
 // =====================================================================================================================
+template <bool kSiren>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const float4* __restrict__ raw, const float4* __restrict__ d_raw,
                    const uint8_t* __restrict__ saved, uint8_t* __restrict__ scratch) {
@@ -190,13 +227,17 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
             }
             if (half == 0) hg_out[T * kRowsSub + r] = make_float4(gc0, gc1, gc2, gs);
             {
-                // d h_d = (d rgb pre) . W_rgb, relu'(h_d): this half produces columns half*64 .. +63 = K-block `half` of step 0
-                const uint2 hm = *reinterpret_cast<const uint2*>(saved + hdmask_off(n_sub, T, half, r));
+                // d h_d = (d rgb pre) . W_rgb, act'(h_d): this half produces columns half*64 .. +63 = K-block `half` of step 0
+                uint2 hm = make_uint2(0u, 0u);
+                if (!kSiren) hm = *reinterpret_cast<const uint2*>(saved + hdmask_off(n_sub, T, half, r));
                 const uint32_t wr = tab + (uint32_t)(kBwdTabWRgb + half * 64) * 4u;
                 if (!first_tile) { mbar_wait(done_bar, sp_phase); sp_phase ^= 1u; }          // previous tile's d h0 copy
                 first_tile = false;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
+                    // SirenNeRF: cos(t) of layers_dir.1, quarter half * 2 + (q >> 2) (32 columns each), word q & 3
+                    uint4 cwq = make_uint4(0u, 0u, 0u, 0u);
+                    if (kSiren) cwq = ldg128(saved + siren_cos9_off(n_sub, T, half * 2 + (q >> 2), q & 3, r));
                     float f[8];
 #pragma unroll
                     for (int hq = 0; hq < 2; ++hq) {
@@ -207,32 +248,39 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                         f[4 * hq + 2] = fmaf(gc2, w2.z, fmaf(gc1, w1.z, gc0 * w0.z));
                         f[4 * hq + 3] = fmaf(gc2, w2.w, fmaf(gc1, w1.w, gc0 * w0.w));
                     }
-                    const uint32_t bits = (q >> 2) ? hm.y : hm.x;
-                    const int i0 = 4 * (q & 3);
-                    const uint32_t w0 = pack_bf16(f[0], f[1]) & mask_get(bits, i0 + 0), w1 = pack_bf16(f[2], f[3]) & mask_get(bits, i0 + 1);
-                    const uint32_t w2 = pack_bf16(f[4], f[5]) & mask_get(bits, i0 + 2), w3 = pack_bf16(f[6], f[7]) & mask_get(bits, i0 + 3);
+                    uint32_t w0 = pack_bf16(f[0], f[1]), w1 = pack_bf16(f[2], f[3]), w2 = pack_bf16(f[4], f[5]), w3 = pack_bf16(f[6], f[7]);
+                    if (kSiren) {
+                        w0 = mul_bf16x2(w0, cwq.x); w1 = mul_bf16x2(w1, cwq.y); w2 = mul_bf16x2(w2, cwq.z); w3 = mul_bf16x2(w3, cwq.w);
+                    } else {
+                        const uint32_t bits = (q >> 2) ? hm.y : hm.x;
+                        const int i0 = 4 * (q & 3);
+                        w0 &= mask_get(bits, i0 + 0); w1 &= mask_get(bits, i0 + 1); w2 &= mask_get(bits, i0 + 2); w3 &= mask_get(bits, i0 + 3);
+                    }
                     st_shared_v4(h_base + (uint32_t)half * kBlk + row_off + xoff[q], w0, w1, w2, w3);
                 }
             }
             arrive_act(act_local, act_leader, cx.rank, lane);
             spill_sig();
-            auto mptr = [&](int l) -> const uint8_t* { return saved + mask_off(n_sub, l, T, half, r); };
+            // activation-derivative checkpoint of layer l for this thread: relu bits (NeRF) / first cosine word of quarter 2 * half (SirenNeRF)
+            auto mptr = [&](int l) -> const uint8_t* {
+                return kSiren ? saved + siren_cos_off(n_sub, l, T, half * 2, 0, r) : saved + mask_off(n_sub, l, T, half, r);
+            };
             // step 0: d g (linear)
-            bwd_epi<0>(t_half, h_half, xoff, nullptr, 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
+            bwd_epi<0, kSiren>(t_half, h_half, xoff, nullptr, 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
             arrive_act(act_local, act_leader, cx.rank, lane);
             spill_sig();
-            // step 1: d h7 (+ sigma head), relu'(h7)
-            bwd_epi<1>(t_half, h_half, xoff, mptr(7), gs, wsig_half, acc_bar, acc_phase, done_bar, sp_phase);
+            // step 1: d h7 (+ sigma head), act'(h7)
+            bwd_epi<1, kSiren>(t_half, h_half, xoff, mptr(7), gs, wsig_half, acc_bar, acc_phase, done_bar, sp_phase);
             arrive_act(act_local, act_leader, cx.rank, lane);
             spill_sig();
             // steps 2..7: d h6 .. d h1
             for (int s = 2; s < 8; ++s) {
-                bwd_epi<2>(t_half, h_half, xoff, mptr(8 - s), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
+                bwd_epi<2, kSiren>(t_half, h_half, xoff, mptr(8 - s), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
                 arrive_act(act_local, act_leader, cx.rank, lane);
                 spill_sig();
             }
             // step 8: d h0 -> dPre0: only wgrad reads it (layers_pos.0 has no dgrad), no MMA follows
-            bwd_epi<2>(t_half, h_half, xoff, mptr(0), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
+            bwd_epi<2, kSiren>(t_half, h_half, xoff, mptr(0), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
             fence_proxy_async_smem();
             tc_fence_before();
             __syncwarp();
@@ -249,25 +297,42 @@ struct WUnit {
     int g_off, g_nb;        // gradient tensor in scratch: block offset, blocks per tile (4 = two 128-row output halves, 2 = one)
     int x_off, x_nb;        // layer-input tensor in saved: block offset, blocks per tile
     int layer;              // nerf_layer index (w_off, in, b_off)
-    int col_off, n_valid;   // columns [col_off, col_off + n_valid) of dW come from this X tensor
+    int col_off, n_valid;   // columns [col_off, col_off + n_valid) of dW come from this X tensor ...
     int bias;               // this unit also reduces the bias gradient
+    int x_col0;             // ... from its columns [x_col0, x_col0 + n_valid)
+    float scale;            // dW = scale * G^T X (30 for SirenNeRF's sine layers, whose G is the gradient wrt t = 30 (W x + b))
 };
 constexpr int kWUnits = 12;
 __constant__ WUnit c_wunits[kWUnits] = {
-    {scr_gh(0), 4, kSavPE, 1, 0, 0, 60, 1},
-    {scr_gh(1), 4, sav_h(0), 4, 1, 0, 256, 1},
-    {scr_gh(2), 4, sav_h(1), 4, 2, 0, 256, 1},
-    {scr_gh(3), 4, sav_h(2), 4, 3, 0, 256, 1},
-    {scr_gh(4), 4, sav_h(3), 4, 4, 0, 256, 1},
-    {scr_gh(5), 4, kSavPE, 1, 5, 0, 60, 0},
-    {scr_gh(5), 4, sav_h(4), 4, 5, 60, 256, 1},
-    {scr_gh(6), 4, sav_h(5), 4, 6, 0, 256, 1},
-    {scr_gh(7), 4, sav_h(6), 4, 7, 0, 256, 1},
-    {kScrGG, 4, sav_h(7), 4, 8, 0, 256, 1},
-    {kScrGD1, 2, kSavGL, 4, 9, 0, 256, 1},
-    {kScrGD1, 2, kSavDE, 1, 9, 256, 24, 0},
+    {scr_gh(0), 4, kSavPE, 1, 0, 0, 60, 1, 0, 1.0f},
+    {scr_gh(1), 4, sav_h(0), 4, 1, 0, 256, 1, 0, 1.0f},
+    {scr_gh(2), 4, sav_h(1), 4, 2, 0, 256, 1, 0, 1.0f},
+    {scr_gh(3), 4, sav_h(2), 4, 3, 0, 256, 1, 0, 1.0f},
+    {scr_gh(4), 4, sav_h(3), 4, 4, 0, 256, 1, 0, 1.0f},
+    {scr_gh(5), 4, kSavPE, 1, 5, 0, 60, 0, 0, 1.0f},
+    {scr_gh(5), 4, sav_h(4), 4, 5, 60, 256, 1, 0, 1.0f},
+    {scr_gh(6), 4, sav_h(5), 4, 6, 0, 256, 1, 0, 1.0f},
+    {scr_gh(7), 4, sav_h(6), 4, 7, 0, 256, 1, 0, 1.0f},
+    {kScrGG, 4, sav_h(7), 4, 8, 0, 256, 1, 0, 1.0f},
+    {kScrGD1, 2, kSavGL, 4, 9, 0, 256, 1, 0, 1.0f},
+    {kScrGD1, 2, kSavDE, 1, 9, 256, 24, 0, 0, 1.0f},
 };
-constexpr int kWCostTotal = 5 + 4 * 8 + 5 + 8 + 2 * 8 + 8 + 6 + 3;      // half-block loads per 64-row stage, all units: 83
+// SirenNeRF: the aux tile [pos(3), 1, 1, dir(3)] feeds layers_pos.0, the skip layer and layers_dir.1
+__constant__ WUnit c_wunits_siren[kWUnits] = {
+    {scr_gh(0), 4, kSsAUX, 1, 0, 0, 3, 1, 0, 30.0f},
+    {scr_gh(1), 4, ss_h(0), 4, 1, 0, 256, 1, 0, 30.0f},
+    {scr_gh(2), 4, ss_h(1), 4, 2, 0, 256, 1, 0, 30.0f},
+    {scr_gh(3), 4, ss_h(2), 4, 3, 0, 256, 1, 0, 30.0f},
+    {scr_gh(4), 4, ss_h(3), 4, 4, 0, 256, 1, 0, 30.0f},
+    {scr_gh(5), 4, kSsAUX, 1, 5, 0, 3, 0, 0, 30.0f},
+    {scr_gh(5), 4, ss_h(4), 4, 5, 3, 256, 1, 0, 30.0f},
+    {scr_gh(6), 4, ss_h(5), 4, 6, 0, 256, 1, 0, 30.0f},
+    {scr_gh(7), 4, ss_h(6), 4, 7, 0, 256, 1, 0, 30.0f},
+    {kScrGG, 4, ss_h(7), 4, 8, 0, 256, 1, 0, 1.0f},
+    {kScrGD1, 2, kSsGL, 4, 9, 0, 256, 1, 0, 30.0f},
+    {kScrGD1, 2, kSsAUX, 1, 9, 256, 3, 0, 5, 30.0f},
+};
+constexpr int kWCostTotal = 5 + 4 * 8 + 5 + 8 + 2 * 8 + 8 + 6 + 3;      // half-block loads per 64-row stage, all units: 83 (both models)
 
 constexpr int kWStages = 3;
 constexpr uint32_t kWSlot = 65536;                                       // up to 8 half blocks of 8 KB
@@ -278,8 +343,12 @@ constexpr int kWThreads = 192;                                           // prod
 struct WPiece { int u; long long t0, t1; };
 // CTA b owns the slice [b, b+1) * total / grid of the cost line (units laid end to end, each n_sub tiles x cost(u)); both
 // ends are rounded to tiles with the same function, so neighbouring CTAs agree on the boundary.
+template <bool kSiren>
+__device__ __forceinline__ WUnit wunit(int u) { return kSiren ? c_wunits_siren[u] : c_wunits[u]; }
+
+template <bool kSiren>
 __device__ __forceinline__ bool wpiece(int u, long long n_sub, long long lo, long long hi, long long& base, WPiece& pc) {
-    const WUnit un = c_wunits[u];
+    const WUnit un = wunit<kSiren>(u);
     const long long cost = un.g_nb + un.x_nb;
     const long long b0 = base, b1 = base + n_sub * cost;
     base = b1;
@@ -291,6 +360,7 @@ __device__ __forceinline__ bool wpiece(int u, long long n_sub, long long lo, lon
     return pc.t0 < pc.t1;
 }
 
+template <bool kSiren>
 __global__ void __launch_bounds__(kWThreads, 1)
 nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub, float* __restrict__ d_params) {
     extern __shared__ uint8_t smem_raw[];
@@ -320,8 +390,8 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
             long long base = 0;
             for (int u = 0; u < kWUnits; ++u) {
                 WPiece pc;
-                if (!wpiece(u, n_sub, lo, hi, base, pc)) continue;
-                const WUnit un = c_wunits[u];
+                if (!wpiece<kSiren>(u, n_sub, lo, hi, base, pc)) continue;
+                const WUnit un = wunit<kSiren>(u);
                 const uint8_t* gsrc = scratch + (size_t)un.g_off * n_sub * kBlk;
                 const uint8_t* xsrc = saved + (size_t)un.x_off * n_sub * kBlk;
                 const uint32_t bytes = (uint32_t)(un.g_nb + un.x_nb) * 8192u;
@@ -348,8 +418,8 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
         const uint64_t d_hi = make_desc(0, 8192, 1024, kLayoutSW128);
         for (int u = 0; u < kWUnits; ++u) {
             WPiece pc;
-            if (!wpiece(u, n_sub, lo, hi, base, pc)) continue;
-            const WUnit un = c_wunits[u];
+            if (!wpiece<kSiren>(u, n_sub, lo, hi, base, pc)) continue;
+            const WUnit un = wunit<kSiren>(u);
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)un.x_nb * 64u) | (1u << 15) | (1u << 16);
             const int n_m = un.g_nb >> 1;
             if (!first_piece) { mbar_wait(tmem_empty, te_phase); te_phase ^= 1u; tc_fence_after(); }
@@ -384,9 +454,9 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
         long long base = 0;
         for (int u = 0; u < kWUnits; ++u) {
             WPiece pc;
-            if (!wpiece(u, n_sub, lo, hi, base, pc)) continue;
-            const WUnit un = c_wunits[u];
-            const LayerDesc L = nerf_layer(un.layer);
+            if (!wpiece<kSiren>(u, n_sub, lo, hi, base, pc)) continue;
+            const WUnit un = wunit<kSiren>(u);
+            const LayerDesc L = kSiren ? siren_layer(un.layer) : nerf_layer(un.layer);
             const bool do_bias = un.bias && w < un.g_nb;
             float s0 = 0.f, s1 = 0.f;
             for (long long st = 0; st < 2 * (pc.t1 - pc.t0); ++st) {
@@ -419,14 +489,14 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
-                        const int col = j * 32 + e;
-                        if (col < un.n_valid) atomicAdd(dW + o * L.in + un.col_off + col, __uint_as_float(v[e]));
+                        const int col = j * 32 + e - un.x_col0;
+                        if (col >= 0 && col < un.n_valid) atomicAdd(dW + o * L.in + un.col_off + col, un.scale * __uint_as_float(v[e]));
                     }
                 }
             }
             if (do_bias) {
-                atomicAdd(d_params + L.b_off + w * 64 + 2 * lane, s0);
-                atomicAdd(d_params + L.b_off + w * 64 + 2 * lane + 1, s1);
+                atomicAdd(d_params + L.b_off + w * 64 + 2 * lane, un.scale * s0);
+                atomicAdd(d_params + L.b_off + w * 64 + 2 * lane + 1, un.scale * s1);
             }
             tc_fence_before();
             __syncwarp();
@@ -448,8 +518,9 @@ __device__ __forceinline__ void fma8(float (&acc)[8], float g, const uint4& x) {
     acc[4] = fmaf(g, __uint_as_float(x.z << 16), acc[4]); acc[5] = fmaf(g, __uint_as_float(x.z & 0xFFFF0000u), acc[5]);
     acc[6] = fmaf(g, __uint_as_float(x.w << 16), acc[6]); acc[7] = fmaf(g, __uint_as_float(x.w & 0xFFFF0000u), acc[7]);
 }
+// h7_off / hd_off: block offsets of the two input tensors in `saved`; Ls / Lc: the heads' slots in the flat parameter vector
 __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub,
-                                                              float* __restrict__ d_params) {
+                                                              float* __restrict__ d_params, int h7_off, int hd_off, LayerDesc Ls, LayerDesc Lc) {
     __shared__ float red_s[4][256 + 1];          // sigma: per-warp partial weight gradients (+ bias sum)
     __shared__ float red_c[8][384 + 3];          // rgb: per half-warp partials (+ 3 bias sums)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -457,7 +528,7 @@ __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __r
     const uint32_t c = (uint32_t)lane & 7u;                 // logical chunk of the row this thread owns (columns blk*64 + c*8 ..)
     if (warp < 4) {
         const int blk = lane >> 3;
-        const uint8_t* __restrict__ xt = saved + (size_t)sav_h(7) * n_sub * kBlk + (size_t)blk * kBlk;
+        const uint8_t* __restrict__ xt = saved + (size_t)h7_off * n_sub * kBlk + (size_t)blk * kBlk;
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
         for (long long T = blockIdx.x; T < n_sub; T += gridDim.x) {
             const uint8_t* tile = xt + (size_t)T * 4 * kBlk;
@@ -480,7 +551,7 @@ __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __r
         if (lane == 0) red_s[warp][256] = bsum;
     } else {
         const int blk = (lane >> 3) & 1, sub = lane >> 4;   // half warp `sub` takes every other row
-        const uint8_t* __restrict__ xt = saved + (size_t)kSavHD * n_sub * kBlk + (size_t)blk * kBlk;
+        const uint8_t* __restrict__ xt = saved + (size_t)hd_off * n_sub * kBlk + (size_t)blk * kBlk;
         float a0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
               a2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, b0 = 0.f, b1 = 0.f, b2 = 0.f;
         for (long long T = blockIdx.x; T < n_sub; T += gridDim.x) {
@@ -514,12 +585,12 @@ __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __r
     // one atomic per output and CTA
     const int t = threadIdx.x;
     {
-        const LayerDesc L = nerf_layer(10);
+        const LayerDesc L = Ls;
         atomicAdd(d_params + L.w_off + t, red_s[0][t] + red_s[1][t] + red_s[2][t] + red_s[3][t]);
         if (t == 0) atomicAdd(d_params + L.b_off, red_s[0][256] + red_s[1][256] + red_s[2][256] + red_s[3][256]);
     }
     {
-        const LayerDesc L = nerf_layer(11);
+        const LayerDesc L = Lc;
         for (int i = t; i < 387; i += 256) {
             float sum = 0.f;
 #pragma unroll
@@ -534,44 +605,42 @@ int pair_grid(long long rows, unsigned* grid);   // mlp_tc.cu
 }  // namespace tc
 }  // namespace b2r
 
+static inline bool train_kind(int k) { return k == B2R_MODEL_NERF || k == B2R_MODEL_SIREN; }
+
 extern "C" size_t b2r_mlp_tc_bwd_packed_bytes(int model_kind) {
-    return model_kind == B2R_MODEL_NERF ? (size_t)b2r::tc::kBwdPackedBytes : 0;
+    return train_kind(model_kind) ? (size_t)b2r::tc::kBwdPackedBytes : 0;
 }
 
 extern "C" int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* packed_out, void* stream) {
     using namespace b2r;
-    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF, "b2r_mlp_tc_pack_bwd: only the NeRF model has a tensor-core training path (kind %d)", model_kind);
+    B2R_CHECK_ARG(train_kind(model_kind), "b2r_mlp_tc_pack_bwd: only the NeRF and SirenNeRF models have a fused tensor-core training path (kind %d)", model_kind);
     B2R_CHECK_ARG(params && packed_out, "b2r_mlp_tc_pack_bwd: NULL pointer");
     B2R_CHECK_ARG(((uintptr_t)packed_out & 15) == 0, "b2r_mlp_tc_pack_bwd: packed_out must be 16-byte aligned");
     long long threads = tc::kBwdChunkBytes / 16;
-    tc::nerf_pack_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, (uint8_t*)packed_out);
+    if (model_kind == B2R_MODEL_SIREN)
+        tc::nerf_pack_bwd_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, (uint8_t*)packed_out);
+    else
+        tc::nerf_pack_bwd_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, (uint8_t*)packed_out);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_pack_bwd");
     return 0;
 }
 
 extern "C" size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows) {
-    if (model_kind != B2R_MODEL_NERF || rows < 0) return 0;
+    if (!train_kind(model_kind) || rows < 0) return 0;
     return (size_t)b2r::tc::n_sub_tiles(rows) * ((size_t)b2r::tc::kScrBlocks * b2r::tc::kBlk + b2r::tc::kRowsSub * 16);
 }
 
-extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows, const float* raw, const float* d_raw,
-                                    const void* saved, void* scratch, size_t scratch_bytes, float* d_params, void* stream) {
+template <bool kSiren>
+static int train_bwd_launch(const void* packed_bwd, long long rows, const float* raw, const float* d_raw, const void* saved, void* scratch,
+                            float* d_params, cudaStream_t st) {
     using namespace b2r;
-    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF, "b2r_mlp_tc_train_bwd: only the NeRF model has a tensor-core training path (kind %d)", model_kind);
-    B2R_CHECK_ARG(packed_bwd && raw && d_raw && saved && scratch && d_params, "b2r_mlp_tc_train_bwd: NULL pointer");
-    B2R_CHECK_ARG((((uintptr_t)packed_bwd | (uintptr_t)raw | (uintptr_t)d_raw | (uintptr_t)saved | (uintptr_t)scratch | (uintptr_t)d_params) & 15) == 0,
-                  "b2r_mlp_tc_train_bwd: buffers must be 16-byte aligned");
-    B2R_CHECK_ARG(rows >= 0, "b2r_mlp_tc_train_bwd: negative row count");
-    B2R_CHECK_ARG(scratch_bytes >= b2r_mlp_tc_train_scratch_bytes(model_kind, rows), "b2r_mlp_tc_train_bwd: scratch too small (%zu B)", scratch_bytes);
-    if (rows == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     unsigned grid = 0;
     int rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc bwd smem attribute");
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_bwd_kernel<kSiren>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc bwd smem attribute");
     if (rc) return rc;
-    tc::nerf_tc_bwd_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed_bwd, rows, (const float4*)raw, (const float4*)d_raw,
-                                                                      (const uint8_t*)saved, (uint8_t*)scratch);
+    tc::nerf_tc_bwd_kernel<kSiren><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed_bwd, rows, (const float4*)raw, (const float4*)d_raw,
+                                                                              (const uint8_t*)saved, (uint8_t*)scratch);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (dgrad)");
     const long long n_sub = tc::n_sub_tiles(rows);
     int dev = 0, sms = 0;
@@ -579,14 +648,30 @@ extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long
     if (rc) return rc;
     rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel<kSiren>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
     if (rc) return rc;
     const long long work = n_sub * tc::kWUnits;
     unsigned wgrid = (unsigned)(work < sms ? work : sms);
-    tc::nerf_tc_wgrad_kernel<<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
+    tc::nerf_tc_wgrad_kernel<kSiren><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (wgrad)");
     unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
-    tc::nerf_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
+    tc::nerf_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params,
+                                                      kSiren ? tc::ss_h(7) : tc::sav_h(7), kSiren ? tc::kSsHD : tc::kSavHD,
+                                                      kSiren ? siren_layer(10) : nerf_layer(10), kSiren ? siren_layer(11) : nerf_layer(11));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (heads)");
     return 0;
+}
+
+extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows, const float* raw, const float* d_raw,
+                                    const void* saved, void* scratch, size_t scratch_bytes, float* d_params, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(train_kind(model_kind), "b2r_mlp_tc_train_bwd: only the NeRF and SirenNeRF models have a fused tensor-core training path (kind %d)", model_kind);
+    B2R_CHECK_ARG(packed_bwd && raw && d_raw && saved && scratch && d_params, "b2r_mlp_tc_train_bwd: NULL pointer");
+    B2R_CHECK_ARG((((uintptr_t)packed_bwd | (uintptr_t)raw | (uintptr_t)d_raw | (uintptr_t)saved | (uintptr_t)scratch | (uintptr_t)d_params) & 15) == 0,
+                  "b2r_mlp_tc_train_bwd: buffers must be 16-byte aligned");
+    B2R_CHECK_ARG(rows >= 0, "b2r_mlp_tc_train_bwd: negative row count");
+    B2R_CHECK_ARG(scratch_bytes >= b2r_mlp_tc_train_scratch_bytes(model_kind, rows), "b2r_mlp_tc_train_bwd: scratch too small (%zu B)", scratch_bytes);
+    if (rows == 0) return 0;
+    if (model_kind == B2R_MODEL_SIREN) return train_bwd_launch<true>(packed_bwd, rows, raw, d_raw, saved, scratch, d_params, (cudaStream_t)stream);
+    return train_bwd_launch<false>(packed_bwd, rows, raw, d_raw, saved, scratch, d_params, (cudaStream_t)stream);
 }

@@ -126,6 +126,20 @@ __device__ __forceinline__ uint32_t relu_mask2(uint32_t h2) {
 __device__ __forceinline__ void mask_put(uint32_t& bits, uint32_t w, int i) { bits |= relu_mask2(w) & (0x00010001u << i); }
 __device__ __forceinline__ uint32_t mask_get(uint32_t bits, int i) { return ((bits >> i) & 0x00010001u) * 0xFFFFu; }
 
+// SirenNeRF training checkpoints: tiles AUX [pos(3), 1, 1, dir(3)] | H0..H7 | GL | HD, then cos(t) of the nine sine layers as
+// bf16x2 words stored THREAD-MAJOR -- [layer 0..7][T][quarter cq][word w 0..7][row r] uint4 (the 64 columns of a quarter = 32
+// words = 8 uint4 per thread), then the same for layers_dir.1 with 4 uint4 per quarter (32 columns): lanes of a warp touch
+// consecutive 16-byte words, so the forward's stores and the reverse mode's loads are fully coalesced.
+constexpr int kSsAUX = 0, kSsH0 = 1, kSsGL = 33, kSsHD = 37, kSsBlocks = 39;
+__host__ __device__ constexpr int ss_h(int l) { return kSsH0 + 4 * l; }
+__host__ __device__ constexpr size_t siren_saved_bytes_per_sub() { return (size_t)kSsBlocks * kBlk + 8 * 65536 + 32768; }
+__device__ __forceinline__ size_t siren_cos_off(size_t n_sub, int layer, size_t T, int cq, int w, int r) {
+    return (size_t)kSsBlocks * n_sub * kBlk + ((((size_t)layer * n_sub + T) * 4 + cq) * 8 + w) * 2048 + (size_t)r * 16;
+}
+__device__ __forceinline__ size_t siren_cos9_off(size_t n_sub, size_t T, int cq, int w, int r) {
+    return (size_t)kSsBlocks * n_sub * kBlk + (size_t)8 * n_sub * 65536 + (((T * 4 + cq) * 4 + w) * 2048) + (size_t)r * 16;
+}
+
 __device__ __forceinline__ void stg128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -295,12 +309,12 @@ __device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, cons
 
 // common prologue: barriers, TMEM allocation (both CTAs), cluster rendezvous; returns the TMEM base address
 // act_count: arrivals per act_ready phase (epilogue warps per sub-tile x 2 CTAs)
-__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp, uint32_t act_count = 16) {
+__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp, uint32_t act_count = 16, uint32_t spill_count = 8) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
         for (int g = 0; g < 2; ++g) {
             mbar_init(cx.act_ready + 8 * g, act_count); mbar_init(cx.acc_full + 8 * g, 1);
-            mbar_init(cx.spill_ready + 8 * g, 8); mbar_init(cx.spill_done + 8 * g, 1);
+            mbar_init(cx.spill_ready + 8 * g, spill_count); mbar_init(cx.spill_done + 8 * g, 1);
         }
         fence_barrier_init();
     }

@@ -394,7 +394,7 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
 
 class _MlpTcTrain(torch.autograd.Function):
     """Fused bf16 tensor-core forward that keeps the layer inputs as tiled bf16 tensors, and its reverse mode
-    (dgrad + wgrad + heads, mlp_tc_train.cu).  NeRF model only."""
+    (dgrad + wgrad + heads, mlp_tc_train.cu).  NeRF and SirenNeRF models."""
 
     @staticmethod
     def forward(ctx, flat, model, kind, rays, z, x):
@@ -461,7 +461,7 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
         gp = _GRAD_PRECISION
         if gp == "auto":
             gp = "bf16"
-        if gp == "bf16" and kind == models.KIND_NERF:
+        if gp == "bf16" and kind in (models.KIND_NERF, models.KIND_SIREN):
             return _MlpTcTrain.apply(flat, net, kind, rays, z, x)
         return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, {"fp32": 0, "tf32": 1, "bf16": 2}[gp])
     inp, rows, keep = _make_input(rays, z, x, grid)

@@ -22,7 +22,8 @@ from . import models, ops
 
 
 class NerfTrainStep:
-    """Fused training step for two NeRF models (coarse + fine), bf16 tensor-core MLP arithmetic, fp32 master weights.
+    """Fused training step for two NeRF (or two SirenNeRF) models (coarse + fine), bf16 tensor-core MLP arithmetic, fp32
+    master weights.
 
     Arguments mirror the names train_nerf.py reads from its config: ``learning_rate``, ``learning_rate_decay`` (in
     thousands of steps, train_nerf.py:171), ``use_alpha``, the render settings and the batch size.  ``batch_size`` is the
@@ -31,8 +32,10 @@ class NerfTrainStep:
     def __init__(self, coarse_model, fine_model, near, far, coarse_sample_num, fine_sample_num, batch_size, *,
                  learning_rate=5e-4, learning_rate_decay=0, use_alpha=False, betas=(0.9, 0.999), eps=1e-8, graph=True,
                  group=None):
-        if models.model_kind(coarse_model) != models.KIND_NERF or models.model_kind(fine_model) != models.KIND_NERF:
-            raise TypeError("NerfTrainStep needs two NeRF models (nerf/nerf.py:52-94)")
+        kind = models.model_kind(coarse_model)
+        if kind not in (models.KIND_NERF, models.KIND_SIREN) or models.model_kind(fine_model) != kind:
+            raise TypeError("NerfTrainStep needs two NeRF or two SirenNeRF models (nerf/nerf.py:52-94, 120-170; train_nerf.py:89-95)")
+        self.kind = kind
         self.models = (coarse_model, fine_model)
         self.dev = next(coarse_model.parameters()).device
         if self.dev.type != "cuda":
@@ -44,13 +47,13 @@ class NerfTrainStep:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.use_graph = bool(graph)
-        n = models.NERF_NUMEL
+        n = models.NERF_NUMEL if kind == models.KIND_NERF else models.SIREN_NUMEL
         self.n = n
         # flat fp32 master weights of both models; the nn.Parameters become views of it
         self.params = torch.empty((2 * n,), dtype=torch.float32, device=self.dev)
         for i, m in enumerate(self.models):
             off = i * n
-            for p in models.param_list(m, models.KIND_NERF):
+            for p in models.param_list(m, kind):
                 k = p.numel()
                 self.params[off:off + k].copy_(p.detach().reshape(-1))
                 p.data = self.params[off:off + k].view(p.shape)
@@ -74,7 +77,7 @@ class NerfTrainStep:
 
     # ---- the step, as plain launches on the current stream -------------------------------------------------------
     def _forward_backward(self):
-        n, kind = self.n, models.KIND_NERF
+        n, kind = self.n, self.kind
         rays, rays_d = self.in_rays, self.in_rays[:, 1]
         bg = float(self.batch * self.world)
         if self._draw_t:
