@@ -149,7 +149,13 @@ int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_ml
  * b2r_mlp_tc_train_bwd: d_raw[rows,4] -> d_params (flat fp32, ACCUMULATED into: caller zeroes).  packed_bwd: transposed
  * weights from b2r_mlp_tc_pack_bwd (b2r_mlp_tc_bwd_packed_bytes bytes); raw = the forward's output; scratch:
  * b2r_mlp_tc_train_scratch_bytes(kind, rows) bytes (per-layer d(pre-activation) tiles for the weight-gradient GEMMs).
- * Only B2R_MODEL_NERF has this path; other kinds return <0 (callers use the fp32 / tf32 layer-wise path). */
+ * B2R_MODEL_NERF and B2R_MODEL_SIREN (nerf/nerf.py:97-170) use these entry points as they are.  B2R_MODEL_FILM
+ * (FilmSirenNeRF, use_dir = 1; autograd through pi_GAN/modules.py:101-118 as used by pi_GAN/train.py:134 and
+ * synthesis.py:107): b2r_mlp_tc_train_fwd takes ONE latent's packed image (b2r_mlp_tc_pack with that latent's film);
+ * the reverse mode is b2r_mlp_tc_pack_bwd_film + b2r_mlp_tc_train_bwd_film, which also returns d film[9,512]
+ * (d gamma | d beta per layer).  d_folded: B2R_FILM_NUMEL floats of workspace (zeroed by the call: gradients of the
+ * FiLM-folded weights W' = 30 gamma W, s' = 30 (gamma b + beta)); d_params / d_film are ACCUMULATED into and either may
+ * be NULL (synthesis.py only needs d film). */
 size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows);
 int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,
                          size_t saved_bytes, void* stream);
@@ -158,6 +164,10 @@ int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* packed_out, v
 size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows);
 int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows, const float* raw, const float* d_raw,
                          const void* saved, void* scratch, size_t scratch_bytes, float* d_params, void* stream);
+int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, void* packed_out, void* stream);
+int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, long long rows, const float* raw,
+                              const float* d_raw, const void* saved, void* scratch, size_t scratch_bytes, float* d_folded,
+                              float* d_params, float* d_film, void* stream);
 
 /* ---- fused Adam on a flat fp32 bucket ----------- optimizer.step() + LR decay, nerf/train_nerf.py:168-175 ----------
  * torch.optim.Adam semantics (no weight decay / amsgrad) on n contiguous floats; grads are multiplied by grad_scale first

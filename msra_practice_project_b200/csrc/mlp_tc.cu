@@ -412,9 +412,11 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
 //   MODE 2: -> partial rgb head, no store (hidden_layer_rgb, modules.py:114-116)
 // t_q: TMEM address of the quarter; head: shared-memory address of the quarter's fp32 head weights; h_blk: this thread's row in
 // the destination K-block.  No table loads in MODE 0: per element FMUL (1/2pi) + MUFU.SIN + half a bf16x2 pack.
-template <int MODE>
+// kSave (training forward): cos(acc) is stored as bf16x2 words, two uint4 per 16-column unit, thread-major at
+// cosp + w * 2048 (tc_core.cuh: film_cos_off), and MODE 2 also writes its bf16 output into shared memory (h_blk) for the spill.
+template <int MODE, bool kSave>
 __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h_blk, const uint32_t (&xoff)[8], float& sigma, float& rgb0,
-                                         float& rgb1, float& rgb2) {
+                                         float& rgb1, float& rgb2, uint8_t* __restrict__ cosp) {
     // 4 units of 16 columns, the TMEM load of unit u+1 in flight while unit u is evaluated
     uint32_t va[16], vb[16];
     tmem_ld16(t_q, va);
@@ -426,6 +428,13 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h
         float f[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) f[e] = __sinf(__uint_as_float(v[e]));
+        if (kSave) {
+            uint32_t cw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cw[e] = pack_bf16(__cosf(__uint_as_float(v[2 * e])), __cosf(__uint_as_float(v[2 * e + 1])));
+            stg128(cosp + (size_t)(2 * u) * 2048, cw[0], cw[1], cw[2], cw[3]);
+            stg128(cosp + (size_t)(2 * u + 1) * 2048, cw[4], cw[5], cw[6], cw[7]);
+        }
         if (MODE == 1) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -442,7 +451,8 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h
                 rgb1 = fmaf(f[4 * q + 0], w1.x, fmaf(f[4 * q + 1], w1.y, fmaf(f[4 * q + 2], w1.z, fmaf(f[4 * q + 3], w1.w, rgb1))));
                 rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
             }
-        } else {
+        }
+        if (MODE != 2 || kSave) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
                 st_shared_v4(h_blk + xoff[u * 2 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
@@ -469,9 +479,11 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h
 // after the other (b2r_mlp_tc_pack_film_batched); rows [b * rows_per_latent, (b+1) * rows_per_latent) belong to latent b
 // (rows_per_latent is a multiple of the 256-row tile); the producer streams the tile's latent's weights and the epilogue
 // warps reload the small fp32 tables when their next tile is another latent's.
+// kSave = training forward (one latent): tiles + cosine checkpoints for the reverse mode, as in siren_tc_kernel<true>.
+template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int sigma_only, float4* __restrict__ raw_out,
-               int n_latents, long long rows_per_latent) {
+               int n_latents, long long rows_per_latent, uint8_t* __restrict__ saved) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -490,14 +502,38 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(tab + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
         }
     }
-    const uint32_t tmem_base = tc_prologue(cx, warp, 32);      // act_ready: 16 warps x 2 CTAs arrive per sub-tile and step
+    if (kSave) {   // the aux blocks are copied out whole: their never-written chunks must not hold stale bits
+        for (int i = threadIdx.x; i < 2 * (int)(kPeBytes / 16); i += kThreads) {
+            const uint32_t gg = (uint32_t)i / (kPeBytes / 16), o = (uint32_t)i % (kPeBytes / 16);
+            st_shared_v4(cx.smem + gg * kSubBytes + o * 16u, 0u, 0u, 0u, 0u);
+        }
+    }
+    const uint32_t tmem_base = tc_prologue(cx, warp, 32, 16);  // act_ready: 16 warps x 2 CTAs arrive per sub-tile and step
 
     if (warp == 0) {
         if (lane == 0) producer_loop_fn<FilmSched>(cx, packed_of, pl, n_steps, 1);
     } else if (warp == 1) {
         if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, 1);
         else if (lane == 0) relay_loop<FilmSched>(cx, pl, n_steps, 1);
-    } else if (warp >= kCtrlWarps) {
+    } else if (warp < kCtrlWarps) {
+        if (kSave && lane == 0) {
+            // ===== spill thread of sub-tile g =====
+            const int g = warp - 2;
+            const uint32_t aux = cx.smem + (uint32_t)g * kSubBytes, hreg = aux + kPeBytes;
+            const uint32_t ready = cx.spill_ready + 8 * g, done = cx.spill_done + 8 * g;
+            const size_t n_sub = (size_t)pl.n_pairs * 4;
+            uint32_t ph = 0;
+            for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+                const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+                auto tile = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
+                auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
+                mbar_wait(ready, ph); bulk_s2g(tile(kFsAUX, 1), aux, kBlk); bulk_s2g(tile(fs_h(0), 4), hreg, 4 * kBlk); finish();    // aux, h0
+                for (int l = 1; l < 8; ++l) { mbar_wait(ready, ph); bulk_s2g(tile(fs_h(l), 4), hreg, 4 * kBlk); finish(); }             // h1 .. h7
+                mbar_wait(ready, ph); bulk_s2g(tile(kFsHC, 4), hreg, 4 * kBlk); finish();                                                // hidden_layer_rgb output
+            }
+            bulk_wait_all();
+        }
+    } else {
         // warp = 4 + cq*4 + quad: column quarter cq (64 columns = K-block cq), TMEM lane quadrant quad; thread = row r of BOTH sub-tiles
         const int ew = warp - kCtrlWarps;
         const int cq = ew >> 2, quad = ew & 3;
@@ -508,7 +544,11 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         uint32_t xoff[8];
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
-        uint32_t acc_phase[2] = {0u, 0u};
+        uint32_t acc_phase[2] = {0u, 0u}, sp_phase[2] = {0u, 0u};
+        bool first_tile = true;
+        const size_t n_sub = (size_t)pl.n_pairs * 4;
+        auto spill_sig = [&](int g) { if (kSave && lane == 0) mbar_arrive(cx.spill_ready + 8 * g); };
+        auto spill_wait = [&](int g) { if (kSave) { mbar_wait(cx.spill_done + 8 * g, sp_phase[g]); sp_phase[g] ^= 1u; } };
         auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSubBytes; };
         auto t_q = [&](int g) -> uint32_t { return tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)cq * 64u; };
         auto h_blk = [&](int g) -> uint32_t { return sub_base(g) + kPeBytes + (uint32_t)cq * 16384u + row_off; };
@@ -541,10 +581,12 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 valid[g] = row[g] < rows;
                 float pnt[3], vdir[3];
                 load_row(src, valid[g] ? row[g] : rows - 1, pnt, vdir);
+                if (!first_tile) spill_wait(g);                      // previous tile's last copy
+                const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 // ---- input_layer on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    uint32_t pk[16];
+                    uint32_t pk[16], ck[16];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
@@ -554,41 +596,62 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                         float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
                         float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
                         float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
-                        pk[2 * q + 0] = pack_bf16(__sinf(fmaf(a0, sc.x, sh.x)), __sinf(fmaf(a1, sc.y, sh.y)));
-                        pk[2 * q + 1] = pack_bf16(__sinf(fmaf(a2, sc.z, sh.z)), __sinf(fmaf(a3, sc.w, sh.w)));
+                        const float t0 = fmaf(a0, sc.x, sh.x), t1 = fmaf(a1, sc.y, sh.y), t2 = fmaf(a2, sc.z, sh.z), t3 = fmaf(a3, sc.w, sh.w);
+                        pk[2 * q + 0] = pack_bf16(__sinf(t0), __sinf(t1));
+                        pk[2 * q + 1] = pack_bf16(__sinf(t2), __sinf(t3));
+                        if (kSave) { ck[2 * q + 0] = pack_bf16(__cosf(t0), __cosf(t1)); ck[2 * q + 1] = pack_bf16(__cosf(t2), __cosf(t3)); }
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q) {
+                        st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                        if (kSave) stg128(saved + film_cos_off(n_sub, 0, T, cq, jj * 4 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
+                    }
                 }
                 if (cq == 0) {
-                    // aux block = [view direction (3), 1, 1, 0 ...] (16 K): the direction columns of hidden_layer_rgb and the two
-                    // constant ones that pick up every layer's FiLM shift (hi + lo)
-                    st_shared_v4(sub_base(g) + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 1.0f), pack_bf16(1.0f, 0.f), 0u);
+                    // aux block = [view direction (3), 1, 1, position (3), 0 ...] (16 K): the direction columns of hidden_layer_rgb and the
+                    // two constant ones that pick up every layer's FiLM shift (hi + lo); the position columns meet zero weights in the
+                    // forward and are the input-layer operand of the training wgrad
+                    st_shared_v4(sub_base(g) + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 1.0f), pack_bf16(1.0f, pnt[0]),
+                                 pack_bf16(pnt[1], pnt[2]));
                     st_shared_v4(sub_base(g) + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
                 }
                 arrive(g);
+                spill_sig(g);
             }
+            first_tile = false;
+            auto cosp = [&](int layer, int g) -> uint8_t* {
+                return kSave ? saved + film_cos_off(n_sub, layer, (size_t)((2 * p + cx.rank) * 2 + g), cq, 0, r) : nullptr;
+            };
 
             float sigma[2] = {0.f, 0.f}, rgb0[2] = {0.f, 0.f}, rgb1[2] = {0.f, 0.f}, rgb2[2] = {0.f, 0.f};
             for (int s = 0; s < 6; ++s) {                               // hidden_layers.0 .. 5
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     wait_acc(g);
-                    film_epi<0>(t_q(g), 0u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                    spill_wait(g);
+                    film_epi<0, kSave>(t_q(g), 0u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g], cosp(s + 1, g));
                     arrive(g);
+                    spill_sig(g);
                 }
             }
 #pragma unroll
             for (int g = 0; g < 2; ++g) {                               // hidden_layers.6 (+ sigma head)
                 wait_acc(g);
-                film_epi<1>(t_q(g), tab + (uint32_t)(kFWS + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
-                if (!sigma_only) arrive(g);
+                spill_wait(g);
+                film_epi<1, kSave>(t_q(g), tab + (uint32_t)(kFWS + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g], cosp(7, g));
+                if (!sigma_only) { arrive(g); spill_sig(g); }
             }
             if (!sigma_only) {
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {                           // hidden_layer_rgb (+ rgb head)
                     wait_acc(g);
-                    film_epi<2>(t_q(g), tab + (uint32_t)(kFWR + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g]);
+                    spill_wait(g);
+                    film_epi<2, kSave>(t_q(g), tab + (uint32_t)(kFWR + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g], cosp(8, g));
+                    if (kSave) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        spill_sig(g);
+                    }
                 }
             }
             tc_fence_before();
@@ -702,9 +765,9 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (model_kind == B2R_MODEL_FILM) {
-        rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+        rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
-        tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0);
+        tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0, nullptr);
     } else {
         rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
@@ -742,17 +805,18 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+    rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
     if (rc) return rc;
     // n_latents == 1 still goes through the batched indexing (latent 0 for every row) when rows_per_latent covers all rows
-    tc::film_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only,
-                                                                                     (float4*)raw_out, n_latents, rows_per_latent);
+    tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only,
+                                                                                            (float4*)raw_out, n_latents, rows_per_latent, nullptr);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd_film_batched");
     return 0;
 }
 
 extern "C" size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows) {
     if (model_kind == B2R_MODEL_SIREN && rows >= 0) return b2r::tc::siren_saved_bytes(rows);
+    if (model_kind == B2R_MODEL_FILM && rows >= 0) return (size_t)b2r::tc::n_sub_tiles(rows) * b2r::tc::film_saved_bytes_per_sub();
     if (model_kind != B2R_MODEL_NERF || rows < 0) return 0;
     return (size_t)b2r::tc::n_sub_tiles(rows) * b2r::tc::saved_bytes_per_sub();
 }
@@ -760,8 +824,8 @@ extern "C" size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows) {
 extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,
                                     size_t saved_bytes, void* stream) {
     using namespace b2r;
-    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_SIREN,
-                  "b2r_mlp_tc_train_fwd: only the NeRF and SirenNeRF models have a fused tensor-core training path (kind %d)", model_kind);
+    B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_SIREN || model_kind == B2R_MODEL_FILM,
+                  "b2r_mlp_tc_train_fwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(packed && raw_out && saved, "b2r_mlp_tc_train_fwd: NULL pointer");
     B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out | (uintptr_t)saved) & 15) == 0, "b2r_mlp_tc_train_fwd: buffers must be 16-byte aligned");
     int rc = check_mlp_input(in);
@@ -770,6 +834,17 @@ extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2
     B2R_CHECK_ARG(saved_bytes >= b2r_mlp_tc_train_saved_bytes(model_kind, rows), "b2r_mlp_tc_train_fwd: saved buffer too small (%zu B)", saved_bytes);
     if (rows == 0) return 0;
     if (model_kind == B2R_MODEL_SIREN) return tc::siren_train_fwd(packed, in, rows, raw_out, saved, (cudaStream_t)stream);
+    if (model_kind == B2R_MODEL_FILM) {                 // packed = one latent's image (use_dir = 1 layout)
+        unsigned fgrid = 0;
+        rc = tc::pair_grid(rows, &fgrid);
+        if (rc) return rc;
+        rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+        if (rc) return rc;
+        tc::film_tc_kernel<true><<<fgrid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, 0,
+                                                                                               (float4*)raw_out, 1, 0, (uint8_t*)saved);
+        B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd (FiLM-SIREN)");
+        return 0;
+    }
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;

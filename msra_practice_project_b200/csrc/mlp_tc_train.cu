@@ -332,7 +332,30 @@ __constant__ WUnit c_wunits_siren[kWUnits] = {
     {kScrGD1, 2, kSsGL, 4, 9, 0, 256, 1, 0, 30.0f},
     {kScrGD1, 2, kSsAUX, 1, 9, 256, 3, 0, 5, 30.0f},
 };
-constexpr int kWCostTotal = 5 + 4 * 8 + 5 + 8 + 2 * 8 + 8 + 6 + 3;      // half-block loads per 64-row stage, all units: 83 (both models)
+// FiLM-SIREN (pi_GAN/modules.py:101-118): G_l = gradient wrt the sine argument t_l of layer l (0 = input_layer, 1..7 =
+// hidden_layers.0..6, 8 = hidden_layer_rgb); the aux tile [dir(3), 1, 1, pos(3)] is the input of input_layer and the direction
+// columns of hidden_layer_rgb.  The units produce the gradients of the FOLDED parameters (W' = 30 gamma W, s' = 30 (gamma b + beta));
+// film_grad_finish_kernel turns them into d W, d b, d gamma, d beta.
+__constant__ WUnit c_wunits_film[10] = {
+    {fscr_g(0), 4, kFsAUX, 1, 0, 0, 3, 1, 5, 1.0f},
+    {fscr_g(1), 4, fs_h(0), 4, 1, 0, 256, 1, 0, 1.0f},
+    {fscr_g(2), 4, fs_h(1), 4, 2, 0, 256, 1, 0, 1.0f},
+    {fscr_g(3), 4, fs_h(2), 4, 3, 0, 256, 1, 0, 1.0f},
+    {fscr_g(4), 4, fs_h(3), 4, 4, 0, 256, 1, 0, 1.0f},
+    {fscr_g(5), 4, fs_h(4), 4, 5, 0, 256, 1, 0, 1.0f},
+    {fscr_g(6), 4, fs_h(5), 4, 6, 0, 256, 1, 0, 1.0f},
+    {fscr_g(7), 4, fs_h(6), 4, 7, 0, 256, 1, 0, 1.0f},
+    {fscr_g(8), 4, fs_h(7), 4, 9, 0, 256, 1, 0, 1.0f},
+    {fscr_g(8), 4, kFsAUX, 1, 9, 256, 3, 0, 0, 1.0f},
+};
+// model kinds of the wgrad kernel (= B2R_MODEL_*: 0 NeRF, 1 FiLM-SIREN, 2 SirenNeRF)
+constexpr int kKNerf = B2R_MODEL_NERF, kKFilm = B2R_MODEL_FILM, kKSiren = B2R_MODEL_SIREN;
+template <int KIND> __host__ __device__ constexpr int n_wunits() { return KIND == kKFilm ? 10 : kWUnits; }
+// half-block loads per 64-row stage, all units: 83 (NeRF, SirenNeRF), 74 (FiLM-SIREN)
+template <int KIND> __host__ __device__ constexpr int wcost_total() { return KIND == kKFilm ? 5 + 7 * 8 + 8 + 5 : 5 + 4 * 8 + 5 + 8 + 2 * 8 + 8 + 6 + 3; }
+template <int KIND> __host__ __device__ constexpr LayerDesc wlayer(int i) {
+    return KIND == kKFilm ? film_layer(i, true) : (KIND == kKSiren ? siren_layer(i) : nerf_layer(i));
+}
 
 constexpr int kWStages = 3;
 constexpr uint32_t kWSlot = 65536;                                       // up to 8 half blocks of 8 KB
@@ -343,12 +366,12 @@ constexpr int kWThreads = 192;                                           // prod
 struct WPiece { int u; long long t0, t1; };
 // CTA b owns the slice [b, b+1) * total / grid of the cost line (units laid end to end, each n_sub tiles x cost(u)); both
 // ends are rounded to tiles with the same function, so neighbouring CTAs agree on the boundary.
-template <bool kSiren>
-__device__ __forceinline__ WUnit wunit(int u) { return kSiren ? c_wunits_siren[u] : c_wunits[u]; }
+template <int KIND>
+__device__ __forceinline__ WUnit wunit(int u) { return KIND == kKFilm ? c_wunits_film[u] : (KIND == kKSiren ? c_wunits_siren[u] : c_wunits[u]); }
 
-template <bool kSiren>
+template <int KIND>
 __device__ __forceinline__ bool wpiece(int u, long long n_sub, long long lo, long long hi, long long& base, WPiece& pc) {
-    const WUnit un = wunit<kSiren>(u);
+    const WUnit un = wunit<KIND>(u);
     const long long cost = un.g_nb + un.x_nb;
     const long long b0 = base, b1 = base + n_sub * cost;
     base = b1;
@@ -360,7 +383,7 @@ __device__ __forceinline__ bool wpiece(int u, long long n_sub, long long lo, lon
     return pc.t0 < pc.t1;
 }
 
-template <bool kSiren>
+template <int KIND>
 __global__ void __launch_bounds__(kWThreads, 1)
 nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub, float* __restrict__ d_params) {
     extern __shared__ uint8_t smem_raw[];
@@ -381,17 +404,17 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot_addr));
 
-    const long long total = n_sub * kWCostTotal;
+    const long long total = n_sub * wcost_total<KIND>();
     const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             long long base = 0;
-            for (int u = 0; u < kWUnits; ++u) {
+            for (int u = 0; u < n_wunits<KIND>(); ++u) {
                 WPiece pc;
-                if (!wpiece<kSiren>(u, n_sub, lo, hi, base, pc)) continue;
-                const WUnit un = wunit<kSiren>(u);
+                if (!wpiece<KIND>(u, n_sub, lo, hi, base, pc)) continue;
+                const WUnit un = wunit<KIND>(u);
                 const uint8_t* gsrc = scratch + (size_t)un.g_off * n_sub * kBlk;
                 const uint8_t* xsrc = saved + (size_t)un.x_off * n_sub * kBlk;
                 const uint32_t bytes = (uint32_t)(un.g_nb + un.x_nb) * 8192u;
@@ -416,10 +439,10 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
         long long base = 0;
         // A = dPre half blocks, B = X half blocks: MN-major SWIZZLE_128B, LBO = 8 KB (next 64 columns), SBO = 1 KB (next 8 rows of K)
         const uint64_t d_hi = make_desc(0, 8192, 1024, kLayoutSW128);
-        for (int u = 0; u < kWUnits; ++u) {
+        for (int u = 0; u < n_wunits<KIND>(); ++u) {
             WPiece pc;
-            if (!wpiece<kSiren>(u, n_sub, lo, hi, base, pc)) continue;
-            const WUnit un = wunit<kSiren>(u);
+            if (!wpiece<KIND>(u, n_sub, lo, hi, base, pc)) continue;
+            const WUnit un = wunit<KIND>(u);
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)un.x_nb * 64u) | (1u << 15) | (1u << 16);
             const int n_m = un.g_nb >> 1;
             if (!first_piece) { mbar_wait(tmem_empty, te_phase); te_phase ^= 1u; tc_fence_after(); }
@@ -452,11 +475,11 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
         uint32_t stage = 0, phase = 0, af_phase = 0;
         long long base = 0;
-        for (int u = 0; u < kWUnits; ++u) {
+        for (int u = 0; u < n_wunits<KIND>(); ++u) {
             WPiece pc;
-            if (!wpiece<kSiren>(u, n_sub, lo, hi, base, pc)) continue;
-            const WUnit un = wunit<kSiren>(u);
-            const LayerDesc L = kSiren ? siren_layer(un.layer) : nerf_layer(un.layer);
+            if (!wpiece<KIND>(u, n_sub, lo, hi, base, pc)) continue;
+            const WUnit un = wunit<KIND>(u);
+            const LayerDesc L = wlayer<KIND>(un.layer);
             const bool do_bias = un.bias && w < un.g_nb;
             float s0 = 0.f, s1 = 0.f;
             for (long long st = 0; st < 2 * (pc.t1 - pc.t0); ++st) {
@@ -600,6 +623,270 @@ __global__ void __launch_bounds__(256) nerf_head_wgrad_kernel(const uint8_t* __r
     }
 }
 
+// =====================================================================================================================
+// FiLM-SIREN reverse mode (pi_GAN/train.py:134 / synthesis.py:107: autograd through FilmSirenNeRF.forward, modules.py:101-118)
+// =====================================================================================================================
+// The forward (film_tc_kernel<true>, mlp_tc.cu) evaluates t_l = W'_l x + s'_l with the FiLM scale folded into the weights
+// (W' = 30 gamma W, s' = 30 (gamma b + beta)) and keeps h_l = sin(t_l) as tiles and cos(t_l) thread-major.  G_l = dL/dt_l:
+//   G8 = (d rgb_pre . W_rgb) cos(t8)                                   CUDA cores (K = 3), written as the first A operand
+//   step 0: G7 = (G8 . W'_rgb[:, 0:256] + gs w_sigma) cos(t7)          hidden_layer_rgb
+//   step s = 1..7: G_{7-s} = (G_{8-s} . W'_{hidden_layers.(7-s)}) cos(t_{7-s})
+// Every G_l is spilled for wgrad (units c_wunits_film), which yields d W' and d s'; film_grad_finish_kernel recovers
+//   d W = 30 gamma (.) d W',  d b = 30 gamma d s',  d gamma = 30 (sum_j W_ij d W'_ij + b_i d s'_i),  d beta = 30 d s'.
+struct FilmBwdSched {
+    static constexpr int kSteps = 8;
+    __host__ __device__ static constexpr int n_pre(int, int) { return 0; }
+    __host__ __device__ static constexpr int n_h(int, int) { return 4; }
+    __host__ __device__ static constexpr int n_post(int, int) { return 0; }
+    __host__ __device__ static constexpr int n(int) { return 256; }
+    static constexpr int kPostMmas = 1;
+};
+constexpr long long kFilmBwdChunkBytes = step_base<FilmBwdSched>(FilmBwdSched::kSteps);
+static_assert(kFilmBwdChunkBytes == 32LL * 32768, "FiLM bwd packed chunk bytes");
+constexpr int kFBwdTabWSigma = 0, kFBwdTabWRgb = 256, kFBwdTabFloats = 1024;          // w_sigma[256] | w_rgb[3][256]
+constexpr long long kFilmBwdPackedBytes = kFilmBwdChunkBytes + kFBwdTabFloats * 4;
+static_assert(kFBwdTabFloats * 4 <= (int)kTabBytes, "FiLM bwd table region");
+// film_layer index / film row of dgrad step s
+__host__ __device__ constexpr int fbwd_layer(int s) { return s == 0 ? 9 : 8 - s; }
+__host__ __device__ constexpr int fbwd_film_row(int s) { return 8 - s; }
+
+// B[n][k] = 30 gamma_k W[k][n]: n = input feature (output column of dX), k = output feature (the forward's folded row k)
+__global__ void film_pack_bwd_kernel(const float* __restrict__ params, const float* __restrict__ film, uint8_t* __restrict__ packed) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < kFilmBwdChunkBytes / 16) {
+        int s, c, hf, row, grp;
+        locate<FilmBwdSched>(t * 16, s, c, hf, row, grp);
+        const LayerDesc L = film_layer(fbwd_layer(s), true);
+        const float* __restrict__ gamma = film + fbwd_film_row(s) * 512;
+        const int n = hf * 128 + row;
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = c * 64 + grp * 8 + e;
+            v[e] = __float2bfloat16_rn(30.0f * gamma[k] * params[L.w_off + (long long)k * L.in + n]);
+        }
+        uint8_t* dst = packed + step_base<FilmBwdSched>(s) + (long long)(c * 2 + hf) * half_bytes<FilmBwdSched>(s) +
+                       sw128_offset((uint32_t)row, (uint32_t)grp);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+    if (t < kFBwdTabFloats) {
+        float* tab = reinterpret_cast<float*>(packed + kFilmBwdChunkBytes);
+        const int i = (int)t;
+        tab[i] = i < kFBwdTabWRgb ? params[film_layer(8, true).w_off + i] : params[film_layer(10, true).w_off + (i - kFBwdTabWRgb)];
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+film_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const float4* __restrict__ raw, const float4* __restrict__ d_raw,
+                   const uint8_t* __restrict__ saved, uint8_t* __restrict__ scratch) {
+    extern __shared__ uint8_t smem_raw[];
+    const Ctx cx = make_ctx(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PairLoop pl(rows);
+    {   // w_sigma | w_rgb -> shared memory
+        const float4* tab_g = reinterpret_cast<const float4*>(packed + kFilmBwdChunkBytes);
+        for (int i = threadIdx.x; i < kFBwdTabFloats / 4; i += kThreads) {
+            float4 v = __ldg(tab_g + i);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cx.smem + kTabOff + 16u * i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+        }
+    }
+    const uint32_t tmem_base = tc_prologue(cx, warp);
+
+    if (warp == 0) {
+        if (lane == 0) producer_loop<FilmBwdSched>(cx, packed, pl, FilmBwdSched::kSteps, 0);
+    } else if (warp == 1) {
+        if (cx.rank == 0) mma_loop<FilmBwdSched>(cx, tmem_base, pl, FilmBwdSched::kSteps, 0);
+        else if (lane == 0) relay_loop<FilmBwdSched>(cx, pl, FilmBwdSched::kSteps, 0);
+    } else if (warp < kCtrlWarps) {
+        if (lane == 0) {
+            // ===== spill thread of sub-tile g: G8, G7 .. G0 (the A operands) -> tiled tensors in `scratch` =====
+            const int g = warp - 2;
+            const uint32_t hreg = cx.smem + (uint32_t)g * kSubBytes + kPeBytes;
+            const uint32_t ready = cx.spill_ready + 8 * g, done = cx.spill_done + 8 * g;
+            const size_t n_sub = (size_t)pl.n_pairs * 4;
+            uint32_t ph = 0;
+            for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+                const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+                for (int l = 8; l >= 0; --l) {
+                    mbar_wait(ready, ph);
+                    bulk_s2g(scratch + ((size_t)fscr_g(l) * n_sub + T * 4) * kBlk, hreg, 4 * kBlk);
+                    bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u;
+                }
+            }
+            bulk_wait_all();
+        }
+    } else {
+        const int ew = warp - kCtrlWarps;
+        const int g = ew >> 3, half = (ew >> 2) & 1, quad = ew & 3;
+        const int r = (quad << 5) | lane;
+        const uint32_t sub = cx.smem + (uint32_t)g * kSubBytes;
+        const uint32_t h_base = sub + kPeBytes;
+        const uint32_t t_addr = tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const uint32_t xr = (uint32_t)(r & 7);
+        const uint32_t tab = cx.smem + kTabOff;
+        const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
+        const uint32_t acc_bar = cx.acc_full + 8 * g;
+        const uint32_t ready_bar = cx.spill_ready + 8 * g, done_bar = cx.spill_done + 8 * g;
+        const uint32_t t_half = t_addr + (uint32_t)half * 128u;
+        const uint32_t h_half = h_base + row_off + (uint32_t)half * 2u * kBlk;
+        const uint32_t wsig_half = tab + (uint32_t)(kFBwdTabWSigma + half * 128) * 4u;
+        uint32_t xoff[8];
+#pragma unroll
+        for (uint32_t c = 0; c < 8; ++c) xoff[c] = (c ^ xr) << 4;
+        uint32_t acc_phase = 0, sp_phase = 0;
+        bool first_tile = true;
+        const size_t n_sub = (size_t)pl.n_pairs * 4;
+        float4* __restrict__ hg_out = reinterpret_cast<float4*>(scratch + (size_t)kFScrBlocks * n_sub * kBlk);
+        for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+            const long long row = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
+            const bool valid = row < rows;
+            const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
+            auto spill_sig = [&]() { if (lane == 0) mbar_arrive(ready_bar); };
+            // ---- heads: d raw -> (d rgb pre-sigmoid, d sigma pre-relu); rows past the end contribute zero everywhere
+            float gc0 = 0.f, gc1 = 0.f, gc2 = 0.f, gs = 0.f;
+            if (valid) {
+                const float4 y = __ldg(raw + row), dy = __ldg(d_raw + row);
+                gc0 = dy.x * (y.x * (1.0f - y.x));
+                gc1 = dy.y * (y.y * (1.0f - y.y));
+                gc2 = dy.z * (y.z * (1.0f - y.z));
+                gs = y.w > 0.f ? dy.w : 0.f;
+            }
+            if (half == 0) hg_out[T * kRowsSub + r] = make_float4(gc0, gc1, gc2, gs);
+            {
+                // G8 = (d rgb pre . W_rgb) cos(t8): this half produces columns half*128 .. +127 = K-blocks 2*half, 2*half + 1
+                const uint32_t wr = tab + (uint32_t)(kFBwdTabWRgb + half * 128) * 4u;
+                if (!first_tile) { mbar_wait(done_bar, sp_phase); sp_phase ^= 1u; }          // previous tile's G0 copy
+                first_tile = false;
+#pragma unroll 4
+                for (int q = 0; q < 16; ++q) {
+                    const uint4 cwq = ldg128(saved + film_cos_off(n_sub, 8, T, half * 2 + (q >> 3), q & 7, r));
+                    float f[8];
+#pragma unroll
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const uint32_t wa = wr + (uint32_t)(q * 8 + hq * 4) * 4u;
+                        const float4 w0 = lds128(wa), w1 = lds128(wa + 1024u), w2 = lds128(wa + 2048u);
+                        f[4 * hq + 0] = fmaf(gc2, w2.x, fmaf(gc1, w1.x, gc0 * w0.x));
+                        f[4 * hq + 1] = fmaf(gc2, w2.y, fmaf(gc1, w1.y, gc0 * w0.y));
+                        f[4 * hq + 2] = fmaf(gc2, w2.z, fmaf(gc1, w1.z, gc0 * w0.z));
+                        f[4 * hq + 3] = fmaf(gc2, w2.w, fmaf(gc1, w1.w, gc0 * w0.w));
+                    }
+                    const uint32_t w0 = mul_bf16x2(pack_bf16(f[0], f[1]), cwq.x), w1 = mul_bf16x2(pack_bf16(f[2], f[3]), cwq.y);
+                    const uint32_t w2 = mul_bf16x2(pack_bf16(f[4], f[5]), cwq.z), w3 = mul_bf16x2(pack_bf16(f[6], f[7]), cwq.w);
+                    st_shared_v4(h_half + (uint32_t)(q >> 3) * kBlk + ((((uint32_t)q & 7u) ^ xr) << 4), w0, w1, w2, w3);
+                }
+            }
+            arrive_act(act_local, act_leader, cx.rank, lane);
+            spill_sig();
+            // cos(t_l) checkpoint of this thread: first word of quarter 2 * half
+            auto mptr = [&](int l) -> const uint8_t* { return saved + film_cos_off(n_sub, l, T, half * 2, 0, r); };
+            // step 0: G7 (+ sigma head)
+            bwd_epi<1, true>(t_half, h_half, xoff, mptr(7), gs, wsig_half, acc_bar, acc_phase, done_bar, sp_phase);
+            arrive_act(act_local, act_leader, cx.rank, lane);
+            spill_sig();
+            // steps 1..6: G6 .. G1
+            for (int s = 1; s < 7; ++s) {
+                bwd_epi<2, true>(t_half, h_half, xoff, mptr(7 - s), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
+                arrive_act(act_local, act_leader, cx.rank, lane);
+                spill_sig();
+            }
+            // step 7: G0: only wgrad reads it (the input layer's input is the position), no MMA follows
+            bwd_epi<2, true>(t_half, h_half, xoff, mptr(0), 0.f, 0u, acc_bar, acc_phase, done_bar, sp_phase);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            spill_sig();
+        }
+    }
+    tc_teardown(tmem_base, warp);
+}
+
+// output_layer_sigma (256 -> 1, input h7) and output_layer_rgb (256 -> 3, input = hidden_layer_rgb's output HC): weight and
+// bias gradients from HG and the saved tiles.  A thread owns one 16-byte chunk (8 columns) of a 256-column row (a warp reads
+// one 512-byte row of the 4 blocks per step); the 8 warps take every 8th row, 4 rows in flight per thread.
+__global__ void __launch_bounds__(256) film_head_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub,
+                                                              float* __restrict__ d_out, LayerDesc Ls, LayerDesc Lc) {
+    __shared__ float red[8][1024 + 4];           // per warp: d w_sigma[256] | d w_rgb[3][256] | 4 bias sums (sigma, rgb)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4* __restrict__ hg = reinterpret_cast<const float4*>(scratch + (size_t)kFScrBlocks * n_sub * kBlk);
+    const uint32_t c = (uint32_t)lane & 7u;
+    const int blk = lane >> 3;
+    float as[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+          a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float bs = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    for (long long T = blockIdx.x; T < n_sub; T += gridDim.x) {
+        const uint8_t* t7 = saved + ((size_t)fs_h(7) * n_sub + (size_t)T * 4 + blk) * kBlk;
+        const uint8_t* tc = saved + ((size_t)kFsHC * n_sub + (size_t)T * 4 + blk) * kBlk;
+        const float4* g = hg + T * kRowsSub;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += 4) {
+            uint4 x7[4], xc[4]; float4 gg[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t row = (uint32_t)(warp + 8 * (i0 + i));
+                const uint32_t o = row * 128u + ((c ^ (row & 7u)) << 4);
+                x7[i] = ldg128(t7 + o);
+                xc[i] = ldg128(tc + o);
+                gg[i] = __ldg(&g[row]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                fma8(as, gg[i].w, x7[i]); fma8(a0, gg[i].x, xc[i]); fma8(a1, gg[i].y, xc[i]); fma8(a2, gg[i].z, xc[i]);
+                bs += gg[i].w; b0 += gg[i].x; b1 += gg[i].y; b2 += gg[i].z;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = blk * 64 + (int)c * 8 + j;
+        red[warp][col] = as[j]; red[warp][256 + col] = a0[j]; red[warp][512 + col] = a1[j]; red[warp][768 + col] = a2[j];
+    }
+    if (lane == 0) { red[warp][1024] = bs; red[warp][1025] = b0; red[warp][1026] = b1; red[warp][1027] = b2; }   // every lane saw the same rows
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1028; i += 256) {
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += red[k][i];
+        float* dst = i < 256 ? d_out + Ls.w_off + i : (i < 1024 ? d_out + Lc.w_off + (i - 256) : (i == 1024 ? d_out + Ls.b_off : d_out + Lc.b_off + (i - 1025)));
+        atomicAdd(dst, sum);
+    }
+}
+
+// folded gradients -> parameter / FiLM gradients.  One warp per (FiLM layer, output feature i); the first CTAs' spare threads
+// add the head gradients.  d_params / d_film are ACCUMULATED into (each element by exactly one thread); either may be NULL.
+__global__ void __launch_bounds__(256) film_grad_finish_kernel(const float* __restrict__ params, const float* __restrict__ film,
+                                                               const float* __restrict__ d_folded, float* __restrict__ d_params,
+                                                               float* __restrict__ d_film) {
+    const int gw = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (gw < 9 * 256) {
+        const int fl = gw >> 8, i = gw & 255;
+        const LayerDesc L = film_layer(fl == 8 ? 9 : fl, true);
+        const float gsc = 30.0f * film[fl * 512 + i];
+        const float* __restrict__ w = params + L.w_off + (long long)i * L.in;
+        const float* __restrict__ dwp = d_folded + L.w_off + (long long)i * L.in;
+        float acc = 0.f;
+        for (int j = lane; j < L.in; j += 32) {
+            const float d = dwp[j];
+            acc = fmaf(w[j], d, acc);
+            if (d_params) d_params[L.w_off + (long long)i * L.in + j] += gsc * d;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float ds = d_folded[L.b_off + i];
+            if (d_params) d_params[L.b_off + i] += gsc * ds;
+            if (d_film) {
+                d_film[fl * 512 + i] += 30.0f * fmaf(params[L.b_off + i], ds, acc);
+                d_film[fl * 512 + 256 + i] += 30.0f * ds;
+            }
+        }
+    } else if (d_params) {
+        const int t = (gw - 9 * 256) * 32 + lane;          // head parameters: plain gradients
+        const LayerDesc Ls = film_layer(8, true), Lc = film_layer(10, true);
+        if (t < 257) d_params[Ls.w_off + t] += d_folded[Ls.w_off + t];                  // w_sigma[256], b_sigma
+        else if (t < 257 + 771) d_params[Lc.w_off + (t - 257)] += d_folded[Lc.w_off + (t - 257)];   // w_rgb[3][256], b_rgb[3]
+    }
+}
+
 int pair_grid(long long rows, unsigned* grid);   // mlp_tc.cu
 
 }  // namespace tc
@@ -608,7 +895,18 @@ int pair_grid(long long rows, unsigned* grid);   // mlp_tc.cu
 static inline bool train_kind(int k) { return k == B2R_MODEL_NERF || k == B2R_MODEL_SIREN; }
 
 extern "C" size_t b2r_mlp_tc_bwd_packed_bytes(int model_kind) {
+    if (model_kind == B2R_MODEL_FILM) return (size_t)b2r::tc::kFilmBwdPackedBytes;
     return train_kind(model_kind) ? (size_t)b2r::tc::kBwdPackedBytes : 0;
+}
+
+extern "C" int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, void* packed_out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(params && film && packed_out, "b2r_mlp_tc_pack_bwd_film: NULL pointer");
+    B2R_CHECK_ARG(((uintptr_t)packed_out & 15) == 0, "b2r_mlp_tc_pack_bwd_film: packed_out must be 16-byte aligned");
+    long long threads = tc::kFilmBwdChunkBytes / 16;
+    tc::film_pack_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, film, (uint8_t*)packed_out);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_pack_bwd_film");
+    return 0;
 }
 
 extern "C" int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* packed_out, void* stream) {
@@ -626,6 +924,8 @@ extern "C" int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* pa
 }
 
 extern "C" size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows) {
+    if (model_kind == B2R_MODEL_FILM && rows >= 0)
+        return (size_t)b2r::tc::n_sub_tiles(rows) * ((size_t)b2r::tc::kFScrBlocks * b2r::tc::kBlk + b2r::tc::kRowsSub * 16);
     if (!train_kind(model_kind) || rows < 0) return 0;
     return (size_t)b2r::tc::n_sub_tiles(rows) * ((size_t)b2r::tc::kScrBlocks * b2r::tc::kBlk + b2r::tc::kRowsSub * 16);
 }
@@ -648,11 +948,11 @@ static int train_bwd_launch(const void* packed_bwd, long long rows, const float*
     if (rc) return rc;
     rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel<kSiren>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel<kSiren ? tc::kKSiren : tc::kKNerf>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
     if (rc) return rc;
     const long long work = n_sub * tc::kWUnits;
     unsigned wgrid = (unsigned)(work < sms ? work : sms);
-    tc::nerf_tc_wgrad_kernel<kSiren><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
+    tc::nerf_tc_wgrad_kernel<kSiren ? tc::kKSiren : tc::kKNerf><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (wgrad)");
     unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
     tc::nerf_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params,
@@ -674,4 +974,49 @@ extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long
     if (rows == 0) return 0;
     if (model_kind == B2R_MODEL_SIREN) return train_bwd_launch<true>(packed_bwd, rows, raw, d_raw, saved, scratch, d_params, (cudaStream_t)stream);
     return train_bwd_launch<false>(packed_bwd, rows, raw, d_raw, saved, scratch, d_params, (cudaStream_t)stream);
+}
+
+extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, long long rows, const float* raw,
+                                         const float* d_raw, const void* saved, void* scratch, size_t scratch_bytes, float* d_folded,
+                                         float* d_params, float* d_film, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(packed_bwd && params && film && raw && d_raw && saved && scratch && d_folded, "b2r_mlp_tc_train_bwd_film: NULL pointer");
+    B2R_CHECK_ARG((((uintptr_t)packed_bwd | (uintptr_t)raw | (uintptr_t)d_raw | (uintptr_t)saved | (uintptr_t)scratch | (uintptr_t)d_folded) & 15) == 0,
+                  "b2r_mlp_tc_train_bwd_film: buffers must be 16-byte aligned");
+    B2R_CHECK_ARG(rows >= 0, "b2r_mlp_tc_train_bwd_film: negative row count");
+    B2R_CHECK_ARG(scratch_bytes >= b2r_mlp_tc_train_scratch_bytes(B2R_MODEL_FILM, rows), "b2r_mlp_tc_train_bwd_film: scratch too small (%zu B)", scratch_bytes);
+    if (rows == 0 || (!d_params && !d_film)) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = cuda_result(cudaMemsetAsync(d_folded, 0, (size_t)B2R_FILM_NUMEL * sizeof(float), st), "cudaMemsetAsync(d_folded)");
+    if (rc) return rc;
+    unsigned grid = 0;
+    rc = tc::pair_grid(rows, &grid);
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc bwd smem attribute");
+    if (rc) return rc;
+    tc::film_tc_bwd_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed_bwd, rows, (const float4*)raw, (const float4*)d_raw,
+                                                                      (const uint8_t*)saved, (uint8_t*)scratch);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (dgrad)");
+    const long long n_sub = tc::n_sub_tiles(rows);
+    int dev = 0, sms = 0;
+    rc = cuda_result(cudaGetDevice(&dev), "cudaGetDevice");
+    if (rc) return rc;
+    rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel<tc::kKFilm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
+    if (rc) return rc;
+    const long long work = n_sub * tc::n_wunits<tc::kKFilm>();
+    unsigned wgrid = (unsigned)(work < sms ? work : sms);
+    tc::nerf_tc_wgrad_kernel<tc::kKFilm><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_folded);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (wgrad)");
+    if (d_params) {
+        unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
+        tc::film_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_folded, film_layer(8, true),
+                                                          film_layer(10, true));
+        B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (heads)");
+    }
+    const int warps = 9 * 256 + (257 + 771 + 31) / 32;
+    tc::film_grad_finish_kernel<<<(warps + 7) / 8, 256, 0, st>>>(params, film, d_folded, d_params, d_film);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (finish)");
+    return 0;
 }

@@ -140,6 +140,18 @@ __device__ __forceinline__ size_t siren_cos9_off(size_t n_sub, size_t T, int cq,
     return (size_t)kSsBlocks * n_sub * kBlk + (size_t)8 * n_sub * 65536 + (((T * 4 + cq) * 4 + w) * 2048) + (size_t)r * 16;
 }
 
+// FiLM-SIREN training checkpoints: tiles AUX [dir(3), 1, 1, pos(3)] | H0..H7 (inputs of hidden_layers.0..6 and hidden_layer_rgb) |
+// HC (hidden_layer_rgb output), then cos(t) of the nine sine layers in the thread-major layout of siren_cos_off
+constexpr int kFsAUX = 0, kFsH0 = 1, kFsHC = 33, kFsBlocks = 37;
+__host__ __device__ constexpr int fs_h(int l) { return kFsH0 + 4 * l; }
+__host__ __device__ constexpr size_t film_saved_bytes_per_sub() { return (size_t)kFsBlocks * kBlk + 9 * 65536; }
+__device__ __forceinline__ size_t film_cos_off(size_t n_sub, int layer, size_t T, int cq, int w, int r) {
+    return (size_t)kFsBlocks * n_sub * kBlk + ((((size_t)layer * n_sub + T) * 4 + cq) * 8 + w) * 2048 + (size_t)r * 16;
+}
+// reverse-mode scratch of the FiLM path: G8 (d t of hidden_layer_rgb) | G7 .. G0, then the head gradients HG
+constexpr int kFScrBlocks = 36;
+__host__ __device__ constexpr int fscr_g(int l) { return 4 * (8 - l); }        // G8 first (written first), G0 last
+
 __device__ __forceinline__ void stg128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

@@ -433,6 +433,55 @@ class _MlpTcTrain(torch.autograd.Function):
         return d_flat, None, None, None, None, None
 
 
+class _MlpTcTrainFilm(torch.autograd.Function):
+    """FiLM-SIREN (use_dir) on the fused tensor-core training path: forward with one latent's folded weights that keeps the
+    sine layers' inputs as bf16 tiles and cos(t) as thread-major bf16x2 words; reverse mode = dgrad + wgrad on the folded
+    weights + the kernel that unfolds them into d weights and d film[9,512] (mlp_tc_train.cu).  Replaces autograd through
+    FilmSirenNeRF.forward (pi_GAN/modules.py:101-118) for pi_GAN/train.py:134 and synthesis.py:107."""
+
+    @staticmethod
+    def forward(ctx, flat, film, rays, z, x):
+        kind = models.KIND_FILM
+        inp, rows, keep = _make_input(rays, z, x, None)
+        dev = flat.device
+        raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        packed = pack_tc(flat.detach(), kind, film.detach(), True)
+        nbytes = lib().b2r_mlp_tc_train_saved_bytes(kind, rows)
+        saved = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
+        if rows > 0:
+            with torch.cuda.device(dev):
+                check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, _stream(flat)),
+                      "b2r_mlp_tc_train_fwd")
+        ctx.rows = rows
+        ctx.save_for_backward(flat, film, raw, saved)
+        del keep
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        flat, film, raw, saved = ctx.saved_tensors
+        need_w, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_w or need_f):
+            return (None,) * 5
+        dev = flat.device
+        d_flat = torch.zeros_like(flat) if need_w else None
+        d_film = torch.zeros_like(film) if need_f else None
+        if ctx.rows > 0:
+            kind = models.KIND_FILM
+            d_raw = _cuda_f32(d_raw, "d_raw")
+            fd, fl = flat.detach(), film.detach()
+            packed_bwd = torch.empty((lib().b2r_mlp_tc_bwd_packed_bytes(kind),), dtype=torch.uint8, device=dev)
+            sbytes = lib().b2r_mlp_tc_train_scratch_bytes(kind, ctx.rows)
+            scratch = torch.empty((sbytes,), dtype=torch.uint8, device=dev)
+            d_folded = torch.empty_like(fd)
+            with torch.cuda.device(dev):
+                check(lib().b2r_mlp_tc_pack_bwd_film(ptr(fd), ptr(fl), ptr(packed_bwd), _stream(flat)), "b2r_mlp_tc_pack_bwd_film")
+                check(lib().b2r_mlp_tc_train_bwd_film(ptr(packed_bwd), ptr(fd), ptr(fl), ctx.rows, ptr(raw), ptr(d_raw), ptr(saved),
+                                                      ptr(scratch), sbytes, ptr(d_folded), ptr(d_flat), ptr(d_film), _stream(flat)),
+                      "b2r_mlp_tc_train_bwd_film")
+        return d_flat, d_film, None, None, None
+
+
 def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, x: torch.Tensor | None = None,
         grid: tuple | None = None, precision: str | None = None, sigma_only: bool = False) -> torch.Tensor:
     """Evaluate the radiance field on rows described by (rays, z) | x | grid -> raw[rows,4]
@@ -463,6 +512,8 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
             gp = "bf16"
         if gp == "bf16" and kind in (models.KIND_NERF, models.KIND_SIREN):
             return _MlpTcTrain.apply(flat, net, kind, rays, z, x)
+        if gp == "bf16" and kind == models.KIND_FILM and use_dir:
+            return _MlpTcTrainFilm.apply(flat, film, rays, z, x)
         return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, {"fp32": 0, "tf32": 1, "bf16": 2}[gp])
     inp, rows, keep = _make_input(rays, z, x, grid)
     raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)

@@ -57,14 +57,21 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     per_sub_saved = 40 * 16384 + 8 * 2 * 128 * 16 + 2 * 128 * 8
     assert lib.b2r_mlp_tc_train_saved_bytes(0, 1000) == 8 * per_sub_saved
     assert lib.b2r_mlp_tc_train_scratch_bytes(0, 1000) == 8 * (38 * 16384 + 128 * 16)
-    assert lib.b2r_mlp_tc_train_saved_bytes(1, 1000) == 0 and lib.b2r_mlp_tc_train_saved_bytes(0, 0) == 0
-    assert lib.b2r_mlp_tc_bwd_packed_bytes(0) == 34 * 32768 + 640 * 4 and lib.b2r_mlp_tc_bwd_packed_bytes(1) == 0
+    assert lib.b2r_mlp_tc_train_saved_bytes(3, 1000) == 0 and lib.b2r_mlp_tc_train_saved_bytes(0, 0) == 0
+    assert lib.b2r_mlp_tc_bwd_packed_bytes(0) == 34 * 32768 + 640 * 4 and lib.b2r_mlp_tc_bwd_packed_bytes(3) == 0
+    # FiLM-SIREN: 37 tile blocks + 9 layers of thread-major cosine words per sub-tile; 36 gradient blocks + head gradients
+    assert lib.b2r_mlp_tc_train_saved_bytes(1, 1000) == 8 * (37 * 16384 + 9 * 65536)
+    assert lib.b2r_mlp_tc_train_scratch_bytes(1, 1000) == 8 * (36 * 16384 + 128 * 16)
+    assert lib.b2r_mlp_tc_bwd_packed_bytes(1) == 32 * 32768 + 1024 * 4
     assert lib.b2r_mlp_tc_packed_bytes(1) == 8 * 5 * 32768 + 2308 * 4                                     # FiLM-SIREN
     assert lib.b2r_mlp_tc_packed_bytes(2) == 8 * 5 * 32768 + 5 * 16384 + 1668 * 4      # SirenNeRF
     assert lib.b2r_mlp_f32_workspace_bytes(2, 10, 1) == 10 * 4620 * 4
     inp = _lib.MlpInput()
     inp.x, inp.n_rays, inp.n_samples = 256, 512, 1
-    assert lib.b2r_mlp_tc_train_fwd(1, 16, C.byref(inp), 16, 16, 1 << 30, None) < 0 and b"NeRF" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_train_fwd(3, 16, C.byref(inp), 16, 16, 1 << 30, None) < 0 and b"unknown model kind" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_train_bwd(1, 16, 512, 16, 16, 16, 16, 1 << 30, 16, None) < 0 and b"NeRF" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_pack_bwd_film(None, None, 16, None) < 0
+    assert lib.b2r_mlp_tc_train_bwd_film(16, 16, 16, 512, 16, 16, 16, 16, 64, 16, 16, 16, None) < 0 and b"scratch" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_fwd(0, 16, C.byref(inp), 16, 16, 64, None) < 0 and b"too small" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_bwd(0, 16, 512, 16, 16, 16, 16, 64, 16, None) < 0 and b"scratch" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_fwd_film_batched(16, 2, 100, C.byref(inp), 16, 0, None) < 0 and b"multiple of 256" in lib.b2r_last_error()
