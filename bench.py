@@ -496,7 +496,7 @@ def run_secondary(args, config=None, embedded=False):
     elif config == "pigan_grad":
         # pi-GAN gradient step through the renderer (pi_GAN/train.py:128-134 generator update without the discriminator; the
         # latent inversion of synthesis.py:92-107 is the same with frozen weights): 4 latents x 64x64, 24+24 samples, gradients to the
-        # FiLM parameters and the FiLM-SIREN weights; coarse pass without gradient, fine pass layer-wise fp32 + reverse mode
+        # FiLM parameters and the FiLM-SIREN weights; coarse pass without gradient, fine pass on the fused tensor-core training path (render_batch, all latents batched)
         n_lat, res, s_ = 4, 64, 24
         b, c = shard.shard_range(n_lat, rank, world)
         torch.manual_seed(0)
@@ -524,8 +524,9 @@ def run_secondary(args, config=None, embedded=False):
         rows = n_lat * res * res * 2 * s_
         line = dict(metric="rays/s, pi-GAN gradient step through the renderer (4 latents x 64x64, 24+24 samples; d/dfilm + d/dweights)",
                     value=n_lat * res * res / (ms * 1e-3), unit="rays/s", ms_per_step=ms, dtype="bf16", scaling="strong",
-                    config=dict(workload="pi-GAN generator-side gradient step, latents sharded over ranks, coarse pass bf16 inference, fine pass "
-                                         "layer-wise forward + CUDA reverse mode with bf16 tcgen05 GEMMs (FiLM d gamma / d beta and weight gradients)"),
+                    config=dict(workload="pi-GAN generator-side gradient step, latents sharded over ranks, coarse pass bf16 inference (no gradient), fine pass "
+                                         "on the fused tcgen05 training path for all latents in one launch sequence (bf16 tile + cosine checkpoints, "
+                                         "fused dgrad, MN-major wgrad on the FiLM-folded weights, unfold into d gamma / d beta / d weights)"),
                     tflops=rows * 1053696 * 3 / (ms * 1e-3) / 1e12)
     elif config == "pigan":
         n_lat, res, s_ = 64, 128, 24

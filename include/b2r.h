@@ -164,10 +164,16 @@ int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* packed_out, v
 size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows);
 int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows, const float* raw, const float* d_raw,
                          const void* saved, void* scratch, size_t scratch_bytes, float* d_params, void* stream);
-int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, void* packed_out, void* stream);
-int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, long long rows, const float* raw,
-                              const float* d_raw, const void* saved, void* scratch, size_t scratch_bytes, float* d_folded,
-                              float* d_params, float* d_film, void* stream);
+/* FiLM-SIREN, B latents in one launch sequence (Generator.forward's loop WITH gradients, pi_GAN/modules.py:176-184 +
+ * pi_GAN/train.py:134): packed = B images from b2r_mlp_tc_pack_film_batched, rows [b*rows_per_latent, (b+1)*rows_per_latent)
+ * belong to latent b (rows_per_latent a multiple of 512); film [B,9,512]; packed_bwd = B images from b2r_mlp_tc_pack_bwd_film;
+ * d_folded: B * B2R_FILM_NUMEL floats; d_film [B,9,512]; d_params sums over the latents.  n_latents = 1: rows_per_latent ignored. */
+int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in,
+                                      float* raw_out, void* saved, size_t saved_bytes, void* stream);
+int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, int n_latents, void* packed_out, void* stream);
+int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, int n_latents, long long rows_per_latent,
+                              long long rows, const float* raw, const float* d_raw, const void* saved, void* scratch,
+                              size_t scratch_bytes, float* d_folded, float* d_params, float* d_film, void* stream);
 
 /* ---- fused Adam on a flat fp32 bucket ----------- optimizer.step() + LR decay, nerf/train_nerf.py:168-175 ----------
  * torch.optim.Adam semantics (no weight decay / amsgrad) on n contiguous floats; grads are multiplied by grad_scale first
@@ -183,7 +189,7 @@ int b2r_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * One launch for B latents.  packed: B images of b2r_mlp_tc_packed_bytes(B2R_MODEL_FILM) bytes one after the other, made by
  * b2r_mlp_tc_pack_film_batched from film[B,9,512] (the FiLM scale / shift are folded into each latent's bf16 weights).
  * Rows [b*rows_per_latent, (b+1)*rows_per_latent) of the input are evaluated with latent b; rows_per_latent must be a
- * multiple of 256. */
+ * multiple of 512 (the two 256-row tiles of a CTA pair share one set of weights). */
 int b2r_mlp_tc_pack_film_batched(const float* params, const float* film, int use_dir, int n_latents, void* packed_out, void* stream);
 int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in, float* raw_out,
                                 int sigma_only, void* stream);

@@ -477,7 +477,7 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h
 //
 // Batched mode (Generator.forward's latent loop in one launch, pi_GAN/modules.py:176-184): n_latents > 1 packed images one
 // after the other (b2r_mlp_tc_pack_film_batched); rows [b * rows_per_latent, (b+1) * rows_per_latent) belong to latent b
-// (rows_per_latent is a multiple of the 256-row tile); the producer streams the tile's latent's weights and the epilogue
+// (rows_per_latent is a multiple of the 512 rows of a CTA pair, which shares one set of weights); the producer streams the tile's latent's weights and the epilogue
 // warps reload the small fp32 tables when their next tile is another latent's.
 // kSave = training forward (one latent): tiles + cosine checkpoints for the reverse mode, as in siren_tc_kernel<true>.
 template <bool kSave>
@@ -798,8 +798,9 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
     int rc = check_mlp_input(in);
     if (rc) return rc;
     long long rows = row_count(in);
-    B2R_CHECK_ARG(rows_per_latent > 0 && rows_per_latent % tc::kRowsTile == 0,
-                  "b2r_mlp_tc_fwd_film_batched: rows_per_latent (%lld) must be a positive multiple of %d", rows_per_latent, tc::kRowsTile);
+    // a CTA pair (2 x 256 rows) shares one set of weights: both of its tiles must belong to the same latent
+    B2R_CHECK_ARG(rows_per_latent > 0 && rows_per_latent % (2 * tc::kRowsTile) == 0,
+                  "b2r_mlp_tc_fwd_film_batched: rows_per_latent (%lld) must be a positive multiple of %d", rows_per_latent, 2 * tc::kRowsTile);
     B2R_CHECK_ARG(n_latents >= 1 && rows <= rows_per_latent * (long long)n_latents, "b2r_mlp_tc_fwd_film_batched: %lld rows need more than %d latents", rows, n_latents);
     if (rows == 0) return 0;
     unsigned grid = 0;
@@ -811,6 +812,30 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
     tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only,
                                                                                             (float4*)raw_out, n_latents, rows_per_latent, nullptr);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd_film_batched");
+    return 0;
+}
+
+extern "C" int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in,
+                                                 float* raw_out, void* saved, size_t saved_bytes, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(packed && raw_out && saved, "b2r_mlp_tc_train_fwd_film_batched: NULL pointer");
+    B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out | (uintptr_t)saved) & 15) == 0, "b2r_mlp_tc_train_fwd_film_batched: buffers must be 16-byte aligned");
+    int rc = check_mlp_input(in);
+    if (rc) return rc;
+    long long rows = row_count(in);
+    B2R_CHECK_ARG(rows_per_latent > 0 && rows_per_latent % (2 * tc::kRowsTile) == 0,
+                  "b2r_mlp_tc_train_fwd_film_batched: rows_per_latent (%lld) must be a positive multiple of %d", rows_per_latent, 2 * tc::kRowsTile);
+    B2R_CHECK_ARG(n_latents >= 1 && rows <= rows_per_latent * (long long)n_latents, "b2r_mlp_tc_train_fwd_film_batched: %lld rows need more than %d latents", rows, n_latents);
+    B2R_CHECK_ARG(saved_bytes >= b2r_mlp_tc_train_saved_bytes(B2R_MODEL_FILM, rows), "b2r_mlp_tc_train_fwd_film_batched: saved buffer too small (%zu B)", saved_bytes);
+    if (rows == 0) return 0;
+    unsigned grid = 0;
+    rc = tc::pair_grid(rows, &grid);
+    if (rc) return rc;
+    rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+    if (rc) return rc;
+    tc::film_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, 0,
+                                                                                           (float4*)raw_out, n_latents, rows_per_latent, (uint8_t*)saved);
+    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd_film_batched");
     return 0;
 }
 

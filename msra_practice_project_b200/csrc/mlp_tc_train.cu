@@ -385,7 +385,8 @@ __device__ __forceinline__ bool wpiece(int u, long long n_sub, long long lo, lon
 
 template <int KIND>
 __global__ void __launch_bounds__(kWThreads, 1)
-nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub, float* __restrict__ d_params) {
+nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ scratch, long long n_sub, float* __restrict__ d_params,
+                     long long t_begin, long long t_count) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t full = smem + kWBarOff, empty = full + 8 * kWStages, acc_full = empty + 8 * kWStages, tmem_empty = acc_full + 8,
@@ -404,7 +405,8 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(slot_addr));
 
-    const long long total = n_sub * wcost_total<KIND>();
+    // the tensors are laid out for n_sub sub-tiles; this launch reduces over sub-tiles [t_begin, t_begin + t_count) (one latent of a batch)
+    const long long total = t_count * wcost_total<KIND>();
     const long long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == 0) {
@@ -413,12 +415,12 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
             long long base = 0;
             for (int u = 0; u < n_wunits<KIND>(); ++u) {
                 WPiece pc;
-                if (!wpiece<KIND>(u, n_sub, lo, hi, base, pc)) continue;
+                if (!wpiece<KIND>(u, t_count, lo, hi, base, pc)) continue;
                 const WUnit un = wunit<KIND>(u);
                 const uint8_t* gsrc = scratch + (size_t)un.g_off * n_sub * kBlk;
                 const uint8_t* xsrc = saved + (size_t)un.x_off * n_sub * kBlk;
                 const uint32_t bytes = (uint32_t)(un.g_nb + un.x_nb) * 8192u;
-                for (long long T = pc.t0; T < pc.t1; ++T) {
+                for (long long T = t_begin + pc.t0; T < t_begin + pc.t1; ++T) {
                     for (int hs = 0; hs < 2; ++hs) {
                         mbar_wait(empty + 8 * stage, phase ^ 1u);
                         mbar_arrive_expect_tx(full + 8 * stage, bytes);
@@ -441,7 +443,7 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
         const uint64_t d_hi = make_desc(0, 8192, 1024, kLayoutSW128);
         for (int u = 0; u < n_wunits<KIND>(); ++u) {
             WPiece pc;
-            if (!wpiece<KIND>(u, n_sub, lo, hi, base, pc)) continue;
+            if (!wpiece<KIND>(u, t_count, lo, hi, base, pc)) continue;
             const WUnit un = wunit<KIND>(u);
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)un.x_nb * 64u) | (1u << 15) | (1u << 16);
             const int n_m = un.g_nb >> 1;
@@ -477,7 +479,7 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
         long long base = 0;
         for (int u = 0; u < n_wunits<KIND>(); ++u) {
             WPiece pc;
-            if (!wpiece<KIND>(u, n_sub, lo, hi, base, pc)) continue;
+            if (!wpiece<KIND>(u, t_count, lo, hi, base, pc)) continue;
             const WUnit un = wunit<KIND>(u);
             const LayerDesc L = wlayer<KIND>(un.layer);
             const bool do_bias = un.bias && w < un.g_nb;
@@ -651,8 +653,11 @@ __host__ __device__ constexpr int fbwd_layer(int s) { return s == 0 ? 9 : 8 - s;
 __host__ __device__ constexpr int fbwd_film_row(int s) { return 8 - s; }
 
 // B[n][k] = 30 gamma_k W[k][n]: n = input feature (output column of dX), k = output feature (the forward's folded row k)
-__global__ void film_pack_bwd_kernel(const float* __restrict__ params, const float* __restrict__ film, uint8_t* __restrict__ packed) {
+// blockIdx.y = latent: film [n_latents][9][512] -> n_latents images of kFilmBwdPackedBytes
+__global__ void film_pack_bwd_kernel(const float* __restrict__ params, const float* __restrict__ film_all, uint8_t* __restrict__ packed_all) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const float* __restrict__ film = film_all + (size_t)blockIdx.y * B2R_FILM_PARAMS;
+    uint8_t* __restrict__ packed = packed_all + (size_t)blockIdx.y * kFilmBwdPackedBytes;
     if (t < kFilmBwdChunkBytes / 16) {
         int s, c, hf, row, grp;
         locate<FilmBwdSched>(t * 16, s, c, hf, row, grp);
@@ -678,7 +683,7 @@ __global__ void film_pack_bwd_kernel(const float* __restrict__ params, const flo
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 film_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const float4* __restrict__ raw, const float4* __restrict__ d_raw,
-                   const uint8_t* __restrict__ saved, uint8_t* __restrict__ scratch) {
+                   const uint8_t* __restrict__ saved, uint8_t* __restrict__ scratch, int n_latents, long long rows_per_latent) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -693,7 +698,11 @@ film_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
     const uint32_t tmem_base = tc_prologue(cx, warp);
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<FilmBwdSched>(cx, packed, pl, FilmBwdSched::kSteps, 0);
+        // batched: rows [b * rows_per_latent, (b+1) * rows_per_latent) use latent b's transposed folded weights (a tile pair never straddles)
+        auto packed_of = [&](long long p) -> const uint8_t* {
+            return packed + (n_latents > 1 ? (size_t)((2 * p * kRowsTile) / rows_per_latent) * kFilmBwdPackedBytes : (size_t)0);
+        };
+        if (lane == 0) producer_loop_fn<FilmBwdSched>(cx, packed_of, pl, FilmBwdSched::kSteps, 0);
     } else if (warp == 1) {
         if (cx.rank == 0) mma_loop<FilmBwdSched>(cx, tmem_base, pl, FilmBwdSched::kSteps, 0);
         else if (lane == 0) relay_loop<FilmBwdSched>(cx, pl, FilmBwdSched::kSteps, 0);
@@ -852,38 +861,35 @@ __global__ void __launch_bounds__(256) film_head_wgrad_kernel(const uint8_t* __r
     }
 }
 
-// folded gradients -> parameter / FiLM gradients.  One warp per (FiLM layer, output feature i); the first CTAs' spare threads
-// add the head gradients.  d_params / d_film are ACCUMULATED into (each element by exactly one thread); either may be NULL.
-__global__ void __launch_bounds__(256) film_grad_finish_kernel(const float* __restrict__ params, const float* __restrict__ film,
-                                                               const float* __restrict__ d_folded, float* __restrict__ d_params,
-                                                               float* __restrict__ d_film) {
+// folded gradients -> parameter / FiLM gradients.  One warp per (FiLM layer, output feature i); blockIdx.y = latent (its film row
+// block, its d_folded, its d_film).  d_params (shared by the latents: float atomics) and d_film are ACCUMULATED into; either may be NULL.
+__global__ void __launch_bounds__(256) film_grad_finish_kernel(const float* __restrict__ params, const float* __restrict__ film_all,
+                                                               const float* __restrict__ d_folded_all, float* __restrict__ d_params,
+                                                               float* __restrict__ d_film_all) {
     const int gw = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-    if (gw < 9 * 256) {
-        const int fl = gw >> 8, i = gw & 255;
-        const LayerDesc L = film_layer(fl == 8 ? 9 : fl, true);
-        const float gsc = 30.0f * film[fl * 512 + i];
-        const float* __restrict__ w = params + L.w_off + (long long)i * L.in;
-        const float* __restrict__ dwp = d_folded + L.w_off + (long long)i * L.in;
-        float acc = 0.f;
-        for (int j = lane; j < L.in; j += 32) {
-            const float d = dwp[j];
-            acc = fmaf(w[j], d, acc);
-            if (d_params) d_params[L.w_off + (long long)i * L.in + j] += gsc * d;
+    if (gw >= 9 * 256) return;
+    const float* __restrict__ film = film_all + (size_t)blockIdx.y * B2R_FILM_PARAMS;
+    const float* __restrict__ d_folded = d_folded_all + (size_t)blockIdx.y * B2R_FILM_NUMEL;
+    const int fl = gw >> 8, i = gw & 255;
+    const LayerDesc L = film_layer(fl == 8 ? 9 : fl, true);
+    const float gsc = 30.0f * film[fl * 512 + i];
+    const float* __restrict__ w = params + L.w_off + (long long)i * L.in;
+    const float* __restrict__ dwp = d_folded + L.w_off + (long long)i * L.in;
+    float acc = 0.f;
+    for (int j = lane; j < L.in; j += 32) {
+        const float d = dwp[j];
+        acc = fmaf(w[j], d, acc);
+        if (d_params) atomicAdd(d_params + L.w_off + (long long)i * L.in + j, gsc * d);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        const float ds = d_folded[L.b_off + i];
+        if (d_params) atomicAdd(d_params + L.b_off + i, gsc * ds);
+        if (d_film_all) {
+            float* __restrict__ d_film = d_film_all + (size_t)blockIdx.y * B2R_FILM_PARAMS;
+            d_film[fl * 512 + i] += 30.0f * fmaf(params[L.b_off + i], ds, acc);
+            d_film[fl * 512 + 256 + i] += 30.0f * ds;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float ds = d_folded[L.b_off + i];
-            if (d_params) d_params[L.b_off + i] += gsc * ds;
-            if (d_film) {
-                d_film[fl * 512 + i] += 30.0f * fmaf(params[L.b_off + i], ds, acc);
-                d_film[fl * 512 + 256 + i] += 30.0f * ds;
-            }
-        }
-    } else if (d_params) {
-        const int t = (gw - 9 * 256) * 32 + lane;          // head parameters: plain gradients
-        const LayerDesc Ls = film_layer(8, true), Lc = film_layer(10, true);
-        if (t < 257) d_params[Ls.w_off + t] += d_folded[Ls.w_off + t];                  // w_sigma[256], b_sigma
-        else if (t < 257 + 771) d_params[Lc.w_off + (t - 257)] += d_folded[Lc.w_off + (t - 257)];   // w_rgb[3][256], b_rgb[3]
     }
 }
 
@@ -899,12 +905,15 @@ extern "C" size_t b2r_mlp_tc_bwd_packed_bytes(int model_kind) {
     return train_kind(model_kind) ? (size_t)b2r::tc::kBwdPackedBytes : 0;
 }
 
-extern "C" int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, void* packed_out, void* stream) {
+extern "C" int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, int n_latents, void* packed_out, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(params && film && packed_out, "b2r_mlp_tc_pack_bwd_film: NULL pointer");
     B2R_CHECK_ARG(((uintptr_t)packed_out & 15) == 0, "b2r_mlp_tc_pack_bwd_film: packed_out must be 16-byte aligned");
+    B2R_CHECK_ARG(n_latents >= 0 && n_latents <= 65535, "b2r_mlp_tc_pack_bwd_film: n_latents out of range");
+    if (n_latents == 0) return 0;
     long long threads = tc::kFilmBwdChunkBytes / 16;
-    tc::film_pack_bwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, film, (uint8_t*)packed_out);
+    tc::film_pack_bwd_kernel<<<dim3((unsigned)((threads + 255) / 256), (unsigned)n_latents), 256, 0, (cudaStream_t)stream>>>(params, film,
+                                                                                                                            (uint8_t*)packed_out);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_pack_bwd_film");
     return 0;
 }
@@ -952,7 +961,7 @@ static int train_bwd_launch(const void* packed_bwd, long long rows, const float*
     if (rc) return rc;
     const long long work = n_sub * tc::kWUnits;
     unsigned wgrid = (unsigned)(work < sms ? work : sms);
-    tc::nerf_tc_wgrad_kernel<kSiren ? tc::kKSiren : tc::kKNerf><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params);
+    tc::nerf_tc_wgrad_kernel<kSiren ? tc::kKSiren : tc::kKNerf><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params, 0, n_sub);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (wgrad)");
     unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
     tc::nerf_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params,
@@ -976,18 +985,20 @@ extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long
     return train_bwd_launch<false>(packed_bwd, rows, raw, d_raw, saved, scratch, d_params, (cudaStream_t)stream);
 }
 
-extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, long long rows, const float* raw,
-                                         const float* d_raw, const void* saved, void* scratch, size_t scratch_bytes, float* d_folded,
-                                         float* d_params, float* d_film, void* stream) {
+extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, int n_latents, long long rows_per_latent,
+                                         long long rows, const float* raw, const float* d_raw, const void* saved, void* scratch,
+                                         size_t scratch_bytes, float* d_folded, float* d_params, float* d_film, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(packed_bwd && params && film && raw && d_raw && saved && scratch && d_folded, "b2r_mlp_tc_train_bwd_film: NULL pointer");
     B2R_CHECK_ARG((((uintptr_t)packed_bwd | (uintptr_t)raw | (uintptr_t)d_raw | (uintptr_t)saved | (uintptr_t)scratch | (uintptr_t)d_folded) & 15) == 0,
                   "b2r_mlp_tc_train_bwd_film: buffers must be 16-byte aligned");
-    B2R_CHECK_ARG(rows >= 0, "b2r_mlp_tc_train_bwd_film: negative row count");
+    B2R_CHECK_ARG(rows >= 0 && n_latents >= 1 && n_latents <= 65535, "b2r_mlp_tc_train_bwd_film: bad row / latent count");
+    B2R_CHECK_ARG(n_latents == 1 || (rows_per_latent > 0 && rows_per_latent % (2 * tc::kRowsTile) == 0 && rows <= rows_per_latent * (long long)n_latents),
+                  "b2r_mlp_tc_train_bwd_film: rows_per_latent (%lld) must be a positive multiple of %d covering all rows", rows_per_latent, 2 * tc::kRowsTile);
     B2R_CHECK_ARG(scratch_bytes >= b2r_mlp_tc_train_scratch_bytes(B2R_MODEL_FILM, rows), "b2r_mlp_tc_train_bwd_film: scratch too small (%zu B)", scratch_bytes);
     if (rows == 0 || (!d_params && !d_film)) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = cuda_result(cudaMemsetAsync(d_folded, 0, (size_t)B2R_FILM_NUMEL * sizeof(float), st), "cudaMemsetAsync(d_folded)");
+    int rc = cuda_result(cudaMemsetAsync(d_folded, 0, (size_t)n_latents * B2R_FILM_NUMEL * sizeof(float), st), "cudaMemsetAsync(d_folded)");
     if (rc) return rc;
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
@@ -995,7 +1006,7 @@ extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* pa
     rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc bwd smem attribute");
     if (rc) return rc;
     tc::film_tc_bwd_kernel<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed_bwd, rows, (const float4*)raw, (const float4*)d_raw,
-                                                                      (const uint8_t*)saved, (uint8_t*)scratch);
+                                                                      (const uint8_t*)saved, (uint8_t*)scratch, n_latents, rows_per_latent);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (dgrad)");
     const long long n_sub = tc::n_sub_tiles(rows);
     int dev = 0, sms = 0;
@@ -1005,18 +1016,25 @@ extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* pa
     if (rc) return rc;
     rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel<tc::kKFilm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
     if (rc) return rc;
-    const long long work = n_sub * tc::n_wunits<tc::kKFilm>();
-    unsigned wgrid = (unsigned)(work < sms ? work : sms);
-    tc::nerf_tc_wgrad_kernel<tc::kKFilm><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_folded);
-    B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (wgrad)");
-    if (d_params) {
+    // one wgrad launch per latent over its own sub-tiles (the folded weights, hence their gradients, are per latent)
+    const long long sub_per_latent = n_latents > 1 ? rows_per_latent / tc::kRowsSub : n_sub;
+    for (int b = 0; b < n_latents; ++b) {
+        const long long t0 = (long long)b * sub_per_latent;
+        const long long tn = (t0 + sub_per_latent <= n_sub ? sub_per_latent : n_sub - t0);
+        if (tn <= 0) break;
+        const long long work = tn * tc::n_wunits<tc::kKFilm>();
+        unsigned wgrid = (unsigned)(work < sms ? work : sms);
+        tc::nerf_tc_wgrad_kernel<tc::kKFilm><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub,
+                                                                                       d_folded + (size_t)b * B2R_FILM_NUMEL, t0, tn);
+        B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (wgrad)");
+    }
+    if (d_params) {    // the heads are not FiLM-folded: plain gradients straight into d_params
         unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
-        tc::film_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_folded, film_layer(8, true),
+        tc::film_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params, film_layer(8, true),
                                                           film_layer(10, true));
         B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (heads)");
     }
-    const int warps = 9 * 256 + (257 + 771 + 31) / 32;
-    tc::film_grad_finish_kernel<<<(warps + 7) / 8, 256, 0, st>>>(params, film, d_folded, d_params, d_film);
+    tc::film_grad_finish_kernel<<<dim3(9 * 256 / 8, (unsigned)n_latents), 256, 0, st>>>(params, film, d_folded, d_params, d_film);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (finish)");
     return 0;
 }

@@ -83,13 +83,17 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
     film_params[B,9,512], poses[B,4,4] -> images [B,3,H,W].  This is the latent-sharding unit for
     multi-GPU runs (each rank renders its slice of B).
 
-    Without gradients and with the bf16 tensor-core MLP the B latents are rendered by ONE launch sequence (rays of all poses,
-    one batched MLP launch per pass with per-latent FiLM tables); otherwise latent by latent through render_image."""
+    With the bf16 tensor-core MLP the B latents are rendered by ONE launch sequence (rays of all poses, one batched MLP launch
+    per pass with per-latent FiLM tables) -- also WITH gradients (pi_GAN/train.py:134: the fine pass runs on the fused
+    training path for all latents at once, the coarse pass carries no gradient as in render_image); otherwise latent by
+    latent through render_image."""
     b = film_params.shape[0]
     w, h, sc, sf = int(width), int(height), int(coarse_sample_num), int(fine_sample_num)
     used = precision or ops.get_mlp_precision()
-    batched = (not torch.is_grad_enabled() or not _needs_grad(model, film_params)) and used == "bf16" and b > 0 \
-        and (w * h * sc) % 256 == 0 and (w * h * (sc + sf)) % 256 == 0
+    grad = torch.is_grad_enabled() and _needs_grad(model, film_params)
+    net = model.module if isinstance(model, torch.nn.DataParallel) else model
+    grad_ok = ops.get_grad_precision() in ("auto", "bf16") and bool(getattr(net, "use_dir", True)) and isinstance(film_params, torch.Tensor)
+    batched = (not grad or grad_ok) and used == "bf16" and b > 0 and (w * h * sc) % 512 == 0 and (w * h * (sc + sf)) % 512 == 0
     if not batched:
         imgs = []
         for i in range(b):
@@ -113,8 +117,13 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
         raw = ops.mlp_film_batched(model, film, rays, z, n * sc)
         _, _, _, wts, _ = ops.composite_forward(raw, z, rays[:, 1], True)
         z_f = ops.sample_pdf(mids, wts[:, 1:-1], sf, u=u, z_coarse=z, want_samples=False)["sorted"]
-        raw_f = ops.mlp_film_batched(model, film, rays, z_f, n * (sc + sf))
-        rgb, _, _, _, _ = ops.composite_forward(raw_f, z_f, rays[:, 1], False)
+        if not grad:
+            raw_f = ops.mlp_film_batched(model, film, rays, z_f, n * (sc + sf))
+            rgb, _, _, _, _ = ops.composite_forward(raw_f, z_f, rays[:, 1], False)
+    if grad:
+        film_g = film_params.to(dev).reshape(b, 9, 512)
+        raw_f = ops.mlp_film_batched_train(model, film_g, rays, z_f, n * (sc + sf))
+        rgb = ops.composite(raw_f, z_f, rays[:, 1], False)[0]
     return rgb.reshape(b, h, w, 3).permute(0, 3, 1, 2).contiguous()
 
 

@@ -1125,3 +1125,38 @@ def test_film_siren_fused_training_path(rows_shape):
     rel = (film.grad - res["bf16"][1]["film"]).norm().item() / max(res["bf16"][1]["film"].norm().item(), 1e-20)
     assert rel < 1e-3, rel                  # float atomics: the summation order differs between runs
     print("FiLM-SIREN fused training path (%d x %d rows): worst relative gradient error %.3g vs fp32" % (n, s, worst))
+
+
+def test_pigan_render_batch_with_gradients_matches_per_latent_loop():
+    """render_batch with autograd on (pi_GAN/train.py:134: Generator.forward's latent loop + loss.backward()): all latents go
+    through ONE fused training forward / dgrad launch with per-latent folded weights, one wgrad launch per latent and the
+    unfold kernel -- images bit-identical to the per-latent loop, d film[B,9,512] and the weight gradients equal up to the
+    summation order of the float atomics."""
+    torch.manual_seed(0)
+    net = models.FilmSirenNeRF().cuda()
+    g = torch.Generator().manual_seed(4)
+    b, res, s_ = 3, 32, 8                                     # 32*32*16 = 16384 fine rows per latent
+    film = torch.cat([1.0 + 0.2 * torch.randn(b, 9, 256, generator=g), 0.1 * torch.randn(b, 9, 256, generator=g)], -1).cuda().requires_grad_(True)
+    poses = [pigan_render.camera_pos_to_transform_matrix(1, 0.3 * np.sin(i), 0.15 * np.cos(i)) for i in range(b)]
+    focal = np.float64(res / 2 / np.tan(6 * np.pi / 180))
+    t = torch.rand(b, res * res, s_, generator=g).cuda()
+    target = torch.rand(b, 3, res, res, generator=g).cuda()
+    imgs = pigan_render.render_batch(net, film, poses, res, res, focal, 0.5, 1.5, s_, s_, t_rand=t)
+    ((imgs - target) ** 2).mean().backward()
+    got = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    got["film"] = film.grad.detach().clone()
+    net.zero_grad(set_to_none=True)
+    film.grad = None
+    loop = []
+    for i in range(b):
+        net.set_film_params(film[i])
+        loop.append(pigan_render.render_image(res, res, focal, poses[i], 0.5, 1.5, net, net, s_, s_, t_rand=t[i]))
+    loop = torch.stack(loop).permute(0, 3, 1, 2)
+    ((loop - target) ** 2).mean().backward()
+    assert torch.equal(imgs.detach(), loop.detach()), (imgs - loop).abs().max().item()
+    ref = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+    ref["film"] = film.grad.detach().clone()
+    for k in ref:
+        rel = (ref[k] - got[k]).norm().item() / max(ref[k].norm().item(), 1e-20)
+        assert rel < 1e-3, (k, rel)
+    assert got["film"].abs().sum(dim=(1, 2)).min().item() > 0          # every latent received its own d film
