@@ -91,6 +91,13 @@ int b2r_sample_pdf(const float* bins, long long bins_stride, const float* weight
                    const float* u, long long n_rays, int nb, int n_fine,
                    const float* z_coarse, int n_coarse,
                    float* samples_out, float* sorted_out, float* cdf_out, void* stream);
+/* b2r_sample_pdf runs instantiations with compile-time sizes for the shapes of BASELINE.json's configs (64+128, 64+64,
+ * 24+24) and the run-time-size kernel otherwise; b2r_sample_pdf_generic forces the latter (same arguments, bit-identical
+ * results: the parity tests compare the two). */
+int b2r_sample_pdf_generic(const float* bins, long long bins_stride, const float* weights, long long w_stride,
+                        const float* u, long long n_rays, int nb, int n_fine,
+                        const float* z_coarse, int n_coarse,
+                        float* samples_out, float* sorted_out, float* cdf_out, void* stream);
 
 /* ---- K3: radiance-field MLP --- run_network nerf/render.py:59-75 + NeRF.forward nerf/nerf.py:75-94
  *                                 + FilmSirenNeRF.forward pi_GAN/modules.py:101-118 ------------

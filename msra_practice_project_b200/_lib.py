@@ -37,6 +37,8 @@ SIGNATURES = {
                                     c_float_p, c_float_p, C.c_void_p]),
     "b2r_sample_pdf": (C.c_int, [c_float_p, c_ll, c_float_p, c_ll, c_float_p, c_ll, C.c_int, C.c_int, c_float_p, C.c_int,
                                  c_float_p, c_float_p, c_float_p, C.c_void_p]),
+    "b2r_sample_pdf_generic": (C.c_int, [c_float_p, c_ll, c_float_p, c_ll, c_float_p, c_ll, C.c_int, C.c_int, c_float_p, C.c_int,
+                                 c_float_p, c_float_p, c_float_p, C.c_void_p]),
     "b2r_mlp_f32_workspace_bytes": (C.c_size_t, [C.c_int, c_ll, C.c_int]),
     "b2r_mlp_f32_fwd": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_void_p,
                                   C.c_size_t, C.c_int, C.c_int, C.c_void_p]),

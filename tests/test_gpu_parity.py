@@ -1160,3 +1160,53 @@ def test_pigan_render_batch_with_gradients_matches_per_latent_loop():
         rel = (ref[k] - got[k]).norm().item() / max(ref[k].norm().item(), 1e-20)
         assert rel < 1e-3, (k, rel)
     assert got["film"].abs().sum(dim=(1, 2)).min().item() > 0          # every latent received its own d film
+
+
+@pytest.mark.parametrize("shape", [(40000, 63, 128, 64, False), (33000, 23, 24, 24, True), (5000, 63, 64, 64, False), (3000, 31, 37, 18, False),
+                                   (2000, 2, 5, 3, True)])
+def test_sample_pdf_specialised_kernels_bit_identical_to_generic(shape):
+    """b2r_sample_pdf runs instantiations with compile-time sizes for the BASELINE shapes (64+128, 64+64, 24+24): samples,
+    merged rows and CDF must be bit-identical to the run-time-size kernel (b2r_sample_pdf_generic) on the same inputs --
+    peaked / flat / zero weights, shared and per-ray bins, odd row lengths (both entries run the generic kernel there) -- and,
+    given the kernel's CDF, to the oracle's searchsorted + lerp (north_star: indices bit-exact given identical CDFs)."""
+    from msra_practice_project_b200._lib import lib, check
+    n, nb, sf, sc, per_ray_bins = shape
+    g = torch.Generator().manual_seed(nb * 1000 + sf)
+    w_full = torch.rand(n, nb + 1, generator=g) ** 8                      # peaked, like compositing weights
+    w_full[::7] = 0.0                                                    # all-zero rows: uniform pdf, denom clamp
+    w_full[1::11, : nb // 2] = 0.0
+    w_full = w_full.cuda()
+    w = w_full[:, 1:-1] if nb > 2 else w_full[:, 1:2]                    # strided view, pointer + 1 (render_rays' weights[:, 1:-1])
+    if per_ray_bins:
+        bins = (torch.sort(torch.rand(n, nb, generator=g), -1).values * 4 + 2).cuda()
+        b_stride = nb
+    else:
+        bins = torch.linspace(2.1, 5.9, nb).cuda()
+        b_stride = 0
+    u = torch.linspace(0.0, 1.0, sf, device="cpu").cuda()
+    zc = (torch.sort(torch.rand(n, sc, generator=g), -1).values * 4 + 2).cuda()
+    if not per_ray_bins:
+        zc = zc.clamp(min=2.1)                                           # ties between coarse and fine entries (u = 0 -> bins[0] = 2.1)
+    outs = {}
+    for name in ("b2r_sample_pdf", "b2r_sample_pdf_generic"):
+        samples = torch.full((n, sf), -1.0, device="cuda")
+        merged = torch.full((n, sc + sf), -1.0, device="cuda")
+        cdf = torch.full((n, nb), -1.0, device="cuda")
+        fn = getattr(lib(), name)
+        check(fn(bins.data_ptr(), b_stride, w.data_ptr(), w.stride(0), u.data_ptr(), n, nb, sf, zc.data_ptr(), sc, samples.data_ptr(),
+                 merged.data_ptr(), cdf.data_ptr(), torch.cuda.current_stream().cuda_stream), name)
+        # merge only (the render path's call: no samples / cdf output)
+        merged2 = torch.full((n, sc + sf), -1.0, device="cuda")
+        check(fn(bins.data_ptr(), b_stride, w.data_ptr(), w.stride(0), u.data_ptr(), n, nb, sf, zc.data_ptr(), sc, None, merged2.data_ptr(), None,
+                 torch.cuda.current_stream().cuda_stream), name)
+        torch.cuda.synchronize()
+        assert torch.equal(merged, merged2)
+        outs[name] = (samples, merged, cdf)
+    a, b = outs["b2r_sample_pdf"], outs["b2r_sample_pdf_generic"]
+    assert torch.equal(a[2], b[2]), "cdf"
+    assert torch.equal(a[0], b[0]), "samples"
+    assert torch.equal(a[1], b[1]), "merged"
+    assert torch.equal(a[1], torch.sort(torch.cat([zc, a[0]], -1), -1).values)
+    sub = slice(0, 512)
+    ref, _ = orc.sample_pdf_from_cdf(bins[sub].cpu().numpy() if per_ray_bins else bins.cpu().numpy(), a[2][sub].cpu().numpy(), u.cpu().numpy())
+    assert np.array_equal(a[0][sub].cpu().numpy(), ref)
