@@ -205,6 +205,103 @@ class FilmSirenNeRF(torch.nn.Module):
         return ops.mlp_points(self, x)
 
 
+class MappingNetwork(torch.nn.Module):
+    """z -> film_params[B,9,512] (gamma || beta per FiLM layer); module names, creation order (= RNG consumption) and the
+    gamma = 1 / beta = 0 head-bias init of pi_GAN/modules.py:34-68.  B x 256 GEMMs: stays on cuBLAS; the
+    nine heads run as ONE GEMM on the concatenated weights."""
+
+    def __init__(self, input_dim=256, output_dim=256, output_layers=8, hidden_dim=256, hidden_layers=3):
+        super().__init__()
+        self.input_layer = torch.nn.Sequential(torch.nn.Linear(input_dim, hidden_dim), torch.nn.LeakyReLU(0.2))
+        hidden = []
+        for _ in range(hidden_layers - 1):
+            hidden += [torch.nn.Linear(hidden_dim, hidden_dim), torch.nn.LeakyReLU(0.2)]
+        self.hidden_layers = torch.nn.Sequential(*hidden)
+        heads = [torch.nn.Linear(hidden_dim, 2 * output_dim) for _ in range(output_layers + 1)]
+        with torch.no_grad():
+            for head in heads:
+                head.bias[:output_dim] = 1
+                head.bias[output_dim:] = 0
+        self.output_layers = torch.nn.ModuleList(heads)
+
+    def forward(self, input_tensor):
+        h = self.hidden_layers(self.input_layer(input_tensor))
+        w = torch.cat([head.weight for head in self.output_layers])
+        b = torch.cat([head.bias for head in self.output_layers])
+        return torch.nn.functional.linear(h, w, b).reshape(h.shape[0], len(self.output_layers), -1)
+
+
+class Renderer:
+    """Camera / sampling settings + the render call of pi_GAN/modules.py:120-161 (poses drawn with np.random like the reference)."""
+
+    def __init__(self, width, height, near=0.1, far=1.9, fov=12, coarse_samples=64, fine_samples=128, horizontal_std=0.3,
+                 vertical_std=0.15):
+        self.width, self.height, self.fov = width, height, fov
+        self.focal = width / 2 / np.tan(fov / 2 * np.pi / 180)
+        self.near, self.far = near, far
+        self.coarse_samples, self.fine_samples = coarse_samples, fine_samples
+        self.horizontal_std, self.vertical_std = horizontal_std, vertical_std
+
+    def set_params(self, width=None, height=None, near=None, far=None, fov=None, coarse_samples=None, fine_samples=None,
+                   horizontal_std=None, vertical_std=None):
+        refocus = width is not None or fov is not None
+        for name, v in (("width", width), ("height", height), ("near", near), ("far", far), ("fov", fov), ("coarse_samples", coarse_samples),
+                        ("fine_samples", fine_samples), ("horizontal_std", horizontal_std), ("vertical_std", vertical_std)):
+            if v is not None:
+                setattr(self, name, v)
+        if refocus:
+            self.focal = self.width / 2 / np.tan(self.fov / 2 * np.pi / 180)
+
+    def draw_pose(self, theta=None, phi=None):
+        """(theta, phi) ~ N(0, std) in the reference's draw order (theta first), then the camera matrix."""
+        from . import pigan_render
+        theta = np.random.randn() * self.horizontal_std if theta is None else theta
+        phi = np.random.randn() * self.vertical_std if phi is None else phi
+        return pigan_render.camera_pos_to_transform_matrix(1, theta, phi)
+
+    def __call__(self, model, theta=None, phi=None):
+        from . import pigan_render
+        return pigan_render.render_image(self.width, self.height, self.focal, self.draw_pose(theta, phi), self.near, self.far, model, model,
+                                         self.coarse_samples, self.fine_samples)
+
+
+class Generator(torch.nn.Module):
+    """pi-GAN generator (pi_GAN/modules.py:164-197): same constructor, sub-module names and state-dict keys.  forward() maps
+    z[B,input_dim] to film_params and renders ALL B latents through pigan_render.render_batch -- one launch sequence, with the
+    autograd graph to the FiLM-SIREN weights and, through film_params, to the mapping network -- instead of the reference's
+    per-latent Python loop; poses and jitter are drawn in the reference's order."""
+
+    def __init__(self, input_dim, output_size, near=0.1, far=1.9, fov=12, coarse_samples=64, fine_samples=128, horizontal_std=0.3,
+                 vertical_std=0.15, use_dir=True):
+        super().__init__()
+        self.input_dim = input_dim
+        self.film_siren_nerf = FilmSirenNeRF(use_dir=use_dir)
+        self.mapping_network = MappingNetwork(input_dim=input_dim)
+        self.renderer = Renderer(output_size, output_size, near, far, fov, coarse_samples, fine_samples, horizontal_std, vertical_std)
+
+    def forward(self, input_tensor, *, poses=None, t_rand=None, precision=None):
+        """poses / t_rand[B, H*W, coarse_samples] / precision: keyword-only additions (parity runs pass the jitter tensor)."""
+        from . import pigan_render
+        film_params = self.mapping_network(input_tensor)
+        r = self.renderer
+        if poses is None:
+            poses = [r.draw_pose() for _ in range(film_params.shape[0])]
+        return pigan_render.render_batch(self.film_siren_nerf, film_params, poses, r.width, r.height, r.focal, r.near, r.far,
+                                         r.coarse_samples, r.fine_samples, t_rand=t_rand, precision=precision)
+
+    def get_mapping(self, input_tensor):
+        return self.mapping_network(input_tensor)
+
+    def set_film_params(self, film_params):
+        self.film_siren_nerf.set_film_params(film_params)
+
+    def set_resolution(self, resolution):
+        self.renderer.set_params(width=resolution, height=resolution)
+
+    def render(self, theta=None, phi=None):
+        return self.renderer(self.film_siren_nerf, theta, phi)
+
+
 def damp_nerf_(model: NeRF) -> NeRF:
     """'Trained-like' 1/f synthetic field used for end-to-end parity: scale the
     posenc band i columns by 2^-i, sigma head x8, sigma bias -1."""

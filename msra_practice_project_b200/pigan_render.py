@@ -89,6 +89,8 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
     latent through render_image."""
     b = film_params.shape[0]
     w, h, sc, sf = int(width), int(height), int(coarse_sample_num), int(fine_sample_num)
+    if next(model.parameters()).device.type != "cuda":
+        raise RuntimeError("model parameters must live on a CUDA device: the B200 render path has no CPU fallback")
     used = precision or ops.get_mlp_precision()
     grad = torch.is_grad_enabled() and _needs_grad(model, film_params)
     net = model.module if isinstance(model, torch.nn.DataParallel) else model

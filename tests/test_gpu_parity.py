@@ -1210,3 +1210,40 @@ def test_sample_pdf_specialised_kernels_bit_identical_to_generic(shape):
     sub = slice(0, 512)
     ref, _ = orc.sample_pdf_from_cdf(bins[sub].cpu().numpy() if per_ray_bins else bins.cpu().numpy(), a[2][sub].cpu().numpy(), u.cpu().numpy())
     assert np.array_equal(a[0][sub].cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_generator_forward_backward_vs_reference(golden, mode):
+    """models.Generator.forward (pi_GAN/modules.py:176-184 + train.py:134) against the unmodified reference's Generator on the
+    same z, poses (np.random.seed(3)) and jitter: image and the gradient of an image loss with respect to EVERY parameter of
+    the FiLM-SIREN field and of the mapping network (which receives d film[B,9,512] from the renderer).  fp32: the exact
+    per-latent path (1e-4 on the image); bf16: all latents in one fused launch sequence (2e-2 on the image)."""
+    gg = golden.generator
+    torch.manual_seed(0)
+    gen = models.Generator(256, 8, near=0.5, far=1.5, fov=12, coarse_samples=8, fine_samples=8).cuda()
+    z, target, t_rand = cu(gg["z"]), cu(gg["target"]), cu(gg["t_rand"])
+    old_g = ops.set_grad_precision(mode)
+    try:
+        np.random.seed(3)
+        img = gen(z, t_rand=t_rand, precision=mode)
+        loss = ((img - target) ** 2).mean()
+        loss.backward()
+    finally:
+        ops.set_grad_precision(old_g)
+    err = (img.detach().cpu().numpy() - gg["img"])
+    tol = 1e-4 if mode == "fp32" else 2e-2
+    assert np.abs(err).max() < tol, np.abs(err).max()
+    assert abs(float(loss.detach()) - float(gg["loss"])) < (1e-5 if mode == "fp32" else 2e-3)
+    worst = 0.0
+    for name, p in gen.named_parameters():
+        assert p.grad is not None, name
+        g = p.grad.detach().reshape(-1).double().cpu()
+        ref_l2, ref_s = float(gg[f"g.{name}.l2"]), gg[f"g.{name}.sample"].astype(np.float64)
+        got_s = g[::53].numpy()
+        rel = np.linalg.norm(got_s - ref_s) / max(np.linalg.norm(ref_s), 1e-20)
+        worst = max(worst, rel)
+        if mode == "fp32":
+            assert abs(float(g.norm()) - ref_l2) <= 2e-2 * ref_l2 + 1e-9 and rel < 2e-2, (name, rel, float(g.norm()), ref_l2)
+        else:       # 128 rays: bf16 rounding is not averaged out (cf. test_film_siren_fused_training_path)
+            assert abs(float(g.norm()) - ref_l2) <= 0.3 * ref_l2 + 1e-9 and rel < 0.5, (name, rel, float(g.norm()), ref_l2)
+    print("Generator %s: image max-abs %.3g, worst relative gradient-sample error %.3g" % (mode, np.abs(err).max(), worst))

@@ -158,3 +158,34 @@ def test_siren_nerf_oracle_and_init(golden):
     # 30x sine argument gain per layer: fp32 round-off differences between numpy and ATen matmuls reach a few 1e-5
     np.testing.assert_allclose(out[:, :3], g["out"][:, :3], atol=2e-4, rtol=0)
     np.testing.assert_allclose(out[:, 3], g["out"][:, 3], atol=2e-4, rtol=1e-3)
+
+
+def test_generator_host_side_matches_reference(golden):
+    """models.Generator / MappingNetwork / Renderer (pi_GAN/modules.py:34-68,120-197): same state-dict keys and seed-0 init as
+    the reference (SHA), the mapping network's film_params[B,9,512] on the golden z, and the (theta, phi) draws in the
+    reference's order -- the host side of Generator.forward; its render is a -m gpu test."""
+    import hashlib
+    gg = golden.generator
+    torch.manual_seed(0)
+    gen = models.Generator(256, 8, near=0.5, far=1.5, fov=12, coarse_samples=8, fine_samples=8)
+    h = hashlib.sha256()
+    sd = gen.state_dict()
+    for k in sd:
+        h.update(k.encode()); h.update(np.ascontiguousarray(sd[k].numpy()).tobytes())
+    assert h.hexdigest() == str(gg["state_sha"])
+    with torch.no_grad():
+        film = gen.get_mapping(torch.from_numpy(gg["z"]))
+    assert tuple(film.shape) == (2, 9, 512)
+    np.testing.assert_allclose(film.numpy(), gg["film"], atol=2e-6, rtol=0)
+    assert np.all(film.numpy()[:, :, :256].mean(-1) > 0.9)          # gamma ~ 1, beta ~ 0: the head-bias init (modules.py:56-58)
+    np.random.seed(3)
+    r = gen.renderer
+    from msra_practice_project_b200 import pigan_render
+    for i in range(2):
+        pose = r.draw_pose()
+        want = pigan_render.camera_pos_to_transform_matrix(1, gg["theta_phi"][i, 0], gg["theta_phi"][i, 1])
+        np.testing.assert_array_equal(pose, want)
+    gen.set_resolution(16)
+    assert r.width == 16 and r.height == 16 and abs(r.focal - 16 / 2 / np.tan(6 * np.pi / 180)) < 1e-9
+    with pytest.raises(RuntimeError):
+        gen(torch.from_numpy(gg["z"]))                                # CPU model: the render path has no CPU fallback
