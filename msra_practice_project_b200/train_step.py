@@ -187,3 +187,67 @@ class NerfTrainStep:
             self.state[1] = self.lr0 * (0.1 ** ((t - 1) / self.decay_steps)) if self.decay_steps > 0 else self.lr0
             self.state[2] = 1.0 - b1 ** t
             self.state[3] = math.sqrt(1.0 - b2 ** t)
+
+
+class RayBatcher:
+    """The GPU-resident training-ray buffer and the two batch samplers of ``nerf/train_nerf.py``:
+
+    * lines 78-84: rays of every training pose + the pixels' rgba as ONE shuffled ``[N*H*W, 10]`` device tensor.  The
+      reference builds it on the host with numpy ``get_rays`` (N x H x W x 6 floats) and uploads it; here the rays are
+      generated on the device (``ops.raygen``, bit-exact origins, directions <= 1 ulp) and only the images cross PCIe.  The
+      permutation is drawn with ``np.random.shuffle`` on an index vector, which consumes numpy's stream exactly like the
+      reference's in-place shuffle of the rows and yields the same row order;
+    * lines 125-137: the start-up sampler -- a random training image, the rays of its CENTRE crop (``get_rays`` of a
+      half-size image with the full-size focal), ``batch_size`` pixels without replacement (``np.random.choice`` twice, in
+      the reference's order);
+    * lines 139-145: consecutive ``batch_size`` slices; at the end of an epoch the reference draws ``torch.randperm`` but
+      assigns the shuffled copy to a misspelt name (``rays_rgb``), so the order never changes -- ``reshuffle=False`` (default)
+      reproduces that (the draw still happens), ``reshuffle=True`` applies the permutation.
+
+    ``next_batch`` / ``startup_batch`` return ``(rays[B,2,3], rgb[B,3], alpha[B])`` views for ``NerfTrainStep``; with a process
+    group every rank draws the same global batch and keeps its ``rank``-th slice."""
+
+    def __init__(self, images, poses, focal, batch_size, *, device=None, reshuffle=False, rank=0, world=1):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("RayBatcher keeps the ray buffer on a CUDA device: there is no CPU fallback")
+        self.dev, self.focal, self.batch = dev, focal, int(batch_size)
+        self.images = torch.as_tensor(images, dtype=torch.float32).to(dev)                     # [N,H,W,4]
+        self.poses = [p for p in (poses.detach().cpu().numpy() if isinstance(poses, torch.Tensor) else poses)]
+        n, h, w, _ = self.images.shape
+        self.n, self.h, self.w = n, h, w
+        rays = torch.cat([ops.raygen(w, h, focal, p[:3, :4], device=dev).reshape(-1, 6) for p in self.poses])      # [N*H*W,6]
+        rows = torch.cat([rays, self.images.reshape(-1, 4)], 1)
+        import numpy as np
+        perm = np.arange(rows.shape[0])
+        np.random.shuffle(perm)                                                                # same draws as shuffling the rows
+        self.rays_rgba = rows[torch.from_numpy(perm).to(dev)].contiguous()
+        self.batch_num = -(-rows.shape[0] // self.batch)
+        self.batch_idx = 0
+        self.reshuffle = bool(reshuffle)
+        self.rank, self.world = int(rank), int(world)
+
+    def _split(self, batch):
+        if self.world > 1:
+            per = batch.shape[0] // self.world
+            batch = batch[self.rank * per:(self.rank + 1) * per]
+        return batch[:, :6].reshape(-1, 2, 3), batch[:, 6:9], batch[:, 9]
+
+    def startup_batch(self):
+        import numpy as np
+        sw, sh, left, top = int(self.w / 2), int(self.h / 2), int(self.w / 4), int(self.h / 4)
+        i = np.random.choice(range(self.n))
+        rays = ops.raygen(sw, sh, self.focal, self.poses[i][:3, :4], device=self.dev).reshape(-1, 6)
+        rgba = self.images[i, top:top + sh, left:left + sw].reshape(-1, 4)
+        idx = np.random.choice(range(sw * sh), size=self.batch, replace=False)
+        return self._split(torch.cat([rays, rgba], 1)[torch.from_numpy(idx).to(self.dev)])
+
+    def next_batch(self):
+        b = self.rays_rgba[self.batch_idx * self.batch:(self.batch_idx + 1) * self.batch]
+        self.batch_idx += 1
+        if self.batch_idx == self.batch_num:
+            shuffle_idx = torch.randperm(self.rays_rgba.shape[0])                              # train_nerf.py:143 (CPU generator)
+            if self.reshuffle:
+                self.rays_rgba = self.rays_rgba[shuffle_idx.to(self.dev)]
+            self.batch_idx = 0
+        return self._split(b)

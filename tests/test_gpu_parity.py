@@ -1247,3 +1247,45 @@ def test_generator_forward_backward_vs_reference(golden, mode):
         else:       # 128 rays: bf16 rounding is not averaged out (cf. test_film_siren_fused_training_path)
             assert abs(float(g.norm()) - ref_l2) <= 0.3 * ref_l2 + 1e-9 and rel < 0.5, (name, rel, float(g.norm()), ref_l2)
     print("Generator %s: image max-abs %.3g, worst relative gradient-sample error %.3g" % (mode, np.abs(err).max(), worst))
+
+
+def test_ray_batcher_matches_train_nerf_batching():
+    """train_step.RayBatcher against a numpy restatement of nerf/train_nerf.py:78-84 (shuffled [N*H*W,10] buffer), :125-137
+    (start-up centre-crop sampler) and :139-145 (batch slices; the epoch 'reshuffle' that never takes effect) under the same
+    np.random seed: identical pixel order (rgba bit-exact, ray origins bit-exact, directions to 1 ulp)."""
+    from msra_practice_project_b200.train_step import RayBatcher
+    rs = np.random.RandomState(1)
+    n, h, w, bs = 3, 8, 12, 40
+    images = rs.rand(n, h, w, 4).astype(np.float32)
+    poses = np.stack([pigan_render.camera_pos_to_transform_matrix(4.0, 0.4 * i, -0.5 + 0.1 * i) for i in range(n)]).astype(np.float32)
+    focal = w * 1.3875
+    # reference arithmetic (numpy on the host)
+    np.random.seed(7)
+    rays = np.stack([np.stack(orc.get_rays(w, h, focal, p[:3, :4]), 0) for p in poses], 0)          # [N, ro+rd, H, W, 3]
+    rays = np.reshape(np.transpose(rays, [0, 2, 3, 1, 4]), [-1, 6])
+    ref = np.concatenate([rays, np.reshape(images, [-1, 4])], 1).astype(np.float32)
+    np.random.shuffle(ref)
+    si = np.random.choice(range(n))
+    s_rays = np.reshape(np.transpose(np.stack(orc.get_rays(int(w / 2), int(h / 2), focal, poses[si][:3, :4]), 0), [1, 2, 0, 3]), [-1, 6])
+    s_rgba = np.reshape(images[si][int(h / 4):int(h / 4) + int(h / 2), int(w / 4):int(w / 4) + int(w / 2)], [-1, 4])
+    s_ref = np.concatenate([s_rays, s_rgba], 1).astype(np.float32)[np.random.choice(range(s_rays.shape[0]), size=bs // 2, replace=False)]
+    # device batcher, same numpy stream
+    np.random.seed(7)
+    rb = RayBatcher(images, poses, focal, bs)
+    got = rb.rays_rgba.cpu().numpy()
+    assert got.shape == ref.shape == (n * h * w, 10)
+    assert np.array_equal(got[:, 6:], ref[:, 6:]) and np.array_equal(got[:, :3], ref[:, :3])
+    np.testing.assert_allclose(got[:, 3:6], ref[:, 3:6], rtol=3e-7, atol=1e-7)
+    rb.batch = bs // 2
+    r0, c0, a0 = rb.startup_batch()
+    assert np.array_equal(torch.cat([c0, a0[:, None]], 1).cpu().numpy(), s_ref[:, 6:])
+    np.testing.assert_allclose(r0.reshape(-1, 6).cpu().numpy(), s_ref[:, :6], rtol=3e-7, atol=1e-7)
+    rb.batch = bs
+    seen = []
+    for _ in range(rb.batch_num + 1):                        # one epoch + the first batch of the next
+        r, c, a = rb.next_batch()
+        seen.append(torch.cat([r.reshape(-1, 6), c, a[:, None]], 1).cpu().numpy())
+    assert np.array_equal(np.concatenate(seen[:-1])[:, 6:], ref[:, 6:])
+    assert np.array_equal(seen[-1], seen[0])                 # as shipped, the reference never reorders the buffer
+    rb2 = RayBatcher(images, poses, focal, bs, rank=1, world=2)
+    assert rb2.next_batch()[0].shape == (bs // 2, 2, 3)
