@@ -146,3 +146,21 @@ def density_grid(model, N=256, max_batch=64 ** 3, *, begin=0, count=None, precis
             raw = ops.mlp(model, grid=(N, b, c), precision=precision, sigma_only=True)
             out.append(-raw[:, 3])
     return out[0] if len(out) == 1 else torch.cat(out)
+
+
+def create_mesh_sdf(generator, N=256, max_batch=64 ** 3, *, z=None, precision=None):
+    """The sampling half of ``create_mesh`` (pi_GAN/utils.py:42-97; called by extract_mesh.py:49): draw z ~ N(0,1) on the
+    device, map it to FiLM parameters, condition the field and query -sigma on the N^3 lattice of [-0.1, 0.1]^3 with zero view
+    direction.  Returns what the reference hands to ``convert_sdf_samples_to_ply`` -- ``sdf_values`` as a CPU tensor
+    [N,N,N] (x slowest) -- plus ``voxel_origin`` and ``voxel_size``; marching cubes / PLY writing stay with the reference
+    (CPU, skimage: out of scope).  ``generator``: models.Generator or the reference's Generator (same attributes)."""
+    dev = next(generator.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("generator parameters must live on a CUDA device: the B200 render path has no CPU fallback")
+    if z is None:
+        z = torch.randn(1, generator.input_dim, device=dev)               # pi_GAN/utils.py:48
+    with torch.no_grad():
+        film_params = generator.get_mapping(z.to(dev))
+        generator.set_film_params(film_params[0])
+        sdf = density_grid(generator.film_siren_nerf, N=N, max_batch=max_batch, precision=precision)
+    return sdf.reshape(N, N, N).cpu(), [-0.1, -0.1, -0.1], 0.2 / (N - 1)

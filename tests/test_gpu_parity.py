@@ -1289,3 +1289,23 @@ def test_ray_batcher_matches_train_nerf_batching():
     assert np.array_equal(seen[-1], seen[0])                 # as shipped, the reference never reorders the buffer
     rb2 = RayBatcher(images, poses, focal, bs, rank=1, world=2)
     assert rb2.next_batch()[0].shape == (bs // 2, 2, 3)
+
+
+def test_create_mesh_sdf_matches_density_query(golden):
+    """pigan_render.create_mesh_sdf (the sampling half of create_mesh, pi_GAN/utils.py:42-97, as extract_mesh.py:49 calls it on a
+    Generator): -sigma on the lattice equals the per-point MLP evaluation of the conditioned field (fp32 path 1e-4; the
+    lattice coordinates themselves are pinned against the reference by test_mlp_fp32_film_and_grid's 6^3 golden)."""
+    torch.manual_seed(0)
+    gen = models.Generator(256, 16, near=0.5, far=1.5).cuda()
+    z = torch.randn(1, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    n = 12
+    sdf, origin, voxel = pigan_render.create_mesh_sdf(gen, N=n, max_batch=500, z=z, precision="fp32")
+    assert tuple(sdf.shape) == (n, n, n) and origin == [-0.1, -0.1, -0.1] and abs(voxel - 0.2 / (n - 1)) < 1e-12
+    idx = torch.arange(n ** 3)
+    pts = torch.stack([(idx // n // n) % n, (idx // n) % n, idx % n], -1).float() * np.float32(voxel) + (-0.1)
+    x = torch.cat([pts, torch.zeros_like(pts)], -1).cuda()
+    with torch.no_grad():
+        ref = -ops.mlp(gen.film_siren_nerf, x=x, precision="fp32")[:, 3]
+    np.testing.assert_allclose(sdf.reshape(-1).numpy(), ref.cpu().numpy(), atol=1e-4, rtol=0)
+    sdf_bf, _, _ = pigan_render.create_mesh_sdf(gen, N=n, z=z)
+    assert np.abs(sdf_bf.numpy() - sdf.numpy()).max() < 2e-2
