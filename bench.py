@@ -97,6 +97,37 @@ def cpu_baseline(args, n_rays: int, repeats: int = 1):
                        f"ATen port of the reference path (oracle/torch_port.py), {best:.2f} s; host has {os.cpu_count()} logical cores"), best
 
 
+def gpu_eager_incumbent(args, n_rays: int = 16384, repeats: int = 3):
+    """The same ATen port run with every tensor on the B200 (stock eager PyTorch, fp32 matmuls, the reference's own 16,384-ray
+    chunk, nerf/render.py:150): the honest GPU incumbent SURVEY 8(d) asks to be timed beside the CPU path -- what the
+    reference itself would reach on this GPU.  A baseline like cpu_baseline, never part of the measured product path."""
+    import torch
+    from oracle import render_oracle as orc, torch_port as tp
+    from msra_practice_project_b200 import models, pigan_render
+    torch.manual_seed(0)
+    c, f = models.NeRF(), models.NeRF()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sc_ = {k: v.to(dev) for k, v in c.state_dict().items()}
+    sf_ = {k: v.to(dev) for k, v in f.state_dict().items()}
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+    rays = orc.image_rays(args.width, args.height, args.width * 1.3875, pose)
+    mid = (args.height // 2) * args.width
+    rays = torch.from_numpy(np.ascontiguousarray(rays[mid:mid + n_rays])).to(dev)
+    best = None
+    with torch.no_grad(), torch.device(dev):
+        for _ in range(repeats + 1):                       # first pass = warm-up, not counted
+            t_rand = torch.rand(rays.shape[0], args.coarse)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            tp.render_rays(rays, 2.0, 6.0, lambda x: tp.nerf_mlp(sc_, x), lambda x: tp.nerf_mlp(sf_, x), args.coarse, args.fine, t_rand)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if _ > 0:
+                best = dt if best is None else min(best, dt)
+    return dict(value=rays.shape[0] / best, unit="rays/s", kind="port", device="this B200, stock eager PyTorch fp32",
+                sample=f"{rays.shape[0]}-ray chunk of the frame (the reference's own chunk size), {args.coarse}+{args.fine} samples, best of {repeats}: {best * 1e3:.1f} ms")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -325,6 +356,10 @@ def run_b200(args):
     base = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         base, _ = cpu_baseline(args, args.cpu_rays)
+        try:
+            base["gpu_eager_incumbent"] = gpu_eager_incumbent(args)
+        except Exception as e:
+            base["gpu_eager_incumbent"] = {"error": repr(e)[:200]}
 
     # the other BASELINE.json configs (training step, pi-GAN batch, density grid, SirenNeRF frame), measured in the same job
     secondary = []

@@ -8,6 +8,7 @@ tensors and raises otherwise -- there is no CPU or PyTorch-op fallback.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import weakref
 
 import numpy as np
@@ -221,13 +222,15 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: tor
 # ---- K3 / K7 / K8 ------------------------------------------------------------------------------------------
 _pack_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
 _pack_bwd_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+_pack_lock = threading.Lock()       # nn.DataParallel renders from one thread per GPU (pi_GAN/train.py:50): guard the shared dicts
 
 
 def invalidate_packed(model) -> None:
     """Forget the cached bf16 weight images of `model` (call after changing its parameters in a way torch cannot see,
     e.g. a kernel writing the flat master buffer: train_step.NerfTrainStep does this after every step)."""
-    _pack_cache.pop(model, None)
-    _pack_bwd_cache.pop(model, None)
+    with _pack_lock:
+        _pack_cache.pop(model, None)
+        _pack_bwd_cache.pop(model, None)
 
 
 def _packed_weights(model, kind: int, flat: torch.Tensor, film: torch.Tensor | None, use_dir: bool) -> torch.Tensor:
@@ -237,7 +240,8 @@ def _packed_weights(model, kind: int, flat: torch.Tensor, film: torch.Tensor | N
     key = tuple((p.data_ptr(), p._version) for p in ps)
     # FiLM tensors are rebuilt per latent (set_film_params) and may reuse a freed address, so a pointer /
     # version key cannot prove they are unchanged: FiLM models are re-packed on every call (~10 us).
-    hit = _pack_cache.get(model) if film is None else None
+    with _pack_lock:
+        hit = _pack_cache.get(model) if film is None else None
     if hit is not None and hit[0] == key:
         return hit[1]
     nbytes = lib().b2r_mlp_tc_packed_bytes(kind)
@@ -247,7 +251,8 @@ def _packed_weights(model, kind: int, flat: torch.Tensor, film: torch.Tensor | N
     with torch.cuda.device(flat.device):
         check(lib().b2r_mlp_tc_pack(kind, ptr(flat), ptr(film), int(use_dir), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack")
     if film is None:
-        _pack_cache[model] = (key, packed)
+        with _pack_lock:
+            _pack_cache[model] = (key, packed)
     return packed
 
 
@@ -321,14 +326,16 @@ def _packed_bwd_weights(model, kind: int, flat: torch.Tensor) -> torch.Tensor:
     """transposed bf16 weight images for the dgrad kernel, cached per model like the forward pack."""
     ps = models.param_list(model, kind)
     key = tuple((p.data_ptr(), p._version) for p in ps)
-    hit = _pack_bwd_cache.get(model)
+    with _pack_lock:
+        hit = _pack_bwd_cache.get(model)
     if hit is not None and hit[0] == key:
         return hit[1]
     nbytes = lib().b2r_mlp_tc_bwd_packed_bytes(kind)
     packed = torch.empty((nbytes,), dtype=torch.uint8, device=flat.device)
     with torch.cuda.device(flat.device):
         check(lib().b2r_mlp_tc_pack_bwd(kind, ptr(flat), ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_bwd")
-    _pack_bwd_cache[model] = (key, packed)
+    with _pack_lock:
+        _pack_bwd_cache[model] = (key, packed)
     return packed
 
 
