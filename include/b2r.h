@@ -157,7 +157,7 @@ int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_ml
  * weights from b2r_mlp_tc_pack_bwd (b2r_mlp_tc_bwd_packed_bytes bytes); raw = the forward's output; scratch:
  * b2r_mlp_tc_train_scratch_bytes(kind, rows) bytes (per-layer d(pre-activation) tiles for the weight-gradient GEMMs).
  * B2R_MODEL_NERF and B2R_MODEL_SIREN (nerf/nerf.py:97-170) use these entry points as they are.  B2R_MODEL_FILM
- * (FilmSirenNeRF, use_dir = 1; autograd through pi_GAN/modules.py:101-118 as used by pi_GAN/train.py:134 and
+ * (FilmSirenNeRF; autograd through pi_GAN/modules.py:101-118 as used by pi_GAN/train.py:134 and
  * synthesis.py:107): b2r_mlp_tc_train_fwd takes ONE latent's packed image (b2r_mlp_tc_pack with that latent's film);
  * the reverse mode is b2r_mlp_tc_pack_bwd_film + b2r_mlp_tc_train_bwd_film, which also returns d film[9,512]
  * (d gamma | d beta per layer).  d_folded: B2R_FILM_NUMEL floats of workspace (zeroed by the call: gradients of the
@@ -174,11 +174,12 @@ int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows,
 /* FiLM-SIREN, B latents in one launch sequence (Generator.forward's loop WITH gradients, pi_GAN/modules.py:176-184 +
  * pi_GAN/train.py:134): packed = B images from b2r_mlp_tc_pack_film_batched, rows [b*rows_per_latent, (b+1)*rows_per_latent)
  * belong to latent b (rows_per_latent a multiple of 512); film [B,9,512]; packed_bwd = B images from b2r_mlp_tc_pack_bwd_film;
- * d_folded: B * B2R_FILM_NUMEL floats; d_film [B,9,512]; d_params sums over the latents.  n_latents = 1: rows_per_latent ignored. */
+ * d_folded: B * B2R_FILM_NUMEL floats; d_film [B,9,512]; d_params sums over the latents.  n_latents = 1: rows_per_latent ignored.
+ * use_dir: the FilmSirenNeRF(use_dir=...) flag (0: hidden_layer_rgb has 256 inputs, flat layout B2R_FILM_NODIR_NUMEL). */
 int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in,
                                       float* raw_out, void* saved, size_t saved_bytes, void* stream);
-int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, int n_latents, void* packed_out, void* stream);
-int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, int n_latents, long long rows_per_latent,
+int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, int use_dir, int n_latents, void* packed_out, void* stream);
+int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, int use_dir, int n_latents, long long rows_per_latent,
                               long long rows, const float* raw, const float* d_raw, const void* saved, void* scratch,
                               size_t scratch_bytes, float* d_folded, float* d_params, float* d_film, void* stream);
 

@@ -62,8 +62,8 @@ SIGNATURES = {
                                        c_float_p, C.c_void_p]),
     "b2r_mlp_tc_train_fwd_film_batched": (C.c_int, [C.c_void_p, C.c_int, c_ll, C.POINTER(MlpInput), c_float_p, C.c_void_p, C.c_size_t,
                                                     C.c_void_p]),
-    "b2r_mlp_tc_pack_bwd_film": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "b2r_mlp_tc_train_bwd_film": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, c_ll, c_ll, c_float_p, c_float_p, C.c_void_p,
+    "b2r_mlp_tc_pack_bwd_film": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "b2r_mlp_tc_train_bwd_film": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, C.c_int, c_ll, c_ll, c_float_p, c_float_p, C.c_void_p,
                                             C.c_void_p, C.c_size_t, c_float_p, c_float_p, c_float_p, C.c_void_p]),
 }
 

@@ -349,12 +349,16 @@ __constant__ WUnit c_wunits_film[10] = {
     {fscr_g(8), 4, kFsAUX, 1, 9, 256, 3, 0, 0, 1.0f},
 };
 // model kinds of the wgrad kernel (= B2R_MODEL_*: 0 NeRF, 1 FiLM-SIREN, 2 SirenNeRF)
-constexpr int kKNerf = B2R_MODEL_NERF, kKFilm = B2R_MODEL_FILM, kKSiren = B2R_MODEL_SIREN;
-template <int KIND> __host__ __device__ constexpr int n_wunits() { return KIND == kKFilm ? 10 : kWUnits; }
-// half-block loads per 64-row stage, all units: 83 (NeRF, SirenNeRF), 74 (FiLM-SIREN)
-template <int KIND> __host__ __device__ constexpr int wcost_total() { return KIND == kKFilm ? 5 + 7 * 8 + 8 + 5 : 5 + 4 * 8 + 5 + 8 + 2 * 8 + 8 + 6 + 3; }
+// kKFilmNoDir: FilmSirenNeRF(use_dir=False) -- hidden_layer_rgb has 256 inputs: the parameter offsets move and the last unit (its
+// direction columns) does not exist
+constexpr int kKNerf = B2R_MODEL_NERF, kKFilm = B2R_MODEL_FILM, kKSiren = B2R_MODEL_SIREN, kKFilmNoDir = 3;
+template <int KIND> __host__ __device__ constexpr int n_wunits() { return KIND == kKFilm ? 10 : (KIND == kKFilmNoDir ? 9 : kWUnits); }
+// half-block loads per 64-row stage, all units: 83 (NeRF, SirenNeRF), 74 / 69 (FiLM-SIREN with / without view direction)
+template <int KIND> __host__ __device__ constexpr int wcost_total() {
+    return KIND == kKFilm ? 5 + 7 * 8 + 8 + 5 : (KIND == kKFilmNoDir ? 5 + 7 * 8 + 8 : 5 + 4 * 8 + 5 + 8 + 2 * 8 + 8 + 6 + 3);
+}
 template <int KIND> __host__ __device__ constexpr LayerDesc wlayer(int i) {
-    return KIND == kKFilm ? film_layer(i, true) : (KIND == kKSiren ? siren_layer(i) : nerf_layer(i));
+    return KIND == kKFilm ? film_layer(i, true) : (KIND == kKFilmNoDir ? film_layer(i, false) : (KIND == kKSiren ? siren_layer(i) : nerf_layer(i)));
 }
 
 constexpr int kWStages = 3;
@@ -367,7 +371,9 @@ struct WPiece { int u; long long t0, t1; };
 // CTA b owns the slice [b, b+1) * total / grid of the cost line (units laid end to end, each n_sub tiles x cost(u)); both
 // ends are rounded to tiles with the same function, so neighbouring CTAs agree on the boundary.
 template <int KIND>
-__device__ __forceinline__ WUnit wunit(int u) { return KIND == kKFilm ? c_wunits_film[u] : (KIND == kKSiren ? c_wunits_siren[u] : c_wunits[u]); }
+__device__ __forceinline__ WUnit wunit(int u) {
+    return (KIND == kKFilm || KIND == kKFilmNoDir) ? c_wunits_film[u] : (KIND == kKSiren ? c_wunits_siren[u] : c_wunits[u]);
+}
 
 template <int KIND>
 __device__ __forceinline__ bool wpiece(int u, long long n_sub, long long lo, long long hi, long long& base, WPiece& pc) {
@@ -654,14 +660,15 @@ __host__ __device__ constexpr int fbwd_film_row(int s) { return 8 - s; }
 
 // B[n][k] = 30 gamma_k W[k][n]: n = input feature (output column of dX), k = output feature (the forward's folded row k)
 // blockIdx.y = latent: film [n_latents][9][512] -> n_latents images of kFilmBwdPackedBytes
-__global__ void film_pack_bwd_kernel(const float* __restrict__ params, const float* __restrict__ film_all, uint8_t* __restrict__ packed_all) {
+__global__ void film_pack_bwd_kernel(const float* __restrict__ params, const float* __restrict__ film_all, uint8_t* __restrict__ packed_all, int use_dir) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool ud = use_dir != 0;
     const float* __restrict__ film = film_all + (size_t)blockIdx.y * B2R_FILM_PARAMS;
     uint8_t* __restrict__ packed = packed_all + (size_t)blockIdx.y * kFilmBwdPackedBytes;
     if (t < kFilmBwdChunkBytes / 16) {
         int s, c, hf, row, grp;
         locate<FilmBwdSched>(t * 16, s, c, hf, row, grp);
-        const LayerDesc L = film_layer(fbwd_layer(s), true);
+        const LayerDesc L = film_layer(fbwd_layer(s), ud);
         const float* __restrict__ gamma = film + fbwd_film_row(s) * 512;
         const int n = hf * 128 + row;
         __nv_bfloat16 v[8];
@@ -677,7 +684,7 @@ __global__ void film_pack_bwd_kernel(const float* __restrict__ params, const flo
     if (t < kFBwdTabFloats) {
         float* tab = reinterpret_cast<float*>(packed + kFilmBwdChunkBytes);
         const int i = (int)t;
-        tab[i] = i < kFBwdTabWRgb ? params[film_layer(8, true).w_off + i] : params[film_layer(10, true).w_off + (i - kFBwdTabWRgb)];
+        tab[i] = i < kFBwdTabWRgb ? params[film_layer(8, ud).w_off + i] : params[film_layer(10, ud).w_off + (i - kFBwdTabWRgb)];
     }
 }
 
@@ -865,13 +872,13 @@ __global__ void __launch_bounds__(256) film_head_wgrad_kernel(const uint8_t* __r
 // block, its d_folded, its d_film).  d_params (shared by the latents: float atomics) and d_film are ACCUMULATED into; either may be NULL.
 __global__ void __launch_bounds__(256) film_grad_finish_kernel(const float* __restrict__ params, const float* __restrict__ film_all,
                                                                const float* __restrict__ d_folded_all, float* __restrict__ d_params,
-                                                               float* __restrict__ d_film_all) {
+                                                               float* __restrict__ d_film_all, int use_dir) {
     const int gw = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (gw >= 9 * 256) return;
     const float* __restrict__ film = film_all + (size_t)blockIdx.y * B2R_FILM_PARAMS;
-    const float* __restrict__ d_folded = d_folded_all + (size_t)blockIdx.y * B2R_FILM_NUMEL;
+    const float* __restrict__ d_folded = d_folded_all + (size_t)blockIdx.y * (use_dir ? B2R_FILM_NUMEL : B2R_FILM_NODIR_NUMEL);
     const int fl = gw >> 8, i = gw & 255;
-    const LayerDesc L = film_layer(fl == 8 ? 9 : fl, true);
+    const LayerDesc L = film_layer(fl == 8 ? 9 : fl, use_dir != 0);
     const float gsc = 30.0f * film[fl * 512 + i];
     const float* __restrict__ w = params + L.w_off + (long long)i * L.in;
     const float* __restrict__ dwp = d_folded + L.w_off + (long long)i * L.in;
@@ -905,7 +912,7 @@ extern "C" size_t b2r_mlp_tc_bwd_packed_bytes(int model_kind) {
     return train_kind(model_kind) ? (size_t)b2r::tc::kBwdPackedBytes : 0;
 }
 
-extern "C" int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, int n_latents, void* packed_out, void* stream) {
+extern "C" int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, int use_dir, int n_latents, void* packed_out, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(params && film && packed_out, "b2r_mlp_tc_pack_bwd_film: NULL pointer");
     B2R_CHECK_ARG(((uintptr_t)packed_out & 15) == 0, "b2r_mlp_tc_pack_bwd_film: packed_out must be 16-byte aligned");
@@ -913,7 +920,7 @@ extern "C" int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, 
     if (n_latents == 0) return 0;
     long long threads = tc::kFilmBwdChunkBytes / 16;
     tc::film_pack_bwd_kernel<<<dim3((unsigned)((threads + 255) / 256), (unsigned)n_latents), 256, 0, (cudaStream_t)stream>>>(params, film,
-                                                                                                                            (uint8_t*)packed_out);
+                                                                                                                            (uint8_t*)packed_out, use_dir);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_pack_bwd_film");
     return 0;
 }
@@ -985,7 +992,7 @@ extern "C" int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long
     return train_bwd_launch<false>(packed_bwd, rows, raw, d_raw, saved, scratch, d_params, (cudaStream_t)stream);
 }
 
-extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, int n_latents, long long rows_per_latent,
+extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, int use_dir, int n_latents, long long rows_per_latent,
                                          long long rows, const float* raw, const float* d_raw, const void* saved, void* scratch,
                                          size_t scratch_bytes, float* d_folded, float* d_params, float* d_film, void* stream) {
     using namespace b2r;
@@ -998,7 +1005,7 @@ extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* pa
     B2R_CHECK_ARG(scratch_bytes >= b2r_mlp_tc_train_scratch_bytes(B2R_MODEL_FILM, rows), "b2r_mlp_tc_train_bwd_film: scratch too small (%zu B)", scratch_bytes);
     if (rows == 0 || (!d_params && !d_film)) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = cuda_result(cudaMemsetAsync(d_folded, 0, (size_t)n_latents * B2R_FILM_NUMEL * sizeof(float), st), "cudaMemsetAsync(d_folded)");
+    int rc = cuda_result(cudaMemsetAsync(d_folded, 0, (size_t)n_latents * (use_dir ? B2R_FILM_NUMEL : B2R_FILM_NODIR_NUMEL) * sizeof(float), st), "cudaMemsetAsync(d_folded)");
     if (rc) return rc;
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
@@ -1014,7 +1021,11 @@ extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* pa
     if (rc) return rc;
     rc = cuda_result(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "SM count");
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_wgrad_kernel<tc::kKFilm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
+    const bool ud = use_dir != 0;
+    auto wkern = ud ? tc::nerf_tc_wgrad_kernel<tc::kKFilm> : tc::nerf_tc_wgrad_kernel<tc::kKFilmNoDir>;
+    const int n_units = ud ? tc::n_wunits<tc::kKFilm>() : tc::n_wunits<tc::kKFilmNoDir>();
+    const size_t numel = ud ? B2R_FILM_NUMEL : B2R_FILM_NODIR_NUMEL;
+    rc = cuda_result(cudaFuncSetAttribute(wkern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kWSmem), "tc wgrad smem attribute");
     if (rc) return rc;
     // one wgrad launch per latent over its own sub-tiles (the folded weights, hence their gradients, are per latent)
     const long long sub_per_latent = n_latents > 1 ? rows_per_latent / tc::kRowsSub : n_sub;
@@ -1022,19 +1033,18 @@ extern "C" int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* pa
         const long long t0 = (long long)b * sub_per_latent;
         const long long tn = (t0 + sub_per_latent <= n_sub ? sub_per_latent : n_sub - t0);
         if (tn <= 0) break;
-        const long long work = tn * tc::n_wunits<tc::kKFilm>();
+        const long long work = tn * n_units;
         unsigned wgrid = (unsigned)(work < sms ? work : sms);
-        tc::nerf_tc_wgrad_kernel<tc::kKFilm><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub,
-                                                                                       d_folded + (size_t)b * B2R_FILM_NUMEL, t0, tn);
+        wkern<<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_folded + (size_t)b * numel, t0, tn);
         B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (wgrad)");
     }
     if (d_params) {    // the heads are not FiLM-folded: plain gradients straight into d_params
         unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
-        tc::film_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params, film_layer(8, true),
-                                                          film_layer(10, true));
+        tc::film_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params, film_layer(8, ud),
+                                                          film_layer(10, ud));
         B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (heads)");
     }
-    tc::film_grad_finish_kernel<<<dim3(9 * 256 / 8, (unsigned)n_latents), 256, 0, st>>>(params, film, d_folded, d_params, d_film);
+    tc::film_grad_finish_kernel<<<dim3(9 * 256 / 8, (unsigned)n_latents), 256, 0, st>>>(params, film, d_folded, d_params, d_film, use_dir);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd_film (finish)");
     return 0;
 }

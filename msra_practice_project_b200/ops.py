@@ -449,7 +449,7 @@ class _MlpTcTrainFilm(torch.autograd.Function):
     (Generator.forward's loop, pi_GAN/modules.py:176-184, in one launch sequence)."""
 
     @staticmethod
-    def forward(ctx, flat, film, rays, z, x, rows_per_latent):
+    def forward(ctx, flat, film, rays, z, x, rows_per_latent, use_dir=True):
         kind = models.KIND_FILM
         inp, rows, keep = _make_input(rays, z, x, None)
         dev = flat.device
@@ -461,14 +461,14 @@ class _MlpTcTrainFilm(torch.autograd.Function):
         saved = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
         if rows > 0:
             with torch.cuda.device(dev):
-                check(lib().b2r_mlp_tc_pack_film_batched(ptr(fd), ptr(fl), 1, n_lat, ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_film_batched")
+                check(lib().b2r_mlp_tc_pack_film_batched(ptr(fd), ptr(fl), int(use_dir), n_lat, ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_film_batched")
                 if n_lat == 1:
                     check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, _stream(flat)),
                           "b2r_mlp_tc_train_fwd")
                 else:
                     check(lib().b2r_mlp_tc_train_fwd_film_batched(ptr(packed), n_lat, int(rows_per_latent), C.byref(inp), ptr(raw), ptr(saved),
                                                                   nbytes, _stream(flat)), "b2r_mlp_tc_train_fwd_film_batched")
-        ctx.rows, ctx.n_lat, ctx.rows_per_latent = rows, n_lat, int(rows_per_latent)
+        ctx.rows, ctx.n_lat, ctx.rows_per_latent, ctx.use_dir = rows, n_lat, int(rows_per_latent), int(bool(use_dir))
         ctx.save_for_backward(flat, film, raw, saved)
         del keep
         return raw
@@ -478,7 +478,7 @@ class _MlpTcTrainFilm(torch.autograd.Function):
         flat, film, raw, saved = ctx.saved_tensors
         need_w, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_w or need_f):
-            return (None,) * 6
+            return (None,) * 7
         dev = flat.device
         d_flat = torch.zeros_like(flat) if need_w else None
         d_film = torch.zeros(film.shape, dtype=torch.float32, device=dev) if need_f else None
@@ -491,11 +491,11 @@ class _MlpTcTrainFilm(torch.autograd.Function):
             scratch = torch.empty((sbytes,), dtype=torch.uint8, device=dev)
             d_folded = torch.empty((ctx.n_lat, fd.numel()), dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
-                check(lib().b2r_mlp_tc_pack_bwd_film(ptr(fd), ptr(fl), ctx.n_lat, ptr(packed_bwd), _stream(flat)), "b2r_mlp_tc_pack_bwd_film")
-                check(lib().b2r_mlp_tc_train_bwd_film(ptr(packed_bwd), ptr(fd), ptr(fl), ctx.n_lat, ctx.rows_per_latent, ctx.rows, ptr(raw),
+                check(lib().b2r_mlp_tc_pack_bwd_film(ptr(fd), ptr(fl), ctx.use_dir, ctx.n_lat, ptr(packed_bwd), _stream(flat)), "b2r_mlp_tc_pack_bwd_film")
+                check(lib().b2r_mlp_tc_train_bwd_film(ptr(packed_bwd), ptr(fd), ptr(fl), ctx.use_dir, ctx.n_lat, ctx.rows_per_latent, ctx.rows, ptr(raw),
                                                       ptr(d_raw), ptr(saved), ptr(scratch), sbytes, ptr(d_folded), ptr(d_flat), ptr(d_film),
                                                       _stream(flat)), "b2r_mlp_tc_train_bwd_film")
-        return d_flat, d_film, None, None, None, None
+        return d_flat, d_film, None, None, None, None, None
 
 
 def mlp_film_batched_train(model, film: torch.Tensor, rays: torch.Tensor, z: torch.Tensor, rows_per_latent: int) -> torch.Tensor:
@@ -503,8 +503,9 @@ def mlp_film_batched_train(model, film: torch.Tensor, rays: torch.Tensor, z: tor
     autograd graph to the model's parameters and to film[B,9,512] (fused tensor-core training path, bf16 arithmetic)."""
     kind = models.model_kind(model)
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
-    if kind != models.KIND_FILM or not bool(getattr(net, "use_dir", True)):
-        raise TypeError("mlp_film_batched_train needs a FilmSirenNeRF(use_dir=True) model")
+    if kind != models.KIND_FILM:
+        raise TypeError("mlp_film_batched_train needs a FilmSirenNeRF model")
+    use_dir = bool(getattr(net, "use_dir", True))
     if rows_per_latent <= 0 or rows_per_latent % 512 != 0:
         raise RuntimeError("rows_per_latent must be a positive multiple of 512")
     ps = models.param_list(net, kind)
@@ -512,7 +513,7 @@ def mlp_film_batched_train(model, film: torch.Tensor, rays: torch.Tensor, z: tor
         raise RuntimeError("model parameters must live on a CUDA device: the B200 render path has no CPU fallback")
     if film.dim() != 3 or tuple(film.shape[1:]) != (9, 512) or not film.is_cuda:
         raise RuntimeError(f"film must be a CUDA tensor [B,9,512], got {tuple(film.shape)}")
-    return _MlpTcTrainFilm.apply(models.flat_params(net, kind), film.float(), rays, z, None, int(rows_per_latent))
+    return _MlpTcTrainFilm.apply(models.flat_params(net, kind), film.float(), rays, z, None, int(rows_per_latent), use_dir)
 
 
 def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, x: torch.Tensor | None = None,
@@ -545,8 +546,8 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
             gp = "bf16"
         if gp == "bf16" and kind in (models.KIND_NERF, models.KIND_SIREN):
             return _MlpTcTrain.apply(flat, net, kind, rays, z, x)
-        if gp == "bf16" and kind == models.KIND_FILM and use_dir:
-            return _MlpTcTrainFilm.apply(flat, film, rays, z, x, 0)
+        if gp == "bf16" and kind == models.KIND_FILM:
+            return _MlpTcTrainFilm.apply(flat, film, rays, z, x, 0, use_dir)
         return _MlpF32.apply(flat, film, kind, use_dir, rays, z, x, {"fp32": 0, "tf32": 1, "bf16": 2}[gp])
     inp, rows, keep = _make_input(rays, z, x, grid)
     raw = torch.empty((rows, 4), dtype=torch.float32, device=dev)

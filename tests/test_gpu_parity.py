@@ -1064,15 +1064,15 @@ def test_siren_fused_train_step_trains(golden):
     assert step.global_step == 5 and torch.isfinite(step.params).all()
 
 
-@pytest.mark.parametrize("rows_shape", [(37, 24), (700, 32), (1, 1)])
+@pytest.mark.parametrize("rows_shape", [(37, 24), (700, 32), (1, 1), (300, 16, False)])
 def test_film_siren_fused_training_path(rows_shape):
     """FiLM-SIREN on the fused tensor-core training path (film_tc_kernel<true> with bf16 tiles + cosine checkpoints,
     film_tc_bwd_kernel, MN-major wgrad on the FOLDED weights, film_grad_finish_kernel unfolding them into d W, d b, d gamma,
     d beta): the training forward is bit-identical to the inference kernel; every parameter gradient and d film[9,512] against
     the exact fp32 layer-wise path; the d-film-only call (synthesis.py:92-107: weights frozen) returns the same d film."""
-    n, s = rows_shape
+    n, s = rows_shape[:2]
     g = torch.Generator().manual_seed(n + 11)
-    net = seeded_film()
+    net = seeded_film(use_dir=len(rows_shape) < 3)            # (.., False): FilmSirenNeRF(use_dir=False), 256-input hidden_layer_rgb
     film = torch.cat([1.0 + 0.1 * torch.randn(9, 256, generator=g), 0.1 * torch.randn(9, 256, generator=g)], -1).cuda().requires_grad_(True)
     o = torch.tensor([0.0, 0.0, 1.0]).expand(n, 3)
     d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * 0.25 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
