@@ -82,7 +82,7 @@ __global__ void siren_pack_kernel(const float* __restrict__ params, uint8_t* __r
 //   MODE 0: sin(acc) -> bf16 h;   MODE 1: same + partial sigma head;   MODE 2: acc -> bf16 h (linear layers_dir.0);
 //   MODE 3: N = 128 (32 columns per quarter): sin(acc) -> partial rgb head (kSave: also bf16 h_d into shared memory at h_blk)
 // head: shared-memory address of this quarter's fp32 head weights.  kSave (training forward): cos(acc) of the sine layers is
-// stored as bf16x2 words, two uint4 per 16-column unit, thread-major at cosp + w * 2048 (tc_core.cuh: siren_cos_off).
+// stored as one byte per element, one uint4 per 16-column unit, thread-major at cosp + u * 2048 (tc_core.cuh: cos_q4, siren_cos_off).
 template <int MODE, bool kSave>
 __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t h_blk, const uint32_t (&xoff)[8], float& sigma, float& rgb0,
                                           float& rgb1, float& rgb2, uint8_t* __restrict__ cosp) {
@@ -98,11 +98,11 @@ __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t 
 #pragma unroll
         for (int e = 0; e < 16; ++e) f[e] = MODE == 2 ? __uint_as_float(v[e]) : __sinf(__uint_as_float(v[e]));
         if (kSave && MODE != 2) {
-            uint32_t cw[8];
+            uint32_t cw[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) cw[e] = pack_bf16(__cosf(__uint_as_float(v[2 * e])), __cosf(__uint_as_float(v[2 * e + 1])));
-            stg128(cosp + (size_t)(2 * u) * 2048, cw[0], cw[1], cw[2], cw[3]);
-            stg128(cosp + (size_t)(2 * u + 1) * 2048, cw[4], cw[5], cw[6], cw[7]);
+            for (int e = 0; e < 4; ++e)
+                cw[e] = cos_q4(__uint_as_float(v[4 * e]), __uint_as_float(v[4 * e + 1]), __uint_as_float(v[4 * e + 2]), __uint_as_float(v[4 * e + 3]));
+            stg128(cosp + (size_t)u * 2048, cw[0], cw[1], cw[2], cw[3]);
         }
         if (MODE == 1) {
 #pragma unroll
@@ -224,7 +224,7 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                 // ---- layers_pos.0 on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                    uint32_t pk[16], ck[16];
+                    uint32_t pk[16], ck[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
@@ -237,12 +237,12 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                         const float t0 = fmaf(a0, 30.0f, sh.x), t1 = fmaf(a1, 30.0f, sh.y), t2 = fmaf(a2, 30.0f, sh.z), t3 = fmaf(a3, 30.0f, sh.w);
                         pk[2 * q + 0] = pack_bf16(__sinf(t0), __sinf(t1));
                         pk[2 * q + 1] = pack_bf16(__sinf(t2), __sinf(t3));
-                        if (kSave) { ck[2 * q + 0] = pack_bf16(__cosf(t0), __cosf(t1)); ck[2 * q + 1] = pack_bf16(__cosf(t2), __cosf(t3)); }
+                        if (kSave) ck[q] = cos_q4(t0, t1, t2, t3);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                        if (kSave) stg128(saved + siren_cos_off(n_sub, 0, T, cq, jj * 4 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
+                        if (kSave && q < 2) stg128(saved + siren_cos_off(n_sub, 0, T, cq, jj * 2 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
                     }
                 }
                 if (cq == 0) {

@@ -81,20 +81,20 @@ __device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
 // One dgrad step's epilogue for this warp's half (128) of the columns.
 //   MODE 0: linear (d g: layers_dir.0 has no activation);  MODE 1: + gs * w_sigma (sigma-head term), act'(h7);  MODE 2: act'(h)
 // act' = relu' from the layer's relu bits (NeRF: one prefetched 16-byte word per thread) or, kSiren, cos(t) from the forward's
-// thread-major bf16x2 checkpoint (four 16-byte words per 32-column group, the next group's in flight).
+// thread-major byte checkpoint (two 16-byte words per 32-column group, the next group's in flight; tc_core.cuh: cos_unq).
 // The result (bf16) is written in place as the next step's A operand; the spill thread copies the same tile to global memory
 // for wgrad.  dptr: NeRF: this thread's relu-bit word of the layer; SirenNeRF: its first cosine word (quarter 2 * half, w = 0).
 template <int MODE, bool kSiren>
 __device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const uint32_t (&xoff)[8], const uint8_t* __restrict__ dptr,
                                         float gs, uint32_t wsig_half, uint32_t acc_bar, uint32_t& acc_phase, uint32_t done_bar, uint32_t& sp_phase) {
     uint4 mk4 = make_uint4(0u, 0u, 0u, 0u);
-    uint4 cw[4];
-    // cosine words of 32-column group jj: quarter (jj >> 1) of this half, words (jj & 1) * 4 .. + 3; 2048 B between words, 8 words per quarter
-    auto cos_ptr = [&](int jj, int q) -> const uint8_t* { return dptr + (size_t)((jj >> 1) * 8 + (jj & 1) * 4 + q) * 2048; };
+    uint4 cw[2];
+    // cosine bytes of 32-column group jj: quarter (jj >> 1) of this half, words (jj & 1) * 2, + 1; 2048 B between words, 4 words per quarter
+    auto cos_ptr = [&](int jj, int q) -> const uint8_t* { return dptr + (size_t)((jj >> 1) * 4 + (jj & 1) * 2 + q) * 2048; };
     if (MODE != 0) {
         if (kSiren) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cw[q] = ldg128(cos_ptr(0, q));
+            for (int q = 0; q < 2; ++q) cw[q] = ldg128(cos_ptr(0, q));
         } else mk4 = ldg128(dptr);
     }
     mbar_wait_cluster(acc_bar, acc_phase);
@@ -107,10 +107,10 @@ __device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const 
     for (int jj = 0; jj < 4; ++jj) {
         uint32_t v[32];
         tmem_ld32(t_half + (uint32_t)jj * 32u, v);
-        uint4 cn[4];
+        uint4 cn[2];
         if (kSiren && MODE != 0 && jj < 3) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cn[q] = ldg128(cos_ptr(jj + 1, q));
+            for (int q = 0; q < 2; ++q) cn[q] = ldg128(cos_ptr(jj + 1, q));
         }
         tmem_ld_wait();
         float f[32];
@@ -126,21 +126,21 @@ __device__ __forceinline__ void bwd_epi(uint32_t t_half, uint32_t h_half, const 
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+            if (kSiren && MODE != 0) {         // fp32 product with the checkpointed cosine, then one rounding to bf16
+                const uint4 c = cw[q >> 1];
+                cos_mul8(f + 8 * q, (q & 1) ? c.z : c.x, (q & 1) ? c.w : c.y);
+            }
             uint32_t w0 = pack_bf16(f[8 * q + 0], f[8 * q + 1]), w1 = pack_bf16(f[8 * q + 2], f[8 * q + 3]);
             uint32_t w2 = pack_bf16(f[8 * q + 4], f[8 * q + 5]), w3 = pack_bf16(f[8 * q + 6], f[8 * q + 7]);
-            if (MODE != 0) {
-                if (kSiren) {
-                    w0 = mul_bf16x2(w0, cw[q].x); w1 = mul_bf16x2(w1, cw[q].y); w2 = mul_bf16x2(w2, cw[q].z); w3 = mul_bf16x2(w3, cw[q].w);
-                } else {
-                    w0 &= mask_get(mk[jj], 4 * q + 0); w1 &= mask_get(mk[jj], 4 * q + 1);
-                    w2 &= mask_get(mk[jj], 4 * q + 2); w3 &= mask_get(mk[jj], 4 * q + 3);
-                }
+            if (MODE != 0 && !kSiren) {
+                w0 &= mask_get(mk[jj], 4 * q + 0); w1 &= mask_get(mk[jj], 4 * q + 1);
+                w2 &= mask_get(mk[jj], 4 * q + 2); w3 &= mask_get(mk[jj], 4 * q + 3);
             }
             st_shared_v4(h_half + (uint32_t)(jj >> 1) * kBlk + xoff[(jj & 1) * 4 + q], w0, w1, w2, w3);
         }
         if (kSiren && MODE != 0 && jj < 3) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cw[q] = cn[q];
+            for (int q = 0; q < 2; ++q) cw[q] = cn[q];
         }
     }
 }
@@ -233,11 +233,11 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                 const uint32_t wr = tab + (uint32_t)(kBwdTabWRgb + half * 64) * 4u;
                 if (!first_tile) { mbar_wait(done_bar, sp_phase); sp_phase ^= 1u; }          // previous tile's d h0 copy
                 first_tile = false;
+                uint4 cwq = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    // SirenNeRF: cos(t) of layers_dir.1, quarter half * 2 + (q >> 2) (32 columns each), word q & 3
-                    uint4 cwq = make_uint4(0u, 0u, 0u, 0u);
-                    if (kSiren) cwq = ldg128(saved + siren_cos9_off(n_sub, T, half * 2 + (q >> 2), q & 3, r));
+                    // SirenNeRF: cos(t) of layers_dir.1, quarter half * 2 + (q >> 2) (32 columns each), word (q & 3) >> 1 (16 columns)
+                    if (kSiren && (q & 1) == 0) cwq = ldg128(saved + siren_cos9_off(n_sub, T, half * 2 + (q >> 2), (q & 3) >> 1, r));
                     float f[8];
 #pragma unroll
                     for (int hq = 0; hq < 2; ++hq) {
@@ -248,10 +248,9 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                         f[4 * hq + 2] = fmaf(gc2, w2.z, fmaf(gc1, w1.z, gc0 * w0.z));
                         f[4 * hq + 3] = fmaf(gc2, w2.w, fmaf(gc1, w1.w, gc0 * w0.w));
                     }
+                    if (kSiren) cos_mul8(f, (q & 1) ? cwq.z : cwq.x, (q & 1) ? cwq.w : cwq.y);
                     uint32_t w0 = pack_bf16(f[0], f[1]), w1 = pack_bf16(f[2], f[3]), w2 = pack_bf16(f[4], f[5]), w3 = pack_bf16(f[6], f[7]);
-                    if (kSiren) {
-                        w0 = mul_bf16x2(w0, cwq.x); w1 = mul_bf16x2(w1, cwq.y); w2 = mul_bf16x2(w2, cwq.z); w3 = mul_bf16x2(w3, cwq.w);
-                    } else {
+                    if (!kSiren) {
                         const uint32_t bits = (q >> 2) ? hm.y : hm.x;
                         const int i0 = 4 * (q & 3);
                         w0 &= mask_get(bits, i0 + 0); w1 &= mask_get(bits, i0 + 1); w2 &= mask_get(bits, i0 + 2); w3 &= mask_get(bits, i0 + 3);
@@ -774,9 +773,10 @@ film_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                 const uint32_t wr = tab + (uint32_t)(kFBwdTabWRgb + half * 128) * 4u;
                 if (!first_tile) { mbar_wait(done_bar, sp_phase); sp_phase ^= 1u; }          // previous tile's G0 copy
                 first_tile = false;
+                uint4 cwq = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 4
                 for (int q = 0; q < 16; ++q) {
-                    const uint4 cwq = ldg128(saved + film_cos_off(n_sub, 8, T, half * 2 + (q >> 3), q & 7, r));
+                    if ((q & 1) == 0) cwq = ldg128(saved + film_cos_off(n_sub, 8, T, half * 2 + (q >> 3), (q & 7) >> 1, r));
                     float f[8];
 #pragma unroll
                     for (int hq = 0; hq < 2; ++hq) {
@@ -787,8 +787,8 @@ film_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                         f[4 * hq + 2] = fmaf(gc2, w2.z, fmaf(gc1, w1.z, gc0 * w0.z));
                         f[4 * hq + 3] = fmaf(gc2, w2.w, fmaf(gc1, w1.w, gc0 * w0.w));
                     }
-                    const uint32_t w0 = mul_bf16x2(pack_bf16(f[0], f[1]), cwq.x), w1 = mul_bf16x2(pack_bf16(f[2], f[3]), cwq.y);
-                    const uint32_t w2 = mul_bf16x2(pack_bf16(f[4], f[5]), cwq.z), w3 = mul_bf16x2(pack_bf16(f[6], f[7]), cwq.w);
+                    cos_mul8(f, (q & 1) ? cwq.z : cwq.x, (q & 1) ? cwq.w : cwq.y);
+                    const uint32_t w0 = pack_bf16(f[0], f[1]), w1 = pack_bf16(f[2], f[3]), w2 = pack_bf16(f[4], f[5]), w3 = pack_bf16(f[6], f[7]);
                     st_shared_v4(h_half + (uint32_t)(q >> 3) * kBlk + ((((uint32_t)q & 7u) ^ xr) << 4), w0, w1, w2, w3);
                 }
             }

@@ -126,27 +126,50 @@ __device__ __forceinline__ uint32_t relu_mask2(uint32_t h2) {
 __device__ __forceinline__ void mask_put(uint32_t& bits, uint32_t w, int i) { bits |= relu_mask2(w) & (0x00010001u << i); }
 __device__ __forceinline__ uint32_t mask_get(uint32_t bits, int i) { return ((bits >> i) & 0x00010001u) * 0xFFFFu; }
 
-// SirenNeRF training checkpoints: tiles AUX [pos(3), 1, 1, dir(3)] | H0..H7 | GL | HD, then cos(t) of the nine sine layers as
-// bf16x2 words stored THREAD-MAJOR -- [layer 0..7][T][quarter cq][word w 0..7][row r] uint4 (the 64 columns of a quarter = 32
-// words = 8 uint4 per thread), then the same for layers_dir.1 with 4 uint4 per quarter (32 columns): lanes of a warp touch
-// consecutive 16-byte words, so the forward's stores and the reverse mode's loads are fully coalesced.
+// cos(t) checkpoints of the sine layers (training): ONE BYTE per activation, offset-binary fixed point
+//   ub = clamp(round(128 cos t), -128, 127) + 128        (absolute error <= 2^-8, the same as a bf16 near |cos| = 1)
+// stored THREAD-MAJOR -- [layer][T][quarter cq of 64 columns][word w 0..3][row r] uint4, word w = columns 16 w .. 16 w + 15 of the
+// quarter -- so the 32 lanes of a warp touch 512 contiguous bytes and the forward's stores / the reverse mode's loads are fully
+// coalesced (the trick that made the relu bits cheap), at 256 B per row and layer.
+// four sine arguments -> four packed bytes (t0 in the low byte).  1.5 * 2^23 + 128 + 128 c rounds to an integer whose low
+// mantissa byte is ub; cos is clamped below 1 so that 128 c + 128 never reaches 256.
+__device__ __forceinline__ uint32_t cos_q4(float t0, float t1, float t2, float t3) {
+    constexpr float kMagic = 12582912.0f + 128.0f, kTop = 0.9921875f;
+    const uint32_t a = __float_as_uint(fmaf(fminf(__cosf(t0), kTop), 128.0f, kMagic)), b = __float_as_uint(fmaf(fminf(__cosf(t1), kTop), 128.0f, kMagic));
+    const uint32_t c = __float_as_uint(fmaf(fminf(__cosf(t2), kTop), 128.0f, kMagic)), d = __float_as_uint(fmaf(fminf(__cosf(t3), kTop), 128.0f, kMagic));
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+// byte K of a packed word -> cos: the byte becomes mantissa bits 8..15 of a float with exponent 2^8 (256 + ub / 128), minus 257
+template <int K>
+__device__ __forceinline__ float cos_unq(uint32_t word) {
+    return __uint_as_float(__byte_perm(word, 0x43800000u, 0x7604u | (K << 4))) - 257.0f;
+}
+// f[0..7] *= cos of the 8 bytes in (lo, hi)
+__device__ __forceinline__ void cos_mul8(float* f, uint32_t lo, uint32_t hi) {
+    f[0] *= cos_unq<0>(lo); f[1] *= cos_unq<1>(lo); f[2] *= cos_unq<2>(lo); f[3] *= cos_unq<3>(lo);
+    f[4] *= cos_unq<0>(hi); f[5] *= cos_unq<1>(hi); f[6] *= cos_unq<2>(hi); f[7] *= cos_unq<3>(hi);
+}
+constexpr size_t kCosLayerBytes = 32768;                 // per 128-row sub-tile and 256-column layer: 4 quarters x 4 words x 2 KB
+
+// SirenNeRF training checkpoints: tiles AUX [pos(3), 1, 1, dir(3)] | H0..H7 | GL | HD, then the cosine bytes of layers_pos.0..7
+// and of layers_dir.1 (128 columns: 4 "quarters" of 32 columns = 2 words each)
 constexpr int kSsAUX = 0, kSsH0 = 1, kSsGL = 33, kSsHD = 37, kSsBlocks = 39;
 __host__ __device__ constexpr int ss_h(int l) { return kSsH0 + 4 * l; }
-__host__ __device__ constexpr size_t siren_saved_bytes_per_sub() { return (size_t)kSsBlocks * kBlk + 8 * 65536 + 32768; }
+__host__ __device__ constexpr size_t siren_saved_bytes_per_sub() { return (size_t)kSsBlocks * kBlk + 8 * kCosLayerBytes + kCosLayerBytes / 2; }
 __device__ __forceinline__ size_t siren_cos_off(size_t n_sub, int layer, size_t T, int cq, int w, int r) {
-    return (size_t)kSsBlocks * n_sub * kBlk + ((((size_t)layer * n_sub + T) * 4 + cq) * 8 + w) * 2048 + (size_t)r * 16;
+    return (size_t)kSsBlocks * n_sub * kBlk + ((((size_t)layer * n_sub + T) * 4 + cq) * 4 + w) * 2048 + (size_t)r * 16;
 }
 __device__ __forceinline__ size_t siren_cos9_off(size_t n_sub, size_t T, int cq, int w, int r) {
-    return (size_t)kSsBlocks * n_sub * kBlk + (size_t)8 * n_sub * 65536 + (((T * 4 + cq) * 4 + w) * 2048) + (size_t)r * 16;
+    return (size_t)kSsBlocks * n_sub * kBlk + (size_t)8 * n_sub * kCosLayerBytes + (((T * 4 + cq) * 2 + w) * 2048) + (size_t)r * 16;
 }
 
 // FiLM-SIREN training checkpoints: tiles AUX [dir(3), 1, 1, pos(3)] | H0..H7 (inputs of hidden_layers.0..6 and hidden_layer_rgb) |
-// HC (hidden_layer_rgb output), then cos(t) of the nine sine layers in the thread-major layout of siren_cos_off
+// HC (hidden_layer_rgb output), then the cosine bytes of the nine sine layers
 constexpr int kFsAUX = 0, kFsH0 = 1, kFsHC = 33, kFsBlocks = 37;
 __host__ __device__ constexpr int fs_h(int l) { return kFsH0 + 4 * l; }
-__host__ __device__ constexpr size_t film_saved_bytes_per_sub() { return (size_t)kFsBlocks * kBlk + 9 * 65536; }
+__host__ __device__ constexpr size_t film_saved_bytes_per_sub() { return (size_t)kFsBlocks * kBlk + 9 * kCosLayerBytes; }
 __device__ __forceinline__ size_t film_cos_off(size_t n_sub, int layer, size_t T, int cq, int w, int r) {
-    return (size_t)kFsBlocks * n_sub * kBlk + ((((size_t)layer * n_sub + T) * 4 + cq) * 8 + w) * 2048 + (size_t)r * 16;
+    return (size_t)kFsBlocks * n_sub * kBlk + ((((size_t)layer * n_sub + T) * 4 + cq) * 4 + w) * 2048 + (size_t)r * 16;
 }
 // reverse-mode scratch of the FiLM path: G8 (d t of hidden_layer_rgb) | G7 .. G0, then the head gradients HG
 constexpr int kFScrBlocks = 36;

@@ -59,8 +59,8 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     assert lib.b2r_mlp_tc_train_scratch_bytes(0, 1000) == 8 * (38 * 16384 + 128 * 16)
     assert lib.b2r_mlp_tc_train_saved_bytes(3, 1000) == 0 and lib.b2r_mlp_tc_train_saved_bytes(0, 0) == 0
     assert lib.b2r_mlp_tc_bwd_packed_bytes(0) == 34 * 32768 + 640 * 4 and lib.b2r_mlp_tc_bwd_packed_bytes(3) == 0
-    # FiLM-SIREN: 37 tile blocks + 9 layers of thread-major cosine words per sub-tile; 36 gradient blocks + head gradients
-    assert lib.b2r_mlp_tc_train_saved_bytes(1, 1000) == 8 * (37 * 16384 + 9 * 65536)
+    # FiLM-SIREN: 37 tile blocks + 9 layers of thread-major cosine bytes per sub-tile; 36 gradient blocks + head gradients
+    assert lib.b2r_mlp_tc_train_saved_bytes(1, 1000) == 8 * (37 * 16384 + 9 * 32768)
     assert lib.b2r_mlp_tc_train_scratch_bytes(1, 1000) == 8 * (36 * 16384 + 128 * 16)
     assert lib.b2r_mlp_tc_bwd_packed_bytes(1) == 32 * 32768 + 1024 * 4
     assert lib.b2r_mlp_tc_packed_bytes(1) == 8 * 5 * 32768 + 2308 * 4                                     # FiLM-SIREN
