@@ -147,7 +147,7 @@ def run_reference(args):
                                      f"each step = a {args.ref_rays}-ray sample of the frame on the host CPU"),
                 cpu_baseline=base, e2e=dict(value=v, unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 samples_per_s=v * (2 * args.coarse + args.fine), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---- clocks sampler ---------------------------------------------------------------------------------------
@@ -384,7 +384,7 @@ def run_b200(args):
                              d2h_bytes_per_step=int(n_rays * 5 * 4), ms_per_step=e2e_ms),
                     gpu_launches=int(7 * args.steps * world), clocks=clocks.summary(), roofline=roof, hbm_kernels=hbm_kernels,
                     cpu_baseline=base, secondary=secondary)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -609,12 +609,30 @@ def run_secondary(args, config=None, embedded=False):
         torch.cuda.empty_cache()
         return line
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to fd 1 behind Python's back (NCCL's "NCCL version ..." banner under NCCL_DEBUG=VERSION): keep stdout for the
+    # JSON line alone by pointing fd 1 at stderr for everything else.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

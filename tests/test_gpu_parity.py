@@ -1309,3 +1309,25 @@ def test_create_mesh_sdf_matches_density_query(golden):
     np.testing.assert_allclose(sdf.reshape(-1).numpy(), ref.cpu().numpy(), atol=1e-4, rtol=0)
     sdf_bf, _, _ = pigan_render.create_mesh_sdf(gen, N=n, z=z)
     assert np.abs(sdf_bf.numpy() - sdf.numpy()).max() < 2e-2
+
+
+def test_bench_contract_one_json_line_with_all_keys():
+    """bench.py's contract on a reduced frame: stdout carries exactly ONE JSON line with the driver's keys (metric, value, unit,
+    n_gpus, steps, warmup, ms_per_step, higher_is_better, scaling, vs_baseline, dtype, data, config.workload, e2e with byte
+    counts, gpu_launches, clocks, roofline with bound / achieved / peak / frac / traffic); everything else goes to stderr."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--width", "128", "--height", "128", "--steps", "2", "--warmup", "3",
+                        "--no-cpu-baseline", "--no-secondary"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:2000]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+              "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] >= 3 and d["unit"] == "rays/s" and d["value"] > 0
+    assert "workload" in d["config"] and d["e2e"]["value"] > 0 and d["e2e"]["d2h_bytes_per_step"] == 128 * 128 * 5 * 4
+    assert d["gpu_launches"] > 0 and d["roofline"]["bound"] == "tensor" and 0 < d["roofline"]["frac"] < 1.2
+    for k in ("achieved", "peak", "unit", "traffic"):
+        assert k in d["roofline"]
