@@ -1331,3 +1331,12 @@ def test_bench_contract_one_json_line_with_all_keys():
     assert d["gpu_launches"] > 0 and d["roofline"]["bound"] == "tensor" and 0 < d["roofline"]["frac"] < 1.2
     for k in ("achieved", "peak", "unit", "traffic"):
         assert k in d["roofline"]
+
+
+def test_film_batched_training_random_shapes():
+    """tools/stress_film_train.py (random latent counts, rows per latent, samples per ray: odd tile counts, latents that
+    start in the middle of a CTA's tile walk): the batched fused training call reproduces latent 0's rows bit-exactly and its
+    d film to the summation order; no barrier-protocol hang (run under a timeout)."""
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_film_train.py")], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert r.returncode == 0 and "stress ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
