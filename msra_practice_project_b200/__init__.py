@@ -4,7 +4,9 @@ Sub-modules
 -----------
 nerf_render   drop-in for the reference's ``nerf/render.py``
 pigan_render  drop-in for the reference's ``pi_GAN/render.py``
-models        NeRF / FilmSirenNeRF parameter containers (reference state-dict keys)
+models        NeRF / SirenNeRF / FilmSirenNeRF and the pi-GAN Generator / MappingNetwork / Renderer (reference state-dict keys)
+train_step    NerfTrainStep (fused CUDA-graph training step) and RayBatcher (GPU-resident ray buffer, start-up crop sampler)
+dist          ray / latent sharding helpers over torch.distributed (image gather, gradient all-reduce)
 ops           autograd-aware wrappers over the C-ABI CUDA library (``libb2r.so``)
 _lib          ctypes binding of ``include/b2r.h``
 """
