@@ -1340,3 +1340,58 @@ def test_film_batched_training_random_shapes():
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "stress_film_train.py")], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0 and "stress ok" in r.stdout, (r.stdout[-1500:], r.stderr[-1500:])
+
+
+@pytest.mark.parametrize("kind", ["nerf", "siren", "film"])
+def test_fused_training_full_size_properties(kind):
+    """The fused tensor-core training path at BASELINE's full training shape (4096 rays x 256 MLP rows = 1,048,576 rows: too
+    many for the fp32 comparison to be cheap) through size-independent properties:
+      * head bias gradients are plain column sums of the head gradients: d b_sigma = sum_rows [sigma > 0] d_raw_sigma and
+        d b_rgb = sum_rows d_raw_rgb * y (1 - y), recomputed here from (raw, d_raw) alone;
+      * the reverse mode is linear in d_raw and scaling by 2 is exact in binary floating point (bf16 rounding included), so
+        doubling the upstream gradient must double every gradient up to the summation order of the fp32 atomics;
+      * everything is finite and no gradient tensor is identically zero."""
+    g = torch.Generator().manual_seed(17)
+    n, s = 4096, 256
+    torch.manual_seed(0)
+    film = None
+    if kind == "nerf":
+        net = models.damp_nerf_(models.NeRF()).cuda()
+        sig_b, rgb_b = "output_layer_sigma.bias", "output_layer_rgb.bias"
+    elif kind == "siren":
+        net = models.SirenNeRF().cuda()
+        sig_b, rgb_b = "output_layer_sigma.bias", "output_layer_rgb.bias"
+    else:
+        net = models.FilmSirenNeRF().cuda()
+        film = torch.cat([1.0 + 0.1 * torch.randn(9, 256, generator=g), 0.1 * torch.randn(9, 256, generator=g)], -1).cuda().requires_grad_(True)
+        sig_b, rgb_b = "output_layer_sigma.0.bias", "output_layer_rgb.0.bias"
+    o = torch.tensor([0.0, 0.0, 1.2]).expand(n, 3)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g) * 0.25 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
+    rays = torch.stack([o, d], 1).cuda()
+    z = (torch.sort(torch.rand(n, s, generator=g), -1).values * 1.0 + 0.5).cuda()
+    up = torch.randn(n * s, 4, generator=g).cuda()
+    res = []
+    for scale in (1.0, 2.0):
+        net.zero_grad(set_to_none=True)
+        if film is not None:
+            film.grad = None
+            net.set_film_params(film)
+        raw = ops.mlp(net, rays=rays, z=z)
+        assert raw.shape == (n * s, 4)
+        (raw * (up * scale)).sum().backward()
+        grads = {k: p.grad.detach().clone() for k, p in net.named_parameters()}
+        if film is not None:
+            grads["film"] = film.grad.detach().clone()
+        res.append((raw.detach(), grads))
+    raw, g1 = res[0]
+    g2 = res[1][1]
+    y = raw[:, :3].double()
+    want_rgb = (up[:, :3].double() * y * (1 - y)).sum(0)
+    want_sig = (up[:, 3].double() * (raw[:, 3] > 0)).sum()
+    assert torch.allclose(g1[rgb_b].double(), want_rgb, rtol=2e-4, atol=2e-3), (g1[rgb_b], want_rgb)
+    assert abs(g1[sig_b].double().item() - want_sig.item()) <= 2e-4 * abs(want_sig.item()) + 2e-2, (g1[sig_b], want_sig)
+    for k in g1:
+        a, b = g1[k].reshape(-1).double(), g2[k].reshape(-1).double()
+        assert torch.isfinite(a).all() and a.abs().max() > 0, k
+        rel = (2 * a - b).norm().item() / max(b.norm().item(), 1e-30)
+        assert rel < 1e-4, (k, rel)
