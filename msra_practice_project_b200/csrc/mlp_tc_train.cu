@@ -70,14 +70,6 @@ __global__ void nerf_pack_bwd_kernel(const float* __restrict__ params, uint8_t* 
     }
 }
 
-__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
-    __nv_bfloat162 x, y;
-    *reinterpret_cast<uint32_t*>(&x) = a;
-    *reinterpret_cast<uint32_t*>(&y) = b;
-    x = __hmul2(x, y);
-    return *reinterpret_cast<uint32_t*>(&x);
-}
-
 // One dgrad step's epilogue for this warp's half (128) of the columns.
 //   MODE 0: linear (d g: layers_dir.0 has no activation);  MODE 1: + gs * w_sigma (sigma-head term), act'(h7);  MODE 2: act'(h)
 // act' = relu' from the layer's relu bits (NeRF: one prefetched 16-byte word per thread) or, kSiren, cos(t) from the forward's
