@@ -1395,3 +1395,70 @@ def test_fused_training_full_size_properties(kind):
         assert torch.isfinite(a).all() and a.abs().max() > 0, k
         rel = (2 * a - b).norm().item() / max(b.norm().item(), 1e-30)
         assert rel < 1e-4, (k, rel)
+
+
+@pytest.mark.parametrize("kind", ["nerf", "film", "siren"])
+def test_training_kernels_stay_inside_their_buffers(kind):
+    """The training forward / reverse mode write exactly the bytes their size queries declare: `saved`, `scratch`, `d_folded`
+    and the gradient buffers are carved out of larger allocations filled with a canary byte; after forward + backward through
+    the C ABI every byte past the declared sizes is untouched and the declared regions were actually written."""
+    import ctypes as C
+    from msra_practice_project_b200._lib import lib, check, MlpInput
+    L = lib()
+    kid = {"nerf": models.KIND_NERF, "film": models.KIND_FILM, "siren": models.KIND_SIREN}[kind]
+    torch.manual_seed(0)
+    net = {"nerf": models.NeRF, "film": models.FilmSirenNeRF, "siren": models.SirenNeRF}[kind]().cuda()
+    flat = models.flat_params(net).detach().contiguous()
+    g = torch.Generator().manual_seed(5)
+    n_lat, rows = (3, 3 * 1536) if kind == "film" else (1, 1000)          # FiLM: 3 latents x 1536 rows; others: a ragged count
+    x = torch.cat([torch.rand(rows, 3, generator=g) - 0.5, torch.nn.functional.normalize(torch.randn(rows, 3, generator=g), dim=-1)], -1).cuda()
+    d_raw = torch.randn(rows, 4, generator=g).cuda()
+    inp = MlpInput()
+    inp.x, inp.n_rays, inp.n_samples = x.data_ptr(), rows, 1
+    st = torch.cuda.current_stream().cuda_stream
+    pad, canary = 1 << 20, 0xCD
+
+    def guarded(nbytes):
+        buf = torch.full((nbytes + pad,), canary, dtype=torch.uint8, device="cuda")
+        return buf
+
+    def intact(buf, nbytes, name):
+        assert bool((buf[nbytes:] == canary).all()), f"{name}: wrote past its {nbytes} declared bytes"
+        assert not bool((buf[:nbytes] == canary).all()), f"{name}: never written"
+
+    sv_bytes = L.b2r_mlp_tc_train_saved_bytes(kid, rows)
+    sc_bytes = L.b2r_mlp_tc_train_scratch_bytes(kid, rows)
+    saved, scratch = guarded(sv_bytes), guarded(sc_bytes)
+    raw = guarded(rows * 16)
+    n_par = flat.numel()
+    d_params = guarded(n_par * 4)
+    d_params[:n_par * 4] = 0
+    if kind == "film":
+        film = torch.cat([1.0 + 0.1 * torch.randn(n_lat, 9, 256, generator=g), 0.1 * torch.randn(n_lat, 9, 256, generator=g)], -1).cuda().contiguous()
+        pk_bytes, pb_bytes = L.b2r_mlp_tc_packed_bytes(kid), L.b2r_mlp_tc_bwd_packed_bytes(kid)
+        packed, packed_bwd = guarded(n_lat * pk_bytes), guarded(n_lat * pb_bytes)
+        d_folded, d_film = guarded(n_lat * n_par * 4), guarded(n_lat * 4608 * 4)
+        d_film[:n_lat * 4608 * 4] = 0
+        check(L.b2r_mlp_tc_pack_film_batched(flat.data_ptr(), film.data_ptr(), 1, n_lat, packed.data_ptr(), st), "pack")
+        check(L.b2r_mlp_tc_train_fwd_film_batched(packed.data_ptr(), n_lat, 1536, C.byref(inp), raw.data_ptr(), saved.data_ptr(), sv_bytes, st), "fwd")
+        check(L.b2r_mlp_tc_pack_bwd_film(flat.data_ptr(), film.data_ptr(), 1, n_lat, packed_bwd.data_ptr(), st), "pack_bwd")
+        check(L.b2r_mlp_tc_train_bwd_film(packed_bwd.data_ptr(), flat.data_ptr(), film.data_ptr(), 1, n_lat, 1536, rows, raw.data_ptr(), d_raw.data_ptr(),
+                                          saved.data_ptr(), scratch.data_ptr(), sc_bytes, d_folded.data_ptr(), d_params.data_ptr(), d_film.data_ptr(),
+                                          st), "bwd")
+        torch.cuda.synchronize()
+        for buf, nb, name in ((packed, n_lat * pk_bytes, "packed"), (packed_bwd, n_lat * pb_bytes, "packed_bwd"), (d_folded, n_lat * n_par * 4, "d_folded"),
+                              (d_film, n_lat * 4608 * 4, "d_film")):
+            intact(buf, nb, name)
+    else:
+        pk_bytes, pb_bytes = L.b2r_mlp_tc_packed_bytes(kid), L.b2r_mlp_tc_bwd_packed_bytes(kid)
+        packed, packed_bwd = guarded(pk_bytes), guarded(pb_bytes)
+        check(L.b2r_mlp_tc_pack(kid, flat.data_ptr(), None, 1, packed.data_ptr(), st), "pack")
+        check(L.b2r_mlp_tc_train_fwd(kid, packed.data_ptr(), C.byref(inp), raw.data_ptr(), saved.data_ptr(), sv_bytes, st), "fwd")
+        check(L.b2r_mlp_tc_pack_bwd(kid, flat.data_ptr(), packed_bwd.data_ptr(), st), "pack_bwd")
+        check(L.b2r_mlp_tc_train_bwd(kid, packed_bwd.data_ptr(), rows, raw.data_ptr(), d_raw.data_ptr(), saved.data_ptr(), scratch.data_ptr(), sc_bytes,
+                                     d_params.data_ptr(), st), "bwd")
+        torch.cuda.synchronize()
+        intact(packed, pk_bytes, "packed"); intact(packed_bwd, pb_bytes, "packed_bwd")
+    intact(saved, sv_bytes, "saved"); intact(scratch, sc_bytes, "scratch"); intact(raw, rows * 16, "raw"); intact(d_params, n_par * 4, "d_params")
+    gp = d_params[:n_par * 4].view(torch.float32)
+    assert torch.isfinite(gp).all() and gp.abs().max() > 0
