@@ -962,7 +962,7 @@ static int train_bwd_launch(const void* packed_bwd, long long rows, const float*
     unsigned wgrid = (unsigned)(work < sms ? work : sms);
     tc::nerf_tc_wgrad_kernel<kSiren ? tc::kKSiren : tc::kKNerf><<<wgrid, tc::kWThreads, tc::kWSmem, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params, 0, n_sub);
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_bwd (wgrad)");
-    unsigned hgrid = (unsigned)(n_sub < 2LL * sms ? n_sub : 2LL * sms);
+    unsigned hgrid = (unsigned)(n_sub < 4LL * sms ? n_sub : 4LL * sms);
     tc::nerf_head_wgrad_kernel<<<hgrid, 256, 0, st>>>((const uint8_t*)saved, (const uint8_t*)scratch, n_sub, d_params,
                                                       kSiren ? tc::ss_h(7) : tc::sav_h(7), kSiren ? tc::kSsHD : tc::kSavHD,
                                                       kSiren ? siren_layer(10) : nerf_layer(10), kSiren ? siren_layer(11) : nerf_layer(11));
