@@ -118,6 +118,26 @@ typedef struct b2r_mlp_input {
     long long grid_begin;
 } b2r_mlp_input;
 
+/* ---- the last interval of every ray ------------------------------------ raw_to_outputs nerf/render.py:91-93 ----
+ * dists[-1] = 1e10 makes alpha_last = 1 - exp(-sigma_last * 1e10 * |d|) a STEP FUNCTION of sign(sigma_last): the sign
+ * of the LAST sample's pre-relu density decides whether the ray's remaining transmittance lands on that sample or on
+ * the white background, so a bf16-rounded sigma that crosses zero changes a ray's colour by up to T_last.
+ * The bf16 tensor-core kernels therefore report, for rows r with (r + 1) % samples_per_ray == 0, every ray whose
+ * |sigma_pre| is inside the error band of the bf16 arithmetic:
+ *     |sigma_pre| <= rel * scale + abs,   scale = sum_k |w_sigma[k] * h[k]| of that row   (ReLU trunk: NeRF)
+ *                                         scale = sum_k |w_sigma[k]|                      (sine trunks, |h| <= 1)
+ * and b2r_mlp_f32_last_sigma re-evaluates exactly those rows with the fp32 CUDA-core path (bit-identical to
+ * b2r_mlp_f32_fwd on the same rows) and overwrites raw[row, 3].
+ * count: one device int the CALLER ZEROES; ray_ids[capacity]: flagged ray indices (row / samples_per_ray) in
+ * arbitrary order; count may exceed capacity (entries beyond it are dropped: size capacity = number of rays). */
+typedef struct b2r_last_sample {
+    int samples_per_ray;
+    int capacity;
+    int* count;
+    int* ray_ids;
+    float rel, abs;
+} b2r_last_sample;
+
 /* fp32 path (CUDA cores).  params: flat fp32 parameters (B2R_*_NUMEL floats, state-dict order);
  * film: [9,512] (FiLM model only).  workspace: b2r_mlp_f32_workspace_bytes(kind, rows, save)
  * bytes; with save_activations != 0 the workspace holds every layer's output afterwards and is
@@ -146,8 +166,17 @@ int b2r_mlp_tc_pack(int model_kind, const float* params, const float* film, int 
                     void* packed_out, void* stream);
 /* use_dir: the FilmSirenNeRF(use_dir=...) flag the weights were packed with (ignored for NeRF).
  * sigma_only != 0 (FiLM only): stop after the sigma head, raw_out[:, :3] = 0 (create_mesh density query). */
+/* last: nullable; when given (rays or x mode), the kernel also lists the rays whose last sample needs the fp32 sign check. */
 int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_mlp_input* in, float* raw_out,
-                   int sigma_only, void* stream);
+                   int sigma_only, const b2r_last_sample* last, void* stream);
+/* fp32 re-evaluation of sigma for the last sample of the n_ids listed rays (trunk + sigma head only): raw_io[(ray *
+ * samples_per_ray + samples_per_ray - 1) * 4 + 3] = relu(sigma_pre) with the arithmetic of b2r_mlp_f32_fwd (gemm_mode 0).
+ * film: [n_latents,9,512] for the FiLM model (n_latents = 1: one [9,512] tensor); with n_latents > 1 source row r belongs
+ * to latent r / rows_per_latent (the batched entry points below).  workspace: b2r_mlp_f32_workspace_bytes(kind, n_ids, 0)
+ * + 4 * n_ids bytes. */
+int b2r_mlp_f32_last_sigma(int model_kind, const float* params, const float* film, int use_dir, int n_latents,
+                           long long rows_per_latent, const b2r_mlp_input* in, int samples_per_ray, const int* ray_ids,
+                           int n_ids, float* raw_io, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K8 on the tensor cores: training forward + reverse mode of the NeRF MLP (bf16 operands, fp32 accumulate) --------
  * Replaces autograd through NeRF.forward (nerf/nerf.py:75-94) as used by nerf/train_nerf.py:151-168.
@@ -200,7 +229,7 @@ int b2r_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * multiple of 512 (the two 256-row tiles of a CTA pair share one set of weights). */
 int b2r_mlp_tc_pack_film_batched(const float* params, const float* film, int use_dir, int n_latents, void* packed_out, void* stream);
 int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in, float* raw_out,
-                                int sigma_only, void* stream);
+                                int sigma_only, const b2r_last_sample* last, void* stream);
 
 /* ---- image-space output ---------------------------------------------------- to8b  nerf/render.py:5 ---------------
  * out[i] = (uint8)(255 * clip(x[i], 0, 1)) with numpy's float32 product and truncation (show_nerf.py:60-66,

@@ -24,6 +24,12 @@ class MlpInput(C.Structure):
                 ("n_samples", C.c_int), ("grid_n", C.c_int), ("grid_begin", c_ll)]
 
 
+class LastSample(C.Structure):
+    """struct b2r_last_sample (include/b2r.h)."""
+    _fields_ = [("samples_per_ray", C.c_int), ("capacity", C.c_int), ("count", C.c_void_p), ("ray_ids", C.c_void_p),
+                ("rel", C.c_float), ("abs", C.c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol include/b2r.h declares (checked by tests/test_abi.py)
 SIGNATURES = {
     "b2r_last_error": (C.c_char_p, []),
@@ -47,14 +53,16 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_size_t, c_float_p, c_float_p, C.c_int, C.c_void_p]),
     "b2r_mlp_tc_packed_bytes": (C.c_size_t, [C.c_int]),
     "b2r_mlp_tc_pack": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "b2r_mlp_tc_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_int, C.c_void_p]),
+    "b2r_mlp_tc_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.POINTER(MlpInput), c_float_p, C.c_int, C.POINTER(LastSample), C.c_void_p]),
+    "b2r_mlp_f32_last_sigma": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_int, c_ll, C.POINTER(MlpInput), C.c_int, C.c_void_p, C.c_int,
+                                         c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b2r_mlp_tc_train_saved_bytes": (C.c_size_t, [C.c_int, c_ll]),
     "b2r_mlp_tc_train_fwd": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(MlpInput), c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b2r_mlp_tc_bwd_packed_bytes": (C.c_size_t, [C.c_int]),
     "b2r_mlp_tc_pack_bwd": (C.c_int, [C.c_int, c_float_p, C.c_void_p, C.c_void_p]),
     "b2r_mlp_tc_train_scratch_bytes": (C.c_size_t, [C.c_int, c_ll]),
     "b2r_mlp_tc_pack_film_batched": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "b2r_mlp_tc_fwd_film_batched": (C.c_int, [C.c_void_p, C.c_int, c_ll, C.POINTER(MlpInput), c_float_p, C.c_int, C.c_void_p]),
+    "b2r_mlp_tc_fwd_film_batched": (C.c_int, [C.c_void_p, C.c_int, c_ll, C.POINTER(MlpInput), c_float_p, C.c_int, C.POINTER(LastSample), C.c_void_p]),
     "b2r_to8b": (C.c_int, [c_float_p, c_ll, C.c_void_p, C.c_void_p]),
     "b2r_adam_step": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_ll, c_float_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),

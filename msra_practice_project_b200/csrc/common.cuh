@@ -91,6 +91,10 @@ struct RowSource {
     int grid_n;
     long long grid_begin;
     float voxel;   // 0.2/(N-1) rounded to float (pi_GAN/utils.py:57)
+    // gather mode (b2r_mlp_f32_last_sigma): row i of the launch is the LAST sample of ray pick[i], i.e. source row
+    // pick[i] * pick_s + pick_s - 1 of the rays / x description above
+    const int* pick;
+    int pick_s;
 };
 
 inline RowSource make_row_source(const b2r_mlp_input* in) {
@@ -98,6 +102,7 @@ inline RowSource make_row_source(const b2r_mlp_input* in) {
     s.rays = in->rays; s.z = in->z; s.x = in->x; s.n_rays = in->n_rays; s.n_samples = in->n_samples;
     s.grid_n = in->grid_n; s.grid_begin = in->grid_begin;
     s.voxel = in->grid_n > 1 ? (float)(0.2 / (double)(in->grid_n - 1)) : 0.f;
+    s.pick = nullptr; s.pick_s = 0;
     return s;
 }
 inline long long row_count(const b2r_mlp_input* in) {
@@ -107,9 +112,13 @@ int check_mlp_input(const b2r_mlp_input* in);
 
 // position = o + d*z as two rounded ops (torch: mul then add, nerf/render.py:134), unit view
 // direction = d/|d| (render.py:122), lattice coordinates as pi_GAN/utils.py:64-72.
-__device__ __forceinline__ void load_row(const RowSource& s, long long row, float p[3], float v[3]) {
+// ray_out (optional): the ray the row belongs to (rays mode; the row itself otherwise).
+__device__ __forceinline__ void load_row(const RowSource& s, long long row, float p[3], float v[3], long long* ray_out = nullptr) {
+    if (s.pick) row = (long long)s.pick[row] * s.pick_s + (s.pick_s - 1);
+    if (ray_out) *ray_out = row;
     if (s.rays) {
         long long r = row / s.n_samples;
+        if (ray_out) *ray_out = r;
         const float* ray = s.rays + r * 6;
         float zz = s.z[row];
         float d0 = ray[3], d1 = ray[4], d2 = ray[5];

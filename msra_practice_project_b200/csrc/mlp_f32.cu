@@ -127,13 +127,16 @@ __global__ void siren_encode_kernel(RowSource src, long long row0, long long row
 
 // ---- narrow heads (N <= 3 outputs): one warp per row ---------------------------------------------
 // out[row*4 + col0 + n] = act(x[row,:] . W[n,:] + b[n]);  act: 1 relu, 2 sigmoid
+// pick != NULL (b2r_mlp_f32_last_sigma): row i is the last sample of ray pick[i] and its result goes to that row of raw.
 template <int N>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__ X, long long ldx, int K,
                                                        const float* __restrict__ W, const float* __restrict__ b,
-                                                       long long rows, int act, float* __restrict__ raw, int col0) {
+                                                       long long rows, int act, float* __restrict__ raw, int col0,
+                                                       const int* __restrict__ pick = nullptr, int pick_s = 0) {
     const int lane = threadIdx.x & 31;
     long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     if (row >= rows) return;
+    const long long out_row = pick ? (long long)pick[row] * pick_s + (pick_s - 1) : row;
     float acc[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) acc[n] = 0.f;
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
         for (int n = 0; n < N; ++n) {
             float v = __fadd_rn(acc[n], b[n]);
             v = act == 1 ? fmaxf(v, 0.f) : 1.0f / (1.0f + expf(-v));
-            raw[row * 4 + col0 + n] = v;
+            raw[out_row * 4 + col0 + n] = v;
         }
     }
 }
@@ -293,6 +296,8 @@ __global__ void __launch_bounds__(256) siren_first_layer_kernel(const float* __r
 // 2 = bf16 tensor cores (bgemm.cuh: fp32 buffers converted while staging, MN-major operands instead of transposes).
 // thread_local, set at every API entry: the library stays re-entrant (nn.DataParallel calls it from one thread per GPU).
 static thread_local int t_gemm_mode = 0;
+// b2r_mlp_f32_last_sigma on a latent batch: latent of every gathered row (FiLM scale / shift row of the sine epilogue)
+static thread_local const int* t_row_lat = nullptr;
 
 template <bool kPT, bool kQT>
 static int launch_gemm(GemmArgs g, cudaStream_t st, const char* what) {
@@ -319,6 +324,7 @@ static int fwd_layer(const float* X, long long ldx, Lin L, int k_off, int K, flo
     g.P = X; g.ldp = ldx; g.Q = L.W + k_off; g.ldq = L.in; g.C = Y; g.ldc = ldy;
     g.I = rows; g.J = L.out; g.R = K; g.r_chunk = K; g.epi = epi; g.bias = L.b;
     g.gamma = gamma; g.beta = beta; g.pre = pre; g.ldpre = 256;
+    if (gamma && t_row_lat) { g.row_lat = t_row_lat; g.lat_stride = B2R_FILM_PARAMS; }
     return launch_gemm<false, false>(g, st, "mlp_f32 forward gemm");
 }
 // dX = G W[:, k_off:k_off+K]  (optionally += existing, optionally relu-masked by `mask`)
@@ -347,8 +353,9 @@ static int wgrad_layer(const float* G, long long ldg, const float* X, long long 
 #define B2R_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 
 // ---- NeRF forward on rows [row0, row0+rows) into workspace ws (indexed from 0) -----------------------
+// last_only: the rows are the gathered last samples of src.pick's rays; stop after the sigma head and scatter its output
 static int nerf_forward_rows(const float* params, const RowSource& src, long long row0, long long rows, NerfWs& ws,
-                             float* raw, cudaStream_t st) {
+                             float* raw, cudaStream_t st, bool last_only = false) {
     {
         long long threads = rows * 14;
         nerf_encode_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, row0, rows, ws.B5, ws.B9);
@@ -363,8 +370,10 @@ static int nerf_forward_rows(const float* params, const RowSource& src, long lon
     unsigned hgrid = (unsigned)((rows * 32 + 255) / 256);
     {
         Lin s = lin(params, nerf_layer(10));
-        head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.H[7], 256, 256, s.W, s.b, rows, 1, raw + row0 * 4, 3);
+        if (last_only) head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.H[7], 256, 256, s.W, s.b, rows, 1, raw, 3, src.pick + row0, src.pick_s);
+        else head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.H[7], 256, 256, s.W, s.b, rows, 1, raw + row0 * 4, 3);
         B2R_TRY(cuda_result(cudaGetLastError(), "nerf sigma head"));
+        if (last_only) return 0;
     }
     B2R_TRY(fwd_layer(ws.H[7], 256, lin(params, nerf_layer(8)), 0, 256, ws.B9, NerfWs::kB9, rows, EPI_STORE, st));
     B2R_TRY(fwd_layer(ws.B9, NerfWs::kB9, lin(params, nerf_layer(9)), 0, 280, ws.HD, 128, rows, EPI_RELU, st));
@@ -377,7 +386,7 @@ static int nerf_forward_rows(const float* params, const RowSource& src, long lon
 }
 
 static int film_forward_rows(const float* params, const float* film, bool use_dir, const RowSource& src, long long row0,
-                             long long rows, FilmWs& ws, float* raw, bool save, cudaStream_t st) {
+                             long long rows, FilmWs& ws, float* raw, bool save, cudaStream_t st, bool last_only = false) {
     film_encode_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(src, row0, rows, ws.X0, ws.B8);
     B2R_TRY(cuda_result(cudaGetLastError(), "film_encode"));
     B2R_TRY(fwd_layer(ws.X0, FilmWs::kX0, lin(params, film_layer(0, use_dir)), 0, 3, ws.H[0], ws.ldH[0], rows, EPI_FILM_SIN, st,
@@ -388,8 +397,10 @@ static int film_forward_rows(const float* params, const float* film, bool use_di
     unsigned hgrid = (unsigned)((rows * 32 + 255) / 256);
     {
         Lin s = lin(params, film_layer(8, use_dir));
-        head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.B8, FilmWs::kB8, 256, s.W, s.b, rows, 1, raw + row0 * 4, 3);
+        if (last_only) head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.B8, FilmWs::kB8, 256, s.W, s.b, rows, 1, raw, 3, src.pick + row0, src.pick_s);
+        else head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.B8, FilmWs::kB8, 256, s.W, s.b, rows, 1, raw + row0 * 4, 3);
         B2R_TRY(cuda_result(cudaGetLastError(), "film sigma head"));
+        if (last_only) return 0;
     }
     int kc = use_dir ? 259 : 256;
     B2R_TRY(fwd_layer(ws.B8, FilmWs::kB8, lin(params, film_layer(9, use_dir)), 0, kc, ws.HC, 256, rows, EPI_FILM_SIN, st,
@@ -403,7 +414,7 @@ static int film_forward_rows(const float* params, const float* film, bool use_di
 }
 
 static int siren_forward_rows(const float* params, const RowSource& src, long long row0, long long rows, SirenWs& ws, float* raw, bool save,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool last_only = false) {
     siren_encode_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(src, row0, rows, ws.X0, ws.B5, ws.B9);
     B2R_TRY(cuda_result(cudaGetLastError(), "siren_encode"));
     auto L = [&](int i) { return lin(params, siren_layer(i)); };
@@ -417,8 +428,10 @@ static int siren_forward_rows(const float* params, const RowSource& src, long lo
     unsigned hgrid = (unsigned)((rows * 32 + 255) / 256);
     {
         Lin s = L(10);
-        head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.H[7], 256, 256, s.W, s.b, rows, 1, raw + row0 * 4, 3);
+        if (last_only) head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.H[7], 256, 256, s.W, s.b, rows, 1, raw, 3, src.pick + row0, src.pick_s);
+        else head_fwd_kernel<1><<<hgrid, 256, 0, st>>>(ws.H[7], 256, 256, s.W, s.b, rows, 1, raw + row0 * 4, 3);
         B2R_TRY(cuda_result(cudaGetLastError(), "siren sigma head"));
+        if (last_only) return 0;
     }
     B2R_TRY(fwd_layer(ws.H[7], 256, L(8), 0, 256, ws.B9, SirenWs::kB, rows, EPI_STORE, st));                                                  // linear
     {
@@ -483,6 +496,64 @@ extern "C" int b2r_mlp_f32_fwd(int model_kind, const float* params, const float*
         }
     }
     return 0;
+}
+
+namespace b2r {
+// latent of every gathered row: source row = pick[i] * s + s - 1
+__global__ void row_latent_kernel(const int* __restrict__ pick, int n, int s, long long rows_per_latent, int n_latents, int* __restrict__ row_lat) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long lat = ((long long)pick[i] * s + (s - 1)) / rows_per_latent;
+    row_lat[i] = (int)(lat < n_latents ? lat : n_latents - 1);
+}
+}  // namespace b2r
+
+// The last interval of a ray is 1e10 (nerf/render.py:92): sign(sigma_pre) of the last sample decides the ray (include/b2r.h,
+// b2r_last_sample).  Re-evaluates the listed rays' last samples with the exact fp32 engine -- the same kernels, operand order
+// and rounding as b2r_mlp_f32_fwd, so the result equals what the fp32 path computes for that row bit for bit.
+extern "C" int b2r_mlp_f32_last_sigma(int model_kind, const float* params, const float* film, int use_dir, int n_latents,
+                                      long long rows_per_latent, const b2r_mlp_input* in, int samples_per_ray, const int* ray_ids,
+                                      int n_ids, float* raw_io, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace b2r;
+    t_gemm_mode = 0;
+    B2R_CHECK_ARG(known_kind(model_kind), "b2r_mlp_f32_last_sigma: unknown model kind %d", model_kind);
+    B2R_CHECK_ARG(params && raw_io && workspace && ray_ids, "b2r_mlp_f32_last_sigma: NULL pointer");
+    B2R_CHECK_ARG(model_kind != B2R_MODEL_FILM || film, "b2r_mlp_f32_last_sigma: FiLM model needs film params");
+    B2R_TRY(check_mlp_input(in));
+    B2R_CHECK_ARG(in->grid_n == 0, "b2r_mlp_f32_last_sigma: rays / x rows only");
+    B2R_CHECK_ARG(samples_per_ray >= 1 && (!in->rays || samples_per_ray == in->n_samples), "b2r_mlp_f32_last_sigma: samples_per_ray (%d) must equal n_samples in rays mode", samples_per_ray);
+    B2R_CHECK_ARG(n_ids >= 0 && n_latents >= 1 && (n_latents == 1 || rows_per_latent > 0), "b2r_mlp_f32_last_sigma: bad n_ids / n_latents / rows_per_latent");
+    const size_t lat_bytes = ((size_t)n_ids * 4 + 15) & ~(size_t)15;
+    B2R_CHECK_ARG(workspace_bytes >= b2r_mlp_f32_workspace_bytes(model_kind, n_ids, 0) + lat_bytes, "b2r_mlp_f32_last_sigma: workspace too small (%zu B)", workspace_bytes);
+    B2R_CHECK_ARG(aligned16(workspace) && aligned16(params), "b2r_mlp_f32_last_sigma: params / workspace must be 16-byte aligned");
+    if (n_ids == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    RowSource src = make_row_source(in);
+    src.pick = ray_ids; src.pick_s = samples_per_ray;
+    int* row_lat = (int*)workspace;
+    float* act = (float*)((char*)workspace + lat_bytes);
+    const bool batched = model_kind == B2R_MODEL_FILM && n_latents > 1;
+    if (batched) {
+        row_latent_kernel<<<(unsigned)((n_ids + 255) / 256), 256, 0, st>>>(ray_ids, n_ids, samples_per_ray, rows_per_latent, n_latents, row_lat);
+        B2R_TRY(cuda_result(cudaGetLastError(), "row_latent"));
+    }
+    int rc = 0;
+    for (long long r0 = 0; r0 < n_ids && rc == 0; r0 += kInferChunk) {
+        long long n = n_ids - r0 < kInferChunk ? n_ids - r0 : kInferChunk;
+        if (model_kind == B2R_MODEL_NERF) {
+            NerfWs ws(act, n);
+            rc = nerf_forward_rows(params, src, r0, n, ws, raw_io, st, true);
+        } else if (model_kind == B2R_MODEL_SIREN) {
+            SirenWs ws(act, n);
+            rc = siren_forward_rows(params, src, r0, n, ws, raw_io, false, st, true);
+        } else {
+            FilmWs ws(act, n);
+            t_row_lat = batched ? row_lat + r0 : nullptr;
+            rc = film_forward_rows(params, film, use_dir != 0, src, r0, n, ws, raw_io, false, st, true);
+            t_row_lat = nullptr;
+        }
+    }
+    return rc;
 }
 
 extern "C" size_t b2r_mlp_f32_bwd_scratch_bytes(int model_kind, long long rows) {

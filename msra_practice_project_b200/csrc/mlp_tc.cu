@@ -145,10 +145,12 @@ __global__ void film_pack_kernel(const float* __restrict__ params, const float* 
 // kSave (training forward): the relu bits of every activation are gathered into mk[jj] (tc_core.cuh: mask_put) and MODE 3
 // also writes relu(h_d) as bf16 into shared memory (block = this half at h_half), so that the spill thread can copy the
 // tile to global memory with the bulk-copy engine.
+// want_abs (MODE 1; warp-uniform: some row of this warp is the last sample of a ray and the sign check is on): asum += sum |w_sigma h|
+// of this half (the scale of the bf16 error band, tc_core.cuh LastFlag); only warps that hold a ray's last sample pay for it.
 template <int MODE, bool kSave>
 __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, uint32_t head_half, uint32_t h_half,
                                          const uint32_t (&xoff)[8], float& sigma, float& rgb0, float& rgb1, float& rgb2,
-                                         uint32_t (&mk)[4]) {
+                                         uint32_t (&mk)[4], bool want_abs = false, float* asum = nullptr) {
     constexpr int NJH = MODE == 3 ? 2 : 4;
 #pragma unroll
     for (int jj = 0; jj < NJH; ++jj) {
@@ -174,6 +176,18 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
                 sigma = fmaf(fmaxf(f[4 * q + 1], 0.f), w.y, sigma);
                 sigma = fmaf(fmaxf(f[4 * q + 2], 0.f), w.z, sigma);
                 sigma = fmaf(fmaxf(f[4 * q + 3], 0.f), w.w, sigma);
+            }
+            if (want_abs) {                                         // separate pass: keeps the hot loop's register allocation
+                float a = *asum;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 w = lds128(head_half + (uint32_t)(jj * 32 + q * 4) * 4u);
+                    a = fmaf(fmaxf(f[4 * q + 0], 0.f), fabsf(w.x), a);
+                    a = fmaf(fmaxf(f[4 * q + 1], 0.f), fabsf(w.y), a);
+                    a = fmaf(fmaxf(f[4 * q + 2], 0.f), fabsf(w.z), a);
+                    a = fmaf(fmaxf(f[4 * q + 3], 0.f), fabsf(w.w), a);
+                }
+                *asum = a;
             }
         }
         if (MODE == 3) {
@@ -228,7 +242,8 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
 // warps wait for "tile has been read" (spill_done) before they overwrite it in place.
 template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved) {
+nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved,
+               LastFlag lf) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,6 +296,7 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         const uint32_t xr = (uint32_t)(r & 7);
         const uint32_t tab = cx.smem + kTabOff;
         const uint32_t part = cx.smem + kPartOff + (uint32_t)(g * kRowsSub + r) * 16u;
+        const uint32_t part2 = cx.smem + kPart2Off + (uint32_t)(g * kRowsSub + r) * 4u;
         const uint32_t bar_id = 1 + g;                      // named barrier of this sub-tile's 8 warps
         const uint32_t act_local = cx.act_ready + 8 * g, act_leader = mapa(act_local, 0);
         const uint32_t acc_bar = cx.acc_full + 8 * g;
@@ -305,7 +321,11 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 if (kSave) *reinterpret_cast<uint4*>(saved + mask_off(n_sub, l, T, half, r)) = make_uint4(mk[0], mk[1], mk[2], mk[3]);
             };
             float pnt[3], vdir[3];
-            load_row(src, valid ? row : rows - 1, pnt, vdir);
+            long long ray = 0;
+            load_row(src, valid ? row : rows - 1, pnt, vdir, &ray);
+            const bool check_last = valid && last_of_ray(lf, src, row, ray);      // this row decides its ray's last interval
+            const bool warp_checks = __any_sync(0xffffffffu, check_last);
+            float asum = 0.f;
             if (!first_tile) spill_wait();                          // previous tile's h_d copy
             first_tile = false;
             {
@@ -345,7 +365,8 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 wait_acc();                                             // layers_pos.7 (+ sigma head)
                 spill_wait();
                 uint32_t mk[4] = {0u, 0u, 0u, 0u};
-                nerf_epi<1, kSave>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2, mk);
+                nerf_epi<1, kSave>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2, mk,
+                                   warp_checks, &asum);
                 arrive_act(act_local, act_leader, cx.rank, lane);
                 spill_sig();
                 put_mask(7, mk);
@@ -385,8 +406,10 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             }
             tc_fence_before();
             // combine the two halves' head partial sums and write raw[row] = (sigmoid rgb, relu sigma)
-            if (half == 1)
+            if (half == 1) {
                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part), "f"(rgb0), "f"(rgb1), "f"(rgb2), "f"(sigma) : "memory");
+                if (check_last) asm volatile("st.shared.f32 [%0], %1;" ::"r"(part2), "f"(asum) : "memory");
+            }
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             if (half == 0) {
                 float4 o2 = lds128(part);
@@ -396,8 +419,16 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     o.x = 1.0f / (1.0f + __expf(-(rgb0 + o2.x + bh.y)));
                     o.y = 1.0f / (1.0f + __expf(-(rgb1 + o2.y + bh.z)));
                     o.z = 1.0f / (1.0f + __expf(-(rgb2 + o2.z + bh.w)));
-                    o.w = fmaxf(sigma + o2.w + bh.x, 0.f);
+                    const float pre = sigma + o2.w + bh.x;
+                    o.w = fmaxf(pre, 0.f);
                     raw_out[row] = o;
+                    if (check_last) {
+                        // sign(pre) is a step function of the ray's colour (nerf/render.py:92): inside the bf16 error band
+                        // the fp32 path decides (b2r_mlp_f32_last_sigma)
+                        float a2;
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(a2) : "r"(part2));
+                        if (fabsf(pre) <= fmaf(lf.rel, asum + a2, lf.abs)) flag_ray(lf, ray);
+                    }
                 }
             }
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");         // partial slot reusable
@@ -483,7 +514,7 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h
 template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int sigma_only, float4* __restrict__ raw_out,
-               int n_latents, long long rows_per_latent, uint8_t* __restrict__ saved) {
+               int n_latents, long long rows_per_latent, uint8_t* __restrict__ saved, LastFlag lf) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -547,6 +578,15 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         uint32_t acc_phase[2] = {0u, 0u}, sp_phase[2] = {0u, 0u};
         bool first_tile = true;
         const size_t n_sub = (size_t)pl.n_pairs * 4;
+        // last-sample sign check (tc_core.cuh LastFlag): sine outputs are bounded by 1, so the error band of sigma_pre scales with
+        // |w_sigma|_1 (the same for every latent: FiLM only modulates the hidden layers)
+        float wl1 = 0.f;
+        if (lf.count && cq < 2) {
+            for (int i = 0; i < 64; ++i) {
+                const float4 w = lds128(tab + (uint32_t)(kFWS + 4 * i) * 4u);
+                wl1 += (fabsf(w.x) + fabsf(w.y)) + (fabsf(w.z) + fabsf(w.w));
+            }
+        }
         auto spill_sig = [&](int g) { if (kSave && lane == 0) mbar_arrive(cx.spill_ready + 8 * g); };
         auto spill_wait = [&](int g) { if (kSave) { mbar_wait(cx.spill_done + 8 * g, sp_phase[g]); sp_phase[g] ^= 1u; } };
         auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSubBytes; };
@@ -573,14 +613,18 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     asm volatile("bar.sync 3, 512;" ::: "memory");
                 }
             }
-            bool valid[2];
+            bool valid[2], chk[2];
             long long row[2];
+            int ray[2];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 row[g] = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
                 valid[g] = row[g] < rows;
                 float pnt[3], vdir[3];
-                load_row(src, valid[g] ? row[g] : rows - 1, pnt, vdir);
+                long long ray_ll = 0;
+                load_row(src, valid[g] ? row[g] : rows - 1, pnt, vdir, &ray_ll);
+                chk[g] = valid[g] && last_of_ray(lf, src, row[g], ray_ll);
+                ray[g] = (int)ray_ll;
                 if (!first_tile) spill_wait(g);                      // previous tile's last copy
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 // ---- input_layer on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
@@ -677,8 +721,10 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                         o.y = 1.0f / (1.0f + __expf(-((p0.y + p1.y) + (p2.y + p3.y) + bh.z)));
                         o.z = 1.0f / (1.0f + __expf(-((p0.z + p1.z) + (p2.z + p3.z) + bh.w)));
                     }
-                    o.w = fmaxf((p0.w + p1.w) + (p2.w + p3.w) + bh.x, 0.f);
+                    const float pre = (p0.w + p1.w) + (p2.w + p3.w) + bh.x;
+                    o.w = fmaxf(pre, 0.f);
                     raw_out[out_row] = o;
+                    if ((cq == 0 ? chk[0] : chk[1]) && fabsf(pre) <= fmaf(lf.rel, wl1, lf.abs)) flag_ray(lf, cq == 0 ? ray[0] : ray[1]);
                 }
             }
             asm volatile("bar.sync 3, 512;" ::: "memory");         // partial slots (and the aux rows they overlay) reusable
@@ -695,7 +741,7 @@ namespace tc {
 // SirenNeRF (mlp_tc_siren.cu)
 size_t siren_packed_bytes();
 int siren_pack(const float* params, void* packed_out, cudaStream_t st);
-int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, cudaStream_t st);
+int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, const b2r_last_sample* last, cudaStream_t st);
 size_t siren_saved_bytes(long long rows);
 int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, void* saved, cudaStream_t st);
 }  // namespace tc
@@ -748,8 +794,22 @@ int pair_grid(long long rows, unsigned* grid) {
 }  // namespace tc
 }  // namespace b2r
 
+namespace b2r {
+namespace tc {
+int check_last_sample(const b2r_last_sample* last, const b2r_mlp_input* in, const char* who) {
+    if (!last) return 0;
+    B2R_CHECK_ARG(last->count && last->ray_ids && last->capacity >= 0, "%s: last-sample check needs count / ray_ids", who);
+    B2R_CHECK_ARG(in->grid_n == 0, "%s: the last-sample check is for rays / x rows, not grid queries", who);
+    B2R_CHECK_ARG(last->samples_per_ray >= 1 && (!in->rays || last->samples_per_ray == in->n_samples),
+                  "%s: samples_per_ray (%d) must equal n_samples in rays mode", who, last->samples_per_ray);
+    B2R_CHECK_ARG(last->rel >= 0.f && last->abs >= 0.f, "%s: negative last-sample thresholds", who);
+    return 0;
+}
+}  // namespace tc
+}  // namespace b2r
+
 extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_mlp_input* in, float* raw_out,
-                              int sigma_only, void* stream) {
+                              int sigma_only, const b2r_last_sample* last, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(packed && raw_out, "b2r_mlp_tc_fwd: NULL pointer");
     B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out) & 15) == 0, "b2r_mlp_tc_fwd: packed / raw_out must be 16-byte aligned");
@@ -759,7 +819,9 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (rows == 0) return 0;
     B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM || model_kind == B2R_MODEL_SIREN, "b2r_mlp_tc_fwd: unknown model kind %d", model_kind);
     B2R_CHECK_ARG(!(sigma_only && model_kind != B2R_MODEL_FILM), "b2r_mlp_tc_fwd: sigma_only is a FiLM-SIREN mode");
-    if (model_kind == B2R_MODEL_SIREN) return tc::siren_fwd(packed, in, rows, raw_out, (cudaStream_t)stream);
+    rc = tc::check_last_sample(last, in, "b2r_mlp_tc_fwd");
+    if (rc) return rc;
+    if (model_kind == B2R_MODEL_SIREN) return tc::siren_fwd(packed, in, rows, raw_out, last, (cudaStream_t)stream);
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
@@ -767,11 +829,13 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (model_kind == B2R_MODEL_FILM) {
         rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
-        tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0, nullptr);
+        tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0, nullptr,
+                                                                              tc::make_last_flag(last));
     } else {
         rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
-        tc::nerf_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr);
+        tc::nerf_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr,
+                                                                              tc::make_last_flag(last));
     }
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
     return 0;
@@ -791,7 +855,7 @@ extern "C" int b2r_mlp_tc_pack_film_batched(const float* params, const float* fi
 }
 
 extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in, float* raw_out,
-                                           int sigma_only, void* stream) {
+                                           int sigma_only, const b2r_last_sample* last, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(packed && raw_out, "b2r_mlp_tc_fwd_film_batched: NULL pointer");
     B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out) & 15) == 0, "b2r_mlp_tc_fwd_film_batched: buffers must be 16-byte aligned");
@@ -803,6 +867,8 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
                   "b2r_mlp_tc_fwd_film_batched: rows_per_latent (%lld) must be a positive multiple of %d", rows_per_latent, 2 * tc::kRowsTile);
     B2R_CHECK_ARG(n_latents >= 1 && rows <= rows_per_latent * (long long)n_latents, "b2r_mlp_tc_fwd_film_batched: %lld rows need more than %d latents", rows, n_latents);
     if (rows == 0) return 0;
+    rc = tc::check_last_sample(last, in, "b2r_mlp_tc_fwd_film_batched");
+    if (rc) return rc;
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
@@ -810,7 +876,8 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
     if (rc) return rc;
     // n_latents == 1 still goes through the batched indexing (latent 0 for every row) when rows_per_latent covers all rows
     tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only,
-                                                                                            (float4*)raw_out, n_latents, rows_per_latent, nullptr);
+                                                                                            (float4*)raw_out, n_latents, rows_per_latent, nullptr,
+                                                                                            tc::make_last_flag(last));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd_film_batched");
     return 0;
 }
@@ -834,7 +901,8 @@ extern "C" int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_laten
     rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
     if (rc) return rc;
     tc::film_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, 0,
-                                                                                           (float4*)raw_out, n_latents, rows_per_latent, (uint8_t*)saved);
+                                                                                           (float4*)raw_out, n_latents, rows_per_latent, (uint8_t*)saved,
+                                                                                           tc::make_last_flag(nullptr));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd_film_batched");
     return 0;
 }
@@ -866,7 +934,7 @@ extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2
         rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
         tc::film_tc_kernel<true><<<fgrid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, 0,
-                                                                                               (float4*)raw_out, 1, 0, (uint8_t*)saved);
+                                                                                               (float4*)raw_out, 1, 0, (uint8_t*)saved, tc::make_last_flag(nullptr));
         B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd (FiLM-SIREN)");
         return 0;
     }
@@ -876,7 +944,7 @@ extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2
     rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
     if (rc) return rc;
     tc::nerf_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
-                                                                                           (float4*)raw_out, (uint8_t*)saved);
+                                                                                           (float4*)raw_out, (uint8_t*)saved, tc::make_last_flag(nullptr));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd");
     return 0;
 }

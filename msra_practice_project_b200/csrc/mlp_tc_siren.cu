@@ -137,7 +137,8 @@ __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t 
 // sine layer is stored thread-major for the reverse mode (mlp_tc_train.cu).
 template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved) {
+siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved,
+                LastFlag lf) {
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,6 +199,14 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
         uint32_t acc_phase[2] = {0u, 0u}, sp_phase[2] = {0u, 0u};
         bool first_tile = true;
         const size_t n_sub = (size_t)pl.n_pairs * 4;
+        // last-sample sign check (tc_core.cuh LastFlag): |h| <= 1, so the error band of sigma_pre scales with |w_sigma|_1
+        float wl1 = 0.f;
+        if (lf.count && cq < 2) {
+            for (int i = 0; i < 64; ++i) {
+                const float4 w = lds128(tab + (uint32_t)(kSWS + 4 * i) * 4u);
+                wl1 += (fabsf(w.x) + fabsf(w.y)) + (fabsf(w.z) + fabsf(w.w));
+            }
+        }
         // kSave: tile written (and fenced by arrive_act) -> spill thread; wait until the previous copy has read shared memory
         auto spill_sig = [&](int g) { if (kSave && lane == 0) mbar_arrive(cx.spill_ready + 8 * g); };
         auto spill_wait = [&](int g) { if (kSave) { mbar_wait(cx.spill_done + 8 * g, sp_phase[g]); sp_phase[g] ^= 1u; } };
@@ -211,14 +220,18 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
             tc_fence_after();
         };
         for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
-            bool valid[2];
+            bool valid[2], chk[2];
             long long row[2];
+            int ray[2];
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 row[g] = (2 * p + cx.rank) * kRowsTile + g * kRowsSub + r;
                 valid[g] = row[g] < rows;
                 float pnt[3], vdir[3];
-                load_row(src, valid[g] ? row[g] : rows - 1, pnt, vdir);
+                long long ray_ll = 0;
+                load_row(src, valid[g] ? row[g] : rows - 1, pnt, vdir, &ray_ll);
+                chk[g] = valid[g] && last_of_ray(lf, src, row[g], ray_ll);
+                ray[g] = (int)ray_ll;
                 if (!first_tile) spill_wait(g);                      // previous tile's h_d copy
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 // ---- layers_pos.0 on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
@@ -320,8 +333,10 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                     o.x = 1.0f / (1.0f + __expf(-((p0.x + p1.x) + (p2.x + p3.x) + bh.y)));
                     o.y = 1.0f / (1.0f + __expf(-((p0.y + p1.y) + (p2.y + p3.y) + bh.z)));
                     o.z = 1.0f / (1.0f + __expf(-((p0.z + p1.z) + (p2.z + p3.z) + bh.w)));
-                    o.w = fmaxf((p0.w + p1.w) + (p2.w + p3.w) + bh.x, 0.f);
+                    const float pre = (p0.w + p1.w) + (p2.w + p3.w) + bh.x;
+                    o.w = fmaxf(pre, 0.f);
                     raw_out[out_row] = o;
+                    if ((cq == 0 ? chk[0] : chk[1]) && fabsf(pre) <= fmaf(lf.rel, wl1, lf.abs)) flag_ray(lf, cq == 0 ? ray[0] : ray[1]);
                 }
             }
             asm volatile("bar.sync 3, 512;" ::: "memory");
@@ -341,13 +356,13 @@ int siren_pack(const float* params, void* packed_out, cudaStream_t st) {
     return 0;
 }
 
-int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, cudaStream_t st) {
+int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, const b2r_last_sample* last, cudaStream_t st) {
     unsigned grid = 0;
     int rc = pair_grid(rows, &grid);
     if (rc) return rc;
     rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes), "tc smem attribute");
     if (rc) return rc;
-    siren_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr);
+    siren_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr, make_last_flag(last));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd (SirenNeRF)");
     return 0;
 }
@@ -360,7 +375,8 @@ int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows,
     if (rc) return rc;
     rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes), "tc smem attribute");
     if (rc) return rc;
-    siren_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, (uint8_t*)saved);
+    siren_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, (uint8_t*)saved,
+                                                              make_last_flag(nullptr));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd (SirenNeRF)");
     return 0;
 }

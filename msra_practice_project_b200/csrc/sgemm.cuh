@@ -31,6 +31,7 @@ struct GemmArgs {
     float* pre; long long ldpre;            // optional pre-activation copy (EPI_FILM_SIN, saved for backward)
     const float* mask; long long ldmask;    // EPI_DGRAD: multiply by (mask[i,j] > 0) when non-null
     int accumulate;                          // EPI_DGRAD: add the existing C before masking
+    const int* row_lat; long long lat_stride;   // EPI_FILM_SIN (fp32 engine only): row i uses gamma / beta + row_lat[i] * lat_stride
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GPAD = 4;
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g) {
                     if (g.pre) g.pre[i * g.ldpre + j] = a_lin;
                     // sin(w0 * (gamma * x + beta)), w0 = 30 (pi_GAN/modules.py:22-25)
                     // gamma == NULL: plain SIREN layer sin(30 (W x + b)) (nerf/nerf.py:111-112)
-                    *c = g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[j], a_lin), g.beta[j]))) : sinf(__fmul_rn(30.0f, a_lin));
+                    const long long lo = g.row_lat ? (long long)g.row_lat[i] * g.lat_stride : 0;
+                    *c = g.gamma ? sinf(__fmul_rn(30.0f, __fadd_rn(__fmul_rn(g.gamma[lo + j], a_lin), g.beta[lo + j]))) : sinf(__fmul_rn(30.0f, a_lin));
                     break;
                 }
                 case EPI_DGRAD: {

@@ -189,7 +189,9 @@ constexpr uint32_t kTabOff = kRingOff + kStages * kStageBytes;          // fp32 
 constexpr uint32_t kTabBytes = kNerfTabFloats * 4;                      // 12,816
 constexpr uint32_t kPartOff = kTabOff + kTabBytes;                      // head partial sums: 2 x 128 x float4
 constexpr uint32_t kPartBytes = 2 * kRowsSub * 16;
-constexpr uint32_t kBarOff = kPartOff + kPartBytes;                     // mbarriers + TMEM slot
+constexpr uint32_t kPart2Off = kPartOff + kPartBytes;                   // NeRF last-sample check: the other column half's sum |w h|
+constexpr uint32_t kPart2Bytes = 2 * kRowsSub * 4;
+constexpr uint32_t kBarOff = kPart2Off + kPart2Bytes;                   // mbarriers + TMEM slot
 constexpr uint32_t kSmemBytes = kBarOff + 128 + 1024;                   // + alignment slack
 static_assert(kBarOff % 8 == 0 && kSmemBytes <= 232448, "shared-memory budget");
 
@@ -211,6 +213,32 @@ __device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
     c.spill_done = c.spill_ready + 16;     // spill thread -> epilogue warps: the bulk store has read the tile (count 1)
     c.rank = cluster_ctarank();
     return c;
+}
+
+// ---- last-sample sign check (include/b2r.h: b2r_last_sample) -----------------------------------------------------------
+// The kernels list every ray whose LAST sample's pre-relu sigma lies inside the bf16 error band; the host re-evaluates those
+// rows in fp32 (b2r_mlp_f32_last_sigma).  count == nullptr: off.
+struct LastFlag {
+    int* count;
+    int* ray_ids;
+    int capacity, s;
+    float rel, abs;
+};
+inline LastFlag make_last_flag(const b2r_last_sample* l) {
+    LastFlag f{nullptr, nullptr, 0, 1, 0.f, 0.f};
+    if (l) { f.count = l->count; f.ray_ids = l->ray_ids; f.capacity = l->capacity; f.s = l->samples_per_ray; f.rel = l->rel; f.abs = l->abs; }
+    return f;
+}
+// is `row` the last sample of its ray?  ray = load_row's ray_out (rays mode: row / n_samples == row / lf.s)
+__device__ __forceinline__ bool last_of_ray(const LastFlag& lf, const RowSource& src, long long row, long long& ray) {
+    if (!lf.count) return false;
+    if (src.rays) return row - ray * src.n_samples == src.n_samples - 1;
+    ray = row / lf.s;
+    return row - ray * lf.s == lf.s - 1;
+}
+__device__ __forceinline__ void flag_ray(const LastFlag& lf, long long ray) {
+    const int slot = atomicAdd(lf.count, 1);
+    if (slot < lf.capacity) lf.ray_ids[slot] = (int)ray;
 }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {

@@ -53,7 +53,8 @@ def gather_image(rgb: torch.Tensor, depth: torch.Tensor, acc: torch.Tensor, out:
 
 
 def render_image_sharded(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
-                         fine_sample_num, *, t_rand_full: torch.Tensor | None = None, precision=None, group=None):
+                         fine_sample_num, *, t_rand_full: torch.Tensor | None = None, precision=None, group=None,
+                         exact_last_sample=None):
     """render_image (nerf/render.py:150-167) with the frame's rays sharded over the ranks of
     `group`; returns (rgb[H,W,3], depth[H,W,1], acc[H,W,1]) CUDA tensors on every rank.
     Every rank draws the SAME global jitter (same seed) and slices its rows, so the result does not
@@ -69,7 +70,8 @@ def render_image_sharded(width, height, focal, pose, near, far, coarse_model, fi
     with torch.no_grad():
         o = nerf_render.render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model,
                                             coarse_sample_num, fine_sample_num, ray_begin=begin, ray_count=count,
-                                            t_rand=t_rand_full[begin:begin + count], precision=precision)
+                                            t_rand=t_rand_full[begin:begin + count], precision=precision,
+                                            exact_last_sample=exact_last_sample)
         out = torch.empty((n, 5), dtype=torch.float32, device=dev)
         gather_image(o[3], o[4], o[5], out, n, rank, world, group)
     h, w = int(height), int(width)

@@ -7,7 +7,10 @@ re-exported because those callers rely on the star-import leaking them (train_ne
 
 Backwards-compatible keyword-only additions: ``t_rand`` (inject the jitter the reference draws
 with torch.rand, for parity runs), ``z_lin`` / ``u`` (inject the two torch.linspace vectors),
-``precision`` ("bf16" tensor-core MLP or "fp32"), ``stages`` (dict that receives intermediates).
+``precision`` ("bf16" tensor-core MLP or "fp32"), ``stages`` (dict that receives intermediates),
+``exact_last_sample`` (None = the module default ops.get_exact_last_sample(), which is True: the bf16 path
+re-evaluates in fp32 the last sample of every ray whose sigma is inside the bf16 error band of zero, because the
+1e10 last interval of nerf/render.py:92 turns the SIGN of that sigma into a whole-ray decision).
 
 There is no CPU path: tensors and models must live on a CUDA device.
 """
@@ -43,16 +46,17 @@ def sample_pdf(bins, weights, N_samples, *, u=None):
     return ops.sample_pdf(bins, weights, int(N_samples), u=u)["samples"]
 
 
-def run_network(ray_samples, view_dirs, network, chunk=1024 * 64, *, precision=None):
+def run_network(ray_samples, view_dirs, network, chunk=1024 * 64, *, precision=None, exact_last_sample=None):
     """nerf/render.py:59-75 -- evaluate ``network`` on every sample point -> [N,S,4].
 
     ``chunk`` is accepted for signature compatibility; the fused kernel has O(tile) memory so the
-    points are evaluated in one launch."""
+    points are evaluated in one launch.  The rows keep their [N,S] structure, so the bf16 path can apply
+    the last-sample sign check exactly as render_rays does."""
     n, s = ray_samples.shape[0], ray_samples.shape[1]
     pts = ray_samples.reshape(-1, 3)
     vd = view_dirs[:, None, :].expand(n, s, 3).reshape(-1, 3)
     x = torch.cat([pts, vd], -1)
-    return ops.mlp(network, x=x, precision=precision).reshape(n, s, 4)
+    return ops.mlp(network, x=x, precision=precision, exact_last_sample=exact_last_sample, samples_per_ray=s).reshape(n, s, 4)
 
 
 def raw_to_outputs(raw, z_vals, rays_d):
@@ -62,14 +66,16 @@ def raw_to_outputs(raw, z_vals, rays_d):
 
 def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num, *,
                 t_rand=None, z_lin=None, u=None, precision=None, stages=None, coarse_no_grad=False,
-                exact_last_sample=False):
+                exact_last_sample=None):
     """nerf/render.py:106-147 -- coarse pass, sample_pdf on the un-jittered mids with
     weights[:,1:-1], sort-merge, fine pass on all Sc+Sf samples.  Returns the reference's 6-tuple
     (rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f).  ``coarse_no_grad`` runs the coarse pass in
     inference mode (used by the pi-GAN wrappers, whose loss never touches the coarse outputs).
-    ``exact_last_sample`` re-evaluates the LAST sample of every ray with the fp32 MLP when the bf16
-    tensor-core path is in use: its interval is 1e10 (nerf/render.py:92), so alpha_last is a step
-    function of sign(sigma_last) and a bf16 rounding flips ~0.2 % of rays."""
+    ``exact_last_sample`` (default on): the bf16 tensor-core path lists the rays whose LAST sample's
+    pre-relu sigma lies inside the bf16 error band and re-evaluates those rows with the fp32 engine:
+    that sample's interval is 1e10 (nerf/render.py:92), so alpha_last is a step function of
+    sign(sigma_last) and a bf16 rounding would flip ~0.2 % of rays by up to 0.6.
+    Applies to passes that run without gradients (renders; the pi-GAN coarse pass)."""
     if not isinstance(rays, torch.Tensor):
         rays = torch.as_tensor(np.asarray(rays), dtype=torch.float32)
     if not rays.is_cuda:
@@ -106,14 +112,9 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
 
 
 def _mlp_rays(model, rays, z, precision, exact_last_sample):
-    """run_network on (rays, z) -> raw[N,S,4]; optionally the last sample of each ray in fp32."""
+    """run_network on (rays, z) -> raw[N,S,4] (bf16 inference: with the last-sample sign check, ops.mlp)."""
     n, s = z.shape
-    raw = ops.mlp(model, rays=rays, z=z, precision=precision).view(n, s, 4)
-    used = precision or ops.get_mlp_precision()
-    if exact_last_sample and used == "bf16" and not raw.requires_grad:
-        last = ops.mlp(model, rays=rays, z=z[:, -1:].contiguous(), precision="fp32")
-        raw[:, -1, :] = last
-    return raw
+    return ops.mlp(model, rays=rays, z=z, precision=precision, exact_last_sample=exact_last_sample).view(n, s, 4)
 
 
 def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
@@ -125,7 +126,7 @@ def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
 
 def render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                         fine_sample_num, chunk=REFERENCE_RAY_CHUNK, *, ray_begin=0, ray_count=None, t_rand=None,
-                        precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=False):
+                        precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=None):
     """Device-resident core of render_image: renders flattened pixel rows [ray_begin, +ray_count)
     and returns the six per-ray outputs of the fine AND coarse pass as CUDA tensors.  Rays are
     generated on the device (K1); ``launch_rays`` bounds the rays per kernel launch sequence."""
@@ -150,7 +151,7 @@ def render_image_device(width, height, focal, pose, near, far, coarse_model, fin
 
 
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=False):
+                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None):
     """nerf/render.py:150-167 -- numpy (H,W,3), (H,W,1), (H,W,1) = fine rgb / depth / acc."""
     with torch.no_grad():
         out = render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
@@ -162,18 +163,18 @@ def render_image(width, height, focal, pose, near, far, coarse_model, fine_model
 
 
 def render_video(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                 chunk=1024 * 16):
+                 chunk=1024 * 16, *, precision=None, exact_last_sample=None):
     """nerf/render.py:170-182 -- stacked per-pose render_image outputs."""
     rgb_video, depth_video, acc_video = [], [], []
     for _, p in enumerate(tqdm(poses)):
         rgb, depth, acc = render_image(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
-                                       fine_sample_num, chunk)
+                                       fine_sample_num, chunk, precision=precision, exact_last_sample=exact_last_sample)
         rgb_video.append(rgb); depth_video.append(depth); acc_video.append(acc)
     return np.stack(rgb_video), np.stack(depth_video), np.stack(acc_video)
 
 
 def render_video_u8(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                    chunk=1024 * 16, *, precision=None):
+                    chunk=1024 * 16, *, precision=None, exact_last_sample=None):
     """render_video + to8b (what show_nerf.py:55-66 does per frame on the host) with the quantisation on the device and the
     frames streamed out through two pinned buffers: frame k's 1.9 MB uint8 copy overlaps frame k+1's render, and the host
     waits only once per frame on an event.  Returns rgb uint8 [P,H,W,3]."""
@@ -181,14 +182,15 @@ def render_video_u8(width, height, focal, poses, near, far, coarse_model, fine_m
     h, w = int(height), int(width)
     poses = list(poses)
     out = np.empty((len(poses), h, w, 3), dtype=np.uint8)
-    pinned = [torch.empty((h, w, 3), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    # device="cpu": the reference's scripts set a CUDA default tensor type (demo_view.py, test_nerf.py)
+    pinned = [torch.empty((h, w, 3), dtype=torch.uint8, device="cpu", pin_memory=True) for _ in range(2)]
     events = [torch.cuda.Event() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
     pending = [None, None]
     with torch.no_grad():
         for k, p in enumerate(tqdm(poses)):
             o = render_image_device(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
-                                    fine_sample_num, chunk, precision=precision)
+                                    fine_sample_num, chunk, precision=precision, exact_last_sample=exact_last_sample)
             frame = ops.to8b(o[3]).reshape(h, w, 3)
             slot = k & 1
             if pending[slot] is not None:                       # the buffer's previous frame must have landed

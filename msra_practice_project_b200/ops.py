@@ -15,10 +15,10 @@ import numpy as np
 import torch
 
 from . import _lib, models
-from ._lib import MlpInput, check, lib, ptr
+from ._lib import LastSample, MlpInput, check, lib, ptr
 
 # MLP arithmetic used when no gradient is required: "bf16" = fused tcgen05 kernel (mlp_tc.cu),
-# "fp32" = layer-wise CUDA-core path (mlp_f32.cu).  Gradients always use the fp32 path.
+# "fp32" = layer-wise CUDA-core path (mlp_f32.cu).  The arithmetic of the gradient path is _GRAD_PRECISION below.
 _MLP_PRECISION = "bf16"
 
 
@@ -52,6 +52,65 @@ def set_grad_precision(p: str) -> str:
 
 def get_grad_precision() -> str:
     return _GRAD_PRECISION
+
+
+# ---- the last interval of every ray (nerf/render.py:92: dists[-1] = 1e10) ------------------------------------------------------
+# alpha_last is a step function of sign(sigma_last), so a bf16-rounded density that crosses zero at the LAST sample flips a whole
+# ray.  The bf16 kernels list the rays whose last pre-relu sigma is inside the bf16 error band
+#     |sigma_pre| <= rel * scale + abs      (include/b2r.h: b2r_last_sample; scale = sum |w_sigma h| for the ReLU trunk,
+#                                            |w_sigma|_1 for the sine trunks)
+# and those rows (a few % of the rays) are re-evaluated by the exact fp32 engine.  On by default for every no-grad bf16 render;
+# `exact_last_sample=False` / set_exact_last_sample(False) gives the raw bf16 result.  rel: >= 8 standard deviations of the measured
+# bf16 error of sigma_pre relative to the scale.
+_EXACT_LAST = True
+_LAST_REL = {models.KIND_NERF: 2.0 ** -7, models.KIND_FILM: 2.0 ** -8, models.KIND_SIREN: 2.0 ** -8}
+_LAST_ABS = 1e-6
+last_sample_stats = {"calls": 0, "rays": 0, "flagged": 0}      # running totals (bench / tests report the flagged fraction)
+
+
+def set_exact_last_sample(flag: bool) -> bool:
+    global _EXACT_LAST
+    old, _EXACT_LAST = _EXACT_LAST, bool(flag)
+    return old
+
+
+def get_exact_last_sample() -> bool:
+    return _EXACT_LAST
+
+
+def set_last_sample_band(kind: int, rel: float, abs_: float | None = None) -> None:
+    """Override the flagging band of one model kind (calibration runs)."""
+    global _LAST_ABS
+    _LAST_REL[kind] = float(rel)
+    if abs_ is not None:
+        _LAST_ABS = float(abs_)
+
+
+def _last_sample_begin(kind: int, rows: int, spr: int, dev):
+    """(LastSample struct, tensors to keep alive) for a launch of `rows` rows with `spr` samples per ray."""
+    n_rays = rows // spr
+    count = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ids = torch.empty((max(n_rays, 1),), dtype=torch.int32, device=dev)
+    ls = LastSample(int(spr), int(n_rays), count.data_ptr(), ids.data_ptr(), float(_LAST_REL[kind]), float(_LAST_ABS))
+    return ls, (count, ids)
+
+
+def _last_sample_finish(kind: int, flat, film, use_dir, n_latents, rows_per_latent, inp, spr: int, keep, raw) -> int:
+    """Reads the number of flagged rays (the one host sync of the pass) and re-evaluates their last samples in fp32."""
+    count, ids = keep
+    n_rays = ids.shape[0]
+    n = min(int(count.item()), n_rays)
+    last_sample_stats["calls"] += 1
+    last_sample_stats["rays"] += int(n_rays)
+    last_sample_stats["flagged"] += n
+    if n == 0:
+        return 0
+    dev = raw.device
+    ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, n, 0) + ((n * 4 + 15) & ~15)
+    ws = torch.empty((ws_bytes // 4,), dtype=torch.float32, device=dev)
+    check(lib().b2r_mlp_f32_last_sigma(kind, ptr(flat), ptr(film), int(use_dir), int(n_latents), int(rows_per_latent), C.byref(inp), int(spr),
+                                       ids.data_ptr(), n, ptr(raw), ptr(ws), ws_bytes, _stream(raw)), "b2r_mlp_f32_last_sigma")
+    return n
 
 
 def _cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
@@ -517,10 +576,14 @@ def mlp_film_batched_train(model, film: torch.Tensor, rays: torch.Tensor, z: tor
 
 
 def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, x: torch.Tensor | None = None,
-        grid: tuple | None = None, precision: str | None = None, sigma_only: bool = False) -> torch.Tensor:
+        grid: tuple | None = None, precision: str | None = None, sigma_only: bool = False,
+        exact_last_sample: bool | None = None, samples_per_ray: int | None = None) -> torch.Tensor:
     """Evaluate the radiance field on rows described by (rays, z) | x | grid -> raw[rows,4]
     (run_network + network.forward, nerf/render.py:59-75).  Differentiable wrt the model's
-    parameters (and FiLM parameters) when any of them requires grad and grad mode is on."""
+    parameters (and FiLM parameters) when any of them requires grad and grad mode is on.
+
+    bf16 inference on ray samples -- (rays, z), or x with ``samples_per_ray`` given -- also runs the last-sample sign check
+    (see _EXACT_LAST above) unless ``exact_last_sample`` is False."""
     kind = models.model_kind(model)
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
     use_dir = bool(getattr(net, "use_dir", True))
@@ -556,8 +619,14 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
     with torch.cuda.device(dev):
         if precision == "bf16":
             packed = _packed_weights(net, kind, flat, film, use_dir)
-            check(lib().b2r_mlp_tc_fwd(kind, ptr(packed), int(use_dir), C.byref(inp), ptr(raw), int(sigma_only), _stream(flat)),
-                  "b2r_mlp_tc_fwd")
+            spr = z.shape[1] if rays is not None else (int(samples_per_ray) if (x is not None and samples_per_ray) else 0)
+            want_last = (_EXACT_LAST if exact_last_sample is None else bool(exact_last_sample)) and spr > 0 and not sigma_only \
+                and rows % spr == 0
+            ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if want_last else (None, None)
+            check(lib().b2r_mlp_tc_fwd(kind, ptr(packed), int(use_dir), C.byref(inp), ptr(raw), int(sigma_only),
+                                       C.byref(ls) if ls is not None else None, _stream(flat)), "b2r_mlp_tc_fwd")
+            if ls is not None:
+                _last_sample_finish(kind, flat, film, use_dir, 1, 0, inp, spr, ls_keep, raw)
         else:
             ws_bytes = lib().b2r_mlp_f32_workspace_bytes(kind, rows, 0)
             ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=dev)
@@ -573,7 +642,7 @@ def mlp_points(model, x: torch.Tensor) -> torch.Tensor:
 
 
 def mlp_film_batched(model, film: torch.Tensor, rays: torch.Tensor, z: torch.Tensor, rows_per_latent: int,
-                     sigma_only: bool = False) -> torch.Tensor:
+                     sigma_only: bool = False, exact_last_sample: bool | None = None) -> torch.Tensor:
     """FiLM-SIREN on (rays, z) rows for B latents in ONE launch (Generator.forward's per-latent loop, pi_GAN/modules.py:176-184):
     film[B,9,512]; rows [b * rows_per_latent, (b+1) * rows_per_latent) use latent b.  Inference only (bf16 tensor-core kernel)."""
     kind = models.model_kind(model)
@@ -598,8 +667,13 @@ def mlp_film_batched(model, film: torch.Tensor, rays: torch.Tensor, z: torch.Ten
     with torch.cuda.device(dev):
         check(lib().b2r_mlp_tc_pack_film_batched(ptr(flat), ptr(film), int(use_dir), n_lat, ptr(packed), _stream(flat)),
               "b2r_mlp_tc_pack_film_batched")
+        spr = z.shape[1]
+        want_last = (_EXACT_LAST if exact_last_sample is None else bool(exact_last_sample)) and not sigma_only
+        ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if want_last else (None, None)
         check(lib().b2r_mlp_tc_fwd_film_batched(ptr(packed), n_lat, int(rows_per_latent), C.byref(inp), ptr(raw), int(sigma_only),
-                                                _stream(flat)), "b2r_mlp_tc_fwd_film_batched")
+                                                C.byref(ls) if ls is not None else None, _stream(flat)), "b2r_mlp_tc_fwd_film_batched")
+        if ls is not None:
+            _last_sample_finish(kind, flat, film, use_dir, n_lat, int(rows_per_latent), inp, spr, ls_keep, raw)
     del keep
     return raw
 

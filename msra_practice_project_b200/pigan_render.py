@@ -37,25 +37,25 @@ def camera_pos_to_transform_matrix(radius, theta, phi):
 
 
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                 chunk=1024 * 16, *, t_rand=None, precision=None):
+                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None):
     """pi_GAN/render.py:195-206 -- fine rgb as a torch tensor [H,W,3] on the device, carrying the
     autograd graph to the model parameters and the FiLM parameters (pi_GAN/train.py:134,
     synthesis.py:107).  In pi-GAN coarse_model is fine_model and only the fine rgb is consumed, so
     the coarse pass carries no gradient and runs in inference mode."""
     out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                  chunk, t_rand, precision, coarse_no_grad=True)
+                  chunk, t_rand, precision, coarse_no_grad=True, exact_last_sample=exact_last_sample)
     return out[3].reshape(int(height), int(width), 3)
 
 
 def _render(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk, t_rand, precision,
-            coarse_no_grad=False, exact_last_sample=False):
+            coarse_no_grad=False, exact_last_sample=None):
     return render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk,
                                t_rand=t_rand, precision=precision, coarse_no_grad=coarse_no_grad,
                                exact_last_sample=exact_last_sample)
 
 
 def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
-                    fine_sample_num, chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=False):
+                    fine_sample_num, chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None):
     """pi_GAN/render.py:209-226 -- numpy (H,W,3), (H,W,1), (H,W,1)."""
     with torch.no_grad():
         out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
@@ -66,19 +66,19 @@ def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_mo
 
 
 def render_video_np(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num,
-                    fine_sample_num, chunk=1024 * 16):
+                    fine_sample_num, chunk=1024 * 16, *, precision=None, exact_last_sample=None):
     """pi_GAN/render.py:229-241.  The reference unpacks three values from render_image (which returns
     one tensor) and so raises as shipped; this calls render_image_np as evidently meant."""
     rgb_video, depth_video, acc_video = [], [], []
     for _, p in enumerate(tqdm(poses)):
         rgb, depth, acc = render_image_np(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
-                                          fine_sample_num, chunk)
+                                          fine_sample_num, chunk, precision=precision, exact_last_sample=exact_last_sample)
         rgb_video.append(rgb); depth_video.append(depth); acc_video.append(acc)
     return np.stack(rgb_video), np.stack(depth_video), np.stack(acc_video)
 
 
 def render_batch(model, film_params, poses, width, height, focal, near, far, coarse_sample_num, fine_sample_num, *,
-                 t_rand=None, precision=None):
+                 t_rand=None, precision=None, exact_last_sample=None):
     """Batched counterpart of Generator.forward's per-latent loop (pi_GAN/modules.py:176-184):
     film_params[B,9,512], poses[B,4,4] -> images [B,3,H,W].  This is the latent-sharding unit for
     multi-GPU runs (each rank renders its slice of B).
@@ -101,7 +101,7 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
             model.set_film_params(film_params[i])
             tr = None if t_rand is None else t_rand[i]
             imgs.append(render_image(width, height, focal, poses[i], near, far, model, model, coarse_sample_num,
-                                     fine_sample_num, t_rand=tr, precision=precision))
+                                     fine_sample_num, t_rand=tr, precision=precision, exact_last_sample=exact_last_sample))
         return torch.stack(imgs).permute(0, 3, 1, 2).contiguous()
     dev = next(model.parameters()).device
     n = w * h
@@ -115,11 +115,11 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
         u = torch.linspace(0.0, 1.0, steps=sf, device="cpu").to(dev)
         film = torch.as_tensor(film_params, dtype=torch.float32).to(dev).reshape(b, 9, 512)
         z, mids = ops.stratified_z(z_lin, t_all)
-        raw = ops.mlp_film_batched(model, film, rays, z, n * sc)
+        raw = ops.mlp_film_batched(model, film, rays, z, n * sc, exact_last_sample=exact_last_sample)
         _, _, _, wts, _ = ops.composite_forward(raw, z, rays[:, 1], True)
         z_f = ops.sample_pdf(mids, wts[:, 1:-1], sf, u=u, z_coarse=z, want_samples=False)["sorted"]
         if not grad:
-            raw_f = ops.mlp_film_batched(model, film, rays, z_f, n * (sc + sf))
+            raw_f = ops.mlp_film_batched(model, film, rays, z_f, n * (sc + sf), exact_last_sample=exact_last_sample)
             rgb, _, _, _, _ = ops.composite_forward(raw_f, z_f, rays[:, 1], False)
     if grad:
         film_g = film_params.to(dev).reshape(b, 9, 512)

@@ -44,7 +44,7 @@ def test_bad_arguments_return_negative_and_set_message():
     rc = lib.b2r_sample_pdf(None, 0, None, 0, None, 1, 4, 4, None, 0, None, None, None, None)
     assert rc < 0
     inp = _lib.MlpInput()
-    rc = lib.b2r_mlp_tc_fwd(0, 16, 1, C.byref(inp), 16, 0, None)
+    rc = lib.b2r_mlp_tc_fwd(0, 16, 1, C.byref(inp), 16, 0, None, None)
     assert rc < 0 and b"exactly one" in lib.b2r_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "b2r_mlp_tc_fwd")
@@ -76,9 +76,20 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     assert lib.b2r_mlp_tc_train_fwd_film_batched(16, 2, 256, C.byref(inp), 16, 16, 1 << 30, None) < 0 and b"multiple of 512" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_fwd(0, 16, C.byref(inp), 16, 16, 64, None) < 0 and b"too small" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_bwd(0, 16, 512, 16, 16, 16, 16, 64, 16, None) < 0 and b"scratch" in lib.b2r_last_error()
-    assert lib.b2r_mlp_tc_fwd_film_batched(16, 2, 100, C.byref(inp), 16, 0, None) < 0 and b"multiple of 512" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_fwd_film_batched(16, 2, 100, C.byref(inp), 16, 0, None, None) < 0 and b"multiple of 512" in lib.b2r_last_error()
     inp.n_rays = 1024
-    assert lib.b2r_mlp_tc_fwd_film_batched(16, 1, 512, C.byref(inp), 16, 0, None) < 0 and b"latents" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_fwd_film_batched(16, 1, 512, C.byref(inp), 16, 0, None, None) < 0 and b"latents" in lib.b2r_last_error()
+    # last-sample sign check (b2r_last_sample): argument validation of the kernels that flag and of the fp32 re-evaluation
+    ls = _lib.LastSample(64, 8, None, None, 0.01, 0.0)
+    assert lib.b2r_mlp_tc_fwd(0, 16, 1, C.byref(inp), 16, 0, C.byref(ls), None) < 0 and b"count / ray_ids" in lib.b2r_last_error()
+    rin = _lib.MlpInput()
+    rin.rays, rin.z, rin.n_rays, rin.n_samples = 256, 256, 8, 64
+    ls = _lib.LastSample(32, 8, 16, 16, 0.01, 0.0)
+    assert lib.b2r_mlp_tc_fwd(0, 16, 1, C.byref(rin), 16, 0, C.byref(ls), None) < 0 and b"samples_per_ray" in lib.b2r_last_error()
+    assert lib.b2r_mlp_f32_last_sigma(0, 16, None, 1, 1, 0, C.byref(rin), 32, 16, 4, 16, 16, 1 << 30, None) < 0 and b"samples_per_ray" in lib.b2r_last_error()
+    assert lib.b2r_mlp_f32_last_sigma(0, 16, None, 1, 1, 0, C.byref(rin), 64, 16, 4, 16, 16, 64, None) < 0 and b"workspace too small" in lib.b2r_last_error()
+    assert lib.b2r_mlp_f32_last_sigma(1, 16, None, 1, 1, 0, C.byref(rin), 64, 16, 4, 16, 16, 1 << 30, None) < 0 and b"film" in lib.b2r_last_error()
+    assert lib.b2r_mlp_f32_last_sigma(0, 16, None, 1, 1, 0, C.byref(rin), 64, 16, 0, 16, 16, 1 << 30, None) == 0          # nothing flagged
     assert lib.b2r_mlp_tc_pack_film_batched(None, None, 1, 2, None, None) < 0
     assert lib.b2r_adam_step(None, None, None, None, 4, None, 1e-3, 0.1, 0.0, 0.9, 0.999, 1e-8, 1.0, None) < 0
     assert lib.b2r_to8b(None, 4, None, None) < 0 and lib.b2r_to8b(None, 0, None, None) == 0
