@@ -65,20 +65,28 @@ def peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
 
 
-# ---- CPU arm: the numpy oracle (port of the reference algorithm) on the host cores -----------------------
+# ---- CPU arm: the reference's own render path on the host cores ---------------------------------------------------
 def cpu_baseline(args, n_rays: int, repeats: int = 1):
-    """Times the ATen port of the reference path (oracle/torch_port.py: the same torch CPU ops the
-    reference calls, MKL on every host thread) on a bounded sample of the same workload (same weights,
-    sample counts, camera, a contiguous block of the frame's rays); rays are independent, so rays/s
-    extrapolates linearly to the frame."""
+    """Times the reference's CPU implementation of the path on a bounded sample of the same workload (same weights -- seed 0
+    reproduces the reference's init bit for bit --, sample counts, camera, a contiguous block of the frame's rays); rays are
+    independent, so rays/s extrapolates linearly to the frame.
+
+    kind "reference": the UNMODIFIED nerf/render.py + nerf/nerf.py (oracle/_ref, a git-ignored verbatim copy made by
+    tools/install_ref.sh; oracle/ref_loader.py) -- render_rays called exactly as nerf/render.py:160 calls it, torch CPU ops on
+    every host thread.  kind "port": oracle/torch_port.py (the same ATen calls restated) when no copy of the reference is
+    reachable."""
     import torch
-    from oracle import render_oracle as orc, torch_port as tp
+    from oracle import ref_loader, render_oracle as orc, torch_port as tp
     from msra_practice_project_b200 import models, pigan_render
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    ref = ref_loader.load_reference()
     torch.manual_seed(0)
-    c, f = models.NeRF(), models.NeRF()
-    sc_, sf_ = dict(c.state_dict()), dict(f.state_dict())
+    if ref is not None:
+        c, f = ref["nerf_nerf"].NeRF(), ref["nerf_nerf"].NeRF()
+    else:
+        c, f = models.NeRF(), models.NeRF()
+        sc_, sf_ = dict(c.state_dict()), dict(f.state_dict())
     pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
     rays = orc.image_rays(args.width, args.height, args.width * 1.3875, pose)
     mid = (args.height // 2) * args.width
@@ -87,14 +95,105 @@ def cpu_baseline(args, n_rays: int, repeats: int = 1):
     torch.manual_seed(5)
     with torch.no_grad():
         for _ in range(repeats):
-            t_rand = torch.rand(rays.shape[0], args.coarse)
             t0 = time.perf_counter()
-            tp.render_rays(rays, 2.0, 6.0, lambda x: tp.nerf_mlp(sc_, x), lambda x: tp.nerf_mlp(sf_, x), args.coarse, args.fine, t_rand)
+            if ref is not None:
+                ref["nerf_render"].render_rays(rays, 2.0, 6.0, c, f, args.coarse, args.fine)       # draws its own jitter (:131)
+            else:
+                t_rand = torch.rand(rays.shape[0], args.coarse)
+                tp.render_rays(rays, 2.0, 6.0, lambda x: tp.nerf_mlp(sc_, x), lambda x: tp.nerf_mlp(sf_, x), args.coarse, args.fine, t_rand)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-    return dict(value=rays.shape[0] / best, unit="rays/s", cores=int(torch.get_num_threads()), kind="port",
-                sample=f"{rays.shape[0]} rays of the {args.width}x{args.height} frame, {args.coarse}+{args.fine} samples, fp32 "
-                       f"ATen port of the reference path (oracle/torch_port.py), {best:.2f} s; host has {os.cpu_count()} logical cores"), best
+    what = ("the unmodified reference nerf/render.py:render_rays + nerf/nerf.py:NeRF (oracle/_ref)" if ref is not None
+            else "ATen port of the reference path (oracle/torch_port.py)")
+    return dict(value=rays.shape[0] / best, unit="rays/s", cores=int(torch.get_num_threads()), kind="reference" if ref is not None else "port",
+                sample=f"{rays.shape[0]} rays of the {args.width}x{args.height} frame, {args.coarse}+{args.fine} samples, fp32, "
+                       f"{what}, {best:.2f} s; host has {os.cpu_count()} logical cores"), best
+
+
+def cpu_baseline_secondary(args, config: str):
+    """cpu_baseline of a secondary BASELINE.json config: the unmodified reference on the host cores, on a bounded
+    sample of that config's workload (units are independent: rays / latents / grid points extrapolate linearly).  None when
+    no copy of the reference is reachable."""
+    import torch
+    from oracle import ref_loader, render_oracle as orc
+    from msra_practice_project_b200 import pigan_render
+    ref = ref_loader.load_reference()
+    if ref is None:
+        return None
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = int(torch.get_num_threads())
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+
+    def frame_rays(n):
+        r = orc.image_rays(800, 800, 800 * 1.3875, pose)
+        return torch.from_numpy(np.ascontiguousarray(r[320000:320000 + n]))
+    if config in ("train", "siren_train"):
+        # nerf/train_nerf.py:151-167: render_rays + MSE(coarse) + MSE(fine) + backward on a 1024-ray sample (the reference's own batch
+        # size, nerf/configs/lego.json:16); anomaly mode as shipped (nerf/nerf.py:2 switches it on) and off
+        n = 1024
+        torch.manual_seed(0)
+        cls = ref["nerf_nerf"].NeRF if config == "train" else ref["nerf_nerf"].SirenNeRF
+        c, f = cls(), cls()
+        rays = frame_rays(n)
+        torch.manual_seed(1)
+        target = torch.rand(n, 3)
+        out = {}
+        for anomaly in (True, False):
+            torch.autograd.set_detect_anomaly(anomaly)
+            t0 = time.perf_counter()
+            rc, _, _, rf, _, _ = ref["nerf_render"].render_rays(rays, 2.0, 6.0, c, f, args.coarse, args.fine)
+            loss = torch.mean((rc - target) ** 2) + torch.mean((rf - target) ** 2)
+            loss.backward()
+            out[anomaly] = time.perf_counter() - t0
+        torch.autograd.set_detect_anomaly(True)
+        return dict(value=n / out[False], unit="rays/s", cores=cores, kind="reference", value_anomaly_mode_as_shipped=n / out[True],
+                    sample=f"{n}-ray batch: unmodified render_rays + MSE losses + backward (no optimiser), {out[False]:.2f} s with anomaly mode off, "
+                           f"{out[True]:.2f} s as shipped (nerf/nerf.py:2)")
+    if config == "siren":
+        n = 4096
+        torch.manual_seed(0)
+        c, f = ref["nerf_nerf"].SirenNeRF(), ref["nerf_nerf"].SirenNeRF()
+        rays = frame_rays(n)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            ref["nerf_render"].render_rays(rays, 2.0, 6.0, c, f, args.coarse, args.fine)
+            dt = time.perf_counter() - t0
+        return dict(value=n / dt, unit="rays/s", cores=cores, kind="reference", sample=f"{n} rays of the frame through the unmodified render_rays + SirenNeRF, {dt:.2f} s")
+    torch.manual_seed(0)
+    net = ref["pigan_modules"].FilmSirenNeRF()
+    g = torch.Generator().manual_seed(0)
+    film = torch.cat([1.0 + 0.2 * torch.randn(9, 256, generator=g), 0.1 * torch.randn(9, 256, generator=g)], -1)
+    net.set_film_params(film)
+    if config in ("pigan", "pigan_grad"):
+        res = 64 if config == "pigan_grad" else 128
+        focal = np.float64(res / 2 / np.tan(6 * np.pi / 180))
+        p = pigan_render.camera_pos_to_transform_matrix(1, 0.0, 0.15)
+        if config == "pigan":
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                ref["pigan_render"].render_image(res, res, focal, p, 0.5, 1.5, net, net, 24, 24)
+                dt = time.perf_counter() - t0
+            what = "one latent (1 of 64): unmodified pi_GAN/render.py:render_image + FilmSirenNeRF"
+        else:
+            film_g = film.clone().requires_grad_(True)
+            net.set_film_params(film_g)
+            t0 = time.perf_counter()
+            img = ref["pigan_render"].render_image(res, res, focal, p, 0.5, 1.5, net, net, 24, 24)
+            (img ** 2).mean().backward()
+            dt = time.perf_counter() - t0
+            what = "one latent (1 of 4): unmodified render_image + backward to the FiLM parameters and weights (anomaly mode as shipped)"
+        return dict(value=res * res / dt, unit="rays/s", cores=cores, kind="reference", sample=f"{what}, {res}x{res}, 24+24 samples, {dt:.2f} s")
+    # grid: the create_mesh query loop (pi_GAN/utils.py:80-91) on 1/64 of the 256^3 lattice, 65,536-point batches, zero directions
+    n = 256 ** 3 // 64
+    idx = torch.arange(n)
+    xyz = torch.stack([(idx // 256 // 256 % 256).float(), (idx // 256 % 256).float(), (idx % 256).float()], -1) * (0.2 / 255) - 0.1
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for h in range(0, n, 65536):
+            x = torch.cat([xyz[h:h + 65536], torch.zeros(min(65536, n - h), 3)], -1)
+            _ = -net(x)[:, 3]
+        dt = time.perf_counter() - t0
+    return dict(value=n / dt, unit="points/s", cores=cores, kind="reference", sample=f"{n} lattice points (1/64 of 256^3) through the unmodified FilmSirenNeRF.forward in 65,536-point batches, {dt:.2f} s")
 
 
 def gpu_eager_incumbent(args, n_rays: int = 16384, repeats: int = 3):
@@ -624,6 +723,11 @@ def run_secondary(args, config=None, embedded=False):
                     config=dict(workload="256^3 lattice in [-0.1,0.1]^3, coordinates generated on the device, sigma-only FiLM-SIREN kernel"),
                     tflops=n3 * 919552 / (ms * 1e-3) / 1e12)
     line.update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, vs_baseline=None, data="synthetic")
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_secondary(args, config)
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)[:200]}
     if embedded:
         torch.cuda.empty_cache()
         return line

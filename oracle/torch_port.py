@@ -3,9 +3,11 @@
 The reference's arithmetic library for this path is PyTorch ATen: on a CPU it runs
 MKL sgemm + vectorised elementwise kernels on all host threads.  ``render_oracle.py`` (numpy) is the
 bit-level checker; this file restates the same algorithm with the same ATen calls the reference makes,
-so that the CPU baseline timed by ``bench.py`` (``cpu_baseline`` and ``--impl reference``) runs at the
-speed the reference itself would on the box's host cores.  The reference is pure Python that cannot
-travel to the GPU box (/root/reference does not exist there), hence a port and not ``oracle/_ref``.
+so that a CPU baseline can be timed at the speed the reference itself would reach on the box's host
+cores.  ``bench.py`` (``cpu_baseline`` and ``--impl reference``) times the UNMODIFIED reference from the
+git-ignored copy ``oracle/_ref`` (tools/install_ref.sh, oracle/ref_loader.py) and falls back to this
+port (``kind: "port"``) only when that copy is absent; the port is also the "stock eager PyTorch on the
+same B200" incumbent.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and bench.py's CPU arm may import this module.  It is
 pinned by tests/test_oracle_golden.py against the golden outputs of the unmodified reference.
