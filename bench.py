@@ -28,7 +28,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 NERF_FLOP_PER_ROW = 1182976          # unpadded algorithmic FLOP per MLP evaluation
-TC_DRAM_BYTES_PER_ROW = 15.8         # profiles/r1_nerf_tc_ncu.txt: (53.6 MB read + 145.0 MB written) / 12,582,912 rows
+
+
+def tc_dram_traffic(rows: int):
+    """(bytes, source) of one fused-MLP launch of `rows` rows: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full capture of
+    the HEADLINE launches (profiles/r2_headline_nerf_tc_ncu.json: the 122.88 M-row fine pass of the 800x800 frame); the launch this bench
+    times has exactly that shape at N = 1, other row counts are scaled per row."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_headline_nerf_tc_ncu.json")))["fine"]
+    except Exception:
+        return None, "profiles/r2_headline_nerf_tc_ncu.json missing"
+    exact = rows == d["rows"]
+    return int(d["dram_bytes_read"] + d["dram_bytes_write"]) if exact else int(d["bytes_per_row"] * rows), \
+        ("dram__bytes_read.sum + dram__bytes_write.sum of this very launch shape (122.88 M rows), " if exact else
+         f"{d['bytes_per_row']:.2f} B/row measured on the 122.88 M-row launch, scaled to this launch's rows, ") + \
+        "ncu --set full, profiles/r2_headline_nerf_tc_ncu.txt; algorithmic = 16 B/row written + 4 B/row (z) + 24 B/ray read"
 METRIC = "rays/s, NeRF 800x800 render, 64 coarse + 128 fine samples/ray"
 
 
@@ -408,9 +422,7 @@ def run_b200(args):
         roof = dict(bound="tensor", kernel="nerf_tc_kernel (fine pass)", achieved=achieved, peak=pk["bf16"], unit="TFLOP/s",
                     frac=achieved / pk["bf16"], frac_of_sustained=achieved / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
                     peak_source=pk["src"], rows_per_launch=rows, ms_per_launch=k_ms, flop_per_row=NERF_FLOP_PER_ROW,
-                    traffic=int(rows * TC_DRAM_BYTES_PER_ROW),
-                    traffic_source="dram__bytes_read+write per row of the ncu --set full capture in profiles/ (fine-pass launch), "
-                                   "scaled to this launch's rows; algorithmic = 16 B/row written")
+                    traffic=tc_dram_traffic(rows)[0], traffic_source=tc_dram_traffic(rows)[1])
     # ---- the HBM-bound stages, each timed alone with CUDA events on the launching stream
     hbm_kernels = []
     with torch.no_grad():

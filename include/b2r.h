@@ -193,8 +193,10 @@ int b2r_mlp_f32_last_sigma(int model_kind, const float* params, const float* fil
  * FiLM-folded weights W' = 30 gamma W, s' = 30 (gamma b + beta)); d_params / d_film are ACCUMULATED into and either may
  * be NULL (synthesis.py only needs d film). */
 size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows);
+/* last (nullable): the last-sample sign check of b2r_mlp_tc_fwd, so that the training forward reports the same raw values
+ * as the render (the caller then runs b2r_mlp_f32_last_sigma on raw_out before it composites). */
 int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,
-                         size_t saved_bytes, void* stream);
+                         size_t saved_bytes, const b2r_last_sample* last, void* stream);
 size_t b2r_mlp_tc_bwd_packed_bytes(int model_kind);
 int b2r_mlp_tc_pack_bwd(int model_kind, const float* params, void* packed_out, void* stream);
 size_t b2r_mlp_tc_train_scratch_bytes(int model_kind, long long rows);
@@ -206,7 +208,7 @@ int b2r_mlp_tc_train_bwd(int model_kind, const void* packed_bwd, long long rows,
  * d_folded: B * B2R_FILM_NUMEL floats; d_film [B,9,512]; d_params sums over the latents.  n_latents = 1: rows_per_latent ignored.
  * use_dir: the FilmSirenNeRF(use_dir=...) flag (0: hidden_layer_rgb has 256 inputs, flat layout B2R_FILM_NODIR_NUMEL). */
 int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in,
-                                      float* raw_out, void* saved, size_t saved_bytes, void* stream);
+                                      float* raw_out, void* saved, size_t saved_bytes, const b2r_last_sample* last, void* stream);
 int b2r_mlp_tc_pack_bwd_film(const float* params, const float* film, int use_dir, int n_latents, void* packed_out, void* stream);
 int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const float* film, int use_dir, int n_latents, long long rows_per_latent,
                               long long rows, const float* raw, const float* d_raw, const void* saved, void* scratch,

@@ -57,7 +57,7 @@ SIGNATURES = {
     "b2r_mlp_f32_last_sigma": (C.c_int, [C.c_int, c_float_p, c_float_p, C.c_int, C.c_int, c_ll, C.POINTER(MlpInput), C.c_int, C.c_void_p, C.c_int,
                                          c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b2r_mlp_tc_train_saved_bytes": (C.c_size_t, [C.c_int, c_ll]),
-    "b2r_mlp_tc_train_fwd": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(MlpInput), c_float_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b2r_mlp_tc_train_fwd": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(MlpInput), c_float_p, C.c_void_p, C.c_size_t, C.POINTER(LastSample), C.c_void_p]),
     "b2r_mlp_tc_bwd_packed_bytes": (C.c_size_t, [C.c_int]),
     "b2r_mlp_tc_pack_bwd": (C.c_int, [C.c_int, c_float_p, C.c_void_p, C.c_void_p]),
     "b2r_mlp_tc_train_scratch_bytes": (C.c_size_t, [C.c_int, c_ll]),
@@ -69,7 +69,7 @@ SIGNATURES = {
     "b2r_mlp_tc_train_bwd": (C.c_int, [C.c_int, C.c_void_p, c_ll, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                        c_float_p, C.c_void_p]),
     "b2r_mlp_tc_train_fwd_film_batched": (C.c_int, [C.c_void_p, C.c_int, c_ll, C.POINTER(MlpInput), c_float_p, C.c_void_p, C.c_size_t,
-                                                    C.c_void_p]),
+                                                    C.POINTER(LastSample), C.c_void_p]),
     "b2r_mlp_tc_pack_bwd_film": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "b2r_mlp_tc_train_bwd_film": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, C.c_int, c_ll, c_ll, c_float_p, c_float_p, C.c_void_p,
                                             C.c_void_p, C.c_size_t, c_float_p, c_float_p, c_float_p, C.c_void_p]),

@@ -743,7 +743,7 @@ size_t siren_packed_bytes();
 int siren_pack(const float* params, void* packed_out, cudaStream_t st);
 int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, const b2r_last_sample* last, cudaStream_t st);
 size_t siren_saved_bytes(long long rows);
-int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, void* saved, cudaStream_t st);
+int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, void* saved, const b2r_last_sample* last, cudaStream_t st);
 }  // namespace tc
 }  // namespace b2r
 
@@ -883,7 +883,7 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
 }
 
 extern "C" int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_latents, long long rows_per_latent, const b2r_mlp_input* in,
-                                                 float* raw_out, void* saved, size_t saved_bytes, void* stream) {
+                                                 float* raw_out, void* saved, size_t saved_bytes, const b2r_last_sample* last, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(packed && raw_out && saved, "b2r_mlp_tc_train_fwd_film_batched: NULL pointer");
     B2R_CHECK_ARG((((uintptr_t)packed | (uintptr_t)raw_out | (uintptr_t)saved) & 15) == 0, "b2r_mlp_tc_train_fwd_film_batched: buffers must be 16-byte aligned");
@@ -895,6 +895,8 @@ extern "C" int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_laten
     B2R_CHECK_ARG(n_latents >= 1 && rows <= rows_per_latent * (long long)n_latents, "b2r_mlp_tc_train_fwd_film_batched: %lld rows need more than %d latents", rows, n_latents);
     B2R_CHECK_ARG(saved_bytes >= b2r_mlp_tc_train_saved_bytes(B2R_MODEL_FILM, rows), "b2r_mlp_tc_train_fwd_film_batched: saved buffer too small (%zu B)", saved_bytes);
     if (rows == 0) return 0;
+    rc = tc::check_last_sample(last, in, "b2r_mlp_tc_train_fwd_film_batched");
+    if (rc) return rc;
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
@@ -902,7 +904,7 @@ extern "C" int b2r_mlp_tc_train_fwd_film_batched(const void* packed, int n_laten
     if (rc) return rc;
     tc::film_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, 0,
                                                                                            (float4*)raw_out, n_latents, rows_per_latent, (uint8_t*)saved,
-                                                                                           tc::make_last_flag(nullptr));
+                                                                                           tc::make_last_flag(last));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd_film_batched");
     return 0;
 }
@@ -915,7 +917,7 @@ extern "C" size_t b2r_mlp_tc_train_saved_bytes(int model_kind, long long rows) {
 }
 
 extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2r_mlp_input* in, float* raw_out, void* saved,
-                                    size_t saved_bytes, void* stream) {
+                                    size_t saved_bytes, const b2r_last_sample* last, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_SIREN || model_kind == B2R_MODEL_FILM,
                   "b2r_mlp_tc_train_fwd: unknown model kind %d", model_kind);
@@ -926,7 +928,9 @@ extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2
     long long rows = row_count(in);
     B2R_CHECK_ARG(saved_bytes >= b2r_mlp_tc_train_saved_bytes(model_kind, rows), "b2r_mlp_tc_train_fwd: saved buffer too small (%zu B)", saved_bytes);
     if (rows == 0) return 0;
-    if (model_kind == B2R_MODEL_SIREN) return tc::siren_train_fwd(packed, in, rows, raw_out, saved, (cudaStream_t)stream);
+    rc = tc::check_last_sample(last, in, "b2r_mlp_tc_train_fwd");
+    if (rc) return rc;
+    if (model_kind == B2R_MODEL_SIREN) return tc::siren_train_fwd(packed, in, rows, raw_out, saved, last, (cudaStream_t)stream);
     if (model_kind == B2R_MODEL_FILM) {                 // packed = one latent's image (use_dir = 1 layout)
         unsigned fgrid = 0;
         rc = tc::pair_grid(rows, &fgrid);
@@ -934,7 +938,7 @@ extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2
         rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
         tc::film_tc_kernel<true><<<fgrid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, 0,
-                                                                                               (float4*)raw_out, 1, 0, (uint8_t*)saved, tc::make_last_flag(nullptr));
+                                                                                               (float4*)raw_out, 1, 0, (uint8_t*)saved, tc::make_last_flag(last));
         B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd (FiLM-SIREN)");
         return 0;
     }
@@ -944,7 +948,7 @@ extern "C" int b2r_mlp_tc_train_fwd(int model_kind, const void* packed, const b2
     rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
     if (rc) return rc;
     tc::nerf_tc_kernel<true><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows,
-                                                                                           (float4*)raw_out, (uint8_t*)saved, tc::make_last_flag(nullptr));
+                                                                                           (float4*)raw_out, (uint8_t*)saved, tc::make_last_flag(last));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd");
     return 0;
 }

@@ -369,14 +369,14 @@ int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float
 
 size_t siren_saved_bytes(long long rows) { return (size_t)n_sub_tiles(rows) * siren_saved_bytes_per_sub(); }
 
-int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, void* saved, cudaStream_t st) {
+int siren_train_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float* raw_out, void* saved, const b2r_last_sample* last, cudaStream_t st) {
     unsigned grid = 0;
     int rc = pair_grid(rows, &grid);
     if (rc) return rc;
     rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes), "tc smem attribute");
     if (rc) return rc;
     siren_tc_kernel<true><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, (uint8_t*)saved,
-                                                              make_last_flag(nullptr));
+                                                              make_last_flag(last));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_train_fwd (SirenNeRF)");
     return 0;
 }

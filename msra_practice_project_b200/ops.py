@@ -423,7 +423,7 @@ def tc_train_forward(packed: torch.Tensor, kind: int, rays: torch.Tensor, z: tor
     saved = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
     if rows > 0:
         with torch.cuda.device(dev):
-            check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, _stream(packed)),
+            check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, None, _stream(packed)),
                   "b2r_mlp_tc_train_fwd")
     del keep
     return raw, saved
@@ -473,8 +473,14 @@ class _MlpTcTrain(torch.autograd.Function):
         saved = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
         if rows > 0:
             with torch.cuda.device(dev):
-                check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, _stream(flat)),
-                      "b2r_mlp_tc_train_fwd")
+                # the same last-sample sign check as the render (autograd callers such as the unmodified train_nerf.py loop see the
+                # render's raw values; d sigma_last is zero on either side of the step, so the reverse mode is unaffected)
+                spr = z.shape[1] if rays is not None else 0
+                ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if (_EXACT_LAST and spr > 0) else (None, None)
+                check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes,
+                                                 C.byref(ls) if ls is not None else None, _stream(flat)), "b2r_mlp_tc_train_fwd")
+                if ls is not None:
+                    _last_sample_finish(kind, fd, None, True, 1, 0, inp, spr, ls_keep, raw)
         ctx.model, ctx.kind, ctx.rows = model, kind, rows
         ctx.save_for_backward(flat, raw, saved)
         del keep
@@ -521,12 +527,17 @@ class _MlpTcTrainFilm(torch.autograd.Function):
         if rows > 0:
             with torch.cuda.device(dev):
                 check(lib().b2r_mlp_tc_pack_film_batched(ptr(fd), ptr(fl), int(use_dir), n_lat, ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_film_batched")
+                spr = z.shape[1] if rays is not None else 0
+                ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if (_EXACT_LAST and spr > 0) else (None, None)
+                lsp = C.byref(ls) if ls is not None else None
                 if n_lat == 1:
-                    check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, _stream(flat)),
+                    check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, lsp, _stream(flat)),
                           "b2r_mlp_tc_train_fwd")
                 else:
                     check(lib().b2r_mlp_tc_train_fwd_film_batched(ptr(packed), n_lat, int(rows_per_latent), C.byref(inp), ptr(raw), ptr(saved),
-                                                                  nbytes, _stream(flat)), "b2r_mlp_tc_train_fwd_film_batched")
+                                                                  nbytes, lsp, _stream(flat)), "b2r_mlp_tc_train_fwd_film_batched")
+                if ls is not None:
+                    _last_sample_finish(kind, fd, fl, use_dir, n_lat, int(rows_per_latent), inp, spr, ls_keep, raw)
         ctx.rows, ctx.n_lat, ctx.rows_per_latent, ctx.use_dir = rows, n_lat, int(rows_per_latent), int(bool(use_dir))
         ctx.save_for_backward(flat, film, raw, saved)
         del keep

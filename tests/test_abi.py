@@ -68,13 +68,13 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     assert lib.b2r_mlp_f32_workspace_bytes(2, 10, 1) == 10 * 4620 * 4
     inp = _lib.MlpInput()
     inp.x, inp.n_rays, inp.n_samples = 256, 512, 1
-    assert lib.b2r_mlp_tc_train_fwd(3, 16, C.byref(inp), 16, 16, 1 << 30, None) < 0 and b"unknown model kind" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_train_fwd(3, 16, C.byref(inp), 16, 16, 1 << 30, None, None) < 0 and b"unknown model kind" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_bwd(1, 16, 512, 16, 16, 16, 16, 1 << 30, 16, None) < 0 and b"NeRF" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_pack_bwd_film(None, None, 1, 1, 16, None) < 0
     assert lib.b2r_mlp_tc_train_bwd_film(16, 16, 16, 1, 1, 0, 512, 16, 16, 16, 16, 64, 16, 16, 16, None) < 0 and b"scratch" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_bwd_film(16, 16, 16, 0, 2, 256, 512, 16, 16, 16, 16, 1 << 30, 16, 16, 16, None) < 0 and b"multiple of 512" in lib.b2r_last_error()
-    assert lib.b2r_mlp_tc_train_fwd_film_batched(16, 2, 256, C.byref(inp), 16, 16, 1 << 30, None) < 0 and b"multiple of 512" in lib.b2r_last_error()
-    assert lib.b2r_mlp_tc_train_fwd(0, 16, C.byref(inp), 16, 16, 64, None) < 0 and b"too small" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_train_fwd_film_batched(16, 2, 256, C.byref(inp), 16, 16, 1 << 30, None, None) < 0 and b"multiple of 512" in lib.b2r_last_error()
+    assert lib.b2r_mlp_tc_train_fwd(0, 16, C.byref(inp), 16, 16, 64, None, None) < 0 and b"too small" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_train_bwd(0, 16, 512, 16, 16, 16, 16, 64, 16, None) < 0 and b"scratch" in lib.b2r_last_error()
     assert lib.b2r_mlp_tc_fwd_film_batched(16, 2, 100, C.byref(inp), 16, 0, None, None) < 0 and b"multiple of 512" in lib.b2r_last_error()
     inp.n_rays = 1024
