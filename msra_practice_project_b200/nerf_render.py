@@ -75,7 +75,9 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     pre-relu sigma lies inside the bf16 error band and re-evaluates those rows with the fp32 engine:
     that sample's interval is 1e10 (nerf/render.py:92), so alpha_last is a step function of
     sign(sigma_last) and a bf16 rounding would flip ~0.2 % of rays by up to 0.6.
-    Applies to passes that run without gradients (renders; the pi-GAN coarse pass)."""
+    Applies to passes that run without gradients (renders; the pi-GAN coarse pass).  Passes that carry
+    gradients run the raw bf16 forward (mixed-precision training; d sigma_last is zero either way) unless
+    ops.set_exact_last_sample(train=True) is set -- an explicit switch, not a silent skip."""
     if not isinstance(rays, torch.Tensor):
         rays = torch.as_tensor(np.asarray(rays), dtype=torch.float32)
     if not rays.is_cuda:

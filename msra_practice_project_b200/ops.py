@@ -63,14 +63,25 @@ def get_grad_precision() -> str:
 # `exact_last_sample=False` / set_exact_last_sample(False) gives the raw bf16 result.  rel: >= 8 standard deviations of the measured
 # bf16 error of sigma_pre relative to the scale.
 _EXACT_LAST = True
+# Passes that carry gradients (ops.mlp under autograd, NerfTrainStep) evaluate the RAW bf16 forward by default: the mixed-precision
+# training recipe.  d sigma_last is zero on both sides of the step, so only the forward value of ~0.2 % of the rays
+# differs, and the two host syncs + fp32 launches per pass would cost ~8 % of a training step.  set_exact_last_sample(train=True)
+# makes the autograd forward apply the same check as the render (its reverse mode is unaffected).
+_EXACT_LAST_TRAIN = False
 _LAST_REL = {models.KIND_NERF: 2.0 ** -7, models.KIND_FILM: 2.0 ** -8, models.KIND_SIREN: 2.0 ** -8}
 _LAST_ABS = 1e-6
 last_sample_stats = {"calls": 0, "rays": 0, "flagged": 0}      # running totals (bench / tests report the flagged fraction)
 
 
-def set_exact_last_sample(flag: bool) -> bool:
-    global _EXACT_LAST
-    old, _EXACT_LAST = _EXACT_LAST, bool(flag)
+def set_exact_last_sample(flag: bool | None = None, train: bool | None = None) -> bool:
+    """Switch the last-sample sign check of no-grad bf16 passes (``flag``) and / or of the autograd training forward (``train``).
+    Returns the previous value of ``flag``'s switch."""
+    global _EXACT_LAST, _EXACT_LAST_TRAIN
+    old = _EXACT_LAST
+    if flag is not None:
+        _EXACT_LAST = bool(flag)
+    if train is not None:
+        _EXACT_LAST_TRAIN = bool(train)
     return old
 
 
@@ -473,10 +484,10 @@ class _MlpTcTrain(torch.autograd.Function):
         saved = torch.empty((max(nbytes, 16),), dtype=torch.uint8, device=dev)
         if rows > 0:
             with torch.cuda.device(dev):
-                # the same last-sample sign check as the render (autograd callers such as the unmodified train_nerf.py loop see the
-                # render's raw values; d sigma_last is zero on either side of the step, so the reverse mode is unaffected)
+                # opt-in (_EXACT_LAST_TRAIN): the same last-sample sign check as the render, so that autograd callers see the render's
+                # raw values; d sigma_last is zero on either side of the step, so the reverse mode is unaffected
                 spr = z.shape[1] if rays is not None else 0
-                ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if (_EXACT_LAST and spr > 0) else (None, None)
+                ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if (_EXACT_LAST_TRAIN and spr > 0) else (None, None)
                 check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes,
                                                  C.byref(ls) if ls is not None else None, _stream(flat)), "b2r_mlp_tc_train_fwd")
                 if ls is not None:
@@ -528,7 +539,7 @@ class _MlpTcTrainFilm(torch.autograd.Function):
             with torch.cuda.device(dev):
                 check(lib().b2r_mlp_tc_pack_film_batched(ptr(fd), ptr(fl), int(use_dir), n_lat, ptr(packed), _stream(flat)), "b2r_mlp_tc_pack_film_batched")
                 spr = z.shape[1] if rays is not None else 0
-                ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if (_EXACT_LAST and spr > 0) else (None, None)
+                ls, ls_keep = _last_sample_begin(kind, rows, spr, dev) if (_EXACT_LAST_TRAIN and spr > 0) else (None, None)
                 lsp = C.byref(ls) if ls is not None else None
                 if n_lat == 1:
                     check(lib().b2r_mlp_tc_train_fwd(kind, ptr(packed), C.byref(inp), ptr(raw), ptr(saved), nbytes, lsp, _stream(flat)),

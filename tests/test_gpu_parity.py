@@ -413,6 +413,30 @@ def test_last_sample_sign_check_sine_models():
     _last_sample_case(sn, rays_s, zs, lb, run=lambda on: ops.mlp(sn, rays=rays_s, z=zs, precision="bf16", exact_last_sample=on))
 
 
+def test_last_sample_check_in_the_autograd_forward_is_an_explicit_switch():
+    """ops.set_exact_last_sample(train=True): the training forward reports the render's raw values (default: raw bf16)."""
+    c, _ = seeded_nerf()
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -30 * np.pi / 180)
+    rays = ops.raygen(128, 100, 128 * 1.3875, pose)
+    torch.manual_seed(11)
+    z, _ = ops.stratified_z(torch.linspace(2.0, 6.0, 64).cuda(), torch.rand(rays.shape[0], 64, device="cuda"))
+    with torch.no_grad():
+        on = ops.mlp(c, rays=rays, z=z, precision="bf16")
+        off = ops.mlp(c, rays=rays, z=z, precision="bf16", exact_last_sample=False)
+    assert not torch.equal(on, off)
+    old = ops.set_grad_precision("bf16")
+    try:
+        assert torch.equal(ops.mlp(c, rays=rays, z=z).detach(), off)
+        ops.set_exact_last_sample(train=True)
+        raw = ops.mlp(c, rays=rays, z=z)
+        assert torch.equal(raw.detach(), on)
+        raw.sum().backward()
+        assert all(torch.isfinite(p.grad).all() for p in c.parameters())
+    finally:
+        ops.set_exact_last_sample(train=False)
+        ops.set_grad_precision(old)
+
+
 def test_tc_pack_cache_invalidation():
     c, _ = seeded_nerf()
     x = torch.rand(300, 6, device="cuda")
@@ -1087,7 +1111,7 @@ def test_siren_nerf_fused_training_path(rows_shape):
     z = (torch.sort(torch.rand(n, s, generator=g), -1).values * 1.0 + 0.5).cuda()
     up = torch.randn(n * s, 4, generator=g).cuda()
     with torch.no_grad():
-        raw_inf = ops.mlp(net, rays=rays, z=z, precision="bf16")
+        raw_inf = ops.mlp(net, rays=rays, z=z, precision="bf16", exact_last_sample=False)   # gradient passes run the raw bf16 forward
     res = {}
     for mode in ("fp32", "bf16"):
         old = ops.set_grad_precision(mode)
@@ -1159,7 +1183,7 @@ def test_film_siren_fused_training_path(rows_shape):
     up = torch.randn(n * s, 4, generator=g).cuda()
     net.set_film_params(film)
     with torch.no_grad():
-        raw_inf = ops.mlp(net, rays=rays, z=z, precision="bf16")
+        raw_inf = ops.mlp(net, rays=rays, z=z, precision="bf16", exact_last_sample=False)   # gradient passes run the raw bf16 forward
         raw_f32 = ops.mlp(net, rays=rays, z=z, precision="fp32")
     # relu(sigma) is a step function of the pre-activation's sign: on the few rows where bf16 rounds it across zero the
     # two paths differentiate different functions, so those rows get no upstream sigma gradient (teacher-forced parity)
