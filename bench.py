@@ -319,10 +319,14 @@ def run_b200(args):
     t_rand = torch.rand((n_rays, sc), device=dev)[begin:begin + count].contiguous()
     gathered = torch.empty((n_rays, 5), dtype=torch.float32, device=dev) if world > 1 else None
 
+    my_rows = shard.frame_slice(gathered, n_rays, rank, world) if world > 1 else None
+
     def step_device():
         with torch.no_grad():
+            # N > 1: the fine composite writes (rgb, depth, acc) straight into this rank's rows of the frame buffer and the
+            # all-gather runs in place on it (no pack / staging copy)
             out = nerf_render.render_image_device(W, H, focal, pose, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin,
-                                                  ray_count=count, t_rand=t_rand, precision=args.precision)
+                                                  ray_count=count, t_rand=t_rand, precision=args.precision, fine_out=my_rows)
             if world > 1:
                 shard.gather_image(out[3], out[4], out[5], gathered, n_rays, rank, world)
         return out
@@ -370,6 +374,31 @@ def run_b200(args):
                            passes_per_step=passes // args.steps, ms_per_step_check_off=off_ms, rays_per_s_check_off=n_rays / (off_ms * 1e-3),
                            cost_fraction=ms_per_step / off_ms - 1.0)
 
+    # ---- N > 1: the gathered frame must equal what ONE GPU renders.  Rank 0 re-renders, alone, the two pixel rows either side of
+    # every shard boundary (and the frame's first / last row) from the same global jitter and compares them bit for bit with the
+    # rows the other ranks sent (the driver's GPU test box has one GPU, so the 2-GPU pytest never runs there).
+    sharded_equals_single = None
+    if world > 1:
+        step_device()
+        torch.cuda.synchronize()
+        if rank == 0:
+            torch.manual_seed(5)
+            t_full = torch.rand((n_rays, sc), device=dev)
+            ok, checked = True, 0
+            spans = [(0, W), (n_rays - W, W)] + [(shard.shard_range(n_rays, r, world)[0] - W, 2 * W) for r in range(1, world)]
+            with torch.no_grad():
+                for b0, cnt in spans:
+                    o = nerf_render.render_image_device(W, H, focal, pose, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=b0, ray_count=cnt,
+                                                        t_rand=t_full[b0:b0 + cnt], precision=args.precision)
+                    alone = torch.cat([o[3], o[4][:, None], o[5][:, None]], -1)
+                    ok = ok and bool(torch.equal(alone, gathered[b0:b0 + cnt]))
+                    checked += cnt
+            sharded_equals_single = dict(equal=ok, rays_checked=checked, what="rank 0 alone vs the gathered frame: first / last pixel row and "
+                                         "the two rows either side of every shard boundary, bit for bit")
+            assert ok, "the gathered frame differs from the single-GPU render"
+            del t_full
+        barrier()
+
     # ---- end to end through the public API: host pose in, numpy images out
     pinned_pose = torch.from_numpy(np.ascontiguousarray(pose)).pin_memory()
 
@@ -377,7 +406,8 @@ def run_b200(args):
         with torch.no_grad():
             p = pinned_pose.numpy()              # host pose -> kernel arguments of the ray generator (the step's H2D)
             out = nerf_render.render_image_device(W, H, focal, p, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin,
-                                                  ray_count=count, t_rand=None if world == 1 else t_rand, precision=args.precision)
+                                                  ray_count=count, t_rand=None if world == 1 else t_rand, precision=args.precision,
+                                                  fine_out=my_rows)
             if world > 1:
                 shard.gather_image(out[3], out[4], out[5], gathered, n_rays, rank, world)
                 if rank == 0:
@@ -512,7 +542,8 @@ def run_b200(args):
                     # raygen, stratified_z, 2 x (fused MLP, composite), sample_pdf + per pass with flagged rays the fp32 re-evaluation
                     # (encode, 8 layer GEMMs, sigma head)
                     gpu_launches=int((7 + (20 if last_sample and last_sample["rays_reevaluated_fp32_per_step"] else 0)) * args.steps * world),
-                    last_sample=last_sample, clocks=clocks.summary(), roofline=roof, hbm_kernels=hbm_kernels,
+                    last_sample=last_sample, sharded_equals_single=sharded_equals_single, clocks=clocks.summary(), roofline=roof,
+                    hbm_kernels=hbm_kernels,
                     cpu_baseline=base, secondary=secondary)
         emit(line)
     if world > 1:

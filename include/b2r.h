@@ -74,6 +74,13 @@ int b2r_composite_fwd(const float* raw, const float* z, const float* rays_d, int
                       long long n_rays, int n_samples, float* rgb_out, float* depth_out,
                       float* acc_out, float* weights_out, void* stream);
 
+/* the same with strided outputs: ray r's colour at rgb_out[r * rgb_stride .. + 2], depth at depth_out[r * depth_stride], acc at
+ * acc_out[r * acc_stride] -- e.g. (base, 5), (base + 3, 5), (base + 4, 5) writes rows of the packed [N,5] frame buffer that the
+ * multi-GPU image gather exchanges (nerf/render.py:161-166 concatenates the three maps on the host). */
+int b2r_composite_fwd_strided(const float* raw, const float* z, const float* rays_d, int d_stride,
+                              long long n_rays, int n_samples, float* rgb_out, int rgb_stride, float* depth_out,
+                              int depth_stride, float* acc_out, int acc_stride, float* weights_out, void* stream);
+
 /* reverse mode of the above wrt raw (autograd in the reference, nerf/train_nerf.py:167).
  * g_depth / g_acc nullable (treated as zero).  d_raw[N,S,4]. */
 int b2r_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,

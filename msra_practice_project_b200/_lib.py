@@ -39,6 +39,8 @@ SIGNATURES = {
     "b2r_stratified_z": (C.c_int, [c_float_p, c_float_p, c_ll, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "b2r_composite_fwd": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, c_ll, C.c_int, c_float_p, c_float_p,
                                     c_float_p, c_float_p, C.c_void_p]),
+    "b2r_composite_fwd_strided": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, c_ll, C.c_int, c_float_p, C.c_int, c_float_p, C.c_int,
+                                            c_float_p, C.c_int, c_float_p, C.c_void_p]),
     "b2r_composite_bwd": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, c_ll, C.c_int, c_float_p, c_float_p,
                                     c_float_p, c_float_p, C.c_void_p]),
     "b2r_sample_pdf": (C.c_int, [c_float_p, c_ll, c_float_p, c_ll, c_float_p, c_ll, C.c_int, C.c_int, c_float_p, C.c_int,

@@ -32,8 +32,8 @@ __device__ __forceinline__ float warp_scan_mul(float p, int lane) {
 template <bool kWeights>
 __global__ void __launch_bounds__(256) composite_fwd_kernel(
     const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
-    long long n_rays, int S, float* __restrict__ rgb_out, float* __restrict__ depth_out,
-    float* __restrict__ acc_out, float* __restrict__ w_out) {
+    long long n_rays, int S, float* __restrict__ rgb_out, int rgb_stride, float* __restrict__ depth_out, int depth_stride,
+    float* __restrict__ acc_out, int acc_stride, float* __restrict__ w_out) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -80,9 +80,108 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(
         ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); ad = warp_sum(ad); aa = warp_sum(aa);
         if (lane == 0) {
             float bg = 1.0f - aa;                          // white background, always (render.py:101)
-            rgb_out[ray * 3 + 0] = ar + bg; rgb_out[ray * 3 + 1] = ag + bg; rgb_out[ray * 3 + 2] = ab + bg;
-            depth_out[ray] = ad;
-            acc_out[ray] = aa;
+            float* c = rgb_out + ray * rgb_stride;
+            c[0] = ar + bg; c[1] = ag + bg; c[2] = ab + bg;
+            depth_out[ray * depth_stride] = ad;
+            acc_out[ray * acc_stride] = aa;
+        }
+    }
+}
+
+
+// Single-chunk forward for the shapes that matter (S <= L x LANES): a group of LANES lanes (16: two rays per warp; 32: one) owns a
+// ray and every lane owns L CONSECUTIVE samples -- L x 16 contiguous bytes of raw, L x 4 of z and of the weights, moved as 16-byte
+// vectors -- so the transmittance is L - 1 serial products per lane plus ONE log2(LANES)-step scan per ray, and the five per-ray
+// sums are reduced once.  For S = 64 this is 2 rays per warp pass and about half the warp-instructions per ray of the chunked
+// kernel above (which stays as the fallback for other sizes).  Same arithmetic per sample; the product scan associates
+// differently, which moves T by a few ulp (tests: <= 1e-5 against the reference's golden outputs).
+// Outputs are strided so that a caller can have (rgb, depth, acc) written straight into rows of a packed [N,5] buffer
+// (the multi-GPU image gather, dist.py).
+template <int L, int LANES, bool kWeights>
+__global__ void __launch_bounds__(256) composite_fwd_group_kernel(
+    const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
+    long long n_rays, int S, float* __restrict__ rgb_out, int rgb_stride, float* __restrict__ depth_out, int depth_stride,
+    float* __restrict__ acc_out, int acc_stride, float* __restrict__ w_out) {
+    constexpr int RPW = 32 / LANES;                       // rays per warp pass
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);                    // lane within the ray's group
+    const int sub = lane / LANES;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool vec = (S % 4) == 0 && L % 4 == 0;          // 16-byte z loads / weight stores are aligned
+    for (long long ray0 = warp0 * RPW; ray0 < n_rays; ray0 += n_warps * RPW) {
+        const long long ray = ray0 + sub;
+        const bool live = ray < n_rays;
+        const long long rr_ = live ? ray : n_rays - 1;
+        const float norm = ray_norm(rays_d + rr_ * d_stride);
+        const float4* rr = raw + rr_ * S;
+        const float* zz = z + rr_ * S;
+        const int k0 = gl * L;
+        float4 r[L];
+        float zv[L + 1];
+#pragma unroll
+        for (int j = 0; j < L; ++j) r[j] = (k0 + j < S) ? rr[k0 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < L; j += 4) {
+                float4 t = (k0 + j < S) ? *reinterpret_cast<const float4*>(zz + k0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                zv[j] = t.x; zv[j + 1] = t.y; zv[j + 2] = t.z; zv[j + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < L; ++j) zv[j] = (k0 + j < S) ? zz[k0 + j] : 0.f;
+        }
+        zv[L] = __shfl_down_sync(kFull, zv[0], 1, LANES);       // first z of the next lane's run
+        float a[L], q[L], pl = 1.0f;
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            const int k = k0 + j;
+            const bool v = k < S;
+            float d = (k == S - 1) ? 1e10f : __fsub_rn(zv[j + 1], zv[j]);
+            d = __fmul_rn(d, norm);
+            a[j] = v ? 1.0f - __expf(-r[j].w * d) : 0.f;
+            q[j] = v ? (1.0f - a[j]) + 1e-10f : 1.0f;
+            pl *= q[j];
+        }
+        float p = pl;                                          // inclusive product scan over the group's lanes
+#pragma unroll
+        for (int o = 1; o < LANES; o <<= 1) {
+            float t = __shfl_up_sync(kFull, p, o, LANES);
+            if (gl >= o) p *= t;
+        }
+        float T = __shfl_up_sync(kFull, p, 1, LANES);
+        if (gl == 0) T = 1.0f;
+        float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f, w[L];
+#pragma unroll
+        for (int j = 0; j < L; ++j) {
+            w[j] = a[j] * T;
+            T *= q[j];
+            ar = fmaf(w[j], r[j].x, ar); ag = fmaf(w[j], r[j].y, ag); ab = fmaf(w[j], r[j].z, ab);
+            ad = fmaf(w[j], zv[j], ad); aa += w[j];
+        }
+        if (kWeights && live) {
+            float* wo = w_out + ray * S + k0;
+            if (vec) {
+#pragma unroll
+                for (int j = 0; j < L; j += 4)
+                    if (k0 + j < S) *reinterpret_cast<float4*>(wo + j) = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < L; ++j)
+                    if (k0 + j < S) wo[j] = w[j];
+            }
+        }
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            ar += __shfl_xor_sync(kFull, ar, o); ag += __shfl_xor_sync(kFull, ag, o); ab += __shfl_xor_sync(kFull, ab, o);
+            ad += __shfl_xor_sync(kFull, ad, o); aa += __shfl_xor_sync(kFull, aa, o);
+        }
+        if (gl == 0 && live) {
+            const float bg = 1.0f - aa;                    // white background, always (render.py:101)
+            float* c = rgb_out + ray * rgb_stride;
+            c[0] = ar + bg; c[1] = ag + bg; c[2] = ab + bg;
+            depth_out[ray * depth_stride] = ad;
+            acc_out[ray * acc_stride] = aa;
         }
     }
 }
@@ -159,23 +258,52 @@ static inline unsigned ray_grid(long long n_rays) {
 
 }  // namespace b2r
 
-extern "C" int b2r_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
-                                 long long n_rays, int n_samples, float* rgb_out, float* depth_out,
-                                 float* acc_out, float* weights_out, void* stream) {
+namespace b2r {
+template <int L, int LANES>
+static void launch_group(bool weights, unsigned grid, cudaStream_t st, const float* raw, const float* z, const float* rays_d, int d_stride,
+                         long long n_rays, int S, float* rgb, int rs, float* depth, int ds, float* acc, int as, float* w) {
+    if (weights)
+        composite_fwd_group_kernel<L, LANES, true><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, S, rgb, rs, depth, ds, acc, as, w);
+    else
+        composite_fwd_group_kernel<L, LANES, false><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, S, rgb, rs, depth, ds, acc, as, nullptr);
+}
+}  // namespace b2r
+
+extern "C" int b2r_composite_fwd_strided(const float* raw, const float* z, const float* rays_d, int d_stride,
+                                         long long n_rays, int n_samples, float* rgb_out, int rgb_stride, float* depth_out,
+                                         int depth_stride, float* acc_out, int acc_stride, float* weights_out, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(raw && z && rays_d && rgb_out && depth_out && acc_out, "b2r_composite_fwd: NULL pointer");
     B2R_CHECK_ARG(n_rays >= 0 && n_samples >= 1, "b2r_composite_fwd: need n_rays >= 0, n_samples >= 1");
     B2R_CHECK_ARG(d_stride >= 3, "b2r_composite_fwd: d_stride must be >= 3");
+    B2R_CHECK_ARG(rgb_stride >= 3 && depth_stride >= 1 && acc_stride >= 1, "b2r_composite_fwd: output strides must be >= 3 / 1 / 1");
     B2R_CHECK_ARG(((uintptr_t)raw & 15) == 0, "b2r_composite_fwd: raw must be 16-byte aligned");
     if (n_rays == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned grid = ray_grid(n_rays);
-    if (weights_out)
-        composite_fwd_kernel<true><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, n_samples, rgb_out, depth_out, acc_out, weights_out);
-    else
-        composite_fwd_kernel<false><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, n_samples, rgb_out, depth_out, acc_out, nullptr);
+    const int S = n_samples;
+    const bool w = weights_out != nullptr;
+    // 16-byte z loads / weight stores of the grouped kernels need aligned rows
+    const bool al = (((uintptr_t)z | (uintptr_t)weights_out) & 15) == 0;
+    if (S <= 256 && (al || S % 4 != 0)) {
+        const unsigned g2 = ray_grid((n_rays + 1) / 2), g1 = ray_grid(n_rays);
+        if (S <= 64) launch_group<4, 16>(w, g2, st, raw, z, rays_d, d_stride, n_rays, S, rgb_out, rgb_stride, depth_out, depth_stride, acc_out, acc_stride, weights_out);
+        else if (S <= 128) launch_group<4, 32>(w, g1, st, raw, z, rays_d, d_stride, n_rays, S, rgb_out, rgb_stride, depth_out, depth_stride, acc_out, acc_stride, weights_out);
+        else launch_group<8, 32>(w, g1, st, raw, z, rays_d, d_stride, n_rays, S, rgb_out, rgb_stride, depth_out, depth_stride, acc_out, acc_stride, weights_out);
+    } else {
+        unsigned grid = ray_grid(n_rays);
+        if (w)
+            composite_fwd_kernel<true><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, S, rgb_out, rgb_stride, depth_out, depth_stride, acc_out, acc_stride, weights_out);
+        else
+            composite_fwd_kernel<false><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, S, rgb_out, rgb_stride, depth_out, depth_stride, acc_out, acc_stride, nullptr);
+    }
     B2R_LAUNCH_CHECK("b2r_composite_fwd");
     return 0;
+}
+
+extern "C" int b2r_composite_fwd(const float* raw, const float* z, const float* rays_d, int d_stride,
+                                 long long n_rays, int n_samples, float* rgb_out, float* depth_out,
+                                 float* acc_out, float* weights_out, void* stream) {
+    return b2r_composite_fwd_strided(raw, z, rays_d, d_stride, n_rays, n_samples, rgb_out, 3, depth_out, 1, acc_out, 1, weights_out, stream);
 }
 
 extern "C" int b2r_composite_bwd(const float* raw, const float* z, const float* rays_d, int d_stride,

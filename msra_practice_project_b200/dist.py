@@ -29,15 +29,22 @@ def shard_range(n: int, rank: int, world: int, align: int = 1) -> tuple[int, int
 def gather_image(rgb: torch.Tensor, depth: torch.Tensor, acc: torch.Tensor, out: torch.Tensor, n_rays: int,
                  rank: int, world: int, group=None) -> torch.Tensor:
     """All-gather each rank's [count,5] = (rgb, depth, acc) rows into `out`[n_rays,5] (every rank
-    receives the frame).  Ranks own unequal row counts, so this is all_gather over a list of
-    views of `out` -- NCCL writes in place, no staging copy on the receive side."""
-    mine = torch.cat([rgb, depth[:, None], acc[:, None]], -1).contiguous()
+    receives the frame).  When the three maps already ARE this rank's rows of `out` (the composite kernel wrote them there:
+    render_image_device(fine_out=frame_slice(out, ...))) and the blocks are equal, the collective runs IN PLACE on `out` with no
+    pack or staging copy at all; otherwise the rows are packed first, and ragged blocks are padded to the largest."""
+    begin, count = shard_range(n_rays, rank, world)
+    mine = out[begin:begin + count]
+    in_place = (rgb.data_ptr() == mine.data_ptr() and depth.data_ptr() == mine.data_ptr() + 12 and acc.data_ptr() == mine.data_ptr() + 16
+                and rgb.stride(0) == 5 and depth.stride(0) == 5 and acc.stride(0) == 5) if count > 0 else True
+    if not in_place:
+        mine = torch.cat([rgb, depth[:, None], acc[:, None]], -1).contiguous()
     if world == 1:
-        out[: mine.shape[0]].copy_(mine)
+        if not in_place:
+            out[: mine.shape[0]].copy_(mine)
         return out
     counts = [shard_range(n_rays, r, world)[1] for r in range(world)]
     if min(counts) == max(counts):
-        # equal blocks: the collective writes every rank's rows straight into the final buffer
+        # equal blocks: the collective writes every rank's rows straight into the final buffer (in place when `mine` is a slice of it)
         dist.all_gather_into_tensor(out, mine, group=group)
         return out
     # ragged blocks: pad to the largest, gather, unpack
@@ -50,6 +57,13 @@ def gather_image(rgb: torch.Tensor, depth: torch.Tensor, acc: torch.Tensor, out:
         b, c = shard_range(n_rays, r, world)
         out[b:b + c] = stage[r * cmax:r * cmax + c]
     return out
+
+
+def frame_slice(out: torch.Tensor, n_rays: int, rank: int, world: int) -> torch.Tensor:
+    """This rank's rows of the gathered [n_rays,5] frame buffer: pass it as ``fine_out`` so that the composite kernel writes
+    (rgb, depth, acc) where the gather expects them (nerf/render.py:161-166 concatenates on the host instead)."""
+    begin, count = shard_range(n_rays, rank, world)
+    return out[begin:begin + count]
 
 
 def render_image_sharded(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
@@ -68,11 +82,11 @@ def render_image_sharded(width, height, focal, pose, near, far, coarse_model, fi
     if t_rand_full is None:
         t_rand_full = nerf_render._draw_t_rand(n, int(coarse_sample_num), nerf_render.REFERENCE_RAY_CHUNK, dev)
     with torch.no_grad():
+        out = torch.empty((n, 5), dtype=torch.float32, device=dev)
         o = nerf_render.render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model,
                                             coarse_sample_num, fine_sample_num, ray_begin=begin, ray_count=count,
                                             t_rand=t_rand_full[begin:begin + count], precision=precision,
-                                            exact_last_sample=exact_last_sample)
-        out = torch.empty((n, 5), dtype=torch.float32, device=dev)
+                                            exact_last_sample=exact_last_sample, fine_out=frame_slice(out, n, rank, world))
         gather_image(o[3], o[4], o[5], out, n, rank, world, group)
     h, w = int(height), int(width)
     return out[:, :3].reshape(h, w, 3), out[:, 3].reshape(h, w, 1), out[:, 4].reshape(h, w, 1)

@@ -66,7 +66,7 @@ def raw_to_outputs(raw, z_vals, rays_d):
 
 def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num, *,
                 t_rand=None, z_lin=None, u=None, precision=None, stages=None, coarse_no_grad=False,
-                exact_last_sample=None):
+                exact_last_sample=None, fine_out=None):
     """nerf/render.py:106-147 -- coarse pass, sample_pdf on the un-jittered mids with
     weights[:,1:-1], sort-merge, fine pass on all Sc+Sf samples.  Returns the reference's 6-tuple
     (rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f).  ``coarse_no_grad`` runs the coarse pass in
@@ -75,6 +75,8 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     pre-relu sigma lies inside the bf16 error band and re-evaluates those rows with the fp32 engine:
     that sample's interval is 1e10 (nerf/render.py:92), so alpha_last is a step function of
     sign(sigma_last) and a bf16 rounding would flip ~0.2 % of rays by up to 0.6.
+    ``fine_out`` [N,5] (no-grad renders): the fine pass writes (rgb, depth, acc) into its rows -- a rank's slice
+    of the gathered frame buffer -- and the returned fine maps are views of it.
     Applies to passes that run without gradients (renders; the pi-GAN coarse pass).  Passes that carry
     gradients run the raw bf16 forward (mixed-precision training; d sigma_last is zero either way) unless
     ops.set_exact_last_sample(train=True) is set -- an explicit switch, not a silent skip."""
@@ -106,7 +108,7 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
                          want_samples=stages is not None)
     z_fine = res["sorted"]
     raw_f = _mlp_rays(fine_model, rays, z_fine, precision, exact_last_sample)
-    rgb_f, depth_f, acc_f, w_f = ops.composite(raw_f, z_fine, rays_d, want_weights=stages is not None)
+    rgb_f, depth_f, acc_f, w_f = ops.composite(raw_f, z_fine, rays_d, want_weights=stages is not None, packed_out=fine_out)
     if stages is not None:
         stages.update(z_coarse=z_vals, mids=mids, raw_coarse=raw, weights_coarse=weights, z_samples=res["samples"],
                       z_fine=z_fine, raw_fine=raw_f, weights_fine=w_f)
@@ -128,10 +130,11 @@ def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
 
 def render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                         fine_sample_num, chunk=REFERENCE_RAY_CHUNK, *, ray_begin=0, ray_count=None, t_rand=None,
-                        precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=None):
+                        precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=None, fine_out=None):
     """Device-resident core of render_image: renders flattened pixel rows [ray_begin, +ray_count)
     and returns the six per-ray outputs of the fine AND coarse pass as CUDA tensors.  Rays are
-    generated on the device (K1); ``launch_rays`` bounds the rays per kernel launch sequence."""
+    generated on the device (K1); ``launch_rays`` bounds the rays per kernel launch sequence.
+    ``fine_out`` [ray_count,5]: destination rows of the fine (rgb, depth, acc) -- see render_rays."""
     dev = _model_device(coarse_model)
     width, height = int(width), int(height)
     total = width * height
@@ -146,9 +149,11 @@ def render_image_device(width, height, focal, pose, near, far, coarse_model, fin
         rays = ops.raygen(width, height, focal, pose, ray_begin + b, cnt, device=dev)
         outs.append(render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
                                 t_rand=t_rand[b:b + cnt], precision=precision, coarse_no_grad=coarse_no_grad,
-                                exact_last_sample=exact_last_sample))
+                                exact_last_sample=exact_last_sample, fine_out=None if fine_out is None else fine_out[b:b + cnt]))
     if len(outs) == 1:
         return outs[0]
+    if fine_out is not None:                   # the fine maps already sit in fine_out's rows
+        return tuple(torch.cat([o[i] for o in outs]) for i in range(3)) + (fine_out[:, :3], fine_out[:, 3], fine_out[:, 4])
     return tuple(torch.cat([o[i] for o in outs]) for i in range(6))
 
 

@@ -176,21 +176,35 @@ def _dirs_view(rays_d: torch.Tensor):
     return d, d.data_ptr(), 3
 
 
-def composite_forward(raw, z, rays_d, want_weights: bool = True):
-    """b2r_composite_fwd without autograd: (rgb, depth, acc, weights | None, (raw, z, dirs tensor, dirs stride))."""
-    raw = _cuda_f32(raw, "raw")
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    """float4 accesses need 16-byte aligned rows: a contiguous-but-offset view such as raw[1:] is copied (the reference accepts it)."""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def composite_forward(raw, z, rays_d, want_weights: bool = True, packed_out: torch.Tensor | None = None):
+    """b2r_composite_fwd without autograd: (rgb, depth, acc, weights | None, (raw, z, dirs tensor, dirs stride)).
+    packed_out [N,5] (optional): the kernel writes (rgb, depth, acc) straight into its rows and the returned maps are views of it
+    (the rank's slice of the gathered frame buffer, dist.py)."""
+    raw = _aligned16(_cuda_f32(raw, "raw"))
     z = _cuda_f32(z, "z_vals")
     keep, dptr, dstride = _dirs_view(rays_d.detach())
     n, s = z.shape
     dev = z.device
-    rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
-    depth = torch.empty((n,), dtype=torch.float32, device=dev)
-    acc = torch.empty((n,), dtype=torch.float32, device=dev)
+    if packed_out is not None:
+        if tuple(packed_out.shape) != (n, 5) or packed_out.dtype != torch.float32 or not packed_out.is_cuda or not packed_out.is_contiguous():
+            raise RuntimeError(f"packed_out must be a contiguous fp32 CUDA tensor [{n},5]")
+        rgb, depth, acc = packed_out[:, :3], packed_out[:, 3], packed_out[:, 4]
+        strides = (5, 5, 5)
+    else:
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        depth = torch.empty((n,), dtype=torch.float32, device=dev)
+        acc = torch.empty((n,), dtype=torch.float32, device=dev)
+        strides = (3, 1, 1)
     w = torch.empty((n, s), dtype=torch.float32, device=dev) if want_weights else None
     if n > 0:
         with torch.cuda.device(dev):
-            check(lib().b2r_composite_fwd(ptr(raw), ptr(z), dptr, dstride, n, s, ptr(rgb), ptr(depth), ptr(acc), ptr(w),
-                                          _stream(z)), "b2r_composite_fwd")
+            check(lib().b2r_composite_fwd_strided(ptr(raw), ptr(z), dptr, dstride, n, s, rgb.data_ptr(), strides[0], depth.data_ptr(), strides[1],
+                                                  acc.data_ptr(), strides[2], ptr(w), _stream(z)), "b2r_composite_fwd")
     return rgb, depth, acc, w, (raw, z, keep, dstride)
 
 
@@ -198,7 +212,7 @@ def composite_backward(ctx4, g_rgb, g_depth=None, g_acc=None) -> torch.Tensor:
     """b2r_composite_bwd: d_raw[N,S,4] from the upstream gradients of (rgb, depth, acc); ctx4 = composite_forward's last item."""
     raw, z, keep, dstride = ctx4
     n, s = z.shape
-    d_raw = torch.empty_like(raw)
+    d_raw = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
     if n == 0:
         return d_raw
     g_rgb = _cuda_f32(g_rgb, "g_rgb")
@@ -229,7 +243,7 @@ class _Composite(torch.autograd.Function):
         g_rgb = torch.zeros((n, 3), device=z.device) if g_rgb is None else _cuda_f32(g_rgb, "g_rgb")
         g_depth = None if g_depth is None else _cuda_f32(g_depth, "g_depth")
         g_acc = None if g_acc is None else _cuda_f32(g_acc, "g_acc")
-        d_raw = torch.empty_like(raw)
+        d_raw = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
         if n == 0:
             return d_raw, None, None, None
         with torch.cuda.device(z.device):
@@ -238,10 +252,16 @@ class _Composite(torch.autograd.Function):
         return d_raw, None, None, None
 
 
-def composite(raw, z_vals, rays_d, want_weights: bool = True):
+def composite(raw, z_vals, rays_d, want_weights: bool = True, packed_out: torch.Tensor | None = None):
     """raw_to_outputs (nerf/render.py:78-103): (rgb[N,3], depth[N], acc[N], weights[N,S] or None).
     Differentiable wrt ``raw``; the weights are returned detached (the reference only uses them
-    through sample_pdf, whose result is detached, nerf/render.py:141)."""
+    through sample_pdf, whose result is detached, nerf/render.py:141).  ``packed_out`` [N,5] (no-grad passes only): the three
+    maps are written into its rows and returned as views (composite_forward)."""
+    if packed_out is not None:
+        if torch.is_grad_enabled() and isinstance(raw, torch.Tensor) and raw.requires_grad:
+            raise RuntimeError("packed_out is for passes without gradients")
+        rgb, depth, acc, w, _ = composite_forward(raw.detach(), z_vals, rays_d, want_weights, packed_out)
+        return rgb, depth, acc, w
     rgb, depth, acc, w = _Composite.apply(raw, z_vals, rays_d, bool(want_weights))
     return rgb, depth, acc, (w if want_weights else None)
 

@@ -40,6 +40,12 @@ def _worker(rank, world, port, n_rays, q):
         out = torch.full((n_rays, 5), -1.0)
         shard.gather_image(full[b:b + c, :3].clone(), full[b:b + c, 3].clone(), full[b:b + c, 4].clone(), out, n_rays, rank, world)
         ok_gather = bool(torch.equal(out, full))
+        # in place: the rank's rows already sit in the frame buffer (the composite kernel writes them there): no pack, no staging
+        out2 = torch.full((n_rays, 5), -1.0)
+        sl = shard.frame_slice(out2, n_rays, rank, world)
+        sl.copy_(full[b:b + c])
+        shard.gather_image(sl[:, :3], sl[:, 3], sl[:, 4], out2, n_rays, rank, world)
+        ok_gather = ok_gather and bool(torch.equal(out2, full))
         # gradient all-reduce of two small "models": every rank holds grad = rank+1 -> mean = (world+1)/2
         torch.manual_seed(0)
         ms = [torch.nn.Linear(3, 4), torch.nn.Linear(4, 2)]
