@@ -63,6 +63,8 @@ def parse():
     ap.add_argument("--ref-rays", type=int, default=16384, help="--impl reference: rays per step (the reference's own chunk, nerf/render.py:150)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="headline run: skip the other BASELINE.json configs")
+    ap.add_argument("--train-batch", type=int, default=4096, help="training configs: rays of the GLOBAL batch (4096 = BASELINE.json configs[2]; "
+                    "512 on one GPU reproduces one rank's share of the 8-GPU step for profiling)")
     ap.add_argument("--no-graph", action="store_true", help="training config: launch the step's kernels directly (for ncu)")
     ap.add_argument("--config", default="render", choices=["render", "train", "pigan", "grid", "siren", "siren_train", "pigan_grad"],
                     help="render = the headline NeRF 800x800 frame (default; BASELINE.json configs[1]); the others are the "
@@ -590,7 +592,7 @@ def run_secondary(args, config=None, embedded=False):
     if config == "train":
         # nerf/train_nerf.py:151-168: render_rays on a 4096-ray batch, MSE(coarse)+MSE(fine), backward, Adam; the batch is
         # sharded over ranks and the flat fp32 gradient bucket is all-reduced once per step
-        n_batch, sc, sf = 4096, args.coarse, args.fine
+        n_batch, sc, sf = args.train_batch, args.coarse, args.fine
         b, c = shard.shard_range(n_batch, rank, world)
         torch.manual_seed(0)
         coarse, fine = models.NeRF().to(dev), models.NeRF().to(dev)
@@ -621,9 +623,9 @@ def run_secondary(args, config=None, embedded=False):
                 opt.step()
         ms = timed(step, args.steps, args.warmup)
         rows = n_batch * (2 * sc + sf)
-        line = dict(metric="rays/s, NeRF training step (4096-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
+        line = dict(metric=f"rays/s, NeRF training step ({n_batch}-ray batch, fwd+bwd, 64+128 samples, Adam)", value=n_batch / (ms * 1e-3),
                     unit="rays/s", ms_per_step=ms, dtype={"tf32": "tf32", "fp32": "f32", "bf16": "bf16"}[args.grad_precision], scaling="strong",
-                    config=dict(workload="NeRF train step, 4096 rays sharded over ranks, " + (
+                    config=dict(workload=f"NeRF train step, {n_batch} rays sharded over ranks, " + (
                         "fused tcgen05 MLP forward with bf16 activations kept in HBM + fused dgrad / MN-major wgrad reverse mode (bf16 operands, fp32 "
                         "accumulate), fused Adam, whole step replayed as CUDA graphs, " if args.grad_precision == "bf16" else
                         f"layer-wise MLP forward with saved fp32 activations + CUDA reverse mode, GEMMs in {args.grad_precision}, ") +

@@ -87,6 +87,21 @@ int b2r_composite_bwd(const float* raw, const float* z, const float* rays_d, int
                       long long n_rays, int n_samples, const float* g_rgb, const float* g_depth,
                       const float* g_acc, float* d_raw, void* stream);
 
+/* training: the loss of nerf/train_nerf.py:157-166 and the reverse mode of the composite in one launch.
+ *   loss = mean((rgb - target_rgb)^2) [+ alpha_weight * mean((acc - target_acc)^2)] over the GLOBAL batch of 1 / *inv_count rays
+ * (inv_count: device float, so that a CUDA graph replays with the count of a short last batch); the kernel recomputes the ray's
+ * forward, forms g_rgb = 2 (rgb - target) inv_count / 3 and g_acc = 2 alpha_weight (acc - target_acc) inv_count itself (g_depth = 0:
+ * the reference's loss never uses depth) and writes d_raw[N,S,4].  ray_weight[N] (nullable) scales a ray's loss term (0 for padding).
+ * sums[0] += sum w (rgb - target)^2 over rays and channels, sums[1] += sum w (acc - target_acc)^2 (caller zeroes). */
+int b2r_composite_loss_bwd(const float* raw, const float* z, const float* rays_d, int d_stride, long long n_rays, int n_samples,
+                           const float* target_rgb, const float* target_acc, const float* ray_weight, const float* inv_count,
+                           float alpha_weight, float* d_raw, float* sums, void* stream);
+
+/* loss and PSNR of a training step from the four sums of two b2r_composite_loss_bwd calls (sums[0..1] fine pass, [2..3] coarse):
+ * loss = (s0 + s2) inv_count / 3 + alpha_weight (s1 + s3) inv_count; psnr = -10 log10(s0 inv_local / 3)  (train_nerf.py:158-166). */
+int b2r_train_loss_finish(const float* sums, const float* inv_count, float alpha_weight, const float* inv_local, float* loss,
+                          float* psnr, void* stream);
+
 /* ---- K5/K6: hierarchical resampling --- sample_pdf nerf/render.py:27-56, sort-merge :142 ---
  * bins: nb values per ray, bins_stride floats apart (0 = one shared row, as in render_rays);
  * weights: nb-1 values per ray, w_stride floats apart (render_rays passes weights[:,1:-1]:

@@ -43,6 +43,9 @@ SIGNATURES = {
                                             c_float_p, C.c_int, c_float_p, C.c_void_p]),
     "b2r_composite_bwd": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, c_ll, C.c_int, c_float_p, c_float_p,
                                     c_float_p, c_float_p, C.c_void_p]),
+    "b2r_composite_loss_bwd": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, c_ll, C.c_int, c_float_p, c_float_p, c_float_p, c_float_p,
+                                         C.c_float, c_float_p, c_float_p, C.c_void_p]),
+    "b2r_train_loss_finish": (C.c_int, [c_float_p, c_float_p, C.c_float, c_float_p, c_float_p, c_float_p, C.c_void_p]),
     "b2r_sample_pdf": (C.c_int, [c_float_p, c_ll, c_float_p, c_ll, c_float_p, c_ll, C.c_int, C.c_int, c_float_p, C.c_int,
                                  c_float_p, c_float_p, c_float_p, C.c_void_p]),
     "b2r_sample_pdf_generic": (C.c_int, [c_float_p, c_ll, c_float_p, c_ll, c_float_p, c_ll, C.c_int, C.c_int, c_float_p, C.c_int,

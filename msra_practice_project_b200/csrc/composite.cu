@@ -250,6 +250,94 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(
     }
 }
 
+
+// Training: loss + reverse mode of the composite in ONE kernel (nerf/train_nerf.py:157-167).  The reference computes
+//   loss = mean((rgb - target)^2) [+ 0.1 * mean((acc - target_alpha)^2)]      over the GLOBAL batch
+// with ~40 elementwise / reduction launches between raw_to_outputs and backward(); here pass 1 recomputes the forward of the ray
+// (as composite_bwd_kernel does), the upstream gradients follow from the ray's own rgb / acc
+//   g_rgb = 2 (rgb - target) inv_count / 3,   g_acc = 2 alpha_weight (acc - target_alpha) inv_count,   g_depth = 0
+// and pass 2 is the reverse scan.  ray_weight (nullable): 0 for the padded rays of a short last batch.
+// sums[0] += sum_rays w sum_ch (rgb - target)^2, sums[1] += sum_rays w (acc - target_alpha)^2 (one atomic per CTA).
+template <int CH>
+__global__ void __launch_bounds__(256) composite_loss_bwd_kernel(
+    const float4* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays_d, int d_stride,
+    long long n_rays, int S, const float* __restrict__ target_rgb, const float* __restrict__ target_acc,
+    const float* __restrict__ ray_weight, const float* __restrict__ inv_count_p, float alpha_weight,
+    float4* __restrict__ d_raw, float* __restrict__ sums) {
+    __shared__ float s_part[2][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float inv_count = *inv_count_p;
+    float loss_rgb = 0.f, loss_acc = 0.f;
+    for (long long ray = warp0; ray < n_rays; ray += n_warps) {
+        const float norm = ray_norm(rays_d + ray * d_stride);
+        const float4* rr = raw + ray * S;
+        const float* zz = z + ray * S;
+        float e[CH], T[CH], w[CH], dist[CH], cr[CH], cg[CH], cb[CH];
+        float carry = 1.0f, ar = 0.f, ag = 0.f, ab = 0.f, aa = 0.f;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            int k = c * 32 + lane;
+            bool valid = k < S;
+            float4 r = valid ? rr[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float zk = valid ? zz[k] : 0.f;
+            float zn = k + 1 < S ? zz[k + 1] : 0.f;
+            float dd = (k == S - 1) ? 1e10f : __fsub_rn(zn, zk);
+            dd = __fmul_rn(dd, norm);
+            float ee = valid ? expf(-__fmul_rn(r.w, dd)) : 1.0f;
+            float alpha = __fsub_rn(1.0f, ee);
+            float q = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+            float p = warp_scan_mul(q, lane);
+            float excl = __shfl_up_sync(kFull, p, 1);
+            if (lane == 0) excl = 1.0f;
+            float t = carry * excl;
+            carry *= __shfl_sync(kFull, p, 31);
+            e[c] = ee; T[c] = t; w[c] = valid ? alpha * t : 0.f; dist[c] = dd;
+            cr[c] = r.x; cg[c] = r.y; cb[c] = r.z;
+            ar = fmaf(w[c], r.x, ar); ag = fmaf(w[c], r.y, ag); ab = fmaf(w[c], r.z, ab); aa += w[c];
+        }
+        ar = warp_sum(ar); ag = warp_sum(ag); ab = warp_sum(ab); aa = warp_sum(aa);
+        const float bg = 1.0f - aa;
+        const float wt = ray_weight ? ray_weight[ray] : 1.0f;
+        const float er = ar + bg - target_rgb[ray * 3 + 0], eg = ag + bg - target_rgb[ray * 3 + 1], eb = ab + bg - target_rgb[ray * 3 + 2];
+        const float ea = target_acc ? aa - target_acc[ray] : 0.f;
+        const float sc_rgb = 2.0f * inv_count * (1.0f / 3.0f) * wt;
+        const float gr = er * sc_rgb, gg = eg * sc_rgb, gb = eb * sc_rgb;
+        const float ga = target_acc ? 2.0f * alpha_weight * inv_count * wt * ea : 0.f;
+        if (lane == 0) { loss_rgb += wt * (er * er + eg * eg + eb * eb); loss_acc += wt * ea * ea; }
+        float carry_r = 0.f;
+#pragma unroll
+        for (int c = CH - 1; c >= 0; --c) {
+            int k = c * 32 + lane;
+            const float gw = (k < S) ? (gr * (cr[c] - 1.0f) + gg * (cg[c] - 1.0f) + gb * (cb[c] - 1.0f) + ga) : 0.f;
+            float s = gw * w[c];
+            float p = s;                                   // inclusive suffix sum over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                float t = __shfl_down_sync(kFull, p, o);
+                if (lane + o < 32) p += t;
+            }
+            float R = (p - s) + carry_r;
+            carry_r += __shfl_sync(kFull, p, 0);
+            if (k < S) {
+                float q = __fadd_rn(e[c], 1e-10f);
+                float g_alpha = gw * T[c] - R / q;
+                float g_sigma = g_alpha * dist[c] * e[c];
+                d_raw[ray * S + k] = make_float4(w[c] * gr, w[c] * gg, w[c] * gb, g_sigma);
+            }
+        }
+    }
+    if (lane == 0) { s_part[0][wid] = loss_rgb; s_part[1][wid] = loss_acc; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_part[threadIdx.x][i];
+        if (t != 0.f) atomicAdd(sums + threadIdx.x, t);
+    }
+}
+
 static inline unsigned ray_grid(long long n_rays) {
     long long want = (n_rays + 7) / 8;             // 8 warps per CTA
     long long cap = 148LL * 8;
@@ -332,5 +420,53 @@ extern "C" int b2r_composite_bwd(const float* raw, const float* z, const float* 
     else B2R_BWD(16);
 #undef B2R_BWD
     B2R_LAUNCH_CHECK("b2r_composite_bwd");
+    return 0;
+}
+
+extern "C" int b2r_composite_loss_bwd(const float* raw, const float* z, const float* rays_d, int d_stride, long long n_rays, int n_samples,
+                                      const float* target_rgb, const float* target_acc, const float* ray_weight, const float* inv_count,
+                                      float alpha_weight, float* d_raw, float* sums, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(raw && z && rays_d && target_rgb && inv_count && d_raw && sums, "b2r_composite_loss_bwd: NULL pointer");
+    B2R_CHECK_ARG(n_rays >= 0 && n_samples >= 1 && n_samples <= 512, "b2r_composite_loss_bwd: need 1 <= n_samples <= 512");
+    B2R_CHECK_ARG(d_stride >= 3, "b2r_composite_loss_bwd: d_stride must be >= 3");
+    B2R_CHECK_ARG((((uintptr_t)raw | (uintptr_t)d_raw) & 15) == 0, "b2r_composite_loss_bwd: raw / d_raw must be 16-byte aligned");
+    if (n_rays == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned grid = ray_grid(n_rays);
+    int ch = (n_samples + 31) / 32;
+#define B2R_LBWD(CH)                                                                                               \
+    composite_loss_bwd_kernel<CH><<<grid, 256, 0, st>>>((const float4*)raw, z, rays_d, d_stride, n_rays, n_samples, \
+                                                        target_rgb, target_acc, ray_weight, inv_count, alpha_weight, (float4*)d_raw, sums)
+    if (ch <= 1) B2R_LBWD(1);
+    else if (ch <= 2) B2R_LBWD(2);
+    else if (ch <= 3) B2R_LBWD(3);
+    else if (ch <= 4) B2R_LBWD(4);
+    else if (ch <= 6) B2R_LBWD(6);
+    else if (ch <= 8) B2R_LBWD(8);
+    else if (ch <= 12) B2R_LBWD(12);
+    else B2R_LBWD(16);
+#undef B2R_LBWD
+    B2R_LAUNCH_CHECK("b2r_composite_loss_bwd");
+    return 0;
+}
+
+namespace b2r {
+// loss = (sums[0] + sums[2]) inv_count / 3 + alpha_weight (sums[1] + sums[3]) inv_count      (train_nerf.py:158-166; [0..1] fine, [2..3] coarse)
+// psnr = -10 log10(sums[0] inv_local / 3)                                                    (train_nerf.py:160: fine pass, this rank's rays)
+__global__ void train_loss_finish_kernel(const float* __restrict__ sums, const float* __restrict__ inv_count, float alpha_weight,
+                                         const float* __restrict__ inv_local, float* __restrict__ loss, float* __restrict__ psnr) {
+    const float ic = *inv_count;
+    *loss = (sums[0] + sums[2]) * ic * (1.0f / 3.0f) + alpha_weight * (sums[1] + sums[3]) * ic;
+    *psnr = -10.0f * log10f(sums[0] * (*inv_local) * (1.0f / 3.0f));
+}
+}  // namespace b2r
+
+extern "C" int b2r_train_loss_finish(const float* sums, const float* inv_count, float alpha_weight, const float* inv_local, float* loss,
+                                     float* psnr, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(sums && inv_count && inv_local && loss && psnr, "b2r_train_loss_finish: NULL pointer");
+    train_loss_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums, inv_count, alpha_weight, inv_local, loss, psnr);
+    B2R_LAUNCH_CHECK("b2r_train_loss_finish");
     return 0;
 }

@@ -224,6 +224,22 @@ def composite_backward(ctx4, g_rgb, g_depth=None, g_acc=None) -> torch.Tensor:
     return d_raw
 
 
+def composite_loss_backward(raw, z, rays_d, target_rgb, target_acc, ray_weight, inv_count, alpha_weight: float, sums: torch.Tensor) -> torch.Tensor:
+    """b2r_composite_loss_bwd: the train_nerf.py:157-166 loss and the composite's reverse mode in one launch -> d_raw[N,S,4];
+    sums[0] += sum w (rgb - target)^2, sums[1] += sum w (acc - target_acc)^2 (2 floats, caller zeroes)."""
+    raw = _aligned16(_cuda_f32(raw, "raw"))
+    z = _cuda_f32(z, "z_vals")
+    keep, dptr, dstride = _dirs_view(rays_d.detach())
+    n, s = z.shape
+    d_raw = torch.empty(raw.shape, dtype=torch.float32, device=raw.device)
+    if n > 0:
+        with torch.cuda.device(z.device):
+            check(lib().b2r_composite_loss_bwd(ptr(raw), ptr(z), dptr, dstride, n, s, ptr(target_rgb), ptr(target_acc), ptr(ray_weight), ptr(inv_count),
+                                               float(alpha_weight), ptr(d_raw), ptr(sums), _stream(z)), "b2r_composite_loss_bwd")
+    del keep
+    return d_raw
+
+
 class _Composite(torch.autograd.Function):
     @staticmethod
     def forward(ctx, raw, z, rays_d, want_weights):
@@ -487,6 +503,13 @@ def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, 
         check(lib().b2r_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(state), float(lr0),
                                   float(decay_rate), float(decay_steps), float(betas[0]), float(betas[1]), float(eps),
                                   float(grad_scale), _stream(params)), "b2r_adam_step")
+
+
+def train_loss_finish(sums, inv_count, alpha_weight: float, inv_local, loss, psnr) -> None:
+    """b2r_train_loss_finish: loss / PSNR of a training step from the four sums of the two composite_loss_backward calls."""
+    with torch.cuda.device(sums.device):
+        check(lib().b2r_train_loss_finish(ptr(sums), ptr(inv_count), float(alpha_weight), ptr(inv_local), ptr(loss), ptr(psnr), _stream(sums)),
+              "b2r_train_loss_finish")
 
 
 class _MlpTcTrain(torch.autograd.Function):

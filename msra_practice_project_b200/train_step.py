@@ -46,6 +46,8 @@ class NerfTrainStep:
         self.use_alpha, self.betas, self.eps = bool(use_alpha), betas, float(eps)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.batch < 1:
+            raise ValueError("batch_size must be >= 1 ray per rank")
         self.use_graph = bool(graph)
         n = models.NERF_NUMEL if kind == models.KIND_NERF else models.SIREN_NUMEL
         self.n = n
@@ -70,49 +72,62 @@ class NerfTrainStep:
         self.in_rgb = torch.zeros((b, 3), dtype=torch.float32, device=self.dev)
         self.in_alpha = torch.zeros((b,), dtype=torch.float32, device=self.dev)
         self.in_t = torch.zeros((b, self.sc), dtype=torch.float32, device=self.dev)
+        # a short last batch (train_nerf.py:139-150 trains on whatever the final slice of an epoch holds) runs through the same fixed-shape
+        # launch sequence: the missing rays are padding with loss weight 0, and the loss is normalised by the true global ray count, which
+        # lives on the device (counts = [1 / global rays, 1 / this rank's rays]) so that the captured graphs replay unchanged
+        self.ray_w = torch.ones((b,), dtype=torch.float32, device=self.dev)
+        self.counts = torch.tensor([1.0 / (b * self.world), 1.0 / b], dtype=torch.float32, device=self.dev)
+        self._n_valid, self._global = b, b * self.world
+        self.sums = torch.zeros((4,), dtype=torch.float32, device=self.dev)      # [fine rgb, fine acc, coarse rgb, coarse acc] squared errors
         self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.psnr = torch.zeros((), dtype=torch.float32, device=self.dev)
         self._graphs = None
         self._draw_t = True
+        self._side = torch.cuda.Stream(device=self.dev) if self.world > 1 else None
 
     # ---- the step, as plain launches on the current stream -------------------------------------------------------
-    def _forward_backward(self):
+    # 17 launches of libb2r kernels + 2 fills + the jitter draw: stratified z, 2 x (pack, fused forward), composite (coarse: its weights feed
+    # sample_pdf), sample_pdf + merge, 2 x (loss + composite reverse in one kernel, transposed pack, dgrad, wgrad, heads), loss finish, Adam.
+    # The loss / PSNR / upstream-gradient arithmetic of train_nerf.py:157-166 (about 40 elementwise and reduction launches under autograd)
+    # lives inside b2r_composite_loss_bwd.
+    def _forward_and_fine_backward(self):
         n, kind = self.n, self.kind
         rays, rays_d = self.in_rays, self.in_rays[:, 1]
-        bg = float(self.batch * self.world)
         if self._draw_t:
             self.in_t.copy_(torch.rand((self.batch, self.sc), device=self.dev))            # nerf/render.py:131
         flat_c, flat_f = self.params[:n], self.params[n:]
         z, mids = ops.stratified_z(self.z_lin, self.in_t)
         raw_c, saved_c = ops.tc_train_forward(ops.pack_tc(flat_c, kind), kind, rays, z)
-        rgb_c, _, acc_c, w_c, ctx_c = ops.composite_forward(raw_c, z, rays_d, True)
+        _, _, _, w_c, _ = ops.composite_forward(raw_c, z, rays_d, True)
         z_f = ops.sample_pdf(mids, w_c[:, 1:-1], self.sf, u=self.u, z_coarse=z, want_samples=False)["sorted"]
         raw_f, saved_f = ops.tc_train_forward(ops.pack_tc(flat_f, kind), kind, rays, z_f)
-        rgb_f, _, acc_f, _, ctx_f = ops.composite_forward(raw_f, z_f, rays_d, False)
-        # train_nerf.py:157-166
-        e_c, e_f = rgb_c - self.in_rgb, rgb_f - self.in_rgb
-        loss_c, loss_f = (e_c * e_c).sum() / (bg * 3), (e_f * e_f).sum() / (bg * 3)
-        self.psnr.copy_(-10.0 * torch.log10((e_f * e_f).mean()))
-        g_acc_c = g_acc_f = None
-        if self.use_alpha:
-            a_c, a_f = acc_c - self.in_alpha, acc_f - self.in_alpha
-            loss_c = loss_c + 0.1 * (a_c * a_c).sum() / bg
-            loss_f = loss_f + 0.1 * (a_f * a_f).sum() / bg
-            g_acc_c, g_acc_f = a_c * (0.2 / bg), a_f * (0.2 / bg)
-        self.loss.copy_(loss_f + loss_c)
         self.grads.zero_()
-        d_raw_f = ops.composite_backward(ctx_f, e_f * (2.0 / (bg * 3)), None, g_acc_f)
+        self.sums.zero_()
+        alpha_t = self.in_alpha if self.use_alpha else None
+        aw = 0.1 if self.use_alpha else 0.0                                               # train_nerf.py:161-163
+        d_raw_f = ops.composite_loss_backward(raw_f, z_f, rays_d, self.in_rgb, alpha_t, self.ray_w, self.counts[:1], aw, self.sums[:2])
         ops.tc_train_backward(ops.pack_tc_bwd(flat_f, kind), kind, raw_f, d_raw_f, saved_f, self.grads[n:])
-        d_raw_c = ops.composite_backward(ctx_c, e_c * (2.0 / (bg * 3)), None, g_acc_c)
-        ops.tc_train_backward(ops.pack_tc_bwd(flat_c, kind), kind, raw_c, d_raw_c, saved_c, self.grads[:n])
+        self._coarse = (raw_c, z, saved_c, alpha_t, aw)
+
+    def _coarse_backward(self):
+        n, kind = self.n, self.kind
+        raw_c, z, saved_c, alpha_t, aw = self._coarse
+        d_raw_c = ops.composite_loss_backward(raw_c, z, self.in_rays[:, 1], self.in_rgb, alpha_t, self.ray_w, self.counts[:1], aw, self.sums[2:])
+        ops.tc_train_backward(ops.pack_tc_bwd(self.params[:n], kind), kind, raw_c, d_raw_c, saved_c, self.grads[:n])
+        ops.train_loss_finish(self.sums, self.counts[:1], aw, self.counts[1:], self.loss, self.psnr)
+
+    def _forward_backward(self):
+        self._forward_and_fine_backward()
+        self._coarse_backward()
 
     def _optimize(self):
         ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.state, self.lr0, 0.1, self.decay_steps,
                       self.betas, self.eps)
 
     def _capture(self):
-        """warm up on a side stream, capture forward+backward and the optimiser as two graphs, restore the state the
-        warm-up steps changed (weights, moments, step count; the RNG offset is not restored)."""
+        """warm up on a side stream, capture the step as three graphs -- forward + fine backward | coarse backward | optimiser: the seams
+        are where the two gradient all-reduces go -- and restore the state the warm-up steps changed (weights, moments, step count; the
+        RNG offset is not restored)."""
         keep = [t.clone() for t in (self.params, self.exp_avg, self.exp_avg_sq, self.state)]
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
@@ -121,40 +136,72 @@ class NerfTrainStep:
                 self._forward_backward()
                 self._optimize()
         torch.cuda.current_stream(self.dev).wait_stream(s)
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
-            self._forward_backward()
+            self._forward_and_fine_backward()
         with torch.cuda.graph(g2, pool=g1.pool()):
+            self._coarse_backward()
+        with torch.cuda.graph(g3, pool=g1.pool()):
             self._optimize()
         for t, k in zip((self.params, self.exp_avg, self.exp_avg_sq, self.state), keep):
             t.copy_(k)
-        self._graphs = (g1, g2)
+        self._graphs = (g1, g2, g3)
 
-    def __call__(self, batch_rays, batch_rgb, batch_alpha=None, t_rand=None):
-        """One optimisation step on this rank's rays [batch,2,3] / colours [batch,3] (/ alpha [batch]).  Returns
-        (loss, psnr) as 0-d CUDA tensors (global-batch loss share of this rank, fine-pass PSNR of this rank's rays);
-        no host synchronisation happens here."""
-        self.in_rays.copy_(torch.as_tensor(batch_rays).reshape(self.batch, 2, 3), non_blocking=True)
-        self.in_rgb.copy_(torch.as_tensor(batch_rgb).reshape(self.batch, 3), non_blocking=True)
+    def _set_valid(self, n_valid: int, global_count: int | None):
+        g = n_valid * self.world if global_count is None else int(global_count)
+        if (n_valid, g) == (self._n_valid, self._global):
+            return
+        self.ray_w[:n_valid] = 1.0
+        self.ray_w[n_valid:] = 0.0
+        self.counts.copy_(torch.tensor([1.0 / max(g, 1), 1.0 / max(n_valid, 1)], dtype=torch.float32), non_blocking=False)
+        self._n_valid, self._global = n_valid, g
+
+    def __call__(self, batch_rays, batch_rgb, batch_alpha=None, t_rand=None, global_count=None):
+        """One optimisation step on this rank's rays [n,2,3] / colours [n,3] (/ alpha [n]), n <= batch_size (a short last batch is padded
+        with zero-weight rays; ``global_count`` = the rays of the step over all ranks when the ranks' shares differ, RayBatcher.global_count).
+        Returns (loss, psnr) as 0-d CUDA tensors (global-batch loss share of this rank, fine-pass PSNR of this rank's rays); no host
+        synchronisation happens here."""
+        batch_rays = torch.as_tensor(batch_rays)
+        n_valid = int(batch_rays.reshape(-1, 2, 3).shape[0])
+        if n_valid > self.batch or n_valid < 1:
+            raise ValueError(f"this step was built for at most {self.batch} rays per rank, got {n_valid}")
+        self._set_valid(n_valid, global_count)
+        self.in_rays[:n_valid].copy_(batch_rays.reshape(n_valid, 2, 3), non_blocking=True)
+        if n_valid < self.batch:
+            # the padding must be a VALID ray (a zero direction would put NaNs into the MLP, and 0 * NaN into the gradients)
+            self.in_rays[n_valid:] = self.in_rays[0]
+        self.in_rgb[:n_valid].copy_(torch.as_tensor(batch_rgb).reshape(n_valid, 3), non_blocking=True)
         if self.use_alpha:
             if batch_alpha is None:
                 raise ValueError("use_alpha=True needs batch_alpha")
-            self.in_alpha.copy_(torch.as_tensor(batch_alpha).reshape(self.batch), non_blocking=True)
+            self.in_alpha[:n_valid].copy_(torch.as_tensor(batch_alpha).reshape(n_valid), non_blocking=True)
         draw = t_rand is None
         if not draw:
-            self.in_t.copy_(torch.as_tensor(t_rand).reshape(self.batch, self.sc), non_blocking=True)
+            self.in_t[:n_valid].copy_(torch.as_tensor(t_rand).reshape(n_valid, self.sc), non_blocking=True)
+        if self.use_graph and (self._graphs is None or draw != self._draw_t):
+            self._draw_t = draw
+            self._capture()
+        self._draw_t = draw
+        main = torch.cuda.current_stream(self.dev)
+        n = self.n
+        # fine model first: its gradient half is all-reduced on a side stream while the coarse model's reverse mode runs
         if self.use_graph:
-            if self._graphs is None or draw != self._draw_t:
-                self._draw_t = draw
-                self._capture()
             self._graphs[0].replay()
         else:
-            self._draw_t = draw
-            self._forward_backward()
+            self._forward_and_fine_backward()
         if self.world > 1:
-            dist.all_reduce(self.grads, group=self.group)                     # one 4.75 MB bucket, summed (loss is / global batch)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                dist.all_reduce(self.grads[n:], group=self.group)                 # 2.4 MB, summed (the loss is / global count)
         if self.use_graph:
             self._graphs[1].replay()
+        else:
+            self._coarse_backward()
+        if self.world > 1:
+            dist.all_reduce(self.grads[:n], group=self.group)
+            main.wait_stream(self._side)
+        if self.use_graph:
+            self._graphs[2].replay()
         else:
             self._optimize()
         for m in self.models:                       # the weights changed behind torch's version counters
@@ -212,6 +259,9 @@ class RayBatcher:
         if dev.type != "cuda":
             raise RuntimeError("RayBatcher keeps the ray buffer on a CUDA device: there is no CPU fallback")
         self.dev, self.focal, self.batch = dev, focal, int(batch_size)
+        if self.batch % int(world) != 0:
+            raise ValueError(f"batch_size ({self.batch}) must be a multiple of the number of ranks ({world}): NerfTrainStep(batch_size=batch // world)")
+        self.global_count = self.batch
         self.images = torch.as_tensor(images, dtype=torch.float32).to(dev)                     # [N,H,W,4]
         self.poses = [p for p in (poses.detach().cpu().numpy() if isinstance(poses, torch.Tensor) else poses)]
         n, h, w, _ = self.images.shape
@@ -228,8 +278,11 @@ class RayBatcher:
         self.rank, self.world = int(rank), int(world)
 
     def _split(self, batch):
+        """this rank's share of a global batch: contiguous slices of ceil(m / world) rows (the last ranks' may be shorter or empty for
+        the short final batch of an epoch); ``global_count`` = m, what the step's loss is normalised by."""
+        self.global_count = int(batch.shape[0])
         if self.world > 1:
-            per = batch.shape[0] // self.world
+            per = -(-batch.shape[0] // self.world)
             batch = batch[self.rank * per:(self.rank + 1) * per]
         return batch[:, :6].reshape(-1, 2, 3), batch[:, 6:9], batch[:, 9]
 

@@ -1393,6 +1393,51 @@ def test_ray_batcher_matches_train_nerf_batching():
     assert rb2.next_batch()[0].shape == (bs // 2, 2, 3)
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_train_step_takes_the_short_last_batch_of_an_epoch(graph):
+    """nerf/train_nerf.py:139-150 trains on whatever the last slice of an epoch holds.  NerfTrainStep(batch_size=B) takes n < B rays:
+    padded with zero-weight rays, loss normalised by n -- the same loss / PSNR / weights as a step built for exactly n rays."""
+    from msra_practice_project_b200.train_step import NerfTrainStep, RayBatcher
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -0.5)
+    sc, sf, big, small = 16, 24, 96, 40
+    rays = ops.raygen(32, 24, 32 * 1.3875, pose, 100, big)
+    g = torch.Generator().manual_seed(4)
+    target, alpha = torch.rand(big, 3, generator=g).cuda(), torch.rand(big, generator=g).cuda()
+    ts = [torch.rand(big, sc, generator=g).cuda() for _ in range(3)]
+    def fresh(b):
+        torch.manual_seed(0)
+        c, f = models.damp_nerf_(models.NeRF()).cuda(), models.damp_nerf_(models.NeRF()).cuda()
+        return NerfTrainStep(c, f, 2.0, 6.0, sc, sf, b, learning_rate=5e-4, use_alpha=True, graph=graph)
+    small_step = fresh(small)
+    ls, ps = small_step(rays[:small], target[:small], alpha[:small], t_rand=ts[1][:small])
+    step = fresh(big)
+    l, p_ = step(rays[:small], target[:small], alpha[:small], t_rand=ts[1][:small])           # the big trainer's first step is SHORT
+    assert abs(float(l) - float(ls)) < 1e-5 * max(1.0, float(ls)) and abs(float(p_) - float(ps)) < 1e-3, (float(l), float(ls))
+    dp = (step.params - small_step.params).abs()          # Adam's first step is +-lr: a near-zero gradient may flip sign with the atomics' order
+    assert dp.max().item() <= 2 * 5e-4 + 1e-6 and dp.mean().item() < 2e-5, (dp.max().item(), dp.mean().item())
+    for n_, t in ((big, ts[0]), (small, ts[2]), (big, ts[1])):                                 # full, short, full again
+        l, p_ = step(rays[:n_], target[:n_], alpha[:n_], t_rand=t[:n_])
+        assert np.isfinite(float(l)) and np.isfinite(float(p_))
+    assert step.global_step == 4
+    # the batcher + trainer run a whole epoch incl. its short last batch
+    rs = np.random.RandomState(1)
+    images = rs.rand(2, 6, 10, 4).astype(np.float32)                                   # 120 rays, batches of 32: 32, 32, 32, 24
+    poses = np.stack([pigan_render.camera_pos_to_transform_matrix(4.0, 0.4 * i, -0.5) for i in range(2)]).astype(np.float32)
+    rb = RayBatcher(images, poses, 10 * 1.3875, 32)
+    torch.manual_seed(0)
+    c, f = models.damp_nerf_(models.NeRF()).cuda(), models.damp_nerf_(models.NeRF()).cuda()
+    tr = NerfTrainStep(c, f, 2.0, 6.0, sc, sf, 32, use_alpha=True, graph=graph)
+    sizes = []
+    for _ in range(rb.batch_num):
+        r, cc, a = rb.next_batch()
+        sizes.append(r.shape[0])
+        l, _ = tr(r, cc, a, global_count=rb.global_count)
+        assert np.isfinite(float(l))
+    assert sizes == [32, 32, 32, 24] and tr.global_step == 4
+    with pytest.raises(ValueError):
+        RayBatcher(images, poses, 10 * 1.3875, 33, world=2)
+
+
 def test_create_mesh_sdf_matches_density_query(golden):
     """pigan_render.create_mesh_sdf (the sampling half of create_mesh, pi_GAN/utils.py:42-97, as extract_mesh.py:49 calls it on a
     Generator): -sigma on the lattice equals the per-point MLP evaluation of the conditioned field (fp32 path 1e-4; the
