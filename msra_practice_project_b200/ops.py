@@ -68,7 +68,7 @@ _EXACT_LAST = True
 # differs, and the two host syncs + fp32 launches per pass would cost ~8 % of a training step.  set_exact_last_sample(train=True)
 # makes the autograd forward apply the same check as the render (its reverse mode is unaffected).
 _EXACT_LAST_TRAIN = False
-_LAST_REL = {models.KIND_NERF: 2.0 ** -7, models.KIND_FILM: 2.0 ** -8, models.KIND_SIREN: 2.0 ** -8}
+_LAST_REL = {models.KIND_NERF: 2.0 ** -7, models.KIND_FILM: 2.0 ** -9, models.KIND_SIREN: 2.0 ** -9}
 _LAST_ABS = 1e-6
 last_sample_stats = {"calls": 0, "rays": 0, "flagged": 0}      # running totals (bench / tests report the flagged fraction)
 
