@@ -66,7 +66,7 @@ def raw_to_outputs(raw, z_vals, rays_d):
 
 def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num, *,
                 t_rand=None, z_lin=None, u=None, precision=None, stages=None, coarse_no_grad=False,
-                exact_last_sample=None, fine_out=None):
+                exact_last_sample=None, fine_out=None, coarse_outputs_unused=False):
     """nerf/render.py:106-147 -- coarse pass, sample_pdf on the un-jittered mids with
     weights[:,1:-1], sort-merge, fine pass on all Sc+Sf samples.  Returns the reference's 6-tuple
     (rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f).  ``coarse_no_grad`` runs the coarse pass in
@@ -77,6 +77,9 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     sign(sigma_last) and a bf16 rounding would flip ~0.2 % of rays by up to 0.6.
     ``fine_out`` [N,5] (no-grad renders): the fine pass writes (rgb, depth, acc) into its rows -- a rank's slice
     of the gathered frame buffer -- and the returned fine maps are views of it.
+    ``coarse_outputs_unused`` (the pi-GAN wrappers, which return only the fine colour): the COARSE pass skips the check --
+    its last sample only reaches the coarse rgb / depth / acc maps (sample_pdf reads weights[:, 1:-1], nerf/render.py:140),
+    so nothing the caller sees changes, and a training step keeps running without a host synchronisation.
     Applies to passes that run without gradients (renders; the pi-GAN coarse pass).  Passes that carry
     gradients run the raw bf16 forward (mixed-precision training; d sigma_last is zero either way) unless
     ops.set_exact_last_sample(train=True) is set -- an explicit switch, not a silent skip."""
@@ -99,7 +102,7 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
 
     z_vals, mids = ops.stratified_z(z_lin, t_rand)
     with torch.set_grad_enabled(torch.is_grad_enabled() and not coarse_no_grad):
-        raw = _mlp_rays(coarse_model, rays, z_vals, precision, exact_last_sample)
+        raw = _mlp_rays(coarse_model, rays, z_vals, precision, False if coarse_outputs_unused else exact_last_sample)
         rgb_c, depth_c, acc_c, weights = ops.composite(raw, z_vals, rays_d, want_weights=True)
 
     if u is None:
@@ -130,7 +133,8 @@ def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
 
 def render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                         fine_sample_num, chunk=REFERENCE_RAY_CHUNK, *, ray_begin=0, ray_count=None, t_rand=None,
-                        precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=None, fine_out=None):
+                        precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=None, fine_out=None,
+                        coarse_outputs_unused=False):
     """Device-resident core of render_image: renders flattened pixel rows [ray_begin, +ray_count)
     and returns the six per-ray outputs of the fine AND coarse pass as CUDA tensors.  Rays are
     generated on the device (K1); ``launch_rays`` bounds the rays per kernel launch sequence.
@@ -149,7 +153,8 @@ def render_image_device(width, height, focal, pose, near, far, coarse_model, fin
         rays = ops.raygen(width, height, focal, pose, ray_begin + b, cnt, device=dev)
         outs.append(render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
                                 t_rand=t_rand[b:b + cnt], precision=precision, coarse_no_grad=coarse_no_grad,
-                                exact_last_sample=exact_last_sample, fine_out=None if fine_out is None else fine_out[b:b + cnt]))
+                                exact_last_sample=exact_last_sample, fine_out=None if fine_out is None else fine_out[b:b + cnt],
+                                coarse_outputs_unused=coarse_outputs_unused))
     if len(outs) == 1:
         return outs[0]
     if fine_out is not None:                   # the fine maps already sit in fine_out's rows

@@ -43,15 +43,15 @@ def render_image(width, height, focal, pose, near, far, coarse_model, fine_model
     synthesis.py:107).  In pi-GAN coarse_model is fine_model and only the fine rgb is consumed, so
     the coarse pass carries no gradient and runs in inference mode."""
     out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                  chunk, t_rand, precision, coarse_no_grad=True, exact_last_sample=exact_last_sample)
+                  chunk, t_rand, precision, coarse_no_grad=True, exact_last_sample=exact_last_sample, coarse_outputs_unused=True)
     return out[3].reshape(int(height), int(width), 3)
 
 
 def _render(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk, t_rand, precision,
-            coarse_no_grad=False, exact_last_sample=None):
+            coarse_no_grad=False, exact_last_sample=None, coarse_outputs_unused=False):
     return render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk,
                                t_rand=t_rand, precision=precision, coarse_no_grad=coarse_no_grad,
-                               exact_last_sample=exact_last_sample)
+                               exact_last_sample=exact_last_sample, coarse_outputs_unused=coarse_outputs_unused)
 
 
 def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
@@ -115,7 +115,8 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
         u = torch.linspace(0.0, 1.0, steps=sf, device="cpu").to(dev)
         film = torch.as_tensor(film_params, dtype=torch.float32).to(dev).reshape(b, 9, 512)
         z, mids = ops.stratified_z(z_lin, t_all)
-        raw = ops.mlp_film_batched(model, film, rays, z, n * sc, exact_last_sample=exact_last_sample)
+        # coarse pass: only weights[:, 1:-1] are used (the image is the fine colour), so its last sample needs no sign check
+        raw = ops.mlp_film_batched(model, film, rays, z, n * sc, exact_last_sample=False)
         _, _, _, wts, _ = ops.composite_forward(raw, z, rays[:, 1], True)
         z_f = ops.sample_pdf(mids, wts[:, 1:-1], sf, u=u, z_coarse=z, want_samples=False)["sorted"]
         if not grad:
