@@ -407,15 +407,16 @@ def run_b200(args):
     def step_e2e():
         with torch.no_grad():
             p = pinned_pose.numpy()              # host pose -> kernel arguments of the ray generator (the step's H2D)
+            if world == 1:                       # the call a user of nerf/render.py makes: numpy images out (one pinned D2H of [rays,5])
+                return nerf_render.render_image(W, H, focal, p, 2.0, 6.0, coarse, fine, sc, sf, precision=args.precision)
             out = nerf_render.render_image_device(W, H, focal, p, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin,
                                                   ray_count=count, t_rand=None if world == 1 else t_rand, precision=args.precision,
                                                   fine_out=my_rows)
             if world > 1:
                 shard.gather_image(out[3], out[4], out[5], gathered, n_rays, rank, world)
                 if rank == 0:
-                    return gathered.cpu().numpy()
-                return None
-            return out[3].cpu().numpy(), out[4].cpu().numpy(), out[5].cpu().numpy()
+                    return nerf_render.maps_to_numpy(gathered, H, W)
+            return None
 
     step_e2e()
     barrier()
@@ -692,39 +693,38 @@ def run_secondary(args, config=None, embedded=False):
                                          "checkpoints, fused dgrad / MN-major wgrad reverse mode, fused Adam, CUDA-graph replay"),
                     tflops=rows * 1123840 * 3 / (ms * 1e-3) / 1e12)
     elif config == "pigan_grad":
-        # pi-GAN gradient step through the renderer (pi_GAN/train.py:128-134 generator update without the discriminator; the
-        # latent inversion of synthesis.py:92-107 is the same with frozen weights): 4 latents x 64x64, 24+24 samples, gradients to the
-        # FiLM parameters and the FiLM-SIREN weights; coarse pass without gradient, fine pass on the fused tensor-core training path (render_batch, all latents batched)
+        # pi-GAN generator update (pi_GAN/train.py:121-145 without the discriminator, which is out of scope): 4 latents x 64x64, 24+24
+        # samples; z -> mapping network -> FiLM -> all latents rendered in one launch sequence (coarse pass without gradient, SURVEY A.6;
+        # fine pass on the fused tensor-core training path) -> image loss -> gradients of every generator parameter (FiLM-SIREN weights
+        # and, through d film, the mapping network) -> Adam(betas (0, 0.9)) with the train.py:140-145 schedule.  train_step.GeneratorStep:
+        # captured once, replayed as three CUDA graphs (forward | backward | optimiser) with the gradient all-reduce between the last two.
+        from msra_practice_project_b200.train_step import GeneratorStep
         n_lat, res, s_ = 4, 64, 24
         b, c = shard.shard_range(n_lat, rank, world)
         torch.manual_seed(0)
-        net = models.FilmSirenNeRF().to(dev)
+        gen = models.Generator(256, res, near=0.5, far=1.5, fov=12, coarse_samples=s_, fine_samples=s_).to(dev)
+        gstep = GeneratorStep(gen, max(c, 1), graph=not args.no_graph)
         g = torch.Generator().manual_seed(0)
-        film = torch.cat([1.0 + 0.2 * torch.randn(n_lat, 9, 256, generator=g), 0.1 * torch.randn(n_lat, 9, 256, generator=g)], -1).to(dev)
-        film.requires_grad_(True)
-        focal = np.float64(res / 2 / np.tan(6 * np.pi / 180))
-        poses = [pigan_render.camera_pos_to_transform_matrix(1, 0.3 * np.sin(i), 0.15 * np.cos(i)) for i in range(n_lat)]
+        zs = torch.randn((n_lat, 256), generator=g).to(dev)
+        poses = np.stack([pigan_render.camera_pos_to_transform_matrix(1, 0.3 * np.sin(i), 0.15 * np.cos(i)) for i in range(n_lat)])
         target = torch.rand((n_lat, 3, res, res), generator=g).to(dev)
 
         def step():
-            from msra_practice_project_b200 import ops
-            old = ops.set_grad_precision("bf16")
-            try:
-                net.zero_grad(set_to_none=True)
-                film.grad = None
-                if c > 0:
-                    imgs = pigan_render.render_batch(net, film[b:b + c], poses[b:b + c], res, res, focal, 0.5, 1.5, s_, s_)
-                    ((imgs - target[b:b + c]) ** 2).mean().backward()
-                shard.allreduce_gradients([net], average=False)
-            finally:
-                ops.set_grad_precision(old)
+            if c > 0:
+                imgs = gstep.forward(zs[b:b + c], poses[b:b + c])
+                gstep.backward(2.0 * (imgs - target[b:b + c]) / float(n_lat * 3 * res * res))      # d/d imgs of the global-batch MSE
+            else:                                    # more ranks than latents: this rank only joins the all-reduce and applies the update
+                dist.all_reduce(gstep.grads.zero_())
+                gstep._opt()
         ms = timed(step, min(args.steps, 3), args.warmup)
         rows = n_lat * res * res * 2 * s_
         line = dict(metric="rays/s, pi-GAN gradient step through the renderer (4 latents x 64x64, 24+24 samples; d/dfilm + d/dweights)",
                     value=n_lat * res * res / (ms * 1e-3), unit="rays/s", ms_per_step=ms, dtype="bf16", scaling="strong",
-                    config=dict(workload="pi-GAN generator-side gradient step, latents sharded over ranks, coarse pass bf16 inference (no gradient), fine pass "
-                                         "on the fused tcgen05 training path for all latents in one launch sequence (bf16 tile + cosine checkpoints, "
-                                         "fused dgrad, MN-major wgrad on the FiLM-folded weights, unfold into d gamma / d beta / d weights)"),
+                    config=dict(workload="pi-GAN generator update (train.py:121-145 minus the discriminator), latents sharded over ranks: mapping network, "
+                                         "coarse pass bf16 inference (no gradient), fine pass on the fused tcgen05 training path for all latents in one "
+                                         "launch sequence (bf16 tile + cosine checkpoints, fused dgrad, MN-major wgrad on the FiLM-folded weights, unfold "
+                                         "into d gamma / d beta / d weights), mapping-network backward, fused Adam; the whole step replayed as CUDA graphs "
+                                         "(train_step.GeneratorStep)" + ("" if not args.no_graph else " [--no-graph: launched eagerly]")),
                     tflops=rows * 1053696 * 3 / (ms * 1e-3) / 1e12)
     elif config == "pigan":
         n_lat, res, s_ = 64, 128, 24

@@ -60,6 +60,13 @@ int b2r_device_ok(void);
 int b2r_raygen(const double* c2w_host, int width, int height, double focal, int compute_f64,
                long long ray_begin, long long ray_count, float* rays_out, void* stream);
 
+/* The same ray table for n_poses FULL images whose poses live in DEVICE memory: poses_dev[n_poses,12] doubles (row-major 3x4),
+ * rays_out[n_poses * H * W, 2, 3].  Replaces the per-latent get_rays calls of Generator.forward's loop
+ * (pi_GAN/modules.py:176-184 -> Renderer.__call__ :153-161 -> render_image pi_GAN/render.py:197-200); nothing that changes from
+ * step to step is a kernel argument, so a captured CUDA graph replays with new poses.  Bit-identical to b2r_raygen per pose. */
+int b2r_raygen_poses(const double* poses_dev, int n_poses, int width, int height, double focal, int compute_f64,
+                     float* rays_out, void* stream);
+
 /* ---- K2: stratified coarse samples ------------------- render_rays nerf/render.py:123-132 --
  * z_lin[Sc] = torch.linspace(near, far, Sc) made by the caller (its rounding is a contract);
  * t_rand[N,Sc] = the jitter (torch.rand in the reference, :131);
@@ -245,6 +252,12 @@ int b2r_mlp_tc_train_bwd_film(const void* packed_bwd, const float* params, const
 int b2r_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
                   float lr0, float decay_rate, float decay_steps, float beta1, float beta2, float eps, float grad_scale,
                   void* stream);
+
+/* The same step with the schedule of pi_GAN/train.py:140-145: lr_t = lr_end + (lr0 - lr_end) * decay_rate^((t-1)/decay_steps)
+ * (the generator's Adam, pi_GAN/train.py:53: betas (0, 0.9)); lr_end = 0 is b2r_adam_step. */
+int b2r_adam_step_floor(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                        float lr0, float lr_end, float decay_rate, float decay_steps, float beta1, float beta2, float eps,
+                        float grad_scale, void* stream);
 
 /* ---- batched FiLM-SIREN evaluation --------- Generator.forward's per-latent loop, pi_GAN/modules.py:176-184 --------
  * One launch for B latents.  packed: B images of b2r_mlp_tc_packed_bytes(B2R_MODEL_FILM) bytes one after the other, made by

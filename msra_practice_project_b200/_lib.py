@@ -36,6 +36,7 @@ SIGNATURES = {
     "b2r_version": (C.c_int, []),
     "b2r_device_ok": (C.c_int, []),
     "b2r_raygen": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_double, C.c_int, c_ll, c_ll, c_float_p, C.c_void_p]),
+    "b2r_raygen_poses": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, c_float_p, C.c_void_p]),
     "b2r_stratified_z": (C.c_int, [c_float_p, c_float_p, c_ll, C.c_int, c_float_p, c_float_p, C.c_void_p]),
     "b2r_composite_fwd": (C.c_int, [c_float_p, c_float_p, c_float_p, C.c_int, c_ll, C.c_int, c_float_p, c_float_p,
                                     c_float_p, c_float_p, C.c_void_p]),
@@ -71,6 +72,8 @@ SIGNATURES = {
     "b2r_to8b": (C.c_int, [c_float_p, c_ll, C.c_void_p, C.c_void_p]),
     "b2r_adam_step": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_ll, c_float_p, C.c_float, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_void_p]),
+    "b2r_adam_step_floor": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_ll, c_float_p, C.c_float, C.c_float, C.c_float, C.c_float,
+                                      C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]),
     "b2r_mlp_tc_train_bwd": (C.c_int, [C.c_int, C.c_void_p, c_ll, c_float_p, c_float_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                        c_float_p, C.c_void_p]),
     "b2r_mlp_tc_train_fwd_film_batched": (C.c_int, [C.c_void_p, C.c_int, c_ll, C.POINTER(MlpInput), c_float_p, C.c_void_p, C.c_size_t,

@@ -10,11 +10,13 @@
 namespace b2r {
 
 // state: [0] step count (int32 bits), [1] lr_t, [2] 1 - b1^t, [3] sqrt(1 - b2^t)
-__global__ void adam_tick_kernel(float* __restrict__ state, float lr0, float decay_rate, float decay_steps, float beta1, float beta2) {
+__global__ void adam_tick_kernel(float* __restrict__ state, float lr0, float lr_end, float decay_rate, float decay_steps, float beta1, float beta2) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int t = __float_as_int(state[0]) + 1;
     state[0] = __int_as_float(t);
-    const double lr = decay_steps > 0.f ? (double)lr0 * pow((double)decay_rate, (double)(t - 1) / (double)decay_steps) : (double)lr0;
+    // train_nerf.py:170-175 (lr_end = 0) and pi_GAN/train.py:140-145 (floor lr_end): lr_end + (lr0 - lr_end) * rate^((t-1) / decay_steps)
+    const double lr = decay_steps > 0.f ? (double)lr_end + ((double)lr0 - (double)lr_end) * pow((double)decay_rate, (double)(t - 1) / (double)decay_steps)
+                                        : (double)lr0;
     state[1] = (float)lr;
     state[2] = (float)(1.0 - pow((double)beta1, (double)t));
     state[3] = (float)sqrt(1.0 - pow((double)beta2, (double)t));
@@ -46,16 +48,26 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float4* __restrict__ p, 
 
 }  // namespace b2r
 
+extern "C" int b2r_adam_step_floor(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                                   float lr0, float lr_end, float decay_rate, float decay_steps, float beta1, float beta2, float eps,
+                                   float grad_scale, void* stream);
+
 extern "C" int b2r_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
                              float lr0, float decay_rate, float decay_steps, float beta1, float beta2, float eps, float grad_scale,
                              void* stream) {
+    return b2r_adam_step_floor(params, grads, exp_avg, exp_avg_sq, n, state, lr0, 0.0f, decay_rate, decay_steps, beta1, beta2, eps, grad_scale, stream);
+}
+
+extern "C" int b2r_adam_step_floor(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float* state,
+                                   float lr0, float lr_end, float decay_rate, float decay_steps, float beta1, float beta2, float eps,
+                                   float grad_scale, void* stream) {
     using namespace b2r;
     B2R_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && state, "b2r_adam_step: NULL pointer");
     B2R_CHECK_ARG(n >= 0, "b2r_adam_step: negative size");
     B2R_CHECK_ARG((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq | (uintptr_t)state) & 15) == 0,
                   "b2r_adam_step: buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    adam_tick_kernel<<<1, 32, 0, st>>>(state, lr0, decay_rate, decay_steps, beta1, beta2);
+    adam_tick_kernel<<<1, 32, 0, st>>>(state, lr0, lr_end, decay_rate, decay_steps, beta1, beta2);
     B2R_LAUNCH_CHECK("b2r_adam_step (tick)");
     if (n == 0) return 0;
     const long long n4 = n / 4;

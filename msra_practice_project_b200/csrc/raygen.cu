@@ -65,6 +65,45 @@ __global__ void raygen_f64_kernel(Cam<double> cam, int width, float half_w, floa
     }
 }
 
+// B full images from B poses that live in DEVICE memory (poses[B,12] doubles, row-major 3x4): the ray table of
+// Generator.forward's per-latent loop (pi_GAN/modules.py:176-184, one random pose per latent) in one launch, with nothing
+// step-dependent in the kernel arguments -- so a CUDA graph that contains it can be replayed with new poses.  Same arithmetic
+// as the two kernels above (mode = compute_f64 of b2r_raygen: 0 = all float32, bit 0 = float64 division, bit 1 = float64 pose).
+__global__ void raygen_poses_kernel(const double* __restrict__ poses, int width, long long rays_per_pose, long long total,
+                                    float half_w, float half_h, double focal, int mode, float* __restrict__ rays) {
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long b = t / rays_per_pose, pix = t - b * rays_per_pose;
+    const double* P = poses + b * 12;
+    float i = (float)(pix % width), j = (float)(pix / width);
+    float* out = rays + t * 6;
+    if (mode) {
+        double dx, dy;
+        if (mode & 1) {
+            dx = __ddiv_rn((double)__fsub_rn(i, half_w), focal);
+            dy = __ddiv_rn((double)(-__fsub_rn(j, half_h)), focal);
+        } else {
+            dx = (double)__fdiv_rn(__fsub_rn(i, half_w), (float)focal);
+            dy = (double)__fdiv_rn(-__fsub_rn(j, half_h), (float)focal);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            out[k] = (float)P[4 * k + 3];
+            double s = __dadd_rn(__dmul_rn(dx, P[4 * k + 0]), __dmul_rn(dy, P[4 * k + 1]));
+            out[3 + k] = (float)__dadd_rn(s, __dmul_rn(-1.0, P[4 * k + 2]));
+        }
+    } else {
+        const float dx = __fdiv_rn(__fsub_rn(i, half_w), (float)focal);
+        const float dy = __fdiv_rn(-__fsub_rn(j, half_h), (float)focal);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            out[k] = (float)P[4 * k + 3];
+            float s = __fadd_rn(__fmul_rn(dx, (float)P[4 * k + 0]), __fmul_rn(dy, (float)P[4 * k + 1]));
+            out[3 + k] = __fadd_rn(s, __fmul_rn(-1.0f, (float)P[4 * k + 2]));
+        }
+    }
+}
+
 // z = lower + (upper - lower) * t, three separately rounded ops as in torch (render.py:132).
 __global__ void stratified_kernel(const float* __restrict__ z_lin, const float* __restrict__ t_rand,
                                   long long total, int sc, float* __restrict__ z_out,
@@ -132,6 +171,21 @@ extern "C" int b2r_raygen(const double* c2w_host, int width, int height, double 
         raygen_f32_kernel<<<(unsigned)((ray_count * 6 + block - 1) / block), block, 0, st>>>(camf, width, half_w, half_h, (float)focal, ray_begin,
                                                                                             ray_count, rays_out);
     B2R_LAUNCH_CHECK("b2r_raygen");
+    return 0;
+}
+
+extern "C" int b2r_raygen_poses(const double* poses_dev, int n_poses, int width, int height, double focal, int compute_f64,
+                                float* rays_out, void* stream) {
+    using namespace b2r;
+    B2R_CHECK_ARG(n_poses >= 0, "b2r_raygen_poses: negative pose count");
+    if (n_poses == 0) return 0;
+    B2R_CHECK_ARG(poses_dev && rays_out, "b2r_raygen_poses: NULL pointer");
+    B2R_CHECK_ARG(width > 0 && height > 0 && focal != 0.0, "b2r_raygen_poses: bad image geometry");
+    const long long per = (long long)width * height, total = per * n_poses;
+    float half_w = (float)(width * 0.5), half_h = (float)(height * 0.5);
+    raygen_poses_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(poses_dev, width, per, total, half_w, half_h, focal,
+                                                                                          compute_f64 & 3, rays_out);
+    B2R_LAUNCH_CHECK("b2r_raygen_poses");
     return 0;
 }
 

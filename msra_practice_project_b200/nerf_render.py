@@ -162,16 +162,37 @@ def render_image_device(width, height, focal, pose, near, far, coarse_model, fin
     return tuple(torch.cat([o[i] for o in outs]) for i in range(6))
 
 
+_host_stage: dict = {}      # (device index, rays) -> pinned [rays,5] staging buffer of the image read-back
+
+
+def maps_to_numpy(packed: torch.Tensor, h: int, w: int):
+    """The frame's fine (rgb, depth, acc) rows [H*W,5] on the device -> the three numpy images the reference returns
+    (nerf/render.py:161-166).  ONE device-to-host copy through a cached page-locked buffer (12.8 MB for an 800x800 frame: three
+    pageable ``.cpu()`` copies of strided views cost several ms more), then the maps are copied out so the caller owns them."""
+    key = (packed.device.index, int(packed.shape[0]))
+    stage = _host_stage.get(key)
+    if stage is None:
+        if len(_host_stage) >= 8:
+            _host_stage.clear()
+        stage = torch.empty((int(packed.shape[0]), 5), dtype=torch.float32, device="cpu", pin_memory=True)
+        _host_stage[key] = stage
+    stage.copy_(packed, non_blocking=True)
+    torch.cuda.current_stream(packed.device).synchronize()
+    a = stage.numpy()
+    return (np.ascontiguousarray(a[:, :3]).reshape(h, w, 3), np.ascontiguousarray(a[:, 3]).reshape(h, w, 1),
+            np.ascontiguousarray(a[:, 4]).reshape(h, w, 1))
+
+
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
                  chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None):
     """nerf/render.py:150-167 -- numpy (H,W,3), (H,W,1), (H,W,1) = fine rgb / depth / acc."""
-    with torch.no_grad():
-        out = render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
-                                  fine_sample_num, chunk, t_rand=t_rand, precision=precision,
-                                  exact_last_sample=exact_last_sample)
     h, w = int(height), int(width)
-    return (out[3].cpu().numpy().reshape(h, w, 3), out[4].cpu().numpy().reshape(h, w, 1),
-            out[5].cpu().numpy().reshape(h, w, 1))
+    with torch.no_grad():
+        packed = torch.empty((h * w, 5), dtype=torch.float32, device=_model_device(coarse_model))
+        render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
+                            fine_sample_num, chunk, t_rand=t_rand, precision=precision,
+                            exact_last_sample=exact_last_sample, fine_out=packed)
+    return maps_to_numpy(packed, h, w)
 
 
 def render_video(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,

@@ -153,6 +153,37 @@ def raygen(width: int, height: int, focal, c2w, begin: int = 0, count: int | Non
     return out
 
 
+def raygen_poses(width: int, height: int, focal, poses: torch.Tensor, pose_f64: bool = False) -> torch.Tensor:
+    """The [B*H*W,2,3] ray table of B full images whose poses are a DEVICE tensor [B,3|4,4] (b2r_raygen_poses): per pose bit-identical
+    to raygen(), but nothing step-dependent is a kernel argument, so it can sit inside a captured CUDA graph (train_step.GeneratorStep).
+    ``pose_f64``: the poses came from float64 numpy matrices (numpy's promotion, see b2r_raygen); float32 poses convert exactly."""
+    if not isinstance(poses, torch.Tensor) or not poses.is_cuda or poses.dim() != 3 or poses.shape[1] < 3 or poses.shape[2] != 4:
+        raise RuntimeError("poses must be a CUDA tensor [B,3,4] or [B,4,4]")
+    p = poses[:, :3, :].to(torch.float64).contiguous()
+    b = p.shape[0]
+    f64 = (1 if isinstance(focal, np.float64) else 0) | (2 if pose_f64 else 0)
+    out = torch.empty((b * int(width) * int(height), 2, 3), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        check(lib().b2r_raygen_poses(ptr(p), b, int(width), int(height), float(focal), f64, ptr(out), _stream(out)), "b2r_raygen_poses")
+    return out
+
+
+_linspace_cache: dict = {}
+
+
+def host_linspace(a: float, b: float, n: int, device) -> torch.Tensor:
+    """torch.linspace(a, b, n) made on the HOST (its last-bit rounding is a contract) and kept on the device, cached per
+    (a, b, n, device): callers inside a captured CUDA graph must not issue a host-to-device copy."""
+    key = (float(a), float(b), int(n), str(device))
+    t = _linspace_cache.get(key)
+    if t is None:
+        if len(_linspace_cache) >= 64:
+            _linspace_cache.clear()
+        t = torch.linspace(float(a), float(b), steps=int(n), device="cpu").to(device)
+        _linspace_cache[key] = t
+    return t
+
+
 def stratified_z(z_lin: torch.Tensor, t_rand: torch.Tensor):
     """z_vals[N,Sc], mids[Sc-1] from linspace(near,far,Sc) and the jitter (nerf/render.py:123-132)."""
     z_lin = _cuda_f32(z_lin, "z_lin")
@@ -310,6 +341,9 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, n_samples: int, u: tor
         u = torch.linspace(0.0, 1.0, steps=int(n_samples), device="cpu").to(dev)   # host-made: its rounding is a contract
     u = _cuda_f32(u, "u")
     sf = int(n_samples)
+    if u.dim() != 1 or u.numel() != sf:
+        # the kernel reads exactly n_samples entries and merges them as a SORTED list (non-decreasing, like torch.linspace(0, 1, n))
+        raise RuntimeError(f"u must be a 1-D tensor of n_samples = {sf} non-decreasing values, got shape {tuple(u.shape)}")
     samples = torch.empty((n, sf), dtype=torch.float32, device=dev) if want_samples else None
     cdf = torch.empty((n, nb), dtype=torch.float32, device=dev) if want_cdf else None
     merged, zc, sc = None, None, 0
@@ -493,16 +527,16 @@ def tc_train_backward(packed_bwd: torch.Tensor, kind: int, raw: torch.Tensor, d_
 
 def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, state: torch.Tensor,
               lr0: float, decay_rate: float = 1.0, decay_steps: float = 0.0, betas=(0.9, 0.999), eps: float = 1e-8,
-              grad_scale: float = 1.0) -> None:
-    """b2r_adam_step: torch.optim.Adam on a flat fp32 bucket with the train_nerf.py:170-175 learning-rate decay; the step
-    counter lives in `state` (4 floats on the device, zero before the first step)."""
+              grad_scale: float = 1.0, lr_end: float = 0.0) -> None:
+    """b2r_adam_step_floor: torch.optim.Adam on a flat fp32 bucket with the learning-rate decay of train_nerf.py:170-175 (lr_end = 0)
+    or pi_GAN/train.py:140-145 (floor lr_end); the step counter lives in `state` (4 floats on the device, zero before the first step)."""
     for t in (params, grads, exp_avg, exp_avg_sq, state):
         if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
             raise RuntimeError("adam_step needs contiguous fp32 CUDA tensors")
     with torch.cuda.device(params.device):
-        check(lib().b2r_adam_step(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(state), float(lr0),
-                                  float(decay_rate), float(decay_steps), float(betas[0]), float(betas[1]), float(eps),
-                                  float(grad_scale), _stream(params)), "b2r_adam_step")
+        check(lib().b2r_adam_step_floor(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(state), float(lr0),
+                                        float(lr_end), float(decay_rate), float(decay_steps), float(betas[0]), float(betas[1]), float(eps),
+                                        float(grad_scale), _stream(params)), "b2r_adam_step_floor")
 
 
 def train_loss_finish(sums, inv_count, alpha_weight: float, inv_local, loss, psnr) -> None:

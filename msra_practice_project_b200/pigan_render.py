@@ -12,8 +12,8 @@ import torch
 from tqdm import tqdm
 
 from . import ops
-from .nerf_render import (REFERENCE_RAY_CHUNK, _draw_t_rand, get_rays, raw_to_outputs, render_image_device, render_rays, run_network,
-                          sample_pdf, to8b)
+from .nerf_render import (REFERENCE_RAY_CHUNK, _draw_t_rand, get_rays, maps_to_numpy, raw_to_outputs, render_image_device, render_rays,
+                          run_network, sample_pdf, to8b)
 
 __all__ = ["np", "torch", "tqdm", "to8b", "trans_t", "rot_phi", "rot_theta", "blender_coord",
            "camera_pos_to_transform_matrix", "get_rays", "sample_pdf", "run_network", "raw_to_outputs", "render_rays",
@@ -57,12 +57,12 @@ def _render(width, height, focal, pose, near, far, coarse_model, fine_model, sc,
 def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                     fine_sample_num, chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None):
     """pi_GAN/render.py:209-226 -- numpy (H,W,3), (H,W,1), (H,W,1)."""
-    with torch.no_grad():
-        out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                      chunk, t_rand, precision, exact_last_sample=exact_last_sample)
     h, w = int(height), int(width)
-    return (out[3].cpu().numpy().reshape(h, w, 3), out[4].cpu().numpy().reshape(h, w, 1),
-            out[5].cpu().numpy().reshape(h, w, 1))
+    with torch.no_grad():
+        packed = torch.empty((h * w, 5), dtype=torch.float32, device=next(coarse_model.parameters()).device)
+        render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
+                            chunk, t_rand=t_rand, precision=precision, exact_last_sample=exact_last_sample, fine_out=packed)
+    return maps_to_numpy(packed, h, w)
 
 
 def render_video_np(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num,
@@ -106,13 +106,16 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
     dev = next(model.parameters()).device
     n = w * h
     with torch.no_grad():
-        rays = torch.cat([ops.raygen(w, h, focal, poses[i], device=dev) for i in range(b)])            # [B*HW,2,3]
+        if isinstance(poses, torch.Tensor) and poses.is_cuda:
+            rays = ops.raygen_poses(w, h, focal, poses)         # poses on the device: one launch, replayable inside a CUDA graph
+        else:
+            rays = torch.cat([ops.raygen(w, h, focal, poses[i], device=dev) for i in range(b)])        # [B*HW,2,3]
         if t_rand is None:
             t_all = torch.cat([_draw_t_rand(n, sc, REFERENCE_RAY_CHUNK, dev) for _ in range(b)])         # the reference's draw order
         else:
             t_all = torch.as_tensor(t_rand, dtype=torch.float32).to(dev).reshape(b * n, sc)
-        z_lin = torch.linspace(float(near), float(far), steps=sc, device="cpu").to(dev)
-        u = torch.linspace(0.0, 1.0, steps=sf, device="cpu").to(dev)
+        z_lin = ops.host_linspace(near, far, sc, dev)
+        u = ops.host_linspace(0.0, 1.0, sf, dev)
         film = torch.as_tensor(film_params, dtype=torch.float32).to(dev).reshape(b, 9, 512)
         z, mids = ops.stratified_z(z_lin, t_all)
         # coarse pass: only weights[:, 1:-1] are used (the image is the fine colour), so its last sample needs no sign check

@@ -304,3 +304,180 @@ class RayBatcher:
                 self.rays_rgba = self.rays_rgba[shuffle_idx.to(self.dev)]
             self.batch_idx = 0
         return self._split(b)
+
+
+class GeneratorStep:
+    """The generator update of ``pi_GAN/train.py:121-145`` as CUDA graphs around the caller's discriminator (which is out of scope
+    here):
+
+        images = step.forward(z)                       # graph 1: mapping network -> FiLM -> all latents rendered in one launch sequence
+        g_loss = loss_f(discriminator(images)).mean()  # the caller's code, eager
+        step.backward(torch.autograd.grad(g_loss, images)[0])    # graph 2: composite reverse -> fused FiLM-SIREN reverse mode ->
+                                                       # d film -> mapping network;  [all-reduce];  graph 3: fused Adam + LR schedule
+
+    Under autograd the same step is ~170 launches issued from Python (generator(z) + loss.backward() + torch.optim.Adam over 50
+    parameter tensors): at the reference's early-stage shapes the GPU finishes before the host has queued the launches.  Here the
+    launch sequence is captured once per (batch, resolution, sample counts) and replayed; everything that changes between steps
+    lives in device buffers: z, the camera poses (b2r_raygen_poses reads them from device memory), the jitter (drawn by the
+    captured torch.rand, whose Philox offset torch advances per replay), the upstream gradient, the step count and the decayed
+    learning rate (b2r_adam_step_floor: lr_end + (lr0 - lr_end) * 0.1^((t-1) / (lr_decay * 1000)), train.py:140-145).
+
+    The generator stays an ordinary ``nn.Module`` (``models.Generator`` or the reference's own class -- same attributes): its
+    parameters become views of one flat fp32 buffer (state_dict() / torch.save keep working), Adam's moments are flat too.
+    Multi-GPU: every rank runs its slice of the latent batch; ``backward`` all-reduces the flat gradient bucket once (SUM; scale the
+    upstream gradient for the global batch, as g_loss.mean() over the global batch does)."""
+
+    def __init__(self, generator, batch_size, *, learning_rate=5e-5, learning_rate_end=1e-5, lr_decay=500, betas=(0.0, 0.9), eps=1e-8,
+                 graph=True, group=None):
+        self.gen = generator
+        net = generator.film_siren_nerf
+        if models.model_kind(net) != models.KIND_FILM:
+            raise TypeError("GeneratorStep needs a pi-GAN Generator (film_siren_nerf + mapping_network, pi_GAN/modules.py:164-197)")
+        ps = [p for p in generator.parameters()]
+        self.dev = ps[0].device
+        if self.dev.type != "cuda":
+            raise RuntimeError("the generator must live on a CUDA device: the B200 training step has no CPU fallback")
+        self.batch = int(batch_size)
+        if self.batch < 1:
+            raise ValueError("batch_size must be >= 1 latent per rank")
+        self.lr0, self.lr_end, self.decay_steps = float(learning_rate), float(learning_rate_end), float(lr_decay) * 1000.0
+        self.betas, self.eps = betas, float(eps)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.use_graph = bool(graph)
+        n = sum(p.numel() for p in ps)
+        n_pad = (n + 3) // 4 * 4
+        self.n = n
+        self.params = torch.zeros((n_pad,), dtype=torch.float32, device=self.dev)
+        off = 0
+        for p in ps:                                     # generator.parameters() order = the order torch.optim.Adam would see
+            k = p.numel()
+            self.params[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.params[off:off + k].view(p.shape)
+            off += k
+        self._plist = ps
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.state = torch.zeros((4,), dtype=torch.float32, device=self.dev)
+        self.z = torch.zeros((self.batch, int(generator.input_dim)), dtype=torch.float32, device=self.dev)
+        self.poses = torch.zeros((self.batch, 4, 4), dtype=torch.float32, device=self.dev)
+        self._poses_host = torch.zeros((self.batch, 4, 4), dtype=torch.float32, device="cpu", pin_memory=True)
+        self.d_images = None
+        self.images = None
+        self.t_rand = None                               # injected jitter [B, H*W, coarse_samples] (parity runs); None: drawn per step
+        self._draw_t = True
+        self._graphs, self._key = None, None
+
+    # ---- the three pieces, as plain launches on the current stream ---------------------------------------------------
+    def _fwd(self):
+        with torch.enable_grad():
+            self.images = _generator_forward(self.gen, self.z, self.poses, None if self._draw_t else self.t_rand)
+        if self.d_images is None or self.d_images.shape != self.images.shape:
+            self.d_images = torch.zeros_like(self.images)
+
+    def _bwd(self):
+        gs = torch.autograd.grad([self.images], self._plist, [self.d_images], allow_unused=True)
+        flat = [(g if g is not None else torch.zeros_like(p)).reshape(-1) for g, p in zip(gs, self._plist)]
+        torch.cat(flat, out=self.grads[:self.n])
+
+    def _opt(self):
+        ops.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.state, self.lr0, 0.1, self.decay_steps, self.betas,
+                      self.eps, lr_end=self.lr_end)
+
+    def _shape_key(self):
+        r = self.gen.renderer
+        return (int(r.width), int(r.height), int(r.coarse_samples), int(r.fine_samples), float(r.near), float(r.far), float(r.focal), self._draw_t)
+
+    def _capture(self):
+        """warm up on a side stream (this also fills the host-made linspace caches, so the capture sees no host-to-device copy), capture
+        forward | backward | optimiser, and restore what the warm-up steps changed (weights, moments, step count)."""
+        keep = [t.clone() for t in (self.params, self.exp_avg, self.exp_avg_sq, self.state)]
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._fwd()
+                self.d_images.fill_(1e-3)
+                self._bwd()
+                self._opt()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.d_images = torch.zeros_like(self.images)         # allocated OUTSIDE the graphs' pool: the caller's gradient is copied into it
+        with torch.cuda.graph(g1):
+            self._fwd()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self._bwd()
+        with torch.cuda.graph(g3, pool=g1.pool()):
+            self._opt()
+        for t, k in zip((self.params, self.exp_avg, self.exp_avg_sq, self.state), keep):
+            t.copy_(k)
+        self._graphs = (g1, g2, g3)
+
+    # ---- public API --------------------------------------------------------------------------------------------------
+    def forward(self, z=None, poses=None, t_rand=None) -> torch.Tensor:
+        """images [B,3,H,W] for this rank's latents z[B,input_dim] (None: drawn with torch.randn like train.py:126) and camera poses
+        [B,4,4] (None: drawn with np.random in the reference's order, modules.py:153-158).  The returned tensor is a static buffer that the
+        next forward() overwrites; it is detached -- differentiate the caller's loss with respect to it and hand the result to backward()."""
+        import numpy as np
+        if z is None:
+            z = torch.randn(self.batch, self.z.shape[1], device=self.dev)
+        if tuple(z.shape) != tuple(self.z.shape):
+            raise ValueError(f"this step was built for z of shape {tuple(self.z.shape)}, got {tuple(z.shape)}")
+        self.z.copy_(z, non_blocking=True)
+        if poses is None:
+            poses = np.stack([self.gen.renderer.draw_pose() for _ in range(self.batch)])
+        if isinstance(poses, torch.Tensor) and poses.is_cuda:
+            self.poses.copy_(poses.reshape(self.batch, 4, 4))
+        else:
+            self._poses_host.copy_(torch.as_tensor(np.asarray(poses, dtype=np.float32)).reshape(self.batch, 4, 4))
+            self.poses.copy_(self._poses_host, non_blocking=True)
+        self._draw_t = t_rand is None
+        if t_rand is not None:                           # parity runs inject the jitter the reference draws with torch.rand (render.py:131)
+            r = self.gen.renderer
+            shape = (self.batch, int(r.width) * int(r.height), int(r.coarse_samples))
+            if self.t_rand is None or tuple(self.t_rand.shape) != shape:
+                self.t_rand = torch.zeros(shape, dtype=torch.float32, device=self.dev)
+                self._graphs = None
+            self.t_rand.copy_(torch.as_tensor(t_rand).reshape(shape), non_blocking=True)
+        if self.use_graph:
+            key = self._shape_key()
+            if self._graphs is None or key != self._key:
+                self._key = key
+                self._capture()
+            self._graphs[0].replay()
+        else:
+            self._fwd()
+        return self.images.detach()
+
+    def backward(self, d_images: torch.Tensor) -> None:
+        """d loss / d images [B,3,H,W] of the images the last forward() returned -> gradients -> (all-reduce) -> Adam step."""
+        if self.images is None:
+            raise RuntimeError("backward() needs a forward() first")
+        if tuple(d_images.shape) != tuple(self.images.shape):
+            raise ValueError(f"d_images must have the images' shape {tuple(self.images.shape)}, got {tuple(d_images.shape)}")
+        self.d_images.copy_(d_images, non_blocking=True)
+        if self.use_graph:
+            self._graphs[1].replay()
+        else:
+            self._bwd()
+        if self.world > 1:
+            dist.all_reduce(self.grads, group=self.group)
+        if self.use_graph:
+            self._graphs[2].replay()
+        else:
+            self._opt()
+
+    @property
+    def global_step(self) -> int:
+        return int(self.state[:1].view(torch.int32).item())
+
+
+def _generator_forward(gen, z, poses, t_rand):
+    """Generator.forward (pi_GAN/modules.py:176-184) -- also for the reference's own class (same sub-modules): mapping network, then all
+    latents through render_batch with the poses read from device memory."""
+    from . import pigan_render
+    film = gen.mapping_network(z)
+    r = gen.renderer
+    return pigan_render.render_batch(gen.film_siren_nerf, film, poses, r.width, r.height, r.focal, r.near, r.far, r.coarse_samples,
+                                     r.fine_samples, t_rand=t_rand)
