@@ -352,11 +352,16 @@ template <int KIND> __host__ __device__ constexpr LayerDesc wlayer(int i) {
     return KIND == kKFilm ? film_layer(i, true) : (KIND == kKFilmNoDir ? film_layer(i, false) : (KIND == kKSiren ? siren_layer(i) : nerf_layer(i)));
 }
 
-constexpr int kWStages = 3;
-constexpr uint32_t kWSlot = 65536;                                       // up to 8 half blocks of 8 KB
-constexpr uint32_t kWBarOff = kWStages * kWSlot;
-constexpr uint32_t kWSmem = kWBarOff + 128 + 1024;
+// Operand ring of the wgrad kernel: 192 KB cut into stages of (g_nb + x_nb) half blocks of 8 KB -- 3 stages of 64 KB for the 256 x 256
+// units, up to 8 stages for the narrow ones (pos-enc / dir-enc / aux inputs: 24-40 KB per stage).  With a fixed 3-stage ring the narrow
+// units had only 72-120 KB in flight per SM and were latency-bound: their CTAs finished 25-45 % after the others (per-CTA timers:
+// 537 us against a median of 417 us on the 262,144-row coarse pass) and set the kernel's duration.
+constexpr int kWMaxStages = 8;
+constexpr uint32_t kWRing = 196608;
+constexpr uint32_t kWBarOff = kWRing;
+constexpr uint32_t kWSmem = kWBarOff + 256 + 1024;
 constexpr int kWThreads = 192;                                           // producer, MMA issuer, 4 reduce / flush warps
+__host__ __device__ constexpr int wstages(int cost) { return (int)(kWRing / ((uint32_t)cost * 8192u)) < kWMaxStages ? (int)(kWRing / ((uint32_t)cost * 8192u)) : kWMaxStages; }
 
 struct WPiece { int u; long long t0, t1; };
 // CTA b owns the slice [b, b+1) * total / grid of the cost line (units laid end to end, each n_sub tiles x cost(u)); both
@@ -386,11 +391,11 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
                      long long t_begin, long long t_count) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t full = smem + kWBarOff, empty = full + 8 * kWStages, acc_full = empty + 8 * kWStages, tmem_empty = acc_full + 8,
+    const uint32_t full = smem + kWBarOff, empty = full + 8 * kWMaxStages, acc_full = empty + 8 * kWMaxStages, tmem_empty = acc_full + 8,
                    slot_addr = tmem_empty + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kWStages; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 5); }
+        for (int s = 0; s < kWMaxStages; ++s) { mbar_init(full + 8 * s, 1); mbar_init(empty + 8 * s, 5); }
         mbar_init(acc_full, 1);
         mbar_init(tmem_empty, 4);
         fence_barrier_init();
@@ -408,7 +413,9 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
 
     if (warp == 0) {
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
+            // every piece starts at stage 0 of ITS stage size; `par` holds one phase bit per barrier (the number of stages differs between
+            // pieces, so the barriers are not used equally often)
+            uint32_t par = 0;
             long long base = 0;
             for (int u = 0; u < n_wunits<KIND>(); ++u) {
                 WPiece pc;
@@ -417,23 +424,28 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
                 const uint8_t* gsrc = scratch + (size_t)un.g_off * n_sub * kBlk;
                 const uint8_t* xsrc = saved + (size_t)un.x_off * n_sub * kBlk;
                 const uint32_t bytes = (uint32_t)(un.g_nb + un.x_nb) * 8192u;
+                const int n_st = wstages(un.g_nb + un.x_nb);
+                int stage = 0;
                 for (long long T = t_begin + pc.t0; T < t_begin + pc.t1; ++T) {
                     for (int hs = 0; hs < 2; ++hs) {
-                        mbar_wait(empty + 8 * stage, phase ^ 1u);
+                        mbar_wait(empty + 8 * stage, ((par >> stage) & 1u) ^ 1u);
+                        par ^= 1u << stage;
                         mbar_arrive_expect_tx(full + 8 * stage, bytes);
-                        const uint32_t dst = smem + stage * kWSlot;
+                        const uint32_t dst = smem + (uint32_t)stage * bytes;
                         for (int i = 0; i < un.g_nb; ++i)
                             bulk_g2s(dst + (uint32_t)i * 8192u, gsrc + ((size_t)T * un.g_nb + i) * kBlk + (size_t)hs * 8192, 8192u, full + 8 * stage);
                         for (int j = 0; j < un.x_nb; ++j)
                             bulk_g2s(dst + (uint32_t)(un.g_nb + j) * 8192u, xsrc + ((size_t)T * un.x_nb + j) * kBlk + (size_t)hs * 8192, 8192u,
                                      full + 8 * stage);
-                        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+                        if (++stage == n_st) stage = 0;
                     }
                 }
+                // the next piece cuts the ring differently: wait until the consumers have released every stage of this one
+                for (int st = 0; st < n_st; ++st) mbar_wait(empty + 8 * st, ((par >> st) & 1u) ^ 1u);
             }
         }
     } else if (warp == 1) {
-        uint32_t stage = 0, phase = 0, te_phase = 0;
+        uint32_t par = 0, te_phase = 0;
         bool first_piece = true;
         long long base = 0;
         // A = dPre half blocks, B = X half blocks: MN-major SWIZZLE_128B, LBO = 8 KB (next 64 columns), SBO = 1 KB (next 8 rows of K)
@@ -447,10 +459,14 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
             if (!first_piece) { mbar_wait(tmem_empty, te_phase); te_phase ^= 1u; tc_fence_after(); }
             first_piece = false;
             uint32_t acc = 0;
+            const int n_st = wstages(un.g_nb + un.x_nb);
+            const uint32_t st_bytes = (uint32_t)(un.g_nb + un.x_nb) * 8192u;
+            int stage = 0;
             for (long long st = 0; st < 2 * (pc.t1 - pc.t0); ++st) {
-                mbar_wait(full + 8 * stage, phase);
+                mbar_wait(full + 8 * stage, (par >> stage) & 1u);
+                par ^= 1u << stage;
                 tc_fence_after();
-                const uint32_t a_s = smem + stage * kWSlot, b_s = a_s + (uint32_t)un.g_nb * 8192u;
+                const uint32_t a_s = smem + (uint32_t)stage * st_bytes, b_s = a_s + (uint32_t)un.g_nb * 8192u;
                 if (elect_one()) {
                     for (int m = 0; m < n_m; ++m) {
 #pragma unroll
@@ -464,7 +480,7 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
                 }
                 __syncwarp();
                 acc = 1;
-                if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+                if (++stage == n_st) stage = 0;
             }
             if (elect_one()) mma_commit(acc_full);
             __syncwarp();
@@ -472,7 +488,7 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
     } else {
         const int w = warp - 2;                    // 0..3: G block reduced by this warp
         const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-        uint32_t stage = 0, phase = 0, af_phase = 0;
+        uint32_t par = 0, af_phase = 0;
         long long base = 0;
         for (int u = 0; u < n_wunits<KIND>(); ++u) {
             WPiece pc;
@@ -481,10 +497,14 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
             const LayerDesc L = wlayer<KIND>(un.layer);
             const bool do_bias = un.bias && w < un.g_nb;
             float s0 = 0.f, s1 = 0.f;
+            const int n_st = wstages(un.g_nb + un.x_nb);
+            const uint32_t st_bytes = (uint32_t)(un.g_nb + un.x_nb) * 8192u;
+            int stage = 0;
             for (long long st = 0; st < 2 * (pc.t1 - pc.t0); ++st) {
-                mbar_wait(full + 8 * stage, phase);
+                mbar_wait(full + 8 * stage, (par >> stage) & 1u);
+                par ^= 1u << stage;
                 if (do_bias) {
-                    const uint32_t blk = smem + stage * kWSlot + (uint32_t)w * 8192u + (uint32_t)(lane & 3) * 4u;
+                    const uint32_t blk = smem + (uint32_t)stage * st_bytes + (uint32_t)w * 8192u + (uint32_t)(lane & 3) * 4u;
 #pragma unroll 8
                     for (uint32_t row = 0; row < 64; ++row) {
                         uint32_t x;
@@ -495,7 +515,7 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + 8 * stage);
-                if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+                if (++stage == n_st) stage = 0;
             }
             // ---- flush the accumulators of this piece
             mbar_wait(acc_full, af_phase);
@@ -509,10 +529,20 @@ nerf_tc_wgrad_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restric
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)quad << 21) + (uint32_t)m * 256u + (uint32_t)j * 32u, v);
                     tmem_ld_wait();
+                    // the thread's 32 values are 128 contiguous bytes of dW's row o: 16-byte vector reductions where the group is whole and aligned
+                    float* __restrict__ prow = dW + o * L.in + un.col_off + (j * 32 - un.x_col0);
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) {
+                    for (int e = 0; e < 32; e += 4) {
                         const int col = j * 32 + e - un.x_col0;
-                        if (col >= 0 && col < un.n_valid) atomicAdd(dW + o * L.in + un.col_off + col, un.scale * __uint_as_float(v[e]));
+                        if (col >= 0 && col + 3 < un.n_valid && ((reinterpret_cast<uintptr_t>(prow + e) & 15) == 0)) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(prow + e), "f"(un.scale * __uint_as_float(v[e])),
+                                         "f"(un.scale * __uint_as_float(v[e + 1])), "f"(un.scale * __uint_as_float(v[e + 2])),
+                                         "f"(un.scale * __uint_as_float(v[e + 3])) : "memory");
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (col + q >= 0 && col + q < un.n_valid) atomicAdd(prow + e + q, un.scale * __uint_as_float(v[e + q]));
+                        }
                     }
                 }
             }
