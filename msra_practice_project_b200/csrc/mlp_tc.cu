@@ -276,9 +276,9 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 auto tile = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
                 auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
                 mbar_wait(ready, ph); bulk_s2g(tile(kSavPE, 1), aux, kBlk); finish();                       // positional encoding
-                for (int l = 0; l < 8; ++l) { mbar_wait(ready, ph); bulk_s2g(tile(sav_h(l), 4), hreg, 4 * kBlk); finish(); }   // h0 .. h7
-                mbar_wait(ready, ph); bulk_s2g(tile(kSavGL, 4), hreg, 4 * kBlk); bulk_s2g(tile(kSavDE, 1), aux, kBlk); finish();   // g, dir-enc
-                mbar_wait(ready, ph); bulk_s2g(tile(kSavHD, 2), hreg, 2 * kBlk); finish();                  // h_d
+                for (int l = 0; l < 8; ++l) { mbar_wait(ready, ph); spill_tile(tile(sav_h(l), 4), hreg, 4); finish(); }   // h0 .. h7
+                mbar_wait(ready, ph); spill_tile(tile(kSavGL, 4), hreg, 4); bulk_s2g(tile(kSavDE, 1), aux, kBlk); finish();   // g, dir-enc
+                mbar_wait(ready, ph); spill_tile(tile(kSavHD, 2), hreg, 2); finish();                  // h_d
             }
             bulk_wait_all();
         }
@@ -558,9 +558,9 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 auto tile = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
                 auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
-                mbar_wait(ready, ph); bulk_s2g(tile(kFsAUX, 1), aux, kBlk); bulk_s2g(tile(fs_h(0), 4), hreg, 4 * kBlk); finish();    // aux, h0
-                for (int l = 1; l < 8; ++l) { mbar_wait(ready, ph); bulk_s2g(tile(fs_h(l), 4), hreg, 4 * kBlk); finish(); }             // h1 .. h7
-                mbar_wait(ready, ph); bulk_s2g(tile(kFsHC, 4), hreg, 4 * kBlk); finish();                                                // hidden_layer_rgb output
+                mbar_wait(ready, ph); bulk_s2g(tile(kFsAUX, 1), aux, kBlk); spill_tile(tile(fs_h(0), 4), hreg, 4); finish();    // aux, h0
+                for (int l = 1; l < 8; ++l) { mbar_wait(ready, ph); spill_tile(tile(fs_h(l), 4), hreg, 4); finish(); }             // h1 .. h7
+                mbar_wait(ready, ph); spill_tile(tile(kFsHC, 4), hreg, 4); finish();                                                // hidden_layer_rgb output
             }
             bulk_wait_all();
         }

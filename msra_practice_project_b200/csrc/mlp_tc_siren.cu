@@ -176,10 +176,10 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 auto tile = [&](int off, int nb) -> uint8_t* { return saved + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
                 auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
-                mbar_wait(ready, ph); bulk_s2g(tile(kSsAUX, 1), aux, kBlk); bulk_s2g(tile(ss_h(0), 4), hreg, 4 * kBlk); finish();    // aux, h0
-                for (int l = 1; l < 8; ++l) { mbar_wait(ready, ph); bulk_s2g(tile(ss_h(l), 4), hreg, 4 * kBlk); finish(); }             // h1 .. h7
-                mbar_wait(ready, ph); bulk_s2g(tile(kSsGL, 4), hreg, 4 * kBlk); finish();                                                // layers_dir.0 output
-                mbar_wait(ready, ph); bulk_s2g(tile(kSsHD, 2), hreg, 2 * kBlk); finish();                                                // h_d
+                mbar_wait(ready, ph); bulk_s2g(tile(kSsAUX, 1), aux, kBlk); spill_tile(tile(ss_h(0), 4), hreg, 4); finish();    // aux, h0
+                for (int l = 1; l < 8; ++l) { mbar_wait(ready, ph); spill_tile(tile(ss_h(l), 4), hreg, 4); finish(); }             // h1 .. h7
+                mbar_wait(ready, ph); spill_tile(tile(kSsGL, 4), hreg, 4); finish();                                                // layers_dir.0 output
+                mbar_wait(ready, ph); spill_tile(tile(kSsHD, 2), hreg, 2); finish();                                                // h_d
             }
             bulk_wait_all();
         }

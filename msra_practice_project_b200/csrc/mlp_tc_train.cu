@@ -174,9 +174,9 @@ nerf_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 auto tile = [&](int off, int nb) -> uint8_t* { return scratch + ((size_t)off * n_sub + T * (size_t)nb) * kBlk; };
                 auto finish = [&]() { bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u; };
-                mbar_wait(ready, ph); bulk_s2g(tile(kScrGD1, 2), hreg, 2 * kBlk); finish();                 // d pre(layers_dir.1)
-                mbar_wait(ready, ph); bulk_s2g(tile(kScrGG, 4), hreg, 4 * kBlk); finish();                  // d g
-                for (int l = 7; l >= 0; --l) { mbar_wait(ready, ph); bulk_s2g(tile(scr_gh(l), 4), hreg, 4 * kBlk); finish(); }
+                mbar_wait(ready, ph); spill_tile(tile(kScrGD1, 2), hreg, 2); finish();                 // d pre(layers_dir.1)
+                mbar_wait(ready, ph); spill_tile(tile(kScrGG, 4), hreg, 4); finish();                  // d g
+                for (int l = 7; l >= 0; --l) { mbar_wait(ready, ph); spill_tile(tile(scr_gh(l), 4), hreg, 4); finish(); }
             }
             bulk_wait_all();
         }
@@ -746,7 +746,7 @@ film_tc_bwd_kernel(const uint8_t* __restrict__ packed, long long rows, const flo
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 for (int l = 8; l >= 0; --l) {
                     mbar_wait(ready, ph);
-                    bulk_s2g(scratch + ((size_t)fscr_g(l) * n_sub + T * 4) * kBlk, hreg, 4 * kBlk);
+                    spill_tile(scratch + ((size_t)fscr_g(l) * n_sub + T * 4) * kBlk, hreg, 4);
                     bulk_commit(); bulk_wait_read(); mbar_arrive(done); ph ^= 1u;
                 }
             }

@@ -184,6 +184,19 @@ __device__ __forceinline__ uint4 ldg128(const uint8_t* p) {
     return v;
 }
 
+// Tile copy shared -> global of the training kernels' spill threads: n_blk blocks of 16 KB as PACED 16 KB bulk copies, two in flight.
+// The SM's bulk-copy engine serves one operation at a time (tools/native/wstream_probe.cu, tma_mix_probe.cu): a single 64 KB copy
+// holds it for ~2,000 clk, during which the weight chunks of the running MMAs (one 16 KB copy per 512 clk) queue behind it.  With
+// 16 KB pieces they interleave: training forward of the fine pass 1.08 -> 1.02 ms (8 KB pieces: 1.04 ms, more engine time per byte).
+// The caller still ends the tile with bulk_commit() + bulk_wait_read().
+__device__ __forceinline__ void spill_tile(uint8_t* dst, uint32_t src_smem, int n_blk) {
+    for (int q = 0; q < n_blk; ++q) {
+        bulk_s2g(dst + (size_t)q * kBlk, src_smem + (uint32_t)q * kBlk, kBlk);
+        bulk_commit();
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+}
+
 // ---- shared-memory map (offsets from the 1024-aligned base; identical in both CTAs of a pair) -------------------
 constexpr uint32_t kTabOff = kRingOff + kStages * kStageBytes;          // fp32 tables (NeRF bias / head weights)
 constexpr uint32_t kTabBytes = kNerfTabFloats * 4;                      // 12,816
