@@ -642,8 +642,9 @@ def run_secondary(args, config=None, embedded=False):
                                     achieved=rows / world * bytes_row / (ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
                                     frac=rows / world * bytes_row / (ms * 1e-3) / 1e9 / pk["hbm"], peak_source=pk["src"],
                                     bytes_per_row=bytes_row, traffic=None,
-                                    note="per-kernel DRAM traffic and times: profiles/r1_train_{fwd,bwd,wgrad}_ncu.txt (forward / dgrad at the "
-                                         "3.93 TB/s write-only ceiling, wgrad at 0.83 of the copy peak)")
+                                    note="per-kernel DRAM traffic and times: profiles/r2_train_{fwd,bwd,wgrad}_ncu.txt (wgrad reads 8.35 GB in 1.21 ms = "
+                                         "at the copy peak; forward / dgrad write 4.3 / 3.8 GB at 4.2 / 3.9 TB/s: bound by the SM-side copy engine "
+                                         "shared between the weight ring and the tile copies, profiles/r2_role_timers.txt, not by HBM)")
     elif config == "siren":
         # SirenNeRF (use_siren, nerf/train_nerf.py:89-91): the 800x800, 64+128 render with the fused SIREN kernel
         w = h = 800

@@ -393,23 +393,26 @@ class GeneratorStep:
         """warm up on a side stream (this also fills the host-made linspace caches, so the capture sees no host-to-device copy), capture
         forward | backward | optimiser, and restore what the warm-up steps changed (weights, moments, step count)."""
         keep = [t.clone() for t in (self.params, self.exp_avg, self.exp_avg_sq, self.state)]
-        s = torch.cuda.Stream(device=self.dev)
-        s.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(s):
-            for _ in range(2):
+        # anomaly mode (the reference switches it on globally when nerf/nerf.py is imported, line 2) checks every backward result for NaNs
+        # on the host, which invalidates a stream capture: the captured passes run with it off
+        with torch.autograd.set_detect_anomaly(False):
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._fwd()
+                    self.d_images.fill_(1e-3)
+                    self._bwd()
+                    self._opt()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            self.d_images = torch.zeros_like(self.images)     # allocated OUTSIDE the graphs' pool: the caller's gradient is copied into it
+            with torch.cuda.graph(g1):
                 self._fwd()
-                self.d_images.fill_(1e-3)
+            with torch.cuda.graph(g2, pool=g1.pool()):
                 self._bwd()
+            with torch.cuda.graph(g3, pool=g1.pool()):
                 self._opt()
-        torch.cuda.current_stream(self.dev).wait_stream(s)
-        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        self.d_images = torch.zeros_like(self.images)         # allocated OUTSIDE the graphs' pool: the caller's gradient is copied into it
-        with torch.cuda.graph(g1):
-            self._fwd()
-        with torch.cuda.graph(g2, pool=g1.pool()):
-            self._bwd()
-        with torch.cuda.graph(g3, pool=g1.pool()):
-            self._opt()
         for t, k in zip((self.params, self.exp_avg, self.exp_avg_sq, self.state), keep):
             t.copy_(k)
         self._graphs = (g1, g2, g3)

@@ -109,6 +109,7 @@ def test_generator_step_drawn_jitter_and_poses_change_between_replays():
     gen = _make(seed=1)
     keys = set(gen.state_dict().keys())
     step = GeneratorStep(gen, 2)
+    torch.autograd.set_detect_anomaly(True)                 # what importing the reference's nerf/nerf.py leaves behind (line 2)
     z = torch.randn(2, 256, device="cuda")
     np.random.seed(0)
     a = step.forward(z).clone()
@@ -120,4 +121,5 @@ def test_generator_step_drawn_jitter_and_poses_change_between_replays():
     c = step.forward(z, pose_fixed).clone()
     d = step.forward(z, pose_fixed).clone()
     assert float((c - d).abs().max()) > 1e-6                 # same z, same poses, no update in between: only the jitter differs
+    torch.autograd.set_detect_anomaly(False)
     assert set(gen.state_dict().keys()) == keys and step.global_step == 1
