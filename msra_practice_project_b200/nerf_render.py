@@ -167,20 +167,20 @@ _host_stage: dict = {}      # (device index, rays) -> pinned [rays,5] staging bu
 
 def maps_to_numpy(packed: torch.Tensor, h: int, w: int):
     """The frame's fine (rgb, depth, acc) rows [H*W,5] on the device -> the three numpy images the reference returns
-    (nerf/render.py:161-166).  ONE device-to-host copy through a cached page-locked buffer (12.8 MB for an 800x800 frame: three
-    pageable ``.cpu()`` copies of strided views cost several ms more), then the maps are copied out so the caller owns them."""
-    key = (packed.device.index, int(packed.shape[0]))
+    (nerf/render.py:161-166).  The rows are de-interleaved on the device, cross PCIe as ONE copy into a cached page-locked buffer
+    (12.8 MB for an 800x800 frame) and leave it as three contiguous arrays that the caller owns."""
+    n = int(packed.shape[0])
+    key = (packed.device.index, n)
     stage = _host_stage.get(key)
     if stage is None:
         if len(_host_stage) >= 8:
             _host_stage.clear()
-        stage = torch.empty((int(packed.shape[0]), 5), dtype=torch.float32, device="cpu", pin_memory=True)
+        stage = torch.empty((n * 5,), dtype=torch.float32, device="cpu", pin_memory=True)
         _host_stage[key] = stage
-    stage.copy_(packed, non_blocking=True)
+    stage.copy_(torch.cat([packed[:, :3].reshape(-1), packed[:, 3], packed[:, 4]]), non_blocking=True)
     torch.cuda.current_stream(packed.device).synchronize()
     a = stage.numpy()
-    return (np.ascontiguousarray(a[:, :3]).reshape(h, w, 3), np.ascontiguousarray(a[:, 3]).reshape(h, w, 1),
-            np.ascontiguousarray(a[:, 4]).reshape(h, w, 1))
+    return a[:3 * n].copy().reshape(h, w, 3), a[3 * n:4 * n].copy().reshape(h, w, 1), a[4 * n:].copy().reshape(h, w, 1)
 
 
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
