@@ -215,3 +215,48 @@ def test_end_to_end_800_damped_field_bf16_vs_fp32():
     print(f"  800x800 damped field, bf16 (default) vs fp32: max-abs rgb {float(err.max()):.4g}, rays > 2e-2: {int((err > 2e-2).sum())} / 640000, "
           f"PSNR {ps:.1f} dB;  sign check off: rays > 2e-2: {int((err0 > 2e-2).sum())}, PSNR {orc.psnr(a[3].cpu().numpy(), b0[3].cpu().numpy()):.1f} dB")
     assert int((err > 2e-2).sum()) == 0 and ps >= 60
+
+
+def test_full_size_training_step_gradients_bf16_vs_fp32():
+    """BASELINE.json configs[2] at full size: ONE 4096-ray training step (64 + 128 samples: 1,048,576 MLP rows, the loss of
+    nerf/train_nerf.py:157-166 on the damped field) through the fused bf16 tensor-core path and through the exact fp32 layer-wise path, same
+    rays / jitter / targets: loss, and EVERY gradient tensor of both models (direction cosine, norm ratio).  Unlike the adversarial zero-mean
+    upstream of test_bf16_tensor_core_training_path (cosine >= 0.95), this is the gradient a training step actually uses; the bounds are the
+    measured values with margin (printed)."""
+    torch.manual_seed(0)
+    c, f = models.damp_nerf_(models.NeRF()).cuda(), models.damp_nerf_(models.NeRF()).cuda()
+    n, sc, sf = 4096, 64, 128
+    g = torch.Generator().manual_seed(3)
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.3, -0.5)
+    rays = ops.raygen(64, 64, 64 * 1.3875, pose)
+    t = torch.rand(n, sc, generator=g).cuda()
+    target = torch.rand(n, 3, generator=g).cuda()
+    res = {}
+    for mode in ("fp32", "bf16"):
+        old = ops.set_grad_precision(mode)
+        try:
+            for m in (c, f):
+                m.zero_grad(set_to_none=True)
+            rc, _, _, rf, _, _ = nerf_render.render_rays(rays, 2.0, 6.0, c, f, sc, sf, t_rand=t)
+            loss = torch.mean((rc - target) ** 2) + torch.mean((rf - target) ** 2)          # train_nerf.py:157-166 (use_alpha off)
+            loss.backward()
+        finally:
+            ops.set_grad_precision(old)
+        res[mode] = (float(loss.detach()), {("c." if m is c else "f.") + k: p.grad.detach().clone() for m in (c, f) for k, p in m.named_parameters()})
+        del rc, rf, loss
+    l32, l16 = res["fp32"][0], res["bf16"][0]
+    assert abs(l16 - l32) < 4e-3 * max(l32, 1e-6), (l16, l32)              # measured 1.0e-3
+    worst_cos, worst_norm, allf, allb = 1.0, 0.0, [], []
+    for k, gf in res["fp32"][1].items():
+        gb = res["bf16"][1][k]
+        gf, gb = gf.reshape(-1).double(), gb.reshape(-1).double()
+        cos = float(torch.dot(gf, gb) / (gf.norm() * gb.norm()).clamp_min(1e-300))
+        ratio = float(gb.norm() / gf.norm().clamp_min(1e-300))
+        worst_cos, worst_norm = min(worst_cos, cos), max(worst_norm, abs(ratio - 1))
+        allf.append(gf); allb.append(gb)
+        assert cos > 0.995 and abs(ratio - 1) < 0.05, (k, cos, ratio)          # measured: worst cosine 0.99845, worst norm deviation 0.0285
+    gf, gb = torch.cat(allf), torch.cat(allb)
+    cos_all = float(torch.dot(gf, gb) / (gf.norm() * gb.norm()))
+    assert cos_all > 0.999, cos_all                                            # measured 0.99978
+    print("full-size training step, bf16 fused path vs fp32: loss %.6f vs %.6f, whole-gradient cosine %.6f, worst per-tensor cosine %.5f, "
+          "worst norm deviation %.4f over %d tensors" % (l16, l32, cos_all, worst_cos, worst_norm, len(allf)))
