@@ -18,15 +18,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 // out_stats[cta]: {load cycles, load latency sum, loads, store cycles, stores}
 __global__ void __launch_bounds__(128, 1) k_mix(const uint8_t* __restrict__ wbuf, uint32_t w_chunks, uint8_t* __restrict__ out, size_t out_chunks,
-                                                int n_loads, int n_stores, uint32_t store_bytes, long long* __restrict__ stats, int pieces, int depth, int lsu_stores) {
+                                                int n_loads, int n_stores, uint32_t store_bytes, long long* __restrict__ stats, int pieces, int depth, int lsu_stores, int ldgsts_loads) {
     extern __shared__ __align__(1024) uint8_t sm[];
     __shared__ __align__(8) unsigned long long bars[8];
     const uint32_t ring = smem_u32(sm), stile = ring + 3 * 16384;
-    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), ldgsts_loads ? 32 : 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     for (uint32_t i = threadIdx.x; i < 2 * 65536 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sm + 3 * 16384)[i] = make_uint4(i, 2u, 3u, 4u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0 && n_loads > 0) {
+    if (ldgsts_loads && threadIdx.x < 32 && n_loads > 0) {
+        // the weight ring fed by LDGSTS (cp.async 16 B per lane, completion through cp.async.mbarrier.arrive.noinc): does not use the bulk-copy engine
+        const int lane = threadIdx.x;
+        long long issue_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lat = 0;
+        const long long t0 = clock64();
+        uint32_t ph = 0;
+        for (int i = 0; i < n_loads + depth; ++i) {
+            const int s = i % depth;
+            if (i >= depth) { mbar_wait(smem_u32(&bars[s]), ph); lat += clock64() - issue_t[s]; if (s == depth - 1) ph ^= 1u; }
+            if (i < n_loads) {
+                const uint8_t* src = wbuf + (size_t)((i * 7 + blockIdx.x) % w_chunks) * 16384 + lane * 16;
+                const uint32_t dst = ring + s * 16384 + lane * 16;
+                issue_t[s] = clock64();
+#pragma unroll 8
+                for (uint32_t o = 0; o < 16384; o += 512) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[s])) : "memory");
+            }
+        }
+        if (lane == 0) { stats[blockIdx.x * 8 + 0] = clock64() - t0; stats[blockIdx.x * 8 + 1] = lat; stats[blockIdx.x * 8 + 2] = n_loads; }
+    }
+    if (!ldgsts_loads && threadIdx.x == 0 && n_loads > 0) {
         long long issue_t[8] = {0, 0, 0, 0, 0, 0, 0, 0}, lat = 0;
         const long long t0 = clock64();
         uint32_t ph = 0;
@@ -80,10 +100,10 @@ int main() {
     const int smem = 3 * 16384 + 2 * 65536 + 1024;
     cudaFuncSetAttribute(k_mix, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     long long h[148 * 8];
-    auto run = [&](const char* name, int grid, int n_loads, int n_stores, uint32_t store_bytes, int pieces = 1, int depth = 3, int lsu = 0) {
+    auto run = [&](const char* name, int grid, int n_loads, int n_stores, uint32_t store_bytes, int pieces = 1, int depth = 3, int lsu = 0, int ldg = 0) {
         for (int rep = 0; rep < 2; ++rep) {
             cudaMemset(stats, 0, 148 * 8 * sizeof(long long));
-            k_mix<<<grid, 128, smem>>>(wbuf, w_chunks, out, out_chunks, n_loads * depth / 3, n_stores, store_bytes, stats, pieces, depth, lsu);
+            k_mix<<<grid, 128, smem>>>(wbuf, w_chunks, out, out_chunks, n_loads * depth / 3, n_stores, store_bytes, stats, pieces, depth, lsu, ldg);
             cudaDeviceSynchronize();
         }
         cudaMemcpy(h, stats, sizeof h, cudaMemcpyDeviceToHost);
@@ -96,12 +116,11 @@ int main() {
                cudaGetErrorString(cudaGetLastError()));
     };
     for (int grid : {1, 148}) {
-        run("loads only (16 KB x 3 in flight)", grid, 4000, 0, 65536);
-        run("TMA stores only (64 KB, 2 in flight)", grid, 0, 1000, 65536);
-        run("LSU stores only (2 warps, 64 KB tiles)", grid, 0, 1000, 65536, 1, 3, 1);
-        run("loads + TMA 64 KB stores", grid, 4000, 1000, 65536);
-        run("loads + TMA 16 KB stores", grid, 4000, 4000, 16384);
-        run("loads + LSU stores (2 warps)", grid, 4000, 1000, 65536, 1, 3, 1);
+        run("TMA loads only (16 KB x 3 in flight)", grid, 4000, 0, 65536);
+        run("LDGSTS loads only (1 warp, 16 KB x 3)", grid, 4000, 0, 65536, 1, 3, 0, 1);
+        run("TMA loads + TMA 16 KB stores", grid, 4000, 4000, 16384);
+        run("LDGSTS loads + TMA 16 KB stores", grid, 4000, 4000, 16384, 1, 3, 0, 1);
+        run("LDGSTS loads + TMA 64 KB stores", grid, 4000, 1000, 65536, 1, 3, 0, 1);
     }
     return 0;
 }
