@@ -123,3 +123,24 @@ def test_generator_step_drawn_jitter_and_poses_change_between_replays():
     assert float((c - d).abs().max()) > 1e-6                 # same z, same poses, no update in between: only the jitter differs
     torch.autograd.set_detect_anomaly(False)
     assert set(gen.state_dict().keys()) == keys and step.global_step == 1
+
+
+def test_generator_step_recaptures_on_resolution_change():
+    """Progressive growing (pi_GAN/train.py:150-160 calls generator.set_resolution between stages): the captured graphs are keyed by
+    the renderer's settings, so a new resolution re-captures and keeps training the same flat parameter buffer."""
+    gen = _make(seed=2, res=16, s=8)
+    step = GeneratorStep(gen, 2, learning_rate=1e-4)
+    z = torch.randn(2, 256, device="cuda")
+    a = step.forward(z)
+    assert tuple(a.shape) == (2, 3, 16, 16)
+    step.backward(torch.full_like(a, 1e-3))
+    before = step.params.clone()
+    gen.set_resolution(32)                                   # focal follows the width (modules.py:141)
+    b = step.forward(z)
+    assert tuple(b.shape) == (2, 3, 32, 32) and torch.isfinite(b).all()
+    step.backward(torch.full_like(b, 1e-3))
+    assert step.global_step == 2 and float((step.params - before).abs().max()) > 0
+    with pytest.raises(ValueError):
+        step.backward(torch.zeros(2, 3, 16, 16, device="cuda"))
+    with pytest.raises(ValueError):
+        step.forward(torch.randn(3, 256, device="cuda"))
