@@ -1314,6 +1314,64 @@ def test_sample_pdf_specialised_kernels_bit_identical_to_generic(shape):
     assert np.array_equal(a[0][sub].cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("shape", [(70001, 63, 128, 64), (9000, 63, 64, 64), (20011, 23, 24, 24)])
+@pytest.mark.parametrize("u_kind", ["linspace", "random", "negative"])
+def test_sample_pdf_rank_kernel_on_render_rays_inputs(shape, u_kind):
+    """The inputs render_rays really passes (nerf/render.py:126-142): bins = mid-points of the coarse strata, shared by all rays,
+    z_coarse = jittered stratified samples (a few jitters exactly 0 or 1-ulp-below-1: coarse samples ON a stratum boundary, where
+    the rank kernel's b + 1 / b + 2 guess is wrong and the ray is redone exactly), weights peaked / zero / flat.  b2r_sample_pdf
+    (rank kernel: guess + verification, exact redo otherwise) must be bit-identical to b2r_sample_pdf_generic in samples, merged
+    rows and CDF, for the reference's linspace u, for a sorted random u (perturbed sampling) and for a u that starts below zero
+    (searchsorted index 0: the whole launch takes the exact path)."""
+    from msra_practice_project_b200._lib import lib, check
+    n, nb, sf, sc = shape
+    g = torch.Generator().manual_seed(nb * 77 + sf)
+    z_lin = torch.linspace(2.0, 6.0, sc)
+    mids = 0.5 * (z_lin[1:] + z_lin[:-1])
+    upper, lower = torch.cat([mids, z_lin[-1:]]), torch.cat([z_lin[:1], mids])
+    t = torch.rand(n, sc, generator=g)
+    t[::5, ::3] = 0.0                                                     # coarse sample exactly on the lower stratum boundary
+    t[3::7, 1::4] = 1.0                                                   # ... on the upper one (ties with the next bin edge)
+    zc = (lower + (upper - lower) * t).cuda().contiguous()
+    w_full = torch.rand(n, sc, generator=g) ** 8
+    w_full[::7] = 0.0
+    w_full[1::11, : sc // 2] = 0.0
+    w_full[2::13] = 1.0
+    w_full[4::17, 5] = 50.0                                               # one dominant bin: most samples in one stratum
+    w_full = w_full.cuda()
+    w = w_full[:, 1:-1]
+    bins = mids.cuda()
+    if u_kind == "linspace":
+        u = torch.linspace(0.0, 1.0, sf)
+    elif u_kind == "random":
+        u = torch.sort(torch.rand(sf, generator=g)).values
+    else:
+        u = torch.linspace(-0.05, 0.9, sf)
+    u = u.cuda()
+    outs = {}
+    for name in ("b2r_sample_pdf", "b2r_sample_pdf_generic"):
+        samples = torch.full((n, sf), -1.0, device="cuda")
+        merged = torch.full((n, sc + sf), -1.0, device="cuda")
+        cdf = torch.full((n, nb), -1.0, device="cuda")
+        fn = getattr(lib(), name)
+        check(fn(bins.data_ptr(), 0, w.data_ptr(), w.stride(0), u.data_ptr(), n, nb, sf, zc.data_ptr(), sc, samples.data_ptr(),
+                 merged.data_ptr(), cdf.data_ptr(), torch.cuda.current_stream().cuda_stream), name)
+        merged2 = torch.full((n, sc + sf), -1.0, device="cuda")
+        check(fn(bins.data_ptr(), 0, w.data_ptr(), w.stride(0), u.data_ptr(), n, nb, sf, zc.data_ptr(), sc, None, merged2.data_ptr(), None,
+                 torch.cuda.current_stream().cuda_stream), name)
+        torch.cuda.synchronize()
+        assert torch.equal(merged, merged2), name
+        outs[name] = (samples, merged, cdf)
+    a, b = outs["b2r_sample_pdf"], outs["b2r_sample_pdf_generic"]
+    assert torch.equal(a[2], b[2]), "cdf"
+    assert torch.equal(a[0], b[0]), "samples"
+    assert torch.equal(a[1], b[1]), "merged"
+    assert torch.equal(a[1], torch.sort(torch.cat([zc, a[0]], -1), -1).values)
+    sub = slice(0, 512)
+    ref, _ = orc.sample_pdf_from_cdf(bins.cpu().numpy(), a[2][sub].cpu().numpy(), u.cpu().numpy())
+    assert np.array_equal(a[0][sub].cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_generator_forward_backward_vs_reference(golden, mode):
     """models.Generator.forward (pi_GAN/modules.py:176-184 + train.py:134) against the unmodified reference's Generator on the
