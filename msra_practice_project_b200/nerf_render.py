@@ -162,25 +162,56 @@ def render_image_device(width, height, focal, pose, near, far, coarse_model, fin
     return tuple(torch.cat([o[i] for o in outs]) for i in range(6))
 
 
-_host_stage: dict = {}      # (device index, rays) -> pinned [rays,5] staging buffer of the image read-back
+_host_stage: dict = {}      # (device index, rays) -> [(pinned [rays*5] staging buffer, its idle storage use count), ...]
+_STAGE_POOL = 4             # staging buffers per frame size: frames the caller may hold at once without a host copy
+
+
+def _storage_uses(buf: torch.Tensor):
+    """Owners of the buffer's storage (the pool's tensor + every live numpy view chain made from it), or None if this torch
+    build cannot tell."""
+    f = getattr(torch._C, "_storage_Use_Count", None)
+    return None if f is None else int(f(buf.untyped_storage()._cdata))
 
 
 def maps_to_numpy(packed: torch.Tensor, h: int, w: int):
     """The frame's fine (rgb, depth, acc) rows [H*W,5] on the device -> the three numpy images the reference returns
-    (nerf/render.py:161-166).  The rows are de-interleaved on the device, cross PCIe as ONE copy into a cached page-locked buffer
-    (12.8 MB for an 800x800 frame) and leave it as three contiguous arrays that the caller owns."""
+    (nerf/render.py:161-166).  The rows are de-interleaved on the device and cross PCIe as ONE copy into a page-locked buffer
+    (12.8 MB for an 800x800 frame); the three images are VIEWS of that buffer -- no host-side copy (three fresh 2.5-7.7 MB
+    arrays cost 1.3-4.6 ms per frame in page faults, and far more on a busy host).  The caller owns them like any array: a
+    buffer goes back to the pool only when the last view of it is gone (storage use count), up to _STAGE_POOL frames of a size can
+    be held at once, and beyond that -- or when the use count is not available -- the images are fresh pageable arrays."""
     n = int(packed.shape[0])
     key = (packed.device.index, n)
-    stage = _host_stage.get(key)
-    if stage is None:
+    flat = torch.cat([packed[:, :3].reshape(-1), packed[:, 3], packed[:, 4]])
+    pool = _host_stage.get(key)
+    if pool is None:
         if len(_host_stage) >= 8:
             _host_stage.clear()
+        pool = _host_stage[key] = []
+    stage = None
+    for buf, idle in pool:
+        if idle is not None and _storage_uses(buf) == idle:
+            stage = buf
+            break
+    if stage is None and len(pool) < _STAGE_POOL:
         stage = torch.empty((n * 5,), dtype=torch.float32, device="cpu", pin_memory=True)
-        _host_stage[key] = stage
-    stage.copy_(torch.cat([packed[:, :3].reshape(-1), packed[:, 3], packed[:, 4]]), non_blocking=True)
-    torch.cuda.current_stream(packed.device).synchronize()
-    a = stage.numpy()
-    return a[:3 * n].copy().reshape(h, w, 3), a[3 * n:4 * n].copy().reshape(h, w, 1), a[4 * n:].copy().reshape(h, w, 1)
+        pool.append((stage, _storage_uses(stage)))
+        if pool[-1][1] is None:                # cannot track the views: hand out copies of this one buffer
+            stage = None
+    if stage is None:
+        idle0 = pool[0][1]
+        if idle0 is None:                      # untracked single buffer: pinned copy + host copies
+            buf = pool[0][0]
+            buf.copy_(flat, non_blocking=True)
+            torch.cuda.current_stream(packed.device).synchronize()
+            a = buf.numpy().copy()
+        else:                                  # every pooled buffer is still held by the caller
+            a = flat.cpu().numpy()
+    else:
+        stage.copy_(flat, non_blocking=True)
+        torch.cuda.current_stream(packed.device).synchronize()
+        a = stage.numpy()
+    return a[:3 * n].reshape(h, w, 3), a[3 * n:4 * n].reshape(h, w, 1), a[4 * n:].reshape(h, w, 1)
 
 
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
@@ -198,12 +229,18 @@ def render_image(width, height, focal, pose, near, far, coarse_model, fine_model
 def render_video(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
                  chunk=1024 * 16, *, precision=None, exact_last_sample=None):
     """nerf/render.py:170-182 -- stacked per-pose render_image outputs."""
-    rgb_video, depth_video, acc_video = [], [], []
-    for _, p in enumerate(tqdm(poses)):
+    poses = list(poses)
+    h, w = int(height), int(width)
+    # every frame is copied into the stacked result as it arrives (np.stack's copy, done early): the frame's staging buffer is free
+    # again for the next pose
+    rgb_video = np.empty((len(poses), h, w, 3), np.float32)
+    depth_video, acc_video = np.empty((len(poses), h, w, 1), np.float32), np.empty((len(poses), h, w, 1), np.float32)
+    for i, p in enumerate(tqdm(poses)):
         rgb, depth, acc = render_image(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
                                        fine_sample_num, chunk, precision=precision, exact_last_sample=exact_last_sample)
-        rgb_video.append(rgb); depth_video.append(depth); acc_video.append(acc)
-    return np.stack(rgb_video), np.stack(depth_video), np.stack(acc_video)
+        rgb_video[i], depth_video[i], acc_video[i] = rgb, depth, acc
+        del rgb, depth, acc
+    return rgb_video, depth_video, acc_video
 
 
 def render_video_u8(width, height, focal, poses, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,

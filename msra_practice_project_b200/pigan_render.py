@@ -69,12 +69,16 @@ def render_video_np(width, height, focal, poses, near, far, coarse_model, fine_m
                     fine_sample_num, chunk=1024 * 16, *, precision=None, exact_last_sample=None):
     """pi_GAN/render.py:229-241.  The reference unpacks three values from render_image (which returns
     one tensor) and so raises as shipped; this calls render_image_np as evidently meant."""
-    rgb_video, depth_video, acc_video = [], [], []
-    for _, p in enumerate(tqdm(poses)):
+    poses = list(poses)
+    h, w = int(height), int(width)
+    rgb_video = np.empty((len(poses), h, w, 3), np.float32)       # frames copied in as they arrive: their staging buffers are reused
+    depth_video, acc_video = np.empty((len(poses), h, w, 1), np.float32), np.empty((len(poses), h, w, 1), np.float32)
+    for i, p in enumerate(tqdm(poses)):
         rgb, depth, acc = render_image_np(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
                                           fine_sample_num, chunk, precision=precision, exact_last_sample=exact_last_sample)
-        rgb_video.append(rgb); depth_video.append(depth); acc_video.append(acc)
-    return np.stack(rgb_video), np.stack(depth_video), np.stack(acc_video)
+        rgb_video[i], depth_video[i], acc_video[i] = rgb, depth, acc
+        del rgb, depth, acc
+    return rgb_video, depth_video, acc_video
 
 
 def render_batch(model, film_params, poses, width, height, focal, near, far, coarse_sample_num, fine_sample_num, *,

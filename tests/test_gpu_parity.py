@@ -637,6 +637,40 @@ def test_drop_in_usage_like_the_reference_scripts():
         torch.set_default_device("cpu")
 
 
+def test_render_image_frames_are_owned_by_the_caller():
+    """render_image hands out views of pooled page-locked buffers (no host copy).  A frame the caller still holds must never be
+    overwritten by later renders -- also beyond the pool size, where the images become fresh pageable arrays -- and a buffer must go
+    back to the pool once its frame is dropped."""
+    from msra_practice_project_b200 import nerf_render
+    torch.manual_seed(0)
+    coarse, fine = models.NeRF().cuda(), models.NeRF().cuda()
+    poses = [pigan_render.camera_pos_to_transform_matrix(4.0, 0.1 * i, -0.5) for i in range(7)]
+    t_rand = torch.rand(24 * 20, 16, device="cuda")
+    held, copies = [], []
+    for p in poses:                                                            # 7 frames held at once (pool: 4)
+        f = nerf_render.render_image(24, 20, 24 * 1.3875, p, 2.0, 6.0, coarse, fine, 16, 16, t_rand=t_rand)
+        assert f[0].shape == (20, 24, 3) and f[1].shape == (20, 24, 1) and f[0].dtype == np.float32
+        held.append(f)
+        copies.append(tuple(a.copy() for a in f))
+    for f, c in zip(held, copies):
+        for a, b in zip(f, c):
+            assert np.array_equal(a, b)
+    assert not np.array_equal(copies[0][0], copies[1][0])                      # the poses do differ
+    pool = nerf_render._host_stage[(torch.cuda.current_device(), 24 * 20)]
+    assert len(pool) == nerf_render._STAGE_POOL
+    if pool[0][1] is not None:                                                 # use counts available: zero-copy hand-out and reuse
+        assert all(nerf_render._storage_uses(b) > idle for b, idle in pool)
+        first = held[0][0]
+        held.clear(); del f, a
+        assert sum(nerf_render._storage_uses(b) == idle for b, idle in pool) == nerf_render._STAGE_POOL - 1     # `first` keeps one
+        again = nerf_render.render_image(24, 20, 24 * 1.3875, poses[3], 2.0, 6.0, coarse, fine, 16, 16, t_rand=t_rand)
+        assert np.array_equal(first, copies[0][0]) and np.array_equal(again[0], copies[3][0])
+        assert len(pool) == nerf_render._STAGE_POOL
+        again[0][0, 0, 0] = 7.0                                                # writable like any array
+    vid = nerf_render.render_video(24, 20, 24 * 1.3875, poses[:3], 2.0, 6.0, coarse, fine, 16, 16)
+    assert vid[0].shape == (3, 20, 24, 3) and vid[1].shape == (3, 20, 24, 1)
+
+
 def test_tf32_layerwise_path_matches_fp32(golden):
     """The tensor-core (tcgen05 kind::tf32) layer-wise path: forward and every gradient against the fp32 CUDA-core path."""
     tr = golden.nerf_train
