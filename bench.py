@@ -376,6 +376,29 @@ def run_b200(args):
                            passes_per_step=passes // args.steps, ms_per_step_check_off=off_ms, rays_per_s_check_off=n_rays / (off_ms * 1e-3),
                            cost_fraction=ms_per_step / off_ms - 1.0)
 
+    # ---- the same frame with the coarse pass stopped after the sigma head (opt-in `coarse_sigma_only`: render_image never returns the
+    # coarse colour, nerf/render.py:150-167).  NOT the headline -- the headline evaluates the whole network on every coarse sample as
+    # the reference does; this is reported as an additional secondary line, with the fine maps compared bit for bit.
+    dce = None
+    if args.precision == "bf16":
+        def step_dce():
+            with torch.no_grad():
+                return nerf_render.render_image_device(W, H, focal, pose, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin, ray_count=count,
+                                                       t_rand=t_rand, precision=args.precision, coarse_sigma_only=True)
+        full = step_device()
+        alt = step_dce()
+        same = all(bool(torch.equal(full[i], alt[i])) for i in (3, 4, 5))
+        del full, alt
+        step_dce()
+        dce_ms = timed(step_dce, args.steps) / args.steps
+        dce = dict(metric=METRIC + " (coarse pass sigma-only)", value=n_rays / (dce_ms * 1e-3), unit="rays/s", ms_per_step=dce_ms, dtype="bf16",
+                   scaling="strong", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, vs_baseline=None,
+                   data="synthetic", fine_maps_bit_identical_to_headline=same,
+                   config=dict(workload="the headline frame with render_image(coarse_sigma_only=True): the coarse pass stops after layers_pos.7 + "
+                                        "the sigma head (its colour is never returned; weights and every fine output are unchanged), "
+                                        "no gather; dead-code elimination, not the headline"))
+        assert same, "coarse_sigma_only changed the fine maps"
+
     # ---- N > 1: the gathered frame must equal what ONE GPU renders.  Rank 0 re-renders, alone, the two pixel rows either side of
     # every shard boundary (and the frame's first / last row) from the same global jitter and compares them bit for bit with the
     # rows the other ranks sent (the driver's GPU test box has one GPU, so the 2-GPU pytest never runs there).
@@ -522,7 +545,7 @@ def run_b200(args):
             base["gpu_eager_incumbent"] = {"error": repr(e)[:200]}
 
     # the other BASELINE.json configs (training step, pi-GAN batch, density grid, SirenNeRF frame), measured in the same job
-    secondary = []
+    secondary = [dce] if dce is not None else []
     if not args.no_secondary:
         for cfg in ("train", "pigan", "grid", "siren", "siren_train", "pigan_grad"):
             try:
@@ -749,6 +772,25 @@ def run_secondary(args, config=None, embedded=False):
                     ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
                     config=dict(workload="pi-GAN generator render, 64 latents sharded over ranks, all latents of a rank in one launch sequence (per-latent FiLM tables)"),
                     images_per_s=n_lat / (ms * 1e-3), tflops=rays * 72 * 1053696 / (ms * 1e-3) / 1e12)
+        if args.precision == "bf16":
+            # opt-in variant (not the number above): coarse pass stopped after the sigma head -- pi_GAN/render.py:195-206 returns the fine colour only
+            t_fix = torch.rand((c * res * res, s_), device=dev)
+            with torch.no_grad():
+                a = pigan_render.render_batch(net, film[b:b + c], poses[b:b + c], res, res, focal, 0.5, 1.5, s_, s_, t_rand=t_fix, precision=args.precision)
+                a2 = pigan_render.render_batch(net, film[b:b + c], poses[b:b + c], res, res, focal, 0.5, 1.5, s_, s_, t_rand=t_fix, precision=args.precision,
+                                               coarse_sigma_only=True)
+            same = bool(torch.equal(a, a2))
+            del a, a2, t_fix
+
+            def step_dce():
+                with torch.no_grad():
+                    imgs = pigan_render.render_batch(net, film[b:b + c], poses[b:b + c], res, res, focal, 0.5, 1.5, s_, s_, precision=args.precision,
+                                                     coarse_sigma_only=True)
+                    if world > 1:
+                        dist.all_gather_into_tensor(out_all, imgs.contiguous())
+            ms2 = timed(step_dce, args.steps, args.warmup)
+            line["coarse_sigma_only"] = dict(ms_per_step=ms2, value=rays / (ms2 * 1e-3), unit="rays/s", images_bit_identical=same,
+                                             note="opt-in dead-code elimination of the coarse pass's colour layer; not the number above")
     else:
         n = 256
         n3 = n ** 3

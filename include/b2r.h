@@ -194,7 +194,8 @@ size_t b2r_mlp_tc_packed_bytes(int model_kind);
 int b2r_mlp_tc_pack(int model_kind, const float* params, const float* film, int use_dir,
                     void* packed_out, void* stream);
 /* use_dir: the FilmSirenNeRF(use_dir=...) flag the weights were packed with (ignored for NeRF).
- * sigma_only != 0 (FiLM only): stop after the sigma head, raw_out[:, :3] = 0 (create_mesh density query). */
+ * sigma_only != 0 (NeRF, FiLM-SIREN): stop after the sigma head, raw_out[:, :3] = 0 (create_mesh density query; coarse passes whose
+ * colour nobody reads); sigma is bit-identical to the full evaluation's. */
 /* last: nullable; when given (rays or x mode), the kernel also lists the rays whose last sample needs the fp32 sign check. */
 int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, const b2r_mlp_input* in, float* raw_out,
                    int sigma_only, const b2r_last_sample* last, void* stream);

@@ -240,10 +240,15 @@ __device__ __forceinline__ void nerf_epi(uint32_t t_half, uint32_t bias_half, ui
 // The tiles are already in shared memory as the next layer's A operand: warps 2 / 3 (one thread each, sub-tile 0 / 1) copy them
 // out with the bulk-copy engine (64 KB per layer and sub-tile, full-line writes) while the next layer's MMAs run; the epilogue
 // warps wait for "tile has been read" (spill_done) before they overwrite it in place.
-template <bool kSave>
+// kSigmaOnly (inference): the walk stops after layers_pos.7 + the sigma head (steps 0..7); raw = (0, 0, 0, relu sigma).  For passes
+// whose colour nobody reads -- the coarse pass of render_image, which returns the fine maps only (nerf/render.py:150-167) and needs
+// the coarse weights, a function of sigma alone, for sample_pdf: sigma is bit-identical to the full walk's (same MMAs, same epilogue).
+template <bool kSave, bool kSigmaOnly = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved,
                LastFlag lf) {
+    static_assert(!(kSave && kSigmaOnly), "the training forward evaluates the whole network");
+    constexpr int kWalk = kSigmaOnly ? 8 : NerfSched::kSteps;
     extern __shared__ uint8_t smem_raw[];
     const Ctx cx = make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -259,10 +264,10 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     const uint32_t tmem_base = tc_prologue(cx, warp);
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<NerfSched>(cx, packed, pl, NerfSched::kSteps, 0);
+        if (lane == 0) producer_loop<NerfSched>(cx, packed, pl, kWalk, 0);
     } else if (warp == 1) {
-        if (cx.rank == 0) mma_loop<NerfSched>(cx, tmem_base, pl, NerfSched::kSteps, 0);
-        else if (lane == 0) relay_loop<NerfSched>(cx, pl, NerfSched::kSteps, 0);
+        if (cx.rank == 0) mma_loop<NerfSched>(cx, tmem_base, pl, kWalk, 0);
+        else if (lane == 0) relay_loop<NerfSched>(cx, pl, kWalk, 0);
     } else if (warp < kCtrlWarps) {
         if (kSave && lane == 0) {
             // ===== spill thread of sub-tile g: shared-memory tiles -> tiled tensors in global memory =====
@@ -367,11 +372,12 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 uint32_t mk[4] = {0u, 0u, 0u, 0u};
                 nerf_epi<1, kSave>(t_half, bias_half + 7u * 1024u, tab + (uint32_t)(kNerfTabWSigma + half * 128) * 4u, h_half, xoff, sigma, rgb0, rgb1, rgb2, mk,
                                    warp_checks, &asum);
-                arrive_act(act_local, act_leader, cx.rank, lane);
+                if (!kSigmaOnly) arrive_act(act_local, act_leader, cx.rank, lane);   // (sigma only: no MMA reads h7)
                 spill_sig();
                 put_mask(7, mk);
             }
             uint32_t mk[4] = {0u, 0u, 0u, 0u};
+            if (!kSigmaOnly) {
             wait_acc();                                                 // layers_dir.0 (linear) + view-direction encoding
             spill_wait();
             nerf_epi<2, kSave>(t_half, bias_half + 8u * 1024u, 0u, h_half, xoff, sigma, rgb0, rgb1, rgb2, mk);
@@ -398,6 +404,7 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             nerf_epi<3, kSave>(tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)half * 64u,
                                tab + (uint32_t)(kNerfTabBias + 9 * 256 + half * 64) * 4u, tab + (uint32_t)(kNerfTabWRgb + half * 64) * 4u,
                                h_base + row_off + (uint32_t)half * kBlk, xoff, sigma, rgb0, rgb1, rgb2, mk);
+            }
             if (kSave) {
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -419,6 +426,7 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     o.x = 1.0f / (1.0f + __expf(-(rgb0 + o2.x + bh.y)));
                     o.y = 1.0f / (1.0f + __expf(-(rgb1 + o2.y + bh.z)));
                     o.z = 1.0f / (1.0f + __expf(-(rgb2 + o2.z + bh.w)));
+                    if (kSigmaOnly) { o.x = 0.f; o.y = 0.f; o.z = 0.f; }
                     const float pre = sigma + o2.w + bh.x;
                     o.w = fmaxf(pre, 0.f);
                     raw_out[row] = o;
@@ -818,7 +826,7 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     long long rows = row_count(in);
     if (rows == 0) return 0;
     B2R_CHECK_ARG(model_kind == B2R_MODEL_NERF || model_kind == B2R_MODEL_FILM || model_kind == B2R_MODEL_SIREN, "b2r_mlp_tc_fwd: unknown model kind %d", model_kind);
-    B2R_CHECK_ARG(!(sigma_only && model_kind != B2R_MODEL_FILM), "b2r_mlp_tc_fwd: sigma_only is a FiLM-SIREN mode");
+    B2R_CHECK_ARG(!(sigma_only && model_kind == B2R_MODEL_SIREN), "b2r_mlp_tc_fwd: sigma_only is a NeRF / FiLM-SIREN mode");
     rc = tc::check_last_sample(last, in, "b2r_mlp_tc_fwd");
     if (rc) return rc;
     if (model_kind == B2R_MODEL_SIREN) return tc::siren_fwd(packed, in, rows, raw_out, last, (cudaStream_t)stream);
@@ -832,10 +840,10 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
         tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0, nullptr,
                                                                               tc::make_last_flag(last));
     } else {
-        rc = cuda_result(cudaFuncSetAttribute(tc::nerf_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+        auto kern = sigma_only ? tc::nerf_tc_kernel<false, true> : tc::nerf_tc_kernel<false, false>;
+        rc = cuda_result(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
         if (rc) return rc;
-        tc::nerf_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr,
-                                                                              tc::make_last_flag(last));
+        kern<<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr, tc::make_last_flag(last));
     }
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd");
     return 0;

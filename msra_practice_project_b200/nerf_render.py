@@ -66,7 +66,7 @@ def raw_to_outputs(raw, z_vals, rays_d):
 
 def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num, *,
                 t_rand=None, z_lin=None, u=None, precision=None, stages=None, coarse_no_grad=False,
-                exact_last_sample=None, fine_out=None, coarse_outputs_unused=False):
+                exact_last_sample=None, fine_out=None, coarse_outputs_unused=False, coarse_sigma_only=False):
     """nerf/render.py:106-147 -- coarse pass, sample_pdf on the un-jittered mids with
     weights[:,1:-1], sort-merge, fine pass on all Sc+Sf samples.  Returns the reference's 6-tuple
     (rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f).  ``coarse_no_grad`` runs the coarse pass in
@@ -80,6 +80,9 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     ``coarse_outputs_unused`` (the pi-GAN wrappers, which return only the fine colour): the COARSE pass skips the check --
     its last sample only reaches the coarse rgb / depth / acc maps (sample_pdf reads weights[:, 1:-1], nerf/render.py:140),
     so nothing the caller sees changes, and a training step keeps running without a host synchronisation.
+    ``coarse_sigma_only`` (opt-in, off by default; bf16 inference of NeRF / FiLM-SIREN models): the coarse pass stops after the sigma
+    head -- dead-code elimination for callers that return only the fine maps (render_image): the coarse weights, and with them every
+    fine output, are bit-identical (tested); the returned coarse rgb map is zero.  Needs a gradient-free coarse pass.
     Applies to passes that run without gradients (renders; the pi-GAN coarse pass).  Passes that carry
     gradients run the raw bf16 forward (mixed-precision training; d sigma_last is zero either way) unless
     ops.set_exact_last_sample(train=True) is set -- an explicit switch, not a silent skip."""
@@ -102,7 +105,10 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
 
     z_vals, mids = ops.stratified_z(z_lin, t_rand)
     with torch.set_grad_enabled(torch.is_grad_enabled() and not coarse_no_grad):
-        raw = _mlp_rays(coarse_model, rays, z_vals, precision, False if coarse_outputs_unused else exact_last_sample)
+        if coarse_sigma_only and torch.is_grad_enabled() and any(p.requires_grad for p in coarse_model.parameters()):
+            raise RuntimeError("coarse_sigma_only needs a gradient-free coarse pass (torch.no_grad() or coarse_no_grad=True)")
+        raw = _mlp_rays(coarse_model, rays, z_vals, precision, False if (coarse_outputs_unused or coarse_sigma_only) else exact_last_sample,
+                        sigma_only=bool(coarse_sigma_only))
         rgb_c, depth_c, acc_c, weights = ops.composite(raw, z_vals, rays_d, want_weights=True)
 
     if u is None:
@@ -118,10 +124,10 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     return rgb_c, depth_c, acc_c, rgb_f, depth_f, acc_f
 
 
-def _mlp_rays(model, rays, z, precision, exact_last_sample):
+def _mlp_rays(model, rays, z, precision, exact_last_sample, sigma_only=False):
     """run_network on (rays, z) -> raw[N,S,4] (bf16 inference: with the last-sample sign check, ops.mlp)."""
     n, s = z.shape
-    return ops.mlp(model, rays=rays, z=z, precision=precision, exact_last_sample=exact_last_sample).view(n, s, 4)
+    return ops.mlp(model, rays=rays, z=z, precision=precision, exact_last_sample=exact_last_sample, sigma_only=sigma_only).view(n, s, 4)
 
 
 def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
@@ -134,7 +140,7 @@ def _draw_t_rand(n: int, sc: int, chunk: int, device) -> torch.Tensor:
 def render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                         fine_sample_num, chunk=REFERENCE_RAY_CHUNK, *, ray_begin=0, ray_count=None, t_rand=None,
                         precision=None, launch_rays=1 << 20, coarse_no_grad=False, exact_last_sample=None, fine_out=None,
-                        coarse_outputs_unused=False):
+                        coarse_outputs_unused=False, coarse_sigma_only=False):
     """Device-resident core of render_image: renders flattened pixel rows [ray_begin, +ray_count)
     and returns the six per-ray outputs of the fine AND coarse pass as CUDA tensors.  Rays are
     generated on the device (K1); ``launch_rays`` bounds the rays per kernel launch sequence.
@@ -154,7 +160,7 @@ def render_image_device(width, height, focal, pose, near, far, coarse_model, fin
         outs.append(render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
                                 t_rand=t_rand[b:b + cnt], precision=precision, coarse_no_grad=coarse_no_grad,
                                 exact_last_sample=exact_last_sample, fine_out=None if fine_out is None else fine_out[b:b + cnt],
-                                coarse_outputs_unused=coarse_outputs_unused))
+                                coarse_outputs_unused=coarse_outputs_unused, coarse_sigma_only=coarse_sigma_only))
     if len(outs) == 1:
         return outs[0]
     if fine_out is not None:                   # the fine maps already sit in fine_out's rows
@@ -215,14 +221,16 @@ def maps_to_numpy(packed: torch.Tensor, h: int, w: int):
 
 
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None):
-    """nerf/render.py:150-167 -- numpy (H,W,3), (H,W,1), (H,W,1) = fine rgb / depth / acc."""
+                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None, coarse_sigma_only=False):
+    """nerf/render.py:150-167 -- numpy (H,W,3), (H,W,1), (H,W,1) = fine rgb / depth / acc.
+    ``coarse_sigma_only=True`` (opt-in): the coarse pass, whose colour this function never returns, stops after the sigma head
+    (render_rays); the three images are bit-identical either way."""
     h, w = int(height), int(width)
     with torch.no_grad():
         packed = torch.empty((h * w, 5), dtype=torch.float32, device=_model_device(coarse_model))
         render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                             fine_sample_num, chunk, t_rand=t_rand, precision=precision,
-                            exact_last_sample=exact_last_sample, fine_out=packed)
+                            exact_last_sample=exact_last_sample, fine_out=packed, coarse_sigma_only=coarse_sigma_only)
     return maps_to_numpy(packed, h, w)
 
 

@@ -684,6 +684,8 @@ def mlp(model, rays: torch.Tensor | None = None, z: torch.Tensor | None = None, 
     bf16 inference on ray samples -- (rays, z), or x with ``samples_per_ray`` given -- also runs the last-sample sign check
     (see _EXACT_LAST above) unless ``exact_last_sample`` is False."""
     kind = models.model_kind(model)
+    if kind == models.KIND_SIREN:
+        sigma_only = False                       # no such kernel for SirenNeRF: the full evaluation is a superset
     net = model.module if isinstance(model, torch.nn.DataParallel) else model
     use_dir = bool(getattr(net, "use_dir", True))
     ps = models.param_list(net, kind)

@@ -37,21 +37,23 @@ def camera_pos_to_transform_matrix(radius, theta, phi):
 
 
 def render_image(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None):
+                 chunk=1024 * 16, *, t_rand=None, precision=None, exact_last_sample=None, coarse_sigma_only=False):
     """pi_GAN/render.py:195-206 -- fine rgb as a torch tensor [H,W,3] on the device, carrying the
     autograd graph to the model parameters and the FiLM parameters (pi_GAN/train.py:134,
     synthesis.py:107).  In pi-GAN coarse_model is fine_model and only the fine rgb is consumed, so
     the coarse pass carries no gradient and runs in inference mode."""
     out = _render(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                  chunk, t_rand, precision, coarse_no_grad=True, exact_last_sample=exact_last_sample, coarse_outputs_unused=True)
+                  chunk, t_rand, precision, coarse_no_grad=True, exact_last_sample=exact_last_sample, coarse_outputs_unused=True,
+                  coarse_sigma_only=coarse_sigma_only)
     return out[3].reshape(int(height), int(width), 3)
 
 
 def _render(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk, t_rand, precision,
-            coarse_no_grad=False, exact_last_sample=None, coarse_outputs_unused=False):
+            coarse_no_grad=False, exact_last_sample=None, coarse_outputs_unused=False, coarse_sigma_only=False):
     return render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, sc, sf, chunk,
                                t_rand=t_rand, precision=precision, coarse_no_grad=coarse_no_grad,
-                               exact_last_sample=exact_last_sample, coarse_outputs_unused=coarse_outputs_unused)
+                               exact_last_sample=exact_last_sample, coarse_outputs_unused=coarse_outputs_unused,
+                               coarse_sigma_only=coarse_sigma_only)
 
 
 def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
@@ -82,7 +84,7 @@ def render_video_np(width, height, focal, poses, near, far, coarse_model, fine_m
 
 
 def render_batch(model, film_params, poses, width, height, focal, near, far, coarse_sample_num, fine_sample_num, *,
-                 t_rand=None, precision=None, exact_last_sample=None):
+                 t_rand=None, precision=None, exact_last_sample=None, coarse_sigma_only=False):
     """Batched counterpart of Generator.forward's per-latent loop (pi_GAN/modules.py:176-184):
     film_params[B,9,512], poses[B,4,4] -> images [B,3,H,W].  This is the latent-sharding unit for
     multi-GPU runs (each rank renders its slice of B).
@@ -90,7 +92,8 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
     With the bf16 tensor-core MLP the B latents are rendered by ONE launch sequence (rays of all poses, one batched MLP launch
     per pass with per-latent FiLM tables) -- also WITH gradients (pi_GAN/train.py:134: the fine pass runs on the fused
     training path for all latents at once, the coarse pass carries no gradient as in render_image); otherwise latent by
-    latent through render_image."""
+    latent through render_image.  ``coarse_sigma_only=True`` (opt-in): the coarse pass, whose colour never reaches the image, stops
+    after the sigma head; the images are bit-identical either way."""
     b = film_params.shape[0]
     w, h, sc, sf = int(width), int(height), int(coarse_sample_num), int(fine_sample_num)
     if next(model.parameters()).device.type != "cuda":
@@ -105,7 +108,8 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
             model.set_film_params(film_params[i])
             tr = None if t_rand is None else t_rand[i]
             imgs.append(render_image(width, height, focal, poses[i], near, far, model, model, coarse_sample_num,
-                                     fine_sample_num, t_rand=tr, precision=precision, exact_last_sample=exact_last_sample))
+                                     fine_sample_num, t_rand=tr, precision=precision, exact_last_sample=exact_last_sample,
+                                     coarse_sigma_only=coarse_sigma_only))
         return torch.stack(imgs).permute(0, 3, 1, 2).contiguous()
     dev = next(model.parameters()).device
     n = w * h
@@ -123,7 +127,7 @@ def render_batch(model, film_params, poses, width, height, focal, near, far, coa
         film = torch.as_tensor(film_params, dtype=torch.float32).to(dev).reshape(b, 9, 512)
         z, mids = ops.stratified_z(z_lin, t_all)
         # coarse pass: only weights[:, 1:-1] are used (the image is the fine colour), so its last sample needs no sign check
-        raw = ops.mlp_film_batched(model, film, rays, z, n * sc, exact_last_sample=False)
+        raw = ops.mlp_film_batched(model, film, rays, z, n * sc, exact_last_sample=False, sigma_only=bool(coarse_sigma_only))
         _, _, _, wts, _ = ops.composite_forward(raw, z, rays[:, 1], True)
         z_f = ops.sample_pdf(mids, wts[:, 1:-1], sf, u=u, z_coarse=z, want_samples=False)["sorted"]
         if not grad:

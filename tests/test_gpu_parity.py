@@ -637,6 +637,48 @@ def test_drop_in_usage_like_the_reference_scripts():
         torch.set_default_device("cpu")
 
 
+def test_coarse_sigma_only_is_dead_code_elimination():
+    """render_image(coarse_sigma_only=True) stops the COARSE pass after the sigma head (its colour is never returned,
+    nerf/render.py:150-167 / pi_GAN/render.py:195-206): sigma of the shortened walk, the coarse weights and every fine output must be
+    bit-identical to the full evaluation's, for NeRF and for the FiLM-SIREN batch render; a coarse pass that carries gradients refuses."""
+    from msra_practice_project_b200 import nerf_render
+    torch.manual_seed(1)
+    coarse, fine = models.NeRF().cuda(), models.NeRF().cuda()
+    pose = pigan_render.camera_pos_to_transform_matrix(4.0, 0.2, -0.4)
+    rays = ops.raygen(48, 40, 48 * 1.3875, pose, 0, 48 * 40, device=torch.device("cuda"))
+    z = torch.sort(torch.rand(48 * 40, 64, device="cuda") * 4 + 2, -1).values
+    with torch.no_grad():
+        raw_full = ops.mlp(coarse, rays=rays, z=z, precision="bf16", exact_last_sample=False)
+        raw_sig = ops.mlp(coarse, rays=rays, z=z, precision="bf16", sigma_only=True)
+        assert torch.equal(raw_full[:, 3], raw_sig[:, 3]) and float(raw_sig[:, :3].abs().max()) == 0.0
+        t_rand = torch.rand(48 * 40, 64, device="cuda")
+        a = nerf_render.render_image_device(48, 40, 48 * 1.3875, pose, 2.0, 6.0, coarse, fine, 64, 128, t_rand=t_rand)
+        b = nerf_render.render_image_device(48, 40, 48 * 1.3875, pose, 2.0, 6.0, coarse, fine, 64, 128, t_rand=t_rand, coarse_sigma_only=True)
+        for i in (3, 4, 5):
+            assert torch.equal(a[i], b[i]), i
+        assert float(b[0].abs().max()) == 0.0        # coarse colour map: zero (its depth / acc come without the last-sample check)
+        ia = nerf_render.render_image(48, 40, 48 * 1.3875, pose, 2.0, 6.0, coarse, fine, 64, 128, t_rand=t_rand)
+        ib = nerf_render.render_image(48, 40, 48 * 1.3875, pose, 2.0, 6.0, coarse, fine, 64, 128, t_rand=t_rand, coarse_sigma_only=True)
+        assert all(np.array_equal(x, y) for x, y in zip(ia, ib))
+        # SirenNeRF has no shortened walk: the switch is accepted and changes nothing
+        sa, sb = models.SirenNeRF().cuda(), models.SirenNeRF().cuda()
+        c = nerf_render.render_image_device(16, 16, 22.0, pose, 2.0, 6.0, sa, sb, 16, 16, t_rand=t_rand[:256, :16])
+        d = nerf_render.render_image_device(16, 16, 22.0, pose, 2.0, 6.0, sa, sb, 16, 16, t_rand=t_rand[:256, :16], coarse_sigma_only=True)
+        assert all(torch.equal(c[i], d[i]) for i in range(6))
+        # FiLM-SIREN batch render (4 latents x 32x32, 24+24: rows per latent a multiple of 512)
+        net = models.FilmSirenNeRF().cuda()
+        g = torch.Generator().manual_seed(0)
+        film = torch.cat([1.0 + 0.2 * torch.randn(4, 9, 256, generator=g), 0.1 * torch.randn(4, 9, 256, generator=g)], -1).cuda()
+        poses = [pigan_render.camera_pos_to_transform_matrix(1, 0.3 * np.sin(i), 0.15 * np.cos(i)) for i in range(4)]
+        tr = torch.rand(4 * 32 * 32, 24, device="cuda")
+        focal = 32 / 2 / np.tan(6 * np.pi / 180)
+        p1 = pigan_render.render_batch(net, film, poses, 32, 32, focal, 0.5, 1.5, 24, 24, t_rand=tr)
+        p2 = pigan_render.render_batch(net, film, poses, 32, 32, focal, 0.5, 1.5, 24, 24, t_rand=tr, coarse_sigma_only=True)
+        assert torch.equal(p1, p2)
+    with pytest.raises(RuntimeError):
+        nerf_render.render_rays(rays.reshape(-1, 2, 3)[:64], 2.0, 6.0, coarse, fine, 16, 16, coarse_sigma_only=True)
+
+
 def test_render_image_frames_are_owned_by_the_caller():
     """render_image hands out views of pooled page-locked buffers (no host copy).  A frame the caller still holds must never be
     overwritten by later renders -- also beyond the pool size, where the images become fresh pageable arrays -- and a buffer must go
