@@ -82,7 +82,7 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     so nothing the caller sees changes, and a training step keeps running without a host synchronisation.
     ``coarse_sigma_only`` (opt-in, off by default; bf16 inference of NeRF / FiLM-SIREN models): the coarse pass stops after the sigma
     head -- dead-code elimination for callers that return only the fine maps (render_image): the coarse weights, and with them every
-    fine output, are bit-identical (tested); the returned coarse rgb map is zero.  Needs a gradient-free coarse pass.
+    fine output, are bit-identical (tested); the returned coarse rgb map carries no colour (background term only).  Needs a gradient-free coarse pass.
     Applies to passes that run without gradients (renders; the pi-GAN coarse pass).  Passes that carry
     gradients run the raw bf16 forward (mixed-precision training; d sigma_last is zero either way) unless
     ops.set_exact_last_sample(train=True) is set -- an explicit switch, not a silent skip."""
