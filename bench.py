@@ -327,8 +327,12 @@ def run_b200(args):
         with torch.no_grad():
             # N > 1: the fine composite writes (rgb, depth, acc) straight into this rank's rows of the frame buffer and the
             # all-gather runs in place on it (no pack / staging copy)
+            # what render_image runs: the whole network on every coarse and fine sample, fine maps conformant (last-sample sign check);
+            # the coarse maps are not part of the frame (nerf/render.py:161-166 returns the fine ones), so the coarse pass's last
+            # samples -- which reach nothing but those maps -- get no sign check (coarse_outputs_unused)
             out = nerf_render.render_image_device(W, H, focal, pose, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin,
-                                                  ray_count=count, t_rand=t_rand, precision=args.precision, fine_out=my_rows)
+                                                  ray_count=count, t_rand=t_rand, precision=args.precision, fine_out=my_rows,
+                                                  coarse_outputs_unused=True)
             if world > 1:
                 shard.gather_image(out[3], out[4], out[5], gathered, n_rays, rank, world)
         return out
@@ -417,7 +421,7 @@ def run_b200(args):
             with torch.no_grad():
                 for b0, cnt in spans:
                     o = nerf_render.render_image_device(W, H, focal, pose, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=b0, ray_count=cnt,
-                                                        t_rand=t_full[b0:b0 + cnt], precision=args.precision)
+                                                        t_rand=t_full[b0:b0 + cnt], precision=args.precision, coarse_outputs_unused=True)
                     alone = torch.cat([o[3], o[4][:, None], o[5][:, None]], -1)
                     ok = ok and bool(torch.equal(alone, gathered[b0:b0 + cnt]))
                     checked += cnt
@@ -437,7 +441,7 @@ def run_b200(args):
                 return nerf_render.render_image(W, H, focal, p, 2.0, 6.0, coarse, fine, sc, sf, precision=args.precision)
             out = nerf_render.render_image_device(W, H, focal, p, 2.0, 6.0, coarse, fine, sc, sf, ray_begin=begin,
                                                   ray_count=count, t_rand=None if world == 1 else t_rand, precision=args.precision,
-                                                  fine_out=my_rows)
+                                                  fine_out=my_rows, coarse_outputs_unused=True)
             if world > 1:
                 shard.gather_image(out[3], out[4], out[5], gathered, n_rays, rank, world)
                 if rank == 0:
@@ -583,7 +587,7 @@ def run_b200(args):
                              d2h_copy_alone_ms=d2h_ms, frames_ms=per_frame, stage_pool=stage_pool),
                     # raygen, stratified_z, 2 x (fused MLP, composite), sample_pdf + per pass with flagged rays the fp32 re-evaluation
                     # (encode, 8 layer GEMMs, sigma head)
-                    gpu_launches=int((7 + (20 if last_sample and last_sample["rays_reevaluated_fp32_per_step"] else 0)) * args.steps * world),
+                    gpu_launches=int((7 + (10 * last_sample["passes_per_step"] if last_sample and last_sample["rays_reevaluated_fp32_per_step"] else 0)) * args.steps * world),
                     last_sample=last_sample, sharded_equals_single=sharded_equals_single, clocks=clocks.summary(), roofline=roof,
                     hbm_kernels=hbm_kernels,
                     cpu_baseline=base, secondary=secondary)
@@ -698,7 +702,7 @@ def run_secondary(args, config=None, embedded=False):
         def step():
             with torch.no_grad():
                 nerf_render.render_image_device(w, h, w * 1.3875, pose, 2.0, 6.0, coarse, fine, args.coarse, args.fine, ray_begin=b, ray_count=c,
-                                                t_rand=t_rand, precision=args.precision)
+                                                t_rand=t_rand, precision=args.precision, coarse_outputs_unused=True)
         ms = timed(step, args.steps, args.warmup)
         rows = n * (2 * args.coarse + args.fine)
         line = dict(metric="rays/s, SirenNeRF 800x800 render, 64 coarse + 128 fine samples/ray", value=n / (ms * 1e-3), unit="rays/s",

@@ -86,7 +86,8 @@ def render_image_sharded(width, height, focal, pose, near, far, coarse_model, fi
         o = nerf_render.render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model,
                                             coarse_sample_num, fine_sample_num, ray_begin=begin, ray_count=count,
                                             t_rand=t_rand_full[begin:begin + count], precision=precision,
-                                            exact_last_sample=exact_last_sample, fine_out=frame_slice(out, n, rank, world))
+                                            exact_last_sample=exact_last_sample, fine_out=frame_slice(out, n, rank, world),
+                                            coarse_outputs_unused=True)
         gather_image(o[3], o[4], o[5], out, n, rank, world, group)
     h, w = int(height), int(width)
     return out[:, :3].reshape(h, w, 3), out[:, 3].reshape(h, w, 1), out[:, 4].reshape(h, w, 1)

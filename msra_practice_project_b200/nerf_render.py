@@ -77,7 +77,8 @@ def render_rays(rays, near, far, coarse_model, fine_model, coarse_sample_num, fi
     sign(sigma_last) and a bf16 rounding would flip ~0.2 % of rays by up to 0.6.
     ``fine_out`` [N,5] (no-grad renders): the fine pass writes (rgb, depth, acc) into its rows -- a rank's slice
     of the gathered frame buffer -- and the returned fine maps are views of it.
-    ``coarse_outputs_unused`` (the pi-GAN wrappers, which return only the fine colour): the COARSE pass skips the check --
+    ``coarse_outputs_unused`` (render_image / render_video and the pi-GAN wrappers, which return only the fine maps): the COARSE pass
+    evaluates the whole network as always but skips the check --
     its last sample only reaches the coarse rgb / depth / acc maps (sample_pdf reads weights[:, 1:-1], nerf/render.py:140),
     so nothing the caller sees changes, and a training step keeps running without a host synchronisation.
     ``coarse_sigma_only`` (opt-in, off by default; bf16 inference of NeRF / FiLM-SIREN models): the coarse pass stops after the sigma
@@ -230,7 +231,8 @@ def render_image(width, height, focal, pose, near, far, coarse_model, fine_model
         packed = torch.empty((h * w, 5), dtype=torch.float32, device=_model_device(coarse_model))
         render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num,
                             fine_sample_num, chunk, t_rand=t_rand, precision=precision,
-                            exact_last_sample=exact_last_sample, fine_out=packed, coarse_sigma_only=coarse_sigma_only)
+                            exact_last_sample=exact_last_sample, fine_out=packed, coarse_sigma_only=coarse_sigma_only,
+                            coarse_outputs_unused=True)      # only the fine maps leave this function: no sign check on coarse rays
     return maps_to_numpy(packed, h, w)
 
 
@@ -268,7 +270,8 @@ def render_video_u8(width, height, focal, poses, near, far, coarse_model, fine_m
     with torch.no_grad():
         for k, p in enumerate(tqdm(poses)):
             o = render_image_device(width, height, focal, p, near, far, coarse_model, fine_model, coarse_sample_num,
-                                    fine_sample_num, chunk, precision=precision, exact_last_sample=exact_last_sample)
+                                    fine_sample_num, chunk, precision=precision, exact_last_sample=exact_last_sample,
+                                    coarse_outputs_unused=True)
             frame = ops.to8b(o[3]).reshape(h, w, 3)
             slot = k & 1
             if pending[slot] is not None:                       # the buffer's previous frame must have landed

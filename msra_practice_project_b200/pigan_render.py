@@ -63,7 +63,8 @@ def render_image_np(width, height, focal, pose, near, far, coarse_model, fine_mo
     with torch.no_grad():
         packed = torch.empty((h * w, 5), dtype=torch.float32, device=next(coarse_model.parameters()).device)
         render_image_device(width, height, focal, pose, near, far, coarse_model, fine_model, coarse_sample_num, fine_sample_num,
-                            chunk, t_rand=t_rand, precision=precision, exact_last_sample=exact_last_sample, fine_out=packed)
+                            chunk, t_rand=t_rand, precision=precision, exact_last_sample=exact_last_sample, fine_out=packed,
+                            coarse_outputs_unused=True)
     return maps_to_numpy(packed, h, w)
 
 
