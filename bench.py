@@ -15,6 +15,7 @@ whose images are returned as numpy arrays (D2H inside the timed region).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -344,12 +345,14 @@ def run_b200(args):
 
     def timed(fn, steps):
         barrier()
+        gc.collect(); gc.disable()              # no cyclic-GC pause of the interpreter inside a timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
+        gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -620,6 +623,7 @@ def run_secondary(args, config=None, embedded=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        gc.collect(); gc.disable()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -628,6 +632,7 @@ def run_secondary(args, config=None, embedded=False):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
