@@ -99,8 +99,27 @@ __device__ __forceinline__ float film_table_value(const float* __restrict__ para
     return val;
 }
 
+// the 8 bf16 of 16-byte group `grp` of weight row n in chunk c (0..3: h columns c*64 + grp*8 ..; 4: the post chunk) of step s
+__device__ __forceinline__ void film_pack_group(const float* __restrict__ params, const float* __restrict__ film, bool ud, int s, int c, int n, int grp,
+                                                __nv_bfloat16 (&v)[8]) {
+    LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);           // hidden_layers.s | hidden_layer_rgb
+    float scale, shift;
+    film_scale_shift(params, film, ud, s, n, scale, shift);
+    const __nv_bfloat16 sh_hi = __float2bfloat16_rn(shift);
+    const __nv_bfloat16 sh_lo = __float2bfloat16_rn(shift - __bfloat162float(sh_hi));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int kk = grp * 8 + e;
+        if (c < 4) v[e] = __float2bfloat16_rn(scale * params[L.w_off + (long long)n * L.in + c * 64 + kk]);
+        else if (kk < 3) v[e] = __float2bfloat16_rn((s == 7 && ud) ? scale * params[L.w_off + (long long)n * L.in + 256 + kk] : 0.f);
+        else if (kk == 3) v[e] = sh_hi;
+        else if (kk == 4) v[e] = sh_lo;
+        else v[e] = __float2bfloat16_rn(0.f);
+    }
+}
+
 // blockIdx.y = latent: packed[latent] = chunks (bf16, rows pre-multiplied by the FiLM scale; post chunk = [W_dir(3) | shift hi | shift lo])
-// + fp32 tables.  film: [n_latents][9][512]
+// + fp32 tables + the inference kernel's blobs.  film: [n_latents][9][512]
 __global__ void film_pack_kernel(const float* __restrict__ params, const float* __restrict__ film_all, int use_dir,
                                  uint8_t* __restrict__ packed_all) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -110,25 +129,18 @@ __global__ void film_pack_kernel(const float* __restrict__ params, const float* 
     if (t < kFilmChunkBytes / 16) {
         int s, c, hf, row, grp;
         locate<FilmSched>(t * 16, s, c, hf, row, grp);
-        LayerDesc L = film_layer(s < 7 ? s + 1 : 9, ud);           // hidden_layers.s | hidden_layer_rgb
-        const int n = hf * 128 + row;
-        float scale, shift;
-        film_scale_shift(params, film, ud, s, n, scale, shift);
-        const __nv_bfloat16 sh_hi = __float2bfloat16_rn(shift);
-        const __nv_bfloat16 sh_lo = __float2bfloat16_rn(shift - __bfloat162float(sh_hi));
         __nv_bfloat16 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int kk = grp * 8 + e;
-            if (c < 4) v[e] = __float2bfloat16_rn(scale * params[L.w_off + (long long)n * L.in + c * 64 + kk]);
-            else if (kk < 3) v[e] = __float2bfloat16_rn((s == 7 && ud) ? scale * params[L.w_off + (long long)n * L.in + 256 + kk] : 0.f);
-            else if (kk == 3) v[e] = sh_hi;
-            else if (kk == 4) v[e] = sh_lo;
-            else v[e] = __float2bfloat16_rn(0.f);
-        }
+        film_pack_group(params, film, ud, s, c, hf * 128 + row, grp, v);
         uint8_t* dst = packed + step_base<FilmSched>(s) + (long long)(c * 2 + hf) * half_bytes<FilmSched>(s) +
                        sw128_offset((uint32_t)row, (uint32_t)grp);
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+    if (t < (kFilmPackedBytes - kFilmExtraOff) / 16) {          // blobs [h chunk 3 | compact post chunk] of the inference kernel (tc_core.cuh)
+        int s, c, hf, row, grp;
+        locate_extra<FilmSched>(t * 16, s, c, hf, row, grp);
+        __nv_bfloat16 v[8];
+        film_pack_group(params, film, ud, s, c, hf * 128 + row, grp, v);
+        *reinterpret_cast<uint4*>(packed + kFilmExtraOff + extra_dst<FilmSched>(s, c, hf, row, grp)) = *reinterpret_cast<const uint4*>(v);
     }
     if (t < kFilmTabFloats) {
         float* tab = reinterpret_cast<float*>(packed + kFilmChunkBytes);
@@ -523,8 +535,11 @@ template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, int sigma_only, float4* __restrict__ raw_out,
                int n_latents, long long rows_per_latent, uint8_t* __restrict__ saved, LastFlag lf) {
+    // inference (kSave = false): compact map -- 4 KB no-swizzle aux operand, 4-stage ring, 4 copies per step (tc_core.cuh MapC)
+    constexpr bool kC = !kSave;
+    constexpr uint32_t kSub = kC ? MapC::kSub : kSubBytes, kAux = kC ? MapC::kAux : kPeBytes;
     extern __shared__ uint8_t smem_raw[];
-    const Ctx cx = make_ctx(smem_raw);
+    const Ctx cx = kC ? make_ctx_c(smem_raw) : make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PairLoop pl(rows);
     const bool batched = n_latents > 1;
@@ -533,7 +548,7 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
     long long cur_lat = latent_of(pl.first < pl.n_pairs ? pl.first : 0);
     const int n_steps = sigma_only ? 7 : FilmSched::kSteps;
     static_assert(kFilmTabFloats * 4 <= (int)(kTabBytes + kPartBytes), "FiLM table region");
-    const uint32_t tab = cx.smem + kTabOff;                    // fp32 tables of the current latent (9.2 KB)
+    const uint32_t tab = cx.smem + (kC ? MapC::kTab : kTabOff);   // fp32 tables of the current latent (9.2 KB)
     {
         const float4* tab_g = reinterpret_cast<const float4*>(packed + (size_t)cur_lat * kFilmPackedBytes + kFilmChunkBytes);
         for (int i = threadIdx.x; i < kFilmTabFloats / 4; i += kThreads) {
@@ -547,13 +562,21 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
             st_shared_v4(cx.smem + gg * kSubBytes + o * 16u, 0u, 0u, 0u, 0u);
         }
     }
-    const uint32_t tmem_base = tc_prologue(cx, warp, 32, 16);  // act_ready: 16 warps x 2 CTAs arrive per sub-tile and step
+    const uint32_t tmem_base = tc_prologue(cx, warp, 32, 16, kC ? MapC::kStagesC : kStages);  // act_ready: 16 warps x 2 CTAs arrive per sub-tile and step
 
     if (warp == 0) {
-        if (lane == 0) producer_loop_fn<FilmSched>(cx, packed_of, pl, n_steps, 1);
+        if (lane == 0) {
+            if (kC) producer_loop_c<FilmSched>(cx, packed_of, kFilmExtraOff, pl, n_steps);
+            else producer_loop_fn<FilmSched>(cx, packed_of, pl, n_steps, 1);
+        }
     } else if (warp == 1) {
-        if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, 1);
-        else if (lane == 0) relay_loop<FilmSched>(cx, pl, n_steps, 1);
+        if (kC) {
+            if (cx.rank == 0) mma_loop_c<FilmSched>(cx, tmem_base, pl, n_steps);
+            else if (lane == 0) relay_loop_c(cx, pl, n_steps);
+        } else {
+            if (cx.rank == 0) mma_loop<FilmSched>(cx, tmem_base, pl, n_steps, 1);
+            else if (lane == 0) relay_loop<FilmSched>(cx, pl, n_steps, 1);
+        }
     } else if (warp < kCtrlWarps) {
         if (kSave && lane == 0) {
             // ===== spill thread of sub-tile g =====
@@ -597,9 +620,12 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
         }
         auto spill_sig = [&](int g) { if (kSave && lane == 0) mbar_arrive(cx.spill_ready + 8 * g); };
         auto spill_wait = [&](int g) { if (kSave) { mbar_wait(cx.spill_done + 8 * g, sp_phase[g]); sp_phase[g] ^= 1u; } };
-        auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSubBytes; };
+        auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSub; };
         auto t_q = [&](int g) -> uint32_t { return tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u + (uint32_t)cq * 64u; };
-        auto h_blk = [&](int g) -> uint32_t { return sub_base(g) + kPeBytes + (uint32_t)cq * 16384u + row_off; };
+        auto h_blk = [&](int g) -> uint32_t { return sub_base(g) + kAux + (uint32_t)cq * 16384u + row_off; };
+        // head partials part[g][r][cq] (float4): upper half of the 16 KB aux block / first K-block of h on the compact map -- both free
+        // once the sub-tile's last MMA is done
+        auto part_of = [&](int g) -> uint32_t { return sub_base(g) + (kC ? kAux : 8192u); };
         auto arrive = [&](int g) { arrive_act(cx.act_ready + 8 * g, act_leader0 + 8 * g, cx.rank, lane); };
         auto wait_acc = [&](int g) {
             mbar_wait_cluster(cx.acc_full + 8 * g, acc_phase[g]);
@@ -663,9 +689,10 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                     // aux block = [view direction (3), 1, 1, position (3), 0 ...] (16 K): the direction columns of hidden_layer_rgb and the
                     // two constant ones that pick up every layer's FiLM shift (hi + lo); the position columns meet zero weights in the
                     // forward and are the input-layer operand of the training wgrad
-                    st_shared_v4(sub_base(g) + row_off + ((0u ^ xr) << 4), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 1.0f), pack_bf16(1.0f, pnt[0]),
-                                 pack_bf16(pnt[1], pnt[2]));
-                    st_shared_v4(sub_base(g) + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
+                    // (compact map: 16-byte K chunk c of row r at c * 2 KB + r * 16, no swizzle)
+                    st_shared_v4(sub_base(g) + (kC ? (uint32_t)r * 16u : row_off + ((0u ^ xr) << 4)), pack_bf16(vdir[0], vdir[1]), pack_bf16(vdir[2], 1.0f),
+                                 pack_bf16(1.0f, pnt[0]), pack_bf16(pnt[1], pnt[2]));
+                    st_shared_v4(sub_base(g) + (kC ? 2048u + (uint32_t)r * 16u : row_off + ((1u ^ xr) << 4)), 0u, 0u, 0u, 0u);
                 }
                 arrive(g);
                 spill_sig(g);
@@ -707,18 +734,20 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 }
             }
             tc_fence_before();
-            // head partials of the four column quarters -> the aux blocks' upper halves (free once the last MMA is done):
+            // head partials of the four column quarters (part_of):
+            // (compact map: the slots overlay h, which sigma_only's last epilogue still writes -- every warp must be past it)
+            if (kC) asm volatile("bar.sync 3, 512;" ::: "memory");
             // part[g][r][cq] as float4; the quarter-0 / quarter-1 warps finish sub-tile 0 / 1
 #pragma unroll
             for (int g = 0; g < 2; ++g)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sub_base(g) + 8192u + (uint32_t)(r * 4 + cq) * 16u), "f"(rgb0[g]),
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part_of(g) + (uint32_t)(r * 4 + cq) * 16u), "f"(rgb0[g]),
                              "f"(rgb1[g]), "f"(rgb2[g]), "f"(sigma[g]) : "memory");
             asm volatile("bar.sync 3, 512;" ::: "memory");
             if (cq < 2) {
                 const int g = cq;
                 const bool ok = cq == 0 ? valid[0] : valid[1];
                 const long long out_row = cq == 0 ? row[0] : row[1];
-                const uint32_t pa = sub_base(g) + 8192u + (uint32_t)(r * 4) * 16u;
+                const uint32_t pa = part_of(g) + (uint32_t)(r * 4) * 16u;
                 const float4 p0 = lds128(pa), p1 = lds128(pa + 16u), p2 = lds128(pa + 32u), p3 = lds128(pa + 48u);
                 if (ok) {
                     const float4 bh = lds128(tab + kFBH * 4u);          // (b_sigma, b_rgb[3])
@@ -835,9 +864,9 @@ extern "C" int b2r_mlp_tc_fwd(int model_kind, const void* packed, int use_dir, c
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (model_kind == B2R_MODEL_FILM) {
-        rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+        rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::MapC::kSmem), "tc smem attribute");
         if (rc) return rc;
-        tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0, nullptr,
+        tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::MapC::kSmem, st>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only, (float4*)raw_out, 1, 0, nullptr,
                                                                               tc::make_last_flag(last));
     } else {
         auto kern = sigma_only ? tc::nerf_tc_kernel<false, true> : tc::nerf_tc_kernel<false, false>;
@@ -880,10 +909,10 @@ extern "C" int b2r_mlp_tc_fwd_film_batched(const void* packed, int n_latents, lo
     unsigned grid = 0;
     rc = tc::pair_grid(rows, &grid);
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes), "tc smem attribute");
+    rc = cuda_result(cudaFuncSetAttribute(tc::film_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::MapC::kSmem), "tc smem attribute");
     if (rc) return rc;
     // n_latents == 1 still goes through the batched indexing (latent 0 for every row) when rows_per_latent covers all rows
-    tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only,
+    tc::film_tc_kernel<false><<<grid, tc::kThreads, tc::MapC::kSmem, (cudaStream_t)stream>>>((const uint8_t*)packed, make_row_source(in), rows, sigma_only,
                                                                                             (float4*)raw_out, n_latents, rows_per_latent, nullptr,
                                                                                             tc::make_last_flag(last));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd_film_batched");

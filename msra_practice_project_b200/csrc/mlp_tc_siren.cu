@@ -31,36 +31,49 @@ static_assert(kSirenChunkBytes == 8 * 5 * 32768LL + 5 * 16384LL, "siren packed c
 // fp32 tables (staged in shared memory): w0[3][256] (layers_pos.0, column-major) | shift0[256] | w_sigma[256] | w_rgb[3][128] |
 //                                        b_sigma, b_rgb[3]
 constexpr int kSW0 = 0, kST0 = 768, kSWS = 1024, kSWR = 1280, kSBH = 1664, kSirenTabFloats = 1668;
-constexpr long long kSirenPackedBytes = kSirenChunkBytes + kSirenTabFloats * 4;
+constexpr long long kSirenExtraOff = kSirenChunkBytes + kSirenTabFloats * 4;             // blobs of the inference kernel (tc_core.cuh: extra_base)
+constexpr long long kSirenPackedBytes = kSirenExtraOff + extra_base<SirenSched>(SirenSched::kSteps);
+static_assert(kSirenExtraOff % 16 == 0 && kSirenPackedBytes % 16 == 0, "bulk copies need 16-byte alignment");
 static_assert(kSirenTabFloats * 4 <= (int)(kTabBytes + kPartBytes), "siren tables fit the table region");
 
 __host__ __device__ constexpr int siren_step_layer(int s) { return s + 1; }      // steps 0..8 = siren_layer 1..9
+
+// the 8 bf16 of 16-byte group `grp` of weight row n in chunk c (0..3: h columns; 4: the post chunk) of step s
+__device__ __forceinline__ void siren_pack_group(const float* __restrict__ params, int s, int c, int n, int grp, __nv_bfloat16 (&v)[8]) {
+    LayerDesc L = siren_layer(siren_step_layer(s));
+    const float scale = s == 7 ? 1.0f : 30.0f;                                          // layers_dir.0 is linear
+    const float shift = scale * params[L.b_off + n];
+    const __nv_bfloat16 sh_hi = __float2bfloat16_rn(shift);
+    const __nv_bfloat16 sh_lo = __float2bfloat16_rn(shift - __bfloat162float(sh_hi));
+    const int h_off = s == 4 ? 3 : 0;                                                   // [pos | h4] (nerf/nerf.py:158)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        int kk = grp * 8 + e;
+        float w = 0.f;
+        if (c < 4) w = scale * params[L.w_off + (long long)n * L.in + h_off + c * 64 + kk];
+        else if (kk < 3) w = s == 4 ? scale * params[L.w_off + (long long)n * L.in + kk] : 0.f;          // raw position
+        else if (kk >= 5 && kk < 8) w = s == 8 ? scale * params[L.w_off + (long long)n * L.in + 256 + (kk - 5)] : 0.f;   // [g | dir] (:166)
+        v[e] = (c == 4 && kk == 3) ? sh_hi : ((c == 4 && kk == 4) ? sh_lo : __float2bfloat16_rn(w));
+    }
+}
 
 __global__ void siren_pack_kernel(const float* __restrict__ params, uint8_t* __restrict__ packed) {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t < kSirenChunkBytes / 16) {
         int s, c, hf, row, grp;
         locate<SirenSched>(t * 16, s, c, hf, row, grp);
-        LayerDesc L = siren_layer(siren_step_layer(s));
-        const int n = hf * (SirenSched::n(s) / 2) + row;
-        const float scale = s == 7 ? 1.0f : 30.0f;                                          // layers_dir.0 is linear
-        const float shift = scale * params[L.b_off + n];
-        const __nv_bfloat16 sh_hi = __float2bfloat16_rn(shift);
-        const __nv_bfloat16 sh_lo = __float2bfloat16_rn(shift - __bfloat162float(sh_hi));
-        const int h_off = s == 4 ? 3 : 0;                                                   // [pos | h4] (nerf/nerf.py:158)
         __nv_bfloat16 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            int kk = grp * 8 + e;
-            float w = 0.f;
-            if (c < 4) w = scale * params[L.w_off + (long long)n * L.in + h_off + c * 64 + kk];
-            else if (kk < 3) w = s == 4 ? scale * params[L.w_off + (long long)n * L.in + kk] : 0.f;          // raw position
-            else if (kk >= 5 && kk < 8) w = s == 8 ? scale * params[L.w_off + (long long)n * L.in + 256 + (kk - 5)] : 0.f;   // [g | dir] (:166)
-            v[e] = (c == 4 && kk == 3) ? sh_hi : ((c == 4 && kk == 4) ? sh_lo : __float2bfloat16_rn(w));
-        }
+        siren_pack_group(params, s, c, hf * (SirenSched::n(s) / 2) + row, grp, v);
         uint8_t* dst = packed + step_base<SirenSched>(s) + (long long)(c * 2 + hf) * half_bytes<SirenSched>(s) +
                        sw128_offset((uint32_t)row, (uint32_t)grp);
         *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    }
+    if (t < (kSirenPackedBytes - kSirenExtraOff) / 16) {        // blobs [h chunk 3 | compact post chunk] of the inference kernel
+        int s, c, hf, row, grp;
+        locate_extra<SirenSched>(t * 16, s, c, hf, row, grp);
+        __nv_bfloat16 v[8];
+        siren_pack_group(params, s, c, hf * (SirenSched::n(s) / 2) + row, grp, v);
+        *reinterpret_cast<uint4*>(packed + kSirenExtraOff + extra_dst<SirenSched>(s, c, hf, row, grp)) = *reinterpret_cast<const uint4*>(v);
     }
     if (t < kSirenTabFloats) {
         float* tab = reinterpret_cast<float*>(packed + kSirenChunkBytes);
@@ -139,11 +152,14 @@ template <bool kSave>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows, float4* __restrict__ raw_out, uint8_t* __restrict__ saved,
                 LastFlag lf) {
+    // inference (kSave = false): compact map -- 4 KB no-swizzle aux operand, 4-stage ring, 4 copies per step (tc_core.cuh MapC)
+    constexpr bool kC = !kSave;
+    constexpr uint32_t kSub = kC ? MapC::kSub : kSubBytes, kAux = kC ? MapC::kAux : kPeBytes;
     extern __shared__ uint8_t smem_raw[];
-    const Ctx cx = make_ctx(smem_raw);
+    const Ctx cx = kC ? make_ctx_c(smem_raw) : make_ctx(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PairLoop pl(rows);
-    const uint32_t tab = cx.smem + kTabOff;
+    const uint32_t tab = cx.smem + (kC ? MapC::kTab : kTabOff);
     {   // fp32 tables (6.7 KB) -> shared memory
         const float4* tab_g = reinterpret_cast<const float4*>(packed + kSirenChunkBytes);
         for (int i = threadIdx.x; i < kSirenTabFloats / 4; i += kThreads) {
@@ -157,13 +173,21 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
             st_shared_v4(cx.smem + g * kSubBytes + o * 16u, 0u, 0u, 0u, 0u);
         }
     }
-    const uint32_t tmem_base = tc_prologue(cx, warp, 32, 16);
+    const uint32_t tmem_base = tc_prologue(cx, warp, 32, 16, kC ? MapC::kStagesC : kStages);
 
     if (warp == 0) {
-        if (lane == 0) producer_loop<SirenSched>(cx, packed, pl, SirenSched::kSteps, 0);
+        if (lane == 0) {
+            if (kC) producer_loop_c<SirenSched>(cx, [packed](long long) { return packed; }, kSirenExtraOff, pl, SirenSched::kSteps);
+            else producer_loop<SirenSched>(cx, packed, pl, SirenSched::kSteps, 0);
+        }
     } else if (warp == 1) {
-        if (cx.rank == 0) mma_loop<SirenSched>(cx, tmem_base, pl, SirenSched::kSteps, 0);
-        else if (lane == 0) relay_loop<SirenSched>(cx, pl, SirenSched::kSteps, 0);
+        if (kC) {
+            if (cx.rank == 0) mma_loop_c<SirenSched>(cx, tmem_base, pl, SirenSched::kSteps);
+            else if (lane == 0) relay_loop_c(cx, pl, SirenSched::kSteps);
+        } else {
+            if (cx.rank == 0) mma_loop<SirenSched>(cx, tmem_base, pl, SirenSched::kSteps, 0);
+            else if (lane == 0) relay_loop<SirenSched>(cx, pl, SirenSched::kSteps, 0);
+        }
     } else if (warp < kCtrlWarps) {
         if (kSave && lane == 0) {
             // ===== spill thread of sub-tile g =====
@@ -210,9 +234,10 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
         // kSave: tile written (and fenced by arrive_act) -> spill thread; wait until the previous copy has read shared memory
         auto spill_sig = [&](int g) { if (kSave && lane == 0) mbar_arrive(cx.spill_ready + 8 * g); };
         auto spill_wait = [&](int g) { if (kSave) { mbar_wait(cx.spill_done + 8 * g, sp_phase[g]); sp_phase[g] ^= 1u; } };
-        auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSubBytes; };
+        auto sub_base = [&](int g) -> uint32_t { return cx.smem + (uint32_t)g * kSub; };
+        auto part_of = [&](int g) -> uint32_t { return sub_base(g) + (kC ? kAux : 8192u); };      // head partials (see film_tc_kernel)
         auto t_row = [&](int g) -> uint32_t { return tmem_base + ((uint32_t)quad << 21) + (uint32_t)g * 256u; };
-        auto h_blk = [&](int g) -> uint32_t { return sub_base(g) + kPeBytes + (uint32_t)cq * 16384u + row_off; };
+        auto h_blk = [&](int g) -> uint32_t { return sub_base(g) + kAux + (uint32_t)cq * 16384u + row_off; };
         auto arrive = [&](int g) { arrive_act(cx.act_ready + 8 * g, act_leader0 + 8 * g, cx.rank, lane); };
         auto wait_acc = [&](int g) {
             mbar_wait_cluster(cx.acc_full + 8 * g, acc_phase[g]);
@@ -260,9 +285,10 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                 }
                 if (cq == 0) {
                     // aux block = [pos(3), 1, 1, dir(3), 0 ...] (16 K): raw inputs of the two skip layers + the constant ones of the shifts
-                    st_shared_v4(sub_base(g) + row_off + ((0u ^ xr) << 4), pack_bf16(pnt[0], pnt[1]), pack_bf16(pnt[2], 1.0f), pack_bf16(1.0f, vdir[0]),
-                                 pack_bf16(vdir[1], vdir[2]));
-                    st_shared_v4(sub_base(g) + row_off + ((1u ^ xr) << 4), 0u, 0u, 0u, 0u);
+                    // (compact map: 16-byte K chunk c of row r at c * 2 KB + r * 16, no swizzle)
+                    st_shared_v4(sub_base(g) + (kC ? (uint32_t)r * 16u : row_off + ((0u ^ xr) << 4)), pack_bf16(pnt[0], pnt[1]), pack_bf16(pnt[2], 1.0f),
+                                 pack_bf16(1.0f, vdir[0]), pack_bf16(vdir[1], vdir[2]));
+                    st_shared_v4(sub_base(g) + (kC ? 2048u + (uint32_t)r * 16u : row_off + ((1u ^ xr) << 4)), 0u, 0u, 0u, 0u);
                 }
                 arrive(g);
                 spill_sig(g);
@@ -306,7 +332,7 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                 spill_wait(g);
                 // kSave: bf16 h_d goes to K-block cq / 2 of the (now free) h region, chunks (cq & 1) * 4 ..; its cosine to the 4-word layout
                 siren_epi<3, kSave>(t_row(g) + (uint32_t)cq * 32u, tab + (uint32_t)(kSWR + cq * 32) * 4u,
-                                    sub_base(g) + kPeBytes + (uint32_t)(cq >> 1) * 16384u + row_off + (uint32_t)0, xoff_hd, sigma[g], rgb0[g], rgb1[g], rgb2[g],
+                                    sub_base(g) + kAux + (uint32_t)(cq >> 1) * 16384u + row_off + (uint32_t)0, xoff_hd, sigma[g], rgb0[g], rgb1[g], rgb2[g],
                                     kSave ? saved + siren_cos9_off(n_sub, (size_t)((2 * p + cx.rank) * 2 + g), cq, 0, r) : nullptr);
                 if (kSave) {
                     fence_proxy_async_smem();
@@ -315,17 +341,18 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                 }
             }
             tc_fence_before();
-            // head partials of the four column quarters -> the aux blocks' upper halves (free once the last MMA is done)
+            // head partials of the four column quarters (part_of)
+            if (kC) asm volatile("bar.sync 3, 512;" ::: "memory");      // the slots overlay h: every warp is past its last epilogue
 #pragma unroll
             for (int g = 0; g < 2; ++g)
-                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sub_base(g) + 8192u + (uint32_t)(r * 4 + cq) * 16u), "f"(rgb0[g]),
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(part_of(g) + (uint32_t)(r * 4 + cq) * 16u), "f"(rgb0[g]),
                              "f"(rgb1[g]), "f"(rgb2[g]), "f"(sigma[g]) : "memory");
             asm volatile("bar.sync 3, 512;" ::: "memory");
             if (cq < 2) {
                 const int g = cq;
                 const bool ok = cq == 0 ? valid[0] : valid[1];
                 const long long out_row = cq == 0 ? row[0] : row[1];
-                const uint32_t pa = sub_base(g) + 8192u + (uint32_t)(r * 4) * 16u;
+                const uint32_t pa = part_of(g) + (uint32_t)(r * 4) * 16u;
                 const float4 p0 = lds128(pa), p1 = lds128(pa + 16u), p2 = lds128(pa + 32u), p3 = lds128(pa + 48u);
                 if (ok) {
                     const float4 bh = lds128(tab + kSBH * 4u);          // (b_sigma, b_rgb[3])
@@ -360,9 +387,9 @@ int siren_fwd(const void* packed, const b2r_mlp_input* in, long long rows, float
     unsigned grid = 0;
     int rc = pair_grid(rows, &grid);
     if (rc) return rc;
-    rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes), "tc smem attribute");
+    rc = cuda_result(cudaFuncSetAttribute(siren_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MapC::kSmem), "tc smem attribute");
     if (rc) return rc;
-    siren_tc_kernel<false><<<grid, kThreads, kSmemBytes, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr, make_last_flag(last));
+    siren_tc_kernel<false><<<grid, kThreads, MapC::kSmem, st>>>((const uint8_t*)packed, make_row_source(in), rows, (float4*)raw_out, nullptr, make_last_flag(last));
     B2R_LAUNCH_CHECK("b2r_mlp_tc_fwd (SirenNeRF)");
     return 0;
 }

@@ -59,6 +59,42 @@ __host__ __device__ constexpr long long step_base(int s) {
     return off;
 }
 
+// ---- compact copy of every step's LAST h chunk + post chunk (sine models, inference kernels; MapC below) ----------------------
+// A post chunk carries 16 K columns of which a SWIZZLE_128B stage image (16 KB, one bulk copy, one ring-stage cycle) uses 32 bytes
+// per row.  The inference kernels of the sine models read, per step and N-half, ONE blob [h chunk 3 (SWIZZLE_128B image) | post chunk
+// in the NO-SWIZZLE core-matrix layout [16-byte K chunk (2)][weight row][16 B]] with one bulk copy: 4 copies per step and sub-tile
+// instead of 5.  The blobs live in an extra area behind the fp32 tables of the packed image (the training kernels keep reading the
+// chunk area, which is unchanged).
+template <class S>
+__host__ __device__ constexpr uint32_t post_bytes(int s) { return (uint32_t)(S::n(s) / 2) * 32u; }
+template <class S>
+__host__ __device__ constexpr long long extra_base(int s) {
+    long long off = 0;
+    for (int t = 0; t < s; ++t) off += 2LL * (half_bytes<S>(t) + post_bytes<S>(t));
+    return off;
+}
+// which (step, half, part) a 16-byte group of the extra area belongs to: c = 3 (h chunk 3: row, grp 0..7 as in `locate`) or
+// c = 4 (post chunk: grp = 16-byte K chunk 0 / 1); dst = byte offset inside the extra area
+template <class S>
+__device__ __forceinline__ void locate_extra(long long byte, int& s, int& c, int& hf, int& row, int& grp) {
+    s = 0;
+    while (s + 1 < S::kSteps && byte >= extra_base<S>(s + 1)) ++s;
+    const int in_step = (int)(byte - extra_base<S>(s));
+    const int hb = (int)half_bytes<S>(s), pb = (int)post_bytes<S>(s);
+    hf = in_step / (hb + pb);
+    const int rem = in_step % (hb + pb);
+    if (rem < hb) {                      // SWIZZLE_128B image: the thread's group is (row, grp) -> written at sw128_offset
+        c = 3; row = rem / 128; grp = (rem % 128) / 16;
+    } else {
+        c = 4; grp = (rem - hb) / (pb / 2); row = ((rem - hb) % (pb / 2)) / 16;
+    }
+}
+template <class S>
+__device__ __forceinline__ long long extra_dst(int s, int c, int hf, int row, int grp) {
+    const long long b = extra_base<S>(s) + (long long)hf * (half_bytes<S>(s) + post_bytes<S>(s));
+    return c == 3 ? b + sw128_offset((uint32_t)row, (uint32_t)grp) : b + half_bytes<S>(s) + (long long)grp * (post_bytes<S>(s) / 2) + row * 16;
+}
+
 constexpr long long kNerfChunkBytes = step_base<NerfSched>(NerfSched::kSteps);      // 1,196,032
 constexpr long long kFilmChunkBytes = step_base<FilmSched>(FilmSched::kSteps);      // 1,310,720
 static_assert(kNerfChunkBytes == 1196032 && kFilmChunkBytes == 8 * 5 * 32768, "packed chunk bytes");
@@ -68,7 +104,9 @@ constexpr long long kNerfPackedBytes = kNerfChunkBytes + kNerfTabFloats * 4;
 // FiLM fp32 tables (all staged in shared memory): w0[3][256] (input layer, column-major) | scale0[256] | shift0[256] |
 //                   w_sigma[256] | w_rgb[3][256] | b_sigma, b_rgb[3]
 constexpr int kFW0 = 0, kFS0 = 768, kFT0 = 1024, kFWS = 1280, kFWR = 1536, kFBH = 2304, kFilmTabFloats = 2308;
-constexpr long long kFilmPackedBytes = kFilmChunkBytes + kFilmTabFloats * 4;
+constexpr long long kFilmExtraOff = kFilmChunkBytes + kFilmTabFloats * 4;               // compact blobs (extra_base) behind the tables
+constexpr long long kFilmPackedBytes = kFilmExtraOff + extra_base<FilmSched>(FilmSched::kSteps);
+static_assert(kFilmExtraOff % 16 == 0 && kFilmPackedBytes % 16 == 0, "bulk copies need 16-byte alignment");
 
 // ---- packed weights: which (step, chunk, half, row, 16-byte group) a byte of the chunk area belongs to ----
 // one thread per 16-byte group: (step, chunk, half, row of the half, 8 consecutive k)
@@ -228,6 +266,40 @@ __device__ __forceinline__ Ctx make_ctx(uint8_t* raw) {
     return c;
 }
 
+// ---- compact shared-memory map of the sine models' INFERENCE kernels (film_tc_kernel<false>, siren_tc_kernel<false>) ----------
+// Their aux operand is ONE 16-K chunk, so it is kept in the no-swizzle core-matrix layout [16-byte K chunk (2)][row (128)][16 B]
+// (4 KB instead of a 16 KB SWIZZLE_128B block; chunk 1 is all zero), which frees 24 KB: the weight ring gets a FOURTH stage, and
+// stage 3 has room for the blob [h chunk 3 | post chunk] (post_bytes above).  Every step has exactly 4 copies per sub-tile, so chunk
+// c always lands in stage c.  Why it matters (profiles/r2_role_timers.txt): a stage cycle (wait for w_empty, bulk copy,
+// relay hop, MMAs, commit) is ~1,480 clk whatever the copy's size, three stages delivered one chunk per ~493 clk, and a sine-model
+// step asked for 5 chunks per 2,176 clk of MMA time (435 clk per chunk): the ring, not the tensor or MUFU pipe, set the pace.
+struct MapC {
+    static constexpr int kStagesC = 4;
+    static constexpr uint32_t kAux = 4096;
+    static constexpr uint32_t kSub = kAux + kHBytes;                              // 68 KB per sub-tile
+    static constexpr uint32_t kRing = 2 * kSub;
+    static constexpr uint32_t kRingBytes = kStagesC * kStageBytes + 4096;         // stage 3: + the largest post chunk
+    static constexpr uint32_t kTab = kRing + kRingBytes;                          // fp32 tables (region of kTabBytes + kPartBytes)
+    static constexpr uint32_t kBar = kTab + kTabBytes + kPartBytes;
+    static constexpr uint32_t kSmem = kBar + 256 + 1024;
+    static constexpr uint32_t kAuxLbo = 2048, kAuxSbo = 128;                      // K-direction / 8-row-group pitch (tools/native/umma_kmajor_noswizzle_probe.cu)
+};
+static_assert(MapC::kBar % 8 == 0 && MapC::kSmem <= 232448 && MapC::kSub % 1024 == 0 && MapC::kAux % 1024 == 0, "compact shared-memory map");
+
+__device__ __forceinline__ Ctx make_ctx_c(uint8_t* raw) {
+    Ctx c;
+    c.smem = (smem_u32(raw) + 1023u) & ~1023u;
+    c.w_full = c.smem + MapC::kBar;
+    c.w_empty = c.w_full + 8 * MapC::kStagesC;
+    c.act_ready = c.w_empty + 8 * MapC::kStagesC;
+    c.acc_full = c.act_ready + 16;
+    c.tmem_slot = c.acc_full + 16;
+    c.spill_ready = c.tmem_slot + 16;      // (unused: the compact kernels keep nothing for a reverse mode)
+    c.spill_done = c.spill_ready + 16;
+    c.rank = cluster_ctarank();
+    return c;
+}
+
 // ---- last-sample sign check (include/b2r.h: b2r_last_sample) -----------------------------------------------------------
 // The kernels list every ray whose LAST sample's pre-relu sigma lies inside the bf16 error band; the host re-evaluates those
 // rows in fp32 (b2r_mlp_f32_last_sigma).  count == nullptr: off.
@@ -383,11 +455,93 @@ __device__ __forceinline__ void mma_loop(const Ctx& cx, uint32_t tmem_base, cons
     }
 }
 
+// ---- the same three roles on the compact map (MapC): 4 stages, 4 copies per step and sub-tile, chunk c in stage c ---------------
+// extra_off: byte offset of the blob area inside a packed image (behind its fp32 tables)
+template <class S, class BaseFn>
+__device__ __forceinline__ void producer_loop_c(const Ctx& cx, BaseFn base_of, long long extra_off, const PairLoop& pl, int n_steps) {
+    uint32_t phase = 0;
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        const uint8_t* __restrict__ packed = base_of(p);
+        for (int s = 0; s < n_steps; ++s) {
+            const uint32_t hb = half_bytes<S>(s), pb = post_bytes<S>(s);
+            const uint8_t* src_w = packed + step_base<S>(s) + (size_t)cx.rank * hb;
+            const uint8_t* src_x = packed + extra_off + extra_base<S>(s) + (size_t)cx.rank * (hb + pb);
+            for (int g = 0; g < 2; ++g) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t bytes = c < 3 ? hb : hb + pb;
+                    mbar_wait_cluster(cx.w_empty + 8 * c, phase ^ 1u);
+                    mbar_arrive_expect_tx(cx.w_full + 8 * c, bytes);
+                    bulk_g2s(cx.smem + MapC::kRing + (uint32_t)c * kStageBytes, c < 3 ? src_w + (size_t)c * 2 * hb : src_x, bytes, cx.w_full + 8 * c);
+                }
+                phase ^= 1u;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void relay_loop_c(const Ctx& cx, const PairLoop& pl, int n_steps) {
+    uint32_t phase = 0;
+    const uint32_t remote0 = mapa(cx.w_full, 0);
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        for (int sg = 0; sg < 2 * n_steps; ++sg) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                mbar_wait_cluster(cx.w_full + 8 * c, phase);
+                mbar_arrive_cluster(remote0 + 8 * c);
+            }
+            phase ^= 1u;
+        }
+    }
+}
+
+template <class S>
+__device__ __forceinline__ void mma_loop_c(const Ctx& cx, uint32_t tmem_base, const PairLoop& pl, int n_steps) {
+    static_assert(S::kPostMmas == 1, "the compact post chunk is one K = 16 step");
+    uint32_t phase = 0, act_phase0 = 0, act_phase1 = 0;
+    const uint64_t d_hi = desc_sw128(0);                          // h blocks and h chunks: K-major SWIZZLE_128B
+    const uint64_t a_ns = make_desc(0, MapC::kAuxLbo, MapC::kAuxSbo, 0);      // aux operand: no swizzle, chunk pitch 2 KB
+    for (long long p = pl.first; p < pl.n_pairs; p += pl.stride) {
+        for (int s = 0; s < n_steps; ++s) {
+            const uint32_t idesc = make_idesc_bf16(256, (uint32_t)S::n(s));
+            const uint32_t hb = half_bytes<S>(s);
+            const uint64_t b_ns = make_desc(0, post_bytes<S>(s) / 2, 128, 0);  // post chunk: chunk pitch = weight rows x 16 B
+            for (int g = 0; g < 2; ++g) {
+                if (g == 0) { mbar_wait_cluster(cx.act_ready, act_phase0); act_phase0 ^= 1u; }
+                else { mbar_wait_cluster(cx.act_ready + 8, act_phase1); act_phase1 ^= 1u; }
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)g * 256u;
+                const uint32_t a_base = cx.smem + (uint32_t)g * MapC::kSub;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    mbar_wait_cluster(cx.w_full + 8 * c, phase);
+                    tc_fence_after();
+                    const uint32_t b_addr = cx.smem + MapC::kRing + (uint32_t)c * kStageBytes;
+                    const uint64_t ad = d_hi | (uint64_t)(((a_base + MapC::kAux + (uint32_t)c * 16384u) >> 4) & 0x3FFFu);
+                    const uint64_t bd = d_hi | (uint64_t)((b_addr >> 4) & 0x3FFFu);
+                    if (elect_one()) {
+                        mma_bf16_2cta(d_tmem, ad, bd, idesc, c == 0 ? 0u : 1u);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k) mma_bf16_2cta(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                        if (c == 3)
+                            mma_bf16_2cta(d_tmem, a_ns | (uint64_t)((a_base >> 4) & 0x3FFFu), b_ns | (uint64_t)(((b_addr + hb) >> 4) & 0x3FFFu), idesc, 1u);
+                        mma_commit_2cta(cx.w_empty + 8 * c, (uint16_t)3);
+                    }
+                    __syncwarp();
+                }
+                phase ^= 1u;
+                if (elect_one()) mma_commit_2cta(cx.acc_full + 8 * g, (uint16_t)3);
+                __syncwarp();
+            }
+        }
+    }
+}
+
 // common prologue: barriers, TMEM allocation (both CTAs), cluster rendezvous; returns the TMEM base address
 // act_count: arrivals per act_ready phase (epilogue warps per sub-tile x 2 CTAs)
-__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp, uint32_t act_count = 16, uint32_t spill_count = 8) {
+__device__ __forceinline__ uint32_t tc_prologue(const Ctx& cx, int warp, uint32_t act_count = 16, uint32_t spill_count = 8, int n_stages = kStages) {
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
+        for (int i = 0; i < n_stages; ++i) { mbar_init(cx.w_full + 8 * i, cx.rank == 0 ? 2 : 1); mbar_init(cx.w_empty + 8 * i, 1); }
         for (int g = 0; g < 2; ++g) {
             mbar_init(cx.act_ready + 8 * g, act_count); mbar_init(cx.acc_full + 8 * g, 1);
             mbar_init(cx.spill_ready + 8 * g, spill_count); mbar_init(cx.spill_done + 8 * g, 1);
