@@ -88,8 +88,9 @@ __device__ __forceinline__ void film_scale_shift(const float* __restrict__ param
 __device__ __forceinline__ float film_table_value(const float* __restrict__ params, const float* __restrict__ film, bool ud, int i) {
     float val;
     if (i < kFS0) {
+        // input_layer weights with the FiLM scale folded in: t_n = sum_k (30 gamma_n W_nk) p_k + shift_n (three fma per output)
         int k = (i - kFW0) / 256, n = (i - kFW0) % 256;
-        val = params[film_layer(0, ud).w_off + n * 3 + k];
+        val = (30.0f * film[n]) * params[film_layer(0, ud).w_off + n * 3 + k];
     } else if (i < kFT0) val = 30.0f * film[i - kFS0];
     else if (i < kFWS) { int n = i - kFT0; val = 30.0f * (film[n] * params[film_layer(0, ud).b_off + n] + film[256 + n]); }
     else if (i < kFWR) val = params[film_layer(8, ud).w_off + (i - kFWS)];
@@ -662,27 +663,35 @@ film_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
                 if (!first_tile) spill_wait(g);                      // previous tile's last copy
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 // ---- input_layer on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    uint32_t pk[16], ck[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
-                        const float4 wx = lds128(tab + kFW0 * 4u + n0), wy = lds128(tab + (kFW0 + 256) * 4u + n0), wz = lds128(tab + (kFW0 + 512) * 4u + n0);
-                        const float4 sc = lds128(tab + kFS0 * 4u + n0), sh = lds128(tab + kFT0 * 4u + n0);
-                        float a0 = fmaf(wz.x, pnt[2], fmaf(wy.x, pnt[1], wx.x * pnt[0]));
-                        float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
-                        float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
-                        float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
-                        const float t0 = fmaf(a0, sc.x, sh.x), t1 = fmaf(a1, sc.y, sh.y), t2 = fmaf(a2, sc.z, sh.z), t3 = fmaf(a3, sc.w, sh.w);
-                        pk[2 * q + 0] = pack_bf16(__sinf(t0), __sinf(t1));
-                        pk[2 * q + 1] = pack_bf16(__sinf(t2), __sinf(t3));
-                        if (kSave) ck[q] = cos_q4(t0, t1, t2, t3);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                        if (kSave && q < 2) stg128(saved + film_cos_off(n_sub, 0, T, cq, jj * 2 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
+if constexpr (kC) {
+                    // column-owned form (tc_core.cuh sine_input_layer): the table stays in registers, positions come by shuffle
+                    sine_input_layer(tab + kFW0 * 4u, tab + kFT0 * 4u, sub_base(g) + kAux + (uint32_t)cq * 16384u, cq, quad, lane, pnt);
+                } else {
+    #pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        uint32_t pk[16], ck[8];
+    #pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
+                            const float4 wx = lds128(tab + kFW0 * 4u + n0), wy = lds128(tab + (kFW0 + 256) * 4u + n0), wz = lds128(tab + (kFW0 + 512) * 4u + n0);
+                            const float4 sh = lds128(tab + kFT0 * 4u + n0);
+                            // scale folded into the table's weights: 3 packed fma per pair of outputs (the input stage is issue-bound)
+                            float t0, t1, t2, t3;
+                            ffma2(t0, t1, wx.x, wx.y, pnt[0], sh.x, sh.y);
+                            ffma2(t2, t3, wx.z, wx.w, pnt[0], sh.z, sh.w);
+                            ffma2(t0, t1, wy.x, wy.y, pnt[1], t0, t1);
+                            ffma2(t2, t3, wy.z, wy.w, pnt[1], t2, t3);
+                            ffma2(t0, t1, wz.x, wz.y, pnt[2], t0, t1);
+                            ffma2(t2, t3, wz.z, wz.w, pnt[2], t2, t3);
+                            pk[2 * q + 0] = pack_bf16(__sinf(t0), __sinf(t1));
+                            pk[2 * q + 1] = pack_bf16(__sinf(t2), __sinf(t3));
+                            if (kSave) ck[q] = cos_q4(t0, t1, t2, t3);
+                        }
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            if (kSave && q < 2) stg128(saved + film_cos_off(n_sub, 0, T, cq, jj * 2 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
+                        }
                     }
                 }
                 if (cq == 0) {

@@ -81,7 +81,7 @@ __global__ void siren_pack_kernel(const float* __restrict__ params, uint8_t* __r
         float val;
         if (i < kST0) {
             int k = (i - kSW0) / 256, n = (i - kSW0) % 256;
-            val = params[siren_layer(0).w_off + n * 3 + k];
+            val = 30.0f * params[siren_layer(0).w_off + n * 3 + k];       // t_n = sum_k (30 W_nk) p_k + 30 b_n
         } else if (i < kSWS) val = 30.0f * params[siren_layer(0).b_off + (i - kST0)];
         else if (i < kSWR) val = params[siren_layer(10).w_off + (i - kSWS)];
         else if (i < kSBH) val = params[siren_layer(11).w_off + (i - kSWR)];
@@ -260,27 +260,32 @@ siren_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long row
                 if (!first_tile) spill_wait(g);                      // previous tile's h_d copy
                 const size_t T = (size_t)((2 * p + cx.rank) * 2 + g);
                 // ---- layers_pos.0 on CUDA cores: this warp produces columns cq*64 .. +63 of h0 (K-block cq)
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    uint32_t pk[16], ck[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
-                        const float4 wx = lds128(tab + kSW0 * 4u + n0), wy = lds128(tab + (kSW0 + 256) * 4u + n0), wz = lds128(tab + (kSW0 + 512) * 4u + n0);
-                        const float4 sh = lds128(tab + kST0 * 4u + n0);
-                        float a0 = fmaf(wz.x, pnt[2], fmaf(wy.x, pnt[1], wx.x * pnt[0]));
-                        float a1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], wx.y * pnt[0]));
-                        float a2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], wx.z * pnt[0]));
-                        float a3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], wx.w * pnt[0]));
-                        const float t0 = fmaf(a0, 30.0f, sh.x), t1 = fmaf(a1, 30.0f, sh.y), t2 = fmaf(a2, 30.0f, sh.z), t3 = fmaf(a3, 30.0f, sh.w);
-                        pk[2 * q + 0] = pack_bf16(__sinf(t0), __sinf(t1));
-                        pk[2 * q + 1] = pack_bf16(__sinf(t2), __sinf(t3));
-                        if (kSave) ck[q] = cos_q4(t0, t1, t2, t3);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-                        if (kSave && q < 2) stg128(saved + siren_cos_off(n_sub, 0, T, cq, jj * 2 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
+if constexpr (kC) {
+                    // column-owned form (tc_core.cuh sine_input_layer): the table stays in registers, positions come by shuffle
+                    sine_input_layer(tab + kSW0 * 4u, tab + kST0 * 4u, sub_base(g) + kAux + (uint32_t)cq * 16384u, cq, quad, lane, pnt);
+                } else {
+    #pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        uint32_t pk[16], ck[8];
+    #pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t n0 = (uint32_t)(cq * 64 + jj * 32 + q * 4) * 4u;
+                            const float4 wx = lds128(tab + kSW0 * 4u + n0), wy = lds128(tab + (kSW0 + 256) * 4u + n0), wz = lds128(tab + (kSW0 + 512) * 4u + n0);
+                            const float4 sh = lds128(tab + kST0 * 4u + n0);
+                            // the factor 30 is folded into the table's weights: 3 fma per output (the packed fp32x2 form cost 132 B of spills here)
+                            const float t0 = fmaf(wz.x, pnt[2], fmaf(wy.x, pnt[1], fmaf(wx.x, pnt[0], sh.x)));
+                            const float t1 = fmaf(wz.y, pnt[2], fmaf(wy.y, pnt[1], fmaf(wx.y, pnt[0], sh.y)));
+                            const float t2 = fmaf(wz.z, pnt[2], fmaf(wy.z, pnt[1], fmaf(wx.z, pnt[0], sh.z)));
+                            const float t3 = fmaf(wz.w, pnt[2], fmaf(wy.w, pnt[1], fmaf(wx.w, pnt[0], sh.w)));
+                            pk[2 * q + 0] = pack_bf16(__sinf(t0), __sinf(t1));
+                            pk[2 * q + 1] = pack_bf16(__sinf(t2), __sinf(t3));
+                            if (kSave) ck[q] = cos_q4(t0, t1, t2, t3);
+                        }
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            st_shared_v4(h_blk(g) + xoff[jj * 4 + q], pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                            if (kSave && q < 2) stg128(saved + siren_cos_off(n_sub, 0, T, cq, jj * 2 + q, r), ck[4 * q], ck[4 * q + 1], ck[4 * q + 2], ck[4 * q + 3]);
+                        }
                     }
                 }
                 if (cq == 0) {

@@ -575,6 +575,43 @@ __device__ __forceinline__ void arrive_act(uint32_t act_bar_local, uint32_t act_
     }
 }
 
+// packed fp32x2 fma (FFMA2): {d0,d1} = {a0,a1} * {b,b} + {c0,c1}, each lane rounded like fmaf
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c0, float c1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %6};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
+}
+
+// Input layer (K = 3) of the sine models in the INFERENCE kernels: h0[row, n] = sin(w'[0][n] p_x + w'[1][n] p_y + w'[2][n] p_z + shift[n])
+// for the warp's 32 rows (quad) and 64 columns (K-block cq), written as bf16 into the SWIZZLE_128B K-block at `kblk`.
+// The epilogue's thread = row mapping would make every thread read the whole table (4 x 16 B per 4 outputs, the same address in all
+// lanes: a broadcast still returns 512 B per warp-load, and the stage was bound by the shared-memory return path: 160 LDS.128 per
+// thread and tile).  Here a lane OWNS 4 consecutive columns (its 16 table values stay in registers), the half-warps take
+// alternate rows and the row's position comes by shuffle: per 4 sines 3 SHFL + 6 FFMA2 + 1 STS.64 instead of 5 LDS.128 + 16 FFMA.
+// Same fma chain per element as the thread = row form (bit-identical).  tab_w / tab_sh: shared-memory addresses of w'[3][256], shift[256];
+// pnt: THIS lane's row's position (row quad * 32 + lane).
+__device__ __forceinline__ void sine_input_layer(uint32_t tab_w, uint32_t tab_sh, uint32_t kblk, int cq, int quad, int lane, const float (&pnt)[3]) {
+    const uint32_t half = (uint32_t)lane >> 4, j = (uint32_t)lane & 15u;
+    const uint32_t n0 = ((uint32_t)cq * 64u + 4u * j) * 4u;
+    const float4 wx = lds128(tab_w + n0), wy = lds128(tab_w + 1024u + n0), wz = lds128(tab_w + 2048u + n0), sh = lds128(tab_sh + n0);
+    const uint32_t base = kblk + (uint32_t)quad * 4096u + half * 128u + (j & 1u) * 8u;      // 32 rows = 4 groups of 8 rows (1,024 B)
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        const int src = 2 * it + (int)half;
+        const float px = __shfl_sync(0xffffffffu, pnt[0], src), py = __shfl_sync(0xffffffffu, pnt[1], src), pz = __shfl_sync(0xffffffffu, pnt[2], src);
+        float t0, t1, t2, t3;
+        ffma2(t0, t1, wx.x, wx.y, px, sh.x, sh.y);
+        ffma2(t2, t3, wx.z, wx.w, px, sh.z, sh.w);
+        ffma2(t0, t1, wy.x, wy.y, py, t0, t1);
+        ffma2(t2, t3, wy.z, wy.w, py, t2, t3);
+        ffma2(t0, t1, wz.x, wz.y, pz, t0, t1);
+        ffma2(t2, t3, wz.z, wz.w, pz, t2, t3);
+        const uint32_t r7 = (uint32_t)((2 * it) & 7) + half;                                  // row & 7 of row quad * 32 + 2 it + half
+        const uint32_t addr = base + (uint32_t)((2 * it) >> 3) * 1024u + (uint32_t)((2 * it) & 7) * 128u + (((j >> 1) ^ r7) << 4);
+        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(pack_bf16(__sinf(t0), __sinf(t1))), "r"(pack_bf16(__sinf(t2), __sinf(t3))) : "memory");
+    }
+}
+
 // packed fp32x2 add (FADD2): {a0,a1} += {b0,b1}
 __device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
     asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
