@@ -478,8 +478,7 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h
         tmem_ld_wait();
         if (u < 3) tmem_ld16(t_q + (uint32_t)(u + 1) * 16u, (u & 1) ? va : vb);
         float f[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) f[e] = __sinf(__uint_as_float(v[e]));
+        sin16(v, f);
         if (kSave) {
             uint32_t cw[4];
 #pragma unroll

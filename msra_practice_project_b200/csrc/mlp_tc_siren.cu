@@ -109,7 +109,8 @@ __device__ __forceinline__ void siren_epi(uint32_t t_q, uint32_t head, uint32_t 
         if (u < NU - 1) tmem_ld16(t_q + (uint32_t)(u + 1) * 16u, (u & 1) ? va : vb);
         float f[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) f[e] = MODE == 2 ? __uint_as_float(v[e]) : __sinf(__uint_as_float(v[e]));
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+        if (MODE != 2) sin16(v, f);
         if (kSave && MODE != 2) {
             uint32_t cw[4];
 #pragma unroll

@@ -582,6 +582,45 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
         : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c0), "f"(c1));
 }
 
+// sin of a PAIR of arguments on the FMA pipe (packed fp32x2: 9 instructions per pair, none on the MUFU / XU pipe):
+// u = x / 2 pi, r = u - round(u) in [-0.5, 0.5] (magic-number rounding), sin(2 pi r) = r P(r^2) with the degree-4 minimax P
+// (max error 6.2e-6 over the period, evaluated in fp32; the bf16 rounding of the result is 2e-3).  B2R_SIN_POLY_PAIRS of every 8 pairs
+// of a sine epilogue take this path instead of MUFU.SIN.  Measured three times (scalar form in round 1, packed form twice in round 2,
+// the last time after the weight ring and the input layer had stopped co-limiting the kernels: profiles/r2_sin_poly_ab.txt): 0 / 1 / 2 /
+// 3 pairs differ by 1-3 % on the 256^3 grid and by less than the box-to-box spread on the pi-GAN batch and the SirenNeRF frame -- the
+// kernels run under the board's power cap, where a sine moved to the FMA pipe is not free.  Default 0 (every sine on MUFU.SIN).
+#ifndef B2R_SIN_POLY_PAIRS
+#define B2R_SIN_POLY_PAIRS 0
+#endif
+constexpr int kSinPolyPairs = B2R_SIN_POLY_PAIRS;
+__device__ __forceinline__ void sin_poly2(float x0, float x1, float& o0, float& o1) {
+    asm("{\n\t.reg .b64 x, m, r, s, p, c;\n\t.reg .b32 i, g;\n\t"
+        "mov.b64 x, {%2, %3};\n\t"
+        "mov.b32 i, 0f3E22F983;\n\tmov.b64 c, {i, i};\n\t"                    // 1 / 2 pi
+        "mov.b32 g, 0f4B400000;\n\tmov.b64 m, {g, g};\n\t"                    // 1.5 * 2^23
+        "fma.rn.f32x2 r, x, c, m;\n\t"                                         // u + magic: u rounded to an integer k
+        "mov.b32 i, 0fBF800000;\n\tmov.b64 s, {i, i};\n\t"
+        "fma.rn.f32x2 r, r, s, m;\n\t"                                         // magic - (k + magic) = -k
+        "fma.rn.f32x2 r, x, c, r;\n\t"                                         // r = u - k
+        "mul.rn.f32x2 s, r, r;\n\t"
+        "mov.b32 i, 0f4203202E;\n\tmov.b64 p, {i, i};\n\t"                    // 32.78142547607422
+        "mov.b32 i, 0fC294F4BF;\n\tmov.b64 c, {i, i};\n\tfma.rn.f32x2 p, p, s, c;\n\t"     // -74.47801971435547
+        "mov.b32 i, 0f42A2BBD0;\n\tmov.b64 c, {i, i};\n\tfma.rn.f32x2 p, p, s, c;\n\t"     // 81.3668212890625
+        "mov.b32 i, 0fC225532A;\n\tmov.b64 c, {i, i};\n\tfma.rn.f32x2 p, p, s, c;\n\t"     // -41.331214904785156
+        "mov.b32 i, 0f40C90ECB;\n\tmov.b64 c, {i, i};\n\tfma.rn.f32x2 p, p, s, c;\n\t"     // 6.283055782318115
+        "mul.rn.f32x2 p, p, r;\n\t"
+        "mov.b64 {%0, %1}, p;\n\t}"
+        : "=f"(o0), "=f"(o1) : "f"(x0), "f"(x1));
+}
+// 16 sines of one accumulator unit: the last kSinPolyPairs pairs on the FMA pipe, the others MUFU.SIN
+__device__ __forceinline__ void sin16(const uint32_t (&v)[16], float (&f)[16]) {
+#pragma unroll
+    for (int pr = 0; pr < 8; ++pr) {
+        if (pr >= 8 - kSinPolyPairs) sin_poly2(__uint_as_float(v[2 * pr]), __uint_as_float(v[2 * pr + 1]), f[2 * pr], f[2 * pr + 1]);
+        else { f[2 * pr] = __sinf(__uint_as_float(v[2 * pr])); f[2 * pr + 1] = __sinf(__uint_as_float(v[2 * pr + 1])); }
+    }
+}
+
 // Input layer (K = 3) of the sine models in the INFERENCE kernels: h0[row, n] = sin(w'[0][n] p_x + w'[1][n] p_y + w'[2][n] p_z + shift[n])
 // for the warp's 32 rows (quad) and 64 columns (K-block cq), written as bf16 into the SWIZZLE_128B K-block at `kblk`.
 // The epilogue's thread = row mapping would make every thread read the whole table (4 x 16 B per 4 outputs, the same address in all
