@@ -282,7 +282,7 @@ struct MapC {
     static constexpr uint32_t kTab = kRing + kRingBytes;                          // fp32 tables (region of kTabBytes + kPartBytes)
     static constexpr uint32_t kBar = kTab + kTabBytes + kPartBytes;
     static constexpr uint32_t kSmem = kBar + 256 + 1024;
-    static constexpr uint32_t kAuxLbo = 2048, kAuxSbo = 128;                      // K-direction / 8-row-group pitch (tools/native/umma_kmajor_noswizzle_probe.cu)
+    static constexpr uint32_t kAuxLbo = 2048, kAuxSbo = 128;                      // K-direction / 8-row-group pitch (tests/native/umma_kmajor_noswizzle_probe.cu)
 };
 static_assert(MapC::kBar % 8 == 0 && MapC::kSmem <= 232448 && MapC::kSub % 1024 == 0 && MapC::kAux % 1024 == 0, "compact shared-memory map");
 

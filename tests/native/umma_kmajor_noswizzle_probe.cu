@@ -3,7 +3,7 @@
 // at c * rows * 16 + r * 16, i.e. core matrices of 8 rows x 16 B are 128 B apart along M / N and rows * 16 B apart along K), and the
 // mix "A = SWIZZLE_128B block, B = no-swizzle" the training forward would use.  D[128, 128] = A[128, 16] B[128, 16]^T, exact integers.
 // The probe tries both LBO / SBO assignments and reports which one the hardware implements.
-// nvcc -O2 -std=c++17 -gencode arch=compute_100a,code=sm_100a umma_kmajor_noswizzle_probe.cu -o umma_kmajor_noswizzle_probe
+// Built by __graft_entry__.build(), run by tests/test_gpu_parity.py::test_umma_kmajor_noswizzle_probe.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

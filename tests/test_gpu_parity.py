@@ -58,6 +58,19 @@ def test_umma_probe():
     assert "mismatches 0 " in lines[0] and "mismatches 0 " in lines[1], out.stdout
 
 
+def test_umma_kmajor_noswizzle_probe():
+    """The no-swizzle K-major operand layout of the sine models' compact aux / post chunks (tc_core.cuh MapC): LBO = pitch of the two
+    16-byte K chunks, SBO = pitch of the 8-row groups, and the mix with a SWIZZLE_128B A operand."""
+    exe = os.path.join(ROOT, "tests", "native", "umma_kmajor_noswizzle_probe")
+    if not os.path.exists(exe):
+        pytest.skip("probe binary not built")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    print(out.stdout)
+    assert "PROBE OK" in out.stdout, out.stdout + out.stderr
+    ok = [l for l in out.stdout.splitlines() if "<-- OK" in l]
+    assert len(ok) == 2 and all("LBO=2048 SBO=128" in l for l in ok), out.stdout        # the assignment the kernels use
+
+
 # ---- K1 / K2 -------------------------------------------------------------------------------------------
 def test_raygen(golden):
     k = golden.kernels
