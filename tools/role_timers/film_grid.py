@@ -26,4 +26,4 @@ lead = a[0::2]
 tot = lead[:, 4].mean()
 print("FiLM grid: mma loop cycles %.0f  wait_wfull %.1f%%  wait_act %.1f%%" % (tot, 100 * lead[:, 2].mean() / tot, 100 * lead[:, 3].mean() / tot))
 print("producer wait_empty %.1f%% of %.0f" % (100 * a[:, 0].mean() / a[:, 1].mean(), a[:, 1].mean()))
-print("epilogue warp 0 wait_acc %.1f%% of %.0f" % (100 * a[:, 11].mean() / a[:, 13].mean(), a[:, 13].mean()))
+print("epilogue warp 0: wait_acc %.1f%%, input stages %.1f%% of %.0f" % (100 * a[:, 11].mean() / a[:, 13].mean(), 100 * a[:, 12].mean() / a[:, 13].mean(), a[:, 13].mean()))
