@@ -189,7 +189,9 @@ int b2r_mlp_f32_bwd(int model_kind, const float* params, const float* film, int 
 
 /* bf16 tensor-core path (tcgen05 / TMEM, weights streamed by the TMA bulk-copy engine).
  * packed: b2r_mlp_tc_packed_bytes(kind) bytes produced by b2r_mlp_tc_pack from the flat fp32
- * parameters (+ film for the FiLM model: gamma/beta/bias are folded into per-column scale/shift). */
+ * parameters (+ film for the FiLM model: gamma/beta/bias are folded into per-column scale/shift).  The image is opaque to the
+ * caller: bf16 weight chunks in the kernels' shared-memory layouts, fp32 tables and, for the sine models, a second copy of every
+ * step's last chunks in the layout of the inference kernels' 4-stage ring (csrc/tc_core.cuh). */
 size_t b2r_mlp_tc_packed_bytes(int model_kind);
 int b2r_mlp_tc_pack(int model_kind, const float* params, const float* film, int use_dir,
                     void* packed_out, void* stream);

@@ -63,8 +63,9 @@ def test_training_and_batched_entry_points_sizes_and_argument_checks():
     assert lib.b2r_mlp_tc_train_saved_bytes(1, 1000) == 8 * (37 * 16384 + 9 * 32768)
     assert lib.b2r_mlp_tc_train_scratch_bytes(1, 1000) == 8 * (36 * 16384 + 128 * 16)
     assert lib.b2r_mlp_tc_bwd_packed_bytes(1) == 32 * 32768 + 1024 * 4
-    assert lib.b2r_mlp_tc_packed_bytes(1) == 8 * 5 * 32768 + 2308 * 4                                     # FiLM-SIREN
-    assert lib.b2r_mlp_tc_packed_bytes(2) == 8 * 5 * 32768 + 5 * 16384 + 1668 * 4      # SirenNeRF
+    # chunk area + fp32 tables + the inference kernels' blobs [h chunk 3 | compact post chunk] per step and N-half (tc_core.cuh extra_base)
+    assert lib.b2r_mlp_tc_packed_bytes(1) == 8 * 5 * 32768 + 2308 * 4 + 8 * 2 * (16384 + 4096)            # FiLM-SIREN
+    assert lib.b2r_mlp_tc_packed_bytes(2) == 8 * 5 * 32768 + 5 * 16384 + 1668 * 4 + 8 * 2 * (16384 + 4096) + 2 * (8192 + 2048)      # SirenNeRF
     assert lib.b2r_mlp_f32_workspace_bytes(2, 10, 1) == 10 * 4620 * 4
     inp = _lib.MlpInput()
     inp.x, inp.n_rays, inp.n_samples = 256, 512, 1

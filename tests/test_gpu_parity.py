@@ -311,6 +311,51 @@ def test_mlp_tc_ragged_rows_vs_fp32(rows):
     assert bool(torch.all(err[:, 3] < 4e-2 * torch.clamp(b[:, 3], min=1.0)))
 
 
+def test_packed_blob_area_matches_chunk_area():
+    """The sine models' packed images carry every step's LAST h chunk and post chunk twice: in the chunk area (SWIZZLE_128B images, read by
+    the training kernels) and as one blob per step and N-half behind the fp32 tables ([h chunk 3 | post chunk in the no-swizzle layout
+    [16-byte K chunk][weight row][16 B]], read by the inference kernels with one bulk copy: tc_core.cuh extra_base / MapC).  Both must hold
+    the same bf16 values."""
+    import numpy as np
+    torch.manual_seed(3)
+    film_net = models.FilmSirenNeRF().cuda()
+    g = torch.Generator().manual_seed(1)
+    film_net.set_film_params(torch.cat([1.0 + 0.2 * torch.randn(9, 256, generator=g), 0.1 * torch.randn(9, 256, generator=g)], -1).cuda())
+    siren_net = models.SirenNeRF().cuda()
+    cases = [(models.KIND_FILM, film_net, models.film_tensor(film_net).contiguous(), [256] * 8, 2308),
+             (models.KIND_SIREN, siren_net, None, [256] * 8 + [128], 1668)]
+
+    def sw128(row, chunk16):
+        return (row >> 3) * 1024 + (row & 7) * 128 + ((chunk16 ^ (row & 7)) << 4)
+
+    for kind, net, film, n_of, tab_floats in cases:
+        packed = ops.pack_tc(models.flat_params(net, kind), kind, film=film).cpu().numpy()
+        hb = [n // 2 * 128 for n in n_of]                          # half-chunk image: n/2 weight rows x 64 K bf16
+        pb = [n // 2 * 32 for n in n_of]                           # compact post chunk: n/2 rows x 16 K bf16
+        step_base = np.concatenate([[0], np.cumsum([2 * 5 * h for h in hb])])
+        extra_off = int(step_base[-1]) + tab_floats * 4
+        extra_base = np.concatenate([[0], np.cumsum([2 * (h + q) for h, q in zip(hb, pb)])])
+        assert packed.size == extra_off + int(extra_base[-1])
+        for s in range(len(n_of)):
+            rows = n_of[s] // 2
+            for hf in range(2):
+                blob = packed[extra_off + int(extra_base[s]) + hf * (hb[s] + pb[s]):][:hb[s] + pb[s]]
+                chunk3 = packed[int(step_base[s]) + (3 * 2 + hf) * hb[s]:][:hb[s]]
+                post = packed[int(step_base[s]) + (4 * 2 + hf) * hb[s]:][:hb[s]]
+                assert np.array_equal(blob[:hb[s]], chunk3), (kind, s, hf)
+                for c2 in range(2):
+                    for row in range(rows):
+                        a = blob[hb[s] + c2 * (pb[s] // 2) + row * 16:][:16]
+                        b = post[sw128(row, c2):][:16]
+                        assert np.array_equal(a, b), (kind, s, hf, c2, row)
+                # the post chunk uses only its first 16 K columns: the rest of the SWIZZLE_128B image is zero
+                used = np.zeros(hb[s], dtype=bool)
+                for row in range(rows):
+                    for c2 in range(2):
+                        used[sw128(row, c2):sw128(row, c2) + 16] = True
+                assert not post[~used].any(), (kind, s, hf)
+
+
 def test_mlp_tc_film_vs_reference(golden):
     """FiLM-SIREN on the tensor-core path: points mode, sigma-only grid mode, use_dir=False, film update."""
     k, p = golden.kernels, golden.pigan
