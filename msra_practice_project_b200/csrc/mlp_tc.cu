@@ -468,7 +468,7 @@ nerf_tc_kernel(const uint8_t* __restrict__ packed, RowSource src, long long rows
 // cosp + u * 2048 (tc_core.cuh: cos_q4, film_cos_off), and MODE 2 also writes its bf16 output into shared memory (h_blk) for the spill.
 template <int MODE, bool kSave>
 __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h_blk, const uint32_t (&xoff)[8], float& sigma, float& rgb0,
-                                         float& rgb1, float& rgb2, uint8_t* __restrict__ cosp) {
+                                         float& rgb1, float& rgb2, uint8_t* __restrict__ cosp, bool write_h = true) {
     // 4 units of 16 columns, the TMEM load of unit u+1 in flight while unit u is evaluated
     uint32_t va[16], vb[16];
     tmem_ld16(t_q, va);
@@ -503,7 +503,7 @@ __device__ __forceinline__ void film_epi(uint32_t t_q, uint32_t head, uint32_t h
                 rgb2 = fmaf(f[4 * q + 0], w2.x, fmaf(f[4 * q + 1], w2.y, fmaf(f[4 * q + 2], w2.z, fmaf(f[4 * q + 3], w2.w, rgb2))));
             }
         }
-        if (MODE != 2 || kSave) {
+        if ((MODE != 2 || kSave) && write_h) {               // (write_h = false: sigma_only's last step, nobody reads its h)
 #pragma unroll
             for (int q = 0; q < 2; ++q)
                 st_shared_v4(h_blk + xoff[u * 2 + q], pack_bf16(f[8 * q + 0], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
@@ -725,7 +725,8 @@ if constexpr (kC) {
             for (int g = 0; g < 2; ++g) {                               // hidden_layers.6 (+ sigma head)
                 wait_acc(g);
                 spill_wait(g);
-                film_epi<1, kSave>(t_q(g), tab + (uint32_t)(kFWS + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g], cosp(7, g));
+                film_epi<1, kSave>(t_q(g), tab + (uint32_t)(kFWS + cq * 64) * 4u, h_blk(g), xoff, sigma[g], rgb0[g], rgb1[g], rgb2[g], cosp(7, g),
+                                   kSave || !sigma_only);
                 if (!sigma_only) { arrive(g); spill_sig(g); }
             }
             if (!sigma_only) {
