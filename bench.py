@@ -834,6 +834,21 @@ def run_secondary(args, config=None, embedded=False):
                     ms_per_step=ms, dtype="bf16" if args.precision == "bf16" else "f32", scaling="strong",
                     config=dict(workload="256^3 lattice in [-0.1,0.1]^3, coordinates generated on the device, sigma-only FiLM-SIREN kernel"),
                     tflops=n3 * 919552 / (ms * 1e-3) / 1e12)
+    # sine models: the fused kernel has TWO rooflines, the tensor pipe and the MUFU unit (one MUFU.SIN per hidden activation, 16 results
+    # per clock and SM); both fractions are reported, the MUFU one at the 1,965 MHz the part can reach without the power cap
+    sines = {"pigan": 72 * 2304, "grid": 2048, "siren": 256 * 2176 / 1.0}.get(config)
+    if sines is not None and world == 1 and args.precision == "bf16":
+        pk = peaks()
+        units = {"pigan": rays if config == "pigan" else 0, "grid": n3 if config == "grid" else 0, "siren": n if config == "siren" else 0}[config]
+        mufu_peak = 16 * 148 * 1.965e9
+        line["roofline"] = dict(bound="tensor", kernel="film_tc_kernel<false>" if config != "siren" else "siren_tc_kernel<false>",
+                                achieved=line["tflops"], peak=pk["bf16"], unit="TFLOP/s", frac=line["tflops"] / pk["bf16"],
+                                frac_of_sustained=(line["tflops"] / pk["bf16_sustained"]) if pk.get("bf16_sustained") else None, peak_source=pk["src"],
+                                traffic=None,
+                                mufu=dict(sines_per_unit=sines, achieved_gsin_s=units * sines / (ms * 1e-3) / 1e9, peak_gsin_s=mufu_peak / 1e9,
+                                          frac=units * sines / (ms * 1e-3) / mufu_peak),
+                                note="whole-pass time (the fused MLP kernel is 95 % of it: profiles/r2_film_grid_ncu.txt, r2_film_role_timers.txt); "
+                                     "the kernel is MUFU-bound (XU pipe 71 % busy under the power cap, 78 % of the epilogue warps' samples on MUFU.SIN)")
     line.update(n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), higher_is_better=True, vs_baseline=None, data="synthetic")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
